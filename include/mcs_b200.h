@@ -1,0 +1,256 @@
+/*
+ * mcs_b200.h -- C ABI of the B200-native MultiCol-SLAM feature hot path.
+ *
+ * One shared library (libmcs_b200.so) replaces the arithmetic behind
+ *   mdBRIEFextractorOct::operator()            (ref include/mdBRIEFextractorOct.h:355-361,
+ *                                               src/mdBRIEFextractorOct.cpp:1244-1337)
+ *   cORBmatcher::SearchByProjection(F, MPs)    (ref src/cORBmatcher.cpp:67-166)
+ *   cORBmatcher::SearchForInitialization       (ref src/cORBmatcher.cpp:579-726)
+ *   cORBmatcher::SearchByBoW(KF, KF)           (ref src/cORBmatcher.cpp:885-966, all-pairs)
+ *   DescriptorDistance64[Masked]               (ref src/cORBmatcher.cpp:2438-2474)
+ *   cCamModelGeneral_::WorldToImg / ImgToWorld (ref src/cam_model_omni.cpp:49-67,146-161)
+ *   CreateMirrorMask level 0                   (ref src/cam_model_omni.cpp:181-220)
+ *
+ * Plain pointers and sizes only; no C++/torch/OpenCV types cross this boundary.
+ * Every function returns an int status (MCS_OK == 0) and never throws.
+ * The C++ classes in include/mcs_shim.hpp adapt these entry points to the
+ * reference's own class signatures.
+ *
+ * Pointers named *_dev are CUDA device pointers on the extractor's device;
+ * everything else is host memory owned by the caller.
+ */
+#ifndef MCS_B200_H
+#define MCS_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCS_OK                0
+#define MCS_ERR_INVALID      -1   /* bad argument (null pointer, size, ...)            */
+#define MCS_ERR_UNSUPPORTED  -2   /* option of the reference that is not built (AGAST) */
+#define MCS_ERR_CUDA         -3   /* CUDA runtime error; see mcs_last_error()          */
+#define MCS_ERR_CAPACITY     -4   /* caller buffer too small                           */
+#define MCS_ERR_NO_DEVICE    -5   /* no usable sm_100 device: there is NO CPU fallback */
+
+#define MCS_MAX_LEVELS       16
+#define MCS_FRAME_GRID_COLS  64   /* ref include/cMultiFrame.h:48 */
+#define MCS_FRAME_GRID_ROWS  48   /* ref include/cMultiFrame.h:47 */
+
+/* Scaramuzza/OCam interior orientation, the 17 doubles of cCamModelGeneral_
+ * (ref include/cam_model_omni.h:47-110; YAML keys Camera.{c,d,e,u0,v0,a0..a4,pol0..pol11,Iw,Ih},
+ * loaded zero-padded to 5 / 12 coefficients by src/cSystem.cpp:144-156). */
+typedef struct mcs_ocam {
+    double c, d, e, u0, v0;
+    double pol[5];        /* forward polynomial  f(rho),   p_deg    == 5  */
+    double inv_pol[12];   /* backward polynomial rho(theta), invP_deg == 12 */
+    int32_t width, height;
+    int32_t mirror_mask;  /* Camera.mirrorMask: 1 -> disc mask, 0 -> all ones */
+    int32_t _pad;
+} mcs_ocam;
+
+/* Constructor arguments of mdBRIEFextractorOct, same order and defaults
+ * (ref include/mdBRIEFextractorOct.h:340-352). */
+typedef struct mcs_extractor_params {
+    int32_t nfeatures;        /* 1000 */
+    float   scale_factor;     /* 1.2f (kept as float: the reference widens the float) */
+    int32_t nlevels;          /* 8 */
+    int32_t edge_threshold;   /* 25 (the reference hard-codes EDGE_THRESHOLD = 25) */
+    int32_t first_level;      /* 0, unused by the reference */
+    int32_t score_type;       /* parsed, ignored by the reference (FAST score always) */
+    int32_t patch_size;       /* 32, unused (PATCH_SIZE constant) */
+    int32_t fast_threshold;   /* 20 */
+    int32_t use_agast;        /* 0; 1 -> MCS_ERR_UNSUPPORTED */
+    int32_t fast_agast_type;  /* 2 == FastFeatureDetector::TYPE_9_16 (only type built) */
+    int32_t do_dbrief;        /* 0: ORB, 1: distorted BRIEF */
+    int32_t learn_masks;      /* 1: mdBRIEF (descriptor + stability mask) */
+    int32_t desc_size;        /* bytes: 16 / 32 / 64 */
+} mcs_extractor_params;
+
+/* Binary-compatible with cv::KeyPoint (28 bytes). */
+typedef struct mcs_keypoint {
+    float   x, y;
+    float   size;
+    float   angle;
+    float   response;
+    int32_t octave;
+    int32_t class_id;
+} mcs_keypoint;
+
+typedef struct mcs_extractor_info {
+    int32_t nlevels;
+    int32_t capacity;                       /* nfeatures + 2*nlevels: max keypoints per image */
+    int32_t desc_size;
+    int32_t features_per_level[MCS_MAX_LEVELS];
+    double  scale_factor[MCS_MAX_LEVELS];
+    double  inv_scale_factor[MCS_MAX_LEVELS];
+} mcs_extractor_info;
+
+typedef struct mcs_extractor mcs_extractor;   /* opaque; one per (camera, thread), not re-entrant */
+
+const char* mcs_last_error(void);             /* thread-local message of the last failure */
+int  mcs_device_count(void);                  /* number of visible sm_100 devices (0 -> none) */
+void mcs_params_default(mcs_extractor_params* p);
+
+/* ---- camera model (C1) ------------------------------------------------------------------- */
+/* Host-side scalar helpers with the reference's exact double arithmetic; callers (cMultiFrame
+ * bearing rays, projection front-ends) use them per point.  The device copies live inside the
+ * descriptor kernel. */
+void mcs_cam_world_to_img(const mcs_ocam* cam, double x, double y, double z, double* u, double* v);
+void mcs_cam_img_to_world(const mcs_ocam* cam, double u, double v, double* x, double* y, double* z);
+/* level-0 mirror mask, h*w bytes, 255 inside the disc / 0 outside (or all 1 when mirror_mask==0) */
+int  mcs_cam_mirror_mask(const mcs_ocam* cam, uint8_t* mask_out);
+
+/* ---- extractor (E0..E9) ------------------------------------------------------------------ */
+int  mcs_extractor_create(const mcs_extractor_params* p, mcs_extractor** out);
+void mcs_extractor_destroy(mcs_extractor* ex);
+int  mcs_extractor_get_info(const mcs_extractor* ex, mcs_extractor_info* info);
+
+/* operator() for one image.  Host buffers, synchronous.
+ *   mask: h x w bytes, mandatory (the reference throws on an empty mask);
+ *   kps_out[capacity], desc_out[capacity*desc_size], dmask_out[capacity*desc_size] (may be NULL
+ *   only when learn_masks==0; when given and learn_masks==0 it is zero-filled like the reference);
+ *   *n_out = number of keypoints.  capacity must be >= info.capacity. */
+int  mcs_extract(mcs_extractor* ex,
+                 const uint8_t* image, int32_t width, int32_t height, int32_t stride,
+                 const uint8_t* mask, int32_t mask_stride,
+                 const mcs_ocam* cam,
+                 mcs_keypoint* kps_out, uint8_t* desc_out, uint8_t* dmask_out,
+                 int32_t capacity, int32_t* n_out);
+
+/* Batched form: n_images images of identical size, image i seen by camera cam_of_image[i]
+ * (index into cams[]/masks[]).  images: n_images*height*stride bytes; masks: n_cams*height*width.
+ * Outputs are fixed-size slots of `capacity` entries per image.  Host buffers (pinned memory
+ * recommended), H2D + kernels + D2H inside the call. */
+int  mcs_extract_batch(mcs_extractor* ex, int32_t n_images,
+                       const uint8_t* images, int32_t width, int32_t height, int32_t stride,
+                       const uint8_t* masks, const mcs_ocam* cams, int32_t n_cams,
+                       const int32_t* cam_of_image,
+                       mcs_keypoint* kps_out, uint8_t* desc_out, uint8_t* dmask_out,
+                       int32_t* counts_out, int32_t capacity);
+
+/* Same, all image/output buffers resident in device memory; asynchronous on `stream`
+ * (a cudaStream_t passed as void*; NULL = the extractor's own stream, then the call
+ * synchronises before returning).  masks/cams/cam_of_image stay host pointers (tiny, cached
+ * on the device by the extractor). */
+int  mcs_extract_batch_device(mcs_extractor* ex, int32_t n_images,
+                              const uint8_t* images_dev, int32_t width, int32_t height, int32_t stride,
+                              const uint8_t* masks, const mcs_ocam* cams, int32_t n_cams,
+                              const int32_t* cam_of_image,
+                              mcs_keypoint* kps_dev, uint8_t* desc_dev, uint8_t* dmask_dev,
+                              int32_t* counts_dev, int32_t capacity, void* stream);
+
+/* Introspection for the parity tests: copy intermediate device buffers of the LAST extract call
+ * (image 0 of the batch unless image_index is given) back to the host.
+ *   what: 0 = unblurred level (w*h bytes), 1 = blurred level, 2 = mask level,
+ *         3 = raw corners of the level as int32 triples (x, y, score) in reference order.
+ *   *w_out,*h_out = level size (for what==3: *w_out = number of corners, *h_out = 3). */
+int  mcs_extractor_debug_read(mcs_extractor* ex, int32_t image_index, int32_t level, int32_t what,
+                              void* out, size_t out_bytes, int32_t* w_out, int32_t* h_out);
+
+/* ---- Hamming distance (M0) --------------------------------------------------------------- */
+int  mcs_descriptor_distance64(const uint64_t* a, const uint64_t* b, int32_t dim);
+int  mcs_descriptor_distance64_masked(const uint64_t* a, const uint64_t* b,
+                                      const uint64_t* mask_a, const uint64_t* mask_b, int32_t dim);
+
+/* ---- brute force (M2 kernel) ------------------------------------------------------------- */
+/* For every query q: the K smallest (distance, index) pairs over the nd database descriptors that
+ * are not flagged in db_skip (nd bytes, may be NULL), ordered by (distance, index) ascending.
+ * Distances are the reference's bit-level popcounts (masked form when qmask/dmask != NULL).
+ * Output: topk_idx[nq*K] (-1 = none), topk_dist[nq*K].  Host buffers. */
+int  mcs_hamming_topk(const uint8_t* q, const uint8_t* qmask, int32_t nq,
+                      const uint8_t* d, const uint8_t* dmask, int32_t nd,
+                      const uint8_t* db_skip, int32_t dim, int32_t K,
+                      int32_t* topk_idx, int32_t* topk_dist);
+int  mcs_hamming_topk_device(const uint8_t* q_dev, const uint8_t* qmask_dev, int32_t nq,
+                             const uint8_t* d_dev, const uint8_t* dmask_dev, int32_t nd,
+                             const uint8_t* db_skip_dev, int32_t dim, int32_t K,
+                             int32_t* topk_idx_dev, int32_t* topk_dist_dev, void* stream);
+
+/* cORBmatcher::SearchByBoW(KF1, KF2, matches12) semantics (ref :885-966): all-pairs scan,
+ * best/second best, `best < th_low`, `best < nnratio*second`, every KF2 entry used at most once,
+ * queries visited in index order.  valid1/valid2: 1 where the keypoint carries a good map point
+ * (NULL = all valid).  matches12[nq] = matched database index or -1.  Returns via *nmatches. */
+int  mcs_match_bruteforce(const uint8_t* q, const uint8_t* qmask, const uint8_t* valid1, int32_t nq,
+                          const uint8_t* d, const uint8_t* dmask, const uint8_t* valid2, int32_t nd,
+                          int32_t dim, int32_t th_low, double nnratio,
+                          int32_t* matches12, int32_t* nmatches);
+
+/* ---- multi-camera frame view + grid window search (G1, M1, M3) ---------------------------- */
+/* Flat view of the fields of cMultiFrame the matchers read (ref include/cMultiFrame.h:90-175).
+ * Keypoints are in the contiguous (camera-major) order of src/cMultiFrame.cpp:168-184. */
+typedef struct mcs_frame_view {
+    int32_t n_cams;
+    int32_t n_keys;                 /* totalN */
+    const mcs_keypoint* keys;       /* [n_keys] contiguous index order (mvKeys) */
+    const int32_t* key_cam;         /* [n_keys] keypoint_to_cam */
+    const uint8_t* desc;            /* [n_keys*dim] descriptor rows in contiguous index order */
+    const uint8_t* dmask;           /* [n_keys*dim] or NULL */
+    const int32_t* cam_width;       /* [n_cams] mnMaxX - mnMinX */
+    const int32_t* cam_height;      /* [n_cams] */
+    int32_t dim;                    /* descriptor bytes */
+    int32_t n_levels;
+    const double* scale_factors;    /* [n_levels] mvScaleFactors */
+} mcs_frame_view;
+
+/* One window query: GetFeaturesInArea(cam, x, y, r, min_level, max_level)
+ * (ref src/cMultiFrame.cpp:272-340) followed by Hamming distance to every candidate. */
+typedef struct mcs_window_query {
+    int32_t cam;
+    int32_t min_level, max_level;   /* -1,-1 = no level filter */
+    int32_t desc_index;             /* row of the query descriptor in the query descriptor array */
+    double  x, y, r;
+} mcs_window_query;
+
+/* Candidate lists in the reference's visiting order (cell-x outer, cell-y inner, insertion
+ * order inside a cell).  cand_idx/cand_dist: [nq*max_cand]; cand_count[nq] holds the TRUE number
+ * of candidates (may exceed max_cand: then only the first max_cand are stored and the call
+ * returns MCS_ERR_CAPACITY so the caller can retry with a larger max_cand). */
+int  mcs_window_search(const mcs_frame_view* frame,
+                       const mcs_window_query* queries, int32_t nq,
+                       const uint8_t* qdesc, const uint8_t* qmask,
+                       int32_t max_cand,
+                       int32_t* cand_idx, int32_t* cand_dist, int32_t* cand_count);
+
+/* cORBmatcher::SearchByProjection(F, vpMapPoints, th) (ref :67-166).
+ * Map points as parallel arrays: for map point i and camera c, entry i*n_cams+c.
+ *   mp_bad[nmp]; in_view[nmp*n_cams]; level[..]; proj_x[..], proj_y[..]; view_cos[..];
+ *   mp_desc[nmp*dim] (+ mp_dmask).
+ * frame_mp[n_keys]: in/out, index of the map point assigned to each keypoint (-1 = none) --
+ * the flat image of F.mvpMapPoints.  having_masks selects the masked distance. */
+typedef struct mcs_mappoint_view {
+    int32_t n_points;
+    const uint8_t* bad;
+    const uint8_t* in_view;
+    const int32_t* level;
+    const double*  proj_x;
+    const double*  proj_y;
+    const double*  view_cos;
+    const uint8_t* desc;
+    const uint8_t* dmask;
+} mcs_mappoint_view;
+
+int  mcs_search_by_projection(const mcs_frame_view* frame, const mcs_mappoint_view* mps,
+                              double th, double nnratio, int32_t th_high, int32_t having_masks,
+                              int32_t* frame_mp, int32_t* nmatches);
+
+/* cORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)
+ * (ref :579-726, checkOrientation is compile-time false: include/cORBmatcher.h:40).
+ * prev_matched[2*n1] in/out (x,y doubles); matches12[n1] out. */
+int  mcs_search_for_initialization(const mcs_frame_view* f1, const mcs_frame_view* f2,
+                                   double* prev_matched, int32_t window_size,
+                                   double nnratio, int32_t th_low, int32_t having_masks,
+                                   int32_t* matches12, int32_t* nmatches);
+
+/* ---- packed per-camera slot for the multi-GPU allgather ----------------------- */
+/* Slot layout (bytes): int32 n; int32 pad[3]; mcs_keypoint kp[capacity];
+ * uint8 desc[capacity*dim]; uint8 dmask[capacity*dim].  Size below. */
+size_t mcs_slot_bytes(int32_t capacity, int32_t dim);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCS_B200_H */

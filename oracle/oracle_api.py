@@ -1,0 +1,118 @@
+"""ctypes wrapper of oracle/libmcs_oracle.so -- TEST INFRASTRUCTURE (see mcs_oracle.cpp header).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/--impl reference legs import this."""
+import ctypes as C
+import pathlib
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(_HERE.parent))
+from multicol_slam_b200.ctypes_defs import (ExtractorInfo, ExtractorParams, FrameView, KEYPOINT_DTYPE,  # noqa: E402
+                                            MapPointView, Ocam, make_ocam, make_params)
+
+_lib = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", str(_HERE), "CXX=g++"])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        so = _HERE / "libmcs_oracle.so"
+        if not so.exists():
+            build()
+        _lib = C.CDLL(str(so))
+        _lib.mcso_extractor_create.restype = C.c_void_p
+        _lib.mcso_fast_atan2.restype = C.c_float
+        _lib.mcso_fast_atan2.argtypes = [C.c_float, C.c_float]
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class OracleExtractor:
+    def __init__(self, **kw):
+        self.params = make_params(**kw)
+        self.h = C.c_void_p(lib().mcso_extractor_create(C.byref(self.params)))
+        if not self.h:
+            raise ValueError("unsupported extractor params")
+        self.info = ExtractorInfo()
+        lib().mcso_extractor_get_info(self.h, C.byref(self.info))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().mcso_extractor_destroy(self.h)
+            self.h = None
+
+    def extract(self, image, mask, cam):
+        """-> (kps structured array, desc [n,ds] u8, dmask [n,ds] u8)"""
+        image = np.ascontiguousarray(image, np.uint8)
+        mask = np.ascontiguousarray(mask, np.uint8)
+        cap, ds = self.info.capacity, self.info.desc_size
+        kps = np.zeros(cap, KEYPOINT_DTYPE)
+        desc = np.zeros((cap, ds), np.uint8)
+        dmask = np.zeros((cap, ds), np.uint8)
+        n = C.c_int(0)
+        oc = cam if isinstance(cam, Ocam) else make_ocam(cam)
+        h, w = image.shape
+        st = lib().mcso_extract(self.h, _p(image), w, h, image.strides[0], _p(mask), mask.strides[0], C.byref(oc),
+                                _p(kps), _p(desc), _p(dmask), cap, C.byref(n))
+        if st != 0:
+            raise RuntimeError(f"oracle extract failed {st}")
+        return kps[:n.value].copy(), desc[:n.value].copy(), dmask[:n.value].copy()
+
+    def debug_read(self, level, what):
+        w, h = C.c_int(0), C.c_int(0)
+        buf = np.zeros(1 << 24, np.uint8)
+        st = lib().mcso_debug_read(self.h, level, what, _p(buf), buf.nbytes, C.byref(w), C.byref(h))
+        if st != 0:
+            raise RuntimeError(f"debug_read {st}")
+        if what == 3:
+            return buf[:w.value * 12].view(np.int32).reshape(-1, 3).copy()
+        return buf[:w.value * h.value].reshape(h.value, w.value).copy()
+
+
+def resize_linear(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros((dh, dw), np.uint8)
+    lib().mcso_resize_linear(_p(src), src.shape[1], src.shape[0], _p(dst), dw, dh)
+    return dst
+
+
+def resize_nearest(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros((dh, dw), np.uint8)
+    lib().mcso_resize_nearest(_p(src), src.shape[1], src.shape[0], _p(dst), dw, dh)
+    return dst
+
+
+def box5(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros_like(src)
+    lib().mcso_box5_reflect101(_p(src), src.shape[1], src.shape[0], _p(dst))
+    return dst
+
+
+def fast_atan2(y, x):
+    return lib().mcso_fast_atan2(C.c_float(y), C.c_float(x))
+
+
+def fast9(img, mask, threshold):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros((img.size, 3), np.int32)
+    n = lib().mcso_fast9(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(mask),
+                         mask.strides[0] if mask is not None else 0, threshold, _p(out), out.shape[0])
+    return out[:n].copy()
+
+
+def octree(xyr, minX, maxX, minY, maxY, N):
+    xyr = np.ascontiguousarray(xyr, np.float32)
+    out = np.zeros((max(len(xyr), 1), 3), np.float32)
+    n = lib().mcso_octree(_p(xyr), len(xyr), minX, maxX, minY, maxY, N, _p(out), out.shape[0])
+    return out[:n].copy()
