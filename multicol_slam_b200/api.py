@@ -1,0 +1,346 @@
+"""ctypes binding of libmcs_b200.so (include/mcs_b200.h) plus thin Python mirrors of the reference's
+operator/matcher interface for this path:
+
+    mdBRIEFextractorOct(...)(image, mask, camModel) -> keypoints, descriptors, descriptorMasks
+        (ref include/mdBRIEFextractorOct.h:333-368, src/mdBRIEFextractorOct.cpp:1244-1337)
+    cORBmatcher(nnratio, checkOri, featDim, havingMasks).SearchByProjection / SearchForInitialization /
+        SearchByBoW(KF1, KF2)   (ref include/cORBmatcher.h:58-158, src/cORBmatcher.cpp:46-166, 579-726, 885-966)
+
+There is no CPU fallback: the shared library must be present (build it with `python __graft_entry__.py`)
+and every compute call needs an sm_100 device, otherwise it raises.
+"""
+import ctypes as C
+import math
+import pathlib
+
+import numpy as np
+
+from .ctypes_defs import (ExtractorInfo, ExtractorParams, FrameView, KEYPOINT_DTYPE, MapPointView, Ocam,
+                          WINDOW_QUERY_DTYPE, make_ocam, make_params)
+
+_PKG = pathlib.Path(__file__).resolve().parent
+_LIB_PATH = _PKG / "libmcs_b200.so"
+_lib = None
+
+MCS_OK, MCS_ERR_INVALID, MCS_ERR_UNSUPPORTED, MCS_ERR_CUDA, MCS_ERR_CAPACITY, MCS_ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5
+
+
+class McsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libmcs_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    """Load libmcs_b200.so; fails loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise ImportError(f"{_LIB_PATH} is missing: the CUDA extension is mandatory (run __graft_entry__.build())")
+        _lib = C.CDLL(str(_LIB_PATH))
+        _lib.mcs_last_error.restype = C.c_char_p
+        _lib.mcs_slot_bytes.restype = C.c_size_t
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise McsError(rc, lib().mcs_last_error().decode())
+
+
+def _p(a):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def device_count():
+    return lib().mcs_device_count()
+
+
+def as_ocam(cam):
+    return cam if isinstance(cam, Ocam) else make_ocam(cam)
+
+
+def mirror_mask(cam):
+    oc = as_ocam(cam)
+    out = np.zeros((oc.height, oc.width), np.uint8)
+    _check(lib().mcs_cam_mirror_mask(C.byref(oc), _p(out)))
+    return out
+
+
+def world_to_img(cam, x, y, z):
+    oc = as_ocam(cam)
+    u, v = C.c_double(), C.c_double()
+    lib().mcs_cam_world_to_img(C.byref(oc), C.c_double(x), C.c_double(y), C.c_double(z), C.byref(u), C.byref(v))
+    return u.value, v.value
+
+
+def img_to_world(cam, u, v):
+    oc = as_ocam(cam)
+    x, y, z = C.c_double(), C.c_double(), C.c_double()
+    lib().mcs_cam_img_to_world(C.byref(oc), C.c_double(u), C.c_double(v), C.byref(x), C.byref(y), C.byref(z))
+    return x.value, y.value, z.value
+
+
+class mdBRIEFextractorOct:
+    """Same constructor arguments, order and defaults as the reference class."""
+    HARRIS_SCORE, FAST_SCORE = 0, 1
+
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, edgeThreshold=25, firstLevel=0, scoreType=0,
+                 patchSize=32, fastThreshold=20, useAgast=False, fastAgastType=2, do_dBrief=False, learnMasks=False,
+                 descSize=32):
+        self.params = ExtractorParams(nfeatures, scaleFactor, nlevels, edgeThreshold, firstLevel, scoreType, patchSize,
+                                      fastThreshold, int(useAgast), fastAgastType, int(do_dBrief), int(learnMasks), descSize)
+        self._h = C.c_void_p()
+        _check(lib().mcs_extractor_create(C.byref(self.params), C.byref(self._h)))
+        self.info = ExtractorInfo()
+        _check(lib().mcs_extractor_get_info(self._h, C.byref(self.info)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().mcs_extractor_destroy(self._h)
+            self._h = None
+
+    # reference getters
+    def GetLevels(self):
+        return self.info.nlevels
+
+    def GetScaleFactor(self):
+        return float(np.float32(self.params.scale_factor))
+
+    def GetMasksLearned(self):
+        return bool(self.params.learn_masks)
+
+    def GetDescriptorSize(self):
+        return self.info.desc_size
+
+    @property
+    def capacity(self):
+        return self.info.capacity
+
+    def __call__(self, image, mask, camModel):
+        """operator(): -> (keypoints structured array [n], descriptors [n,descSize] u8, descriptorMasks [n,descSize] u8).
+        An empty image returns None (the reference returns without touching its outputs)."""
+        if image is None or image.size == 0:
+            return None
+        image = np.ascontiguousarray(image, np.uint8)
+        mask = np.ascontiguousarray(mask, np.uint8)
+        cap, ds = self.info.capacity, self.info.desc_size
+        kps = np.zeros(cap, KEYPOINT_DTYPE)
+        desc = np.zeros((cap, ds), np.uint8)
+        dmask = np.zeros((cap, ds), np.uint8)
+        n = C.c_int32(0)
+        oc = as_ocam(camModel)
+        h, w = image.shape
+        _check(lib().mcs_extract(self._h, _p(image), w, h, image.strides[0], _p(mask), mask.strides[0], C.byref(oc),
+                                 _p(kps), _p(desc), _p(dmask), cap, C.byref(n)))
+        return kps[:n.value].copy(), desc[:n.value].copy(), dmask[:n.value].copy()
+
+    def extract_batch(self, images, masks, cams, cam_of_image):
+        """images [B,H,W] u8 host; masks [n_cams,H,W]; cams list; -> (kps [B,cap], desc [B,cap,ds], dmask, counts [B])"""
+        images = np.ascontiguousarray(images, np.uint8)
+        masks = np.ascontiguousarray(masks, np.uint8)
+        coi = np.ascontiguousarray(cam_of_image, np.int32)
+        B, H, W = images.shape
+        cap, ds = self.info.capacity, self.info.desc_size
+        ocs = (Ocam * len(cams))(*[as_ocam(c) for c in cams])
+        kps = np.zeros((B, cap), KEYPOINT_DTYPE)
+        desc = np.zeros((B, cap, ds), np.uint8)
+        dmask = np.zeros((B, cap, ds), np.uint8)
+        counts = np.zeros(B, np.int32)
+        _check(lib().mcs_extract_batch(self._h, B, _p(images), W, H, W, _p(masks), ocs, len(cams), _p(coi), _p(kps),
+                                       _p(desc), _p(dmask), _p(counts), cap))
+        return kps, desc, dmask, counts
+
+    def extract_batch_device(self, images_t, masks, cams, cam_of_image, out=None, stream=None):
+        """torch CUDA tensors in/out (plumbing only): images_t [B,H,W] uint8 cuda.  Returns dict of cuda tensors
+        {kps [B,cap,7] int32-view, desc [B,cap,ds], dmask, counts [B]}; asynchronous on `stream` when given."""
+        import torch
+        assert images_t.is_cuda and images_t.dtype == torch.uint8 and images_t.is_contiguous()
+        B, H, W = images_t.shape
+        cap, ds = self.info.capacity, self.info.desc_size
+        dev = images_t.device
+        if out is None:
+            out = dict(kps=torch.empty((B, cap, 7), dtype=torch.int32, device=dev),
+                       desc=torch.empty((B, cap, ds), dtype=torch.uint8, device=dev),
+                       dmask=torch.empty((B, cap, ds), dtype=torch.uint8, device=dev),
+                       counts=torch.empty((B,), dtype=torch.int32, device=dev))
+        masks = np.ascontiguousarray(masks, np.uint8)
+        coi = np.ascontiguousarray(cam_of_image, np.int32)
+        ocs = (Ocam * len(cams))(*[as_ocam(c) for c in cams])
+        st = C.c_void_p(stream.cuda_stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream)
+        _check(lib().mcs_extract_batch_device(self._h, B, C.c_void_p(images_t.data_ptr()), W, H, W, _p(masks), ocs, len(cams),
+                                              _p(coi), C.c_void_p(out["kps"].data_ptr()), C.c_void_p(out["desc"].data_ptr()),
+                                              C.c_void_p(out["dmask"].data_ptr()), C.c_void_p(out["counts"].data_ptr()), cap, st))
+        return out
+
+    def debug_read(self, level, what, image_index=0):
+        w, h = C.c_int32(0), C.c_int32(0)
+        buf = np.zeros(1 << 24, np.uint8)
+        _check(lib().mcs_extractor_debug_read(self._h, image_index, level, what, _p(buf), C.c_size_t(buf.nbytes), C.byref(w), C.byref(h)))
+        if what == 3:
+            return buf[:w.value * 12].view(np.int32).reshape(-1, 3).copy()
+        return buf[:w.value * h.value].reshape(h.value, w.value).copy()
+
+
+# ---- matcher --------------------------------------------------------------------------------------
+def DescriptorDistance64(a, b, dim=32):
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    return lib().mcs_descriptor_distance64(_p(a), _p(b), dim)
+
+
+def DescriptorDistance64Masked(a, b, ma, mb, dim=32):
+    a, b, ma, mb = (np.ascontiguousarray(v, np.uint8) for v in (a, b, ma, mb))
+    return lib().mcs_descriptor_distance64_masked(_p(a), _p(b), _p(ma), _p(mb), dim)
+
+
+def hamming_topk(q, d, K=2, qmask=None, dmask=None, db_skip=None):
+    q = np.ascontiguousarray(q, np.uint8)
+    d = np.ascontiguousarray(d, np.uint8)
+    qmask = None if qmask is None else np.ascontiguousarray(qmask, np.uint8)
+    dmask = None if dmask is None else np.ascontiguousarray(dmask, np.uint8)
+    db_skip = None if db_skip is None else np.ascontiguousarray(db_skip, np.uint8)
+    nq, dim = q.shape
+    idx = np.zeros((nq, K), np.int32)
+    dist = np.zeros((nq, K), np.int32)
+    _check(lib().mcs_hamming_topk(_p(q), _p(qmask), nq, _p(d), _p(dmask), d.shape[0], _p(db_skip), dim, K, _p(idx), _p(dist)))
+    return idx, dist
+
+
+def hamming_topk_device(q_t, d_t, K=2, qmask_t=None, dmask_t=None, skip_t=None, out=None, stream=None):
+    """torch CUDA uint8 tensors [nq,dim] / [nd,dim] -> (idx [nq,K] int32, dist [nq,K] int32) cuda tensors."""
+    import torch
+    nq, dim = q_t.shape
+    dev = q_t.device
+    if out is None:
+        out = (torch.empty((nq, K), dtype=torch.int32, device=dev), torch.empty((nq, K), dtype=torch.int32, device=dev))
+    ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+    st = C.c_void_p(stream.cuda_stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream)
+    _check(lib().mcs_hamming_topk_device(ptr(q_t), ptr(qmask_t), nq, ptr(d_t), ptr(dmask_t), d_t.shape[0], ptr(skip_t), dim, K,
+                                         ptr(out[0]), ptr(out[1]), st))
+    return out
+
+
+class Frame:
+    """Flat stand-in for the fields of cMultiFrame / cMultiKeyFrame the matchers read
+    (ref include/cMultiFrame.h:90-175): contiguous keypoints in camera-major order."""
+
+    def __init__(self, keys, key_cam, desc, dmask, cam_sizes, scale_factors):
+        self.keys = np.ascontiguousarray(keys, KEYPOINT_DTYPE)
+        self.key_cam = np.ascontiguousarray(key_cam, np.int32)
+        self.desc = np.ascontiguousarray(desc, np.uint8)
+        self.dmask = None if dmask is None else np.ascontiguousarray(dmask, np.uint8)
+        self.cam_w = np.ascontiguousarray([s[0] for s in cam_sizes], np.int32)
+        self.cam_h = np.ascontiguousarray([s[1] for s in cam_sizes], np.int32)
+        self.scale_factors = np.ascontiguousarray(scale_factors, np.float64)
+
+    @staticmethod
+    def from_cameras(per_cam, cam_sizes, scale_factors):
+        """per_cam: list of (kps, desc, dmask) as returned by the extractor, in camera order (ref :168-184)."""
+        keys = np.concatenate([p[0] for p in per_cam])
+        key_cam = np.concatenate([np.full(len(p[0]), c, np.int32) for c, p in enumerate(per_cam)])
+        desc = np.concatenate([p[1] for p in per_cam])
+        dmask = np.concatenate([p[2] for p in per_cam]) if per_cam[0][2] is not None else None
+        return Frame(keys, key_cam, desc, dmask, cam_sizes, scale_factors)
+
+    def view(self):
+        v = FrameView()
+        v.n_cams, v.n_keys = len(self.cam_w), len(self.keys)
+        v.keys, v.key_cam, v.desc = _p(self.keys).value, _p(self.key_cam).value, _p(self.desc).value
+        v.dmask = _p(self.dmask).value if self.dmask is not None else None
+        v.cam_width, v.cam_height = _p(self.cam_w).value, _p(self.cam_h).value
+        v.dim, v.n_levels = self.desc.shape[1], len(self.scale_factors)
+        v.scale_factors = _p(self.scale_factors).value
+        return v
+
+
+class MapPoints:
+    """Parallel arrays of the cMapPoint tracking fields (ref include/cMapPoint.h: mbTrackInView, mnTrackScaleLevel,
+    mTrackProjX/Y, mTrackViewCos; GetDescriptorPtr / GetDescriptorMaskPtr)."""
+
+    def __init__(self, bad, in_view, level, proj_x, proj_y, view_cos, desc, dmask=None):
+        self.bad = np.ascontiguousarray(bad, np.uint8)
+        self.in_view = np.ascontiguousarray(in_view, np.uint8)
+        self.level = np.ascontiguousarray(level, np.int32)
+        self.proj_x = np.ascontiguousarray(proj_x, np.float64)
+        self.proj_y = np.ascontiguousarray(proj_y, np.float64)
+        self.view_cos = np.ascontiguousarray(view_cos, np.float64)
+        self.desc = np.ascontiguousarray(desc, np.uint8)
+        self.dmask = None if dmask is None else np.ascontiguousarray(dmask, np.uint8)
+
+    def view(self):
+        v = MapPointView()
+        v.n_points = len(self.bad)
+        v.bad, v.in_view, v.level = _p(self.bad).value, _p(self.in_view).value, _p(self.level).value
+        v.proj_x, v.proj_y, v.view_cos = _p(self.proj_x).value, _p(self.proj_y).value, _p(self.view_cos).value
+        v.desc = _p(self.desc).value
+        v.dmask = _p(self.dmask).value if self.dmask is not None else None
+        return v
+
+
+def window_search(frame, queries, qdesc, qmask=None, max_cand=64):
+    queries = np.ascontiguousarray(queries, WINDOW_QUERY_DTYPE)
+    qdesc = np.ascontiguousarray(qdesc, np.uint8)
+    qmask = None if qmask is None else np.ascontiguousarray(qmask, np.uint8)
+    nq = len(queries)
+    idx = np.zeros((nq, max_cand), np.int32)
+    dist = np.zeros((nq, max_cand), np.int32)
+    cnt = np.zeros(nq, np.int32)
+    fv = frame.view()
+    rc = lib().mcs_window_search(C.byref(fv), _p(queries), nq, _p(qdesc), _p(qmask), max_cand, _p(idx), _p(dist), _p(cnt))
+    if rc not in (MCS_OK, MCS_ERR_CAPACITY):
+        _check(rc)
+    return idx, dist, cnt, rc
+
+
+class cORBmatcher:
+    """ref include/cORBmatcher.h:55-178; thresholds as in src/cORBmatcher.cpp:46-64."""
+
+    def __init__(self, nnratio=0.6, checkOri=True, featDim=32, havingMasks=False):
+        self.mfNNratio, self.mbCheckOrientation, self.mbFeatDim, self.havingMasks = nnratio, checkOri, featDim, havingMasks
+        if havingMasks:
+            self.TH_HIGH_, self.TH_LOW_ = int(math.floor(1.5 * featDim)), int(math.floor(featDim))
+        else:
+            self.TH_HIGH_, self.TH_LOW_ = 3 * featDim, 2 * featDim
+
+    def SearchByProjection(self, F, mapPoints, th, frame_mp=None):
+        """SearchByProjection(cMultiFrame&, vector<cMapPoint*>&, th) (ref :67-166).
+        frame_mp: F.mvpMapPoints as int32 indices (-1 = none), updated in place.  Returns (nmatches, frame_mp)."""
+        if frame_mp is None:
+            frame_mp = np.full(len(F.keys), -1, np.int32)
+        frame_mp = np.ascontiguousarray(frame_mp, np.int32)
+        n = C.c_int32(0)
+        fv, mv = F.view(), mapPoints.view()
+        _check(lib().mcs_search_by_projection(C.byref(fv), C.byref(mv), C.c_double(th), C.c_double(self.mfNNratio), self.TH_HIGH_,
+                                              int(self.havingMasks), _p(frame_mp), C.byref(n)))
+        return n.value, frame_mp
+
+    def SearchForInitialization(self, F1, F2, vbPrevMatched, windowSize=10):
+        """ref :579-726.  vbPrevMatched [n1,2] float64 updated in place.  Returns (nmatches, vnMatches12)."""
+        prev = np.ascontiguousarray(vbPrevMatched, np.float64)
+        m12 = np.zeros(len(F1.keys), np.int32)
+        n = C.c_int32(0)
+        f1, f2 = F1.view(), F2.view()
+        _check(lib().mcs_search_for_initialization(C.byref(f1), C.byref(f2), _p(prev), windowSize, C.c_double(self.mfNNratio),
+                                                   self.TH_LOW_, int(self.havingMasks), _p(m12), C.byref(n)))
+        if prev is not vbPrevMatched:
+            vbPrevMatched[...] = prev
+        return n.value, m12
+
+    def SearchByBoW(self, desc1, desc2, mask1=None, mask2=None, valid1=None, valid2=None):
+        """SearchByBoW(cMultiKeyFrame*, cMultiKeyFrame*, vpMatches12) (ref :885-966): all-pairs scan over the
+        map-point-bearing keypoints of two keyframes.  Returns (nmatches, matches12 indices into desc2)."""
+        d1 = np.ascontiguousarray(desc1, np.uint8)
+        d2 = np.ascontiguousarray(desc2, np.uint8)
+        use = self.havingMasks and mask1 is not None and mask2 is not None
+        m1 = np.ascontiguousarray(mask1, np.uint8) if use else None
+        m2 = np.ascontiguousarray(mask2, np.uint8) if use else None
+        v1 = None if valid1 is None else np.ascontiguousarray(valid1, np.uint8)
+        v2 = None if valid2 is None else np.ascontiguousarray(valid2, np.uint8)
+        m12 = np.zeros(len(d1), np.int32)
+        n = C.c_int32(0)
+        _check(lib().mcs_match_bruteforce(_p(d1), _p(m1), _p(v1), len(d1), _p(d2), _p(m2), _p(v2), len(d2), d1.shape[1],
+                                          self.TH_LOW_, C.c_double(self.mfNNratio), _p(m12), C.byref(n)))
+        return n.value, m12

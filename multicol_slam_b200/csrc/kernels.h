@@ -1,0 +1,39 @@
+// kernels.h -- launchers exported by the .cu files to the C-ABI host layer (mcs_api.cu).
+#pragma once
+#include "mcs_common.cuh"
+
+namespace mcs {
+
+struct DescribeArgs {
+    const uint8_t* lvl[kMaxLevels];
+    const uint8_t* blur[kMaxLevels];
+};
+
+cudaError_t upload_constants(const signed char* pairs, const signed char* du, const signed char* dv);
+void launch_pyr_fast(const PyramidGeom& G, int level, int n_images, const uint8_t* src, size_t src_img_bytes,
+                     uint8_t* dst, uint8_t* dst_blur, const uint8_t* mask0, int mask_w, size_t mask_bytes,
+                     const int* cam_of_image, uint32_t* raw, int* raw_count, cudaStream_t st);
+cudaError_t launch_octree(const PyramidGeom& G, const PyramidGeom* G_dev, int n_images, const uint32_t* raw,
+                          const int* raw_count, uint16_t* node_of, uint32_t* sel_xys, int* sel_count, int* status,
+                          cudaStream_t st);
+void launch_describe(const PyramidGeom& G, const PyramidGeom* G_dev, int n_images, const DescribeArgs& args,
+                     const mcs_ocam* cams, const int* cam_of_image, const uint32_t* sel_xys, const int* sel_count,
+                     mcs_keypoint* kps, uint8_t* desc, uint8_t* dmask, int* counts, int capacity, cudaStream_t st);
+
+// matching (match_kernels.cu)
+cudaError_t launch_hamming_topk(const uint8_t* q, const uint8_t* qmask, int nq, const uint8_t* d, const uint8_t* dmask,
+                                int nd, const uint8_t* db_skip, int dim, int K, int* topk_idx, int* topk_dist,
+                                cudaStream_t st);
+struct WindowFrameDev {
+    int n_cams, n_keys, dim;
+    const float* kx; const float* ky; const int* koct;      // [n_keys]
+    const uint8_t* desc; const uint8_t* dmask;              // [n_keys*dim]
+    const int* cell_start;                                  // [n_cams*64*48 + 1] CSR over (cam, ix, iy)
+    const int* cell_items;                                  // [n_in_grid] keypoint ids, ascending inside a cell
+    const double* winv; const double* hinv;                 // [n_cams]
+};
+cudaError_t launch_window_search(const WindowFrameDev& f, const mcs_window_query* q, int nq, const uint8_t* qdesc,
+                                 const uint8_t* qmask, int max_cand, int* cand_idx, int* cand_dist, int* cand_count,
+                                 cudaStream_t st);
+
+}  // namespace mcs

@@ -1,0 +1,251 @@
+// match_kernels.cu -- sm_100a kernels of the matcher half of the hot path.
+//
+//   M2 hamming_topk_kernel : all-pairs bit-level Hamming distance (ref src/cORBmatcher.cpp:2438-2474)
+//                            of nq queries against nd database descriptors, K best (distance, index)
+//                            per query.  One thread owns one query (descriptor words in registers),
+//                            database tiles are staged in shared memory with 128-bit loads and broadcast.
+//                            Bound by the POPC issue rate, not HBM (hard part 7).
+//   M1/M3 window_search_kernel : GetFeaturesInArea (ref src/cMultiFrame.cpp:272-340) + distance to every
+//                            candidate, one warp per query, candidates emitted in the reference's visiting
+//                            order (cell-x outer, cell-y inner, insertion order inside a cell).
+#include "mcs_common.cuh"
+#include "kernels.h"
+
+namespace mcs {
+
+constexpr int kTopKMax = 8;
+constexpr int kDbTile = 256;
+constexpr int kTopkThreads = 128;
+constexpr unsigned long long kNoKey = 0xFFFFFFFFFFFFFFFFull;
+
+template <int WORDS, bool MASKED>
+__global__ void __launch_bounds__(kTopkThreads)
+hamming_topk_kernel(const uint32_t* __restrict__ q, const uint32_t* __restrict__ qmask, const int nq,
+                    const uint32_t* __restrict__ d, const uint32_t* __restrict__ dmask, const int nd,
+                    const uint8_t* __restrict__ skip, const int K, const int chunk,
+                    unsigned long long* __restrict__ part /* [splits][nq][kTopKMax] */) {
+    __shared__ __align__(16) uint32_t s_d[kDbTile * WORDS];
+    __shared__ __align__(16) uint32_t s_m[MASKED ? kDbTile * WORDS : 4];
+    __shared__ uint8_t s_skip[kDbTile];
+
+    const int qi = blockIdx.x * kTopkThreads + threadIdx.x;
+    const bool active = qi < nq;
+    uint32_t qw[WORDS], qm[MASKED ? WORDS : 1];
+#pragma unroll
+    for (int k = 0; k < WORDS; ++k) {
+        qw[k] = active ? q[(size_t)qi * WORDS + k] : 0u;
+        if (MASKED) qm[k] = active ? qmask[(size_t)qi * WORDS + k] : 0u;
+    }
+    unsigned long long best[kTopKMax];
+#pragma unroll
+    for (int k = 0; k < kTopKMax; ++k) best[k] = kNoKey;
+    unsigned worst = 0xFFFFFFFFu;          // distance of the current K-th best
+
+    const int j0 = blockIdx.y * chunk, j1 = min(j0 + chunk, nd);
+    for (int t0 = j0; t0 < j1; t0 += kDbTile) {
+        const int tn = min(kDbTile, j1 - t0);
+        __syncthreads();
+        {   // 128-bit coalesced staging of the database tile
+            const uint4* src = (const uint4*)(d + (size_t)t0 * WORDS);
+            uint4* dst = (uint4*)s_d;
+            for (int i = threadIdx.x; i < tn * WORDS / 4; i += kTopkThreads) dst[i] = src[i];
+            if (MASKED) {
+                const uint4* msrc = (const uint4*)(dmask + (size_t)t0 * WORDS);
+                uint4* mdst = (uint4*)s_m;
+                for (int i = threadIdx.x; i < tn * WORDS / 4; i += kTopkThreads) mdst[i] = msrc[i];
+            }
+            for (int i = threadIdx.x; i < tn; i += kTopkThreads) s_skip[i] = skip ? skip[t0 + i] : 0;
+        }
+        __syncthreads();
+        for (int j = 0; j < tn; ++j) {
+            if (s_skip[j]) continue;       // uniform across the CTA
+            unsigned dist = 0;
+            if (MASKED) {
+#pragma unroll
+                for (int k = 0; k < WORDS; ++k) {
+                    const uint32_t x = qw[k] ^ s_d[j * WORDS + k];
+                    dist += __popc(x & qm[k]) + __popc(x & s_m[j * WORDS + k]);
+                }
+                dist >>= 1;               // integer division by 2 of the reference (:2472)
+            } else {
+#pragma unroll
+                for (int k = 0; k < WORDS; ++k) dist += __popc(qw[k] ^ s_d[j * WORDS + k]);
+            }
+            if (dist < worst) {            // strict: equal distances keep the earlier index
+                unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)(t0 + j);
+#pragma unroll
+                for (int k = 0; k < kTopKMax; ++k) {
+                    if (k < K && key < best[k]) { const unsigned long long t = best[k]; best[k] = key; key = t; }
+                }
+                const unsigned long long kth = best[0];
+                unsigned long long w = kth;
+#pragma unroll
+                for (int k = 1; k < kTopKMax; ++k) if (k < K) w = best[k];
+                worst = (w == kNoKey) ? 0xFFFFFFFFu : (unsigned)(w >> 32);
+            }
+        }
+    }
+    if (active) {
+        unsigned long long* o = part + ((size_t)blockIdx.y * nq + qi) * kTopKMax;
+#pragma unroll
+        for (int k = 0; k < kTopKMax; ++k) o[k] = best[k];
+    }
+}
+
+__global__ void topk_merge_kernel(const unsigned long long* __restrict__ part, const int splits, const int nq, const int K,
+                                  int* __restrict__ topk_idx, int* __restrict__ topk_dist) {
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    unsigned long long best[kTopKMax];
+#pragma unroll
+    for (int k = 0; k < kTopKMax; ++k) best[k] = kNoKey;
+    for (int s = 0; s < splits; ++s) {
+        const unsigned long long* p = part + ((size_t)s * nq + qi) * kTopKMax;
+        for (int i = 0; i < K; ++i) {
+            unsigned long long key = p[i];
+            if (key == kNoKey) break;
+#pragma unroll
+            for (int k = 0; k < kTopKMax; ++k) {
+                if (k < K && key < best[k]) { const unsigned long long t = best[k]; best[k] = key; key = t; }
+            }
+        }
+    }
+    for (int k = 0; k < K; ++k) {
+        const bool none = best[k] == kNoKey;
+        topk_idx[(size_t)qi * K + k] = none ? -1 : (int)(best[k] & 0xFFFFFFFFull);
+        topk_dist[(size_t)qi * K + k] = none ? 0x7FFFFFFF : (int)(best[k] >> 32);
+    }
+}
+
+static unsigned long long* g_part = nullptr;     // per-process scratch for partial top-K lists
+static size_t g_part_bytes = 0;
+
+cudaError_t launch_hamming_topk(const uint8_t* q, const uint8_t* qmask, int nq, const uint8_t* d, const uint8_t* dmask,
+                                int nd, const uint8_t* db_skip, int dim, int K, int* topk_idx, int* topk_dist,
+                                cudaStream_t st) {
+    if (K < 1 || K > kTopKMax || (dim != 16 && dim != 32 && dim != 64)) return cudaErrorInvalidValue;
+    if (nq <= 0) return cudaSuccess;
+    const int qblocks = (nq + kTopkThreads - 1) / kTopkThreads;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // enough CTAs for ~4 waves; database chunks are multiples of the tile
+    int splits = (4 * sms * 8 + qblocks - 1) / qblocks;
+    const int tiles = (nd + kDbTile - 1) / kDbTile;
+    splits = max(1, min(splits, tiles));
+    const int chunk = ((tiles + splits - 1) / splits) * kDbTile;
+    splits = max(1, (nd + chunk - 1) / chunk);
+    const size_t need = (size_t)splits * nq * kTopKMax * sizeof(unsigned long long);
+    if (need > g_part_bytes) {
+        if (g_part) cudaFree(g_part);
+        cudaError_t e = cudaMalloc(&g_part, need);
+        if (e != cudaSuccess) { g_part = nullptr; g_part_bytes = 0; return e; }
+        g_part_bytes = need;
+    }
+    dim3 grid(qblocks, splits);
+    const bool masked = qmask && dmask;
+#define MCS_TOPK(W, M) hamming_topk_kernel<W, M><<<grid, kTopkThreads, 0, st>>>((const uint32_t*)q, (const uint32_t*)qmask, nq, \
+        (const uint32_t*)d, (const uint32_t*)dmask, nd, db_skip, K, chunk, g_part)
+    if (dim == 16) { if (masked) MCS_TOPK(4, true); else MCS_TOPK(4, false); }
+    else if (dim == 32) { if (masked) MCS_TOPK(8, true); else MCS_TOPK(8, false); }
+    else { if (masked) MCS_TOPK(16, true); else MCS_TOPK(16, false); }
+#undef MCS_TOPK
+    topk_merge_kernel<<<(nq + 127) / 128, 128, 0, st>>>(g_part, splits, nq, K, topk_idx, topk_dist);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// window search
+// ------------------------------------------------------------------------------------------------
+template <int WORDS, bool MASKED>
+__global__ void __launch_bounds__(256)
+window_search_kernel(const WindowFrameDev f, const mcs_window_query* __restrict__ queries, const int nq,
+                     const uint32_t* __restrict__ qdesc, const uint32_t* __restrict__ qmask, const int max_cand,
+                     int* __restrict__ cand_idx, int* __restrict__ cand_dist, int* __restrict__ cand_count) {
+    const int lane = threadIdx.x & 31;
+    const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (qi >= nq) return;
+    const mcs_window_query qq = queries[qi];
+    const int cam = qq.cam;
+    const double x = qq.x, y = qq.y, r = qq.r;
+    // cell range (ref src/cMultiFrame.cpp:280-298): floor/ceil of double products, early outs
+    const double wi = f.winv[cam], hi = f.hinv[cam];
+    int count = 0;
+    bool empty = false;
+    int cx0 = (int)floor((x - 0 - r) * wi); cx0 = max(0, cx0); if (cx0 >= MCS_FRAME_GRID_COLS) empty = true;
+    int cx1 = (int)ceil((x - 0 + r) * wi);  cx1 = min(MCS_FRAME_GRID_COLS - 1, cx1); if (cx1 < 0) empty = true;
+    int cy0 = (int)floor((y - 0 - r) * hi); cy0 = max(0, cy0); if (cy0 >= MCS_FRAME_GRID_ROWS) empty = true;
+    int cy1 = (int)ceil((y - 0 + r) * hi);  cy1 = min(MCS_FRAME_GRID_ROWS - 1, cy1); if (cy1 < 0) empty = true;
+    if (!empty) {
+        uint32_t qw[WORDS], qm[MASKED ? WORDS : 1];
+#pragma unroll
+        for (int k = 0; k < WORDS; ++k) {
+            qw[k] = qdesc[(size_t)qq.desc_index * WORDS + k];
+            if (MASKED) qm[k] = qmask[(size_t)qq.desc_index * WORDS + k];
+        }
+        const bool check = !(qq.min_level == -1 && qq.max_level == -1);
+        const bool same = check && qq.min_level == qq.max_level;
+        int* oi = cand_idx + (size_t)qi * max_cand;
+        int* od = cand_dist + (size_t)qi * max_cand;
+        for (int ix = cx0; ix <= cx1; ++ix)
+            for (int iy = cy0; iy <= cy1; ++iy) {
+                const int cell = (cam * MCS_FRAME_GRID_COLS + ix) * MCS_FRAME_GRID_ROWS + iy;
+                const int s = f.cell_start[cell], e = f.cell_start[cell + 1];
+                for (int base = s; base < e; base += 32) {
+                    const int it = base + lane;
+                    bool ok = it < e;
+                    int id = 0;
+                    if (ok) {
+                        id = f.cell_items[it];
+                        const int oct = f.koct[id];
+                        if (check && !same) ok = !(oct < qq.min_level || oct > qq.max_level);
+                        else if (same) ok = (oct == qq.min_level);
+                        // abs(kp.pt.x - x) > r with float - double -> double (ref :328)
+                        if (ok) ok = !(fabs((double)f.kx[id] - x) > r || fabs((double)f.ky[id] - y) > r);
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, ok);
+                    if (ok) {
+                        const int pos = count + __popc(m & ((1u << lane) - 1u));
+                        if (pos < max_cand) {
+                            const uint32_t* dd = (const uint32_t*)f.desc + (size_t)id * WORDS;
+                            unsigned dist = 0;
+                            if (MASKED) {
+                                const uint32_t* mm = (const uint32_t*)f.dmask + (size_t)id * WORDS;
+#pragma unroll
+                                for (int k = 0; k < WORDS; ++k) {
+                                    const uint32_t xw = qw[k] ^ dd[k];
+                                    dist += __popc(xw & qm[k]) + __popc(xw & mm[k]);
+                                }
+                                dist >>= 1;
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < WORDS; ++k) dist += __popc(qw[k] ^ dd[k]);
+                            }
+                            oi[pos] = id;
+                            od[pos] = (int)dist;
+                        }
+                    }
+                    count += __popc(m);
+                }
+            }
+    }
+    if (lane == 0) cand_count[qi] = count;
+}
+
+cudaError_t launch_window_search(const WindowFrameDev& f, const mcs_window_query* q, int nq, const uint8_t* qdesc,
+                                 const uint8_t* qmask, int max_cand, int* cand_idx, int* cand_dist, int* cand_count,
+                                 cudaStream_t st) {
+    if (nq <= 0) return cudaSuccess;
+    const int blocks = (nq * 32 + 255) / 256;
+    const bool masked = qmask && f.dmask;
+#define MCS_WS(W, M) window_search_kernel<W, M><<<blocks, 256, 0, st>>>(f, q, nq, (const uint32_t*)qdesc, (const uint32_t*)qmask, \
+        max_cand, cand_idx, cand_dist, cand_count)
+    if (f.dim == 16) { if (masked) MCS_WS(4, true); else MCS_WS(4, false); }
+    else if (f.dim == 32) { if (masked) MCS_WS(8, true); else MCS_WS(8, false); }
+    else if (f.dim == 64) { if (masked) MCS_WS(16, true); else MCS_WS(16, false); }
+    else return cudaErrorInvalidValue;
+#undef MCS_WS
+    return cudaGetLastError();
+}
+
+}  // namespace mcs

@@ -1,0 +1,547 @@
+// mcs_api.cu -- C-ABI host layer of libmcs_b200.so (see include/mcs_b200.h).
+//
+// Host responsibilities only: parameter tables of the extractor constructor (ref
+// src/mdBRIEFextractorOct.cpp:134-203), per-image-size geometry / look-up tables, device buffers,
+// kernel launches, and the order-dependent bookkeeping of the matchers (greedy assignment rules of
+// ref src/cORBmatcher.cpp:67-166, :579-726, :885-966) replayed over GPU-computed distances.
+// There is no CPU implementation of the image or distance arithmetic in this library: without a CUDA
+// device every compute entry point fails with MCS_ERR_NO_DEVICE.
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "cam_model.cuh"
+#include "kernels.h"
+#include "mcs_common.cuh"
+
+using namespace mcs;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CK(expr)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e__ = (expr);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            cudaGetLastError();                                                                        \
+            return fail(e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver ? MCS_ERR_NO_DEVICE : MCS_ERR_CUDA, \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                          \
+        }                                                                                              \
+    } while (0)
+
+static const signed char kPairs[2048] = {
+#include "brief_pairs_64.inc"
+};
+
+inline int cv_round(double v) { return (int)lrint(v); }
+inline int cv_floor(double v) { int i = (int)v; return i - (i > v); }
+inline int cv_ceil(double v) { int i = (int)v; return i + (i < v); }
+inline short sat_short_round(float v) { int i = (int)lrintf(v); return (short)std::min(std::max(i, -32768), 32767); }
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct mcs_extractor {
+    mcs_extractor_params p;
+    int device = 0;
+    std::vector<double> sf, isf;
+    std::vector<int> quota;
+    int capacity = 0;
+    cudaStream_t stream = nullptr;
+
+    // geometry for the current image size
+    PyramidGeom G;
+    int geom_w = 0, geom_h = 0, geom_stride = 0;
+    DevBuf<uint8_t> lut_blob;
+    DevBuf<PyramidGeom> G_dev;
+
+    // device buffers (grown on demand)
+    int B_cap = 0;
+    DevBuf<uint8_t> in_images;
+    DevBuf<uint8_t> lvl[kMaxLevels], blur[kMaxLevels];
+    DevBuf<uint8_t> masks;
+    DevBuf<mcs_ocam> cams;
+    DevBuf<int> cam_of_image;
+    DevBuf<uint32_t> raw;
+    DevBuf<uint16_t> node_of;
+    DevBuf<int> raw_count, sel_count, status, counts;
+    DevBuf<uint32_t> sel_xys;
+    DevBuf<mcs_keypoint> kps;
+    DevBuf<uint8_t> desc, dmask;
+    int last_n_images = 0;
+};
+
+namespace {
+
+// ---- geometry: everything that depends only on (width, height, params) ------------------------
+int build_geometry(mcs_extractor* ex, int W, int H, int in_stride) {
+    if (ex->geom_w == W && ex->geom_h == H && ex->geom_stride == in_stride) return MCS_OK;
+    PyramidGeom& G = ex->G;
+    std::memset(&G, 0, sizeof(G));
+    const int L = ex->p.nlevels;
+    G.nlevels = L; G.width = W; G.height = H;
+    G.fast_threshold = ex->p.fast_threshold; G.desc_size = ex->p.desc_size;
+    G.do_dbrief = ex->p.do_dbrief; G.learn_masks = ex->p.learn_masks;
+    if (W >= 4096 || H >= 4096) return fail(MCS_ERR_UNSUPPORTED, "images larger than 4095 px are not supported");
+
+    std::vector<int16_t> blob;     // all LUTs, int16
+    struct Off { size_t xofs, xa0, xa1, yofs, yb0, yb1, cellx, celly, mx0, my0; } off[kMaxLevels];
+    std::vector<int16_t> pmx, pmy;
+    size_t raw_off = 0;
+    int sel_off = 0;
+    for (int l = 0; l < L; ++l) {
+        LevelGeom& g = G.lv[l];
+        g.w = cv_round((double)W * ex->isf[l]);
+        g.h = cv_round((double)H * ex->isf[l]);
+        if (g.w < 2 * kEdge + 8 || g.h < 2 * kEdge + 8)
+            return fail(MCS_ERR_UNSUPPORTED, "pyramid level smaller than 58 px");
+        g.pitch = (g.w + 63) & ~63;
+        g.img_bytes = (size_t)g.pitch * g.h;
+        g.sw = l ? G.lv[l - 1].w : W; g.sh = l ? G.lv[l - 1].h : H;
+        g.spitch = l ? G.lv[l - 1].pitch : in_stride;
+        g.tiles_x = (g.w + kTW - 1) / kTW; g.tiles_y = (g.h + kTH - 1) / kTH;
+        g.scale = (float)ex->sf[l];
+        g.patch_size = (float)(int)(32 * ex->sf[l]);
+        g.quota = ex->quota[l];
+        // resize tables (OpenCV resize INTER_LINEAR)
+        std::vector<int16_t> xofs(g.w), xa0(g.w), xa1(g.w), yofs(g.h), yb0(g.h), yb1(g.h), mx(g.w), my(g.h);
+        if (l) {
+            const double scale_x = 1.0 / ((double)g.w / g.sw), scale_y = 1.0 / ((double)g.h / g.sh);
+            if (scale_x > 2.0 || scale_y > 2.0) return fail(MCS_ERR_UNSUPPORTED, "scale factors above 2 are not supported");
+            for (int dx = 0; dx < g.w; ++dx) {
+                float fx = (float)((dx + 0.5) * scale_x - 0.5);
+                int sx = cv_floor(fx);
+                fx -= sx;
+                if (sx < 0) { fx = 0; sx = 0; }
+                if (sx >= g.sw - 1) { fx = 0; sx = g.sw - 1; }
+                xofs[dx] = (int16_t)sx;
+                xa0[dx] = sat_short_round((1.f - fx) * 2048.f);
+                xa1[dx] = sat_short_round(fx * 2048.f);
+                mx[dx] = pmx[std::min(cv_floor(dx * scale_x), g.sw - 1)];
+            }
+            for (int dy = 0; dy < g.h; ++dy) {
+                float fy = (float)((dy + 0.5) * scale_y - 0.5);
+                int sy = cv_floor(fy);
+                fy -= sy;
+                yofs[dy] = (int16_t)sy;
+                yb0[dy] = sat_short_round((1.f - fy) * 2048.f);
+                yb1[dy] = sat_short_round(fy * 2048.f);
+                my[dy] = pmy[std::min(cv_floor(dy * scale_y), g.sh - 1)];
+            }
+        } else {
+            for (int x = 0; x < g.w; ++x) { xofs[x] = (int16_t)x; xa0[x] = 2048; xa1[x] = 0; mx[x] = (int16_t)x; }
+            for (int y = 0; y < g.h; ++y) { yofs[y] = (int16_t)y; yb0[y] = 2048; yb1[y] = 0; my[y] = (int16_t)y; }
+        }
+        pmx = mx; pmy = my;
+        // FAST cell grid (ref :876-949)
+        std::vector<int16_t> cellx(g.w, -1), celly(g.h, -1);
+        const int minB = kEdge - 3, maxBX = g.w - kEdge + 3, maxBY = g.h - kEdge + 3;
+        const double width = maxBX - minB, height = maxBY - minB;
+        g.n_cols = (int)(width / 30.0); g.n_rows = (int)(height / 30.0);
+        if (g.n_cols < 1 || g.n_rows < 1) return fail(MCS_ERR_UNSUPPORTED, "level too small for the 30 px cell grid");
+        g.w_cell = (int)std::ceil(width / g.n_cols); g.h_cell = (int)std::ceil(height / g.n_rows);
+        if ((long long)g.n_cols * g.n_rows * g.w_cell * g.h_cell >= (1 << 24))
+            return fail(MCS_ERR_UNSUPPORTED, "cell-order key overflow");
+        for (int i = 0; i < g.n_rows; ++i) {
+            const double iniY = minB + i * g.h_cell;
+            double maxY = iniY + g.h_cell + 6;
+            if (iniY >= maxBY - 3) continue;
+            if (maxY > maxBY) maxY = maxBY;
+            for (int y = (int)iniY + 3; y < (int)maxY - 3; ++y) celly[y] = (int16_t)i;
+        }
+        for (int j = 0; j < g.n_cols; ++j) {
+            const double iniX = minB + j * g.w_cell;
+            double maxX = iniX + g.w_cell + 6;
+            if (iniX >= maxBX - 6) continue;
+            if (maxX > maxBX) maxX = maxBX;
+            for (int x = (int)iniX + 3; x < (int)maxX - 3; ++x) cellx[x] = (int16_t)j;
+        }
+        // a cell narrower/lower than 7 px yields nothing in cv::FAST; the ranges above are then empty.
+        // octree roots (ref :640-642)
+        g.nodes_ini = cv_round((double)(maxBX - minB) / (maxBY - minB));
+        if (g.nodes_ini < 1) return fail(MCS_ERR_UNSUPPORTED, "portrait images narrower than half their height");
+        g.hX = (double)(maxBX - minB) / g.nodes_ini;
+        g.sel_cap = std::max(g.quota + 3, 4 * g.nodes_ini);
+        g.sel_off = sel_off; sel_off += g.sel_cap;
+        g.raw_cap = ((g.w - 2 * kEdge + 1) / 2 + 1) * ((g.h - 2 * kEdge + 1) / 2 + 1);
+        g.raw_off = raw_off; raw_off += (size_t)((g.raw_cap + 3) & ~3);
+        auto put = [&](const std::vector<int16_t>& v) { size_t o = blob.size(); blob.insert(blob.end(), v.begin(), v.end()); while (blob.size() & 7) blob.push_back(0); return o; };
+        off[l] = {put(xofs), put(xa0), put(xa1), put(yofs), put(yb0), put(yb1), put(cellx), put(celly), put(mx), put(my)};
+    }
+    G.sel_total = sel_off; G.raw_total = raw_off; G.cap = ex->capacity;
+    CK(ex->lut_blob.ensure(blob.size() * sizeof(int16_t)));
+    CK(cudaMemcpyAsync(ex->lut_blob.p, blob.data(), blob.size() * sizeof(int16_t), cudaMemcpyHostToDevice, ex->stream));
+    const int16_t* base = (const int16_t*)ex->lut_blob.p;
+    for (int l = 0; l < L; ++l) {
+        LevelGeom& g = G.lv[l];
+        g.xofs = base + off[l].xofs; g.xa0 = base + off[l].xa0; g.xa1 = base + off[l].xa1;
+        g.yofs = base + off[l].yofs; g.yb0 = base + off[l].yb0; g.yb1 = base + off[l].yb1;
+        g.cellx = base + off[l].cellx; g.celly = base + off[l].celly;
+        g.mx0 = base + off[l].mx0; g.my0 = base + off[l].my0;
+    }
+    CK(ex->G_dev.ensure(1));
+    CK(cudaMemcpyAsync(ex->G_dev.p, &G, sizeof(G), cudaMemcpyHostToDevice, ex->stream));
+    CK(cudaStreamSynchronize(ex->stream));     // blob / G are host temporaries
+    ex->geom_w = W; ex->geom_h = H; ex->geom_stride = in_stride;
+    ex->B_cap = 0;      // level buffers depend on the geometry
+    return MCS_OK;
+}
+
+int ensure_batch(mcs_extractor* ex, int B) {
+    if (B <= ex->B_cap) return MCS_OK;
+    const PyramidGeom& G = ex->G;
+    for (int l = 0; l < G.nlevels; ++l) {
+        CK(ex->lvl[l].ensure(G.lv[l].img_bytes * B + 256));
+        CK(ex->blur[l].ensure(G.lv[l].img_bytes * B + 256));
+    }
+    CK(ex->cam_of_image.ensure(B));
+    CK(ex->raw.ensure(G.raw_total * B));
+    CK(ex->node_of.ensure(G.raw_total * B));
+    CK(ex->raw_count.ensure((size_t)B * G.nlevels));
+    CK(ex->sel_count.ensure((size_t)B * G.nlevels));
+    CK(ex->sel_xys.ensure((size_t)B * G.sel_total));
+    CK(ex->status.ensure(1));
+    ex->B_cap = B;
+    return MCS_OK;
+}
+
+int run_pipeline(mcs_extractor* ex, int n_images, const uint8_t* images_dev, int W, int H, int stride,
+                 const uint8_t* masks, const mcs_ocam* cams, int n_cams, const int* cam_of_image,
+                 mcs_keypoint* kps_dev, uint8_t* desc_dev, uint8_t* dmask_dev, int* counts_dev, int capacity,
+                 cudaStream_t st) {
+    if (n_cams < 1 || n_cams > 64) return fail(MCS_ERR_INVALID, "n_cams must be in [1,64]");
+    for (int i = 0; i < n_images; ++i)
+        if (cam_of_image[i] < 0 || cam_of_image[i] >= n_cams) return fail(MCS_ERR_INVALID, "cam_of_image out of range");
+    int rc = build_geometry(ex, W, H, stride);
+    if (rc) return rc;
+    rc = ensure_batch(ex, n_images);
+    if (rc) return rc;
+    const PyramidGeom& G = ex->G;
+    // small per-call host inputs
+    CK(ex->masks.ensure((size_t)n_cams * W * H));
+    CK(ex->cams.ensure(n_cams));
+    CK(cudaMemcpyAsync(ex->masks.p, masks, (size_t)n_cams * W * H, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ex->cams.p, cams, sizeof(mcs_ocam) * n_cams, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ex->cam_of_image.p, cam_of_image, sizeof(int) * n_images, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ex->raw_count.p, 0, sizeof(int) * n_images * G.nlevels, st));
+    CK(cudaMemsetAsync(ex->status.p, 0, sizeof(int), st));
+    for (int l = 0; l < G.nlevels; ++l) {
+        const uint8_t* src = l ? ex->lvl[l - 1].p : images_dev;
+        const size_t src_bytes = l ? G.lv[l - 1].img_bytes : (size_t)stride * H;
+        launch_pyr_fast(G, l, n_images, src, src_bytes, ex->lvl[l].p, ex->blur[l].p, ex->masks.p, W, (size_t)W * H,
+                        ex->cam_of_image.p, ex->raw.p, ex->raw_count.p, st);
+    }
+    CK(cudaGetLastError());
+    CK(launch_octree(G, ex->G_dev.p, n_images, ex->raw.p, ex->raw_count.p, ex->node_of.p, ex->sel_xys.p, ex->sel_count.p,
+                     ex->status.p, st));
+    CK(cudaGetLastError());
+    DescribeArgs a;
+    for (int l = 0; l < kMaxLevels; ++l) { a.lvl[l] = ex->lvl[l].p; a.blur[l] = ex->blur[l].p; }
+    launch_describe(G, ex->G_dev.p, n_images, a, ex->cams.p, ex->cam_of_image.p, ex->sel_xys.p, ex->sel_count.p, kps_dev,
+                    desc_dev, dmask_dev, counts_dev, capacity, st);
+    CK(cudaGetLastError());
+    ex->last_n_images = n_images;
+    return MCS_OK;
+}
+
+int check_status(mcs_extractor* ex, cudaStream_t st) {
+    int s = 0;
+    CK(cudaMemcpyAsync(&s, ex->status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (s & 1) return fail(MCS_ERR_CAPACITY, "raw corner list overflow");
+    if (s & 2) return fail(MCS_ERR_CAPACITY, "octree node table overflow");
+    if (s & 4) return fail(MCS_ERR_CAPACITY, "selected keypoint slots overflow");
+    return MCS_OK;
+}
+
+bool g_consts_uploaded[64] = {};
+std::mutex g_mu;
+
+int upload_consts_once(int dev) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (dev < 64 && g_consts_uploaded[dev]) return MCS_OK;
+    // the 845 offsets of the IC_Angle disc, umax as in ref :187-202
+    int umax[kHalfPatch + 1];
+    const int vmax = cv_floor(kHalfPatch * std::sqrt(2.f) / 2 + 1);
+    const int vmin = cv_ceil(kHalfPatch * std::sqrt(2.f) / 2);
+    for (int v = 0; v <= vmax; ++v) umax[v] = cv_round(std::sqrt((double)kHalfPatch * kHalfPatch - v * v));
+    for (int v = kHalfPatch, v0 = 0; v >= vmin; --v) {
+        while (umax[v0] == umax[v0 + 1]) ++v0;
+        umax[v] = v0;
+        ++v0;
+    }
+    signed char du[848] = {0}, dv[848] = {0};
+    int n = 0;
+    for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
+        const int d = v == 0 ? kHalfPatch : umax[std::abs(v)];
+        for (int u = -d; u <= d; ++u) { du[n] = (signed char)u; dv[n] = (signed char)v; ++n; }
+    }
+    if (n != 845) return fail(MCS_ERR_INVALID, "disc table size");
+    CK(upload_constants(kPairs, du, dv));
+    if (dev < 64) g_consts_uploaded[dev] = true;
+    return MCS_OK;
+}
+
+}  // namespace
+
+void mcs_set_error_(const std::string& msg) { g_err = msg; }
+
+// ================================================================================================
+extern "C" {
+
+const char* mcs_last_error(void) { return g_err.c_str(); }
+
+int mcs_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; ++i) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ++ok;
+    }
+    return ok;
+}
+
+void mcs_params_default(mcs_extractor_params* p) {
+    if (!p) return;
+    *p = mcs_extractor_params{1000, 1.2f, 8, 25, 0, 0, 32, 20, 0, 2, 0, 0, 32};
+}
+
+void mcs_cam_world_to_img(const mcs_ocam* cam, double x, double y, double z, double* u, double* v) {
+    cam_world_to_img(*cam, x, y, z, *u, *v);
+}
+void mcs_cam_img_to_world(const mcs_ocam* cam, double u, double v, double* x, double* y, double* z) {
+    cam_img_to_world(*cam, u, v, *x, *y, *z);
+}
+int mcs_cam_mirror_mask(const mcs_ocam* cam, uint8_t* out) {
+    if (!cam || !out) return fail(MCS_ERR_INVALID, "null argument");
+    const int w = cam->width, h = cam->height;
+    if (cam->mirror_mask != 1) { std::memset(out, 1, (size_t)w * h); return MCS_OK; }
+    // ref src/cam_model_omni.cpp:187-188 swaps the names on purpose
+    const float u0 = (float)cam->v0, v0 = (float)cam->u0;
+    for (int i = 0; i < h; ++i)
+        for (int j = 0; j < w; ++j) {
+            const float a = (float)std::pow(i - u0, 2), b = (float)std::pow(j - v0, 2);
+            out[(size_t)i * w + j] = std::sqrt(a + b) < (u0 + 22.0f) ? 255 : 0;
+        }
+    return MCS_OK;
+}
+
+int mcs_extractor_create(const mcs_extractor_params* p, mcs_extractor** out) {
+    if (!p || !out) return fail(MCS_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (p->use_agast) return fail(MCS_ERR_UNSUPPORTED, "AGAST detector is not built (north star: FAST-9)");
+    if (p->fast_agast_type != 2) return fail(MCS_ERR_UNSUPPORTED, "only FastFeatureDetector::TYPE_9_16 (type 2) is built");
+    if (p->nlevels < 1 || p->nlevels > kMaxLevels) return fail(MCS_ERR_INVALID, "nlevels must be in [1,16]");
+    if (p->desc_size != 16 && p->desc_size != 32 && p->desc_size != 64) return fail(MCS_ERR_INVALID, "desc_size must be 16, 32 or 64");
+    if (p->nfeatures < 1 || !(p->scale_factor > 1.0f) || p->fast_threshold < 1 || p->fast_threshold > 254)
+        return fail(MCS_ERR_INVALID, "bad nfeatures / scale_factor / fast_threshold");
+    int dev = 0;
+    {
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(MCS_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e)); }
+        int major = 0;
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+        if (major != 10) return fail(MCS_ERR_NO_DEVICE, "device is not sm_100 (B200); this library has no other code path");
+    }
+    int rc = upload_consts_once(dev);
+    if (rc) return rc;
+    mcs_extractor* ex = new mcs_extractor;
+    ex->p = *p; ex->device = dev;
+    // ref :151-179
+    const double sfd = (double)p->scale_factor;
+    ex->sf.resize(p->nlevels); ex->isf.resize(p->nlevels); ex->quota.resize(p->nlevels);
+    ex->sf[0] = 1; ex->isf[0] = 1;
+    for (int i = 1; i < p->nlevels; ++i) ex->sf[i] = ex->sf[i - 1] * sfd;
+    const double inv = 1.0 / sfd;
+    for (int i = 1; i < p->nlevels; ++i) ex->isf[i] = ex->isf[i - 1] * inv;
+    const double factor = 1.0 / sfd;
+    double nd = p->nfeatures * (1 - factor) / (1 - std::pow(factor, p->nlevels));
+    int sum = 0;
+    for (int l = 0; l < p->nlevels - 1; ++l) {
+        ex->quota[l] = cv_round(nd);
+        sum += ex->quota[l];
+        nd *= factor;
+    }
+    ex->quota[p->nlevels - 1] = std::max(p->nfeatures - sum, 0);
+    ex->capacity = 0;
+    for (int l = 0; l < p->nlevels; ++l) {
+        if (ex->quota[l] + 8 > kMaxNodes) { delete ex; return fail(MCS_ERR_UNSUPPORTED, "nfeatures too large for the octree node table"); }
+        ex->capacity += std::max(ex->quota[l] + 2, 16);
+    }
+    if (cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ex;
+        return fail(MCS_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    *out = ex;
+    return MCS_OK;
+}
+
+void mcs_extractor_destroy(mcs_extractor* ex) {
+    if (!ex) return;
+    cudaSetDevice(ex->device);
+    ex->lut_blob.release(); ex->G_dev.release(); ex->in_images.release();
+    for (int l = 0; l < kMaxLevels; ++l) { ex->lvl[l].release(); ex->blur[l].release(); }
+    ex->masks.release(); ex->cams.release(); ex->cam_of_image.release(); ex->raw.release(); ex->node_of.release();
+    ex->raw_count.release(); ex->sel_count.release(); ex->status.release(); ex->counts.release(); ex->sel_xys.release();
+    ex->kps.release(); ex->desc.release(); ex->dmask.release();
+    if (ex->stream) cudaStreamDestroy(ex->stream);
+    delete ex;
+}
+
+int mcs_extractor_get_info(const mcs_extractor* ex, mcs_extractor_info* info) {
+    if (!ex || !info) return fail(MCS_ERR_INVALID, "null argument");
+    std::memset(info, 0, sizeof(*info));
+    info->nlevels = ex->p.nlevels; info->capacity = ex->capacity; info->desc_size = ex->p.desc_size;
+    for (int l = 0; l < ex->p.nlevels; ++l) {
+        info->features_per_level[l] = ex->quota[l];
+        info->scale_factor[l] = ex->sf[l];
+        info->inv_scale_factor[l] = ex->isf[l];
+    }
+    return MCS_OK;
+}
+
+int mcs_extract_batch_device(mcs_extractor* ex, int32_t n_images, const uint8_t* images_dev, int32_t width, int32_t height,
+                             int32_t stride, const uint8_t* masks, const mcs_ocam* cams, int32_t n_cams,
+                             const int32_t* cam_of_image, mcs_keypoint* kps_dev, uint8_t* desc_dev, uint8_t* dmask_dev,
+                             int32_t* counts_dev, int32_t capacity, void* stream) {
+    if (!ex || !images_dev || !masks || !cams || !cam_of_image || !kps_dev || !desc_dev || !counts_dev)
+        return fail(MCS_ERR_INVALID, "null argument");
+    if (n_images < 1 || width < 1 || height < 1 || stride < width) return fail(MCS_ERR_INVALID, "bad image geometry");
+    if (capacity < ex->capacity) return fail(MCS_ERR_CAPACITY, "capacity below mcs_extractor_info.capacity");
+    if (ex->p.learn_masks && !dmask_dev) return fail(MCS_ERR_INVALID, "dmask buffer required when learn_masks is set");
+    CK(cudaSetDevice(ex->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ex->stream;
+    int rc = run_pipeline(ex, n_images, images_dev, width, height, stride, masks, cams, n_cams, cam_of_image, kps_dev, desc_dev,
+                          dmask_dev, counts_dev, capacity, st);
+    if (rc) return rc;
+    if (!stream) return check_status(ex, st);
+    return MCS_OK;
+}
+
+int mcs_extract_batch(mcs_extractor* ex, int32_t n_images, const uint8_t* images, int32_t width, int32_t height, int32_t stride,
+                      const uint8_t* masks, const mcs_ocam* cams, int32_t n_cams, const int32_t* cam_of_image,
+                      mcs_keypoint* kps_out, uint8_t* desc_out, uint8_t* dmask_out, int32_t* counts_out, int32_t capacity) {
+    if (!ex || !images || !masks || !cams || !cam_of_image || !kps_out || !desc_out || !counts_out)
+        return fail(MCS_ERR_INVALID, "null argument");
+    if (n_images < 1 || width < 1 || height < 1 || stride < width) return fail(MCS_ERR_INVALID, "bad image geometry");
+    if (capacity < ex->capacity) return fail(MCS_ERR_CAPACITY, "capacity below mcs_extractor_info.capacity");
+    if (ex->p.learn_masks && !dmask_out) return fail(MCS_ERR_INVALID, "dmask buffer required when learn_masks is set");
+    CK(cudaSetDevice(ex->device));
+    cudaStream_t st = ex->stream;
+    const int ds = ex->p.desc_size;
+    const size_t img_bytes = (size_t)stride * height;
+    CK(ex->in_images.ensure(img_bytes * n_images + 256));
+    CK(ex->kps.ensure((size_t)n_images * capacity));
+    CK(ex->desc.ensure((size_t)n_images * capacity * ds));
+    CK(ex->dmask.ensure((size_t)n_images * capacity * ds));
+    CK(ex->counts.ensure(n_images));
+    CK(cudaMemcpyAsync(ex->in_images.p, images, img_bytes * n_images, cudaMemcpyHostToDevice, st));
+    int rc = run_pipeline(ex, n_images, ex->in_images.p, width, height, stride, masks, cams, n_cams, cam_of_image, ex->kps.p,
+                          ex->desc.p, ex->dmask.p, ex->counts.p, capacity, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(counts_out, ex->counts.p, sizeof(int) * n_images, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(kps_out, ex->kps.p, sizeof(mcs_keypoint) * n_images * capacity, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(desc_out, ex->desc.p, (size_t)n_images * capacity * ds, cudaMemcpyDeviceToHost, st));
+    if (dmask_out) CK(cudaMemcpyAsync(dmask_out, ex->dmask.p, (size_t)n_images * capacity * ds, cudaMemcpyDeviceToHost, st));
+    return check_status(ex, st);
+}
+
+int mcs_extract(mcs_extractor* ex, const uint8_t* image, int32_t width, int32_t height, int32_t stride, const uint8_t* mask,
+                int32_t mask_stride, const mcs_ocam* cam, mcs_keypoint* kps_out, uint8_t* desc_out, uint8_t* dmask_out,
+                int32_t capacity, int32_t* n_out) {
+    if (!ex || !n_out) return fail(MCS_ERR_INVALID, "null argument");
+    if (!image) return MCS_OK;   // empty image: silent return, outputs untouched (ref :1252-1253)
+    if (!mask || !cam) return fail(MCS_ERR_INVALID, "a mask and a camera model are mandatory (ref :913-917 throws on an empty mask)");
+    std::vector<uint8_t> packed;
+    const uint8_t* m = mask;
+    if (mask_stride != width) {
+        packed.resize((size_t)width * height);
+        for (int y = 0; y < height; ++y) std::memcpy(packed.data() + (size_t)y * width, mask + (size_t)y * mask_stride, width);
+        m = packed.data();
+    }
+    const int zero = 0;
+    int count = 0;
+    // the batch entry point writes `capacity` slots per image; here slot 0 is the caller's buffer
+    int rc = mcs_extract_batch(ex, 1, image, width, height, stride, m, cam, 1, &zero, kps_out, desc_out, dmask_out, &count, capacity);
+    if (rc) return rc;
+    *n_out = count;
+    return MCS_OK;
+}
+
+int mcs_extractor_debug_read(mcs_extractor* ex, int32_t image_index, int32_t level, int32_t what, void* out, size_t out_bytes,
+                             int32_t* w_out, int32_t* h_out) {
+    if (!ex || !out || !w_out || !h_out) return fail(MCS_ERR_INVALID, "null argument");
+    if (level < 0 || level >= ex->G.nlevels || image_index < 0 || image_index >= ex->last_n_images)
+        return fail(MCS_ERR_INVALID, "bad level / image index");
+    CK(cudaSetDevice(ex->device));
+    const LevelGeom& g = ex->G.lv[level];
+    const int L = ex->G.nlevels;
+    if (what == 0 || what == 1) {
+        *w_out = g.w; *h_out = g.h;
+        if (out_bytes < (size_t)g.w * g.h) return fail(MCS_ERR_CAPACITY, "buffer too small");
+        const uint8_t* src = (what == 0 ? ex->lvl[level].p : ex->blur[level].p) + (size_t)image_index * g.img_bytes;
+        CK(cudaMemcpy2D(out, g.w, src, g.pitch, g.w, g.h, cudaMemcpyDeviceToHost));
+        return MCS_OK;
+    }
+    if (what == 2) {   // the mask pyramid is never materialised: evaluate the composed nearest-neighbour maps
+        *w_out = g.w; *h_out = g.h;
+        if (out_bytes < (size_t)g.w * g.h) return fail(MCS_ERR_CAPACITY, "buffer too small");
+        std::vector<int16_t> mx(g.w), my(g.h);
+        std::vector<int> coi(ex->last_n_images);
+        CK(cudaMemcpy(mx.data(), g.mx0, g.w * 2, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(my.data(), g.my0, g.h * 2, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(coi.data(), ex->cam_of_image.p, sizeof(int) * ex->last_n_images, cudaMemcpyDeviceToHost));
+        std::vector<uint8_t> m0((size_t)ex->G.width * ex->G.height);
+        CK(cudaMemcpy(m0.data(), ex->masks.p + (size_t)coi[image_index] * m0.size(), m0.size(), cudaMemcpyDeviceToHost));
+        for (int y = 0; y < g.h; ++y)
+            for (int x = 0; x < g.w; ++x) ((uint8_t*)out)[(size_t)y * g.w + x] = m0[(size_t)my[y] * ex->G.width + mx[x]];
+        return MCS_OK;
+    }
+    if (what == 3) {   // raw corners, sorted into the reference order (cell-row-major, then pixel-row-major)
+        int n = 0;
+        CK(cudaMemcpy(&n, ex->raw_count.p + (size_t)image_index * L + level, sizeof(int), cudaMemcpyDeviceToHost));
+        n = std::min(n, g.raw_cap);
+        *w_out = n; *h_out = 3;
+        if (out_bytes < (size_t)n * 12) return fail(MCS_ERR_CAPACITY, "buffer too small");
+        std::vector<uint32_t> c(n);
+        CK(cudaMemcpy(c.data(), ex->raw.p + (size_t)image_index * ex->G.raw_total + g.raw_off, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+        auto key = [&](uint32_t v) {
+            const int x = corner_x(v) - kEdge, y = corner_y(v) - kEdge;
+            const int cj = x / g.w_cell, ci = y / g.h_cell;
+            return (long long)(ci * g.n_cols + cj) * g.w_cell * g.h_cell + (y - ci * g.h_cell) * g.w_cell + (x - cj * g.w_cell);
+        };
+        std::sort(c.begin(), c.end(), [&](uint32_t a, uint32_t b) { return key(a) < key(b); });
+        int32_t* o = (int32_t*)out;
+        for (int i = 0; i < n; ++i) { o[3 * i] = corner_x(c[i]); o[3 * i + 1] = corner_y(c[i]); o[3 * i + 2] = corner_s(c[i]); }
+        return MCS_OK;
+    }
+    return fail(MCS_ERR_INVALID, "unknown `what`");
+}
+
+size_t mcs_slot_bytes(int32_t capacity, int32_t dim) {
+    return 16 + (size_t)capacity * (sizeof(mcs_keypoint) + 2 * (size_t)dim);
+}
+
+}  // extern "C"

@@ -1,0 +1,394 @@
+// mcs_match_api.cu -- C-ABI host layer of the matcher entry points (include/mcs_b200.h).
+//
+// The GPU evaluates every Hamming distance and every grid-window candidate search; the host code here
+// only (a) flattens the caller's frame into the CSR grid of cMultiFrame (ref src/cMultiFrame.cpp:168-184,
+// :342-353) and (b) replays the reference's order-dependent greedy bookkeeping over the GPU results
+// (ref src/cORBmatcher.cpp:121-164, :627-682, :922-961).
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "mcs_common.cuh"
+
+using namespace mcs;
+
+namespace {
+
+int mfail(int code, const std::string& msg);   // records the message for mcs_last_error() (mcs_api.cu)
+
+#define MCK(expr)                                                                                      \
+    do {                                                                                               \
+        cudaError_t e__ = (expr);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            cudaGetLastError();                                                                        \
+            return mfail(e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver ? MCS_ERR_NO_DEVICE : MCS_ERR_CUDA, \
+                         std::string(#expr) + ": " + cudaGetErrorString(e__));                         \
+        }                                                                                              \
+    } while (0)
+
+struct Dev {   // RAII device allocation
+    void* p = nullptr;
+    ~Dev() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 16)); }
+    template <typename T> T* as() { return (T*)p; }
+};
+
+inline int cv_round(double v) { return (int)lrint(v); }
+
+// frame uploaded for window searches
+struct FrameDev {
+    Dev kx, ky, koct, desc, dmask, cell_start, cell_items, winv, hinv;
+    WindowFrameDev view;
+};
+
+int upload_frame(const mcs_frame_view* f, FrameDev& d, cudaStream_t st) {
+    const int n = f->n_keys, nc = f->n_cams;
+    std::vector<float> kx(n), ky(n);
+    std::vector<int> koct(n);
+    std::vector<double> winv(nc), hinv(nc);
+    for (int c = 0; c < nc; ++c) {
+        winv[c] = (double)MCS_FRAME_GRID_COLS / (double)f->cam_width[c];
+        hinv[c] = (double)MCS_FRAME_GRID_ROWS / (double)f->cam_height[c];
+    }
+    const int ncell = nc * MCS_FRAME_GRID_COLS * MCS_FRAME_GRID_ROWS;
+    std::vector<int> cell_of(n), start(ncell + 1, 0);
+    for (int i = 0; i < n; ++i) {
+        kx[i] = f->keys[i].x; ky[i] = f->keys[i].y; koct[i] = f->keys[i].octave;
+        const int c = f->key_cam[i];
+        if (c < 0 || c >= nc) return mfail(MCS_ERR_INVALID, "key_cam out of range");
+        // PosInGrid: cvRound((pt - mnMin) * inv), float - int -> float, times double (ref :345-346)
+        const int px = cv_round((f->keys[i].x - 0) * winv[c]);
+        const int py = cv_round((f->keys[i].y - 0) * hinv[c]);
+        if (px < 0 || px >= MCS_FRAME_GRID_COLS || py < 0 || py >= MCS_FRAME_GRID_ROWS) { cell_of[i] = -1; continue; }
+        cell_of[i] = (c * MCS_FRAME_GRID_COLS + px) * MCS_FRAME_GRID_ROWS + py;
+        ++start[cell_of[i] + 1];
+    }
+    for (int c = 0; c < ncell; ++c) start[c + 1] += start[c];
+    std::vector<int> items(std::max(start[ncell], 1)), fill(start.begin(), start.end() - 1);
+    for (int i = 0; i < n; ++i) if (cell_of[i] >= 0) items[fill[cell_of[i]]++] = i;    // ascending index inside a cell
+    const size_t db = (size_t)n * f->dim;
+    MCK(d.kx.alloc(n * 4)); MCK(d.ky.alloc(n * 4)); MCK(d.koct.alloc(n * 4)); MCK(d.desc.alloc(db));
+    MCK(d.cell_start.alloc((ncell + 1) * 4)); MCK(d.cell_items.alloc(items.size() * 4));
+    MCK(d.winv.alloc(nc * 8)); MCK(d.hinv.alloc(nc * 8));
+    MCK(cudaMemcpyAsync(d.kx.p, kx.data(), n * 4, cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(d.ky.p, ky.data(), n * 4, cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(d.koct.p, koct.data(), n * 4, cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(d.desc.p, f->desc, db, cudaMemcpyHostToDevice, st));
+    if (f->dmask) {
+        MCK(d.dmask.alloc(db));
+        MCK(cudaMemcpyAsync(d.dmask.p, f->dmask, db, cudaMemcpyHostToDevice, st));
+    }
+    MCK(cudaMemcpyAsync(d.cell_start.p, start.data(), (ncell + 1) * 4, cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(d.cell_items.p, items.data(), items.size() * 4, cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(d.winv.p, winv.data(), nc * 8, cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(d.hinv.p, hinv.data(), nc * 8, cudaMemcpyHostToDevice, st));
+    MCK(cudaStreamSynchronize(st));    // host staging vectors die with this scope
+    d.view = WindowFrameDev{nc, n, f->dim, d.kx.as<float>(), d.ky.as<float>(), d.koct.as<int>(), d.desc.as<uint8_t>(),
+                            f->dmask ? d.dmask.as<uint8_t>() : nullptr, d.cell_start.as<int>(), d.cell_items.as<int>(),
+                            d.winv.as<double>(), d.hinv.as<double>()};
+    return MCS_OK;
+}
+
+// run the window-search kernel for host-side queries; grows max_cand until nothing overflows
+int window_search_host(const FrameDev& fd, const std::vector<mcs_window_query>& qs, const uint8_t* qdesc, const uint8_t* qmask,
+                       size_t qdesc_rows, int dim, std::vector<int>& cidx, std::vector<int>& cdist, std::vector<int>& ccount,
+                       int& max_cand, bool allow_grow, cudaStream_t st) {
+    const int nq = (int)qs.size();
+    ccount.assign(nq, 0);
+    if (nq == 0) return MCS_OK;
+    Dev dq, dqd, dqm;
+    MCK(dq.alloc(sizeof(mcs_window_query) * nq));
+    MCK(dqd.alloc(qdesc_rows * dim));
+    MCK(cudaMemcpyAsync(dq.p, qs.data(), sizeof(mcs_window_query) * nq, cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(dqd.p, qdesc, qdesc_rows * dim, cudaMemcpyHostToDevice, st));
+    const bool masked = qmask && fd.view.dmask;
+    if (masked) {
+        MCK(dqm.alloc(qdesc_rows * dim));
+        MCK(cudaMemcpyAsync(dqm.p, qmask, qdesc_rows * dim, cudaMemcpyHostToDevice, st));
+    }
+    for (;;) {
+        Dev di, dd, dc;
+        MCK(di.alloc((size_t)nq * max_cand * 4)); MCK(dd.alloc((size_t)nq * max_cand * 4)); MCK(dc.alloc((size_t)nq * 4));
+        MCK(launch_window_search(fd.view, dq.as<mcs_window_query>(), nq, dqd.as<uint8_t>(), masked ? dqm.as<uint8_t>() : nullptr,
+                                 max_cand, di.as<int>(), dd.as<int>(), dc.as<int>(), st));
+        cidx.resize((size_t)nq * max_cand); cdist.resize((size_t)nq * max_cand);
+        MCK(cudaMemcpyAsync(ccount.data(), dc.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+        MCK(cudaMemcpyAsync(cidx.data(), di.p, (size_t)nq * max_cand * 4, cudaMemcpyDeviceToHost, st));
+        MCK(cudaMemcpyAsync(cdist.data(), dd.p, (size_t)nq * max_cand * 4, cudaMemcpyDeviceToHost, st));
+        MCK(cudaStreamSynchronize(st));
+        const int mx = *std::max_element(ccount.begin(), ccount.end());
+        if (mx <= max_cand) return MCS_OK;
+        if (!allow_grow) return MCS_ERR_CAPACITY;
+        max_cand = (mx + 31) & ~31;
+    }
+}
+
+}  // namespace
+
+void mcs_set_error_(const std::string& msg);   // mcs_api.cu
+namespace { int mfail(int code, const std::string& msg) { mcs_set_error_(msg); return code; } }
+
+extern "C" {
+
+int mcs_descriptor_distance64(const uint64_t* a, const uint64_t* b, int32_t dim) {   // ref :2438-2450
+    uint64_t d = 0;
+    for (int i = 0; i < dim / 8; ++i) d += (uint64_t)__builtin_popcountll(a[i] ^ b[i]);
+    return (int)d;
+}
+
+int mcs_descriptor_distance64_masked(const uint64_t* a, const uint64_t* b, const uint64_t* ma, const uint64_t* mb,
+                                     int32_t dim) {   // ref :2452-2474
+    uint64_t d = 0;
+    for (int i = 0; i < dim / 8; ++i) {
+        const uint64_t x = a[i] ^ b[i];
+        d += (uint64_t)__builtin_popcountll(x & ma[i]);
+        d += (uint64_t)__builtin_popcountll(x & mb[i]);
+    }
+    return (int)(d / 2);
+}
+
+int mcs_hamming_topk_device(const uint8_t* q_dev, const uint8_t* qmask_dev, int32_t nq, const uint8_t* d_dev,
+                            const uint8_t* dmask_dev, int32_t nd, const uint8_t* db_skip_dev, int32_t dim, int32_t K,
+                            int32_t* topk_idx_dev, int32_t* topk_dist_dev, void* stream) {
+    if (!q_dev || !d_dev || !topk_idx_dev || !topk_dist_dev) return mfail(MCS_ERR_INVALID, "null argument");
+    if (nq < 0 || nd < 0 || K < 1 || K > 8) return mfail(MCS_ERR_INVALID, "bad sizes (K must be 1..8)");
+    if (dim != 16 && dim != 32 && dim != 64) return mfail(MCS_ERR_INVALID, "dim must be 16, 32 or 64");
+    MCK(launch_hamming_topk(q_dev, qmask_dev, nq, d_dev, dmask_dev, nd, db_skip_dev, dim, K, topk_idx_dev, topk_dist_dev,
+                            (cudaStream_t)stream));
+    return MCS_OK;
+}
+
+int mcs_hamming_topk(const uint8_t* q, const uint8_t* qmask, int32_t nq, const uint8_t* d, const uint8_t* dmask, int32_t nd,
+                     const uint8_t* db_skip, int32_t dim, int32_t K, int32_t* topk_idx, int32_t* topk_dist) {
+    if (!q || !d || !topk_idx || !topk_dist) return mfail(MCS_ERR_INVALID, "null argument");
+    if (nq <= 0) return MCS_OK;
+    const bool masked = qmask && dmask;
+    Dev dq, dqm, dd, ddm, ds, di, dt;
+    MCK(dq.alloc((size_t)nq * dim)); MCK(dd.alloc((size_t)nd * dim));
+    MCK(di.alloc((size_t)nq * K * 4)); MCK(dt.alloc((size_t)nq * K * 4));
+    MCK(cudaMemcpy(dq.p, q, (size_t)nq * dim, cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dd.p, d, (size_t)nd * dim, cudaMemcpyHostToDevice));
+    if (masked) {
+        MCK(dqm.alloc((size_t)nq * dim)); MCK(ddm.alloc((size_t)nd * dim));
+        MCK(cudaMemcpy(dqm.p, qmask, (size_t)nq * dim, cudaMemcpyHostToDevice));
+        MCK(cudaMemcpy(ddm.p, dmask, (size_t)nd * dim, cudaMemcpyHostToDevice));
+    }
+    if (db_skip) { MCK(ds.alloc(nd)); MCK(cudaMemcpy(ds.p, db_skip, nd, cudaMemcpyHostToDevice)); }
+    int rc = mcs_hamming_topk_device(dq.as<uint8_t>(), masked ? dqm.as<uint8_t>() : nullptr, nq, dd.as<uint8_t>(),
+                                     masked ? ddm.as<uint8_t>() : nullptr, nd, db_skip ? ds.as<uint8_t>() : nullptr, dim, K,
+                                     di.as<int>(), dt.as<int>(), nullptr);
+    if (rc) return rc;
+    MCK(cudaMemcpy(topk_idx, di.p, (size_t)nq * K * 4, cudaMemcpyDeviceToHost));
+    MCK(cudaMemcpy(topk_dist, dt.p, (size_t)nq * K * 4, cudaMemcpyDeviceToHost));
+    return MCS_OK;
+}
+
+int mcs_match_bruteforce(const uint8_t* q, const uint8_t* qmask, const uint8_t* valid1, int32_t nq, const uint8_t* d,
+                         const uint8_t* dmask, const uint8_t* valid2, int32_t nd, int32_t dim, int32_t th_low, double nnratio,
+                         int32_t* matches12, int32_t* nmatches) {
+    if (!q || !d || !matches12 || !nmatches) return mfail(MCS_ERR_INVALID, "null argument");
+    if (dim != 16 && dim != 32 && dim != 64) return mfail(MCS_ERR_INVALID, "dim must be 16, 32 or 64");
+    *nmatches = 0;
+    for (int i = 0; i < nq; ++i) matches12[i] = -1;
+    if (nq <= 0 || nd <= 0) return MCS_OK;
+    const bool masked = qmask && dmask;
+    constexpr int K = 4;
+    Dev dq, dqm, dd, ddm, ds, di, dt;
+    MCK(dq.alloc((size_t)nq * dim)); MCK(dd.alloc((size_t)nd * dim)); MCK(ds.alloc(nd));
+    MCK(di.alloc((size_t)nq * K * 4)); MCK(dt.alloc((size_t)nq * K * 4));
+    MCK(cudaMemcpy(dq.p, q, (size_t)nq * dim, cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dd.p, d, (size_t)nd * dim, cudaMemcpyHostToDevice));
+    if (masked) {
+        MCK(dqm.alloc((size_t)nq * dim)); MCK(ddm.alloc((size_t)nd * dim));
+        MCK(cudaMemcpy(dqm.p, qmask, (size_t)nq * dim, cudaMemcpyHostToDevice));
+        MCK(cudaMemcpy(ddm.p, dmask, (size_t)nd * dim, cudaMemcpyHostToDevice));
+    }
+    std::vector<uint8_t> skip(nd, 0), newly(nd, 0);
+    if (valid2) for (int i = 0; i < nd; ++i) skip[i] = valid2[i] ? 0 : 1;
+    std::vector<int> tidx((size_t)nq * K), tdist((size_t)nq * K);
+    int q0 = 0, nm = 0;
+    while (q0 < nq) {
+        // GPU: K best unmatched database entries for every remaining query (state at the start of the round)
+        MCK(cudaMemcpy(ds.p, skip.data(), nd, cudaMemcpyHostToDevice));
+        const int nrem = nq - q0;
+        int rc = mcs_hamming_topk_device(dq.as<uint8_t>() + (size_t)q0 * dim, masked ? dqm.as<uint8_t>() + (size_t)q0 * dim : nullptr,
+                                         nrem, dd.as<uint8_t>(), masked ? ddm.as<uint8_t>() : nullptr, nd, ds.as<uint8_t>(), dim, K,
+                                         di.as<int>(), dt.as<int>(), nullptr);
+        if (rc) return rc;
+        MCK(cudaMemcpy(tidx.data(), di.p, (size_t)nrem * K * 4, cudaMemcpyDeviceToHost));
+        MCK(cudaMemcpy(tdist.data(), dt.p, (size_t)nrem * K * 4, cudaMemcpyDeviceToHost));
+        std::fill(newly.begin(), newly.end(), 0);
+        // host: sequential replay (ref :899-961); a query whose list is exhausted by entries matched
+        // during this round starts the next round
+        int i1 = q0;
+        for (; i1 < nq; ++i1) {
+            if (valid1 && !valid1[i1]) continue;
+            const int* li = &tidx[(size_t)(i1 - q0) * K];
+            const int* ld = &tdist[(size_t)(i1 - q0) * K];
+            int best1 = INT_MAX, best2 = INT_MAX, bestIdx = -1, found = 0;
+            bool complete = false;      // list holds every unmatched database entry
+            for (int k = 0; k < K; ++k) {
+                if (li[k] < 0) { complete = true; break; }
+                if (newly[li[k]]) continue;
+                if (found == 0) { best1 = ld[k]; bestIdx = li[k]; }
+                else if (found == 1) best2 = ld[k];
+                ++found;
+                if (found == 2) break;
+            }
+            if (found < 2 && !complete) {
+                // second best unknown; irrelevant only if the best already fails the threshold
+                if (!(found == 1 && !(best1 < th_low))) break;
+            }
+            if (best1 < th_low && (double)best1 < nnratio * (double)best2) {
+                matches12[i1] = bestIdx;
+                skip[bestIdx] = 1; newly[bestIdx] = 1;
+                ++nm;
+            }
+        }
+        q0 = i1;
+    }
+    *nmatches = nm;
+    return MCS_OK;
+}
+
+int mcs_window_search(const mcs_frame_view* frame, const mcs_window_query* queries, int32_t nq, const uint8_t* qdesc,
+                      const uint8_t* qmask, int32_t max_cand, int32_t* cand_idx, int32_t* cand_dist, int32_t* cand_count) {
+    if (!frame || !queries || !qdesc || !cand_idx || !cand_dist || !cand_count || max_cand < 1)
+        return mfail(MCS_ERR_INVALID, "null argument");
+    if (nq <= 0) return MCS_OK;
+    FrameDev fd;
+    int rc = upload_frame(frame, fd, nullptr);
+    if (rc) return rc;
+    int rows = 0;
+    for (int i = 0; i < nq; ++i) {
+        if (queries[i].cam < 0 || queries[i].cam >= frame->n_cams) return mfail(MCS_ERR_INVALID, "query camera out of range");
+        rows = std::max(rows, queries[i].desc_index + 1);
+    }
+    std::vector<mcs_window_query> qs(queries, queries + nq);
+    std::vector<int> ci, cd, cc;
+    int mc = max_cand;
+    rc = window_search_host(fd, qs, qdesc, qmask, rows, frame->dim, ci, cd, cc, mc, false, nullptr);
+    if (rc != MCS_OK && rc != MCS_ERR_CAPACITY) return rc;
+    std::memcpy(cand_count, cc.data(), sizeof(int) * nq);
+    std::memcpy(cand_idx, ci.data(), sizeof(int) * (size_t)nq * max_cand);
+    std::memcpy(cand_dist, cd.data(), sizeof(int) * (size_t)nq * max_cand);
+    if (rc == MCS_ERR_CAPACITY) return mfail(MCS_ERR_CAPACITY, "max_cand too small for at least one query");
+    return MCS_OK;
+}
+
+int mcs_search_by_projection(const mcs_frame_view* f, const mcs_mappoint_view* mps, double th, double nnratio, int32_t th_high,
+                             int32_t having_masks, int32_t* frame_mp, int32_t* nmatches) {
+    if (!f || !mps || !frame_mp || !nmatches) return mfail(MCS_ERR_INVALID, "null argument");
+    if (having_masks && (!f->dmask || !mps->dmask)) return mfail(MCS_ERR_INVALID, "masks requested but not supplied");
+    *nmatches = 0;
+    // queries in the reference's visiting order: map point outer, camera inner (ref :74-98)
+    std::vector<mcs_window_query> qs;
+    const bool bFactor = th != 1.0;
+    for (int i = 0; i < mps->n_points; ++i) {
+        if (mps->bad && mps->bad[i]) continue;
+        for (int cam = 0; cam < f->n_cams; ++cam) {
+            const size_t k = (size_t)i * f->n_cams + cam;
+            if (!mps->in_view[k]) continue;
+            const int lvl = mps->level[k];
+            if (lvl < 0 || lvl >= f->n_levels) return mfail(MCS_ERR_INVALID, "map point scale level out of range");
+            double r = mps->view_cos[k] > 0.998 ? 2.5 : 4.0;   // RadiusByViewingCos (ref :169-175)
+            if (bFactor) r *= th;
+            mcs_window_query q;
+            q.cam = cam; q.min_level = lvl - 1; q.max_level = lvl; q.desc_index = i;
+            q.x = mps->proj_x[k]; q.y = mps->proj_y[k]; q.r = r * f->scale_factors[lvl];
+            qs.push_back(q);
+        }
+    }
+    if (qs.empty()) return MCS_OK;
+    FrameDev fd;
+    int rc = upload_frame(f, fd, nullptr);
+    if (rc) return rc;
+    std::vector<int> ci, cd, cc;
+    int mc = 32;
+    rc = window_search_host(fd, qs, mps->desc, having_masks ? mps->dmask : nullptr, mps->n_points, f->dim, ci, cd, cc, mc, true, nullptr);
+    if (rc) return rc;
+    int nm = 0;
+    for (size_t qi = 0; qi < qs.size(); ++qi) {   // greedy replay (ref :100-164)
+        const int n = cc[qi];
+        if (n == 0) continue;
+        int bestDist = INT_MAX, bestLevel = -1, bestDist2 = INT_MAX, bestLevel2 = -1, bestIdx = -1;
+        for (int k = 0; k < n; ++k) {
+            const int idx = ci[qi * mc + k];
+            if (frame_mp[idx] >= 0) continue;
+            const int dist = cd[qi * mc + k];
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel;
+                bestLevel = f->keys[idx].octave; bestIdx = idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = f->keys[idx].octave; bestDist2 = dist;
+            }
+        }
+        if (bestDist <= th_high) {
+            if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+            frame_mp[bestIdx] = qs[qi].desc_index;
+            ++nm;
+        }
+    }
+    *nmatches = nm;
+    return MCS_OK;
+}
+
+int mcs_search_for_initialization(const mcs_frame_view* f1, const mcs_frame_view* f2, double* prev_matched, int32_t window_size,
+                                  double nnratio, int32_t th_low, int32_t having_masks, int32_t* matches12, int32_t* nmatches) {
+    if (!f1 || !f2 || !prev_matched || !matches12 || !nmatches) return mfail(MCS_ERR_INVALID, "null argument");
+    if (f1->dim != f2->dim) return mfail(MCS_ERR_INVALID, "descriptor sizes differ");
+    if (having_masks && (!f1->dmask || !f2->dmask)) return mfail(MCS_ERR_INVALID, "masks requested but not supplied");
+    *nmatches = 0;
+    const int n1 = f1->n_keys;
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    if (n1 == 0 || f2->n_keys == 0) return MCS_OK;
+    std::vector<mcs_window_query> qs(n1);
+    for (int i1 = 0; i1 < n1; ++i1) {
+        mcs_window_query& q = qs[i1];
+        q.cam = f1->key_cam[i1];
+        if (q.cam < 0 || q.cam >= f2->n_cams) return mfail(MCS_ERR_INVALID, "key_cam out of range");
+        q.min_level = q.max_level = f1->keys[i1].octave;
+        q.desc_index = i1;
+        q.x = prev_matched[2 * i1]; q.y = prev_matched[2 * i1 + 1]; q.r = (double)window_size;
+    }
+    FrameDev fd;
+    int rc = upload_frame(f2, fd, nullptr);
+    if (rc) return rc;
+    std::vector<int> ci, cd, cc;
+    int mc = 64;
+    rc = window_search_host(fd, qs, f1->desc, having_masks ? f1->dmask : nullptr, n1, f1->dim, ci, cd, cc, mc, true, nullptr);
+    if (rc) return rc;
+    int nm = 0;
+    std::vector<int> matchedDist(f2->n_keys, INT_MAX), matches21(f2->n_keys, -1);
+    for (int i1 = 0; i1 < n1; ++i1) {            // ref :599-682
+        const int n = cc[i1];
+        if (n == 0) continue;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int k = 0; k < n; ++k) {
+            const int i2 = ci[(size_t)i1 * mc + k], dist = cd[(size_t)i1 * mc + k];
+            if (matchedDist[i2] <= dist) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist <= th_low && bestDist < (double)bestDist2 * nnratio) {
+            if (matches21[bestIdx2] >= 0) { matches12[matches21[bestIdx2]] = -1; --nm; }
+            matches12[i1] = bestIdx2;
+            matches21[bestIdx2] = i1;
+            matchedDist[bestIdx2] = bestDist;
+            ++nm;
+        }
+    }
+    for (int i1 = 0; i1 < n1; ++i1)              // ref :717-720
+        if (matches12[i1] >= 0) {
+            prev_matched[2 * i1] = f2->keys[matches12[i1]].x;
+            prev_matched[2 * i1 + 1] = f2->keys[matches12[i1]].y;
+        }
+    *nmatches = nm;
+    return MCS_OK;
+}
+
+}  // extern "C"

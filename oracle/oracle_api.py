@@ -116,3 +116,64 @@ def octree(xyr, minX, maxX, minY, maxY, N):
     out = np.zeros((max(len(xyr), 1), 3), np.float32)
     n = lib().mcso_octree(_p(xyr), len(xyr), minX, maxX, minY, maxY, N, _p(out), out.shape[0])
     return out[:n].copy()
+
+
+# ---- matcher oracles (take multicol_slam_b200.api.Frame / MapPoints, which are plain array holders) ----
+def match_bruteforce(d1, d2, th_low, nnratio, m1=None, m2=None, valid1=None, valid2=None):
+    d1 = np.ascontiguousarray(d1, np.uint8)
+    d2 = np.ascontiguousarray(d2, np.uint8)
+    m1 = None if m1 is None else np.ascontiguousarray(m1, np.uint8)
+    m2 = None if m2 is None else np.ascontiguousarray(m2, np.uint8)
+    valid1 = None if valid1 is None else np.ascontiguousarray(valid1, np.uint8)
+    valid2 = None if valid2 is None else np.ascontiguousarray(valid2, np.uint8)
+    m12 = np.zeros(len(d1), np.int32)
+    n = C.c_int(0)
+    lib().mcso_match_bruteforce(_p(d1), _p(m1), _p(valid1), len(d1), _p(d2), _p(m2), _p(valid2), len(d2), d1.shape[1],
+                                th_low, C.c_double(nnratio), _p(m12), C.byref(n))
+    return n.value, m12
+
+
+def window_search(frame, queries, qdesc, qmask=None, max_cand=64):
+    from multicol_slam_b200.ctypes_defs import WINDOW_QUERY_DTYPE
+    queries = np.ascontiguousarray(queries, WINDOW_QUERY_DTYPE)
+    qdesc = np.ascontiguousarray(qdesc, np.uint8)
+    qmask = None if qmask is None else np.ascontiguousarray(qmask, np.uint8)
+    nq = len(queries)
+    idx = np.zeros((nq, max_cand), np.int32)
+    dist = np.zeros((nq, max_cand), np.int32)
+    cnt = np.zeros(nq, np.int32)
+    fv = frame.view()
+    rc = lib().mcso_window_search(C.byref(fv), _p(queries), nq, _p(qdesc), _p(qmask), max_cand, _p(idx), _p(dist), _p(cnt))
+    return idx, dist, cnt, rc
+
+
+def search_by_projection(frame, mps, th, nnratio, th_high, having_masks, frame_mp=None):
+    if frame_mp is None:
+        frame_mp = np.full(len(frame.keys), -1, np.int32)
+    frame_mp = np.ascontiguousarray(frame_mp, np.int32).copy()
+    n = C.c_int(0)
+    fv, mv = frame.view(), mps.view()
+    lib().mcso_search_by_projection(C.byref(fv), C.byref(mv), C.c_double(th), C.c_double(nnratio), th_high, int(having_masks),
+                                    _p(frame_mp), C.byref(n))
+    return n.value, frame_mp
+
+
+def search_for_initialization(f1, f2, prev_matched, window, nnratio, th_low, having_masks):
+    prev = np.ascontiguousarray(prev_matched, np.float64).copy()
+    m12 = np.zeros(len(f1.keys), np.int32)
+    n = C.c_int(0)
+    v1, v2 = f1.view(), f2.view()
+    lib().mcso_search_for_initialization(C.byref(v1), C.byref(v2), _p(prev), window, C.c_double(nnratio), th_low,
+                                         int(having_masks), _p(m12), C.byref(n))
+    return n.value, m12, prev
+
+
+def distance64(a, b, dim=32):
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    return lib().mcso_descriptor_distance64(_p(a), _p(b), dim)
+
+
+def distance64_masked(a, b, ma, mb, dim=32):
+    a, b, ma, mb = (np.ascontiguousarray(v, np.uint8) for v in (a, b, ma, mb))
+    return lib().mcso_descriptor_distance64_masked(_p(a), _p(b), _p(ma), _p(mb), dim)

@@ -1,0 +1,180 @@
+"""GPU parity of the matcher half: Hamming top-K / brute force (M2), grid window search (G1) and the
+SearchByProjection / SearchForInitialization replays (M1, M3) vs the CPU oracle.  Integer work: bit-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def popcount_dist(q, d):
+    x = np.bitwise_xor(q[:, None, :], d[None, :, :])
+    return np.unpackbits(x, axis=2).sum(axis=2).astype(np.int32)
+
+
+def rand_desc(rng, n, dim=32):
+    return rng.integers(0, 256, (n, dim)).astype(np.uint8)
+
+
+@pytest.mark.parametrize("dim", [16, 32, 64])
+@pytest.mark.parametrize("masked", [False, True])
+def test_topk_vs_numpy(api, dim, masked):
+    rng = np.random.default_rng(dim + masked)
+    q, d = rand_desc(rng, 300, dim), rand_desc(rng, 1777, dim)
+    d[5] = d[900] = q[7]                        # exact duplicates: ties must keep the lower index
+    K = 4
+    if masked:
+        qm, dm = rand_desc(rng, 300, dim) | rand_desc(rng, 300, dim), rand_desc(rng, 1777, dim) | rand_desc(rng, 1777, dim)
+        x = np.bitwise_xor(q[:, None, :], d[None, :, :])
+        dist = (np.unpackbits(x & qm[:, None, :], axis=2).sum(axis=2) + np.unpackbits(x & dm[None, :, :], axis=2).sum(axis=2)) // 2
+        idx, dd = api.hamming_topk(q, d, K, qm, dm)
+    else:
+        dist = popcount_dist(q, d)
+        idx, dd = api.hamming_topk(q, d, K)
+    order = np.lexsort((np.broadcast_to(np.arange(d.shape[0]), dist.shape), dist), axis=1)[:, :K]
+    assert np.array_equal(idx, order.astype(np.int32))
+    assert np.array_equal(dd, np.take_along_axis(dist, order, axis=1).astype(np.int32))
+    if not masked:
+        assert idx[7, 0] == 5 and idx[7, 1] == 900 and dd[7, 0] == 0
+
+
+def test_topk_skip_and_small(api):
+    rng = np.random.default_rng(3)
+    q, d = rand_desc(rng, 10), rand_desc(rng, 3)
+    skip = np.array([0, 1, 0], np.uint8)
+    idx, dd = api.hamming_topk(q, d, 4, db_skip=skip)
+    dist = popcount_dist(q, d)
+    for i in range(10):
+        cand = sorted([(dist[i, j], j) for j in (0, 2)])
+        assert list(idx[i, :2]) == [c[1] for c in cand] and list(idx[i, 2:]) == [-1, -1]
+        assert list(dd[i, :2]) == [c[0] for c in cand]
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_bruteforce_search_by_bow(api, oa, masked):
+    """SearchByBoW(KF,KF) semantics incl. the greedy one-use rule under heavy contention."""
+    rng = np.random.default_rng(11)
+    nd, nq = 3000, 1200
+    d = rand_desc(rng, nd)
+    # many queries planted on few database entries -> contention for the same best match
+    target = rng.integers(0, 40, nq)
+    q = d[target].copy()
+    flips = rng.integers(0, 30, nq)
+    for i in range(nq):
+        bits = rng.choice(256, flips[i], replace=False)
+        for b in bits:
+            q[i, b // 8] ^= 1 << (b % 8)
+    qm = dm = None
+    if masked:
+        qm = (rng.random((nq, 256)) < 0.85)
+        dm = (rng.random((nd, 256)) < 0.85)
+        qm, dm = np.packbits(qm, axis=1, bitorder="little"), np.packbits(dm, axis=1, bitorder="little")
+    v1 = (rng.random(nq) < 0.9).astype(np.uint8)
+    v2 = (rng.random(nd) < 0.95).astype(np.uint8)
+    matcher = api.cORBmatcher(0.9, False, 32, masked)
+    n, m12 = matcher.SearchByBoW(q, d, qm, dm, v1, v2)
+    on, om12 = oa.match_bruteforce(q, d, matcher.TH_LOW_, 0.9, qm, dm, v1, v2)
+    assert n == on and np.array_equal(m12, om12)
+    assert n > 20
+
+
+def make_frames(api, oa, cams, seeds, nf=600, masks=True):
+    from multicol_slam_b200 import synth
+    ex = api.mdBRIEFextractorOct(nfeatures=nf, do_dBrief=True, learnMasks=masks)
+    per = []
+    for c, s in enumerate(seeds):
+        per.append(ex(synth.frame(cams[c], s), synth.mirror_mask(cams[c]), cams[c]))
+    sf = [ex.info.scale_factor[l] for l in range(8)]
+    return api.Frame.from_cameras(per, [(754, 480)] * len(seeds), sf)
+
+
+def test_window_search_candidates(api, oa, cams):
+    from multicol_slam_b200.ctypes_defs import WINDOW_QUERY_DTYPE
+    F = make_frames(api, oa, cams, [1, 2, 3])
+    rng = np.random.default_rng(0)
+    nq = 700
+    qs = np.zeros(nq, WINDOW_QUERY_DTYPE)
+    qs["cam"] = rng.integers(0, 3, nq)
+    lv = rng.integers(0, 8, nq)
+    kind = rng.integers(0, 3, nq)
+    qs["min_level"] = np.where(kind == 0, -1, np.where(kind == 1, lv, lv - 1))
+    qs["max_level"] = np.where(kind == 0, -1, lv)
+    qs["desc_index"] = rng.integers(0, len(F.keys), nq)
+    qs["x"] = rng.uniform(-30, 790, nq)
+    qs["y"] = rng.uniform(-30, 510, nq)
+    qs["r"] = rng.uniform(1, 60, nq)
+    gi, gd, gc, rc = api.window_search(F, qs, F.desc, F.dmask, max_cand=512)
+    oi, od, oc, orc = oa.window_search(F, qs, F.desc, F.dmask, max_cand=512)
+    assert rc == 0 and orc == 0
+    assert np.array_equal(gc, oc)
+    for i in range(nq):
+        assert np.array_equal(gi[i, :gc[i]], oi[i, :oc[i]]) and np.array_equal(gd[i, :gc[i]], od[i, :oc[i]])
+    assert gc.max() > 20
+    # overflow is reported, true counts are still returned
+    gi2, gd2, gc2, rc2 = api.window_search(F, qs, F.desc, F.dmask, max_cand=4)
+    assert rc2 == api.MCS_ERR_CAPACITY and np.array_equal(gc2, oc)
+
+
+@pytest.mark.parametrize("masks", [False, True])
+def test_search_by_projection(api, oa, cams, masks):
+    F = make_frames(api, oa, cams, [4, 5, 6], masks=masks)
+    rng = np.random.default_rng(2)
+    nmp, nc = 4000, 3
+    src = rng.integers(0, len(F.keys), nmp)
+    desc = F.desc[src].copy()
+    for i in range(nmp):
+        for b in rng.choice(256, rng.integers(0, 41), replace=False):
+            desc[i, b // 8] ^= 1 << (b % 8)
+    dm = F.dmask[src].copy() if masks else None
+    in_view = np.zeros((nmp, nc), np.uint8)
+    level = np.zeros((nmp, nc), np.int32)
+    px = np.zeros((nmp, nc)); py = np.zeros((nmp, nc)); vc = np.zeros((nmp, nc))
+    for i in range(nmp):
+        c = F.key_cam[src[i]]
+        in_view[i, c] = 1
+        level[i, c] = min(7, max(0, F.keys[src[i]]["octave"] + rng.integers(-1, 2)))
+        px[i, c] = F.keys[src[i]]["x"] + rng.normal(0, 2)
+        py[i, c] = F.keys[src[i]]["y"] + rng.normal(0, 2)
+        vc[i, c] = rng.uniform(0.9, 1.0)
+        if rng.random() < 0.2:      # also visible in a second camera
+            c2 = (c + 1) % nc
+            in_view[i, c2] = 1; level[i, c2] = rng.integers(0, 8)
+            px[i, c2] = rng.uniform(0, 754); py[i, c2] = rng.uniform(0, 480); vc[i, c2] = rng.uniform(0.9, 1.0)
+    bad = (rng.random(nmp) < 0.05).astype(np.uint8)
+    mps = api.MapPoints(bad, in_view, level, px, py, vc, desc, dm)
+    matcher = api.cORBmatcher(0.8, False, 32, masks)
+    n, fmp = matcher.SearchByProjection(F, mps, 3.0)
+    on, ofmp = oa.search_by_projection(F, mps, 3.0, 0.8, matcher.TH_HIGH_, masks)
+    assert n == on and np.array_equal(fmp, ofmp)
+    assert n > 500
+    # pre-assigned keypoints are skipped (greedy rule, ref :121)
+    pre = np.full(len(F.keys), -1, np.int32)
+    pre[::3] = 0
+    n2, fmp2 = matcher.SearchByProjection(F, mps, 1.0, pre.copy())
+    on2, ofmp2 = oa.search_by_projection(F, mps, 1.0, 0.8, matcher.TH_HIGH_, masks, pre.copy())
+    assert n2 == on2 and np.array_equal(fmp2, ofmp2)
+
+
+@pytest.mark.parametrize("masks", [False, True])
+def test_search_for_initialization(api, oa, cams, masks):
+    from multicol_slam_b200 import synth
+    ex = api.mdBRIEFextractorOct(nfeatures=800, fastThreshold=5, do_dBrief=True, learnMasks=masks)
+    sf = [ex.info.scale_factor[l] for l in range(8)]
+    fr = []
+    for t in range(2):
+        per = []
+        for c in range(3):
+            stream = synth.texture_stream(cams[c], 2, seed=40 + c)
+            per.append(ex(stream[t], synth.mirror_mask(cams[c]), cams[c]))
+        fr.append(api.Frame.from_cameras(per, [(754, 480)] * 3, sf))
+    F1, F2 = fr
+    prev = np.stack([F1.keys["x"], F1.keys["y"]], axis=1).astype(np.float64)
+    matcher = api.cORBmatcher(0.9, False, 32, masks)
+    p1 = prev.copy()
+    n, m12 = matcher.SearchForInitialization(F1, F2, p1, 50)
+    on, om12, oprev = oa.search_for_initialization(F1, F2, prev, 50, 0.9, matcher.TH_LOW_, masks)
+    assert n == on and np.array_equal(m12, om12) and np.array_equal(p1, oprev)
+    assert n > 200
+    # matched keypoints moved by the stream's (3,2) px/frame motion
+    ok = m12 >= 0
+    dx = F1.keys["x"][ok] - F2.keys["x"][m12[ok]]
+    assert np.median(np.abs(dx - 3.0)) < 1.5
