@@ -56,22 +56,26 @@ __device__ __forceinline__ int fast_score(const uint8_t* p, int t) {
         dm |= (uint32_t)(r[k] < lo) << k;
     }
     if (!has_arc9(bm) && !has_arc9(dm)) return 0;
-    int d[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) d[k] = v - r[k];
-    int mn2[16], mx2[16], mn4[16], mx4[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) { mn2[k] = min(d[k], d[(k + 1) & 15]); mx2[k] = max(d[k], d[(k + 1) & 15]); }
-#pragma unroll
-    for (int k = 0; k < 16; ++k) { mn4[k] = min(mn2[k], mn2[(k + 2) & 15]); mx4[k] = max(mx2[k], mx2[(k + 2) & 15]); }
-    int best = t;
+    // Packed s16x2 lanes: lo = v - r (dark margin), hi = r - v (bright margin); one sliding-min tree over
+    // the circular ring gives, per start k, the minimum over the 9-arc in both lanes (VIMNMX.S16x2).
+    // NOTE: the scalar form max(best, max(mn9, -mx9)) is MISCOMPILED by ptxas 12.9 -O1+ for sm_100a
+    // (the negation is dropped when folded into VIMNMX3) -- see tools/ptxas_vimnmx3_repro.cu.
+    unsigned q[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        const int mn9 = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);
-        const int mx9 = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);
-        best = max(best, max(mn9, -mx9));
+        const int d = v - r[k];
+        q[k] = ((unsigned)d & 0xFFFFu) | ((unsigned)(-d) << 16);
     }
-    return best - 1;
+    unsigned q2[16], q4[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) q2[k] = __vmins2(q[k], q[(k + 1) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) q4[k] = __vmins2(q2[k], q2[(k + 2) & 15]);
+    unsigned m = __vmins2(__vmins2(q4[0], q4[4]), q[8]);
+#pragma unroll
+    for (int k = 1; k < 16; ++k) m = __vmaxs2(m, __vmins2(__vmins2(q4[k], q4[(k + 4) & 15]), q[(k + 8) & 15]));
+    const int dark = (int)(short)(m & 0xFFFFu), bright = (int)(short)(m >> 16);
+    return max(t, max(dark, bright)) - 1;
 }
 
 __global__ void __launch_bounds__(256)
