@@ -143,6 +143,30 @@ int  mcs_extract_batch_device(mcs_extractor* ex, int32_t n_images,
                               mcs_keypoint* kps_dev, uint8_t* desc_dev, uint8_t* dmask_dev,
                               int32_t* counts_dev, int32_t capacity, void* stream);
 
+/* Stream form of the whole path: n_frames multi-camera frames (frame-major: image i = frame i/n_cams,
+ * camera i%n_cams) are extracted, and every image is brute-force matched (bit-level Hamming, masked form when
+ * learn_masks is set) against the same camera of the previous frame: K best (index, distance) per keypoint
+ * slot, (-1, INT_MAX) where none / for frame 0.  match_idx/match_dist: [n_frames*n_cams*capacity*K].
+ * Host buffers; H2D, all kernels and D2H happen inside the call. */
+int  mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams,
+                              const uint8_t* images, int32_t width, int32_t height, int32_t stride,
+                              const uint8_t* masks, const mcs_ocam* cams,
+                              mcs_keypoint* kps_out, uint8_t* desc_out, uint8_t* dmask_out,
+                              int32_t* counts_out, int32_t capacity,
+                              int32_t K, int32_t* match_idx_out, int32_t* match_dist_out);
+
+/* Device-resident matching half of the stream form (descriptor slots as written by
+ * mcs_extract_batch_device); asynchronous on `stream`. dmask_dev may be NULL (unmasked distance). */
+int  mcs_match_stream_device(const uint8_t* desc_dev, const uint8_t* dmask_dev, const int32_t* counts_dev,
+                             int32_t n_frames, int32_t n_cams, int32_t capacity, int32_t dim, int32_t K,
+                             int32_t* match_idx_dev, int32_t* match_dist_dev, void* stream);
+
+/* Per-stage device timings of the LAST extract call, measured with CUDA events on the launching stream when
+ * profiling is enabled: ms[0] = K1 (pyramid+blur+FAST, all levels), ms[1] = K2 octree, ms[2] = K3 describe.
+ * mcs_extractor_set_profiling(ex, 1) turns the event recording on (off by default). */
+int  mcs_extractor_set_profiling(mcs_extractor* ex, int32_t enable);
+int  mcs_extractor_get_timings(mcs_extractor* ex, float* ms3);
+
 /* Introspection for the parity tests: copy intermediate device buffers of the LAST extract call
  * (image 0 of the batch unless image_index is given) back to the host.
  *   what: 0 = unblurred level (w*h bytes), 1 = blurred level, 2 = mask level,

@@ -175,6 +175,33 @@ class mdBRIEFextractorOct:
                                               C.c_void_p(out["dmask"].data_ptr()), C.c_void_p(out["counts"].data_ptr()), cap, st))
         return out
 
+    def extract_match_stream(self, images, masks, cams, K=2, out=None):
+        """images [F,C,H,W] u8 host (frame-major).  Extract every image and brute-force match each (frame,cam)
+        against (frame-1,cam).  Returns dict(kps [F*C,cap], desc, dmask, counts, match_idx [F*C,cap,K], match_dist).
+        `out` may hold preallocated (e.g. pinned) numpy arrays with the same keys."""
+        images = np.ascontiguousarray(images, np.uint8)
+        masks = np.ascontiguousarray(masks, np.uint8)
+        F, Cn, H, W = images.shape
+        cap, ds, B = self.info.capacity, self.info.desc_size, F * Cn
+        ocs = (Ocam * len(cams))(*[as_ocam(c) for c in cams])
+        if out is None:
+            out = dict(kps=np.zeros((B, cap), KEYPOINT_DTYPE), desc=np.zeros((B, cap, ds), np.uint8),
+                       dmask=np.zeros((B, cap, ds), np.uint8), counts=np.zeros(B, np.int32),
+                       match_idx=np.zeros((B, cap, K), np.int32), match_dist=np.zeros((B, cap, K), np.int32))
+        _check(lib().mcs_extract_match_stream(self._h, F, Cn, _p(images), W, H, W, _p(masks), ocs, _p(out["kps"]),
+                                              _p(out["desc"]), _p(out["dmask"]), _p(out["counts"]), cap, K,
+                                              _p(out["match_idx"]), _p(out["match_dist"])))
+        return out
+
+    def set_profiling(self, enable=True):
+        _check(lib().mcs_extractor_set_profiling(self._h, int(enable)))
+
+    def get_timings(self):
+        """(K1 pyramid+blur+FAST all levels, K2 octree, K3 describe) of the last extract call, milliseconds."""
+        ms = (C.c_float * 3)()
+        _check(lib().mcs_extractor_get_timings(self._h, ms))
+        return tuple(ms)
+
     def debug_read(self, level, what, image_index=0):
         w, h = C.c_int32(0), C.c_int32(0)
         buf = np.zeros(1 << 24, np.uint8)
@@ -220,6 +247,20 @@ def hamming_topk_device(q_t, d_t, K=2, qmask_t=None, dmask_t=None, skip_t=None, 
     st = C.c_void_p(stream.cuda_stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream)
     _check(lib().mcs_hamming_topk_device(ptr(q_t), ptr(qmask_t), nq, ptr(d_t), ptr(dmask_t), d_t.shape[0], ptr(skip_t), dim, K,
                                          ptr(out[0]), ptr(out[1]), st))
+    return out
+
+
+def match_stream_device(desc_t, dmask_t, counts_t, n_frames, n_cams, K=2, out=None, stream=None):
+    """torch CUDA tensors: desc [F*C,cap,dim] u8, dmask same or None, counts [F*C] i32 -> (idx, dist) [F*C,cap,K] i32."""
+    import torch
+    B, cap, dim = desc_t.shape
+    dev = desc_t.device
+    if out is None:
+        out = (torch.empty((B, cap, K), dtype=torch.int32, device=dev), torch.empty((B, cap, K), dtype=torch.int32, device=dev))
+    ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+    st = C.c_void_p(stream.cuda_stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream)
+    _check(lib().mcs_match_stream_device(ptr(desc_t), ptr(dmask_t), ptr(counts_t), n_frames, n_cams, cap, dim, K, ptr(out[0]),
+                                         ptr(out[1]), st))
     return out
 
 

@@ -154,6 +154,109 @@ cudaError_t launch_hamming_topk(const uint8_t* q, const uint8_t* qmask, int nq, 
     return cudaGetLastError();
 }
 
+// Stream matching: image i = (frame f, camera c) is matched against image i - n_cams = (f-1, c); both live in
+// fixed-size slots of `capacity` descriptors, the valid counts are read on the device (no host sync).
+// One thread owns one query; the (<= capacity) database descriptors of the previous frame are staged tile by
+// tile in shared memory.  Output: K best (index, distance) per query slot, (-1, INT_MAX) where none.
+template <int WORDS, bool MASKED>
+__global__ void __launch_bounds__(kTopkThreads)
+hamming_stream_kernel(const uint32_t* __restrict__ desc, const uint32_t* __restrict__ dmask, const int* __restrict__ counts,
+                      const int n_cams, const int capacity, const int K, int* __restrict__ out_idx, int* __restrict__ out_dist) {
+    __shared__ __align__(16) uint32_t s_d[kDbTile * WORDS];
+    __shared__ __align__(16) uint32_t s_m[MASKED ? kDbTile * WORDS : 4];
+    const int img = blockIdx.y;
+    const int qi = blockIdx.x * kTopkThreads + threadIdx.x;
+    const bool has_prev = img >= n_cams;                 // frame 0 has no predecessor
+    const int nq = has_prev ? min(counts[img], capacity) : 0;
+    const int nd = has_prev ? min(counts[img - n_cams], capacity) : 0;
+    if ((int)(blockIdx.x * kTopkThreads) >= nq) {        // nothing to match in this block: mark the slots empty
+        if (qi < capacity)
+            for (int k = 0; k < K; ++k) {
+                out_idx[((size_t)img * capacity + qi) * K + k] = -1;
+                out_dist[((size_t)img * capacity + qi) * K + k] = 0x7FFFFFFF;
+            }
+        return;
+    }
+    const bool active = qi < nq;
+    const uint32_t* q = desc + ((size_t)img * capacity + qi) * WORDS;
+    const uint32_t* qmk = MASKED ? dmask + ((size_t)img * capacity + qi) * WORDS : nullptr;
+    uint32_t qw[WORDS], qm[MASKED ? WORDS : 1];
+#pragma unroll
+    for (int k = 0; k < WORDS; ++k) {
+        qw[k] = active ? q[k] : 0u;
+        if (MASKED) qm[k] = active ? qmk[k] : 0u;
+    }
+    unsigned long long best[kTopKMax];
+#pragma unroll
+    for (int k = 0; k < kTopKMax; ++k) best[k] = kNoKey;
+    unsigned worst = 0xFFFFFFFFu;
+    const uint32_t* dbase = desc + (size_t)(img - n_cams) * capacity * WORDS;
+    const uint32_t* mbase = MASKED ? dmask + (size_t)(img - n_cams) * capacity * WORDS : nullptr;
+    for (int t0 = 0; t0 < nd; t0 += kDbTile) {
+        const int tn = min(kDbTile, nd - t0);
+        __syncthreads();
+        {
+            const uint4* src = (const uint4*)(dbase + (size_t)t0 * WORDS);
+            uint4* dst = (uint4*)s_d;
+            for (int i = threadIdx.x; i < tn * WORDS / 4; i += kTopkThreads) dst[i] = src[i];
+            if (MASKED) {
+                const uint4* msrc = (const uint4*)(mbase + (size_t)t0 * WORDS);
+                uint4* mdst = (uint4*)s_m;
+                for (int i = threadIdx.x; i < tn * WORDS / 4; i += kTopkThreads) mdst[i] = msrc[i];
+            }
+        }
+        __syncthreads();
+        for (int j = 0; j < tn; ++j) {
+            unsigned dist = 0;
+            if (MASKED) {
+#pragma unroll
+                for (int k = 0; k < WORDS; ++k) {
+                    const uint32_t x = qw[k] ^ s_d[j * WORDS + k];
+                    dist += __popc(x & qm[k]) + __popc(x & s_m[j * WORDS + k]);
+                }
+                dist >>= 1;
+            } else {
+#pragma unroll
+                for (int k = 0; k < WORDS; ++k) dist += __popc(qw[k] ^ s_d[j * WORDS + k]);
+            }
+            if (dist < worst) {
+                unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)(t0 + j);
+#pragma unroll
+                for (int k = 0; k < kTopKMax; ++k) {
+                    if (k < K && key < best[k]) { const unsigned long long t = best[k]; best[k] = key; key = t; }
+                }
+                unsigned long long w = best[0];
+#pragma unroll
+                for (int k = 1; k < kTopKMax; ++k) if (k < K) w = best[k];
+                worst = (w == kNoKey) ? 0xFFFFFFFFu : (unsigned)(w >> 32);
+            }
+        }
+    }
+    if (qi < capacity) {
+        int* oi = out_idx + ((size_t)img * capacity + qi) * K;
+        int* od = out_dist + ((size_t)img * capacity + qi) * K;
+        for (int k = 0; k < K; ++k) {
+            const bool none = !active || best[k] == kNoKey;
+            oi[k] = none ? -1 : (int)(best[k] & 0xFFFFFFFFull);
+            od[k] = none ? 0x7FFFFFFF : (int)(best[k] >> 32);
+        }
+    }
+}
+
+cudaError_t launch_hamming_stream(const uint8_t* desc, const uint8_t* dmask, const int* counts, int n_frames, int n_cams,
+                                  int capacity, int dim, int K, int* out_idx, int* out_dist, cudaStream_t st) {
+    if (K < 1 || K > kTopKMax || (dim != 16 && dim != 32 && dim != 64)) return cudaErrorInvalidValue;
+    dim3 grid((capacity + kTopkThreads - 1) / kTopkThreads, n_frames * n_cams);
+    const bool masked = dmask != nullptr;
+#define MCS_HS(W, M) hamming_stream_kernel<W, M><<<grid, kTopkThreads, 0, st>>>((const uint32_t*)desc, (const uint32_t*)dmask, counts, \
+        n_cams, capacity, K, out_idx, out_dist)
+    if (dim == 16) { if (masked) MCS_HS(4, true); else MCS_HS(4, false); }
+    else if (dim == 32) { if (masked) MCS_HS(8, true); else MCS_HS(8, false); }
+    else { if (masked) MCS_HS(16, true); else MCS_HS(16, false); }
+#undef MCS_HS
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // window search
 // ------------------------------------------------------------------------------------------------

@@ -90,6 +90,9 @@ struct mcs_extractor {
     DevBuf<mcs_keypoint> kps;
     DevBuf<uint8_t> desc, dmask;
     int last_n_images = 0;
+    DevBuf<int> match_idx, match_dist;
+    bool profiling = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -246,6 +249,7 @@ int run_pipeline(mcs_extractor* ex, int n_images, const uint8_t* images_dev, int
     CK(cudaMemcpyAsync(ex->cam_of_image.p, cam_of_image, sizeof(int) * n_images, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(ex->raw_count.p, 0, sizeof(int) * n_images * G.nlevels, st));
     CK(cudaMemsetAsync(ex->status.p, 0, sizeof(int), st));
+    if (ex->profiling) CK(cudaEventRecord(ex->ev[0], st));
     for (int l = 0; l < G.nlevels; ++l) {
         const uint8_t* src = l ? ex->lvl[l - 1].p : images_dev;
         const size_t src_bytes = l ? G.lv[l - 1].img_bytes : (size_t)stride * H;
@@ -253,14 +257,17 @@ int run_pipeline(mcs_extractor* ex, int n_images, const uint8_t* images_dev, int
                         ex->cam_of_image.p, ex->raw.p, ex->raw_count.p, st);
     }
     CK(cudaGetLastError());
+    if (ex->profiling) CK(cudaEventRecord(ex->ev[1], st));
     CK(launch_octree(G, ex->G_dev.p, n_images, ex->raw.p, ex->raw_count.p, ex->node_of.p, ex->sel_xys.p, ex->sel_count.p,
                      ex->status.p, st));
     CK(cudaGetLastError());
+    if (ex->profiling) CK(cudaEventRecord(ex->ev[2], st));
     DescribeArgs a;
     for (int l = 0; l < kMaxLevels; ++l) { a.lvl[l] = ex->lvl[l].p; a.blur[l] = ex->blur[l].p; }
     launch_describe(G, ex->G_dev.p, n_images, a, ex->cams.p, ex->cam_of_image.p, ex->sel_xys.p, ex->sel_count.p, kps_dev,
                     desc_dev, dmask_dev, counts_dev, capacity, st);
     CK(cudaGetLastError());
+    if (ex->profiling) CK(cudaEventRecord(ex->ev[3], st));
     ex->last_n_images = n_images;
     return MCS_OK;
 }
@@ -406,6 +413,8 @@ void mcs_extractor_destroy(mcs_extractor* ex) {
     ex->masks.release(); ex->cams.release(); ex->cam_of_image.release(); ex->raw.release(); ex->node_of.release();
     ex->raw_count.release(); ex->sel_count.release(); ex->status.release(); ex->counts.release(); ex->sel_xys.release();
     ex->kps.release(); ex->desc.release(); ex->dmask.release();
+    ex->match_idx.release(); ex->match_dist.release();
+    for (int i = 0; i < 4; ++i) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
     if (ex->stream) cudaStreamDestroy(ex->stream);
     delete ex;
 }
@@ -538,6 +547,72 @@ int mcs_extractor_debug_read(mcs_extractor* ex, int32_t image_index, int32_t lev
         return MCS_OK;
     }
     return fail(MCS_ERR_INVALID, "unknown `what`");
+}
+
+int mcs_extractor_set_profiling(mcs_extractor* ex, int32_t enable) {
+    if (!ex) return fail(MCS_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(ex->device));
+    if (enable) for (int i = 0; i < 4; ++i) if (!ex->ev[i]) CK(cudaEventCreate(&ex->ev[i]));
+    ex->profiling = enable != 0;
+    return MCS_OK;
+}
+
+int mcs_extractor_get_timings(mcs_extractor* ex, float* ms3) {
+    if (!ex || !ms3) return fail(MCS_ERR_INVALID, "null argument");
+    if (!ex->profiling || !ex->ev[3]) return fail(MCS_ERR_INVALID, "profiling is not enabled");
+    CK(cudaEventSynchronize(ex->ev[3]));
+    for (int i = 0; i < 3; ++i) CK(cudaEventElapsedTime(&ms3[i], ex->ev[i], ex->ev[i + 1]));
+    return MCS_OK;
+}
+
+int mcs_match_stream_device(const uint8_t* desc_dev, const uint8_t* dmask_dev, const int32_t* counts_dev, int32_t n_frames,
+                            int32_t n_cams, int32_t capacity, int32_t dim, int32_t K, int32_t* match_idx_dev,
+                            int32_t* match_dist_dev, void* stream) {
+    if (!desc_dev || !counts_dev || !match_idx_dev || !match_dist_dev) return fail(MCS_ERR_INVALID, "null argument");
+    if (n_frames < 1 || n_cams < 1 || capacity < 1 || K < 1 || K > 8) return fail(MCS_ERR_INVALID, "bad sizes (K must be 1..8)");
+    if (dim != 16 && dim != 32 && dim != 64) return fail(MCS_ERR_INVALID, "dim must be 16, 32 or 64");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(launch_hamming_stream(desc_dev, dmask_dev, counts_dev, n_frames, n_cams, capacity, dim, K, match_idx_dev, match_dist_dev, st));
+    return MCS_OK;
+}
+
+int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams, const uint8_t* images, int32_t width,
+                             int32_t height, int32_t stride, const uint8_t* masks, const mcs_ocam* cams, mcs_keypoint* kps_out,
+                             uint8_t* desc_out, uint8_t* dmask_out, int32_t* counts_out, int32_t capacity, int32_t K,
+                             int32_t* match_idx_out, int32_t* match_dist_out) {
+    if (!ex || !images || !masks || !cams || !kps_out || !desc_out || !counts_out || !match_idx_out || !match_dist_out)
+        return fail(MCS_ERR_INVALID, "null argument");
+    if (n_frames < 1 || n_cams < 1 || width < 1 || height < 1 || stride < width) return fail(MCS_ERR_INVALID, "bad geometry");
+    if (capacity < ex->capacity) return fail(MCS_ERR_CAPACITY, "capacity below mcs_extractor_info.capacity");
+    if (ex->p.learn_masks && !dmask_out) return fail(MCS_ERR_INVALID, "dmask buffer required when learn_masks is set");
+    if (K < 1 || K > 8) return fail(MCS_ERR_INVALID, "K must be 1..8");
+    CK(cudaSetDevice(ex->device));
+    cudaStream_t st = ex->stream;
+    const int n_images = n_frames * n_cams, ds = ex->p.desc_size;
+    const size_t img_bytes = (size_t)stride * height;
+    std::vector<int> coi(n_images);
+    for (int i = 0; i < n_images; ++i) coi[i] = i % n_cams;
+    CK(ex->in_images.ensure(img_bytes * n_images + 256));
+    CK(ex->kps.ensure((size_t)n_images * capacity));
+    CK(ex->desc.ensure((size_t)n_images * capacity * ds));
+    CK(ex->dmask.ensure((size_t)n_images * capacity * ds));
+    CK(ex->counts.ensure(n_images));
+    CK(ex->match_idx.ensure((size_t)n_images * capacity * K));
+    CK(ex->match_dist.ensure((size_t)n_images * capacity * K));
+    CK(cudaMemcpyAsync(ex->in_images.p, images, img_bytes * n_images, cudaMemcpyHostToDevice, st));
+    int rc = run_pipeline(ex, n_images, ex->in_images.p, width, height, stride, masks, cams, n_cams, coi.data(), ex->kps.p,
+                          ex->desc.p, ex->dmask.p, ex->counts.p, capacity, st);
+    if (rc) return rc;
+    rc = mcs_match_stream_device(ex->desc.p, ex->p.learn_masks ? ex->dmask.p : nullptr, ex->counts.p, n_frames, n_cams, capacity, ds, K,
+                                 ex->match_idx.p, ex->match_dist.p, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(counts_out, ex->counts.p, sizeof(int) * n_images, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(kps_out, ex->kps.p, sizeof(mcs_keypoint) * n_images * capacity, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(desc_out, ex->desc.p, (size_t)n_images * capacity * ds, cudaMemcpyDeviceToHost, st));
+    if (dmask_out) CK(cudaMemcpyAsync(dmask_out, ex->dmask.p, (size_t)n_images * capacity * ds, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(match_idx_out, ex->match_idx.p, sizeof(int) * (size_t)n_images * capacity * K, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(match_dist_out, ex->match_dist.p, sizeof(int) * (size_t)n_images * capacity * K, cudaMemcpyDeviceToHost, st));
+    return check_status(ex, st);
 }
 
 size_t mcs_slot_bytes(int32_t capacity, int32_t dim) {

@@ -178,3 +178,43 @@ def test_search_for_initialization(api, oa, cams, masks):
     ok = m12 >= 0
     dx = F1.keys["x"][ok] - F2.keys["x"][m12[ok]]
     assert np.median(np.abs(dx - 3.0)) < 1.5
+
+
+@pytest.mark.parametrize("masks", [False, True])
+def test_extract_match_stream(api, oa, cams, masks):
+    """The combined stream entry point: extraction identical to per-image calls, matches identical to an
+    all-pairs numpy evaluation of the reference distance (frame t vs t-1, same camera)."""
+    from multicol_slam_b200 import synth
+    F, Cn, K = 3, 3, 2
+    imgs = np.stack([np.stack([synth.texture_stream(cams[c], F, seed=70 + c)[t] for c in range(Cn)]) for t in range(F)])
+    mk = np.stack([synth.mirror_mask(c) for c in cams])
+    ex = api.mdBRIEFextractorOct(nfeatures=500, do_dBrief=True, learnMasks=masks)
+    r = ex.extract_match_stream(imgs, mk, cams, K=K)
+    oe = oa.OracleExtractor(nfeatures=500, do_dbrief=True, learn_masks=masks)
+    per = {}
+    for t in range(F):
+        for c in range(Cn):
+            i = t * Cn + c
+            ok, od, om = oe.extract(imgs[t, c], mk[c], cams[c])
+            n = r["counts"][i]
+            assert n == len(ok) and r["kps"][i, :n].tobytes() == ok.tobytes()
+            assert np.array_equal(r["desc"][i, :n], od) and np.array_equal(r["dmask"][i, :n], om)
+            per[(t, c)] = (od, om)
+    for t in range(F):
+        for c in range(Cn):
+            i = t * Cn + c
+            n = r["counts"][i]
+            if t == 0:
+                assert np.all(r["match_idx"][i] == -1) and np.all(r["match_dist"][i] == 0x7FFFFFFF)
+                continue
+            q, qm = per[(t, c)]
+            d, dm = per[(t - 1, c)]
+            x = np.bitwise_xor(q[:, None, :], d[None, :, :])
+            if masks:
+                dist = (np.unpackbits(x & qm[:, None, :], axis=2).sum(axis=2) + np.unpackbits(x & dm[None, :, :], axis=2).sum(axis=2)) // 2
+            else:
+                dist = np.unpackbits(x, axis=2).sum(axis=2)
+            order = np.lexsort((np.broadcast_to(np.arange(len(d)), dist.shape), dist), axis=1)[:, :K]
+            assert np.array_equal(r["match_idx"][i, :n], order.astype(np.int32))
+            assert np.array_equal(r["match_dist"][i, :n], np.take_along_axis(dist, order, axis=1).astype(np.int32))
+            assert np.all(r["match_idx"][i, n:] == -1)
