@@ -1,0 +1,379 @@
+// describe_kernel.cu -- K3: orientation + descriptor, one warp per selected keypoint.
+//
+//   IC_Angle            ref src/mdBRIEFextractorOct.cpp:221-248   integer moments over the 845-px disc, fastAtan2
+//   undistortPointsOcam ref :1306-1317, include/cam_model_omni.h:127-138
+//   rotate[AndDistort]Pattern  ref :250-301
+//   compute_ORB / compute_dBRIEF / compute_mdBRIEF   ref :303-554
+//   output assembly     ref :1327-1335  (pt *= scale for levels > 0)
+//
+// Layout of the work: lane b of the warp owns descriptor byte b, i.e. the 16 pattern points 16b..16b+15 (8 test
+// pairs).  For the distorted variants the lane keeps the 16 projected points of one pattern in registers, the
+// warp reduces their sum (the reference subtracts the mean of all 512 projected points, :262-281), then every
+// lane rounds and samples its own points: no shuffles, no second projection pass.
+//
+// Fisheye projection cost.  cCamModelGeneral_::WorldToImg evaluates, per pattern point, sqrt + 3 divisions +
+// atan + a 12-term Horner in double (~250 FP64 instructions; 1536 points per mdBRIEF keypoint).  Because the
+// third coordinate is the per-camera constant z = -a0, u = x*g(r)*c + y*g(r)*d + u0 with
+//     g(r) = R(r) / r,   R(r) = rho(atan(-z / r)),      r = sqrt(x^2 + y^2),
+// and R is a smooth 1-D function of r ("the distortion baked into a LUT" of the north star; g itself is not
+// tabulated because the fitted inverse polynomial leaves a tiny rho(-pi/2) != 0, i.e. a 1/r pole).  The host
+// tabulates R per camera as degree-5 polynomials on 1-px intervals fitted in long double (error < 1e-13 px, the
+// rounding noise of the reference's own double evaluation); the device evaluates rsqrt + 5 FMA + the affine map.
+// Only cvRound(u - mean) has to agree with the reference; a projected coordinate closer than 1e-7 px to a
+// rounding tie (p ~ 2e-4 per pattern) makes the warp recompute that pattern with the reference's exact
+// operation sequence (cam_model.cuh).  Radii outside the table take the exact path as well.
+#include <vector>
+
+#include "cam_model.cuh"
+#include "kernels.h"
+#include "mcs_common.cuh"
+
+namespace mcs {
+
+__constant__ signed char c_pairs[2048];          // learned_pattern_64_ORB (ref include/mdBRIEFextractorOct.h:44-47)
+__constant__ signed char c_disc_u[848], c_disc_v[848];   // the 845 (u,v) offsets of the IC_Angle disc
+
+// cv::fastAtan2, evaluated without FMA
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float s = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * s, p3 = -0.3258083974640975f * s;
+    const float p5 = 0.1555786518463281f * s, p7 = -0.04432655554792128f * s;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, (float)2.2204460492503131e-16));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, (float)2.2204460492503131e-16));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+__device__ __forceinline__ int sample_px(const uint8_t* bimg, const uint8_t* uimg, const LevelGeom& g, int row, int col) {
+    // blurred ROI; outside the ROI the reference reads the un-blurred REFLECT_101 ring of its buffer
+    if ((unsigned)row < (unsigned)g.h && (unsigned)col < (unsigned)g.w) return bimg[(size_t)row * g.pitch + col];
+    row = min(max(row, -kEdge), g.h - 1 + kEdge); col = min(max(col, -kEdge), g.w - 1 + kEdge);   // memory-safety clamp
+    return uimg[(size_t)reflect101(row, g.h) * g.pitch + reflect101(col, g.w)];
+}
+
+// R(r) = rho(atan(-z/r)) from the per-camera table; returns false when r is outside the table
+__device__ __forceinline__ bool lut_R(const DistortLut& L, double r, double& g) {
+    const double t = r * L.inv_h;
+    if (!(t < (double)L.n)) return false;
+    const int idx = (int)t;
+    const double tau = fma(2.0, t - (double)idx, -1.0);            // [-1, 1) inside the interval
+    const double2* c = (const double2*)(L.coef + (size_t)idx * 8);
+    const double2 c01 = __ldg(c), c23 = __ldg(c + 1), c45 = __ldg(c + 2);
+    double p = c45.y;
+    p = fma(p, tau, c45.x); p = fma(p, tau, c23.y); p = fma(p, tau, c23.x); p = fma(p, tau, c01.y); p = fma(p, tau, c01.x);
+    g = p;
+    return true;
+}
+
+constexpr int kDescWarps = 8;
+
+// Rare path: one pattern of one keypoint with the reference's exact operation sequence (two projection passes;
+// per-lane partial sums + butterfly: within ~1e-13 of the reference's sequential sum).
+// Returns the descriptor byte(s) of this lane for that pattern, byte bb in bits [8bb, 8bb+8).
+template <int PPL>
+__device__ __noinline__ unsigned exact_pattern(const mcs_ocam* cam, const char2* s_pat, double ca, double sa, double ukx,
+                                               double uky, int lane, int ds, const uint8_t* bimg, const uint8_t* uimg,
+                                               const LevelGeom* g, int kx, int ky) {
+    const double z = -cam->pol[0];
+    double su = 0.0, sv = 0.0;
+    for (int j = 0; j < PPL; ++j) {
+        const char2 pp = s_pat[j * 32 + lane];
+        const double px = (double)pp.x, py = (double)pp.y;
+        const double xr = px * ca - py * sa + ukx;
+        const double yr = px * sa + py * ca + uky;
+        double u, v;
+        cam_world_to_img(*cam, xr, yr, z, u, v);
+        if (lane + 32 * (j >> 4) < ds) { su += u; sv += v; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        su += __shfl_xor_sync(0xffffffffu, su, o);
+        sv += __shfl_xor_sync(0xffffffffu, sv, o);
+    }
+    const double mu = su / (double)(16 * ds), mv = sv / (double)(16 * ds);
+    unsigned out = 0;
+    for (int j = 0; j < PPL; j += 2) {
+        int smp[2];
+        for (int e = 0; e < 2; ++e) {
+            const char2 pp = s_pat[(j + e) * 32 + lane];
+            const double px = (double)pp.x, py = (double)pp.y;
+            const double xr = px * ca - py * sa + ukx;
+            const double yr = px * sa + py * ca + uky;
+            double u, v;
+            cam_world_to_img(*cam, xr, yr, z, u, v);
+            smp[e] = sample_px(bimg, uimg, *g, ky + __double2int_rn(v - mv), kx + __double2int_rn(u - mu));
+        }
+        out |= (unsigned)(smp[0] < smp[1]) << (j >> 1);
+    }
+    return out;
+}
+
+template <int PPL /* pattern points per lane: 16 for descSize <= 32, 32 for descSize 64 */>
+__global__ void __launch_bounds__(kDescWarps * 32, 2)
+describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, const mcs_ocam* __restrict__ cams,
+                const DistortLut* __restrict__ luts, const int* __restrict__ cam_of_image,
+                const uint32_t* __restrict__ sel_xys, const int* __restrict__ sel_count,
+                mcs_keypoint* __restrict__ kps_out, uint8_t* __restrict__ desc_out, uint8_t* __restrict__ dmask_out,
+                int* __restrict__ counts_out, const int capacity, const int n_images) {
+    __shared__ char2 s_pat[PPL * 32];            // [j][lane] : point 16*byte + k with byte = lane + 32*(j/16), k = j%16
+    __shared__ char2 s_disc[848];
+    __shared__ mcs_ocam s_cam[kDescWarps];
+    const int ds = geom->desc_size;
+    for (int i = threadIdx.x; i < PPL * 32; i += blockDim.x) {
+        const int j = i >> 5, ln = i & 31;
+        const int byte = ln + 32 * (j >> 4), pt = 16 * byte + (j & 15);
+        s_pat[i] = byte < ds ? make_char2(c_pairs[2 * pt], c_pairs[2 * pt + 1]) : make_char2(0, 0);
+    }
+    for (int i = threadIdx.x; i < 848; i += blockDim.x) s_disc[i] = make_char2(c_disc_u[i], c_disc_v[i]);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int sel_total = geom->sel_total;
+    const int b = warp_global / sel_total;
+    if (b >= n_images) return;
+    const int slot = warp_global - b * sel_total;
+    const int L = geom->nlevels;
+    int level = 0, off = 0;
+    for (int l = 0; l < L; ++l)
+        if (slot >= geom->lv[l].sel_off) level = l;
+    for (int l = 0; l < level; ++l) off += sel_count[b * L + l];
+    const LevelGeom& g = geom->lv[level];
+    const int p = slot - g.sel_off;
+    const int cnt = sel_count[b * L + level];
+    if (slot == 0 && lane == 0) {
+        int tot = 0;
+        for (int l = 0; l < L; ++l) tot += sel_count[b * L + l];
+        counts_out[b] = min(tot, capacity);
+    }
+    if (p >= cnt) return;
+    const int oidx = off + p;
+    if (oidx >= capacity) return;
+    const uint32_t c = sel_xys[(size_t)b * sel_total + slot];
+    const int kx = corner_x(c), ky = corner_y(c);
+    const uint8_t* uimg = args.lvl[level] + (size_t)b * g.img_bytes;
+    const uint8_t* bimg = args.blur[level] + (size_t)b * g.img_bytes;
+
+    // ---- IC_Angle: integer moments over the 845-pixel disc (sum order is irrelevant for integers) ----
+    int m10 = 0, m01 = 0;
+    {
+        const uint8_t* ctr = uimg + (size_t)ky * g.pitch + kx;
+        for (int i = lane; i < 845; i += 32) {
+            const char2 uv = s_disc[i];
+            const int val = ctr[uv.y * g.pitch + uv.x];
+            m10 += uv.x * val;
+            m01 += uv.y * val;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        }
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+    const int ci = cam_of_image[b];
+    const bool masks = geom->learn_masks != 0, dbrief = geom->do_dbrief != 0 || masks;
+    const float scale = g.scale;
+    const int npat = masks ? 3 : 1;
+    double ca[3], sa[3];
+    {
+        double a0;
+        if (masks) a0 = (double)__fdiv_rn(angle, 57.2957763671875f);              // angle / RHOf      (ref :425)
+        else a0 = (double)__fmul_rn(angle, 0.01745329238474369f);                   // angle * DEG2RADf  (ref :313,367)
+        const double rot = 20.0 / (180.0 / 3.1415926535897932384626433832795);      // 20 / RHOd         (ref :424)
+        sincos(a0, &sa[0], &ca[0]);
+        sincos(a0 + rot, &sa[1], &ca[1]);
+        sincos(a0 - rot, &sa[2], &ca[2]);
+    }
+    constexpr int BPL = PPL / 16;                 // descriptor bytes per lane
+    unsigned val[3][BPL];
+    if (!dbrief) {
+        // ---- ORB: rotatePattern (ref :285-301) ----
+#pragma unroll
+        for (int bb = 0; bb < BPL; ++bb) {
+            unsigned v = 0;
+#pragma unroll
+            for (int bit = 0; bit < 8; ++bit) {
+                int smp[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const char2 pp = s_pat[(16 * bb + 2 * bit + e) * 32 + lane];
+                    const double px = (double)pp.x, py = (double)pp.y;
+                    const int ix = __double2int_rn(px * ca[0] - py * sa[0]);
+                    const int iy = __double2int_rn(px * sa[0] + py * ca[0]);
+                    smp[e] = sample_px(bimg, uimg, g, ky + iy, kx + ix);
+                }
+                v |= (unsigned)(smp[0] < smp[1]) << bit;
+            }
+            val[0][bb] = v;
+        }
+    } else {
+        // ---- dBRIEF / mdBRIEF: rotateAndDistortPattern (ref :250-283) ----
+        const int wib = threadIdx.x >> 5;
+        if (lane < (int)(sizeof(mcs_ocam) / 8)) ((double*)&s_cam[wib])[lane] = ((const double*)&cams[ci])[lane];
+        __syncwarp();
+        const mcs_ocam& cam = s_cam[wib];
+        const DistortLut lut = luts[ci];
+        double ukx, uky;   // undistortPointsOcam(pt.x*scale, pt.y*scale, a0)  (ref :1306-1317)
+        cam_undistort(cam, (double)__fmul_rn((float)kx, scale), (double)__fmul_rn((float)ky, scale), cam.pol[0], ukx, uky);
+        const double inv_n = 1.0 / (double)(16 * ds);
+        const bool lane_valid = (PPL == 32) || (lane < ds);      // descSize 16: lanes 16..31 own no byte
+        for (int q = 0; q < npat; ++q) {
+            double us[PPL], vs[PPL];
+            double su = 0.0, sv = 0.0;
+            bool need_exact = false;
+#pragma unroll
+            for (int j = 0; j < PPL; ++j) {
+                const char2 pp = s_pat[j * 32 + lane];
+                const double px = (double)pp.x, py = (double)pp.y;
+                const double xr = px * ca[q] - py * sa[q] + ukx;
+                const double yr = px * sa[q] + py * ca[q] + uky;
+                const double s2 = fma(xr, xr, yr * yr);
+                const double rinv = rsqrt(s2), r = s2 * rinv;
+                double gg;
+                if (!lut_R(lut, r, gg)) { need_exact = lane_valid; gg = 0.0; }     // also catches s2 == 0 (r = NaN)
+                gg *= rinv;
+                const double uu = xr * gg, vv = yr * gg;
+                us[j] = fma(uu, cam.c, fma(vv, cam.d, cam.u0));
+                vs[j] = fma(uu, cam.e, vv + cam.v0);
+                if (lane_valid) { su += us[j]; sv += vs[j]; }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                su += __shfl_xor_sync(0xffffffffu, su, o);
+                sv += __shfl_xor_sync(0xffffffffu, sv, o);
+            }
+            double mu = su * inv_n, mv = sv * inv_n;
+#pragma unroll
+            for (int j = 0; j < PPL; ++j) {
+                const double du = us[j] - mu, dv = vs[j] - mv;
+                need_exact |= lane_valid && (fabs(fabs(du - rint(du)) - 0.5) < 1e-7 || fabs(fabs(dv - rint(dv)) - 0.5) < 1e-7);
+            }
+            if (__any_sync(0xffffffffu, need_exact)) {
+                const unsigned e = exact_pattern<PPL>(&cam, s_pat, ca[q], sa[q], ukx, uky, lane, ds, bimg, uimg, &g, kx, ky);
+#pragma unroll
+                for (int bb = 0; bb < BPL; ++bb) val[q][bb] = (e >> (8 * bb)) & 0xFFu;
+                continue;
+            }
+#pragma unroll
+            for (int bb = 0; bb < BPL; ++bb) {
+                unsigned v = 0;
+#pragma unroll
+                for (int bit = 0; bit < 8; ++bit) {
+                    const int j0 = 16 * bb + 2 * bit;
+                    const int s0 = sample_px(bimg, uimg, g, ky + __double2int_rn(vs[j0] - mv), kx + __double2int_rn(us[j0] - mu));
+                    const int s1 = sample_px(bimg, uimg, g, ky + __double2int_rn(vs[j0 + 1] - mv), kx + __double2int_rn(us[j0 + 1] - mu));
+                    v |= (unsigned)(s0 < s1) << bit;
+                }
+                val[q][bb] = v;
+            }
+        }
+    }
+#pragma unroll
+    for (int bb = 0; bb < BPL; ++bb) {
+        const int byte = lane + 32 * bb;
+        if (byte < ds) {
+            desc_out[((size_t)b * capacity + oidx) * ds + byte] = (uint8_t)val[0][bb];
+            if (dmask_out) {
+                // stable bit <=> both +-20 degree re-tests agree with the bit (ref :449-451 ...)
+                const unsigned m = masks ? (~((val[1][bb] ^ val[0][bb]) | (val[2][bb] ^ val[0][bb])) & 0xFFu) : 0u;
+                dmask_out[((size_t)b * capacity + oidx) * ds + byte] = (uint8_t)m;
+            }
+        }
+    }
+    if (lane == 0) {
+        mcs_keypoint k;
+        k.x = level ? __fmul_rn((float)kx, scale) : (float)kx;      // pt *= scale for l > 0 (ref :1327-1332)
+        k.y = level ? __fmul_rn((float)ky, scale) : (float)ky;
+        k.size = g.patch_size; k.angle = angle; k.response = (float)corner_s(c);
+        k.octave = level; k.class_id = -1;
+        kps_out[(size_t)b * capacity + oidx] = k;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+cudaError_t upload_constants(const signed char* pairs, const signed char* du, const signed char* dv) {
+    cudaError_t e = cudaMemcpyToSymbol(c_pairs, pairs, 2048);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(c_disc_u, du, 848);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_disc_v, dv, 848);
+}
+
+// Tabulate R(r) = rho(atan(-z/r)) on [0, n) px in unit intervals: 6 monomial coefficients in
+// tau = 2 (r - idx) - 1, interpolating R at the 6 Chebyshev nodes of the interval, all in long double.
+void build_distort_lut(const mcs_ocam& cam, std::vector<double>& coef, int& n_out) {
+    // table extent: largest undistorted radius of any pixel the mirror mask keeps, plus the pattern reach
+    const double scaleF = cam.pol[0];
+    double rmax = 64.0;
+    const double mcx = cam.u0, mcy = cam.v0, mrad = cam.v0 + 22.0;
+    for (int y = 0; y < cam.height; y += 4)
+        for (int x = 0; x < cam.width; x += 4) {
+            if (cam.mirror_mask == 1 && std::hypot(x - mcx, y - mcy) > mrad + 4.0) continue;
+            double wx, wy, wz;
+            cam_img_to_world(cam, (double)x, (double)y, wx, wy, wz);
+            if (!(wz * scaleF < 0.0)) continue;            // behind / on the undistortion plane: no finite image
+            const double ux = -wx / wz * scaleF, uy = -wy / wz * scaleF;
+            const double r = std::hypot(ux, uy);
+            if (std::isfinite(r) && r > rmax) rmax = r;
+        }
+    int n = (int)std::min(8192.0, std::ceil(rmax + 64.0));
+    n_out = n;
+    coef.assign((size_t)n * 8, 0.0);
+    const long double z = -(long double)cam.pol[0];
+    long double nodes[6];
+    for (int k = 0; k < 6; ++k) nodes[k] = cosl((2 * k + 1) * 3.14159265358979323846264338327950288L / 12.0L);
+    for (int i = 0; i < n; ++i) {
+        long double A[6][7];
+        for (int k = 0; k < 6; ++k) {
+            const long double tau = nodes[k], r = (long double)i + (tau + 1.0L) * 0.5L;
+            const long double theta = atanl(-z / r);
+            long double rho = 0.0L;
+            for (int t = 11; t >= 0; --t) rho = rho * theta + (long double)cam.inv_pol[t];
+            long double pw = 1.0L;
+            for (int t = 0; t < 6; ++t) { A[k][t] = pw; pw *= tau; }
+            A[k][6] = rho;
+        }
+        for (int col = 0; col < 6; ++col) {          // Gaussian elimination with partial pivoting
+            int piv = col;
+            for (int r2 = col + 1; r2 < 6; ++r2) if (fabsl(A[r2][col]) > fabsl(A[piv][col])) piv = r2;
+            for (int t = 0; t < 7; ++t) std::swap(A[col][t], A[piv][t]);
+            for (int r2 = 0; r2 < 6; ++r2) {
+                if (r2 == col) continue;
+                const long double f = A[r2][col] / A[col][col];
+                for (int t = col; t < 7; ++t) A[r2][t] -= f * A[col][t];
+            }
+        }
+        for (int t = 0; t < 6; ++t) coef[(size_t)i * 8 + t] = (double)(A[t][6] / A[t][t]);
+    }
+}
+
+cudaError_t launch_describe(const PyramidGeom& G, const PyramidGeom* G_dev, int n_images, const DescribeArgs& args,
+                            const mcs_ocam* cams, const DistortLut* luts, const int* cam_of_image, const uint32_t* sel_xys,
+                            const int* sel_count, mcs_keypoint* kps, uint8_t* desc, uint8_t* dmask, int* counts, int capacity,
+                            cudaStream_t st) {
+    const long long warps = (long long)n_images * G.sel_total;
+    const int blocks = (int)((warps + kDescWarps - 1) / kDescWarps);
+    if (G.desc_size <= 32)
+        describe_kernel<16><<<blocks, kDescWarps * 32, 0, st>>>(G_dev, args, cams, luts, cam_of_image, sel_xys, sel_count, kps, desc,
+                                                               dmask, counts, capacity, n_images);
+    else
+        describe_kernel<32><<<blocks, kDescWarps * 32, 0, st>>>(G_dev, args, cams, luts, cam_of_image, sel_xys, sel_count, kps, desc,
+                                                               dmask, counts, capacity, n_images);
+    return cudaGetLastError();
+}
+
+}  // namespace mcs

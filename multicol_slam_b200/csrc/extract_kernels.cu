@@ -5,8 +5,7 @@
 //                          (ref src/mdBRIEFextractorOct.cpp:1158-1201, :863-949, :1301; OpenCV
 //                          resize/boxFilter/FAST arithmetic of SURVEY.md Appendix A.1/A.3/A.5)
 //   K2 octree_kernel     : DistributeOctTree, one CTA per (image, level)   (ref :569-861)
-//   K3 describe_kernel   : IC angle + rotated/distorted BRIEF pattern + 256-bit tests, one warp per
-//                          keypoint (ref :221-301, :303-554, :1306-1332)
+//   (K3, orientation + descriptor, lives in describe_kernel.cu)
 //
 // Everything is integer / exactly-rounded arithmetic; compile with -fmad=false so that no float or
 // double expression is contracted (the CPU oracle is built with -ffp-contract=off).
@@ -532,188 +531,8 @@ octree_kernel(const PyramidGeom* __restrict__ geom, const int cap /* node capaci
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3  orientation + descriptor
-// ------------------------------------------------------------------------------------------------
-__constant__ signed char c_pairs[2048];          // learned_pattern_64_ORB (ref include/mdBRIEFextractorOct.h:44-47)
-__constant__ signed char c_disc_u[848], c_disc_v[848];   // the 845 (u,v) offsets of the IC_Angle disc
-
-// cv::fastAtan2, evaluated without FMA
-__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
-    const float s = (float)(180.0 / 3.14159265358979323846);
-    const float p1 = 0.9997878412794807f * s, p3 = -0.3258083974640975f * s;
-    const float p5 = 0.1555786518463281f * s, p7 = -0.04432655554792128f * s;
-    const float ax = fabsf(x), ay = fabsf(y);
-    float a, c, c2;
-    if (ax >= ay) {
-        c = __fdiv_rn(ay, __fadd_rn(ax, (float)2.2204460492503131e-16));
-        c2 = __fmul_rn(c, c);
-        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
-    } else {
-        c = __fdiv_rn(ax, __fadd_rn(ay, (float)2.2204460492503131e-16));
-        c2 = __fmul_rn(c, c);
-        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
-    }
-    if (x < 0) a = __fsub_rn(180.f, a);
-    if (y < 0) a = __fsub_rn(360.f, a);
-    return a;
-}
-
-
-__device__ __forceinline__ int sample_px(const uint8_t* bimg, const uint8_t* uimg, const LevelGeom& g, int row, int col) {
-    // blurred ROI; outside the ROI the reference reads the un-blurred REFLECT_101 ring of the buffer
-    if ((unsigned)row < (unsigned)g.h && (unsigned)col < (unsigned)g.w) return bimg[(size_t)row * g.pitch + col];
-    row = min(max(row, -kEdge), g.h - 1 + kEdge); col = min(max(col, -kEdge), g.w - 1 + kEdge);   // memory-safety clamp
-    return uimg[(size_t)reflect101(row, g.h) * g.pitch + reflect101(col, g.w)];
-}
-
-__global__ void __launch_bounds__(256)
-describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, const mcs_ocam* __restrict__ cams,
-                const int* __restrict__ cam_of_image,
-                const uint32_t* __restrict__ sel_xys, const int* __restrict__ sel_count,
-                mcs_keypoint* __restrict__ kps_out, uint8_t* __restrict__ desc_out, uint8_t* __restrict__ dmask_out,
-                int* __restrict__ counts_out, const int capacity, const int n_images) {
-    const int lane = threadIdx.x & 31;
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int sel_total = geom->sel_total;
-    const int b = warp_global / sel_total;
-    if (b >= n_images) return;
-    const int slot = warp_global - b * sel_total;
-    const int L = geom->nlevels;
-    // which level does this slot belong to, and its output index
-    int level = 0, off = 0;
-    for (int l = 0; l < L; ++l) {
-        if (slot >= geom->lv[l].sel_off) level = l;
-    }
-    for (int l = 0; l < level; ++l) off += sel_count[b * L + l];
-    const LevelGeom& g = geom->lv[level];
-    const int p = slot - g.sel_off;
-    const int cnt = sel_count[b * L + level];
-    if (slot == 0 && lane == 0) {
-        int tot = 0;
-        for (int l = 0; l < L; ++l) tot += sel_count[b * L + l];
-        counts_out[b] = min(tot, capacity);
-    }
-    if (p >= cnt) return;
-    const int oidx = off + p;
-    if (oidx >= capacity) return;
-    const uint32_t c = sel_xys[(size_t)b * sel_total + slot];
-    const int kx = corner_x(c), ky = corner_y(c);
-    const uint8_t* uimg = args.lvl[level] + (size_t)b * g.img_bytes;
-    const uint8_t* bimg = args.blur[level] + (size_t)b * g.img_bytes;
-
-    // ---- IC_Angle (ref :221-248): integer moments over the 845-pixel disc ----
-    int m10 = 0, m01 = 0;
-    {
-        const uint8_t* ctr = uimg + (size_t)ky * g.pitch + kx;
-        for (int i = lane; i < 845; i += 32) {
-            const int u = c_disc_u[i], v = c_disc_v[i];
-            const int val = ctr[v * g.pitch + u];
-            m10 += u * val;
-            m01 += v * val;
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-        }
-    }
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
-
-    // ---- pattern rotation (+ fisheye distortion) and the binary tests ----
-    const int ds = geom->desc_size;
-    const mcs_ocam cam = cams[cam_of_image[b]];
-    const bool masks = geom->learn_masks != 0, dbrief = geom->do_dbrief != 0 || masks;
-    const float scale = g.scale;
-    double ukx = 0.0, uky = 0.0;
-    if (dbrief) {   // undistortPointsOcam(pt.x*scale, pt.y*scale, a0)  (ref :1306-1317)
-        cam_undistort(cam, (double)__fmul_rn((float)kx, scale), (double)__fmul_rn((float)ky, scale), cam.pol[0], ukx, uky);
-    }
-    const int npat = masks ? 3 : 1;
-    double ca[3], sa[3];
-    {
-        double a0;
-        if (masks) a0 = (double)__fdiv_rn(angle, 57.2957763671875f);              // angle / RHOf  (ref :425)
-        else a0 = (double)__fmul_rn(angle, 0.01745329238474369f);                   // angle * DEG2RADf (ref :313,367)
-        const double rot = 20.0 / (180.0 / 3.1415926535897932384626433832795);
-        ca[0] = cos(a0); sa[0] = sin(a0);
-        ca[1] = cos(a0 + rot); sa[1] = sin(a0 + rot);
-        ca[2] = cos(a0 - rot); sa[2] = sin(a0 - rot);
-    }
-    const double z = -cam.pol[0];
-    const int npoints = 16 * ds;
-    // mean of the distorted pattern (ref :262-276): per-lane partial sums + butterfly reduction
-    double meanx[3] = {0, 0, 0}, meany[3] = {0, 0, 0};
-    if (dbrief) {
-        for (int q = 0; q < npat; ++q) {
-            double sx = 0.0, sy = 0.0;
-            for (int i = lane; i < npoints; i += 32) {
-                const double px = (double)c_pairs[2 * i], py = (double)c_pairs[2 * i + 1];
-                const double xr = px * ca[q] - py * sa[q] + ukx;
-                const double yr = px * sa[q] + py * ca[q] + uky;
-                double u, v;
-                cam_world_to_img(cam, xr, yr, z, u, v);
-                sx += u; sy += v;
-            }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                sx += __shfl_xor_sync(0xffffffffu, sx, o);
-                sy += __shfl_xor_sync(0xffffffffu, sy, o);
-            }
-            meanx[q] = sx / (double)npoints; meany[q] = sy / (double)npoints;
-        }
-    }
-    for (int byte = lane; byte < ds; byte += 32) {
-        int val = 0, mval = 0;
-        for (int bit = 0; bit < 8; ++bit) {
-            int t[3];
-            for (int q = 0; q < npat; ++q) {
-                int smp[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int i = 16 * byte + 2 * bit + e;
-                    const double px = (double)c_pairs[2 * i], py = (double)c_pairs[2 * i + 1];
-                    int ix, iy;
-                    if (dbrief) {
-                        const double xr = px * ca[q] - py * sa[q] + ukx;
-                        const double yr = px * sa[q] + py * ca[q] + uky;
-                        double u, v;
-                        cam_world_to_img(cam, xr, yr, z, u, v);
-                        ix = __double2int_rn(u - meanx[q]); iy = __double2int_rn(v - meany[q]);
-                    } else {
-                        ix = __double2int_rn(px * ca[q] - py * sa[q]);
-                        iy = __double2int_rn(px * sa[q] + py * ca[q]);
-                    }
-                    smp[e] = sample_px(bimg, uimg, g, ky + iy, kx + ix);
-                }
-                t[q] = smp[0] < smp[1];
-            }
-            val |= t[0] << bit;
-            if (masks) mval |= (int)(((t[1] ^ t[0]) + (t[2] ^ t[0])) == 0) << bit;
-        }
-        desc_out[((size_t)b * capacity + oidx) * ds + byte] = (uint8_t)val;
-        if (dmask_out) dmask_out[((size_t)b * capacity + oidx) * ds + byte] = (uint8_t)mval;
-    }
-    if (lane == 0) {
-        mcs_keypoint k;
-        k.x = level ? __fmul_rn((float)kx, scale) : (float)kx;      // pt *= scale for l > 0 (ref :1327-1332)
-        k.y = level ? __fmul_rn((float)ky, scale) : (float)ky;
-        k.size = g.patch_size; k.angle = angle; k.response = (float)corner_s(c);
-        k.octave = level; k.class_id = -1;
-        kps_out[(size_t)b * capacity + oidx] = k;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // host-callable launchers
 // ------------------------------------------------------------------------------------------------
-cudaError_t upload_constants(const signed char* pairs, const signed char* du, const signed char* dv) {
-    cudaError_t e = cudaMemcpyToSymbol(c_pairs, pairs, 2048);
-    if (e != cudaSuccess) return e;
-    e = cudaMemcpyToSymbol(c_disc_u, du, 848);
-    if (e != cudaSuccess) return e;
-    return cudaMemcpyToSymbol(c_disc_v, dv, 848);
-}
-
 void launch_pyr_fast(const PyramidGeom& G, int level, int n_images, const uint8_t* src, size_t src_img_bytes,
                      uint8_t* dst, uint8_t* dst_blur, const uint8_t* mask0, int mask_w, size_t mask_bytes,
                      const int* cam_of_image, uint32_t* raw, int* raw_count, cudaStream_t st) {
@@ -740,15 +559,6 @@ cudaError_t launch_octree(const PyramidGeom& G, const PyramidGeom* G_dev, int n_
     dim3 grid(G.nlevels, n_images);
     octree_kernel<<<grid, kOctThreads, smem, st>>>(G_dev, cap, raw, G.raw_total, raw_count, node_of, sel_xys, sel_count, status);
     return cudaSuccess;
-}
-
-void launch_describe(const PyramidGeom& G, const PyramidGeom* G_dev, int n_images, const DescribeArgs& args,
-                     const mcs_ocam* cams, const int* cam_of_image, const uint32_t* sel_xys, const int* sel_count, mcs_keypoint* kps,
-                     uint8_t* desc, uint8_t* dmask, int* counts, int capacity, cudaStream_t st) {
-    const long long warps = (long long)n_images * G.sel_total;
-    const int blocks = (int)((warps * 32 + 255) / 256);
-    describe_kernel<<<blocks, 256, 0, st>>>(G_dev, args, cams, cam_of_image, sel_xys, sel_count, kps, desc, dmask, counts, capacity,
-                                            n_images);
 }
 
 }  // namespace mcs

@@ -1,5 +1,7 @@
 // kernels.h -- launchers exported by the .cu files to the C-ABI host layer (mcs_api.cu).
 #pragma once
+#include <vector>
+
 #include "mcs_common.cuh"
 
 namespace mcs {
@@ -16,9 +18,18 @@ void launch_pyr_fast(const PyramidGeom& G, int level, int n_images, const uint8_
 cudaError_t launch_octree(const PyramidGeom& G, const PyramidGeom* G_dev, int n_images, const uint32_t* raw,
                           const int* raw_count, uint16_t* node_of, uint32_t* sel_xys, int* sel_count, int* status,
                           cudaStream_t st);
-void launch_describe(const PyramidGeom& G, const PyramidGeom* G_dev, int n_images, const DescribeArgs& args,
-                     const mcs_ocam* cams, const int* cam_of_image, const uint32_t* sel_xys, const int* sel_count,
-                     mcs_keypoint* kps, uint8_t* desc, uint8_t* dmask, int* counts, int capacity, cudaStream_t st);
+// per-camera table of g(r) = rho(atan(-z/r))/r (describe_kernel.cu): interval i covers r in [i, i+1) px,
+// 8 doubles per interval (6 coefficients in tau = 2(r-i)-1, 2 pad)
+struct DistortLut {
+    const double* coef;
+    int n;
+    double inv_h;
+};
+void build_distort_lut(const mcs_ocam& cam, std::vector<double>& coef, int& n_out);
+cudaError_t launch_describe(const PyramidGeom& G, const PyramidGeom* G_dev, int n_images, const DescribeArgs& args,
+                            const mcs_ocam* cams, const DistortLut* luts, const int* cam_of_image, const uint32_t* sel_xys,
+                            const int* sel_count, mcs_keypoint* kps, uint8_t* desc, uint8_t* dmask, int* counts, int capacity,
+                            cudaStream_t st);
 
 // matching (match_kernels.cu)
 cudaError_t launch_hamming_topk(const uint8_t* q, const uint8_t* qmask, int nq, const uint8_t* d, const uint8_t* dmask,

@@ -91,6 +91,10 @@ struct mcs_extractor {
     DevBuf<uint8_t> desc, dmask;
     int last_n_images = 0;
     DevBuf<int> match_idx, match_dist;
+    // distortion tables, rebuilt when the camera set changes
+    std::vector<mcs_ocam> lut_cams;
+    DevBuf<double> lut_coef;
+    DevBuf<DistortLut> luts;
     bool profiling = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
@@ -246,6 +250,27 @@ int run_pipeline(mcs_extractor* ex, int n_images, const uint8_t* images_dev, int
     CK(ex->cams.ensure(n_cams));
     CK(cudaMemcpyAsync(ex->masks.p, masks, (size_t)n_cams * W * H, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ex->cams.p, cams, sizeof(mcs_ocam) * n_cams, cudaMemcpyHostToDevice, st));
+    if ((ex->p.do_dbrief || ex->p.learn_masks) &&
+        ((int)ex->lut_cams.size() != n_cams || std::memcmp(ex->lut_cams.data(), cams, sizeof(mcs_ocam) * n_cams) != 0)) {
+        std::vector<double> all;
+        std::vector<size_t> offs(n_cams);
+        std::vector<int> ns(n_cams);
+        for (int c = 0; c < n_cams; ++c) {
+            std::vector<double> coef;
+            build_distort_lut(cams[c], coef, ns[c]);
+            offs[c] = all.size();
+            all.insert(all.end(), coef.begin(), coef.end());
+        }
+        CK(cudaStreamSynchronize(st));                 // a previous call may still read the old tables
+        CK(ex->lut_coef.ensure(all.size()));
+        CK(ex->luts.ensure(n_cams));
+        std::vector<DistortLut> h(n_cams);
+        for (int c = 0; c < n_cams; ++c) h[c] = DistortLut{ex->lut_coef.p + offs[c], ns[c], 1.0};
+        CK(cudaMemcpyAsync(ex->lut_coef.p, all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ex->luts.p, h.data(), sizeof(DistortLut) * n_cams, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));                 // host staging vectors die here
+        ex->lut_cams.assign(cams, cams + n_cams);
+    }
     CK(cudaMemcpyAsync(ex->cam_of_image.p, cam_of_image, sizeof(int) * n_images, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(ex->raw_count.p, 0, sizeof(int) * n_images * G.nlevels, st));
     CK(cudaMemsetAsync(ex->status.p, 0, sizeof(int), st));
@@ -264,9 +289,8 @@ int run_pipeline(mcs_extractor* ex, int n_images, const uint8_t* images_dev, int
     if (ex->profiling) CK(cudaEventRecord(ex->ev[2], st));
     DescribeArgs a;
     for (int l = 0; l < kMaxLevels; ++l) { a.lvl[l] = ex->lvl[l].p; a.blur[l] = ex->blur[l].p; }
-    launch_describe(G, ex->G_dev.p, n_images, a, ex->cams.p, ex->cam_of_image.p, ex->sel_xys.p, ex->sel_count.p, kps_dev,
-                    desc_dev, dmask_dev, counts_dev, capacity, st);
-    CK(cudaGetLastError());
+    CK(launch_describe(G, ex->G_dev.p, n_images, a, ex->cams.p, ex->luts.p, ex->cam_of_image.p, ex->sel_xys.p, ex->sel_count.p,
+                       kps_dev, desc_dev, dmask_dev, counts_dev, capacity, st));
     if (ex->profiling) CK(cudaEventRecord(ex->ev[3], st));
     ex->last_n_images = n_images;
     return MCS_OK;
@@ -413,7 +437,7 @@ void mcs_extractor_destroy(mcs_extractor* ex) {
     ex->masks.release(); ex->cams.release(); ex->cam_of_image.release(); ex->raw.release(); ex->node_of.release();
     ex->raw_count.release(); ex->sel_count.release(); ex->status.release(); ex->counts.release(); ex->sel_xys.release();
     ex->kps.release(); ex->desc.release(); ex->dmask.release();
-    ex->match_idx.release(); ex->match_dist.release();
+    ex->match_idx.release(); ex->match_dist.release(); ex->lut_coef.release(); ex->luts.release();
     for (int i = 0; i < 4; ++i) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
     if (ex->stream) cudaStreamDestroy(ex->stream);
     delete ex;
