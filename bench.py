@@ -179,7 +179,9 @@ def main():
     # each rank owns its own temporal chunk of the stream (weak scaling: per-GPU work fixed)
     images = make_stream(cams, F, 1000 + 97 * rank)                          # [F,3,H,W]
     host_images = torch.from_numpy(images).pin_memory()
-    dev_images = host_images.to(dev, non_blocking=True).view(B, H, W).contiguous()
+    PITCH = (W + 63) // 64 * 64                                                # 16-byte aligned rows: K1 stages with 128-bit loads
+    dev_images = torch.zeros((B, H, PITCH), dtype=torch.uint8, device=dev)
+    dev_images[:, :, :W] = host_images.to(dev, non_blocking=True).view(B, H, W)
 
     ex = api.mdBRIEFextractorOct(nfeatures=NFEATURES, nlevels=NLEVELS, do_dBrief=True, learnMasks=True)
     cap, ds = ex.capacity, 32
@@ -197,7 +199,7 @@ def main():
     stream = torch.cuda.Stream(dev)
 
     def step():
-        ex.extract_batch_device(dev_images, masks, cams, coi, out=out, stream=stream)
+        ex.extract_batch_device(dev_images, masks, cams, coi, out=out, stream=stream, width=W)
         api.match_stream_device(out["desc"], out["dmask"], out["counts"], F, N_CAMS, K=K_MATCH, out=(midx, mdist), stream=stream)
         if world > 1:
             dist.all_gather_into_tensor(gathered, packed)

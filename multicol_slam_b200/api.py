@@ -153,12 +153,14 @@ class mdBRIEFextractorOct:
                                        _p(desc), _p(dmask), _p(counts), cap))
         return kps, desc, dmask, counts
 
-    def extract_batch_device(self, images_t, masks, cams, cam_of_image, out=None, stream=None):
-        """torch CUDA tensors in/out (plumbing only): images_t [B,H,W] uint8 cuda.  Returns dict of cuda tensors
-        {kps [B,cap,7] int32-view, desc [B,cap,ds], dmask, counts [B]}; asynchronous on `stream` when given."""
+    def extract_batch_device(self, images_t, masks, cams, cam_of_image, out=None, stream=None, width=None):
+        """torch CUDA tensors in/out (plumbing only): images_t [B,H,P] uint8 cuda, P = row pitch >= width (a 16-byte
+        aligned pitch lets K1 use 128-bit loads).  Returns dict of cuda tensors {kps [B,cap,7] int32-view,
+        desc [B,cap,ds], dmask, counts [B]}; asynchronous on `stream` when given."""
         import torch
         assert images_t.is_cuda and images_t.dtype == torch.uint8 and images_t.is_contiguous()
-        B, H, W = images_t.shape
+        B, H, P = images_t.shape
+        W = P if width is None else width
         cap, ds = self.info.capacity, self.info.desc_size
         dev = images_t.device
         if out is None:
@@ -170,7 +172,7 @@ class mdBRIEFextractorOct:
         coi = np.ascontiguousarray(cam_of_image, np.int32)
         ocs = (Ocam * len(cams))(*[as_ocam(c) for c in cams])
         st = C.c_void_p(stream.cuda_stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream)
-        _check(lib().mcs_extract_batch_device(self._h, B, C.c_void_p(images_t.data_ptr()), W, H, W, _p(masks), ocs, len(cams),
+        _check(lib().mcs_extract_batch_device(self._h, B, C.c_void_p(images_t.data_ptr()), W, H, P, _p(masks), ocs, len(cams),
                                               _p(coi), C.c_void_p(out["kps"].data_ptr()), C.c_void_p(out["desc"].data_ptr()),
                                               C.c_void_p(out["dmask"].data_ptr()), C.c_void_p(out["counts"].data_ptr()), cap, st))
         return out

@@ -484,14 +484,16 @@ int mcs_extract_batch(mcs_extractor* ex, int32_t n_images, const uint8_t* images
     CK(cudaSetDevice(ex->device));
     cudaStream_t st = ex->stream;
     const int ds = ex->p.desc_size;
-    const size_t img_bytes = (size_t)stride * height;
+    // device staging with a 64-byte-aligned pitch so that K1 can use 128-bit loads
+    const int dpitch = (width + 63) & ~63;
+    const size_t img_bytes = (size_t)dpitch * height;
     CK(ex->in_images.ensure(img_bytes * n_images + 256));
     CK(ex->kps.ensure((size_t)n_images * capacity));
     CK(ex->desc.ensure((size_t)n_images * capacity * ds));
     CK(ex->dmask.ensure((size_t)n_images * capacity * ds));
     CK(ex->counts.ensure(n_images));
-    CK(cudaMemcpyAsync(ex->in_images.p, images, img_bytes * n_images, cudaMemcpyHostToDevice, st));
-    int rc = run_pipeline(ex, n_images, ex->in_images.p, width, height, stride, masks, cams, n_cams, cam_of_image, ex->kps.p,
+    CK(cudaMemcpy2DAsync(ex->in_images.p, dpitch, images, stride, width, (size_t)height * n_images, cudaMemcpyHostToDevice, st));
+    int rc = run_pipeline(ex, n_images, ex->in_images.p, width, height, dpitch, masks, cams, n_cams, cam_of_image, ex->kps.p,
                           ex->desc.p, ex->dmask.p, ex->counts.p, capacity, st);
     if (rc) return rc;
     CK(cudaMemcpyAsync(counts_out, ex->counts.p, sizeof(int) * n_images, cudaMemcpyDeviceToHost, st));
@@ -613,7 +615,8 @@ int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams
     CK(cudaSetDevice(ex->device));
     cudaStream_t st = ex->stream;
     const int n_images = n_frames * n_cams, ds = ex->p.desc_size;
-    const size_t img_bytes = (size_t)stride * height;
+    const int dpitch = (width + 63) & ~63;
+    const size_t img_bytes = (size_t)dpitch * height;
     std::vector<int> coi(n_images);
     for (int i = 0; i < n_images; ++i) coi[i] = i % n_cams;
     CK(ex->in_images.ensure(img_bytes * n_images + 256));
@@ -623,8 +626,8 @@ int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams
     CK(ex->counts.ensure(n_images));
     CK(ex->match_idx.ensure((size_t)n_images * capacity * K));
     CK(ex->match_dist.ensure((size_t)n_images * capacity * K));
-    CK(cudaMemcpyAsync(ex->in_images.p, images, img_bytes * n_images, cudaMemcpyHostToDevice, st));
-    int rc = run_pipeline(ex, n_images, ex->in_images.p, width, height, stride, masks, cams, n_cams, coi.data(), ex->kps.p,
+    CK(cudaMemcpy2DAsync(ex->in_images.p, dpitch, images, stride, width, (size_t)height * n_images, cudaMemcpyHostToDevice, st));
+    int rc = run_pipeline(ex, n_images, ex->in_images.p, width, height, dpitch, masks, cams, n_cams, coi.data(), ex->kps.p,
                           ex->desc.p, ex->dmask.p, ex->counts.p, capacity, st);
     if (rc) return rc;
     rc = mcs_match_stream_device(ex->desc.p, ex->p.learn_masks ? ex->dmask.p : nullptr, ex->counts.p, n_frames, n_cams, capacity, ds, K,

@@ -14,7 +14,7 @@ constexpr int kMaxLevels = MCS_MAX_LEVELS;
 constexpr int kTW = 64, kTH = 32, kHalo = 4;
 constexpr int kTileW = kTW + 2 * kHalo;     // 72
 constexpr int kTileH = kTH + 2 * kHalo;     // 40
-constexpr int kSrcW = 160, kSrcH = 88;      // staged source region, enough for scale factors <= 2
+constexpr int kSrcH = 88;                   // staged source rows, enough for scale factors <= 2
 constexpr int kMaxNodes = 2048;             // octree nodes alive at once (>= max quota + 3)
 
 // Per-level geometry + look-up tables (device pointers into one blob built by the host).

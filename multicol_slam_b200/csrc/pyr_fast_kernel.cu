@@ -1,0 +1,261 @@
+// pyr_fast_kernel.cu -- K1: per pyramid level, ONE fused kernel
+//     resize(level l-1 -> l)  +  5x5 box blur  +  FAST-9/16 score  +  per-cell 3x3 NMS  +  mirror-mask filter
+// (ref src/mdBRIEFextractorOct.cpp:1158-1201 ComputePyramid, :863-949 cell loop, :1301 boxFilter; OpenCV
+// resize / boxFilter / FAST arithmetic restated in SURVEY.md Appendix A.1 / A.3 / A.5).
+//
+// One CTA owns a 64x32 tile of level l.  The source region of level l-1 is staged in shared memory with 128-bit
+// loads, the tile (+4 px ring, REFLECT_101 at the image border) is resized once and kept in three shared forms:
+// bytes (for the stores) and two 16-bit-per-pixel copies offset by one pixel, so that ANY horizontally adjacent
+// pixel pair is one aligned 32-bit word.  Blur and FAST then run on pixel PAIRS with the packed 16x2 integer
+// SIMD of sm_100a (VIADD.16x2, VIMNMX3.S16x2):
+//   * box blur: 5 packed loads + 4 packed adds give the horizontal 5-sums of two pixels;
+//   * FAST: E_k = ring_k - centre (packed), 9-arc minima / maxima by two 3-input min (max) levels
+//     (M3_k = min3(E_k,E_k+1,E_k+2), M9_k = min3(M3_k,M3_k+3,M3_k+6)), branch-free exact cornerScore for every
+//     pixel pair: score = max over arcs of max(min9(E), -max9(E)) - 1, corner iff that maximum exceeds the threshold.
+// The kernel is bound by integer issue rate, not by HBM: ~100 thread-instructions per pixel
+// against ~2.5 bytes of DRAM traffic.
+#include "kernels.h"
+#include "mcs_common.cuh"
+
+namespace mcs {
+
+constexpr int kThreads = 256;
+constexpr int kSrcWB = 176;                 // staged source row stride (bytes, multiple of 16)
+constexpr int kT8S = 80;                    // byte tile row stride
+constexpr int kT16S = 72;                   // 16-bit tile row stride (elements)
+constexpr int kScoreS = 68;                 // score tile row stride (66 used)
+constexpr int kMaxTileCorners = kTW * kTH / 4;
+
+__device__ __forceinline__ unsigned vneg2(unsigned a) { return __vadd2(~a, 0x00010001u); }
+
+// packed cornerScore<16> margin of a pixel pair: C = centre pair, R[k] = ring pairs -> max over the 16 arcs of
+// max(min9(R-C), min9(C-R)) per 16-bit lane (signed)
+__device__ __forceinline__ unsigned fast_margin2(unsigned C, const unsigned (&R)[16]) {
+    const unsigned NC = vneg2(C);
+    unsigned E[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) E[k] = __vadd2(R[k], NC);
+    unsigned mn3[16], mx3[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        mn3[k] = __vimin3_s16x2(E[k], E[(k + 1) & 15], E[(k + 2) & 15]);
+        mx3[k] = __vimax3_s16x2(E[k], E[(k + 1) & 15], E[(k + 2) & 15]);
+    }
+    unsigned mn9[16], mx9[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        mn9[k] = __vimin3_s16x2(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]);
+        mx9[k] = __vimax3_s16x2(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]);
+    }
+    unsigned bright = __vimax3_s16x2(mn9[0], mn9[1], mn9[2]);
+    unsigned darkn = __vimin3_s16x2(mx9[0], mx9[1], mx9[2]);
+#pragma unroll
+    for (int k = 3; k < 15; k += 2) {
+        bright = __vimax3_s16x2(bright, mn9[k], mn9[k + 1]);
+        darkn = __vimin3_s16x2(darkn, mx9[k], mx9[k + 1]);
+    }
+    bright = __vmaxs2(bright, mn9[15]);
+    darkn = __vmins2(darkn, mx9[15]);
+    return __vmaxs2(bright, vneg2(darkn));
+}
+
+__global__ void __launch_bounds__(kThreads)
+pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int fast_th, const int src_aligned,
+                const uint8_t* __restrict__ src, const size_t src_img_bytes,
+                uint8_t* __restrict__ dst, uint8_t* __restrict__ dst_blur,
+                const uint8_t* __restrict__ mask0, const int mask_w, const size_t mask_bytes,
+                const int* __restrict__ cam_of_image,
+                uint32_t* __restrict__ raw, const size_t raw_img_stride, int* __restrict__ raw_count) {
+    __shared__ __align__(16) uint8_t s_src[kSrcH * kSrcWB];
+    __shared__ __align__(16) uint8_t s_t8[kTileH * kT8S];
+    __shared__ __align__(16) uint16_t s_a0[kTileH * kT16S];          // s_a0[y][x]   = px(x)
+    __shared__ __align__(16) uint16_t s_a1[kTileH * kT16S];          // s_a1[y][i]   = px(i+1)
+    __shared__ __align__(16) uint32_t s_h[(kTH + 4) * (kTW / 2)];    // packed horizontal 5-sums of pixel pairs
+    __shared__ __align__(16) uint8_t s_score[(kTH + 2) * kScoreS];
+    __shared__ int16_t s_xs0[kTileW], s_xs1[kTileW], s_xa0[kTileW], s_xa1[kTileW];
+    __shared__ int16_t s_ys0[kTileH], s_ys1[kTileH], s_yb0[kTileH], s_yb1[kTileH];
+    __shared__ int16_t s_cellx[kTW + 2], s_celly[kTH + 2];
+    __shared__ uint32_t s_list[kMaxTileCorners];
+    __shared__ int s_n, s_base;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int b = blockIdx.z;
+    const int X0 = blockIdx.x * kTW, Y0 = blockIdx.y * kTH;
+    const uint8_t* simg = src + (size_t)b * src_img_bytes;
+
+    // output-space range needed by this tile; after REFLECT_101 everything lies inside it
+    const int xa = max(X0 - kHalo, 0), xb = min(X0 + kTW + kHalo, g.w) - 1;
+    const int ya = max(Y0 - kHalo, 0), yb = min(Y0 + kTH + kHalo, g.h) - 1;
+    const int sx_lo = g.xofs[xa], sx_hi = min(g.xofs[xb] + 1, g.sw - 1);
+    const int sy_lo = min(max((int)g.yofs[ya], 0), g.sh - 1), sy_hi = min(max(g.yofs[yb] + 1, 0), g.sh - 1);
+    const int sx_base = sx_lo & ~15;
+    if (tid == 0) s_n = 0;
+
+    // ---- per-tile slices of the resize / cell tables ----
+    if (tid < kTileW) {
+        // rows/columns further than the ring beyond the image are never consumed: clamp them into the staged range
+        const int rx = min(max(reflect101(X0 - kHalo + tid, g.w), xa), xb);
+        const int sx = g.xofs[rx];
+        s_xs0[tid] = (int16_t)(sx - sx_base);
+        s_xs1[tid] = (int16_t)(min(sx + 1, g.sw - 1) - sx_base);
+        s_xa0[tid] = g.xa0[rx]; s_xa1[tid] = g.xa1[rx];
+    } else if (tid >= 96 && tid < 96 + kTileH) {
+        const int t = tid - 96;
+        const int ry = min(max(reflect101(Y0 - kHalo + t, g.h), ya), yb);
+        const int sy = g.yofs[ry];
+        s_ys0[t] = (int16_t)(min(max(sy, 0), g.sh - 1) - sy_lo);
+        s_ys1[t] = (int16_t)(min(max(sy + 1, 0), g.sh - 1) - sy_lo);
+        s_yb0[t] = g.yb0[ry]; s_yb1[t] = g.yb1[ry];
+    } else if (tid >= 144 && tid < 144 + kTW + 2) {
+        const int x = X0 - 1 + tid - 144;
+        s_cellx[tid - 144] = (x >= 0 && x < g.w) ? g.cellx[x] : (int16_t)-1;
+    }
+    if (tid < kTH + 2) {
+        const int y = Y0 - 1 + tid;
+        s_celly[tid] = (y >= 0 && y < g.h) ? g.celly[y] : (int16_t)-1;
+    }
+    // ---- stage the source rows: 16-byte chunks, one warp per row ----
+    {
+        const int nrows = sy_hi - sy_lo + 1;
+        if (src_aligned) {
+            const int nchunks = ((sx_hi - sx_base) >> 4) + 1;
+            for (int r = wid; r < nrows; r += kThreads / 32)
+                for (int c = lane; c < nchunks; c += 32)
+                    *(uint4*)(s_src + r * kSrcWB + c * 16) =
+                        __ldg((const uint4*)(simg + (size_t)(sy_lo + r) * g.spitch + sx_base + c * 16));
+        } else {   // caller-supplied image with an unaligned base or stride (level 0 only)
+            const int nb = sx_hi - sx_base + 1;
+            for (int r = wid; r < nrows; r += kThreads / 32)
+                for (int c = lane; c < nb; c += 32) {
+                    const int x = sx_base + c;
+                    s_src[r * kSrcWB + c] = x < g.sw ? simg[(size_t)(sy_lo + r) * g.spitch + x] : (uint8_t)0;
+                }
+        }
+    }
+    __syncthreads();
+
+    // ---- bilinear resize (OpenCV 11-bit fixed point) into the three tile forms; a thread owns a pixel-pair column ----
+    if (tid < (kTileW / 2) * 7) {
+        const int pc = tid % (kTileW / 2), rg = tid / (kTileW / 2);      // 36 pair columns x 7 row groups
+        const int tx = 2 * pc;
+        const int xs00 = s_xs0[tx], xs01 = s_xs1[tx], xs10 = s_xs0[tx + 1], xs11 = s_xs1[tx + 1];
+        const int a00 = s_xa0[tx], a01 = s_xa1[tx], a10 = s_xa0[tx + 1], a11 = s_xa1[tx + 1];
+        for (int ty = rg; ty < kTileH; ty += 7) {
+            const uint8_t* r0 = s_src + s_ys0[ty] * kSrcWB;
+            const uint8_t* r1 = s_src + s_ys1[ty] * kSrcWB;
+            const int b0 = s_yb0[ty], b1 = s_yb1[ty];
+            const int h00 = r0[xs00] * a00 + r0[xs01] * a01, h01 = r1[xs00] * a00 + r1[xs01] * a01;
+            const int h10 = r0[xs10] * a10 + r0[xs11] * a11, h11 = r1[xs10] * a10 + r1[xs11] * a11;
+            int v0 = (((b0 * (h00 >> 4)) >> 16) + ((b1 * (h01 >> 4)) >> 16) + 2) >> 2;
+            int v1 = (((b0 * (h10 >> 4)) >> 16) + ((b1 * (h11 >> 4)) >> 16) + 2) >> 2;
+            v0 = min(max(v0, 0), 255); v1 = min(max(v1, 0), 255);
+            *(uint16_t*)(s_t8 + ty * kT8S + tx) = (uint16_t)(v0 | (v1 << 8));
+            *(uint32_t*)(s_a0 + ty * kT16S + tx) = (uint32_t)v0 | ((uint32_t)v1 << 16);
+            if (tx > 0) s_a1[ty * kT16S + tx - 1] = (uint16_t)v0;
+            s_a1[ty * kT16S + tx] = (uint16_t)v1;
+        }
+    }
+    __syncthreads();
+
+    uint8_t* dimg = dst + (size_t)b * g.img_bytes;
+    uint8_t* bimg = dst_blur + (size_t)b * g.img_bytes;
+    // ---- (a) store the unblurred tile, 4 px per thread ----
+    for (int i = tid; i < kTH * (kTW / 4); i += kThreads) {
+        const int y = i >> 4, x4 = (i & 15) * 4;
+        if (Y0 + y < g.h && X0 + x4 < g.pitch)
+            *(uint32_t*)(dimg + (size_t)(Y0 + y) * g.pitch + X0 + x4) = *(const uint32_t*)(s_t8 + (y + kHalo) * kT8S + x4 + kHalo);
+    }
+    // ---- (b) packed horizontal 5-sums of pixel pairs (rows Y0-2 .. Y0+33) ----
+    for (int i = tid; i < (kTH + 4) * (kTW / 2); i += kThreads) {
+        const int y = i >> 5, j = i & 31;
+        const uint32_t* w0 = (const uint32_t*)(s_a0 + (y + kHalo - 2) * kT16S) + (kHalo / 2 + j);   // pair (x, x+1), x = tile col 4+2j
+        const uint32_t* w1 = (const uint32_t*)(s_a1 + (y + kHalo - 2) * kT16S) + (kHalo / 2 + j);   // pair (x+1, x+2)
+        s_h[i] = __vadd2(__vadd2(__vadd2(w0[-1], w1[-1]), __vadd2(w0[0], w1[0])), w0[1]);
+    }
+    // ---- (c) FAST margins of pixel pairs on the tile + 1 ring; pairs start at tile column 3 (odd) ----
+    for (int i = tid; i < (kTH + 2) * ((kTW + 2) / 2); i += kThreads) {
+        const int y = i / ((kTW + 2) / 2), j = i - y * ((kTW + 2) / 2);
+        const int sx = 2 * j;                                   // score-tile column of the first pixel of the pair
+        const bool in0 = s_cellx[sx] >= 0, in1 = s_cellx[sx + 1] >= 0, iny = s_celly[y] >= 0;
+        unsigned out = 0;
+        if (iny && (in0 || in1)) {
+            // centre pair (px, px+1) with px = tile col 3+2j (odd) -> word j+1 of the odd copy; even dx -> odd copy, odd dx -> even copy
+            const uint32_t* o = (const uint32_t*)(s_a1 + (y + kHalo - 1) * kT16S) + (j + 1);
+            const uint32_t* e = (const uint32_t*)(s_a0 + (y + kHalo - 1) * kT16S) + (j + 2);   // pair starting at px+1
+            constexpr int S = kT16S / 2;                         // row stride in words
+            const unsigned C = o[0];
+            unsigned R[16];
+            R[0] = o[3 * S];       R[1] = e[3 * S];        R[2] = o[2 * S + 1];   R[3] = e[S + 1];
+            R[4] = e[1];           R[5] = e[-S + 1];       R[6] = o[-2 * S + 1];  R[7] = e[-3 * S];
+            R[8] = o[-3 * S];      R[9] = e[-3 * S - 1];   R[10] = o[-2 * S - 1]; R[11] = e[-S - 2];
+            R[12] = e[-2];         R[13] = e[S - 2];       R[14] = o[2 * S - 1];  R[15] = e[3 * S - 1];
+            const unsigned m = fast_margin2(C, R);
+            const int m0 = (int)(short)(m & 0xFFFFu), m1 = (int)(short)(m >> 16);
+            const unsigned s0 = (in0 && m0 > fast_th) ? (unsigned)(m0 - 1) : 0u;
+            const unsigned s1 = (in1 && m1 > fast_th) ? (unsigned)(m1 - 1) : 0u;
+            out = s0 | (s1 << 8);
+        }
+        *(uint16_t*)(s_score + y * kScoreS + sx) = (uint16_t)out;
+    }
+    __syncthreads();
+
+    // ---- (d) blurred tile: vertical 5-sum of the packed row sums, (S+12)/25, 4 px per thread ----
+    for (int i = tid; i < kTH * (kTW / 4); i += kThreads) {
+        const int y = i >> 4, q = i & 15;
+        if (Y0 + y < g.h && X0 + 4 * q < g.pitch) {
+            const uint32_t* h = s_h + y * (kTW / 2) + 2 * q;
+            const unsigned p0 = __vadd2(__vadd2(__vadd2(h[0], h[32]), __vadd2(h[64], h[96])), h[128]);
+            const unsigned p1 = __vadd2(__vadd2(__vadd2(h[1], h[33]), __vadd2(h[65], h[97])), h[129]);
+            // (S + 12) / 25 == ((S + 12) * 5243) >> 17 for S <= 6375 (checked exhaustively in tests)
+            const unsigned o0 = (((p0 & 0xFFFFu) + 12u) * 5243u) >> 17, o1 = (((p0 >> 16) + 12u) * 5243u) >> 17;
+            const unsigned o2 = (((p1 & 0xFFFFu) + 12u) * 5243u) >> 17, o3 = (((p1 >> 16) + 12u) * 5243u) >> 17;
+            *(uint32_t*)(bimg + (size_t)(Y0 + y) * g.pitch + X0 + 4 * q) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
+        }
+    }
+    // ---- (e) per-cell 3x3 non-max suppression, mask filter, tile-local compaction ----
+    const uint8_t* m0p = mask0 + (size_t)cam_of_image[b] * mask_bytes;
+    for (int i = tid; i < kTH * kTW; i += kThreads) {
+        const int y = i >> 6, x = i & 63;
+        const uint8_t* sc = s_score + (y + 1) * kScoreS + x + 1;
+        const int s = sc[0];
+        if (s == 0) continue;
+        const int cx = s_cellx[x + 1], cy = s_celly[y + 1];
+        bool keep = true;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                if (dx == 0 && dy == 0) continue;
+                const bool same = (s_cellx[x + 1 + dx] == cx) && (s_celly[y + 1 + dy] == cy);
+                const int sn = same ? sc[dy * kScoreS + dx] : 0;
+                keep = keep && (s > sn);
+            }
+        if (!keep) continue;
+        const int gx = X0 + x, gy = Y0 + y;
+        if (m0p[(size_t)g.my0[gy] * mask_w + g.mx0[gx]] == 0) continue;
+        const int pos = atomicAdd(&s_n, 1);
+        s_list[pos] = pack_corner(gx, gy, s);
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (n == 0) return;
+    if (tid == 0) s_base = atomicAdd(&raw_count[b * nlevels + level], n);
+    __syncthreads();
+    uint32_t* rlist = raw + (size_t)b * raw_img_stride + g.raw_off;
+    for (int i = tid; i < n; i += kThreads) {
+        const int pos = s_base + i;
+        if (pos < g.raw_cap) rlist[pos] = s_list[i];
+    }
+}
+
+void launch_pyr_fast(const PyramidGeom& G, int level, int n_images, const uint8_t* src, size_t src_img_bytes,
+                     uint8_t* dst, uint8_t* dst_blur, const uint8_t* mask0, int mask_w, size_t mask_bytes,
+                     const int* cam_of_image, uint32_t* raw, int* raw_count, cudaStream_t st) {
+    const LevelGeom& g = G.lv[level];
+    dim3 grid(g.tiles_x, g.tiles_y, n_images);
+    const int aligned = (((uintptr_t)src & 15) == 0 && (g.spitch & 15) == 0 && (src_img_bytes & 15) == 0) ? 1 : 0;
+    pyr_fast_kernel<<<grid, kThreads, 0, st>>>(g, level, G.nlevels, G.fast_threshold, aligned, src, src_img_bytes, dst, dst_blur,
+                                               mask0, mask_w, mask_bytes, cam_of_image, raw, G.raw_total, raw_count);
+}
+
+}  // namespace mcs

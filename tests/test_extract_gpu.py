@@ -169,3 +169,37 @@ def test_full_size_properties(api, cams):
     for i in range(B):
         assert kps[i, :counts[i]].tobytes() == kps2[i, :counts[i]].tobytes()
         assert np.array_equal(desc[i, :counts[i]], desc2[i, :counts[i]])
+
+
+def test_device_api_pitched_and_unaligned(api, oa, cams):
+    """mcs_extract_batch_device: 16-byte aligned pitch (128-bit staging loads) and an unaligned caller image
+    (byte staging path) give the same bytes as the oracle."""
+    import torch
+    from multicol_slam_b200 import synth
+    imgs = np.stack([synth.frame(cams[c], 50 + c) for c in range(3)])
+    masks = np.stack([synth.mirror_mask(c) for c in cams])
+    ex = api.mdBRIEFextractorOct(nfeatures=700, do_dBrief=True, learnMasks=True)
+    oe = oa.OracleExtractor(nfeatures=700, do_dbrief=True, learn_masks=True)
+    ref = [oe.extract(imgs[c], masks[c], cams[c]) for c in range(3)]
+    dev = torch.device("cuda", 0)
+    tight = torch.from_numpy(imgs).to(dev)                                   # stride 754: unaligned rows
+    pitched = torch.zeros((3, 480, 768), dtype=torch.uint8, device=dev)
+    pitched[:, :, :754] = tight
+    st = torch.cuda.Stream(dev)
+    for t, w in ((tight, None), (pitched, 754)):
+        with torch.cuda.stream(st):
+            out = ex.extract_batch_device(t, masks, cams, [0, 1, 2], stream=st, width=w)
+        torch.cuda.synchronize(dev)
+        counts = out["counts"].cpu().numpy()
+        kps = out["kps"].cpu().numpy().view(api.KEYPOINT_DTYPE).reshape(3, -1)
+        for c in range(3):
+            n = counts[c]
+            assert n == len(ref[c][0]) and kps[c, :n].tobytes() == ref[c][0].tobytes()
+            assert np.array_equal(out["desc"][c, :n].cpu().numpy(), ref[c][1])
+            assert np.array_equal(out["dmask"][c, :n].cpu().numpy(), ref[c][2])
+
+
+def test_div25_magic():
+    # K1's blur uses ((S+12)*5243)>>17 for (S+12)/25
+    s = np.arange(0, 25 * 255 + 1, dtype=np.int64)
+    assert np.array_equal(((s + 12) * 5243) >> 17, (s + 12) // 25)
