@@ -31,7 +31,7 @@
 namespace mcs {
 
 __constant__ signed char c_pairs[2048];          // learned_pattern_64_ORB (ref include/mdBRIEFextractorOct.h:44-47)
-__constant__ signed char c_disc_u[848], c_disc_v[848];   // the 845 (u,v) offsets of the IC_Angle disc
+__constant__ signed char c_disc_u[848], c_disc_v[848];   // c_disc_u[0..16] = umax[] of the IC_Angle disc (ref :187-202); rest unused
 
 // cv::fastAtan2, evaluated without FMA
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
@@ -75,7 +75,10 @@ __device__ __forceinline__ bool lut_R(const DistortLut& L, double r, double& g) 
     return true;
 }
 
-constexpr int kDescWarps = 8;
+constexpr int kDescWarps = 4;
+constexpr int kPatchR = 25;                       // staged patch: rows/cols ky/kx -25 .. +25 (keypoints are >= 25 px inside the ROI)
+constexpr int kPatchS = 64;                       // bytes per staged patch row (4-byte aligned start + 51 columns)
+constexpr int kLutWin = 52;                       // staged LUT intervals around the keypoint's undistorted radius
 
 // Rare path: one pattern of one keypoint with the reference's exact operation sequence (two projection passes;
 // per-lane partial sums + butterfly: within ~1e-13 of the reference's sequential sum).
@@ -118,26 +121,44 @@ __device__ __noinline__ unsigned exact_pattern(const mcs_ocam* cam, const char2*
     return out;
 }
 
+// ORB rotation (ref :285-301) and generic sampling straight from global memory; used for ORB when an offset leaves
+// the staged patch (never for sane inputs) -- keeps the reference's read semantics (blurred ROI / reflected ring).
+template <int PPL>
+__device__ __noinline__ unsigned orb_pattern_global(const char2* s_pat, double ca, double sa, int lane, const uint8_t* bimg,
+                                                    const uint8_t* uimg, const LevelGeom* g, int kx, int ky) {
+    unsigned out = 0;
+    for (int j = 0; j < PPL; j += 2) {
+        int smp[2];
+        for (int e = 0; e < 2; ++e) {
+            const char2 pp = s_pat[(j + e) * 32 + lane];
+            const double px = (double)pp.x, py = (double)pp.y;
+            smp[e] = sample_px(bimg, uimg, *g, ky + __double2int_rn(px * sa + py * ca), kx + __double2int_rn(px * ca - py * sa));
+        }
+        out |= (unsigned)(smp[0] < smp[1]) << (j >> 1);
+    }
+    return out;
+}
+
 template <int PPL /* pattern points per lane: 16 for descSize <= 32, 32 for descSize 64 */>
-__global__ void __launch_bounds__(kDescWarps * 32, 2)
+__global__ void __launch_bounds__(kDescWarps * 32, 4)
 describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, const mcs_ocam* __restrict__ cams,
                 const DistortLut* __restrict__ luts, const int* __restrict__ cam_of_image,
                 const uint32_t* __restrict__ sel_xys, const int* __restrict__ sel_count,
                 mcs_keypoint* __restrict__ kps_out, uint8_t* __restrict__ desc_out, uint8_t* __restrict__ dmask_out,
                 int* __restrict__ counts_out, const int capacity, const int n_images) {
     __shared__ char2 s_pat[PPL * 32];            // [j][lane] : point 16*byte + k with byte = lane + 32*(j/16), k = j%16
-    __shared__ char2 s_disc[848];
     __shared__ mcs_ocam s_cam[kDescWarps];
+    __shared__ __align__(16) uint8_t s_patch[kDescWarps][(2 * kPatchR + 1) * kPatchS];
+    __shared__ __align__(16) double s_lut[kDescWarps][kLutWin * 6];
     const int ds = geom->desc_size;
     for (int i = threadIdx.x; i < PPL * 32; i += blockDim.x) {
         const int j = i >> 5, ln = i & 31;
         const int byte = ln + 32 * (j >> 4), pt = 16 * byte + (j & 15);
         s_pat[i] = byte < ds ? make_char2(c_pairs[2 * pt], c_pairs[2 * pt + 1]) : make_char2(0, 0);
     }
-    for (int i = threadIdx.x; i < 848; i += blockDim.x) s_disc[i] = make_char2(c_disc_u[i], c_disc_v[i]);
     __syncthreads();
 
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int sel_total = geom->sel_total;
     const int b = warp_global / sel_total;
@@ -163,16 +184,38 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
     const int kx = corner_x(c), ky = corner_y(c);
     const uint8_t* uimg = args.lvl[level] + (size_t)b * g.img_bytes;
     const uint8_t* bimg = args.blur[level] + (size_t)b * g.img_bytes;
+    const int pitch = g.pitch;
 
-    // ---- IC_Angle: integer moments over the 845-pixel disc (sum order is irrelevant for integers) ----
+    // ---- stage the blurred 51x51 patch: 2 rows per warp instruction, 15 aligned words per row ----
+    uint8_t* patch = s_patch[wib];
+    const int x0 = (kx - kPatchR) & ~3;                    // >= 0: keypoints lie >= 25 px inside the level
+    {
+        const int half = lane >> 4, w = lane & 15;
+        for (int r = half; r < 2 * kPatchR + 1; r += 2)
+            if (w < 15)
+                *(uint32_t*)(patch + r * kPatchS + 4 * w) =
+                    __ldg((const uint32_t*)(bimg + (size_t)(ky - kPatchR + r) * pitch + x0) + w);
+    }
+    const int pofs = kPatchR * kPatchS + (kx - x0);        // patch byte offset of the keypoint itself
+
+    // ---- IC_Angle (ref :221-248): integer moments over the 845-pixel disc, lane = column u = lane-16 (+ u = 16) ----
     int m10 = 0, m01 = 0;
     {
-        const uint8_t* ctr = uimg + (size_t)ky * g.pitch + kx;
-        for (int i = lane; i < 845; i += 32) {
-            const char2 uv = s_disc[i];
-            const int val = ctr[uv.y * g.pitch + uv.x];
-            m10 += uv.x * val;
-            m01 += uv.y * val;
+        const uint8_t* ctr = uimg + (size_t)ky * pitch + kx;
+        const int u = lane - kHalfPatch;                    // -16 .. 15
+        const int au = u < 0 ? -u : u;
+        // |v| <= vmax(u): the disc is symmetric (umax table, ref :187-202); vmax(|u|) = umax[|u|]
+        const int vm = c_disc_u[au];                        // c_disc_u[0..16] doubles as umax[] (see upload_constants)
+        for (int v = -vm; v <= vm; ++v) {
+            const int val = ctr[v * pitch + u];
+            m10 += u * val;
+            m01 += v * val;
+        }
+        if (lane < 2 * c_disc_u[kHalfPatch] + 1) {          // column u = +16: rows |v| <= umax[16]
+            const int v = lane - c_disc_u[kHalfPatch];
+            const int val = ctr[v * pitch + kHalfPatch];
+            m10 += kHalfPatch * val;
+            m01 += v * val;
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
@@ -198,35 +241,56 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
     }
     constexpr int BPL = PPL / 16;                 // descriptor bytes per lane
     unsigned val[3][BPL];
+    __syncwarp();                                 // patch staged
     if (!dbrief) {
         // ---- ORB: rotatePattern (ref :285-301) ----
+        int ix[PPL], iy[PPL];
+        bool far = false;
 #pragma unroll
-        for (int bb = 0; bb < BPL; ++bb) {
-            unsigned v = 0;
+        for (int j = 0; j < PPL; ++j) {
+            const char2 pp = s_pat[j * 32 + lane];
+            const double px = (double)pp.x, py = (double)pp.y;
+            ix[j] = __double2int_rn(px * ca[0] - py * sa[0]);
+            iy[j] = __double2int_rn(px * sa[0] + py * ca[0]);
+            far |= (unsigned)(ix[j] + kPatchR) > 2u * kPatchR || (unsigned)(iy[j] + kPatchR) > 2u * kPatchR;
+        }
+        if (__any_sync(0xffffffffu, far)) {
+            const unsigned e = orb_pattern_global<PPL>(s_pat, ca[0], sa[0], lane, bimg, uimg, &g, kx, ky);
 #pragma unroll
-            for (int bit = 0; bit < 8; ++bit) {
-                int smp[2];
+            for (int bb = 0; bb < BPL; ++bb) val[0][bb] = (e >> (8 * bb)) & 0xFFu;
+        } else {
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const char2 pp = s_pat[(16 * bb + 2 * bit + e) * 32 + lane];
-                    const double px = (double)pp.x, py = (double)pp.y;
-                    const int ix = __double2int_rn(px * ca[0] - py * sa[0]);
-                    const int iy = __double2int_rn(px * sa[0] + py * ca[0]);
-                    smp[e] = sample_px(bimg, uimg, g, ky + iy, kx + ix);
+            for (int bb = 0; bb < BPL; ++bb) {
+                unsigned v = 0;
+#pragma unroll
+                for (int bit = 0; bit < 8; ++bit) {
+                    const int j0 = 16 * bb + 2 * bit;
+                    const int s0 = patch[pofs + iy[j0] * kPatchS + ix[j0]], s1 = patch[pofs + iy[j0 + 1] * kPatchS + ix[j0 + 1]];
+                    v |= (unsigned)(s0 < s1) << bit;
                 }
-                v |= (unsigned)(smp[0] < smp[1]) << bit;
+                val[0][bb] = v;
             }
-            val[0][bb] = v;
         }
     } else {
         // ---- dBRIEF / mdBRIEF: rotateAndDistortPattern (ref :250-283) ----
-        const int wib = threadIdx.x >> 5;
         if (lane < (int)(sizeof(mcs_ocam) / 8)) ((double*)&s_cam[wib])[lane] = ((const double*)&cams[ci])[lane];
         __syncwarp();
         const mcs_ocam& cam = s_cam[wib];
         const DistortLut lut = luts[ci];
         double ukx, uky;   // undistortPointsOcam(pt.x*scale, pt.y*scale, a0)  (ref :1306-1317)
         cam_undistort(cam, (double)__fmul_rn((float)kx, scale), (double)__fmul_rn((float)ky, scale), cam.pol[0], ukx, uky);
+        // stage the window of the distortion table around the keypoint's undistorted radius
+        const double rk = sqrt(ukx * ukx + uky * uky);
+        int i0 = 0;
+        if (rk < (double)lut.n) i0 = max(0, min((int)rk - kLutWin / 2, lut.n - kLutWin));
+        double* wl = s_lut[wib];
+        for (int i = lane; i < kLutWin * 3; i += 32) {
+            const int iv = i / 3, part = i - iv * 3;
+            double2 cc = make_double2(0.0, 0.0);
+            if (i0 + iv < lut.n) cc = __ldg((const double2*)(lut.coef + (size_t)(i0 + iv) * 8) + part);
+            *(double2*)(wl + iv * 6 + 2 * part) = cc;
+        }
+        __syncwarp();
         const double inv_n = 1.0 / (double)(16 * ds);
         const bool lane_valid = (PPL == 32) || (lane < ds);      // descSize 16: lanes 16..31 own no byte
         for (int q = 0; q < npat; ++q) {
@@ -241,8 +305,15 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                 const double yr = px * sa[q] + py * ca[q] + uky;
                 const double s2 = fma(xr, xr, yr * yr);
                 const double rinv = rsqrt(s2), r = s2 * rinv;
-                double gg;
-                if (!lut_R(lut, r, gg)) { need_exact = lane_valid; gg = 0.0; }     // also catches s2 == 0 (r = NaN)
+                // R(r) from the staged window; anything outside it (or s2 == 0 -> NaN) takes the exact path
+                const int idx = (int)r - i0;
+                double gg = 0.0;
+                if (r >= (double)i0 && idx < kLutWin && (int)r < lut.n) {
+                    const double tau = fma(2.0, r - (double)(idx + i0), -1.0);
+                    const double* cf = wl + idx * 6;
+                    gg = cf[5];
+                    gg = fma(gg, tau, cf[4]); gg = fma(gg, tau, cf[3]); gg = fma(gg, tau, cf[2]); gg = fma(gg, tau, cf[1]); gg = fma(gg, tau, cf[0]);
+                } else need_exact = lane_valid;
                 gg *= rinv;
                 const double uu = xr * gg, vv = yr * gg;
                 us[j] = fma(uu, cam.c, fma(vv, cam.d, cam.u0));
@@ -254,11 +325,16 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                 su += __shfl_xor_sync(0xffffffffu, su, o);
                 sv += __shfl_xor_sync(0xffffffffu, sv, o);
             }
-            double mu = su * inv_n, mv = sv * inv_n;
+            const double mu = su * inv_n, mv = sv * inv_n;
+            int ix[PPL], iy[PPL];
 #pragma unroll
             for (int j = 0; j < PPL; ++j) {
                 const double du = us[j] - mu, dv = vs[j] - mv;
-                need_exact |= lane_valid && (fabs(fabs(du - rint(du)) - 0.5) < 1e-7 || fabs(fabs(dv - rint(dv)) - 0.5) < 1e-7);
+                ix[j] = __double2int_rn(du); iy[j] = __double2int_rn(dv);
+                // closer than 1e-7 px to a rounding tie, or outside the staged patch -> exact / generic path
+                const double fu = fabs(du - (double)ix[j]), fv = fabs(dv - (double)iy[j]);
+                need_exact |= lane_valid && (fu > 0.5 - 1e-7 || fv > 0.5 - 1e-7 ||
+                                             (unsigned)(ix[j] + kPatchR) > 2u * kPatchR || (unsigned)(iy[j] + kPatchR) > 2u * kPatchR);
             }
             if (__any_sync(0xffffffffu, need_exact)) {
                 const unsigned e = exact_pattern<PPL>(&cam, s_pat, ca[q], sa[q], ukx, uky, lane, ds, bimg, uimg, &g, kx, ky);
@@ -272,8 +348,7 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
 #pragma unroll
                 for (int bit = 0; bit < 8; ++bit) {
                     const int j0 = 16 * bb + 2 * bit;
-                    const int s0 = sample_px(bimg, uimg, g, ky + __double2int_rn(vs[j0] - mv), kx + __double2int_rn(us[j0] - mu));
-                    const int s1 = sample_px(bimg, uimg, g, ky + __double2int_rn(vs[j0 + 1] - mv), kx + __double2int_rn(us[j0 + 1] - mu));
+                    const int s0 = patch[pofs + iy[j0] * kPatchS + ix[j0]], s1 = patch[pofs + iy[j0 + 1] * kPatchS + ix[j0 + 1]];
                     v |= (unsigned)(s0 < s1) << bit;
                 }
                 val[q][bb] = v;

@@ -322,13 +322,18 @@ int upload_consts_once(int dev) {
         umax[v] = v0;
         ++v0;
     }
+    // the disc is symmetric in u and v, so umax[] gives both the row widths and the column heights
     signed char du[848] = {0}, dv[848] = {0};
     int n = 0;
-    for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
-        const int d = v == 0 ? kHalfPatch : umax[std::abs(v)];
-        for (int u = -d; u <= d; ++u) { du[n] = (signed char)u; dv[n] = (signed char)v; ++n; }
-    }
+    for (int v = -kHalfPatch; v <= kHalfPatch; ++v) n += 2 * (v == 0 ? kHalfPatch : umax[std::abs(v)]) + 1;
     if (n != 845) return fail(MCS_ERR_INVALID, "disc table size");
+    for (int v = 0; v <= kHalfPatch; ++v) {
+        du[v] = (signed char)(v == 0 ? kHalfPatch : umax[v]);
+        // symmetry check: column |u| = v must hold rows |v'| <= umax[v]
+        for (int w = 0; w <= kHalfPatch; ++w)
+            if ((w <= (v == 0 ? kHalfPatch : umax[v])) != (v <= (w == 0 ? kHalfPatch : umax[w])))
+                return fail(MCS_ERR_INVALID, "IC_Angle disc is not symmetric");
+    }
     CK(upload_constants(kPairs, du, dv));
     if (dev < 64) g_consts_uploaded[dev] = true;
     return MCS_OK;
