@@ -147,6 +147,7 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                 mcs_keypoint* __restrict__ kps_out, uint8_t* __restrict__ desc_out, uint8_t* __restrict__ dmask_out,
                 int* __restrict__ counts_out, const int capacity, const int n_images) {
     __shared__ char2 s_pat[PPL * 32];            // [j][lane] : point 16*byte + k with byte = lane + 32*(j/16), k = j%16
+    __shared__ __align__(16) double2 s_patd[PPL * 32];   // same, as doubles (int->double conversions run on the slow XU pipe)
     __shared__ mcs_ocam s_cam[kDescWarps];
     __shared__ __align__(16) uint8_t s_patch[kDescWarps][(2 * kPatchR + 1) * kPatchS];
     __shared__ __align__(16) double s_lut[kDescWarps][kLutWin * 6];
@@ -155,6 +156,7 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
         const int j = i >> 5, ln = i & 31;
         const int byte = ln + 32 * (j >> 4), pt = 16 * byte + (j & 15);
         s_pat[i] = byte < ds ? make_char2(c_pairs[2 * pt], c_pairs[2 * pt + 1]) : make_char2(0, 0);
+        s_patd[i] = make_double2((double)s_pat[i].x, (double)s_pat[i].y);
     }
     __syncthreads();
 
@@ -297,19 +299,22 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
             double us[PPL], vs[PPL];
             double su = 0.0, sv = 0.0;
             bool need_exact = false;
+            // round-to-nearest-even through the 1.5*2^52 trick: no F2I/I2F (XU pipe), same result as lrint
+            constexpr double kMagic = 6755399441055744.0;
 #pragma unroll
             for (int j = 0; j < PPL; ++j) {
-                const char2 pp = s_pat[j * 32 + lane];
-                const double px = (double)pp.x, py = (double)pp.y;
-                const double xr = px * ca[q] - py * sa[q] + ukx;
-                const double yr = px * sa[q] + py * ca[q] + uky;
+                const double2 pp = s_patd[j * 32 + lane];
+                const double xr = pp.x * ca[q] - pp.y * sa[q] + ukx;
+                const double yr = pp.x * sa[q] + pp.y * ca[q] + uky;
                 const double s2 = fma(xr, xr, yr * yr);
                 const double rinv = rsqrt(s2), r = s2 * rinv;
-                // R(r) from the staged window; anything outside it (or s2 == 0 -> NaN) takes the exact path
-                const int idx = (int)r - i0;
+                // R(r) from the staged window; anything outside it (or s2 == 0 -> NaN) takes the exact path.
+                // interval index = rn(r - 0.5): at an exact integer either neighbour is valid (tau = +-1)
+                const double tm = (r - 0.5) + kMagic;
+                const int idx = __double2loint(tm) - i0;
                 double gg = 0.0;
-                if (r >= (double)i0 && idx < kLutWin && (int)r < lut.n) {
-                    const double tau = fma(2.0, r - (double)(idx + i0), -1.0);
+                if (r >= 0.0 && r < (double)lut.n && idx >= 0 && idx < kLutWin) {
+                    const double tau = fma(2.0, r - (tm - kMagic), -1.0);
                     const double* cf = wl + idx * 6;
                     gg = cf[5];
                     gg = fma(gg, tau, cf[4]); gg = fma(gg, tau, cf[3]); gg = fma(gg, tau, cf[2]); gg = fma(gg, tau, cf[1]); gg = fma(gg, tau, cf[0]);
@@ -330,10 +335,11 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
 #pragma unroll
             for (int j = 0; j < PPL; ++j) {
                 const double du = us[j] - mu, dv = vs[j] - mv;
-                ix[j] = __double2int_rn(du); iy[j] = __double2int_rn(dv);
+                const double tu = du + kMagic, tv = dv + kMagic;
+                ix[j] = __double2loint(tu); iy[j] = __double2loint(tv);
                 // closer than 1e-7 px to a rounding tie, or outside the staged patch -> exact / generic path
-                const double fu = fabs(du - (double)ix[j]), fv = fabs(dv - (double)iy[j]);
-                need_exact |= lane_valid && (fu > 0.5 - 1e-7 || fv > 0.5 - 1e-7 ||
+                const double fu = fabs(du - (tu - kMagic)), fv = fabs(dv - (tv - kMagic));
+                need_exact |= lane_valid && (fu > 0.5 - 1e-7 || fv > 0.5 - 1e-7 || !(fabs(du) < 1e6) || !(fabs(dv) < 1e6) ||
                                              (unsigned)(ix[j] + kPatchR) > 2u * kPatchR || (unsigned)(iy[j] + kPatchR) > 2u * kPatchR);
             }
             if (__any_sync(0xffffffffu, need_exact)) {

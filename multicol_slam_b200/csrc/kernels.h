@@ -35,8 +35,9 @@ cudaError_t launch_describe(const PyramidGeom& G, const PyramidGeom* G_dev, int 
 cudaError_t launch_hamming_topk(const uint8_t* q, const uint8_t* qmask, int nq, const uint8_t* d, const uint8_t* dmask,
                                 int nd, const uint8_t* db_skip, int dim, int K, int* topk_idx, int* topk_dist,
                                 cudaStream_t st);
-cudaError_t launch_hamming_stream(const uint8_t* desc, const uint8_t* dmask, const int* counts, int n_frames, int n_cams,
-                                  int capacity, int dim, int K, int* out_idx, int* out_dist, cudaStream_t st);
+cudaError_t launch_hamming_stream(const uint8_t* desc, const uint8_t* dmask, const int* counts, int img_lo, int img_count,
+                                  int n_cams, int capacity, int dim, int K, int* out_idx, int* out_dist, cudaStream_t st);
+void launch_repitch(const uint8_t* src, int src_stride, uint8_t* dst, int dst_pitch, int width, size_t rows, cudaStream_t st);
 struct WindowFrameDev {
     int n_cams, n_keys, dim;
     const float* kx; const float* ky; const int* koct;      // [n_keys]

@@ -161,10 +161,11 @@ cudaError_t launch_hamming_topk(const uint8_t* q, const uint8_t* qmask, int nq, 
 template <int WORDS, bool MASKED>
 __global__ void __launch_bounds__(kTopkThreads)
 hamming_stream_kernel(const uint32_t* __restrict__ desc, const uint32_t* __restrict__ dmask, const int* __restrict__ counts,
-                      const int n_cams, const int capacity, const int K, int* __restrict__ out_idx, int* __restrict__ out_dist) {
+                      const int n_cams, const int capacity, const int K, const int img_lo, int* __restrict__ out_idx,
+                      int* __restrict__ out_dist) {
     __shared__ __align__(16) uint32_t s_d[kDbTile * WORDS];
     __shared__ __align__(16) uint32_t s_m[MASKED ? kDbTile * WORDS : 4];
-    const int img = blockIdx.y;
+    const int img = blockIdx.y + img_lo;
     const int qi = blockIdx.x * kTopkThreads + threadIdx.x;
     const bool has_prev = img >= n_cams;                 // frame 0 has no predecessor
     const int nq = has_prev ? min(counts[img], capacity) : 0;
@@ -243,13 +244,14 @@ hamming_stream_kernel(const uint32_t* __restrict__ desc, const uint32_t* __restr
     }
 }
 
-cudaError_t launch_hamming_stream(const uint8_t* desc, const uint8_t* dmask, const int* counts, int n_frames, int n_cams,
-                                  int capacity, int dim, int K, int* out_idx, int* out_dist, cudaStream_t st) {
+cudaError_t launch_hamming_stream(const uint8_t* desc, const uint8_t* dmask, const int* counts, int img_lo, int img_count,
+                                  int n_cams, int capacity, int dim, int K, int* out_idx, int* out_dist, cudaStream_t st) {
     if (K < 1 || K > kTopKMax || (dim != 16 && dim != 32 && dim != 64)) return cudaErrorInvalidValue;
-    dim3 grid((capacity + kTopkThreads - 1) / kTopkThreads, n_frames * n_cams);
+    if (img_count < 1) return cudaSuccess;
+    dim3 grid((capacity + kTopkThreads - 1) / kTopkThreads, img_count);
     const bool masked = dmask != nullptr;
 #define MCS_HS(W, M) hamming_stream_kernel<W, M><<<grid, kTopkThreads, 0, st>>>((const uint32_t*)desc, (const uint32_t*)dmask, counts, \
-        n_cams, capacity, K, out_idx, out_dist)
+        n_cams, capacity, K, img_lo, out_idx, out_dist)
     if (dim == 16) { if (masked) MCS_HS(4, true); else MCS_HS(4, false); }
     else if (dim == 32) { if (masked) MCS_HS(8, true); else MCS_HS(8, false); }
     else { if (masked) MCS_HS(16, true); else MCS_HS(16, false); }

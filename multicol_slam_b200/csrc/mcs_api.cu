@@ -91,6 +91,8 @@ struct mcs_extractor {
     DevBuf<uint8_t> desc, dmask;
     int last_n_images = 0;
     DevBuf<int> match_idx, match_dist;
+    DevBuf<uint8_t> in_tight;
+    cudaStream_t s_copy = nullptr, s_out = nullptr;
     // distortion tables, rebuilt when the camera set changes
     std::vector<mcs_ocam> lut_cams;
     DevBuf<double> lut_coef;
@@ -236,7 +238,7 @@ int ensure_batch(mcs_extractor* ex, int B) {
 int run_pipeline(mcs_extractor* ex, int n_images, const uint8_t* images_dev, int W, int H, int stride,
                  const uint8_t* masks, const mcs_ocam* cams, int n_cams, const int* cam_of_image,
                  mcs_keypoint* kps_dev, uint8_t* desc_dev, uint8_t* dmask_dev, int* counts_dev, int capacity,
-                 cudaStream_t st) {
+                 cudaStream_t st, bool first_chunk = true) {
     if (n_cams < 1 || n_cams > 64) return fail(MCS_ERR_INVALID, "n_cams must be in [1,64]");
     for (int i = 0; i < n_images; ++i)
         if (cam_of_image[i] < 0 || cam_of_image[i] >= n_cams) return fail(MCS_ERR_INVALID, "cam_of_image out of range");
@@ -245,35 +247,37 @@ int run_pipeline(mcs_extractor* ex, int n_images, const uint8_t* images_dev, int
     rc = ensure_batch(ex, n_images);
     if (rc) return rc;
     const PyramidGeom& G = ex->G;
+    if (first_chunk) {
     // small per-call host inputs
-    CK(ex->masks.ensure((size_t)n_cams * W * H));
-    CK(ex->cams.ensure(n_cams));
-    CK(cudaMemcpyAsync(ex->masks.p, masks, (size_t)n_cams * W * H, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ex->cams.p, cams, sizeof(mcs_ocam) * n_cams, cudaMemcpyHostToDevice, st));
-    if ((ex->p.do_dbrief || ex->p.learn_masks) &&
-        ((int)ex->lut_cams.size() != n_cams || std::memcmp(ex->lut_cams.data(), cams, sizeof(mcs_ocam) * n_cams) != 0)) {
-        std::vector<double> all;
-        std::vector<size_t> offs(n_cams);
-        std::vector<int> ns(n_cams);
-        for (int c = 0; c < n_cams; ++c) {
-            std::vector<double> coef;
-            build_distort_lut(cams[c], coef, ns[c]);
-            offs[c] = all.size();
-            all.insert(all.end(), coef.begin(), coef.end());
+        CK(ex->masks.ensure((size_t)n_cams * W * H));
+        CK(ex->cams.ensure(n_cams));
+        CK(cudaMemcpyAsync(ex->masks.p, masks, (size_t)n_cams * W * H, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ex->cams.p, cams, sizeof(mcs_ocam) * n_cams, cudaMemcpyHostToDevice, st));
+        if ((ex->p.do_dbrief || ex->p.learn_masks) &&
+            ((int)ex->lut_cams.size() != n_cams || std::memcmp(ex->lut_cams.data(), cams, sizeof(mcs_ocam) * n_cams) != 0)) {
+            std::vector<double> all;
+            std::vector<size_t> offs(n_cams);
+            std::vector<int> ns(n_cams);
+            for (int c = 0; c < n_cams; ++c) {
+                std::vector<double> coef;
+                build_distort_lut(cams[c], coef, ns[c]);
+                offs[c] = all.size();
+                all.insert(all.end(), coef.begin(), coef.end());
+            }
+            CK(cudaStreamSynchronize(st));                 // a previous call may still read the old tables
+            CK(ex->lut_coef.ensure(all.size()));
+            CK(ex->luts.ensure(n_cams));
+            std::vector<DistortLut> h(n_cams);
+            for (int c = 0; c < n_cams; ++c) h[c] = DistortLut{ex->lut_coef.p + offs[c], ns[c], 1.0};
+            CK(cudaMemcpyAsync(ex->lut_coef.p, all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(ex->luts.p, h.data(), sizeof(DistortLut) * n_cams, cudaMemcpyHostToDevice, st));
+            CK(cudaStreamSynchronize(st));                 // host staging vectors die here
+            ex->lut_cams.assign(cams, cams + n_cams);
         }
-        CK(cudaStreamSynchronize(st));                 // a previous call may still read the old tables
-        CK(ex->lut_coef.ensure(all.size()));
-        CK(ex->luts.ensure(n_cams));
-        std::vector<DistortLut> h(n_cams);
-        for (int c = 0; c < n_cams; ++c) h[c] = DistortLut{ex->lut_coef.p + offs[c], ns[c], 1.0};
-        CK(cudaMemcpyAsync(ex->lut_coef.p, all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ex->luts.p, h.data(), sizeof(DistortLut) * n_cams, cudaMemcpyHostToDevice, st));
-        CK(cudaStreamSynchronize(st));                 // host staging vectors die here
-        ex->lut_cams.assign(cams, cams + n_cams);
+        CK(cudaMemsetAsync(ex->status.p, 0, sizeof(int), st));
     }
     CK(cudaMemcpyAsync(ex->cam_of_image.p, cam_of_image, sizeof(int) * n_images, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(ex->raw_count.p, 0, sizeof(int) * n_images * G.nlevels, st));
-    CK(cudaMemsetAsync(ex->status.p, 0, sizeof(int), st));
     if (ex->profiling) CK(cudaEventRecord(ex->ev[0], st));
     for (int l = 0; l < G.nlevels; ++l) {
         const uint8_t* src = l ? ex->lvl[l - 1].p : images_dev;
@@ -444,6 +448,9 @@ void mcs_extractor_destroy(mcs_extractor* ex) {
     ex->kps.release(); ex->desc.release(); ex->dmask.release();
     ex->match_idx.release(); ex->match_dist.release(); ex->lut_coef.release(); ex->luts.release();
     for (int i = 0; i < 4; ++i) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
+    ex->in_tight.release();
+    if (ex->s_copy) cudaStreamDestroy(ex->s_copy);
+    if (ex->s_out) cudaStreamDestroy(ex->s_out);
     if (ex->stream) cudaStreamDestroy(ex->stream);
     delete ex;
 }
@@ -497,7 +504,10 @@ int mcs_extract_batch(mcs_extractor* ex, int32_t n_images, const uint8_t* images
     CK(ex->desc.ensure((size_t)n_images * capacity * ds));
     CK(ex->dmask.ensure((size_t)n_images * capacity * ds));
     CK(ex->counts.ensure(n_images));
-    CK(cudaMemcpy2DAsync(ex->in_images.p, dpitch, images, stride, width, (size_t)height * n_images, cudaMemcpyHostToDevice, st));
+    // linear H2D + device re-pitch (a 2-D DMA of short rows is several times slower)
+    CK(ex->in_tight.ensure((size_t)stride * height * n_images + 256));
+    CK(cudaMemcpyAsync(ex->in_tight.p, images, (size_t)stride * height * n_images, cudaMemcpyHostToDevice, st));
+    launch_repitch(ex->in_tight.p, stride, ex->in_images.p, dpitch, width, (size_t)height * n_images, st);
     int rc = run_pipeline(ex, n_images, ex->in_images.p, width, height, dpitch, masks, cams, n_cams, cam_of_image, ex->kps.p,
                           ex->desc.p, ex->dmask.p, ex->counts.p, capacity, st);
     if (rc) return rc;
@@ -603,7 +613,7 @@ int mcs_match_stream_device(const uint8_t* desc_dev, const uint8_t* dmask_dev, c
     if (n_frames < 1 || n_cams < 1 || capacity < 1 || K < 1 || K > 8) return fail(MCS_ERR_INVALID, "bad sizes (K must be 1..8)");
     if (dim != 16 && dim != 32 && dim != 64) return fail(MCS_ERR_INVALID, "dim must be 16, 32 or 64");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(launch_hamming_stream(desc_dev, dmask_dev, counts_dev, n_frames, n_cams, capacity, dim, K, match_idx_dev, match_dist_dev, st));
+    CK(launch_hamming_stream(desc_dev, dmask_dev, counts_dev, 0, n_frames * n_cams, n_cams, capacity, dim, K, match_idx_dev, match_dist_dev, st));
     return MCS_OK;
 }
 
@@ -619,31 +629,71 @@ int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams
     if (K < 1 || K > 8) return fail(MCS_ERR_INVALID, "K must be 1..8");
     CK(cudaSetDevice(ex->device));
     cudaStream_t st = ex->stream;
+    if (!ex->s_copy) CK(cudaStreamCreateWithFlags(&ex->s_copy, cudaStreamNonBlocking));
+    if (!ex->s_out) CK(cudaStreamCreateWithFlags(&ex->s_out, cudaStreamNonBlocking));
     const int n_images = n_frames * n_cams, ds = ex->p.desc_size;
     const int dpitch = (width + 63) & ~63;
-    const size_t img_bytes = (size_t)dpitch * height;
+    // Software pipeline over chunks of frames: H2D (copy stream) | re-pitch + K1..K3 + matching (compute stream) |
+    // D2H (output stream).  The chunk inputs are copied linearly and re-pitched on the device.
+    const int n_chunks = std::min(n_frames, 4);
+    const int fpc = (n_frames + n_chunks - 1) / n_chunks;             // frames per chunk
+    const int ipc = fpc * n_cams;                                     // images per chunk
+    const size_t tight_img = (size_t)stride * height, pitched_img = (size_t)dpitch * height;
     std::vector<int> coi(n_images);
     for (int i = 0; i < n_images; ++i) coi[i] = i % n_cams;
-    CK(ex->in_images.ensure(img_bytes * n_images + 256));
+    CK(ex->in_tight.ensure(2 * tight_img * ipc + 256));
+    CK(ex->in_images.ensure(pitched_img * ipc + 256));
     CK(ex->kps.ensure((size_t)n_images * capacity));
     CK(ex->desc.ensure((size_t)n_images * capacity * ds));
     CK(ex->dmask.ensure((size_t)n_images * capacity * ds));
     CK(ex->counts.ensure(n_images));
     CK(ex->match_idx.ensure((size_t)n_images * capacity * K));
     CK(ex->match_dist.ensure((size_t)n_images * capacity * K));
-    CK(cudaMemcpy2DAsync(ex->in_images.p, dpitch, images, stride, width, (size_t)height * n_images, cudaMemcpyHostToDevice, st));
-    int rc = run_pipeline(ex, n_images, ex->in_images.p, width, height, dpitch, masks, cams, n_cams, coi.data(), ex->kps.p,
-                          ex->desc.p, ex->dmask.p, ex->counts.p, capacity, st);
+    std::vector<cudaEvent_t> ev_in(n_chunks), ev_free(n_chunks), ev_done(n_chunks);
+    for (int c = 0; c < n_chunks; ++c) {
+        CK(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_free[c], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
+    }
+    int rc = MCS_OK;
+    const uint8_t* dmask_for_match = ex->p.learn_masks ? ex->dmask.p : nullptr;
+    for (int c = 0; c < n_chunks && rc == MCS_OK; ++c) {
+        const int img_lo = c * ipc, nimg = std::min(ipc, n_images - img_lo);
+        if (nimg <= 0) break;
+        uint8_t* tight = ex->in_tight.p + (size_t)(c & 1) * tight_img * ipc;
+        if (c >= 2) CK(cudaStreamWaitEvent(ex->s_copy, ev_free[c - 2], 0));          // staging buffer consumed
+        CK(cudaMemcpyAsync(tight, images + (size_t)img_lo * tight_img, tight_img * nimg, cudaMemcpyHostToDevice, ex->s_copy));
+        CK(cudaEventRecord(ev_in[c], ex->s_copy));
+        CK(cudaStreamWaitEvent(st, ev_in[c], 0));
+        launch_repitch(tight, stride, ex->in_images.p, dpitch, width, (size_t)height * nimg, st);
+        CK(cudaEventRecord(ev_free[c], st));
+        rc = run_pipeline(ex, nimg, ex->in_images.p, width, height, dpitch, masks, cams, n_cams, coi.data() + img_lo,
+                          ex->kps.p + (size_t)img_lo * capacity, ex->desc.p + (size_t)img_lo * capacity * ds,
+                          ex->dmask.p + (size_t)img_lo * capacity * ds, ex->counts.p + img_lo, capacity, st, c == 0);
+        if (rc) break;
+        CK(launch_hamming_stream(ex->desc.p, dmask_for_match, ex->counts.p, img_lo, nimg, n_cams, capacity, ds, K, ex->match_idx.p,
+                                 ex->match_dist.p, st));
+        CK(cudaEventRecord(ev_done[c], st));
+        CK(cudaStreamWaitEvent(ex->s_out, ev_done[c], 0));
+        cudaStream_t so = ex->s_out;
+        CK(cudaMemcpyAsync(counts_out + img_lo, ex->counts.p + img_lo, sizeof(int) * nimg, cudaMemcpyDeviceToHost, so));
+        CK(cudaMemcpyAsync(kps_out + (size_t)img_lo * capacity, ex->kps.p + (size_t)img_lo * capacity,
+                           sizeof(mcs_keypoint) * (size_t)nimg * capacity, cudaMemcpyDeviceToHost, so));
+        CK(cudaMemcpyAsync(desc_out + (size_t)img_lo * capacity * ds, ex->desc.p + (size_t)img_lo * capacity * ds,
+                           (size_t)nimg * capacity * ds, cudaMemcpyDeviceToHost, so));
+        if (dmask_out)
+            CK(cudaMemcpyAsync(dmask_out + (size_t)img_lo * capacity * ds, ex->dmask.p + (size_t)img_lo * capacity * ds,
+                               (size_t)nimg * capacity * ds, cudaMemcpyDeviceToHost, so));
+        CK(cudaMemcpyAsync(match_idx_out + (size_t)img_lo * capacity * K, ex->match_idx.p + (size_t)img_lo * capacity * K,
+                           sizeof(int) * (size_t)nimg * capacity * K, cudaMemcpyDeviceToHost, so));
+        CK(cudaMemcpyAsync(match_dist_out + (size_t)img_lo * capacity * K, ex->match_dist.p + (size_t)img_lo * capacity * K,
+                           sizeof(int) * (size_t)nimg * capacity * K, cudaMemcpyDeviceToHost, so));
+    }
+    cudaError_t e1 = cudaStreamSynchronize(ex->s_copy), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(ex->s_out);
+    for (int c = 0; c < n_chunks; ++c) { cudaEventDestroy(ev_in[c]); cudaEventDestroy(ev_free[c]); cudaEventDestroy(ev_done[c]); }
     if (rc) return rc;
-    rc = mcs_match_stream_device(ex->desc.p, ex->p.learn_masks ? ex->dmask.p : nullptr, ex->counts.p, n_frames, n_cams, capacity, ds, K,
-                                 ex->match_idx.p, ex->match_dist.p, st);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(counts_out, ex->counts.p, sizeof(int) * n_images, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(kps_out, ex->kps.p, sizeof(mcs_keypoint) * n_images * capacity, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(desc_out, ex->desc.p, (size_t)n_images * capacity * ds, cudaMemcpyDeviceToHost, st));
-    if (dmask_out) CK(cudaMemcpyAsync(dmask_out, ex->dmask.p, (size_t)n_images * capacity * ds, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(match_idx_out, ex->match_idx.p, sizeof(int) * (size_t)n_images * capacity * K, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(match_dist_out, ex->match_dist.p, sizeof(int) * (size_t)n_images * capacity * K, cudaMemcpyDeviceToHost, st));
+    CK(e1); CK(e2); CK(e3);
+    ex->last_n_images = std::min(ipc, n_images - (n_chunks - 1) * ipc);
     return check_status(ex, st);
 }
 

@@ -248,6 +248,20 @@ pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int
     }
 }
 
+// tight caller rows -> 64-byte aligned pitch (the host entry points copy H2D linearly, then re-pitch on the device:
+// a 2-D DMA of 754-byte rows is several times slower than a linear copy)
+__global__ void repitch_kernel(const uint8_t* __restrict__ src, int src_stride, uint8_t* __restrict__ dst, int dst_pitch, int width,
+                               size_t rows) {
+    const size_t row = blockIdx.x;
+    if (row >= rows) return;
+    const uint8_t* s = src + row * src_stride;
+    uint8_t* d = dst + row * dst_pitch;
+    for (int x = threadIdx.x; x < dst_pitch; x += blockDim.x) d[x] = x < width ? s[x] : (uint8_t)0;
+}
+void launch_repitch(const uint8_t* src, int src_stride, uint8_t* dst, int dst_pitch, int width, size_t rows, cudaStream_t st) {
+    repitch_kernel<<<(unsigned)rows, 256, 0, st>>>(src, src_stride, dst, dst_pitch, width, rows);
+}
+
 void launch_pyr_fast(const PyramidGeom& G, int level, int n_images, const uint8_t* src, size_t src_img_bytes,
                      uint8_t* dst, uint8_t* dst_blur, const uint8_t* mask0, int mask_w, size_t mask_bytes,
                      const int* cam_of_image, uint32_t* raw, int* raw_count, cudaStream_t st) {
