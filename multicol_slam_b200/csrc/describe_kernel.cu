@@ -304,21 +304,24 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
 #pragma unroll
             for (int j = 0; j < PPL; ++j) {
                 const double2 pp = s_patd[j * 32 + lane];
-                const double xr = pp.x * ca[q] - pp.y * sa[q] + ukx;
-                const double yr = pp.x * sa[q] + pp.y * ca[q] + uky;
+                const double xr = fma(pp.x, ca[q], fma(-pp.y, sa[q], ukx));
+                const double yr = fma(pp.x, sa[q], fma(pp.y, ca[q], uky));
                 const double s2 = fma(xr, xr, yr * yr);
-                const double rinv = rsqrt(s2), r = s2 * rinv;
-                // R(r) from the staged window; anything outside it (or s2 == 0 -> NaN) takes the exact path.
-                // interval index = rn(r - 0.5): at an exact integer either neighbour is valid (tau = +-1)
+                // 1/sqrt(s2): hardware approximation (~1e-7) + one third-order step -> < 1e-16 relative
+                double y0;
+                asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(s2));
+                const double e = fma(-(s2 * y0), y0, 1.0);
+                const double rinv = fma(y0 * e, fma(0.375, e, 0.5), y0), r = s2 * rinv;
+                // R(r) from the staged window.  Interval index = rn(r - 0.5): at an exact integer either neighbour is
+                // valid (tau = +-1).  A radius outside the window (or NaN from s2 == 0) is caught below.
                 const double tm = (r - 0.5) + kMagic;
-                const int idx = __double2loint(tm) - i0;
-                double gg = 0.0;
-                if (r >= 0.0 && r < (double)lut.n && idx >= 0 && idx < kLutWin) {
-                    const double tau = fma(2.0, r - (tm - kMagic), -1.0);
-                    const double* cf = wl + idx * 6;
-                    gg = cf[5];
-                    gg = fma(gg, tau, cf[4]); gg = fma(gg, tau, cf[3]); gg = fma(gg, tau, cf[2]); gg = fma(gg, tau, cf[1]); gg = fma(gg, tau, cf[0]);
-                } else need_exact = lane_valid;
+                const unsigned idx = (unsigned)(__double2loint(tm) - i0);
+                const double tau = fma(2.0, r - (tm - kMagic), -1.0);
+                const double2* cf = (const double2*)(wl + min(idx, (unsigned)(kLutWin - 1)) * 6);
+                const double2 c01 = cf[0], c23 = cf[1], c45 = cf[2];
+                double gg = c45.y;
+                gg = fma(gg, tau, c45.x); gg = fma(gg, tau, c23.y); gg = fma(gg, tau, c23.x); gg = fma(gg, tau, c01.y); gg = fma(gg, tau, c01.x);
+                need_exact |= lane_valid && !(idx < (unsigned)kLutWin && r < (double)lut.n);
                 gg *= rinv;
                 const double uu = xr * gg, vv = yr * gg;
                 us[j] = fma(uu, cam.c, fma(vv, cam.d, cam.u0));
@@ -332,16 +335,24 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
             }
             const double mu = su * inv_n, mv = sv * inv_n;
             int ix[PPL], iy[PPL];
+            // Closeness to a rounding tie and the patch range are tracked as integer maxima: the high word of |frac|
+            // orders like the double itself (non-negative), a NaN / huge value has a larger high word than any fraction.
+            int worst_frac = 0, worst_mag = 0;
+            unsigned worst_ofs = 0;
 #pragma unroll
             for (int j = 0; j < PPL; ++j) {
                 const double du = us[j] - mu, dv = vs[j] - mv;
                 const double tu = du + kMagic, tv = dv + kMagic;
                 ix[j] = __double2loint(tu); iy[j] = __double2loint(tv);
-                // closer than 1e-7 px to a rounding tie, or outside the staged patch -> exact / generic path
-                const double fu = fabs(du - (tu - kMagic)), fv = fabs(dv - (tv - kMagic));
-                need_exact |= lane_valid && (fu > 0.5 - 1e-7 || fv > 0.5 - 1e-7 || !(fabs(du) < 1e6) || !(fabs(dv) < 1e6) ||
-                                             (unsigned)(ix[j] + kPatchR) > 2u * kPatchR || (unsigned)(iy[j] + kPatchR) > 2u * kPatchR);
+                const int hu = __double2hiint(du - (tu - kMagic)) & 0x7fffffff, hv = __double2hiint(dv - (tv - kMagic)) & 0x7fffffff;
+                worst_frac = max(worst_frac, max(hu, hv));
+                worst_ofs = max(worst_ofs, max((unsigned)(ix[j] + kPatchR), (unsigned)(iy[j] + kPatchR)));
+                // |du| >= 2^31 would alias in the low word of the magic sum (and shows |frac| == 0): track the magnitude
+                worst_mag = max(worst_mag, max(__double2hiint(du) & 0x7fffffff, __double2hiint(dv) & 0x7fffffff));
             }
+            // closer than ~7e-7 px to a rounding tie (high word of 0.5 - 5e-7), or outside the staged patch -> exact path
+            need_exact |= lane_valid && (worst_frac >= __double2hiint(0.5 - 5e-7) || worst_ofs > 2u * kPatchR ||
+                                         worst_mag >= 0x41d00000 /* 2^30 or NaN */);
             if (__any_sync(0xffffffffu, need_exact)) {
                 const unsigned e = exact_pattern<PPL>(&cam, s_pat, ca[q], sa[q], ukx, uky, lane, ds, bimg, uimg, &g, kx, ky);
 #pragma unroll
