@@ -18,6 +18,73 @@ constexpr int kDbTile = 256;
 constexpr int kTopkThreads = 128;
 constexpr unsigned long long kNoKey = 0xFFFFFFFFFFFFFFFFull;
 
+
+// ---- bit-sliced population count (Harley-Seal carry-save adders) -------------------------------------------------
+// POPC issues on the XU pipe of sm_100 at 16 lanes/clk/SM (4x slower than LOP3), which makes a plain popcount loop
+// the bottleneck of brute-force Hamming.  A carry-save adder (2 LOP3) turns three words into a "ones" and a "twos"
+// word; reducing 16 (8) words this way needs 5 (4) POPC instead of 16 (8).
+// (a ^ b) & c in one LOP3 (immLut = (0xF0 ^ 0xCC) & 0xAA); the compiler otherwise keeps the shared xor separate
+__device__ __forceinline__ uint32_t xor_and(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& sum, uint32_t& carry) {
+    sum = a ^ b ^ c;                       // LOP3 0x96
+    carry = (a & b) | (c & (a | b));       // LOP3 0xE8 (majority)
+}
+__device__ __forceinline__ unsigned popc_sum8(const uint32_t (&w)[8]) {
+    uint32_t s0, c0, s1, c1, s2, c2, t0, d0;
+    csa(w[0], w[1], w[2], s0, c0);
+    csa(w[3], w[4], w[5], s1, c1);
+    csa(s0, s1, w[6], s2, c2);
+    csa(c0, c1, c2, t0, d0);
+    return __popc(s2) + __popc(w[7]) + 2 * __popc(t0) + 4 * __popc(d0);
+}
+__device__ __forceinline__ unsigned popc_sum16(const uint32_t (&w)[16]) {
+    uint32_t s0, c0, s1, c1, s2, c2, s3, c3, s4, c4, s5, c5, s6, c6, t0, d0, t1, d1, t2, d2, f0, e0;
+    csa(w[0], w[1], w[2], s0, c0);
+    csa(w[3], w[4], w[5], s1, c1);
+    csa(w[6], w[7], w[8], s2, c2);
+    csa(w[9], w[10], w[11], s3, c3);
+    csa(w[12], w[13], w[14], s4, c4);
+    csa(s0, s1, s2, s5, c5);
+    csa(s3, s4, w[15], s6, c6);
+    csa(c0, c1, c2, t0, d0);
+    csa(c3, c4, c5, t1, d1);
+    csa(t0, t1, c6, t2, d2);
+    csa(d0, d1, d2, f0, e0);
+    return __popc(s5) + __popc(s6) + 2 * __popc(t2) + 4 * __popc(f0) + 8 * __popc(e0);
+}
+// sum over k of popc(x_k) [unmasked] or popc(x_k & qm_k) + popc(x_k & dm_k) [masked, before the /2], x_k = q_k ^ d_k
+template <int WORDS, bool MASKED>
+__device__ __forceinline__ unsigned hamming_words(const uint32_t (&qw)[WORDS], const uint32_t* qm, const uint32_t* dd, const uint32_t* dm) {
+    unsigned dist = 0;
+    if (MASKED) {
+#pragma unroll
+        for (int h = 0; h < WORDS; h += 8) {
+            uint32_t w[16];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (h + k < WORDS) {
+                    w[2 * k] = xor_and(qw[h + k], dd[h + k], qm[h + k]);
+                    w[2 * k + 1] = xor_and(qw[h + k], dd[h + k], dm[h + k]);
+                } else { w[2 * k] = 0; w[2 * k + 1] = 0; }
+            }
+            dist += popc_sum16(w);
+        }
+    } else {
+#pragma unroll
+        for (int h = 0; h < WORDS; h += 8) {
+            uint32_t w[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w[k] = (h + k < WORDS) ? (qw[h + k] ^ dd[h + k]) : 0u;
+            dist += popc_sum8(w);
+        }
+    }
+    return dist;
+}
+
 template <int WORDS, bool MASKED>
 __global__ void __launch_bounds__(kTopkThreads)
 hamming_topk_kernel(const uint32_t* __restrict__ q, const uint32_t* __restrict__ qmask, const int nq,
@@ -59,18 +126,9 @@ hamming_topk_kernel(const uint32_t* __restrict__ q, const uint32_t* __restrict__
         __syncthreads();
         for (int j = 0; j < tn; ++j) {
             if (s_skip[j]) continue;       // uniform across the CTA
-            unsigned dist = 0;
-            if (MASKED) {
-#pragma unroll
-                for (int k = 0; k < WORDS; ++k) {
-                    const uint32_t x = qw[k] ^ s_d[j * WORDS + k];
-                    dist += __popc(x & qm[k]) + __popc(x & s_m[j * WORDS + k]);
-                }
-                dist >>= 1;               // integer division by 2 of the reference (:2472)
-            } else {
-#pragma unroll
-                for (int k = 0; k < WORDS; ++k) dist += __popc(qw[k] ^ s_d[j * WORDS + k]);
-            }
+            // bit-level Hamming distance; masked form = (popc(x&ma) + popc(x&mb)) / 2, integer division (ref :2472)
+            unsigned dist = hamming_words<WORDS, MASKED>(qw, qm, s_d + j * WORDS, s_m + j * WORDS);
+            if (MASKED) dist >>= 1;
             if (dist < worst) {            // strict: equal distances keep the earlier index
                 unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)(t0 + j);
 #pragma unroll
@@ -208,18 +266,9 @@ hamming_stream_kernel(const uint32_t* __restrict__ desc, const uint32_t* __restr
         }
         __syncthreads();
         for (int j = 0; j < tn; ++j) {
-            unsigned dist = 0;
-            if (MASKED) {
-#pragma unroll
-                for (int k = 0; k < WORDS; ++k) {
-                    const uint32_t x = qw[k] ^ s_d[j * WORDS + k];
-                    dist += __popc(x & qm[k]) + __popc(x & s_m[j * WORDS + k]);
-                }
-                dist >>= 1;
-            } else {
-#pragma unroll
-                for (int k = 0; k < WORDS; ++k) dist += __popc(qw[k] ^ s_d[j * WORDS + k]);
-            }
+            // bit-level Hamming distance; masked form = (popc(x&ma) + popc(x&mb)) / 2, integer division (ref :2472)
+            unsigned dist = hamming_words<WORDS, MASKED>(qw, qm, s_d + j * WORDS, s_m + j * WORDS);
+            if (MASKED) dist >>= 1;
             if (dist < worst) {
                 unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)(t0 + j);
 #pragma unroll

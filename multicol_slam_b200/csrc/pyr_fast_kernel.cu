@@ -23,7 +23,7 @@ constexpr int kThreads = 256;
 constexpr int kSrcWB = 176;                 // staged source row stride (bytes, multiple of 16)
 constexpr int kT8S = 80;                    // byte tile row stride
 constexpr int kT16S = 72;                   // 16-bit tile row stride (elements)
-constexpr int kScoreS = 68;                 // score tile row stride (66 used)
+constexpr int kScoreS = 68;                 // score tile row stride in 16-bit elements (66 used)
 constexpr int kMaxTileCorners = kTW * kTH / 4;
 
 __device__ __forceinline__ unsigned vneg2(unsigned a) { return __vadd2(~a, 0x00010001u); }
@@ -71,13 +71,18 @@ pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int
     __shared__ __align__(16) uint16_t s_a0[kTileH * kT16S];          // s_a0[y][x]   = px(x)
     __shared__ __align__(16) uint16_t s_a1[kTileH * kT16S];          // s_a1[y][i]   = px(i+1)
     __shared__ __align__(16) uint32_t s_h[(kTH + 4) * (kTW / 2)];    // packed horizontal 5-sums of pixel pairs
-    __shared__ __align__(16) uint8_t s_score[(kTH + 2) * kScoreS];
+    __shared__ uint32_t s_ml[kTW / 2], s_mr[kTW / 2], s_mu[kTH], s_md[kTH];   // NMS lane masks (same-cell neighbours)
     __shared__ int16_t s_xs0[kTileW], s_xs1[kTileW], s_xa0[kTileW], s_xa1[kTileW];
     __shared__ int16_t s_ys0[kTileH], s_ys1[kTileH], s_yb0[kTileH], s_yb1[kTileH];
     __shared__ int16_t s_cellx[kTW + 2], s_celly[kTH + 2];
     __shared__ uint32_t s_list[kMaxTileCorners];
     __shared__ int s_n, s_base;
 
+    // 16-bit score tiles (two copies offset by one pixel, like the pixel tiles); they reuse the source staging
+    // area, which is dead once the tile has been resized
+    uint16_t* s_s0 = (uint16_t*)s_src;                                  // s_s0[y][x] = score(x),   x = score-tile column
+    uint16_t* s_s1 = (uint16_t*)s_src + (kTH + 2) * kScoreS;            // s_s1[y][i] = score(i+1)
+    static_assert(2 * (kTH + 2) * kScoreS * 2 <= kSrcH * kSrcWB, "score tiles must fit into the staging area");
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int b = blockIdx.z;
     const int X0 = blockIdx.x * kTW, Y0 = blockIdx.y * kTH;
@@ -119,10 +124,18 @@ pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int
         const int nrows = sy_hi - sy_lo + 1;
         if (src_aligned) {
             const int nchunks = ((sx_hi - sx_base) >> 4) + 1;
-            for (int r = wid; r < nrows; r += kThreads / 32)
-                for (int c = lane; c < nchunks; c += 32)
-                    *(uint4*)(s_src + r * kSrcWB + c * 16) =
-                        __ldg((const uint4*)(simg + (size_t)(sy_lo + r) * g.spitch + sx_base + c * 16));
+            if (nchunks <= 8) {          // scale factors <= 1.5: four rows per warp instruction
+                const int c = lane & 7;
+                for (int r = wid * 4 + (lane >> 3); r < nrows; r += kThreads / 8)
+                    if (c < nchunks)
+                        *(uint4*)(s_src + r * kSrcWB + c * 16) =
+                            __ldg((const uint4*)(simg + (size_t)(sy_lo + r) * g.spitch + sx_base + c * 16));
+            } else {
+                for (int r = wid; r < nrows; r += kThreads / 32)
+                    for (int c = lane; c < nchunks; c += 32)
+                        *(uint4*)(s_src + r * kSrcWB + c * 16) =
+                            __ldg((const uint4*)(simg + (size_t)(sy_lo + r) * g.spitch + sx_base + c * 16));
+            }
         } else {   // caller-supplied image with an unaligned base or stride (level 0 only)
             const int nb = sx_hi - sx_base + 1;
             for (int r = wid; r < nrows; r += kThreads / 32)
@@ -144,11 +157,16 @@ pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int
             const uint8_t* r0 = s_src + s_ys0[ty] * kSrcWB;
             const uint8_t* r1 = s_src + s_ys1[ty] * kSrcWB;
             const int b0 = s_yb0[ty], b1 = s_yb1[ty];
-            const int h00 = r0[xs00] * a00 + r0[xs01] * a01, h01 = r1[xs00] * a00 + r1[xs01] * a01;
-            const int h10 = r0[xs10] * a10 + r0[xs11] * a11, h11 = r1[xs10] * a10 + r1[xs11] * a11;
-            int v0 = (((b0 * (h00 >> 4)) >> 16) + ((b1 * (h01 >> 4)) >> 16) + 2) >> 2;
-            int v1 = (((b0 * (h10 >> 4)) >> 16) + ((b1 * (h11 >> 4)) >> 16) + 2) >> 2;
-            v0 = min(max(v0, 0), 255); v1 = min(max(v1, 0), 255);
+            int v0, v1;
+            if (level == 0) {            // identity resize: the general formula reduces to a copy
+                v0 = r0[xs00]; v1 = r0[xs10];
+            } else {
+                const int h00 = r0[xs00] * a00 + r0[xs01] * a01, h01 = r1[xs00] * a00 + r1[xs01] * a01;
+                const int h10 = r0[xs10] * a10 + r0[xs11] * a11, h11 = r1[xs10] * a10 + r1[xs11] * a11;
+                v0 = (((b0 * (h00 >> 4)) >> 16) + ((b1 * (h01 >> 4)) >> 16) + 2) >> 2;
+                v1 = (((b0 * (h10 >> 4)) >> 16) + ((b1 * (h11 >> 4)) >> 16) + 2) >> 2;
+                v0 = min(max(v0, 0), 255); v1 = min(max(v1, 0), 255);
+            }
             *(uint16_t*)(s_t8 + ty * kT8S + tx) = (uint16_t)(v0 | (v1 << 8));
             *(uint32_t*)(s_a0 + ty * kT16S + tx) = (uint32_t)v0 | ((uint32_t)v1 << 16);
             if (tx > 0) s_a1[ty * kT16S + tx - 1] = (uint16_t)v0;
@@ -157,6 +175,16 @@ pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int
     }
     __syncthreads();
 
+    // same-cell masks for the packed NMS: pair column j holds pixels x = 2j, 2j+1 (score-tile columns x+1, x+2)
+    if (tid < kTW / 2) {
+        const int c0 = s_cellx[2 * tid], c1 = s_cellx[2 * tid + 1], c2 = s_cellx[2 * tid + 2], c3 = s_cellx[2 * tid + 3];
+        s_ml[tid] = (c0 == c1 ? 0xFFFFu : 0u) | (c1 == c2 ? 0xFFFF0000u : 0u);     // left  neighbours of (x, x+1)
+        s_mr[tid] = (c2 == c1 ? 0xFFFFu : 0u) | (c3 == c2 ? 0xFFFF0000u : 0u);     // right neighbours of (x, x+1)
+    } else if (tid >= 64 && tid < 64 + kTH) {
+        const int y = tid - 64;
+        s_mu[y] = s_celly[y] == s_celly[y + 1] ? 0xFFFFFFFFu : 0u;
+        s_md[y] = s_celly[y + 2] == s_celly[y + 1] ? 0xFFFFFFFFu : 0u;
+    }
     uint8_t* dimg = dst + (size_t)b * g.img_bytes;
     uint8_t* bimg = dst_blur + (size_t)b * g.img_bytes;
     // ---- (a) store the unblurred tile, 4 px per thread ----
@@ -177,7 +205,7 @@ pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int
         const int y = i / ((kTW + 2) / 2), j = i - y * ((kTW + 2) / 2);
         const int sx = 2 * j;                                   // score-tile column of the first pixel of the pair
         const bool in0 = s_cellx[sx] >= 0, in1 = s_cellx[sx + 1] >= 0, iny = s_celly[y] >= 0;
-        unsigned out = 0;
+        unsigned s0 = 0, s1 = 0;
         if (iny && (in0 || in1)) {
             // centre pair (px, px+1) with px = tile col 3+2j (odd) -> word j+1 of the odd copy; even dx -> odd copy, odd dx -> even copy
             const uint32_t* o = (const uint32_t*)(s_a1 + (y + kHalo - 1) * kT16S) + (j + 1);
@@ -191,11 +219,12 @@ pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int
             R[12] = e[-2];         R[13] = e[S - 2];       R[14] = o[2 * S - 1];  R[15] = e[3 * S - 1];
             const unsigned m = fast_margin2(C, R);
             const int m0 = (int)(short)(m & 0xFFFFu), m1 = (int)(short)(m >> 16);
-            const unsigned s0 = (in0 && m0 > fast_th) ? (unsigned)(m0 - 1) : 0u;
-            const unsigned s1 = (in1 && m1 > fast_th) ? (unsigned)(m1 - 1) : 0u;
-            out = s0 | (s1 << 8);
+            s0 = (in0 && m0 > fast_th) ? (unsigned)(m0 - 1) : 0u;
+            s1 = (in1 && m1 > fast_th) ? (unsigned)(m1 - 1) : 0u;
         }
-        *(uint16_t*)(s_score + y * kScoreS + sx) = (uint16_t)out;
+        *(uint32_t*)(s_s0 + y * kScoreS + sx) = s0 | (s1 << 16);
+        if (sx > 0) s_s1[y * kScoreS + sx - 1] = (uint16_t)s0;
+        s_s1[y * kScoreS + sx] = (uint16_t)s1;
     }
     __syncthreads();
 
@@ -212,29 +241,32 @@ pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int
             *(uint32_t*)(bimg + (size_t)(Y0 + y) * g.pitch + X0 + 4 * q) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
         }
     }
-    // ---- (e) per-cell 3x3 non-max suppression, mask filter, tile-local compaction ----
+    // ---- (e) per-cell 3x3 non-max suppression on pixel pairs (packed 16x2), mask filter, tile-local compaction ----
+    // Pair j of row y = pixels x = 2j, 2j+1 = score-tile columns 2j+1, 2j+2: centre word from the odd copy, left /
+    // right neighbour pairs from the even copy.  A neighbour outside the pixel's FAST cell counts as 0 (cv::FAST runs per cell).
     const uint8_t* m0p = mask0 + (size_t)cam_of_image[b] * mask_bytes;
-    for (int i = tid; i < kTH * kTW; i += kThreads) {
-        const int y = i >> 6, x = i & 63;
-        const uint8_t* sc = s_score + (y + 1) * kScoreS + x + 1;
-        const int s = sc[0];
-        if (s == 0) continue;
-        const int cx = s_cellx[x + 1], cy = s_celly[y + 1];
-        bool keep = true;
+    for (int i = tid; i < kTH * (kTW / 2); i += kThreads) {
+        const int y = i >> 5, j = i & 31;
+        const uint32_t* e0 = (const uint32_t*)(s_s0 + y * kScoreS) + j;          // row y-1 of the interior row y (score row y)
+        const uint32_t* o0 = (const uint32_t*)(s_s1 + y * kScoreS) + j;
+        constexpr int S = kScoreS / 2;
+        const unsigned C = o0[S];
+        if (C == 0) continue;
+        const unsigned ml = s_ml[j], mr = s_mr[j], mu = s_mu[y], md = s_md[y];
+        const unsigned up = __vimax3_u16x2(e0[0] & ml & mu, o0[0] & mu, e0[1] & mr & mu);
+        const unsigned dn = __vimax3_u16x2(e0[2 * S] & ml & md, o0[2 * S] & md, e0[2 * S + 1] & mr & md);
+        const unsigned nm = __vimax3_u16x2(up, dn, __vmaxu2(e0[S] & ml, e0[S + 1] & mr));
 #pragma unroll
-        for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                if (dx == 0 && dy == 0) continue;
-                const bool same = (s_cellx[x + 1 + dx] == cx) && (s_celly[y + 1 + dy] == cy);
-                const int sn = same ? sc[dy * kScoreS + dx] : 0;
-                keep = keep && (s > sn);
+        for (int h = 0; h < 2; ++h) {
+            const int sv = (int)((C >> (16 * h)) & 0xFFFFu), nv = (int)((nm >> (16 * h)) & 0xFFFFu);
+            if (sv > nv) {                                                        // strict maximum of its 3x3 (sv > 0)
+                const int gx = X0 + 2 * j + h, gy = Y0 + y;
+                if (m0p[(size_t)g.my0[gy] * mask_w + g.mx0[gx]] != 0) {
+                    const int pos = atomicAdd(&s_n, 1);
+                    s_list[pos] = pack_corner(gx, gy, sv);
+                }
             }
-        if (!keep) continue;
-        const int gx = X0 + x, gy = Y0 + y;
-        if (m0p[(size_t)g.my0[gy] * mask_w + g.mx0[gx]] == 0) continue;
-        const int pos = atomicAdd(&s_n, 1);
-        s_list[pos] = pack_corner(gx, gy, s);
+        }
     }
     __syncthreads();
     const int n = s_n;
