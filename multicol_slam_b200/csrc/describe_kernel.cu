@@ -22,6 +22,7 @@
 // Only cvRound(u - mean) has to agree with the reference; a projected coordinate closer than 1e-7 px to a
 // rounding tie (p ~ 2e-4 per pattern) makes the warp recompute that pattern with the reference's exact
 // operation sequence (cam_model.cuh).  Radii outside the table take the exact path as well.
+#include <cstdlib>
 #include <vector>
 
 #include "cam_model.cuh"
@@ -139,8 +140,8 @@ __device__ __noinline__ unsigned orb_pattern_global(const char2* s_pat, double c
     return out;
 }
 
-template <int PPL /* pattern points per lane: 16 for descSize <= 32, 32 for descSize 64 */>
-__global__ void __launch_bounds__(kDescWarps * 32, 4)
+template <int PPL /* pattern points per lane: 16 for descSize <= 32, 32 for descSize 64 */, int MINB = 4>
+__global__ void __launch_bounds__(kDescWarps * 32, MINB)
 describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, const mcs_ocam* __restrict__ cams,
                 const DistortLut* __restrict__ luts, const int* __restrict__ cam_of_image,
                 const uint32_t* __restrict__ sel_xys, const int* __restrict__ sel_count,
@@ -231,15 +232,19 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
     const bool masks = geom->learn_masks != 0, dbrief = geom->do_dbrief != 0 || masks;
     const float scale = g.scale;
     const int npat = masks ? 3 : 1;
-    double ca[3], sa[3];
+    double ca[3], sa[3], a_base, a_rot;
     {
         double a0;
         if (masks) a0 = (double)__fdiv_rn(angle, 57.2957763671875f);              // angle / RHOf      (ref :425)
         else a0 = (double)__fmul_rn(angle, 0.01745329238474369f);                   // angle * DEG2RADf  (ref :313,367)
         const double rot = 20.0 / (180.0 / 3.1415926535897932384626433832795);      // 20 / RHOd         (ref :424)
         sincos(a0, &sa[0], &ca[0]);
-        sincos(a0 + rot, &sa[1], &ca[1]);
-        sincos(a0 - rot, &sa[2], &ca[2]);
+        a_base = a0; a_rot = rot;
+        // angle +- 20 deg by the addition theorems (1e-16 away from cos/sin(a0 +- rot); the exact path below uses the
+        // reference's own cos(angle +- rot) / sin(angle +- rot))
+        const double c20 = 0.93969262078590838405, s20 = 0.34202014332566873304;
+        ca[1] = fma(ca[0], c20, -sa[0] * s20); sa[1] = fma(sa[0], c20, ca[0] * s20);
+        ca[2] = fma(ca[0], c20, sa[0] * s20);  sa[2] = fma(sa[0], c20, -ca[0] * s20);
     }
     constexpr int BPL = PPL / 16;                 // descriptor bytes per lane
     unsigned val[3][BPL];
@@ -299,6 +304,7 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
             double us[PPL], vs[PPL];
             double su = 0.0, sv = 0.0;
             bool need_exact = false;
+            unsigned worst_idx = 0;
             // round-to-nearest-even through the 1.5*2^52 trick: no F2I/I2F (XU pipe), same result as lrint
             constexpr double kMagic = 6755399441055744.0;
 #pragma unroll
@@ -321,7 +327,7 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                 const double2 c01 = cf[0], c23 = cf[1], c45 = cf[2];
                 double gg = c45.y;
                 gg = fma(gg, tau, c45.x); gg = fma(gg, tau, c23.y); gg = fma(gg, tau, c23.x); gg = fma(gg, tau, c01.y); gg = fma(gg, tau, c01.x);
-                need_exact |= lane_valid && !(idx < (unsigned)kLutWin && r < (double)lut.n);
+                worst_idx = max(worst_idx, idx);          // window miss (also r >= table size: i0 <= n - kLutWin); NaN is caught by the tie test
                 gg *= rinv;
                 const double uu = xr * gg, vv = yr * gg;
                 us[j] = fma(uu, cam.c, fma(vv, cam.d, cam.u0));
@@ -337,7 +343,7 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
             int ix[PPL], iy[PPL];
             // Closeness to a rounding tie and the patch range are tracked as integer maxima: the high word of |frac|
             // orders like the double itself (non-negative), a NaN / huge value has a larger high word than any fraction.
-            int worst_frac = 0, worst_mag = 0;
+            int worst_frac = 0;
             unsigned worst_ofs = 0;
 #pragma unroll
             for (int j = 0; j < PPL; ++j) {
@@ -347,14 +353,15 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                 const int hu = __double2hiint(du - (tu - kMagic)) & 0x7fffffff, hv = __double2hiint(dv - (tv - kMagic)) & 0x7fffffff;
                 worst_frac = max(worst_frac, max(hu, hv));
                 worst_ofs = max(worst_ofs, max((unsigned)(ix[j] + kPatchR), (unsigned)(iy[j] + kPatchR)));
-                // |du| >= 2^31 would alias in the low word of the magic sum (and shows |frac| == 0): track the magnitude
-                worst_mag = max(worst_mag, max(__double2hiint(du) & 0x7fffffff, __double2hiint(dv) & 0x7fffffff));
             }
             // closer than ~7e-7 px to a rounding tie (high word of 0.5 - 5e-7), or outside the staged patch -> exact path
+            // (inside the table window |u| is bounded by the fitted polynomial, so the magic-number rounding cannot alias;
+            //  a NaN shows up as a huge high word of the fraction)
             need_exact |= lane_valid && (worst_frac >= __double2hiint(0.5 - 5e-7) || worst_ofs > 2u * kPatchR ||
-                                         worst_mag >= 0x41d00000 /* 2^30 or NaN */);
+                                         worst_idx >= (unsigned)kLutWin);
             if (__any_sync(0xffffffffu, need_exact)) {
-                const unsigned e = exact_pattern<PPL>(&cam, s_pat, ca[q], sa[q], ukx, uky, lane, ds, bimg, uimg, &g, kx, ky);
+                const double aq = q == 0 ? a_base : (q == 1 ? a_base + a_rot : a_base - a_rot);
+                const unsigned e = exact_pattern<PPL>(&cam, s_pat, cos(aq), sin(aq), ukx, uky, lane, ds, bimg, uimg, &g, kx, ky);
 #pragma unroll
                 for (int bb = 0; bb < BPL; ++bb) val[q][bb] = (e >> (8 * bb)) & 0xFFu;
                 continue;
@@ -459,7 +466,17 @@ cudaError_t launch_describe(const PyramidGeom& G, const PyramidGeom* G_dev, int 
                             cudaStream_t st) {
     const long long warps = (long long)n_images * G.sel_total;
     const int blocks = (int)((warps + kDescWarps - 1) / kDescWarps);
-    if (G.desc_size <= 32)
+    static const int variant = getenv("MCS_K3_MINB") ? atoi(getenv("MCS_K3_MINB")) : 5;     // occupancy experiment knob
+    if (G.desc_size <= 32 && variant == 5)
+        describe_kernel<16, 5><<<blocks, kDescWarps * 32, 0, st>>>(G_dev, args, cams, luts, cam_of_image, sel_xys, sel_count, kps, desc,
+                                                                  dmask, counts, capacity, n_images);
+    else if (G.desc_size <= 32 && variant == 6)
+        describe_kernel<16, 6><<<blocks, kDescWarps * 32, 0, st>>>(G_dev, args, cams, luts, cam_of_image, sel_xys, sel_count, kps, desc,
+                                                                  dmask, counts, capacity, n_images);
+    else if (G.desc_size <= 32 && variant == 3)
+        describe_kernel<16, 3><<<blocks, kDescWarps * 32, 0, st>>>(G_dev, args, cams, luts, cam_of_image, sel_xys, sel_count, kps, desc,
+                                                                  dmask, counts, capacity, n_images);
+    else if (G.desc_size <= 32)
         describe_kernel<16><<<blocks, kDescWarps * 32, 0, st>>>(G_dev, args, cams, luts, cam_of_image, sel_xys, sel_count, kps, desc,
                                                                dmask, counts, capacity, n_images);
     else
