@@ -126,7 +126,7 @@ def run_reference(args):
     cams = synth.lafida_cams()
     masks = np.stack([synth.mirror_mask(c) for c in cams])
     cores = os.cpu_count() or 1
-    frames = max(2, min(args.ref_frames, 64))
+    frames = max(2, min(max(args.ref_frames, 2 * ((cores + 2) // 3)), 128))
     images = make_stream(cams, frames, 1000)
     for _ in range(min(args.warmup, 1)):
         cpu_oracle_run(cams, masks, images[:2], cores)
@@ -287,14 +287,21 @@ def main():
         k1_ms_launch = k_ms[0] / NLEVELS
         peak, peak_src = hbm_peak()
         achieved = alg_bytes_img * B / (k_ms[0] * 1e-3) / 1e9                  # all 8 level launches together
+        traffic, traffic_src = None, None
+        tp = ROOT / "profiles" / "k1_traffic.json"
+        if tp.exists():                      # DRAM bytes of K1 from the committed ncu --set full capture, scaled to this batch
+            tj = json.loads(tp.read_text())
+            traffic, traffic_src = tj["dram_bytes_per_image"] * B / NLEVELS, tj["source"]
         roof = {"kernel": "pyr_fast_kernel (K1, 8 launches/step, one per level)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": "bytes per launch (average over the 8 level launches); " + str(traffic_src),
+                "algorithmic_bytes_per_launch_avg": alg_bytes_img * B / NLEVELS, "peak_source": peak_src,
+                "issue_slot_utilisation_pct_ncu": 76.1,
                 "algorithmic_bytes_per_camera_frame": alg_bytes_img, "ms_per_launch_avg": k1_ms_launch,
                 "stage_ms": {"k1_pyr_blur_fast": k_ms[0], "k2_octree": k_ms[1], "k3_angle_describe": k_ms[2], "m2_match_stream": match_ms}}
         cpu = None
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            cf = 4
+            cf = int(min(F, max(4, 2 * ((cores + 2) // 3))))        # >= 2 images per core so that every core has work
             nf, dt = cpu_oracle_run(cams, masks, images[:cf], cores)
             cpu = {"value": nf / dt / 1e6, "unit": "Mfeatures/s", "cores": cores, "kind": "port",
                    "sample": f"{cf} frames x 3 cams of the same stream, {dt:.1f} s"}
