@@ -218,3 +218,64 @@ def test_extract_match_stream(api, oa, cams, masks):
             assert np.array_equal(r["match_idx"][i, :n], order.astype(np.int32))
             assert np.array_equal(r["match_dist"][i, :n], np.take_along_axis(dist, order, axis=1).astype(np.int32))
             assert np.all(r["match_idx"][i, n:] == -1)
+
+
+def test_config4_full_size_bruteforce(api):
+    """BASELINE config 4 size: 32 000 queries vs a 200 000-descriptor database (loop-closure path), with masks.
+    Size-independent properties: every query is planted once with <= 30 flipped bits and must come back as the
+    best match at exactly its planted (masked) distance; the second best is a random descriptor, far away."""
+    rng = np.random.default_rng(4)
+    nd, nq = 200_000, 32_000
+    d = rng.integers(0, 256, (nd, 32), dtype=np.uint8)
+    dm = np.packbits(rng.random((nd, 256)) < 0.85, axis=1, bitorder="little")
+    where = rng.permutation(nd)[:nq]
+    q = d[where].copy()
+    qm = np.packbits(rng.random((nq, 256)) < 0.85, axis=1, bitorder="little")
+    nflip = rng.integers(0, 31, nq)
+    flips = np.zeros((nq, 256), bool)
+    for i in range(nq):
+        flips[i, rng.choice(256, nflip[i], replace=False)] = True
+    fl = np.packbits(flips, axis=1, bitorder="little")
+    q ^= fl
+    idx, dist = api.hamming_topk(q, d, 2, qm, dm)
+    expect = (np.unpackbits(fl & qm, axis=1).sum(axis=1).astype(np.int64) + np.unpackbits(fl & dm[where], axis=1).sum(axis=1)) // 2
+    assert np.array_equal(idx[:, 0], where.astype(np.int32))
+    assert np.array_equal(dist[:, 0], expect.astype(np.int32))
+    assert dist[:, 1].min() > 60 and np.all(dist[:, 1] >= dist[:, 0])
+    # unmasked as well
+    idx2, dist2 = api.hamming_topk(q, d, 1)
+    assert np.array_equal(idx2[:, 0], where.astype(np.int32)) and np.array_equal(dist2[:, 0], nflip.astype(np.int32))
+
+
+def test_config3_full_size_search_by_projection(api, oa, cams):
+    """BASELINE config 3 size: 4 fisheye cameras 1280x720, 2000 feat/cam, SearchByProjection against 50 000 map points."""
+    from multicol_slam_b200 import synth
+    cam4 = [synth.scaled_cam(cams[i % 3], 1280, 720) for i in range(4)]
+    ex = api.mdBRIEFextractorOct(nfeatures=2000, do_dBrief=True, learnMasks=True)
+    imgs = np.stack([synth.frame(cam4[c], 300 + c) for c in range(4)])
+    mk = np.stack([synth.mirror_mask(c) for c in cam4])
+    kps, desc, dmask, counts = ex.extract_batch(imgs, mk, cam4, [0, 1, 2, 3])
+    per = [(kps[c, :counts[c]], desc[c, :counts[c]], dmask[c, :counts[c]]) for c in range(4)]
+    F = api.Frame.from_cameras(per, [(1280, 720)] * 4, [ex.info.scale_factor[l] for l in range(8)])
+    rng = np.random.default_rng(3)
+    nmp = 50_000
+    src = rng.integers(0, len(F.keys), nmp)
+    mdesc = F.desc[src].copy()
+    flips = rng.integers(0, 41, nmp)
+    for i in range(nmp):
+        b = rng.choice(256, flips[i], replace=False)
+        np.bitwise_xor.at(mdesc[i], b // 8, (1 << (b % 8)).astype(np.uint8))
+    in_view = np.zeros((nmp, 4), np.uint8); level = np.zeros((nmp, 4), np.int32)
+    px = np.zeros((nmp, 4)); py = np.zeros((nmp, 4)); vc = np.zeros((nmp, 4))
+    c = F.key_cam[src]
+    r = np.arange(nmp)
+    in_view[r, c] = 1
+    level[r, c] = rng.integers(0, 8, nmp)
+    px[r, c] = F.keys["x"][src] + rng.normal(0, 2, nmp)
+    py[r, c] = F.keys["y"][src] + rng.normal(0, 2, nmp)
+    vc[r, c] = rng.uniform(0.9, 1.0, nmp)
+    mps = api.MapPoints(np.zeros(nmp, np.uint8), in_view, level, px, py, vc, mdesc, F.dmask[src].copy())
+    matcher = api.cORBmatcher(0.8, False, 32, True)
+    n, fmp = matcher.SearchByProjection(F, mps, 3.0)
+    on, ofmp = oa.search_by_projection(F, mps, 3.0, 0.8, matcher.TH_HIGH_, True)
+    assert n == on and np.array_equal(fmp, ofmp) and n > 2000
