@@ -635,7 +635,7 @@ int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams
     const int dpitch = (width + 63) & ~63;
     // Software pipeline over chunks of frames: H2D (copy stream) | re-pitch + K1..K3 + matching (compute stream) |
     // D2H (output stream).  The chunk inputs are copied linearly and re-pitched on the device.
-    const int n_chunks = std::min(std::max(n_frames / 8, 1), 8);       // >= 8 frames per chunk keeps every kernel above one wave
+    const int n_chunks = std::min(std::max(n_frames / 8, 1), 4);       // >= 8 frames per chunk keeps every kernel above one wave
     const int fpc = (n_frames + n_chunks - 1) / n_chunks;             // frames per chunk
     const int ipc = fpc * n_cams;                                     // images per chunk
     const size_t tight_img = (size_t)stride * height, pitched_img = (size_t)dpitch * height;
