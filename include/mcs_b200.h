@@ -261,6 +261,24 @@ int  mcs_search_by_projection(const mcs_frame_view* frame, const mcs_mappoint_vi
                               double th, double nnratio, int32_t th_high, int32_t having_masks,
                               int32_t* frame_mp, int32_t* nmatches);
 
+/* Generic projection-window search: the shape shared by the remaining cORBmatcher searches.
+ * Queries are visited in order; for each one the candidates of GetFeaturesInArea(cam, x, y, r, min_level, max_level)
+ * that are not yet taken (assigned[idx] >= 0) are scanned in the reference's order, best / second best are tracked
+ * with strict `<`, and the best candidate is accepted by `rule`:
+ *   MCS_RULE_RATIO        best <= second*nnratio && best <= threshold   WindowSearch (ref src/cORBmatcher.cpp:420),
+ *                                                                       SearchByProjection(F1,F2,win,..) (:556-558)
+ *   MCS_RULE_BEST         best <= threshold                             SearchByProjection(Current, Last, th) (:2070)
+ *   MCS_RULE_LEVEL_RATIO  best <= threshold && !(bestLevel == secondLevel && best > nnratio*second)
+ *                                                                       SearchByProjection(F, MapPoints, th) (:151-158)
+ * On acceptance assigned[bestIdx] = query_tag[q] (tags must be >= 0).  The caller builds the queries (projection
+ * front-end, "bad"/duplicate filters of the reference loops) and owns `assigned` (in/out, [n_keys], -1 = free). */
+#define MCS_RULE_RATIO        0
+#define MCS_RULE_BEST         1
+#define MCS_RULE_LEVEL_RATIO  2
+int  mcs_search_windows(const mcs_frame_view* frame, const mcs_window_query* queries, int32_t nq,
+                        const uint8_t* qdesc, const uint8_t* qmask, const int32_t* query_tag,
+                        int32_t rule, double nnratio, int32_t threshold, int32_t* assigned, int32_t* nmatches);
+
 /* cORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)
  * (ref :579-726, checkOrientation is compile-time false: include/cORBmatcher.h:40).
  * prev_matched[2*n1] in/out (x,y doubles); matches12[n1] out. */

@@ -338,6 +338,32 @@ def window_search(frame, queries, qdesc, qmask=None, max_cand=64):
     return idx, dist, cnt, rc
 
 
+RULE_RATIO, RULE_BEST, RULE_LEVEL_RATIO = 0, 1, 2
+
+
+def search_windows(frame, queries, qdesc, qmask, query_tag, rule, nnratio, threshold, assigned):
+    """mcs_search_windows: generic projection-window search + greedy acceptance (see include/mcs_b200.h)."""
+    queries = np.ascontiguousarray(queries, WINDOW_QUERY_DTYPE)
+    qdesc = np.ascontiguousarray(qdesc, np.uint8)
+    qmask = None if qmask is None else np.ascontiguousarray(qmask, np.uint8)
+    tags = np.ascontiguousarray(query_tag, np.int32)
+    assigned = np.ascontiguousarray(assigned, np.int32)
+    n = C.c_int32(0)
+    fv = frame.view()
+    if qmask is None:
+        fv.dmask = None
+    _check(lib().mcs_search_windows(C.byref(fv), _p(queries), len(queries), _p(qdesc), _p(qmask), _p(tags), rule,
+                                    C.c_double(nnratio), threshold, _p(assigned), C.byref(n)))
+    return n.value, assigned
+
+
+def _queries(cam, x, y, r, min_level, max_level, desc_index):
+    q = np.zeros(len(cam), WINDOW_QUERY_DTYPE)
+    q["cam"], q["x"], q["y"], q["r"] = cam, x, y, r
+    q["min_level"], q["max_level"], q["desc_index"] = min_level, max_level, desc_index
+    return q
+
+
 class cORBmatcher:
     """ref include/cORBmatcher.h:55-178; thresholds as in src/cORBmatcher.cpp:46-64."""
 
@@ -371,6 +397,44 @@ class cORBmatcher:
         if prev is not vbPrevMatched:
             vbPrevMatched[...] = prev
         return n.value, m12
+
+    def WindowSearch(self, F1, F2, windowSize, valid1, minScaleLevel=0, maxScaleLevel=2**31 - 1):
+        """WindowSearch(F1, F2, windowSize, vpMapPointMatches2, minScaleLevel, maxScaleLevel) (ref :326-474).
+        valid1[i1]: F1 keypoint i1 carries a non-bad map point.  Returns (nmatches, vnMatches21: F1 index per F2 keypoint)."""
+        lv = F1.keys["octave"]
+        sel = np.flatnonzero((np.asarray(valid1) != 0) & ((minScaleLevel <= 0) | (lv >= minScaleLevel)) &
+                             ((maxScaleLevel >= 2**31 - 1) | (lv <= maxScaleLevel)))
+        q = _queries(F1.key_cam[sel], F1.keys["x"][sel].astype(np.float64), F1.keys["y"][sel].astype(np.float64),
+                     float(windowSize), -1, -1, sel)
+        return search_windows(F2, q, F1.desc, F1.dmask if self.havingMasks else None, sel, RULE_RATIO, self.mfNNratio,
+                              self.TH_HIGH_, np.full(len(F2.keys), -1, np.int32))
+
+    def SearchByProjectionFrames(self, F1, F2, windowSize, valid1, uv, in_mask, assigned2=None):
+        """SearchByProjection(F1, F2, windowSize, vpMapPointMatches2) (ref :476-573).  valid1[i1]: keypoint i1 of F1 carries a
+        map point that is not bad, not already found in F2 and not seen before in F1 (the caller's bookkeeping, :490-499);
+        uv[i1, c] = projection of that map point into camera c of F2 (WorldToCamHom_fast), in_mask[i1, c] = isPointInMirrorMask.
+        assigned2 = F2.mvpMapPoints as indices (-1 = NULL).  Returns (nmatches, assigned2 with F1 indices for new matches)."""
+        n1, nc = len(F1.keys), len(F2.cam_w)
+        if assigned2 is None:
+            assigned2 = np.full(len(F2.keys), -1, np.int32)
+        i1, c = np.nonzero((np.asarray(valid1) != 0)[:, None] & (np.asarray(in_mask) != 0))      # i1 outer, camera inner
+        lv = F1.keys["octave"][i1]
+        q = _queries(c, np.asarray(uv)[i1, c, 0], np.asarray(uv)[i1, c, 1], float(windowSize), lv, lv, i1)
+        return search_windows(F2, q, F1.desc, F1.dmask if self.havingMasks else None, i1, RULE_RATIO, self.mfNNratio,
+                              self.TH_HIGH_, assigned2)
+
+    def SearchByProjectionLast(self, CurrentFrame, LastFrame, th, valid_last, uv, in_mask, assigned_cur=None):
+        """SearchByProjection(CurrentFrame, LastFrame, th) (ref :1990-2118, motion model).  valid_last[i]: LastFrame keypoint i has a
+        non-bad, non-outlier map point; uv[i] = its projection into its own camera of CurrentFrame, in_mask[i] = mirror-mask test.
+        Returns (nmatches, CurrentFrame.mvpMapPoints as LastFrame indices)."""
+        if assigned_cur is None:
+            assigned_cur = np.full(len(CurrentFrame.keys), -1, np.int32)
+        sel = np.flatnonzero((np.asarray(valid_last) != 0) & (np.asarray(in_mask) != 0))
+        lv = LastFrame.keys["octave"][sel]
+        r = th * CurrentFrame.scale_factors[lv]
+        q = _queries(LastFrame.key_cam[sel], np.asarray(uv)[sel, 0], np.asarray(uv)[sel, 1], r, lv - 1, lv + 1, sel)
+        return search_windows(CurrentFrame, q, LastFrame.desc, LastFrame.dmask if self.havingMasks else None, sel, RULE_BEST,
+                              self.mfNNratio, self.TH_HIGH_, assigned_cur)
 
     def SearchByBoW(self, desc1, desc2, mask1=None, mask2=None, valid1=None, valid2=None):
         """SearchByBoW(cMultiKeyFrame*, cMultiKeyFrame*, vpMatches12) (ref :885-966): all-pairs scan over the

@@ -194,10 +194,23 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
     const int x0 = (kx - kPatchR) & ~3;                    // >= 0: keypoints lie >= 25 px inside the level
     {
         const int half = lane >> 4, w = lane & 15;
-        for (int r = half; r < 2 * kPatchR + 1; r += 2)
-            if (w < 15)
-                *(uint32_t*)(patch + r * kPatchS + 4 * w) =
-                    __ldg((const uint32_t*)(bimg + (size_t)(ky - kPatchR + r) * pitch + x0) + w);
+        const uint32_t* gp = (const uint32_t*)(bimg + (size_t)(ky - kPatchR + half) * pitch + x0) + w;
+        uint32_t* sp = (uint32_t*)(patch + half * kPatchS) + w;
+        // all loads of a batch are issued before the first store (memory-level parallelism)
+#pragma unroll
+        for (int k0 = 0; k0 < 26; k0 += 13) {
+            uint32_t t[13];
+#pragma unroll
+            for (int k = 0; k < 13; ++k) {
+                const int r = half + 2 * (k0 + k);
+                t[k] = (w < 15 && r < 2 * kPatchR + 1) ? __ldg(gp + (size_t)(k0 + k) * (pitch / 2)) : 0u;
+            }
+#pragma unroll
+            for (int k = 0; k < 13; ++k) {
+                const int r = half + 2 * (k0 + k);
+                if (w < 15 && r < 2 * kPatchR + 1) sp[(k0 + k) * (2 * kPatchS / 4)] = t[k];
+            }
+        }
     }
     const int pofs = kPatchR * kPatchS + (kx - x0);        // patch byte offset of the keypoint itself
 
@@ -209,8 +222,9 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
         const int au = u < 0 ? -u : u;
         // |v| <= vmax(u): the disc is symmetric (umax table, ref :187-202); vmax(|u|) = umax[|u|]
         const int vm = c_disc_u[au];                        // c_disc_u[0..16] doubles as umax[] (see upload_constants)
-        for (int v = -vm; v <= vm; ++v) {
-            const int val = ctr[v * pitch + u];
+#pragma unroll 11
+        for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
+            const int val = (v >= -vm && v <= vm) ? (int)ctr[v * pitch + u] : 0;
             m10 += u * val;
             m01 += v * val;
         }

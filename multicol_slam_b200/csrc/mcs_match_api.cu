@@ -280,6 +280,56 @@ int mcs_window_search(const mcs_frame_view* frame, const mcs_window_query* queri
     return MCS_OK;
 }
 
+int mcs_search_windows(const mcs_frame_view* f, const mcs_window_query* queries, int32_t nq, const uint8_t* qdesc,
+                       const uint8_t* qmask, const int32_t* query_tag, int32_t rule, double nnratio, int32_t threshold,
+                       int32_t* assigned, int32_t* nmatches) {
+    if (!f || !queries || !qdesc || !query_tag || !assigned || !nmatches) return mfail(MCS_ERR_INVALID, "null argument");
+    if (rule < 0 || rule > 2) return mfail(MCS_ERR_INVALID, "unknown rule");
+    *nmatches = 0;
+    if (nq <= 0) return MCS_OK;
+    int rows = 0;
+    for (int i = 0; i < nq; ++i) {
+        if (queries[i].cam < 0 || queries[i].cam >= f->n_cams) return mfail(MCS_ERR_INVALID, "query camera out of range");
+        if (query_tag[i] < 0) return mfail(MCS_ERR_INVALID, "query tags must be >= 0");
+        rows = std::max(rows, queries[i].desc_index + 1);
+    }
+    FrameDev fd;
+    int rc = upload_frame(f, fd, nullptr);
+    if (rc) return rc;
+    std::vector<mcs_window_query> qs(queries, queries + nq);
+    std::vector<int> ci, cd, cc;
+    int mc = 32;
+    rc = window_search_host(fd, qs, qdesc, qmask, rows, f->dim, ci, cd, cc, mc, true, nullptr);
+    if (rc) return rc;
+    int nm = 0;
+    for (int qi = 0; qi < nq; ++qi) {       // sequential greedy replay over the GPU-computed candidate lists
+        const int n = cc[qi];
+        if (n == 0) continue;
+        int bestDist = INT_MAX, bestLevel = -1, bestDist2 = INT_MAX, bestLevel2 = -1, bestIdx = -1;
+        for (int k = 0; k < n; ++k) {
+            const int idx = ci[(size_t)qi * mc + k];
+            if (assigned[idx] >= 0) continue;
+            const int dist = cd[(size_t)qi * mc + k];
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel;
+                bestLevel = f->keys[idx].octave; bestIdx = idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = f->keys[idx].octave; bestDist2 = dist;
+            }
+        }
+        bool ok;
+        if (rule == MCS_RULE_RATIO) ok = (double)bestDist <= (double)bestDist2 * nnratio && bestDist <= threshold;
+        else if (rule == MCS_RULE_BEST) ok = bestDist <= threshold;
+        else ok = bestDist <= threshold && !(bestLevel == bestLevel2 && bestDist > nnratio * bestDist2);
+        if (ok && bestIdx >= 0) {
+            assigned[bestIdx] = query_tag[qi];
+            ++nm;
+        }
+    }
+    *nmatches = nm;
+    return MCS_OK;
+}
+
 int mcs_search_by_projection(const mcs_frame_view* f, const mcs_mappoint_view* mps, double th, double nnratio, int32_t th_high,
                              int32_t having_masks, int32_t* frame_mp, int32_t* nmatches) {
     if (!f || !mps || !frame_mp || !nmatches) return mfail(MCS_ERR_INVALID, "null argument");
@@ -287,6 +337,7 @@ int mcs_search_by_projection(const mcs_frame_view* f, const mcs_mappoint_view* m
     *nmatches = 0;
     // queries in the reference's visiting order: map point outer, camera inner (ref :74-98)
     std::vector<mcs_window_query> qs;
+    std::vector<int> tags;
     const bool bFactor = th != 1.0;
     for (int i = 0; i < mps->n_points; ++i) {
         if (mps->bad && mps->bad[i]) continue;
@@ -301,40 +352,14 @@ int mcs_search_by_projection(const mcs_frame_view* f, const mcs_mappoint_view* m
             q.cam = cam; q.min_level = lvl - 1; q.max_level = lvl; q.desc_index = i;
             q.x = mps->proj_x[k]; q.y = mps->proj_y[k]; q.r = r * f->scale_factors[lvl];
             qs.push_back(q);
+            tags.push_back(i);
         }
     }
     if (qs.empty()) return MCS_OK;
-    FrameDev fd;
-    int rc = upload_frame(f, fd, nullptr);
-    if (rc) return rc;
-    std::vector<int> ci, cd, cc;
-    int mc = 32;
-    rc = window_search_host(fd, qs, mps->desc, having_masks ? mps->dmask : nullptr, mps->n_points, f->dim, ci, cd, cc, mc, true, nullptr);
-    if (rc) return rc;
-    int nm = 0;
-    for (size_t qi = 0; qi < qs.size(); ++qi) {   // greedy replay (ref :100-164)
-        const int n = cc[qi];
-        if (n == 0) continue;
-        int bestDist = INT_MAX, bestLevel = -1, bestDist2 = INT_MAX, bestLevel2 = -1, bestIdx = -1;
-        for (int k = 0; k < n; ++k) {
-            const int idx = ci[qi * mc + k];
-            if (frame_mp[idx] >= 0) continue;
-            const int dist = cd[qi * mc + k];
-            if (dist < bestDist) {
-                bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel;
-                bestLevel = f->keys[idx].octave; bestIdx = idx;
-            } else if (dist < bestDist2) {
-                bestLevel2 = f->keys[idx].octave; bestDist2 = dist;
-            }
-        }
-        if (bestDist <= th_high) {
-            if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
-            frame_mp[bestIdx] = qs[qi].desc_index;
-            ++nm;
-        }
-    }
-    *nmatches = nm;
-    return MCS_OK;
+    mcs_frame_view fv = *f;
+    if (!having_masks) fv.dmask = nullptr;
+    return mcs_search_windows(&fv, qs.data(), (int)qs.size(), mps->desc, having_masks ? mps->dmask : nullptr, tags.data(),
+                              MCS_RULE_LEVEL_RATIO, nnratio, th_high, frame_mp, nmatches);
 }
 
 int mcs_search_for_initialization(const mcs_frame_view* f1, const mcs_frame_view* f2, double* prev_matched, int32_t window_size,

@@ -75,6 +75,7 @@ pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int
     __shared__ int16_t s_xs0[kTileW], s_xs1[kTileW], s_xa0[kTileW], s_xa1[kTileW];
     __shared__ int16_t s_ys0[kTileH], s_ys1[kTileH], s_yb0[kTileH], s_yb1[kTileH];
     __shared__ int16_t s_cellx[kTW + 2], s_celly[kTH + 2];
+    __shared__ int16_t s_mx[kTW], s_my[kTH];                          // level-0 mask coordinates of the tile's pixels
     __shared__ uint32_t s_list[kMaxTileCorners];
     __shared__ int s_n, s_base;
 
@@ -118,6 +119,12 @@ pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int
     if (tid < kTH + 2) {
         const int y = Y0 - 1 + tid;
         s_celly[tid] = (y >= 0 && y < g.h) ? g.celly[y] : (int16_t)-1;
+    } else if (tid >= 64 && tid < 64 + kTW) {
+        const int x = X0 + tid - 64;
+        s_mx[tid - 64] = x < g.w ? g.mx0[x] : (int16_t)0;
+    } else if (tid >= 128 && tid < 128 + kTH) {
+        const int y = Y0 + tid - 128;
+        s_my[tid - 128] = y < g.h ? g.my0[y] : (int16_t)0;
     }
     // ---- stage the source rows: 16-byte chunks, one warp per row ----
     {
@@ -261,7 +268,7 @@ pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int
             const int sv = (int)((C >> (16 * h)) & 0xFFFFu), nv = (int)((nm >> (16 * h)) & 0xFFFFu);
             if (sv > nv) {                                                        // strict maximum of its 3x3 (sv > 0)
                 const int gx = X0 + 2 * j + h, gy = Y0 + y;
-                if (m0p[(size_t)g.my0[gy] * mask_w + g.mx0[gx]] != 0) {
+                if (m0p[(size_t)s_my[y] * mask_w + s_mx[2 * j + h]] != 0) {
                     const int pos = atomicAdd(&s_n, 1);
                     s_list[pos] = pack_corner(gx, gy, sv);
                 }

@@ -27,6 +27,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <list>
+#include <atomic>
+#include <malloc.h>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -979,6 +982,41 @@ int mcso_search_by_projection(const mcs_frame_view* f, const mcs_mappoint_view* 
     return 0;
 }
 
+// Generic window search with the acceptance rules of WindowSearch (src/cORBmatcher.cpp:326-474, rule 0),
+// SearchByProjection(Current, Last, th) (:1990-2118, rule 1) and SearchByProjection(F, MapPoints, th) (:67-166, rule 2);
+// the per-candidate loop is the one those functions share (:385-418, :2046-2068, :115-148).
+int mcso_search_windows(const mcs_frame_view* f, const mcs_window_query* qs, int nq, const uint8_t* qdesc, const uint8_t* qmask,
+                        const int* query_tag, int rule, double nnratio, int threshold, int* assigned, int* nmatches) {
+    Grid g; build_grid(*f, g);
+    std::vector<int> near;
+    const bool masks = qmask && f->dmask;
+    int nm = 0;
+    for (int i = 0; i < nq; ++i) {
+        const mcs_window_query& q = qs[i];
+        features_in_area(*f, g, q.cam, q.x, q.y, q.r, q.min_level, q.max_level, near);
+        if (near.empty()) continue;
+        int bestDist = INT_MAX, bestLevel = -1, bestDist2 = INT_MAX, bestLevel2 = -1, bestIdx = -1;
+        for (int idx : near) {
+            if (assigned[idx] >= 0) continue;
+            const int dist = masks ? dist64m(row64(qdesc, q.desc_index, f->dim), row64(f->desc, idx, f->dim),
+                                             row64(qmask, q.desc_index, f->dim), row64(f->dmask, idx, f->dim), f->dim)
+                                   : dist64(row64(qdesc, q.desc_index, f->dim), row64(f->desc, idx, f->dim), f->dim);
+            if (dist < bestDist) {
+                bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = f->keys[idx].octave; bestIdx = idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = f->keys[idx].octave; bestDist2 = dist;
+            }
+        }
+        bool ok;
+        if (rule == 0) ok = bestDist <= bestDist2 * nnratio && bestDist <= threshold;
+        else if (rule == 1) ok = bestDist <= threshold;
+        else ok = bestDist <= threshold && !(bestLevel == bestLevel2 && bestDist > nnratio * bestDist2);
+        if (ok && bestIdx >= 0) { assigned[bestIdx] = query_tag[i]; ++nm; }
+    }
+    *nmatches = nm;
+    return 0;
+}
+
 // cORBmatcher::SearchForInitialization  src/cORBmatcher.cpp:579-726 (mbCheckOrientation == false)
 int mcso_search_for_initialization(const mcs_frame_view* f1, const mcs_frame_view* f2, double* prev_matched,
                                    int window_size, double nnratio, int th_low, int having_masks, int* matches12,
@@ -1019,6 +1057,62 @@ int mcso_search_for_initialization(const mcs_frame_view* f1, const mcs_frame_vie
         }
     *nmatches = nm;
     return 0;
+}
+
+// Multi-threaded driver for the CPU baseline of bench.py: n_frames x n_cams images (frame-major), one oracle extractor per
+// worker thread (the reference runs one thread per camera, src/cMultiFrame.cpp:128), then SearchByBoW-style brute force
+// of every (frame, camera) against (frame-1, camera).  Returns the number of features; *n_matches gets the match count.
+long mcso_stream_mt(const mcs_extractor_params* p, int n_threads, int n_frames, int n_cams, const uint8_t* images, int w, int h,
+                    const uint8_t* masks, const mcs_ocam* cams, int th_low, double nnratio, long* n_matches) {
+    // keep freed blocks in the per-thread arenas instead of mmap/munmap-ing every large temporary: with many worker
+    // threads the page-fault / mmap_sem traffic otherwise dominates and the baseline stops scaling with the core count
+    mallopt(M_MMAP_THRESHOLD, 1 << 30);
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
+    const int n_img = n_frames * n_cams, ds = p->desc_size;
+    const int cap = p->nfeatures + 16 * p->nlevels;
+    std::vector<std::vector<mcs_keypoint>> kps(n_img);
+    std::vector<std::vector<uint8_t>> desc(n_img), dmask(n_img);
+    std::vector<int> counts(n_img, 0);
+    std::atomic<int> next(0), nextm(n_cams);
+    std::atomic<long> matches(0);
+    auto work = [&]() {
+        Extractor* e = make_extractor(*p);
+        std::vector<mcs_keypoint> k(cap);
+        std::vector<uint8_t> d((size_t)cap * ds), m((size_t)cap * ds);
+        for (int i; (i = next.fetch_add(1)) < n_img;) {
+            const int c = i % n_cams;
+            Img im(w, h), mk(w, h);
+            std::memcpy(im.d.data(), images + (size_t)i * w * h, (size_t)w * h);
+            std::memcpy(mk.d.data(), masks + (size_t)c * w * h, (size_t)w * h);
+            const int n = extract(*e, im, mk, cams[c], k.data(), d.data(), m.data(), cap);
+            counts[i] = std::max(n, 0);
+            kps[i].assign(k.begin(), k.begin() + counts[i]);
+            desc[i].assign(d.begin(), d.begin() + (size_t)counts[i] * ds);
+            dmask[i].assign(m.begin(), m.begin() + (size_t)counts[i] * ds);
+        }
+        delete e;
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(work);
+    for (auto& t : th) t.join();
+    auto matchwork = [&]() {
+        std::vector<int> m12;
+        for (int i; (i = nextm.fetch_add(1)) < n_img;) {
+            m12.assign(counts[i], -1);
+            int nm = 0;
+            mcso_match_bruteforce(desc[i].data(), p->learn_masks ? dmask[i].data() : nullptr, nullptr, counts[i], desc[i - n_cams].data(),
+                                  p->learn_masks ? dmask[i - n_cams].data() : nullptr, nullptr, counts[i - n_cams], ds, th_low, nnratio,
+                                  m12.data(), &nm);
+            matches += nm;
+        }
+    };
+    th.clear();
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(matchwork);
+    for (auto& t : th) t.join();
+    long total = 0;
+    for (int c : counts) total += c;
+    if (n_matches) *n_matches = matches.load();
+    return total;
 }
 
 }  // extern "C"

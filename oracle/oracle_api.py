@@ -177,3 +177,34 @@ def distance64(a, b, dim=32):
 def distance64_masked(a, b, ma, mb, dim=32):
     a, b, ma, mb = (np.ascontiguousarray(v, np.uint8) for v in (a, b, ma, mb))
     return lib().mcso_descriptor_distance64_masked(_p(a), _p(b), _p(ma), _p(mb), dim)
+
+
+def search_windows(frame, queries, qdesc, qmask, query_tag, rule, nnratio, threshold, assigned):
+    from multicol_slam_b200.ctypes_defs import WINDOW_QUERY_DTYPE
+    queries = np.ascontiguousarray(queries, WINDOW_QUERY_DTYPE)
+    qdesc = np.ascontiguousarray(qdesc, np.uint8)
+    qmask = None if qmask is None else np.ascontiguousarray(qmask, np.uint8)
+    tags = np.ascontiguousarray(query_tag, np.int32)
+    assigned = np.ascontiguousarray(assigned, np.int32).copy()
+    n = C.c_int(0)
+    fv = frame.view()
+    if qmask is None:
+        fv.dmask = None
+    lib().mcso_search_windows(C.byref(fv), _p(queries), len(queries), _p(qdesc), _p(qmask), _p(tags), rule, C.c_double(nnratio),
+                              threshold, _p(assigned), C.byref(n))
+    return n.value, assigned
+
+
+def stream_mt(images, masks, cams, n_threads, nfeatures=2000, nlevels=8, do_dbrief=True, learn_masks=True, th_low=32, nnratio=0.9):
+    """images [F,C,H,W]: multi-threaded C++ driver (std::thread) of extraction + previous-frame brute-force matching.
+    Returns (n_features, n_matches).  Used by bench.py's CPU baseline / reference arm."""
+    from multicol_slam_b200.ctypes_defs import Ocam
+    images = np.ascontiguousarray(images, np.uint8)
+    masks = np.ascontiguousarray(masks, np.uint8)
+    F, Cn, H, W = images.shape
+    p = make_params(nfeatures=nfeatures, nlevels=nlevels, do_dbrief=do_dbrief, learn_masks=learn_masks)
+    ocs = (Ocam * Cn)(*[c if isinstance(c, Ocam) else make_ocam(c) for c in cams])
+    nm = C.c_long(0)
+    lib().mcso_stream_mt.restype = C.c_long
+    n = lib().mcso_stream_mt(C.byref(p), n_threads, F, Cn, _p(images), W, H, _p(masks), ocs, th_low, C.c_double(nnratio), C.byref(nm))
+    return n, nm.value

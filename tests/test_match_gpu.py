@@ -279,3 +279,69 @@ def test_config3_full_size_search_by_projection(api, oa, cams):
     n, fmp = matcher.SearchByProjection(F, mps, 3.0)
     on, ofmp = oa.search_by_projection(F, mps, 3.0, 0.8, matcher.TH_HIGH_, True)
     assert n == on and np.array_equal(fmp, ofmp) and n > 2000
+
+
+@pytest.mark.parametrize("masks", [False, True])
+def test_m4_window_searches(api, oa, cams, masks):
+    """The remaining projection-window searches through mcs_search_windows: WindowSearch (:326),
+    SearchByProjection(F1,F2,win) (:476), SearchByProjection(Current,Last,th) (:1990) vs the oracle's generic loop."""
+    from multicol_slam_b200 import synth
+    from multicol_slam_b200.api import RULE_BEST, RULE_RATIO, _queries
+    ex = api.mdBRIEFextractorOct(nfeatures=700, do_dBrief=True, learnMasks=masks)
+    sf = [ex.info.scale_factor[l] for l in range(8)]
+    fr = []
+    for t in range(2):
+        per = [ex(synth.texture_stream(cams[c], 2, seed=60 + c)[t], synth.mirror_mask(cams[c]), cams[c]) for c in range(3)]
+        fr.append(api.Frame.from_cameras(per, [(754, 480)] * 3, sf))
+    F1, F2 = fr
+    rng = np.random.default_rng(8)
+    valid1 = (rng.random(len(F1.keys)) < 0.8).astype(np.uint8)
+    m = api.cORBmatcher(0.8, False, 32, masks)
+    qm = F1.dmask if masks else None
+
+    # WindowSearch
+    n, m21 = m.WindowSearch(F1, F2, 60, valid1, 0, 5)
+    lv = F1.keys["octave"]
+    sel = np.flatnonzero((valid1 != 0) & (lv <= 5))
+    q = _queries(F1.key_cam[sel], F1.keys["x"][sel].astype(np.float64), F1.keys["y"][sel].astype(np.float64), 60.0, -1, -1, sel)
+    on, om21 = oa.search_windows(F2, q, F1.desc, qm, sel, RULE_RATIO, 0.8, m.TH_HIGH_, np.full(len(F2.keys), -1, np.int32))
+    assert n == on and np.array_equal(m21, om21) and n > 300
+
+    # SearchByProjection(F1, F2, windowSize): projections = F1 keypoint position moved by the stream motion, all cameras tried
+    uv = np.zeros((len(F1.keys), 3, 2))
+    in_mask = np.zeros((len(F1.keys), 3), np.uint8)
+    for c in range(3):
+        uv[:, c, 0] = F1.keys["x"] - 3.0 + rng.normal(0, 1, len(F1.keys))
+        uv[:, c, 1] = F1.keys["y"] - 2.0 + rng.normal(0, 1, len(F1.keys))
+        in_mask[:, c] = (F1.key_cam == c) | (rng.random(len(F1.keys)) < 0.1)
+    pre = np.full(len(F2.keys), -1, np.int32)
+    pre[::7] = 0
+    n2, a2 = m.SearchByProjectionFrames(F1, F2, 40, valid1, uv, in_mask, pre.copy())
+    i1, c = np.nonzero((valid1 != 0)[:, None] & (in_mask != 0))
+    q = _queries(c, uv[i1, c, 0], uv[i1, c, 1], 40.0, lv[i1], lv[i1], i1)
+    on2, oa2 = oa.search_windows(F2, q, F1.desc, qm, i1, RULE_RATIO, 0.8, m.TH_HIGH_, pre.copy())
+    assert n2 == on2 and np.array_equal(a2, oa2) and n2 > 300
+
+    # SearchByProjection(CurrentFrame = F2, LastFrame = F1, th)
+    uvl = np.stack([F1.keys["x"] - 3.0, F1.keys["y"] - 2.0], axis=1).astype(np.float64)
+    inm = (rng.random(len(F1.keys)) < 0.95).astype(np.uint8)
+    n3, a3 = m.SearchByProjectionLast(F2, F1, 50.0, valid1, uvl, inm)
+    sel = np.flatnonzero((valid1 != 0) & (inm != 0))
+    l3 = lv[sel]
+    q = _queries(F1.key_cam[sel], uvl[sel, 0], uvl[sel, 1], 50.0 * F2.scale_factors[l3], l3 - 1, l3 + 1, sel)
+    on3, oa3 = oa.search_windows(F2, q, F1.desc, qm, sel, RULE_BEST, 0.8, m.TH_HIGH_, np.full(len(F2.keys), -1, np.int32))
+    assert n3 == on3 and np.array_equal(a3, oa3) and n3 > 300
+
+    # the generic entry point with the level rule reproduces the dedicated SearchByProjection(F, MapPoints) oracle
+    nmp = 1500
+    src = rng.integers(0, len(F2.keys), nmp)
+    nc = 3
+    in_view = np.zeros((nmp, nc), np.uint8); level = np.zeros((nmp, nc), np.int32)
+    px = np.zeros((nmp, nc)); py = np.zeros((nmp, nc)); vc = np.full((nmp, nc), 0.95)
+    cc = F2.key_cam[src]; r = np.arange(nmp)
+    in_view[r, cc] = 1; level[r, cc] = F2.keys["octave"][src]
+    px[r, cc] = F2.keys["x"][src]; py[r, cc] = F2.keys["y"][src]
+    mps = api.MapPoints(np.zeros(nmp, np.uint8), in_view, level, px, py, vc, F2.desc[src], F2.dmask[src] if masks else None)
+    n4, f4 = m.SearchByProjection(F2, mps, 3.0)
+    on4, of4 = oa.search_by_projection(F2, mps, 3.0, 0.8, m.TH_HIGH_, masks)
+    assert n4 == on4 and np.array_equal(f4, of4)
