@@ -84,6 +84,19 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def usable_cores():
+    """Host threads this process may really use: min(affinity, cgroup CPU quota).  The GPU boxes expose 128 logical CPUs but
+    cap the container at a 16-CPU quota (cpu.max = 1600000 100000); more threads than that only add throttling."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
 def cpu_oracle_run(cams, masks, images, n_threads):
     """Oracle port (oracle/mcs_oracle.cpp) over `images` [F,3,H,W] with n_threads host threads: extraction per
     (frame, camera) in parallel (the reference parallelises over cameras, src/cMultiFrame.cpp:128), then the
@@ -105,7 +118,7 @@ def run_reference(args):
         return
     cams = synth.lafida_cams()
     masks = np.stack([synth.mirror_mask(c) for c in cams])
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     frames = max(2, min(max(args.ref_frames, 2 * ((cores + 2) // 3)), 128))
     images = make_stream(cams, frames, 1000)
     for _ in range(max(min(args.warmup, 1), 1)):
@@ -121,7 +134,7 @@ def run_reference(args):
                       "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                       "config": {"workload": WORKLOAD, "sample": sample},
-                      "cpu_baseline": {"value": val, "unit": "Mfeatures/s", "cores": cores, "kind": "port", "sample": sample},
+                      "cpu_baseline": {"value": val, "unit": "Mfeatures/s", "cores": cores, "logical_cpus": os.cpu_count(), "kind": "port", "sample": sample},
                       "e2e": {"value": val, "unit": "Mfeatures/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -280,11 +293,11 @@ def main():
                 "stage_ms": {"k1_pyr_blur_fast": k_ms[0], "k2_octree": k_ms[1], "k3_angle_describe": k_ms[2], "m2_match_stream": match_ms}}
         cpu = None
         if not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
+            cores = usable_cores()
             cf = int(min(F, max(4, 2 * ((cores + 2) // 3))))        # >= 2 images per core so that every core has work
             cpu_oracle_run(cams, masks, images[:cf], cores)          # warm-up (per-thread malloc arenas, page faults)
             nf, dt = cpu_oracle_run(cams, masks, images[:cf], cores)
-            cpu = {"value": nf / dt / 1e6, "unit": "Mfeatures/s", "cores": cores, "kind": "port",
+            cpu = {"value": nf / dt / 1e6, "unit": "Mfeatures/s", "cores": cores, "logical_cpus": os.cpu_count(), "kind": "port",
                    "sample": f"{cf} frames x 3 cams of the same stream, {dt:.1f} s wall on {cores} threads (C++ std::thread driver), after one warm-up pass"}
         print(json.dumps({
             "metric": "Mfeatures/s extract+match", "value": value, "unit": "Mfeatures/s", "n_gpus": world, "steps": args.steps,
