@@ -59,7 +59,7 @@ __device__ __forceinline__ unsigned fast_margin2(unsigned C, const unsigned (&R)
     return __vmaxs2(bright, vneg2(darkn));
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 5)
 pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int fast_th, const int src_aligned,
                 const uint8_t* __restrict__ src, const size_t src_img_bytes,
                 uint8_t* __restrict__ dst, uint8_t* __restrict__ dst_blur,
@@ -160,6 +160,7 @@ pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int
         const int tx = 2 * pc;
         const int xs00 = s_xs0[tx], xs01 = s_xs1[tx], xs10 = s_xs0[tx + 1], xs11 = s_xs1[tx + 1];
         const int a00 = s_xa0[tx], a01 = s_xa1[tx], a10 = s_xa0[tx + 1], a11 = s_xa1[tx + 1];
+#pragma unroll
         for (int ty = rg; ty < kTileH; ty += 7) {
             const uint8_t* r0 = s_src + s_ys0[ty] * kSrcWB;
             const uint8_t* r1 = s_src + s_ys1[ty] * kSrcWB;
@@ -195,12 +196,14 @@ pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int
     uint8_t* dimg = dst + (size_t)b * g.img_bytes;
     uint8_t* bimg = dst_blur + (size_t)b * g.img_bytes;
     // ---- (a) store the unblurred tile, 4 px per thread ----
+#pragma unroll
     for (int i = tid; i < kTH * (kTW / 4); i += kThreads) {
         const int y = i >> 4, x4 = (i & 15) * 4;
         if (Y0 + y < g.h && X0 + x4 < g.pitch)
             *(uint32_t*)(dimg + (size_t)(Y0 + y) * g.pitch + X0 + x4) = *(const uint32_t*)(s_t8 + (y + kHalo) * kT8S + x4 + kHalo);
     }
     // ---- (b) packed horizontal 5-sums of pixel pairs (rows Y0-2 .. Y0+33) ----
+#pragma unroll
     for (int i = tid; i < (kTH + 4) * (kTW / 2); i += kThreads) {
         const int y = i >> 5, j = i & 31;
         const uint32_t* w0 = (const uint32_t*)(s_a0 + (y + kHalo - 2) * kT16S) + (kHalo / 2 + j);   // pair (x, x+1), x = tile col 4+2j
@@ -208,6 +211,7 @@ pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int
         s_h[i] = __vadd2(__vadd2(__vadd2(w0[-1], w1[-1]), __vadd2(w0[0], w1[0])), w0[1]);
     }
     // ---- (c) FAST margins of pixel pairs on the tile + 1 ring; pairs start at tile column 3 (odd) ----
+#pragma unroll
     for (int i = tid; i < (kTH + 2) * ((kTW + 2) / 2); i += kThreads) {
         const int y = i / ((kTW + 2) / 2), j = i - y * ((kTW + 2) / 2);
         const int sx = 2 * j;                                   // score-tile column of the first pixel of the pair
@@ -236,6 +240,7 @@ pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int
     __syncthreads();
 
     // ---- (d) blurred tile: vertical 5-sum of the packed row sums, (S+12)/25, 4 px per thread ----
+#pragma unroll
     for (int i = tid; i < kTH * (kTW / 4); i += kThreads) {
         const int y = i >> 4, q = i & 15;
         if (Y0 + y < g.h && X0 + 4 * q < g.pitch) {
@@ -252,6 +257,7 @@ pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int
     // Pair j of row y = pixels x = 2j, 2j+1 = score-tile columns 2j+1, 2j+2: centre word from the odd copy, left /
     // right neighbour pairs from the even copy.  A neighbour outside the pixel's FAST cell counts as 0 (cv::FAST runs per cell).
     const uint8_t* m0p = mask0 + (size_t)cam_of_image[b] * mask_bytes;
+#pragma unroll
     for (int i = tid; i < kTH * (kTW / 2); i += kThreads) {
         const int y = i >> 5, j = i & 31;
         const uint32_t* e0 = (const uint32_t*)(s_s0 + y * kScoreS) + j;          // row y-1 of the interior row y (score row y)
@@ -269,8 +275,13 @@ pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int
             if (sv > nv) {                                                        // strict maximum of its 3x3 (sv > 0)
                 const int gx = X0 + 2 * j + h, gy = Y0 + y;
                 if (m0p[(size_t)s_my[y] * mask_w + s_mx[2 * j + h]] != 0) {
-                    const int pos = atomicAdd(&s_n, 1);
-                    s_list[pos] = pack_corner(gx, gy, sv);
+                    // warp-aggregated append: one shared-memory atomic per warp and pass
+                    const unsigned am = __activemask();
+                    const int leader = __ffs(am) - 1;
+                    int base = 0;
+                    if (lane == leader) base = atomicAdd(&s_n, __popc(am));
+                    base = __shfl_sync(am, base, leader);
+                    s_list[base + __popc(am & ((1u << lane) - 1u))] = pack_corner(gx, gy, sv);
                 }
             }
         }
