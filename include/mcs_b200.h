@@ -261,6 +261,19 @@ int  mcs_search_by_projection(const mcs_frame_view* frame, const mcs_mappoint_vi
                               double th, double nnratio, int32_t th_high, int32_t having_masks,
                               int32_t* frame_mp, int32_t* nmatches);
 
+/* ---- projection front-end of SearchByProjection (SURVEY 8f "next" row 2) ------------------------ */
+/* cMultiFrame::isInFrustum(cam, pMP, .) for every (map point, camera) (ref src/cMultiFrame.cpp:218-270) with
+ * cMultiCamSys_::WorldToCamHom_fast (ref src/cam_system_omni.cpp:92-112) and isPointInMirrorMask
+ * (ref src/cam_model_omni.cpp:163-178): fills exactly the arrays mcs_mappoint_view / mcs_search_by_projection consume.
+ *   mtmc_inv, mtmc: [n_cams*16] row-major 4x4 (MtMc_inv[c] and Get_MtMc(c)); masks: n_cams level-0 mirror masks (h*w each);
+ *   world_pos, normal: [n_points*3]; min_dist, max_dist: [n_points] (Get{Min,Max}DistanceInvariance);
+ *   outputs indexed [point*n_cams + cam].  Host buffers.  Integer outputs (in_view, level) are exact; the projections go
+ *   through atan(), so they agree with a CPU evaluation to ~1e-13 px. */
+int  mcs_project_mappoints(int32_t n_cams, const double* mtmc_inv, const double* mtmc, const mcs_ocam* cams,
+                           const uint8_t* masks, int32_t n_points, const double* world_pos, const double* normal,
+                           const double* min_dist, const double* max_dist, const double* scale_factors, int32_t n_levels,
+                           uint8_t* in_view, int32_t* level, double* proj_x, double* proj_y, double* view_cos);
+
 /* Generic projection-window search: the shape shared by the remaining cORBmatcher searches.
  * Queries are visited in order; for each one the candidates of GetFeaturesInArea(cam, x, y, r, min_level, max_level)
  * that are not yet taken (assigned[idx] >= 0) are scanned in the reference's order, best / second best are tracked

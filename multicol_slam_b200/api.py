@@ -338,6 +338,27 @@ def window_search(frame, queries, qdesc, qmask=None, max_cand=64):
     return idx, dist, cnt, rc
 
 
+def project_mappoints(mtmc_inv, mtmc, cams, masks, world_pos, normal, min_dist, max_dist, scale_factors):
+    """Batched cMultiFrame::isInFrustum (ref src/cMultiFrame.cpp:218-270): mtmc_inv / mtmc [n_cams,4,4], masks [n_cams,H,W],
+    world_pos / normal [n,3].  Returns (in_view [n,n_cams] u8, level i32, proj_x, proj_y, view_cos f64) -- the MapPoints fields."""
+    mi = np.ascontiguousarray(mtmc_inv, np.float64)
+    mm = np.ascontiguousarray(mtmc, np.float64)
+    masks = np.ascontiguousarray(masks, np.uint8)
+    pos = np.ascontiguousarray(world_pos, np.float64)
+    nrm = np.ascontiguousarray(normal, np.float64)
+    dmin = np.ascontiguousarray(min_dist, np.float64)
+    dmax = np.ascontiguousarray(max_dist, np.float64)
+    sf = np.ascontiguousarray(scale_factors, np.float64)
+    nc, n = len(cams), len(pos)
+    ocs = (Ocam * nc)(*[as_ocam(c) for c in cams])
+    in_view = np.zeros((n, nc), np.uint8)
+    level = np.zeros((n, nc), np.int32)
+    px, py, vc = np.zeros((n, nc)), np.zeros((n, nc)), np.zeros((n, nc))
+    _check(lib().mcs_project_mappoints(nc, _p(mi), _p(mm), ocs, _p(masks), n, _p(pos), _p(nrm), _p(dmin), _p(dmax), _p(sf), len(sf),
+                                       _p(in_view), _p(level), _p(px), _p(py), _p(vc)))
+    return in_view, level, px, py, vc
+
+
 RULE_RATIO, RULE_BEST, RULE_LEVEL_RATIO = 0, 1, 2
 
 

@@ -8,6 +8,7 @@
 //   M1/M3 window_search_kernel : GetFeaturesInArea (ref src/cMultiFrame.cpp:272-340) + distance to every
 //                            candidate, one warp per query, candidates emitted in the reference's visiting
 //                            order (cell-x outer, cell-y inner, insertion order inside a cell).
+#include "cam_model.cuh"
 #include "mcs_common.cuh"
 #include "kernels.h"
 
@@ -399,6 +400,55 @@ cudaError_t launch_window_search(const WindowFrameDev& f, const mcs_window_query
     else if (f.dim == 64) { if (masked) MCS_WS(16, true); else MCS_WS(16, false); }
     else return cudaErrorInvalidValue;
 #undef MCS_WS
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// projection front-end: isInFrustum for every (map point, camera)   (ref src/cMultiFrame.cpp:218-270)
+// ------------------------------------------------------------------------------------------------
+__global__ void frustum_kernel(const int n_cams, const double* __restrict__ mtmc_inv, const double* __restrict__ mtmc,
+                               const mcs_ocam* __restrict__ cams, const uint8_t* __restrict__ masks, const int n_points,
+                               const double* __restrict__ pos, const double* __restrict__ nrm, const double* __restrict__ dmin,
+                               const double* __restrict__ dmax, const double* __restrict__ sf, const int n_levels,
+                               uint8_t* __restrict__ in_view, int* __restrict__ level, double* __restrict__ px, double* __restrict__ py,
+                               double* __restrict__ vcos) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_points * n_cams) return;
+    const int i = t / n_cams, c = t - i * n_cams;
+    in_view[t] = 0; level[t] = 0; px[t] = 0.0; py[t] = 0.0; vcos[t] = 0.0;
+    const double P0 = pos[3 * i], P1 = pos[3 * i + 1], P2 = pos[3 * i + 2];
+    // ptRot = MtMc_inv[c] * (P,1): cv::Matx product, s = 0 + a0 b0 + a1 b1 + a2 b2 + a3 b3 in this order, no FMA
+    const double* M = mtmc_inv + 16 * c;
+    double r[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) r[k] = ((M[4 * k] * P0 + M[4 * k + 1] * P1) + M[4 * k + 2] * P2) + M[4 * k + 3] * 1.0;
+    const mcs_ocam cam = cams[c];
+    double u, v;
+    cam_world_to_img(cam, r[0], r[1], r[2], u, v);
+    // isPointInMirrorMask(u, v, 0)  (ref src/cam_model_omni.cpp:163-178)
+    const int ur = __double2int_rn(u), vr = __double2int_rn(v);
+    if (ur >= cam.width || ur <= 0 || vr >= cam.height || vr <= 0) return;
+    if (masks[(size_t)c * cam.width * cam.height + (size_t)vr * cam.width + ur] == 0) return;
+    // distance to the camera centre, scale-invariance region
+    const double* T = mtmc + 16 * c;
+    const double o0 = P0 - T[3], o1 = P1 - T[7], o2 = P2 - T[11];
+    const double dist = sqrt((o0 * o0 + o1 * o1) + o2 * o2);
+    if (dist < dmin[i] || dist > dmax[i]) return;
+    const double viewCos = ((o0 * nrm[3 * i] + o1 * nrm[3 * i + 1]) + o2 * nrm[3 * i + 2]) / dist;
+    const double ratio = dist / dmin[i];
+    int lv = 0;                                   // std::lower_bound(mvScaleFactors, ratio)
+    while (lv < n_levels && sf[lv] < ratio) ++lv;
+    if (lv >= n_levels) lv = n_levels - 1;
+    in_view[t] = 1; px[t] = u; py[t] = v; level[t] = lv; vcos[t] = viewCos;
+}
+
+cudaError_t launch_frustum(int n_cams, const double* mtmc_inv, const double* mtmc, const mcs_ocam* cams, const uint8_t* masks,
+                           int n_points, const double* pos, const double* nrm, const double* dmin, const double* dmax, const double* sf,
+                           int n_levels, uint8_t* in_view, int* level, double* px, double* py, double* vcos, cudaStream_t st) {
+    const long long n = (long long)n_points * n_cams;
+    if (n <= 0) return cudaSuccess;
+    frustum_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(n_cams, mtmc_inv, mtmc, cams, masks, n_points, pos, nrm, dmin, dmax, sf,
+                                                                n_levels, in_view, level, px, py, vcos);
     return cudaGetLastError();
 }
 

@@ -280,6 +280,47 @@ int mcs_window_search(const mcs_frame_view* frame, const mcs_window_query* queri
     return MCS_OK;
 }
 
+int mcs_project_mappoints(int32_t n_cams, const double* mtmc_inv, const double* mtmc, const mcs_ocam* cams, const uint8_t* masks,
+                          int32_t n_points, const double* world_pos, const double* normal, const double* min_dist,
+                          const double* max_dist, const double* scale_factors, int32_t n_levels, uint8_t* in_view, int32_t* level,
+                          double* proj_x, double* proj_y, double* view_cos) {
+    if (!mtmc_inv || !mtmc || !cams || !masks || !world_pos || !normal || !min_dist || !max_dist || !scale_factors || !in_view ||
+        !level || !proj_x || !proj_y || !view_cos)
+        return mfail(MCS_ERR_INVALID, "null argument");
+    if (n_cams < 1 || n_points < 0 || n_levels < 1) return mfail(MCS_ERR_INVALID, "bad sizes");
+    if (n_points == 0) return MCS_OK;
+    size_t mask_bytes = 0;
+    for (int c = 0; c < n_cams; ++c) {
+        if (cams[c].width != cams[0].width || cams[c].height != cams[0].height)
+            return mfail(MCS_ERR_UNSUPPORTED, "cameras of different image sizes");
+        mask_bytes += (size_t)cams[c].width * cams[c].height;
+    }
+    const size_t n = (size_t)n_points * n_cams;
+    Dev dmi, dm, dc, dk, dp, dn, dmn, dmx, dsf, div, dlv, dpx, dpy, dvc;
+    MCK(dmi.alloc(n_cams * 128)); MCK(dm.alloc(n_cams * 128)); MCK(dc.alloc(n_cams * sizeof(mcs_ocam))); MCK(dk.alloc(mask_bytes));
+    MCK(dp.alloc((size_t)n_points * 24)); MCK(dn.alloc((size_t)n_points * 24)); MCK(dmn.alloc((size_t)n_points * 8));
+    MCK(dmx.alloc((size_t)n_points * 8)); MCK(dsf.alloc(n_levels * 8));
+    MCK(div.alloc(n)); MCK(dlv.alloc(n * 4)); MCK(dpx.alloc(n * 8)); MCK(dpy.alloc(n * 8)); MCK(dvc.alloc(n * 8));
+    MCK(cudaMemcpy(dmi.p, mtmc_inv, n_cams * 128, cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dm.p, mtmc, n_cams * 128, cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dc.p, cams, n_cams * sizeof(mcs_ocam), cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dk.p, masks, mask_bytes, cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dp.p, world_pos, (size_t)n_points * 24, cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dn.p, normal, (size_t)n_points * 24, cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dmn.p, min_dist, (size_t)n_points * 8, cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dmx.p, max_dist, (size_t)n_points * 8, cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dsf.p, scale_factors, n_levels * 8, cudaMemcpyHostToDevice));
+    MCK(launch_frustum(n_cams, dmi.as<double>(), dm.as<double>(), dc.as<mcs_ocam>(), dk.as<uint8_t>(), n_points, dp.as<double>(),
+                       dn.as<double>(), dmn.as<double>(), dmx.as<double>(), dsf.as<double>(), n_levels, div.as<uint8_t>(),
+                       dlv.as<int>(), dpx.as<double>(), dpy.as<double>(), dvc.as<double>(), nullptr));
+    MCK(cudaMemcpy(in_view, div.p, n, cudaMemcpyDeviceToHost));
+    MCK(cudaMemcpy(level, dlv.p, n * 4, cudaMemcpyDeviceToHost));
+    MCK(cudaMemcpy(proj_x, dpx.p, n * 8, cudaMemcpyDeviceToHost));
+    MCK(cudaMemcpy(proj_y, dpy.p, n * 8, cudaMemcpyDeviceToHost));
+    MCK(cudaMemcpy(view_cos, dvc.p, n * 8, cudaMemcpyDeviceToHost));
+    return MCS_OK;
+}
+
 int mcs_search_windows(const mcs_frame_view* f, const mcs_window_query* queries, int32_t nq, const uint8_t* qdesc,
                        const uint8_t* qmask, const int32_t* query_tag, int32_t rule, double nnratio, int32_t threshold,
                        int32_t* assigned, int32_t* nmatches) {

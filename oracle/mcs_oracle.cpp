@@ -982,6 +982,42 @@ int mcso_search_by_projection(const mcs_frame_view* f, const mcs_mappoint_view* 
     return 0;
 }
 
+// cMultiFrame::isInFrustum for every (map point, camera)  src/cMultiFrame.cpp:218-270, with
+// cMultiCamSys_::WorldToCamHom_fast src/cam_system_omni.cpp:92-112 and isPointInMirrorMask src/cam_model_omni.cpp:163-178
+int mcso_project_mappoints(int n_cams, const double* mtmc_inv, const double* mtmc, const mcs_ocam* cams, const uint8_t* masks,
+                           int n_points, const double* pos, const double* nrm, const double* dmin, const double* dmax,
+                           const double* sf, int n_levels, uint8_t* in_view, int* level, double* px, double* py, double* vcos) {
+    for (int i = 0; i < n_points; ++i)
+        for (int c = 0; c < n_cams; ++c) {
+            const size_t t = (size_t)i * n_cams + c;
+            in_view[t] = 0; level[t] = 0; px[t] = py[t] = vcos[t] = 0.0;
+            const double* M = mtmc_inv + 16 * c;
+            double r[3];
+            for (int k = 0; k < 3; ++k) {        // cv::Matx product: s = 0; s += a(i,k) b(k) for k = 0..3
+                double s = 0;
+                s += M[4 * k] * pos[3 * i]; s += M[4 * k + 1] * pos[3 * i + 1]; s += M[4 * k + 2] * pos[3 * i + 2]; s += M[4 * k + 3] * 1.0;
+                r[k] = s;
+            }
+            double u, v;
+            world_to_img(cams[c], r[0], r[1], r[2], u, v);
+            const int ur = cv_round(u), vr = cv_round(v);
+            const int w = cams[c].width, h = cams[c].height;
+            if (ur >= w || ur <= 0 || vr >= h || vr <= 0) continue;
+            if (masks[(size_t)c * w * h + (size_t)vr * w + ur] == 0) continue;
+            const double* T = mtmc + 16 * c;
+            const double o[3] = {pos[3 * i] - T[3], pos[3 * i + 1] - T[7], pos[3 * i + 2] - T[11]};
+            double s2 = 0; for (int k = 0; k < 3; ++k) s2 += o[k] * o[k];
+            const double dist = std::sqrt(s2);
+            if (dist < dmin[i] || dist > dmax[i]) continue;
+            double dot = 0; for (int k = 0; k < 3; ++k) dot += o[k] * nrm[3 * i + k];
+            const double ratio = dist / dmin[i];
+            int lv = (int)(std::lower_bound(sf, sf + n_levels, ratio) - sf);
+            if (lv >= n_levels) lv = n_levels - 1;
+            in_view[t] = 1; px[t] = u; py[t] = v; level[t] = lv; vcos[t] = dot / dist;
+        }
+    return 0;
+}
+
 // Generic window search with the acceptance rules of WindowSearch (src/cORBmatcher.cpp:326-474, rule 0),
 // SearchByProjection(Current, Last, th) (:1990-2118, rule 1) and SearchByProjection(F, MapPoints, th) (:67-166, rule 2);
 // the per-candidate loop is the one those functions share (:385-418, :2046-2068, :115-148).

@@ -208,3 +208,19 @@ def stream_mt(images, masks, cams, n_threads, nfeatures=2000, nlevels=8, do_dbri
     lib().mcso_stream_mt.restype = C.c_long
     n = lib().mcso_stream_mt(C.byref(p), n_threads, F, Cn, _p(images), W, H, _p(masks), ocs, th_low, C.c_double(nnratio), C.byref(nm))
     return n, nm.value
+
+
+def project_mappoints(mtmc_inv, mtmc, cams, masks, world_pos, normal, min_dist, max_dist, scale_factors):
+    from multicol_slam_b200.ctypes_defs import Ocam
+    mi = np.ascontiguousarray(mtmc_inv, np.float64); mm = np.ascontiguousarray(mtmc, np.float64)
+    masks = np.ascontiguousarray(masks, np.uint8)
+    pos = np.ascontiguousarray(world_pos, np.float64); nrm = np.ascontiguousarray(normal, np.float64)
+    dmin = np.ascontiguousarray(min_dist, np.float64); dmax = np.ascontiguousarray(max_dist, np.float64)
+    sf = np.ascontiguousarray(scale_factors, np.float64)
+    nc, n = len(cams), len(pos)
+    ocs = (Ocam * nc)(*[c if isinstance(c, Ocam) else make_ocam(c) for c in cams])
+    in_view = np.zeros((n, nc), np.uint8); level = np.zeros((n, nc), np.int32)
+    px, py, vc = np.zeros((n, nc)), np.zeros((n, nc)), np.zeros((n, nc))
+    lib().mcso_project_mappoints(nc, _p(mi), _p(mm), ocs, _p(masks), n, _p(pos), _p(nrm), _p(dmin), _p(dmax), _p(sf), len(sf),
+                                 _p(in_view), _p(level), _p(px), _p(py), _p(vc))
+    return in_view, level, px, py, vc

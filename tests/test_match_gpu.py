@@ -345,3 +345,47 @@ def test_m4_window_searches(api, oa, cams, masks):
     n4, f4 = m.SearchByProjection(F2, mps, 3.0)
     on4, of4 = oa.search_by_projection(F2, mps, 3.0, 0.8, m.TH_HIGH_, masks)
     assert n4 == on4 and np.array_equal(f4, of4)
+
+
+def _random_rig(rng, n_cams):
+    """MtMc[c] = [R t; 0 1] with random rotations looking roughly outwards, and the rigid inverse (cConverter::invMat)."""
+    mtmc, inv = np.zeros((n_cams, 4, 4)), np.zeros((n_cams, 4, 4))
+    for c in range(n_cams):
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        if np.linalg.det(q) < 0:
+            q[:, 0] = -q[:, 0]
+        t = rng.normal(0, 0.2, 3)
+        mtmc[c, :3, :3], mtmc[c, :3, 3], mtmc[c, 3, 3] = q, t, 1.0
+        inv[c, :3, :3], inv[c, :3, 3], inv[c, 3, 3] = q.T, -(q.T @ t), 1.0
+    return mtmc, inv
+
+
+def test_project_mappoints_and_search(api, oa, cams):
+    """Projection front-end (isInFrustum batched) vs the oracle, then the full chain
+    projection -> SearchByProjection on the GPU against the oracle's chain."""
+    from multicol_slam_b200 import synth
+    rng = np.random.default_rng(12)
+    nc, n = 3, 20000
+    mtmc, inv = _random_rig(rng, nc)
+    masks = np.stack([synth.mirror_mask(c) for c in cams])
+    pos = rng.normal(size=(n, 3)); pos *= (rng.uniform(1.5, 12.0, n) / np.linalg.norm(pos, axis=1))[:, None]
+    nrm = rng.normal(size=(n, 3)); nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+    dmin = rng.uniform(0.5, 4.0, n); dmax = dmin * rng.uniform(1.5, 6.0, n)
+    sf = np.cumprod([1.0] + [1.2000000476837158] * 7)
+    g = api.project_mappoints(inv, mtmc, cams, masks, pos, nrm, dmin, dmax, sf)
+    o = oa.project_mappoints(inv, mtmc, cams, masks, pos, nrm, dmin, dmax, sf)
+    assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1])            # in_view, level: exact
+    assert np.array_equal(g[4], o[4])                                              # view cosine: sqrt/div only -> exact
+    assert np.abs(g[2] - o[2]).max() < 1e-9 and np.abs(g[3] - o[3]).max() < 1e-9   # projections: atan() differs in the last ulp
+    assert 0.1 < g[0].mean() < 0.9
+    # chain: a frame + map points whose descriptors are noisy copies of frame descriptors near their projections
+    ex = api.mdBRIEFextractorOct(nfeatures=1000, do_dBrief=True, learnMasks=True)
+    per = [ex(synth.frame(cams[c], 200 + c), masks[c], cams[c]) for c in range(3)]
+    F = api.Frame.from_cameras(per, [(754, 480)] * 3, [ex.info.scale_factor[l] for l in range(8)])
+    desc = F.desc[rng.integers(0, len(F.keys), n)].copy()
+    mps_g = api.MapPoints(np.zeros(n, np.uint8), g[0], g[1], g[2], g[3], g[4], desc, F.dmask[rng.integers(0, len(F.keys), n)])
+    mps_o = api.MapPoints(np.zeros(n, np.uint8), o[0], o[1], o[2], o[3], o[4], mps_g.desc, mps_g.dmask)
+    m = api.cORBmatcher(0.8, False, 32, True)
+    ng, fg = m.SearchByProjection(F, mps_g, 3.0)
+    no, fo = oa.search_by_projection(F, mps_o, 3.0, 0.8, m.TH_HIGH_, True)
+    assert ng == no and np.array_equal(fg, fo)
