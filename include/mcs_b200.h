@@ -203,6 +203,19 @@ int  mcs_match_bruteforce(const uint8_t* q, const uint8_t* qmask, const uint8_t*
                           int32_t dim, int32_t th_low, double nnratio,
                           int32_t* matches12, int32_t* nmatches);
 
+/* cORBmatcher::SearchForTriangulationRaw(KF1, KF2, ...) (ref src/cORBmatcher.cpp:968-1156): all-pairs scan, same camera only,
+ * over the keypoints that carry NO map point (free1/free2 != 0); per query the candidates with distance <= th_low are
+ * ordered by (distance, index), and the first one within cvRound(2*best) whose bearing rays satisfy the epipolar constraint
+ * CheckDistEpipolarLine(ray1, ray2, E[cam][cam], epi_thresh) (ref src/misc.cpp:53-69) is matched; every KF2 keypoint is used
+ * at most once, queries are visited in index order.  rays: [n*3] doubles; E: [n_cams*n_cams*9] row-major 3x3 (ComputeE).
+ * matches12[n1] = KF2 index or -1. */
+int  mcs_search_for_triangulation(const uint8_t* desc1, const uint8_t* mask1, const int32_t* cam1, const uint8_t* free1,
+                                  const double* rays1, int32_t n1,
+                                  const uint8_t* desc2, const uint8_t* mask2, const int32_t* cam2, const uint8_t* free2,
+                                  const double* rays2, int32_t n2,
+                                  int32_t dim, int32_t th_low, const double* E, int32_t n_cams, double epi_thresh,
+                                  int32_t* matches12, int32_t* nmatches);
+
 /* ---- multi-camera frame view + grid window search (G1, M1, M3) ---------------------------- */
 /* Flat view of the fields of cMultiFrame the matchers read (ref include/cMultiFrame.h:90-175).
  * Keypoints are in the contiguous (camera-major) order of src/cMultiFrame.cpp:168-184. */

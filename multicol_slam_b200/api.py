@@ -457,6 +457,23 @@ class cORBmatcher:
         return search_windows(CurrentFrame, q, LastFrame.desc, LastFrame.dmask if self.havingMasks else None, sel, RULE_BEST,
                               self.mfNNratio, self.TH_HIGH_, assigned_cur)
 
+    def SearchForTriangulationRaw(self, desc1, mask1, cam1, free1, rays1, desc2, mask2, cam2, free2, rays2, E, epi_thresh=1e-2):
+        """SearchForTriangulationRaw(KF1, KF2, ...) (ref :968-1156): free1/free2 flag keypoints WITHOUT a map point, rays = bearing
+        vectors [n,3], E [n_cams,n_cams,3,3] from ComputeE.  Returns (nmatches, vMatches12)."""
+        d1, d2 = np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(desc2, np.uint8)
+        use = self.havingMasks and mask1 is not None and mask2 is not None
+        m1 = np.ascontiguousarray(mask1, np.uint8) if use else None
+        m2 = np.ascontiguousarray(mask2, np.uint8) if use else None
+        c1, c2 = np.ascontiguousarray(cam1, np.int32), np.ascontiguousarray(cam2, np.int32)
+        f1, f2 = np.ascontiguousarray(free1, np.uint8), np.ascontiguousarray(free2, np.uint8)
+        r1, r2 = np.ascontiguousarray(rays1, np.float64), np.ascontiguousarray(rays2, np.float64)
+        Em = np.ascontiguousarray(E, np.float64)
+        m12 = np.zeros(len(d1), np.int32)
+        n = C.c_int32(0)
+        _check(lib().mcs_search_for_triangulation(_p(d1), _p(m1), _p(c1), _p(f1), _p(r1), len(d1), _p(d2), _p(m2), _p(c2), _p(f2), _p(r2),
+                                                  len(d2), d1.shape[1], self.TH_LOW_, _p(Em), Em.shape[0], C.c_double(epi_thresh), _p(m12), C.byref(n)))
+        return n.value, m12
+
     def SearchByBoW(self, desc1, desc2, mask1=None, mask2=None, valid1=None, valid2=None):
         """SearchByBoW(cMultiKeyFrame*, cMultiKeyFrame*, vpMatches12) (ref :885-966): all-pairs scan over the
         map-point-bearing keypoints of two keyframes.  Returns (nmatches, matches12 indices into desc2)."""

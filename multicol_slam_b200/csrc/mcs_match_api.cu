@@ -255,6 +255,103 @@ int mcs_match_bruteforce(const uint8_t* q, const uint8_t* qmask, const uint8_t* 
     return MCS_OK;
 }
 
+// CheckDistEpipolarLine (ref src/misc.cpp:53-69): cv::Matx products accumulate s = 0; s += a*b in index order
+static bool epipolar_ok(const double* r1, const double* r2, const double* E, double thresh) {
+    double t[3];                                       // ray2^T * E  (1x3)
+    for (int j = 0; j < 3; ++j) { double s = 0; for (int i = 0; i < 3; ++i) s += r2[i] * E[3 * i + j]; t[j] = s; }
+    double nom = 0; for (int j = 0; j < 3; ++j) nom += t[j] * r1[j];
+    double ex1[3], etx2[3];
+    for (int i = 0; i < 3; ++i) { double s = 0; for (int k = 0; k < 3; ++k) s += E[3 * i + k] * r1[k]; ex1[i] = s; }
+    for (int i = 0; i < 3; ++i) { double s = 0; for (int k = 0; k < 3; ++k) s += E[3 * k + i] * r2[k]; etx2[i] = s; }
+    const double den = ex1[0] * ex1[0] + ex1[1] * ex1[1] + ex1[2] * ex1[2] + etx2[0] * etx2[0] + etx2[1] * etx2[1] + etx2[2] * etx2[2];
+    if (den == 0.0) return false;
+    return (nom * nom) / den < thresh;
+}
+
+int mcs_search_for_triangulation(const uint8_t* desc1, const uint8_t* mask1, const int32_t* cam1, const uint8_t* free1,
+                                 const double* rays1, int32_t n1, const uint8_t* desc2, const uint8_t* mask2, const int32_t* cam2,
+                                 const uint8_t* free2, const double* rays2, int32_t n2, int32_t dim, int32_t th_low, const double* E,
+                                 int32_t n_cams, double epi_thresh, int32_t* matches12, int32_t* nmatches) {
+    if (!desc1 || !cam1 || !free1 || !rays1 || !desc2 || !cam2 || !free2 || !rays2 || !E || !matches12 || !nmatches)
+        return mfail(MCS_ERR_INVALID, "null argument");
+    if (dim != 16 && dim != 32 && dim != 64) return mfail(MCS_ERR_INVALID, "dim must be 16, 32 or 64");
+    *nmatches = 0;
+    for (int i = 0; i < n1; ++i) matches12[i] = -1;
+    if (n1 <= 0 || n2 <= 0) return MCS_OK;
+    const bool masked = mask1 && mask2;
+    constexpr int K = 8;
+    Dev dd, ddm, ds;
+    MCK(dd.alloc((size_t)n2 * dim)); MCK(ds.alloc(n2));
+    MCK(cudaMemcpy(dd.p, desc2, (size_t)n2 * dim, cudaMemcpyHostToDevice));
+    if (masked) { MCK(ddm.alloc((size_t)n2 * dim)); MCK(cudaMemcpy(ddm.p, mask2, (size_t)n2 * dim, cudaMemcpyHostToDevice)); }
+    std::vector<uint8_t> matched2(n2, 0), skip(n2);
+    int nm = 0;
+    for (int c = 0; c < n_cams; ++c) {                 // queries of camera c only ever see database entries of camera c (ref :1043-1045)
+        std::vector<int> q_idx;
+        for (int i = 0; i < n1; ++i) if (cam1[i] == c && free1[i]) q_idx.push_back(i);
+        if (q_idx.empty()) continue;
+        const int nq = (int)q_idx.size();
+        std::vector<uint8_t> qd((size_t)nq * dim), qmk(masked ? (size_t)nq * dim : 0);
+        for (int k = 0; k < nq; ++k) {
+            std::memcpy(&qd[(size_t)k * dim], desc1 + (size_t)q_idx[k] * dim, dim);
+            if (masked) std::memcpy(&qmk[(size_t)k * dim], mask1 + (size_t)q_idx[k] * dim, dim);
+        }
+        Dev dq, dqm, di, dt;
+        MCK(dq.alloc((size_t)nq * dim)); MCK(di.alloc((size_t)nq * K * 4)); MCK(dt.alloc((size_t)nq * K * 4));
+        MCK(cudaMemcpy(dq.p, qd.data(), (size_t)nq * dim, cudaMemcpyHostToDevice));
+        if (masked) { MCK(dqm.alloc((size_t)nq * dim)); MCK(cudaMemcpy(dqm.p, qmk.data(), (size_t)nq * dim, cudaMemcpyHostToDevice)); }
+        std::vector<int> tidx((size_t)nq * K), tdist((size_t)nq * K);
+        const double* Ecc = E + ((size_t)c * n_cams + c) * 9;
+        // one GPU pass: the K best database entries (distance, index) of every query under the skip state at the start
+        for (int i = 0; i < n2; ++i) skip[i] = (matched2[i] || !free2[i] || cam2[i] != c) ? 1 : 0;
+        MCK(cudaMemcpy(ds.p, skip.data(), n2, cudaMemcpyHostToDevice));
+        int rc = mcs_hamming_topk_device(dq.as<uint8_t>(), masked ? dqm.as<uint8_t>() : nullptr, nq, dd.as<uint8_t>(),
+                                         masked ? ddm.as<uint8_t>() : nullptr, n2, ds.as<uint8_t>(), dim, K, di.as<int>(), dt.as<int>(), nullptr);
+        if (rc) return rc;
+        MCK(cudaMemcpy(tidx.data(), di.p, (size_t)nq * K * 4, cudaMemcpyDeviceToHost));
+        MCK(cudaMemcpy(tdist.data(), dt.p, (size_t)nq * K * 4, cudaMemcpyDeviceToHost));
+        std::vector<int> pi(K), pd(K), marked;
+        for (int k = 0; k < nq; ++k) {                   // sequential replay (ref :1015-1107)
+            const double* r1 = rays1 + 3 * (size_t)q_idx[k];
+            const int* li = &tidx[(size_t)k * K];
+            const int* ld = &tdist[(size_t)k * K];
+            int best = -1, dist_th = 0, found = -1;
+            bool done = false;
+            auto walk = [&](const int* idx, const int* dst) {      // returns true when the list was consumed without a decision
+                for (int e = 0; e < K; ++e) {
+                    if (idx[e] < 0 || dst[e] > th_low) { done = true; return false; }     // no candidate with dist <= TH_LOW_ left
+                    if (matched2[idx[e]]) continue;                                       // taken by an earlier query of this pass
+                    if (best < 0) { best = dst[e]; dist_th = (int)lrint(2.0 * best); }
+                    if (dst[e] > dist_th) { done = true; return false; }
+                    if (epipolar_ok(r1, rays2 + 3 * (size_t)idx[e], Ecc, epi_thresh)) { found = idx[e]; done = true; return false; }
+                    skip[idx[e]] = 2; marked.push_back(idx[e]);                           // examined by this query (paging only)
+                }
+                return true;
+            };
+            if (walk(li, ld)) {
+                // more than K candidates inside both thresholds: page through the rest for this one query on the GPU
+                std::vector<uint8_t> sk(n2);
+                while (!done) {
+                    for (int i = 0; i < n2; ++i) sk[i] = (matched2[i] || !free2[i] || cam2[i] != c || skip[i] == 2) ? 1 : 0;
+                    MCK(cudaMemcpy(ds.p, sk.data(), n2, cudaMemcpyHostToDevice));
+                    rc = mcs_hamming_topk_device(dq.as<uint8_t>() + (size_t)k * dim, masked ? dqm.as<uint8_t>() + (size_t)k * dim : nullptr, 1,
+                                                 dd.as<uint8_t>(), masked ? ddm.as<uint8_t>() : nullptr, n2, ds.as<uint8_t>(), dim, K,
+                                                 di.as<int>(), dt.as<int>(), nullptr);
+                    if (rc) return rc;
+                    MCK(cudaMemcpy(pi.data(), di.p, K * 4, cudaMemcpyDeviceToHost));
+                    MCK(cudaMemcpy(pd.data(), dt.p, K * 4, cudaMemcpyDeviceToHost));
+                    if (!walk(pi.data(), pd.data())) break;
+                }
+            }
+            for (int e : marked) skip[e] = 0;                                             // clear this query's paging marks
+            marked.clear();
+            if (found >= 0) { matches12[q_idx[k]] = found; matched2[found] = 1; ++nm; }
+        }
+    }
+    *nmatches = nm;
+    return MCS_OK;
+}
+
 int mcs_window_search(const mcs_frame_view* frame, const mcs_window_query* queries, int32_t nq, const uint8_t* qdesc,
                       const uint8_t* qmask, int32_t max_cand, int32_t* cand_idx, int32_t* cand_dist, int32_t* cand_count) {
     if (!frame || !queries || !qdesc || !cand_idx || !cand_dist || !cand_count || max_cand < 1)

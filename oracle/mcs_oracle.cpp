@@ -917,6 +917,54 @@ int mcso_match_bruteforce(const uint8_t* q, const uint8_t* qmask, const uint8_t*
     return 0;
 }
 
+// CheckDistEpipolarLine  src/misc.cpp:53-69
+static bool check_epipolar(const double* r1, const double* r2, const double* E, double thresh) {
+    double t[3];
+    for (int j = 0; j < 3; ++j) { double s = 0; for (int i = 0; i < 3; ++i) s += r2[i] * E[3 * i + j]; t[j] = s; }
+    double nom = 0; for (int j = 0; j < 3; ++j) nom += t[j] * r1[j];
+    double ex1[3], etx2[3];
+    for (int i = 0; i < 3; ++i) { double s = 0; for (int k = 0; k < 3; ++k) s += E[3 * i + k] * r1[k]; ex1[i] = s; }
+    for (int i = 0; i < 3; ++i) { double s = 0; for (int k = 0; k < 3; ++k) s += E[3 * k + i] * r2[k]; etx2[i] = s; }
+    const double den = ex1[0] * ex1[0] + ex1[1] * ex1[1] + ex1[2] * ex1[2] + etx2[0] * etx2[0] + etx2[1] * etx2[1] + etx2[2] * etx2[2];
+    if (den == 0.0) return false;
+    return (nom * nom) / den < thresh;
+}
+
+// cORBmatcher::SearchForTriangulationRaw  src/cORBmatcher.cpp:968-1156 (mbCheckOrientation == false)
+int mcso_search_for_triangulation(const uint8_t* desc1, const uint8_t* mask1, const int* cam1, const uint8_t* free1, const double* rays1,
+                                  int n1, const uint8_t* desc2, const uint8_t* mask2, const int* cam2, const uint8_t* free2,
+                                  const double* rays2, int n2, int dim, int th_low, const double* E, int n_cams, double epi_thresh,
+                                  int* matches12, int* nmatches) {
+    const bool masks = mask1 && mask2;
+    std::vector<uint8_t> matched2(n2, 0);
+    int nm = 0;
+    for (int i1 = 0; i1 < n1; ++i1) {
+        matches12[i1] = -1;
+        if (!free1[i1]) continue;
+        std::vector<std::pair<int, size_t>> cand;
+        for (int i2 = 0; i2 < n2; ++i2) {
+            if (matched2[i2] || !free2[i2]) continue;
+            if (cam1[i1] != cam2[i2]) continue;
+            const int dist = masks ? dist64m(row64(desc1, i1, dim), row64(desc2, i2, dim), row64(mask1, i1, dim), row64(mask2, i2, dim), dim)
+                                   : dist64(row64(desc1, i1, dim), row64(desc2, i2, dim), dim);
+            if (dist > th_low) continue;
+            cand.push_back({dist, (size_t)i2});
+        }
+        if (cand.empty()) continue;
+        std::sort(cand.begin(), cand.end());
+        const int dist_th = cv_round(2 * cand.front().first);
+        for (auto& c : cand) {
+            if (c.first > dist_th) break;
+            if (check_epipolar(rays1 + 3 * (size_t)i1, rays2 + 3 * c.second, E + ((size_t)cam1[i1] * n_cams + cam2[c.second]) * 9, epi_thresh)) {
+                matched2[c.second] = 1; matches12[i1] = (int)c.second; ++nm;
+                break;
+            }
+        }
+    }
+    *nmatches = nm;
+    return 0;
+}
+
 // candidate lists: GetFeaturesInArea + distances, reference visiting order
 int mcso_window_search(const mcs_frame_view* f, const mcs_window_query* qs, int nq, const uint8_t* qdesc,
                        const uint8_t* qmask, int max_cand, int* cand_idx, int* cand_dist, int* cand_count) {

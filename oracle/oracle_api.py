@@ -224,3 +224,18 @@ def project_mappoints(mtmc_inv, mtmc, cams, masks, world_pos, normal, min_dist, 
     lib().mcso_project_mappoints(nc, _p(mi), _p(mm), ocs, _p(masks), n, _p(pos), _p(nrm), _p(dmin), _p(dmax), _p(sf), len(sf),
                                  _p(in_view), _p(level), _p(px), _p(py), _p(vc))
     return in_view, level, px, py, vc
+
+
+def search_for_triangulation(d1, m1, c1, f1, r1, d2, m2, c2, f2, r2, E, th_low, epi_thresh=1e-2):
+    d1, d2 = np.ascontiguousarray(d1, np.uint8), np.ascontiguousarray(d2, np.uint8)
+    m1 = None if m1 is None else np.ascontiguousarray(m1, np.uint8)
+    m2 = None if m2 is None else np.ascontiguousarray(m2, np.uint8)
+    c1, c2 = np.ascontiguousarray(c1, np.int32), np.ascontiguousarray(c2, np.int32)
+    f1, f2 = np.ascontiguousarray(f1, np.uint8), np.ascontiguousarray(f2, np.uint8)
+    r1, r2 = np.ascontiguousarray(r1, np.float64), np.ascontiguousarray(r2, np.float64)
+    Em = np.ascontiguousarray(E, np.float64)
+    m12 = np.zeros(len(d1), np.int32)
+    n = C.c_int(0)
+    lib().mcso_search_for_triangulation(_p(d1), _p(m1), _p(c1), _p(f1), _p(r1), len(d1), _p(d2), _p(m2), _p(c2), _p(f2), _p(r2), len(d2),
+                                        d1.shape[1], th_low, _p(Em), Em.shape[0], C.c_double(epi_thresh), _p(m12), C.byref(n))
+    return n.value, m12

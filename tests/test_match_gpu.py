@@ -389,3 +389,40 @@ def test_project_mappoints_and_search(api, oa, cams):
     ng, fg = m.SearchByProjection(F, mps_g, 3.0)
     no, fo = oa.search_by_projection(F, mps_o, 3.0, 0.8, m.TH_HIGH_, True)
     assert ng == no and np.array_equal(fg, fo)
+
+
+@pytest.mark.parametrize("masks", [False, True])
+def test_search_for_triangulation(api, oa, cams, masks):
+    """SearchForTriangulationRaw (ref :968-1156): all-pairs same-camera scan with the epipolar test, incl. the case of more than
+    K candidates inside the thresholds (paging) via many near-duplicate descriptors."""
+    from multicol_slam_b200 import synth
+    rng = np.random.default_rng(21)
+    ex = api.mdBRIEFextractorOct(nfeatures=600, do_dBrief=True, learnMasks=masks)
+    fr = []
+    for t in range(2):
+        per = [ex(synth.texture_stream(cams[c], 2, seed=80 + c)[t], synth.mirror_mask(cams[c]), cams[c]) for c in range(3)]
+        fr.append(api.Frame.from_cameras(per, [(754, 480)] * 3, [ex.info.scale_factor[l] for l in range(8)]))
+    F1, F2 = fr
+
+    def rays(F):
+        out = np.zeros((len(F.keys), 3))
+        for i, k in enumerate(F.keys):
+            out[i] = api.img_to_world(cams[F.key_cam[i]], float(k["x"]), float(k["y"]))
+        return out
+    r1, r2 = rays(F1), rays(F2)
+    # a small sideways translation between the two keyframes: E = [t]x R with R = I
+    t = np.array([1.0, 0.1, 0.0]); t /= np.linalg.norm(t)
+    Ex = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+    E = np.tile(Ex, (3, 3, 1, 1))
+    free1 = (rng.random(len(F1.keys)) < 0.7).astype(np.uint8)
+    free2 = (rng.random(len(F2.keys)) < 0.7).astype(np.uint8)
+    d2 = F2.desc.copy()
+    d2[100:140] = F1.desc[50]                      # 40 database entries identical to one query: > K candidates at distance ~0
+    d2[100:140, 5] ^= rng.integers(0, 4, 40).astype(np.uint8)
+    m = api.cORBmatcher(0.8, False, 32, masks)
+    for thr in (1e-2, 1e-4):
+        n, m12 = m.SearchForTriangulationRaw(F1.desc, F1.dmask, F1.key_cam, free1, r1, d2, F2.dmask, F2.key_cam, free2, r2, E, thr)
+        on, om12 = oa.search_for_triangulation(F1.desc, F1.dmask if masks else None, F1.key_cam, free1, r1, d2, F2.dmask if masks else None,
+                                               F2.key_cam, free2, r2, E, m.TH_LOW_, thr)
+        assert n == on and np.array_equal(m12, om12)
+    assert n > 20
