@@ -233,6 +233,14 @@ typedef struct mcs_frame_view {
     const double* scale_factors;    /* [n_levels] mvScaleFactors */
 } mcs_frame_view;
 
+/* Per-frame epilogue of the cMultiFrame constructor on the GPU (SURVEY 8f "next" row 3; ref src/cMultiFrame.cpp:143-184):
+ * bearing rays camModel.ImgToWorld(pt) of every keypoint ([n_keys*3] doubles, bit-identical to the host evaluation: only
+ * + - * / sqrt) and the 64x48 grid of PosInGrid (:342-353) as CSR over (cam, ix, iy): cell_start [n_cams*64*48 + 1],
+ * cell_items [n_keys] (first *n_in_grid valid), ascending keypoint index inside a cell.  keys/key_cam as in mcs_frame_view
+ * (cam_width/height are taken from cams[]).  Host buffers.  The window searches build their grid with the same kernel. */
+int  mcs_frame_prepare(const mcs_keypoint* keys, const int32_t* key_cam, int32_t n_keys, const mcs_ocam* cams, int32_t n_cams,
+                       double* rays_out, int32_t* cell_start_out, int32_t* cell_items_out, int32_t* n_in_grid);
+
 /* One window query: GetFeaturesInArea(cam, x, y, r, min_level, max_level)
  * (ref src/cMultiFrame.cpp:272-340) followed by Hamming distance to every candidate. */
 typedef struct mcs_window_query {

@@ -338,6 +338,21 @@ def window_search(frame, queries, qdesc, qmask=None, max_cand=64):
     return idx, dist, cnt, rc
 
 
+def frame_prepare(keys, key_cam, cams):
+    """GPU epilogue of the cMultiFrame constructor (ref src/cMultiFrame.cpp:143-184): bearing rays [n,3] and the 64x48 grid as
+    CSR (cell_start [n_cams*64*48+1], cell_items [n_in_grid])."""
+    keys = np.ascontiguousarray(keys, KEYPOINT_DTYPE)
+    key_cam = np.ascontiguousarray(key_cam, np.int32)
+    nc, n = len(cams), len(keys)
+    ocs = (Ocam * nc)(*[as_ocam(c) for c in cams])
+    rays = np.zeros((n, 3))
+    start = np.zeros(nc * 64 * 48 + 1, np.int32)
+    items = np.zeros(max(n, 1), np.int32)
+    ning = C.c_int32(0)
+    _check(lib().mcs_frame_prepare(_p(keys), _p(key_cam), n, ocs, nc, _p(rays), _p(start), _p(items), C.byref(ning)))
+    return rays, start, items[:ning.value].copy()
+
+
 def project_mappoints(mtmc_inv, mtmc, cams, masks, world_pos, normal, min_dist, max_dist, scale_factors):
     """Batched cMultiFrame::isInFrustum (ref src/cMultiFrame.cpp:218-270): mtmc_inv / mtmc [n_cams,4,4], masks [n_cams,H,W],
     world_pos / normal [n,3].  Returns (in_view [n,n_cams] u8, level i32, proj_x, proj_y, view_cos f64) -- the MapPoints fields."""

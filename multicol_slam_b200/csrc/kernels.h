@@ -50,6 +50,9 @@ cudaError_t launch_window_search(const WindowFrameDev& f, const mcs_window_query
                                  const uint8_t* qmask, int max_cand, int* cand_idx, int* cand_dist, int* cand_count,
                                  cudaStream_t st);
 
+cudaError_t launch_frame_prepare(const mcs_keypoint* keys, const int* key_cam, int n_keys, const mcs_ocam* cams, int n_cams, float* kx,
+                                 float* ky, int* koct, double* rays, int* cell_of, int* cursor, int* cell_start, int* cell_items,
+                                 double* winv, double* hinv, cudaStream_t st);
 cudaError_t launch_frustum(int n_cams, const double* mtmc_inv, const double* mtmc, const mcs_ocam* cams, const uint8_t* masks,
                            int n_points, const double* pos, const double* nrm, const double* dmin, const double* dmax, const double* sf,
                            int n_levels, uint8_t* in_view, int* level, double* px, double* py, double* vcos, cudaStream_t st);

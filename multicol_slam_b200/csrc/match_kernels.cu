@@ -404,6 +404,88 @@ cudaError_t launch_window_search(const WindowFrameDev& f, const mcs_window_query
 }
 
 // ------------------------------------------------------------------------------------------------
+// frame epilogue of the cMultiFrame constructor (ref src/cMultiFrame.cpp:143-184, :342-353): bearing rays + 64x48 grid (CSR)
+// ------------------------------------------------------------------------------------------------
+// One CTA of 1024 threads per frame.  cell_of / cursor are global scratch ([n_keys], [n_cell]).
+__global__ void __launch_bounds__(1024)
+frame_prepare_kernel(const mcs_keypoint* __restrict__ keys, const int* __restrict__ key_cam, const int n_keys,
+                     const mcs_ocam* __restrict__ cams, const int n_cams, float* __restrict__ kx, float* __restrict__ ky,
+                     int* __restrict__ koct, double* __restrict__ rays, int* __restrict__ cell_of, int* __restrict__ cursor,
+                     int* __restrict__ cell_start, int* __restrict__ cell_items, double* __restrict__ winv, double* __restrict__ hinv) {
+    __shared__ int s_part[1024];
+    const int tid = threadIdx.x;
+    const int n_cell = n_cams * MCS_FRAME_GRID_COLS * MCS_FRAME_GRID_ROWS;
+    for (int c = tid; c < n_cams; c += 1024) {
+        winv[c] = (double)MCS_FRAME_GRID_COLS / (double)cams[c].width;       // mfGridElementWidthInv (ref :154-157)
+        hinv[c] = (double)MCS_FRAME_GRID_ROWS / (double)cams[c].height;
+    }
+    for (int c = tid; c <= n_cell; c += 1024) cell_start[c] = 0;
+    __syncthreads();
+    // rays, SoA copies, cell of every keypoint, histogram
+    for (int i = tid; i < n_keys; i += 1024) {
+        const mcs_keypoint k = keys[i];
+        const int c = key_cam[i];
+        kx[i] = k.x; ky[i] = k.y; koct[i] = k.octave;
+        if (rays) {
+            double x, y, z;
+            cam_img_to_world(cams[c], (double)k.x, (double)k.y, x, y, z);
+            rays[3 * i] = x; rays[3 * i + 1] = y; rays[3 * i + 2] = z;
+        }
+        // PosInGrid: cvRound((pt - mnMin) * inv): float - int -> float, times double (ref :345-346)
+        const int px = __double2int_rn((double)(k.x - 0.f) * ((double)MCS_FRAME_GRID_COLS / (double)cams[c].width));
+        const int py = __double2int_rn((double)(k.y - 0.f) * ((double)MCS_FRAME_GRID_ROWS / (double)cams[c].height));
+        int cell = -1;
+        if (px >= 0 && px < MCS_FRAME_GRID_COLS && py >= 0 && py < MCS_FRAME_GRID_ROWS) {
+            cell = (c * MCS_FRAME_GRID_COLS + px) * MCS_FRAME_GRID_ROWS + py;
+            atomicAdd(&cell_start[cell + 1], 1);
+        }
+        cell_of[i] = cell;
+    }
+    __syncthreads();
+    // inclusive scan of cell_start[1..n_cell] (contiguous chunk per thread + block scan of the chunk sums)
+    const int chunk = (n_cell + 1023) / 1024;
+    const int lo = 1 + tid * chunk, hi = min(lo + chunk, n_cell + 1);
+    int sum = 0;
+    for (int c = lo; c < hi; ++c) sum += cell_start[c];
+    s_part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = tid >= o ? s_part[tid - o] : 0;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    int run = tid ? s_part[tid - 1] : 0;
+    for (int c = lo; c < hi; ++c) { run += cell_start[c]; cell_start[c] = run; }
+    __syncthreads();
+    for (int c = tid; c < n_cell; c += 1024) cursor[c] = cell_start[c];
+    __syncthreads();
+    for (int i = tid; i < n_keys; i += 1024) {
+        const int cell = cell_of[i];
+        if (cell >= 0) cell_items[atomicAdd(&cursor[cell], 1)] = i;
+    }
+    __syncthreads();
+    // insertion order inside a cell = ascending keypoint index (the constructor pushes in index order, ref :176-181)
+    for (int c = tid; c < n_cell; c += 1024) {
+        const int a = cell_start[c], b = cell_start[c + 1];
+        for (int i = a + 1; i < b; ++i) {
+            const int v = cell_items[i];
+            int j = i - 1;
+            while (j >= a && cell_items[j] > v) { cell_items[j + 1] = cell_items[j]; --j; }
+            cell_items[j + 1] = v;
+        }
+    }
+}
+
+cudaError_t launch_frame_prepare(const mcs_keypoint* keys, const int* key_cam, int n_keys, const mcs_ocam* cams, int n_cams, float* kx,
+                                 float* ky, int* koct, double* rays, int* cell_of, int* cursor, int* cell_start, int* cell_items,
+                                 double* winv, double* hinv, cudaStream_t st) {
+    frame_prepare_kernel<<<1, 1024, 0, st>>>(keys, key_cam, n_keys, cams, n_cams, kx, ky, koct, rays, cell_of, cursor, cell_start,
+                                             cell_items, winv, hinv);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // projection front-end: isInFrustum for every (map point, camera)   (ref src/cMultiFrame.cpp:218-270)
 // ------------------------------------------------------------------------------------------------
 __global__ void frustum_kernel(const int n_cams, const double* __restrict__ mtmc_inv, const double* __restrict__ mtmc,

@@ -46,47 +46,33 @@ struct FrameDev {
 };
 
 int upload_frame(const mcs_frame_view* f, FrameDev& d, cudaStream_t st) {
+    // keypoints go up as they are; SoA copies, grid cell of every keypoint and the CSR grid are built on the device
     const int n = f->n_keys, nc = f->n_cams;
-    std::vector<float> kx(n), ky(n);
-    std::vector<int> koct(n);
-    std::vector<double> winv(nc), hinv(nc);
-    for (int c = 0; c < nc; ++c) {
-        winv[c] = (double)MCS_FRAME_GRID_COLS / (double)f->cam_width[c];
-        hinv[c] = (double)MCS_FRAME_GRID_ROWS / (double)f->cam_height[c];
-    }
+    for (int i = 0; i < n; ++i)
+        if (f->key_cam[i] < 0 || f->key_cam[i] >= nc) return mfail(MCS_ERR_INVALID, "key_cam out of range");
+    std::vector<mcs_ocam> cams(nc);
+    std::memset(cams.data(), 0, sizeof(mcs_ocam) * nc);
+    for (int c = 0; c < nc; ++c) { cams[c].width = f->cam_width[c]; cams[c].height = f->cam_height[c]; }
     const int ncell = nc * MCS_FRAME_GRID_COLS * MCS_FRAME_GRID_ROWS;
-    std::vector<int> cell_of(n), start(ncell + 1, 0);
-    for (int i = 0; i < n; ++i) {
-        kx[i] = f->keys[i].x; ky[i] = f->keys[i].y; koct[i] = f->keys[i].octave;
-        const int c = f->key_cam[i];
-        if (c < 0 || c >= nc) return mfail(MCS_ERR_INVALID, "key_cam out of range");
-        // PosInGrid: cvRound((pt - mnMin) * inv), float - int -> float, times double (ref :345-346)
-        const int px = cv_round((f->keys[i].x - 0) * winv[c]);
-        const int py = cv_round((f->keys[i].y - 0) * hinv[c]);
-        if (px < 0 || px >= MCS_FRAME_GRID_COLS || py < 0 || py >= MCS_FRAME_GRID_ROWS) { cell_of[i] = -1; continue; }
-        cell_of[i] = (c * MCS_FRAME_GRID_COLS + px) * MCS_FRAME_GRID_ROWS + py;
-        ++start[cell_of[i] + 1];
-    }
-    for (int c = 0; c < ncell; ++c) start[c + 1] += start[c];
-    std::vector<int> items(std::max(start[ncell], 1)), fill(start.begin(), start.end() - 1);
-    for (int i = 0; i < n; ++i) if (cell_of[i] >= 0) items[fill[cell_of[i]]++] = i;    // ascending index inside a cell
     const size_t db = (size_t)n * f->dim;
+    Dev dkeys, dkc, dcams, dcell, dcur;
+    MCK(dkeys.alloc((size_t)n * sizeof(mcs_keypoint))); MCK(dkc.alloc((size_t)n * 4)); MCK(dcams.alloc(nc * sizeof(mcs_ocam)));
+    MCK(dcell.alloc((size_t)n * 4)); MCK(dcur.alloc((size_t)ncell * 4));
     MCK(d.kx.alloc(n * 4)); MCK(d.ky.alloc(n * 4)); MCK(d.koct.alloc(n * 4)); MCK(d.desc.alloc(db));
-    MCK(d.cell_start.alloc((ncell + 1) * 4)); MCK(d.cell_items.alloc(items.size() * 4));
+    MCK(d.cell_start.alloc((ncell + 1) * 4)); MCK(d.cell_items.alloc((size_t)std::max(n, 1) * 4));
     MCK(d.winv.alloc(nc * 8)); MCK(d.hinv.alloc(nc * 8));
-    MCK(cudaMemcpyAsync(d.kx.p, kx.data(), n * 4, cudaMemcpyHostToDevice, st));
-    MCK(cudaMemcpyAsync(d.ky.p, ky.data(), n * 4, cudaMemcpyHostToDevice, st));
-    MCK(cudaMemcpyAsync(d.koct.p, koct.data(), n * 4, cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(dkeys.p, f->keys, (size_t)n * sizeof(mcs_keypoint), cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(dkc.p, f->key_cam, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(dcams.p, cams.data(), nc * sizeof(mcs_ocam), cudaMemcpyHostToDevice, st));
     MCK(cudaMemcpyAsync(d.desc.p, f->desc, db, cudaMemcpyHostToDevice, st));
     if (f->dmask) {
         MCK(d.dmask.alloc(db));
         MCK(cudaMemcpyAsync(d.dmask.p, f->dmask, db, cudaMemcpyHostToDevice, st));
     }
-    MCK(cudaMemcpyAsync(d.cell_start.p, start.data(), (ncell + 1) * 4, cudaMemcpyHostToDevice, st));
-    MCK(cudaMemcpyAsync(d.cell_items.p, items.data(), items.size() * 4, cudaMemcpyHostToDevice, st));
-    MCK(cudaMemcpyAsync(d.winv.p, winv.data(), nc * 8, cudaMemcpyHostToDevice, st));
-    MCK(cudaMemcpyAsync(d.hinv.p, hinv.data(), nc * 8, cudaMemcpyHostToDevice, st));
-    MCK(cudaStreamSynchronize(st));    // host staging vectors die with this scope
+    MCK(launch_frame_prepare(dkeys.as<mcs_keypoint>(), dkc.as<int>(), n, dcams.as<mcs_ocam>(), nc, d.kx.as<float>(), d.ky.as<float>(),
+                             d.koct.as<int>(), nullptr, dcell.as<int>(), dcur.as<int>(), d.cell_start.as<int>(), d.cell_items.as<int>(),
+                             d.winv.as<double>(), d.hinv.as<double>(), st));
+    MCK(cudaStreamSynchronize(st));    // host staging vectors and the scratch buffers die with this scope
     d.view = WindowFrameDev{nc, n, f->dim, d.kx.as<float>(), d.ky.as<float>(), d.koct.as<int>(), d.desc.as<uint8_t>(),
                             f->dmask ? d.dmask.as<uint8_t>() : nullptr, d.cell_start.as<int>(), d.cell_items.as<int>(),
                             d.winv.as<double>(), d.hinv.as<double>()};
@@ -374,6 +360,32 @@ int mcs_window_search(const mcs_frame_view* frame, const mcs_window_query* queri
     std::memcpy(cand_idx, ci.data(), sizeof(int) * (size_t)nq * max_cand);
     std::memcpy(cand_dist, cd.data(), sizeof(int) * (size_t)nq * max_cand);
     if (rc == MCS_ERR_CAPACITY) return mfail(MCS_ERR_CAPACITY, "max_cand too small for at least one query");
+    return MCS_OK;
+}
+
+int mcs_frame_prepare(const mcs_keypoint* keys, const int32_t* key_cam, int32_t n_keys, const mcs_ocam* cams, int32_t n_cams,
+                      double* rays_out, int32_t* cell_start_out, int32_t* cell_items_out, int32_t* n_in_grid) {
+    if (!keys || !key_cam || !cams || !rays_out || !cell_start_out || !cell_items_out || !n_in_grid)
+        return mfail(MCS_ERR_INVALID, "null argument");
+    if (n_keys < 0 || n_cams < 1) return mfail(MCS_ERR_INVALID, "bad sizes");
+    for (int i = 0; i < n_keys; ++i)
+        if (key_cam[i] < 0 || key_cam[i] >= n_cams) return mfail(MCS_ERR_INVALID, "key_cam out of range");
+    const int ncell = n_cams * MCS_FRAME_GRID_COLS * MCS_FRAME_GRID_ROWS;
+    Dev dkeys, dkc, dcams, dcell, dcur, dkx, dky, dko, drays, dstart, ditems, dw, dh;
+    const size_t n = (size_t)std::max(n_keys, 1);
+    MCK(dkeys.alloc(n * sizeof(mcs_keypoint))); MCK(dkc.alloc(n * 4)); MCK(dcams.alloc(n_cams * sizeof(mcs_ocam)));
+    MCK(dcell.alloc(n * 4)); MCK(dcur.alloc((size_t)ncell * 4)); MCK(dkx.alloc(n * 4)); MCK(dky.alloc(n * 4)); MCK(dko.alloc(n * 4));
+    MCK(drays.alloc(n * 24)); MCK(dstart.alloc((size_t)(ncell + 1) * 4)); MCK(ditems.alloc(n * 4)); MCK(dw.alloc(n_cams * 8)); MCK(dh.alloc(n_cams * 8));
+    MCK(cudaMemcpy(dkeys.p, keys, (size_t)n_keys * sizeof(mcs_keypoint), cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dkc.p, key_cam, (size_t)n_keys * 4, cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dcams.p, cams, n_cams * sizeof(mcs_ocam), cudaMemcpyHostToDevice));
+    MCK(launch_frame_prepare(dkeys.as<mcs_keypoint>(), dkc.as<int>(), n_keys, dcams.as<mcs_ocam>(), n_cams, dkx.as<float>(), dky.as<float>(),
+                             dko.as<int>(), drays.as<double>(), dcell.as<int>(), dcur.as<int>(), dstart.as<int>(), ditems.as<int>(),
+                             dw.as<double>(), dh.as<double>(), nullptr));
+    MCK(cudaMemcpy(rays_out, drays.p, (size_t)n_keys * 24, cudaMemcpyDeviceToHost));
+    MCK(cudaMemcpy(cell_start_out, dstart.p, (size_t)(ncell + 1) * 4, cudaMemcpyDeviceToHost));
+    MCK(cudaMemcpy(cell_items_out, ditems.p, (size_t)n_keys * 4, cudaMemcpyDeviceToHost));
+    *n_in_grid = cell_start_out[ncell];
     return MCS_OK;
 }
 

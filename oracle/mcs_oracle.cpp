@@ -1030,6 +1030,26 @@ int mcso_search_by_projection(const mcs_frame_view* f, const mcs_mappoint_view* 
     return 0;
 }
 
+// bearing rays + grid of the cMultiFrame constructor  src/cMultiFrame.cpp:143-184, :342-353
+int mcso_frame_prepare(const mcs_keypoint* keys, const int* key_cam, int n_keys, const mcs_ocam* cams, int n_cams, double* rays,
+                       int* cell_start, int* cell_items, int* n_in_grid) {
+    std::vector<int> cw(n_cams), ch(n_cams);
+    for (int c = 0; c < n_cams; ++c) { cw[c] = cams[c].width; ch[c] = cams[c].height; }
+    mcs_frame_view f{};
+    f.n_cams = n_cams; f.n_keys = n_keys; f.keys = keys; f.key_cam = key_cam; f.cam_width = cw.data(); f.cam_height = ch.data();
+    Grid g; build_grid(f, g);
+    int pos = 0;
+    for (size_t c = 0; c < g.cells.size(); ++c) {
+        cell_start[c] = pos;
+        for (int i : g.cells[c]) cell_items[pos++] = i;
+    }
+    cell_start[g.cells.size()] = pos;
+    *n_in_grid = pos;
+    for (int i = 0; i < n_keys; ++i)
+        img_to_world(cams[key_cam[i]], (double)keys[i].x, (double)keys[i].y, rays[3 * i], rays[3 * i + 1], rays[3 * i + 2]);
+    return 0;
+}
+
 // cMultiFrame::isInFrustum for every (map point, camera)  src/cMultiFrame.cpp:218-270, with
 // cMultiCamSys_::WorldToCamHom_fast src/cam_system_omni.cpp:92-112 and isPointInMirrorMask src/cam_model_omni.cpp:163-178
 int mcso_project_mappoints(int n_cams, const double* mtmc_inv, const double* mtmc, const mcs_ocam* cams, const uint8_t* masks,

@@ -239,3 +239,15 @@ def search_for_triangulation(d1, m1, c1, f1, r1, d2, m2, c2, f2, r2, E, th_low, 
     lib().mcso_search_for_triangulation(_p(d1), _p(m1), _p(c1), _p(f1), _p(r1), len(d1), _p(d2), _p(m2), _p(c2), _p(f2), _p(r2), len(d2),
                                         d1.shape[1], th_low, _p(Em), Em.shape[0], C.c_double(epi_thresh), _p(m12), C.byref(n))
     return n.value, m12
+
+
+def frame_prepare(keys, key_cam, cams):
+    from multicol_slam_b200.ctypes_defs import Ocam
+    keys = np.ascontiguousarray(keys, KEYPOINT_DTYPE)
+    key_cam = np.ascontiguousarray(key_cam, np.int32)
+    nc, n = len(cams), len(keys)
+    ocs = (Ocam * nc)(*[c if isinstance(c, Ocam) else make_ocam(c) for c in cams])
+    rays = np.zeros((n, 3)); start = np.zeros(nc * 64 * 48 + 1, np.int32); items = np.zeros(max(n, 1), np.int32)
+    ning = C.c_int(0)
+    lib().mcso_frame_prepare(_p(keys), _p(key_cam), n, ocs, nc, _p(rays), _p(start), _p(items), C.byref(ning))
+    return rays, start, items[:ning.value].copy()

@@ -426,3 +426,18 @@ def test_search_for_triangulation(api, oa, cams, masks):
                                                F2.key_cam, free2, r2, E, m.TH_LOW_, thr)
         assert n == on and np.array_equal(m12, om12)
     assert n > 20
+
+
+def test_frame_prepare_rays_and_grid(api, oa, cams):
+    """Bearing rays + 64x48 grid of the cMultiFrame constructor on the GPU: rays bit-identical to the host
+    evaluation (no libm call involved), CSR grid identical to the reference's per-cell insertion order."""
+    F = make_frames(api, oa, cams, [7, 8, 9], nf=2000)
+    keys = F.keys.copy()
+    keys["x"][::97] = -3.0          # out-of-grid keypoints are dropped by PosInGrid
+    keys["y"][5::89] = 481.0
+    g = api.frame_prepare(keys, F.key_cam, cams)
+    o = oa.frame_prepare(keys, F.key_cam, cams)
+    assert np.array_equal(g[0].view(np.uint64), o[0].view(np.uint64))
+    assert np.array_equal(g[1], o[1]) and np.array_equal(g[2], o[2])
+    assert len(g[2]) < len(keys) and len(g[2]) > 0.9 * len(keys)
+    assert np.allclose(np.linalg.norm(g[0], axis=1), 1.0)
