@@ -304,11 +304,16 @@ int  mcs_project_mappoints(int32_t n_cams, const double* mtmc_inv, const double*
  *   MCS_RULE_BEST         best <= threshold                             SearchByProjection(Current, Last, th) (:2070)
  *   MCS_RULE_LEVEL_RATIO  best <= threshold && !(bestLevel == secondLevel && best > nnratio*second)
  *                                                                       SearchByProjection(F, MapPoints, th) (:151-158)
+ *   MCS_RULE_BEST_FREE    best <= threshold, candidates are NOT skipped when taken and nothing is marked: the per-query
+ *                         answer is written to assigned[q] (best index or -1; `assigned` is then an output of nq entries).
+ *                         This is the matching core of Fuse (:1326-1366, :1620-1660), SearchBySim3 (:1793-1830, :1869-1906)
+ *                         and SearchByProjection(KF, Scw, ...) (:2345-2390): their level filter {l-1, l} goes into the query.
  * On acceptance assigned[bestIdx] = query_tag[q] (tags must be >= 0).  The caller builds the queries (projection
  * front-end, "bad"/duplicate filters of the reference loops) and owns `assigned` (in/out, [n_keys], -1 = free). */
 #define MCS_RULE_RATIO        0
 #define MCS_RULE_BEST         1
 #define MCS_RULE_LEVEL_RATIO  2
+#define MCS_RULE_BEST_FREE    3
 int  mcs_search_windows(const mcs_frame_view* frame, const mcs_window_query* queries, int32_t nq,
                         const uint8_t* qdesc, const uint8_t* qmask, const int32_t* query_tag,
                         int32_t rule, double nnratio, int32_t threshold, int32_t* assigned, int32_t* nmatches);

@@ -374,7 +374,7 @@ def project_mappoints(mtmc_inv, mtmc, cams, masks, world_pos, normal, min_dist, 
     return in_view, level, px, py, vc
 
 
-RULE_RATIO, RULE_BEST, RULE_LEVEL_RATIO = 0, 1, 2
+RULE_RATIO, RULE_BEST, RULE_LEVEL_RATIO, RULE_BEST_FREE = 0, 1, 2, 3
 
 
 def search_windows(frame, queries, qdesc, qmask, query_tag, rule, nnratio, threshold, assigned):
@@ -471,6 +471,20 @@ class cORBmatcher:
         q = _queries(LastFrame.key_cam[sel], np.asarray(uv)[sel, 0], np.asarray(uv)[sel, 1], r, lv - 1, lv + 1, sel)
         return search_windows(CurrentFrame, q, LastFrame.desc, LastFrame.dmask if self.havingMasks else None, sel, RULE_BEST,
                               self.mfNNratio, self.TH_HIGH_, assigned_cur)
+
+    def FuseCandidates(self, KF, uv, in_mask, level, th, mp_desc, mp_dmask=None):
+        """Matching core of Fuse(pKF, curKF, vpMapPoints, th) (ref :1265-1418): for map point i and camera c (in_mask[i,c]) the best
+        keypoint of KF within th*scale[level] of uv[i,c] on levels {level-1, level}, accepted when its distance <= TH_LOW_.
+        Returns best [n, n_cams] (keypoint index or -1); replacing / adding observations stays with the caller (host map bookkeeping)."""
+        in_mask = np.asarray(in_mask) != 0
+        i, c = np.nonzero(in_mask)
+        lv = np.asarray(level)[i, c]
+        q = _queries(c, np.asarray(uv)[i, c, 0], np.asarray(uv)[i, c, 1], th * KF.scale_factors[lv], lv - 1, lv, i)
+        n, res = search_windows(KF, q, mp_desc, mp_dmask if self.havingMasks else None, np.zeros(len(q), np.int32), RULE_BEST_FREE,
+                                self.mfNNratio, self.TH_LOW_, np.full(max(len(q), len(KF.keys)), -1, np.int32))
+        best = np.full(in_mask.shape, -1, np.int32)
+        best[i, c] = res[:len(q)]
+        return best
 
     def SearchForTriangulationRaw(self, desc1, mask1, cam1, free1, rays1, desc2, mask2, cam2, free2, rays2, E, epi_thresh=1e-2):
         """SearchForTriangulationRaw(KF1, KF2, ...) (ref :968-1156): free1/free2 flag keypoints WITHOUT a map point, rays = bearing

@@ -434,7 +434,7 @@ int mcs_search_windows(const mcs_frame_view* f, const mcs_window_query* queries,
                        const uint8_t* qmask, const int32_t* query_tag, int32_t rule, double nnratio, int32_t threshold,
                        int32_t* assigned, int32_t* nmatches) {
     if (!f || !queries || !qdesc || !query_tag || !assigned || !nmatches) return mfail(MCS_ERR_INVALID, "null argument");
-    if (rule < 0 || rule > 2) return mfail(MCS_ERR_INVALID, "unknown rule");
+    if (rule < 0 || rule > 3) return mfail(MCS_ERR_INVALID, "unknown rule");
     *nmatches = 0;
     if (nq <= 0) return MCS_OK;
     int rows = 0;
@@ -454,11 +454,11 @@ int mcs_search_windows(const mcs_frame_view* f, const mcs_window_query* queries,
     int nm = 0;
     for (int qi = 0; qi < nq; ++qi) {       // sequential greedy replay over the GPU-computed candidate lists
         const int n = cc[qi];
-        if (n == 0) continue;
+        if (n == 0) { if (rule == MCS_RULE_BEST_FREE) assigned[qi] = -1; continue; }
         int bestDist = INT_MAX, bestLevel = -1, bestDist2 = INT_MAX, bestLevel2 = -1, bestIdx = -1;
         for (int k = 0; k < n; ++k) {
             const int idx = ci[(size_t)qi * mc + k];
-            if (assigned[idx] >= 0) continue;
+            if (rule != MCS_RULE_BEST_FREE && assigned[idx] >= 0) continue;
             const int dist = cd[(size_t)qi * mc + k];
             if (dist < bestDist) {
                 bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel;
@@ -466,6 +466,12 @@ int mcs_search_windows(const mcs_frame_view* f, const mcs_window_query* queries,
             } else if (dist < bestDist2) {
                 bestLevel2 = f->keys[idx].octave; bestDist2 = dist;
             }
+        }
+        if (rule == MCS_RULE_BEST_FREE) {          // stateless: the answer of query qi
+            const bool hit = bestIdx >= 0 && bestDist <= threshold;
+            assigned[qi] = hit ? bestIdx : -1;
+            nm += hit;
+            continue;
         }
         bool ok;
         if (rule == MCS_RULE_RATIO) ok = (double)bestDist <= (double)bestDist2 * nnratio && bestDist <= threshold;

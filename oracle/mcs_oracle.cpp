@@ -1098,10 +1098,10 @@ int mcso_search_windows(const mcs_frame_view* f, const mcs_window_query* qs, int
     for (int i = 0; i < nq; ++i) {
         const mcs_window_query& q = qs[i];
         features_in_area(*f, g, q.cam, q.x, q.y, q.r, q.min_level, q.max_level, near);
-        if (near.empty()) continue;
+        if (near.empty()) { if (rule == 3) assigned[i] = -1; continue; }
         int bestDist = INT_MAX, bestLevel = -1, bestDist2 = INT_MAX, bestLevel2 = -1, bestIdx = -1;
         for (int idx : near) {
-            if (assigned[idx] >= 0) continue;
+            if (rule != 3 && assigned[idx] >= 0) continue;
             const int dist = masks ? dist64m(row64(qdesc, q.desc_index, f->dim), row64(f->desc, idx, f->dim),
                                              row64(qmask, q.desc_index, f->dim), row64(f->dmask, idx, f->dim), f->dim)
                                    : dist64(row64(qdesc, q.desc_index, f->dim), row64(f->desc, idx, f->dim), f->dim);
@@ -1110,6 +1110,12 @@ int mcso_search_windows(const mcs_frame_view* f, const mcs_window_query* qs, int
             } else if (dist < bestDist2) {
                 bestLevel2 = f->keys[idx].octave; bestDist2 = dist;
             }
+        }
+        if (rule == 3) {   // Fuse / SearchBySim3 core (src/cORBmatcher.cpp:1326-1366): best only, nothing skipped or marked
+            const bool hit = bestIdx >= 0 && bestDist <= threshold;
+            assigned[i] = hit ? bestIdx : -1;
+            nm += hit;
+            continue;
         }
         bool ok;
         if (rule == 0) ok = bestDist <= bestDist2 * nnratio && bestDist <= threshold;

@@ -441,3 +441,25 @@ def test_frame_prepare_rays_and_grid(api, oa, cams):
     assert np.array_equal(g[1], o[1]) and np.array_equal(g[2], o[2])
     assert len(g[2]) < len(keys) and len(g[2]) > 0.9 * len(keys)
     assert np.allclose(np.linalg.norm(g[0], axis=1), 1.0)
+
+
+def test_fuse_candidates_stateless_rule(api, oa, cams):
+    """MCS_RULE_BEST_FREE: the matching core of Fuse / SearchBySim3 (best candidate in {l-1,l}, nothing skipped or marked)."""
+    from multicol_slam_b200.api import RULE_BEST_FREE, _queries
+    KF = make_frames(api, oa, cams, [31, 32, 33], nf=900)
+    rng = np.random.default_rng(5)
+    n = 3000
+    src = rng.integers(0, len(KF.keys), n)
+    uv = np.zeros((n, 3, 2)); in_mask = np.zeros((n, 3), np.uint8); level = np.zeros((n, 3), np.int64)
+    c = KF.key_cam[src]; r = np.arange(n)
+    uv[r, c, 0] = KF.keys["x"][src] + rng.normal(0, 1.5, n); uv[r, c, 1] = KF.keys["y"][src] + rng.normal(0, 1.5, n)
+    in_mask[r, c] = 1; level[r, c] = np.clip(KF.keys["octave"][src] + rng.integers(0, 2, n), 0, 7)
+    m = api.cORBmatcher(0.8, False, 32, True)
+    best = m.FuseCandidates(KF, uv, in_mask, level, 2.5, KF.desc[src], KF.dmask[src])
+    i, cc = np.nonzero(in_mask)
+    lv = level[i, cc]
+    q = _queries(cc, uv[i, cc, 0], uv[i, cc, 1], 2.5 * KF.scale_factors[lv], lv - 1, lv, i)
+    on, ores = oa.search_windows(KF, q, KF.desc[src], KF.dmask[src], np.zeros(len(q), np.int32), RULE_BEST_FREE, 0.8, m.TH_LOW_,
+                                 np.full(max(len(q), len(KF.keys)), -1, np.int32))
+    assert np.array_equal(best[i, cc], ores[:len(q)])
+    assert (best[i, cc] == src).mean() > 0.5 and (best[i, cc] >= 0).sum() == on
