@@ -270,6 +270,15 @@ def main():
     d2h = int(sum(v.numel() * v.element_size() for v in h_out.values()))
     assert int(np_out["counts"].sum()) == feats_rank, "e2e and device-resident runs disagree"
 
+    # ---- single-frame latency of the reference-shaped call: one 3-camera frame through mcs_extract_batch (host in/out) ----
+    lat_ms = None
+    if rank == 0:
+        one = np.ascontiguousarray(himg[0])
+        ex.extract_batch(one, masks, cams, [0, 1, 2])
+        t0 = time.perf_counter()
+        for _ in range(20):
+            ex.extract_batch(one, masks, cams, [0, 1, 2])
+        lat_ms = (time.perf_counter() - t0) / 20 * 1e3
     if rank == 0:
         # ---- roofline of K1 (fused pyramid + blur + FAST), algorithmic bytes per SURVEY 8d / DESIGN.md ----
         P = sum(int(ex.debug_read(l, 0).size) for l in range(NLEVELS))        # sum of pyramid pixels = 1 120 256
@@ -308,7 +317,8 @@ def main():
                        "parallelism": f"stream-sharded x{world}" + (", 1 all_gather of the packed feature buffer" if world > 1 else "")},
             "e2e": {"value": e2e_val, "unit": "Mfeatures/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "mcs_extract_match_stream (C ABI, pinned host buffers)", "steps": e2e_steps},
-            "gpu_launches": args.steps * (NLEVELS + 2 + 1), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}))
+            "gpu_launches": args.steps * (NLEVELS + 2 + 1), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "single_frame_latency_ms": {"value": lat_ms, "what": "one 3-camera frame, mcs_extract_batch with pageable host buffers, mean of 20"}}))
     if world > 1:
         dist.destroy_process_group()
 

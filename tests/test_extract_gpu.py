@@ -203,3 +203,28 @@ def test_div25_magic():
     # K1's blur uses ((S+12)*5243)>>17 for (S+12)/25
     s = np.arange(0, 25 * 255 + 1, dtype=np.int64)
     assert np.array_equal(((s + 12) * 5243) >> 17, (s + 12) // 25)
+
+
+@pytest.mark.parametrize("sf,nl", [(1.5, 5), (2.0, 4), (1.1, 8), (1.33, 6)])
+def test_other_scale_factors(api, oa, cams, sf, nl):
+    """Other pyramid geometries: wide source regions (the 16-lane staging path for scale factors > 1.5), many / few levels."""
+    from multicol_slam_b200 import synth
+    cam = cams[2]
+    compare_all(api, oa, cam, synth.frame(cam, 123), synth.mirror_mask(cam), 800, "mdbrief", scaleFactor=sf, nlevels=nl)
+
+
+def test_odd_sizes_batch(api, oa, cams):
+    """Widths that are not multiples of the tile / vector sizes, in one batch of several images."""
+    from multicol_slam_b200 import synth
+    for (w, h) in [(641, 479), (700, 350)]:
+        cam = synth.scaled_cam(cams[1], w, h)
+        mask = synth.mirror_mask(cam)
+        imgs = np.stack([synth.frame(cam, 500 + i) for i in range(4)])
+        ex = api.mdBRIEFextractorOct(nfeatures=600, do_dBrief=True, learnMasks=True, nlevels=6)
+        kps, desc, dmask, counts = ex.extract_batch(imgs, mask[None], [cam], [0, 0, 0, 0])
+        oe = oa.OracleExtractor(nfeatures=600, do_dbrief=True, learn_masks=True, nlevels=6)
+        for i in range(4):
+            ok, od, om = oe.extract(imgs[i], mask, cam)
+            n = counts[i]
+            assert n == len(ok) and kps[i, :n].tobytes() == ok.tobytes()
+            assert np.array_equal(desc[i, :n], od) and np.array_equal(dmask[i, :n], om)
