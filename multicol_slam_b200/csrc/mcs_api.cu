@@ -137,7 +137,8 @@ int build_geometry(mcs_extractor* ex, int W, int H, int in_stride) {
         std::vector<int16_t> xofs(g.w), xa0(g.w), xa1(g.w), yofs(g.h), yb0(g.h), yb1(g.h), mx(g.w), my(g.h);
         if (l) {
             const double scale_x = 1.0 / ((double)g.w / g.sw), scale_y = 1.0 / ((double)g.h / g.sh);
-            if (scale_x > 2.0 || scale_y > 2.0) return fail(MCS_ERR_UNSUPPORTED, "scale factors above 2 are not supported");
+            // the staged source region of a 72x40 tile must fit 176 x 88 bytes: (72*s + 17) <= 176, (40*s + 2) <= 88
+            if (scale_x > 2.08 || scale_y > 2.08) return fail(MCS_ERR_UNSUPPORTED, "scale factors above 2 are not supported");
             for (int dx = 0; dx < g.w; ++dx) {
                 float fx = (float)((dx + 0.5) * scale_x - 0.5);
                 int sx = cv_floor(fx);
