@@ -54,8 +54,9 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr; n = 0;
         cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
-        if (e == cudaSuccess) n = count;
-        return e;
+        if (e != cudaSuccess) return e;
+        n = count;
+        return cudaMemset(p, 0, count * sizeof(T));      // unused tail slots of the fixed-size outputs read back as zeros
     }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };

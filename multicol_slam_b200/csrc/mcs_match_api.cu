@@ -99,6 +99,8 @@ int window_search_host(const FrameDev& fd, const std::vector<mcs_window_query>& 
     for (;;) {
         Dev di, dd, dc;
         MCK(di.alloc((size_t)nq * max_cand * 4)); MCK(dd.alloc((size_t)nq * max_cand * 4)); MCK(dc.alloc((size_t)nq * 4));
+        MCK(cudaMemsetAsync(di.p, 0xFF, (size_t)nq * max_cand * 4, st));      // unused list entries read back as -1
+        MCK(cudaMemsetAsync(dd.p, 0, (size_t)nq * max_cand * 4, st));
         MCK(launch_window_search(fd.view, dq.as<mcs_window_query>(), nq, dqd.as<uint8_t>(), masked ? dqm.as<uint8_t>() : nullptr,
                                  max_cand, di.as<int>(), dd.as<int>(), dc.as<int>(), st));
         cidx.resize((size_t)nq * max_cand); cdist.resize((size_t)nq * max_cand);
