@@ -56,7 +56,11 @@ struct DevBuf {
         cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
         if (e != cudaSuccess) return e;
         n = count;
-        return cudaMemset(p, 0, count * sizeof(T));      // unused tail slots of the fixed-size outputs read back as zeros
+        // unused tail slots of the fixed-size outputs read back as zeros.  The memset runs on the legacy default stream, the
+        // extractor works on non-blocking streams: wait for it, or it could overtake-zero freshly written data (allocation is rare).
+        e = cudaMemset(p, 0, count * sizeof(T));
+        if (e != cudaSuccess) return e;
+        return cudaDeviceSynchronize();
     }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
