@@ -119,7 +119,7 @@ def run_reference(args):
     cams = synth.lafida_cams()
     masks = np.stack([synth.mirror_mask(c) for c in cams])
     cores = usable_cores()
-    frames = max(2, min(max(args.ref_frames, 2 * ((cores + 2) // 3)), 128))
+    frames = max(2, min(max(args.ref_frames, 2 * cores), 128))
     images = make_stream(cams, frames, 1000)
     for _ in range(max(min(args.warmup, 1), 1)):
         cpu_oracle_run(cams, masks, images, cores)            # warms the per-thread malloc arenas
@@ -303,7 +303,7 @@ def main():
         cpu = None
         if not args.no_cpu_baseline:
             cores = usable_cores()
-            cf = int(min(F, max(4, 2 * ((cores + 2) // 3))))        # >= 2 images per core so that every core has work
+            cf = int(min(F, max(4, 2 * cores)))                     # 6 images per thread: balanced, ~1-2 s of wall time
             cpu_oracle_run(cams, masks, images[:cf], cores)          # warm-up (per-thread malloc arenas, page faults)
             nf, dt = cpu_oracle_run(cams, masks, images[:cf], cores)
             cpu = {"value": nf / dt / 1e6, "unit": "Mfeatures/s", "cores": cores, "logical_cpus": os.cpu_count(), "kind": "port",
