@@ -62,24 +62,18 @@ __device__ __forceinline__ int sample_px(const uint8_t* bimg, const uint8_t* uim
     return uimg[(size_t)reflect101(row, g.h) * g.pitch + reflect101(col, g.w)];
 }
 
-// R(r) = rho(atan(-z/r)) from the per-camera table; returns false when r is outside the table
-__device__ __forceinline__ bool lut_R(const DistortLut& L, double r, double& g) {
-    const double t = r * L.inv_h;
-    if (!(t < (double)L.n)) return false;
-    const int idx = (int)t;
-    const double tau = fma(2.0, t - (double)idx, -1.0);            // [-1, 1) inside the interval
-    const double2* c = (const double2*)(L.coef + (size_t)idx * 8);
-    const double2 c01 = __ldg(c), c23 = __ldg(c + 1), c45 = __ldg(c + 2);
-    double p = c45.y;
-    p = fma(p, tau, c45.x); p = fma(p, tau, c23.y); p = fma(p, tau, c23.x); p = fma(p, tau, c01.y); p = fma(p, tau, c01.x);
-    g = p;
-    return true;
+__device__ __forceinline__ double2 lds_pair(unsigned addr) {
+    double2 r;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(addr));
+    return r;
 }
 
 constexpr int kDescWarps = 4;
 constexpr int kPatchR = 25;                       // staged patch: rows/cols ky/kx -25 .. +25 (keypoints are >= 25 px inside the ROI)
 constexpr int kPatchS = 64;                       // bytes per staged patch row (4-byte aligned start + 51 columns)
-constexpr int kLutWin = 52;                       // staged LUT intervals around the keypoint's undistorted radius
+constexpr int kLutDeg = 9;                        // degree of the per-centre polynomial of R(r)  (kernels.h: DistortLut)
+constexpr int kLutStride = 12;                    // doubles per centre: tau offset, tau scale, kLutDeg + 1 coefficients
+constexpr double kLutReach = 22.5;                // half-width of a centre's interval: pattern radius 15*sqrt(2) + 0.5 + margin
 
 // Rare path: one pattern of one keypoint with the reference's exact operation sequence (two projection passes;
 // per-lane partial sums + butterfly: within ~1e-13 of the reference's sequential sum).
@@ -140,7 +134,8 @@ __device__ __noinline__ unsigned orb_pattern_global(const char2* s_pat, double c
     return out;
 }
 
-template <int PPL /* pattern points per lane: 16 for descSize <= 32, 32 for descSize 64 */, int MINB = 4>
+template <int PPL /* pattern points per lane: 16 for descSize <= 32, 32 for descSize 64 */, int MINB = 4,
+          bool CSM = false /* polynomial coefficients in shared memory instead of registers */>
 __global__ void __launch_bounds__(kDescWarps * 32, MINB)
 describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, const mcs_ocam* __restrict__ cams,
                 const DistortLut* __restrict__ luts, const int* __restrict__ cam_of_image,
@@ -150,8 +145,8 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
     __shared__ char2 s_pat[PPL * 32];            // [j][lane] : point 16*byte + k with byte = lane + 32*(j/16), k = j%16
     __shared__ __align__(16) double2 s_patd[PPL * 32];   // same, as doubles (int->double conversions run on the slow XU pipe)
     __shared__ mcs_ocam s_cam[kDescWarps];
+    __shared__ __align__(16) double s_poly[kDescWarps][kLutStride];
     __shared__ __align__(16) uint8_t s_patch[kDescWarps][(2 * kPatchR + 1) * kPatchS];
-    __shared__ __align__(16) double s_lut[kDescWarps][kLutWin * 6];
     const int ds = geom->desc_size;
     for (int i = threadIdx.x; i < PPL * 32; i += blockDim.x) {
         const int j = i >> 5, ln = i & 31;
@@ -162,12 +157,16 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
     __syncthreads();
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int sel_total = geom->sel_total;
-    const int b = warp_global / sel_total;
-    if (b >= n_images) return;
-    const int slot = warp_global - b * sel_total;
     const int L = geom->nlevels;
+    const long long total_warps = (long long)n_images * sel_total;
+    // persistent blocks: the pattern tables above are built once per block, every warp then walks the slots with a
+    // grid-sized stride
+    for (long long warp_global = (long long)blockIdx.x * kDescWarps + wib; warp_global < total_warps;
+         warp_global += (long long)gridDim.x * kDescWarps) {
+    const int b = (int)(warp_global / sel_total);
+    const int slot = (int)(warp_global - (long long)b * sel_total);
+    __syncwarp();                                 // the previous keypoint's patch is no longer read
     int level = 0, off = 0;
     for (int l = 0; l < L; ++l)
         if (slot >= geom->lv[l].sel_off) level = l;
@@ -180,9 +179,9 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
         for (int l = 0; l < L; ++l) tot += sel_count[b * L + l];
         counts_out[b] = min(tot, capacity);
     }
-    if (p >= cnt) return;
+    if (p >= cnt) continue;
     const int oidx = off + p;
-    if (oidx >= capacity) return;
+    if (oidx >= capacity) continue;
     const uint32_t c = sel_xys[(size_t)b * sel_total + slot];
     const int kx = corner_x(c), ky = corner_y(c);
     const uint8_t* uimg = args.lvl[level] + (size_t)b * g.img_bytes;
@@ -300,25 +299,33 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
         const DistortLut lut = luts[ci];
         double ukx, uky;   // undistortPointsOcam(pt.x*scale, pt.y*scale, a0)  (ref :1306-1317)
         cam_undistort(cam, (double)__fmul_rn((float)kx, scale), (double)__fmul_rn((float)ky, scale), cam.pol[0], ukx, uky);
-        // stage the window of the distortion table around the keypoint's undistorted radius
+        // R(r) around this keypoint: one degree-9 polynomial in tau = (r - m)/hw, valid for every pattern point
+        // (|r - rk| <= 21.3), picked by the keypoint's own undistorted radius; the coefficients live in registers
         const double rk = sqrt(ukx * ukx + uky * uky);
-        int i0 = 0;
-        if (rk < (double)lut.n) i0 = max(0, min((int)rk - kLutWin / 2, lut.n - kLutWin));
-        double* wl = s_lut[wib];
-        for (int i = lane; i < kLutWin * 3; i += 32) {
-            const int iv = i / 3, part = i - iv * 3;
-            double2 cc = make_double2(0.0, 0.0);
-            if (i0 + iv < lut.n) cc = __ldg((const double2*)(lut.coef + (size_t)(i0 + iv) * 8) + part);
-            *(double2*)(wl + iv * 6 + 2 * part) = cc;
+        const bool have_lut = rk < (double)(lut.n - 1);           // false for NaN as well -> exact path
+        double P[kLutDeg + 1], t_off, t_scale;
+        {
+            const double2* cp = (const double2*)(lut.coef + (size_t)(have_lut ? __double2int_rn(rk) : 0) * kLutStride);
+            const double2 h = __ldg(cp);
+            t_off = h.x; t_scale = h.y;
+#pragma unroll
+            for (int k = 0; k < (kLutDeg + 1) / 2; ++k) {
+                const double2 cc = __ldg(cp + 1 + k);
+                P[2 * k] = cc.x; P[2 * k + 1] = cc.y;
+            }
+            if (CSM) {
+                if (lane < kLutStride / 2) ((double2*)s_poly[wib])[lane] = __ldg(cp + lane);
+                __syncwarp();
+            }
         }
-        __syncwarp();
+        const unsigned sp = (unsigned)__cvta_generic_to_shared(s_poly[wib]);
         const double inv_n = 1.0 / (double)(16 * ds);
         const bool lane_valid = (PPL == 32) || (lane < ds);      // descSize 16: lanes 16..31 own no byte
         for (int q = 0; q < npat; ++q) {
             double us[PPL], vs[PPL];
             double su = 0.0, sv = 0.0;
             bool need_exact = false;
-            unsigned worst_idx = 0;
+            int worst_tau = 0;                         // high word of max |tau|
             // round-to-nearest-even through the 1.5*2^52 trick: no F2I/I2F (XU pipe), same result as lrint
             constexpr double kMagic = 6755399441055744.0;
 #pragma unroll
@@ -332,16 +339,23 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                 asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(s2));
                 const double e = fma(-(s2 * y0), y0, 1.0);
                 const double rinv = fma(y0 * e, fma(0.375, e, 0.5), y0), r = s2 * rinv;
-                // R(r) from the staged window.  Interval index = rn(r - 0.5): at an exact integer either neighbour is
-                // valid (tau = +-1).  A radius outside the window (or NaN from s2 == 0) is caught below.
-                const double tm = (r - 0.5) + kMagic;
-                const unsigned idx = (unsigned)(__double2loint(tm) - i0);
-                const double tau = fma(2.0, r - (tm - kMagic), -1.0);
-                const double2* cf = (const double2*)(wl + min(idx, (unsigned)(kLutWin - 1)) * 6);
-                const double2 c01 = cf[0], c23 = cf[1], c45 = cf[2];
-                double gg = c45.y;
-                gg = fma(gg, tau, c45.x); gg = fma(gg, tau, c23.y); gg = fma(gg, tau, c23.x); gg = fma(gg, tau, c01.y); gg = fma(gg, tau, c01.x);
-                worst_idx = max(worst_idx, idx);          // window miss (also r >= table size: i0 <= n - kLutWin); NaN is caught by the tie test
+                // R(r) by Horner; |tau| > 1 (a point outside the fitted interval, or NaN from s2 == 0) is caught below
+                const double tau = fma(r, t_scale, t_off);
+                double gg;
+                if (CSM) {                      // warp-uniform 128-bit broadcast loads, not hoisted (register pressure)
+                    double2 cc = lds_pair(sp + 16 * (kLutDeg + 1) / 2);
+                    gg = fma(cc.y, tau, cc.x);
+#pragma unroll
+                    for (int k = (kLutDeg + 1) / 2 - 1; k >= 1; --k) {
+                        cc = lds_pair(sp + 16 * k);
+                        gg = fma(gg, tau, cc.y); gg = fma(gg, tau, cc.x);
+                    }
+                } else {
+                    gg = P[kLutDeg];
+#pragma unroll
+                    for (int k = kLutDeg - 1; k >= 0; --k) gg = fma(gg, tau, P[k]);
+                }
+                worst_tau = max(worst_tau, __double2hiint(tau) & 0x7fffffff);
                 gg *= rinv;
                 const double uu = xr * gg, vv = yr * gg;
                 us[j] = fma(uu, cam.c, fma(vv, cam.d, cam.u0));
@@ -371,8 +385,8 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
             // closer than ~7e-7 px to a rounding tie (high word of 0.5 - 5e-7), or outside the staged patch -> exact path
             // (inside the table window |u| is bounded by the fitted polynomial, so the magic-number rounding cannot alias;
             //  a NaN shows up as a huge high word of the fraction)
-            need_exact |= lane_valid && (worst_frac >= __double2hiint(0.5 - 5e-7) || worst_ofs > 2u * kPatchR ||
-                                         worst_idx >= (unsigned)kLutWin);
+            need_exact |= !have_lut || (lane_valid && (worst_frac >= __double2hiint(0.5 - 5e-7) || worst_ofs > 2u * kPatchR ||
+                                                       worst_tau >= __double2hiint(1.0)));
             if (__any_sync(0xffffffffu, need_exact)) {
                 const double aq = q == 0 ? a_base : (q == 1 ? a_base + a_rot : a_base - a_rot);
                 const unsigned e = exact_pattern<PPL>(&cam, s_pat, cos(aq), sin(aq), ukx, uky, lane, ds, bimg, uimg, &g, kx, ky);
@@ -413,6 +427,7 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
         k.octave = level; k.class_id = -1;
         kps_out[(size_t)b * capacity + oidx] = k;
     }
+    }   // slot loop
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -445,32 +460,53 @@ void build_distort_lut(const mcs_ocam& cam, std::vector<double>& coef, int& n_ou
         }
     int n = (int)std::min(8192.0, std::ceil(rmax + 64.0));
     n_out = n;
-    coef.assign((size_t)n * 8, 0.0);
+    coef.assign((size_t)n * kLutStride, 0.0);
     const long double z = -(long double)cam.pol[0];
-    long double nodes[6];
-    for (int k = 0; k < 6; ++k) nodes[k] = cosl((2 * k + 1) * 3.14159265358979323846264338327950288L / 12.0L);
+    auto R_exact = [&](long double r) {
+        const long double theta = atanl(-z / r);
+        long double rho = 0.0L;
+        for (int t = 11; t >= 0; --t) rho = rho * theta + (long double)cam.inv_pol[t];
+        return rho;
+    };
+    constexpr int NC = kLutDeg + 1;
+    long double nodes[NC];
+    for (int k = 0; k < NC; ++k) nodes[k] = cosl((2 * k + 1) * 3.14159265358979323846264338327950288L / (2.0L * NC));
     for (int i = 0; i < n; ++i) {
-        long double A[6][7];
-        for (int k = 0; k < 6; ++k) {
-            const long double tau = nodes[k], r = (long double)i + (tau + 1.0L) * 0.5L;
-            const long double theta = atanl(-z / r);
-            long double rho = 0.0L;
-            for (int t = 11; t >= 0; --t) rho = rho * theta + (long double)cam.inv_pol[t];
+        // centre i serves keypoints with rn(rk) == i: their pattern points lie in [i - 21.8, i + 21.8] and r >= 0
+        const long double lo = std::max(0.0L, (long double)i - (long double)kLutReach), hi = (long double)i + (long double)kLutReach;
+        const long double m = 0.5L * (lo + hi), hw = 0.5L * (hi - lo);
+        long double A[NC][NC + 1];
+        for (int k = 0; k < NC; ++k) {
             long double pw = 1.0L;
-            for (int t = 0; t < 6; ++t) { A[k][t] = pw; pw *= tau; }
-            A[k][6] = rho;
+            for (int t = 0; t < NC; ++t) { A[k][t] = pw; pw *= nodes[k]; }
+            A[k][NC] = R_exact(m + hw * nodes[k]);
         }
-        for (int col = 0; col < 6; ++col) {          // Gaussian elimination with partial pivoting
+        for (int col = 0; col < NC; ++col) {          // Gauss-Jordan with partial pivoting
             int piv = col;
-            for (int r2 = col + 1; r2 < 6; ++r2) if (fabsl(A[r2][col]) > fabsl(A[piv][col])) piv = r2;
-            for (int t = 0; t < 7; ++t) std::swap(A[col][t], A[piv][t]);
-            for (int r2 = 0; r2 < 6; ++r2) {
+            for (int r2 = col + 1; r2 < NC; ++r2) if (fabsl(A[r2][col]) > fabsl(A[piv][col])) piv = r2;
+            for (int t = 0; t <= NC; ++t) std::swap(A[col][t], A[piv][t]);
+            for (int r2 = 0; r2 < NC; ++r2) {
                 if (r2 == col) continue;
                 const long double f = A[r2][col] / A[col][col];
-                for (int t = col; t < 7; ++t) A[r2][t] -= f * A[col][t];
+                for (int t = col; t <= NC; ++t) A[r2][t] -= f * A[col][t];
             }
         }
-        for (int t = 0; t < 6; ++t) coef[(size_t)i * 8 + t] = (double)(A[t][6] / A[t][t]);
+        double* e = coef.data() + (size_t)i * kLutStride;
+        const double scale = (double)(1.0L / hw);
+        e[0] = (double)(-m / hw); e[1] = scale;
+        for (int t = 0; t < NC; ++t) e[2 + t] = (double)(A[t][NC] / A[t][t]);
+        // check the fit as the kernel evaluates it (double Horner); a centre whose error could move a rounding
+        // decision past the kernel's 5e-7 px tie guard is disabled (NaN coefficients -> exact path)
+        double worst = 0.0;
+        for (int sidx = 0; sidx <= 96; ++sidx) {
+            const double r = (double)(lo + (hi - lo) * ((long double)sidx + 0.37L) / 97.0L);
+            const double tau = std::fma(r, e[1], e[0]);
+            double gv = e[2 + kLutDeg];
+            for (int t = kLutDeg - 1; t >= 0; --t) gv = std::fma(gv, tau, e[2 + t]);
+            worst = std::max(worst, (double)fabsl((long double)gv - R_exact((long double)r)));
+        }
+        if (!(worst < 2e-8))
+            for (int t = 0; t < kLutStride; ++t) e[t] = std::nan("");
     }
 }
 
@@ -479,14 +515,24 @@ cudaError_t launch_describe(const PyramidGeom& G, const PyramidGeom* G_dev, int 
                             const int* sel_count, mcs_keypoint* kps, uint8_t* desc, uint8_t* dmask, int* counts, int capacity,
                             cudaStream_t st) {
     const long long warps = (long long)n_images * G.sel_total;
-    const int blocks = (int)((warps + kDescWarps - 1) / kDescWarps);
-    static const int variant = getenv("MCS_K3_MINB") ? atoi(getenv("MCS_K3_MINB")) : 5;     // occupancy experiment knob
+    static const int variant = getenv("MCS_K3_MINB") ? atoi(getenv("MCS_K3_MINB")) : 4;     // occupancy experiment knob
+    static const int waves = getenv("MCS_K3_WAVES") ? atoi(getenv("MCS_K3_WAVES")) : 8;
+    static int n_sm = 0;
+    if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+    const long long all_blocks = (warps + kDescWarps - 1) / kDescWarps;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>(all_blocks, (long long)n_sm * 4 * waves));
     if (G.desc_size <= 32 && variant == 5)
         describe_kernel<16, 5><<<blocks, kDescWarps * 32, 0, st>>>(G_dev, args, cams, luts, cam_of_image, sel_xys, sel_count, kps, desc,
                                                                   dmask, counts, capacity, n_images);
     else if (G.desc_size <= 32 && variant == 6)
         describe_kernel<16, 6><<<blocks, kDescWarps * 32, 0, st>>>(G_dev, args, cams, luts, cam_of_image, sel_xys, sel_count, kps, desc,
                                                                   dmask, counts, capacity, n_images);
+    else if (G.desc_size <= 32 && variant == 15)
+        describe_kernel<16, 5, true><<<blocks, kDescWarps * 32, 0, st>>>(G_dev, args, cams, luts, cam_of_image, sel_xys, sel_count, kps, desc,
+                                                                        dmask, counts, capacity, n_images);
+    else if (G.desc_size <= 32 && variant == 16)
+        describe_kernel<16, 6, true><<<blocks, kDescWarps * 32, 0, st>>>(G_dev, args, cams, luts, cam_of_image, sel_xys, sel_count, kps, desc,
+                                                                        dmask, counts, capacity, n_images);
     else if (G.desc_size <= 32 && variant == 3)
         describe_kernel<16, 3><<<blocks, kDescWarps * 32, 0, st>>>(G_dev, args, cams, luts, cam_of_image, sel_xys, sel_count, kps, desc,
                                                                   dmask, counts, capacity, n_images);

@@ -18,8 +18,9 @@ void launch_pyr_fast(const PyramidGeom& G, int level, int n_images, const uint8_
 cudaError_t launch_octree(const PyramidGeom& G, const PyramidGeom* G_dev, int n_images, const uint32_t* raw,
                           const int* raw_count, uint16_t* node_of, uint32_t* sel_xys, int* sel_count, int* status,
                           cudaStream_t st);
-// per-camera table of g(r) = rho(atan(-z/r))/r (describe_kernel.cu): interval i covers r in [i, i+1) px,
-// 8 doubles per interval (6 coefficients in tau = 2(r-i)-1, 2 pad)
+// per-camera table of R(r) = rho(atan(-z/r)) (describe_kernel.cu): entry i is one degree-9 polynomial in
+// tau = r * e[1] + e[0] valid on [max(0, i - 22.5), i + 22.5] -- every pattern point of a keypoint whose undistorted
+// radius rounds to i; 12 doubles per entry (tau offset, tau scale, 10 coefficients)
 struct DistortLut {
     const double* coef;
     int n;
