@@ -326,6 +326,56 @@ int  mcs_search_for_initialization(const mcs_frame_view* f1, const mcs_frame_vie
                                    double nnratio, int32_t th_low, int32_t having_masks,
                                    int32_t* matches12, int32_t* nmatches);
 
+/* ---- bag of words: ORBVocabulary::transform and the feature-vector guided search ------- */
+/* The vocabulary tree of DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> (ref include/cORBVocabulary.h:34,
+ * ThirdParty/DBoW2/DBoW2/TemplatedVocabulary.h) as flat arrays.  Node 0 is the root; parent[0] is ignored.
+ * descriptors: n_nodes x 32 bytes (FORB::L = 32; row 0 unused).  weight[i]: node weight (word weight for leaves).
+ * node_order: the n_nodes-1 non-root node ids in the order the reference's load() appends them to their parent's
+ * children (ref :1596-1608 / :1382-1421); NULL = ascending id.  word_node[w] = node id of word w.
+ * scoring: 0 L1_NORM, 1 L2_NORM, 2 CHI_SQUARE, 3 KL, 4 BHATTACHARYYA, 5 DOT_PRODUCT; weighting: 0 TF_IDF, 1 TF, 2 IDF,
+ * 3 BINARY (ref ThirdParty/DBoW2/DBoW2/BowVector.h:36-59). */
+typedef struct mcs_vocabulary mcs_vocabulary;
+int  mcs_vocabulary_create(int32_t k, int32_t L, int32_t scoring, int32_t weighting, int32_t n_nodes,
+                           const int32_t* parent, const double* weight, const uint8_t* descriptors,
+                           const int32_t* node_order, int32_t n_words, const int32_t* word_node,
+                           mcs_vocabulary** out);
+void mcs_vocabulary_destroy(mcs_vocabulary* voc);
+
+/* transform(feature, word_id, weight, &nid, levelsup) for n descriptors of 32 bytes (ref :1218-1261): the tree
+ * descent on the GPU, one 16-lane group per descriptor, FORB::distance (ref FORB.cpp:84-104), first minimum wins.
+ * node_id[i] = ancestor at level L - levelsup (0 when that level is <= 0).  The reference leaves nid indeterminate
+ * when the leaf is shallower than that level; this library returns the leaf's node id there.  Any output may be NULL. */
+int  mcs_bow_transform(const mcs_vocabulary* voc, const uint8_t* desc, int32_t n, int32_t levelsup,
+                       int32_t* word_id, double* weight, int32_t* node_id);
+
+/* transform(features, BowVector&, FeatureVector&, levelsup) (ref :1126-1194; call sites src/cMultiFrame.cpp:356-363,
+ * src/cMultiKeyFrame.cpp:105-114).  desc = the frame's descriptors of all cameras concatenated in camera order
+ * (cConverter::toDescriptorVector, ref src/cConverter.cpp:58-66).
+ * BowVector: bow_words/bow_values[<= n] ascending word id (std::map order), *n_bow entries, weights accumulated in
+ * feature order and normalised as the scoring type asks.
+ * FeatureVector: CSR -- fv_nodes[<= n] ascending node id, fv_offsets[*n_fv + 1], fv_features[<= n] (ascending feature
+ * index inside a node). */
+int  mcs_bow_vectors(const mcs_vocabulary* voc, const uint8_t* desc, int32_t n, int32_t levelsup,
+                     int32_t* bow_words, double* bow_values, int32_t* n_bow,
+                     int32_t* fv_nodes, int32_t* fv_offsets, int32_t* n_fv, int32_t* fv_features);
+
+/* ORBVocabulary::score(v1, v2) with the vocabulary's scoring type (ref ScoringObject.cpp:23-313); host arithmetic. */
+int  mcs_bow_score(const mcs_vocabulary* voc, const int32_t* words1, const double* values1, int32_t n1,
+                   const int32_t* words2, const double* values2, int32_t n2, double* score);
+
+/* cORBmatcher::SearchByBoW(cMultiKeyFrame*, cMultiFrame&, vpMapPointMatches) (ref src/cORBmatcher.cpp:179-324; call site
+ * src/cTracking.cpp:1177): for every vocabulary node both feature vectors hold, each key-frame keypoint that carries a
+ * good map point (valid1) looks for its best / second best among the frame keypoints of that node that are still
+ * unmatched; accepted if best <= th_low and best < nnratio * second.  Distances for all (node, keypoint) groups are
+ * computed on the GPU, the order-dependent bookkeeping is replayed on the host.  desc1/desc2: n x dim rows in the
+ * concatenated keypoint order the feature vectors index; masks NULL = unmasked.  match_of_2[n2] = key-frame keypoint
+ * index or -1.  checkOrientation is compile-time false in the reference (include/cORBmatcher.h:40). */
+int  mcs_search_by_bow(const uint8_t* desc1, const uint8_t* mask1, const uint8_t* valid1, int32_t n1,
+                       const int32_t* fv1_nodes, const int32_t* fv1_offsets, int32_t n_fv1, const int32_t* fv1_features,
+                       const uint8_t* desc2, const uint8_t* mask2, int32_t n2,
+                       const int32_t* fv2_nodes, const int32_t* fv2_offsets, int32_t n_fv2, const int32_t* fv2_features,
+                       int32_t dim, int32_t th_low, double nnratio, int32_t* match_of_2, int32_t* nmatches);
+
 /* ---- packed per-camera slot for the multi-GPU allgather ----------------------- */
 /* Slot layout (bytes): int32 n; int32 pad[3]; mcs_keypoint kp[capacity];
  * uint8 desc[capacity*dim]; uint8 dmask[capacity*dim].  Size below. */

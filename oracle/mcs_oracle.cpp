@@ -27,6 +27,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <list>
+#include <map>
 #include <atomic>
 #include <malloc.h>
 #include <thread>
@@ -1223,6 +1224,195 @@ long mcso_stream_mt(const mcs_extractor_params* p, int n_threads, int n_frames, 
     for (int c : counts) total += c;
     if (n_matches) *n_matches = matches.load();
     return total;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bag of words: DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> as the reference uses it
+// (include/cORBVocabulary.h:34; ThirdParty/DBoW2/DBoW2/TemplatedVocabulary.h, FORB.cpp, BowVector.cpp,
+//  FeatureVector.cpp, ScoringObject.cpp).  Pinned against the reference's own DBoW2 compiled in place
+//  (oracle/_ref/libdbow2_ref.so, tests/test_bow_cpu.py) and tests/golden/bow_small_voc.npz.
+// ------------------------------------------------------------------------------------------------
+struct mcso_voc {
+    int k, L, scoring, weighting;
+    std::vector<std::vector<int>> children;      // in the order load() appended them
+    std::vector<double> weight;
+    std::vector<uint8_t> desc;                   // n_nodes x 32
+    std::vector<int> word_of_node;
+};
+
+mcso_voc* mcso_voc_create(int k, int L, int scoring, int weighting, int n_nodes, const int* parent, const double* weight,
+                          const uint8_t* desc, const int* node_order, int n_words, const int* word_node) {
+    mcso_voc* v = new mcso_voc();
+    v->k = k; v->L = L; v->scoring = scoring; v->weighting = weighting;
+    v->children.resize(n_nodes);
+    for (int i = 0; i + 1 < n_nodes; ++i) {       // TemplatedVocabulary.h:1596-1608: m_nodes[pid].children.push_back(nid) in file order
+        const int nid = node_order ? node_order[i] : i + 1;
+        v->children[parent[nid]].push_back(nid);
+    }
+    v->weight.assign(weight, weight + n_nodes);
+    v->desc.assign(desc, desc + (size_t)n_nodes * 32);
+    v->word_of_node.assign(n_nodes, -1);
+    for (int w = 0; w < n_words; ++w) v->word_of_node[word_node[w]] = w;     // :1615-1622
+    return v;
+}
+void mcso_voc_destroy(mcso_voc* v) { delete v; }
+
+// FORB::distance  FORB.cpp:84-104: 8 x 32-bit words, bit count (the parallel bit trick there == popcount)
+static int forb_distance(const uint8_t* a, const uint8_t* b) {
+    int d = 0;
+    for (int i = 0; i < 8; ++i) {
+        uint32_t x, y;
+        std::memcpy(&x, a + 4 * i, 4); std::memcpy(&y, b + 4 * i, 4);
+        d += __builtin_popcount(x ^ y);
+    }
+    return d;
+}
+
+// transform(feature, word_id, weight, nid, levelsup)  TemplatedVocabulary.h:1218-1261.
+// nid: the reference only assigns it when the descent passes level L - levelsup (or that level is <= 0 -> root);
+// a shallower leaf leaves the caller's variable indeterminate.  Restated as "the leaf itself" (documented in DESIGN.md).
+static void voc_descend(const mcso_voc* v, const uint8_t* f, int levelsup, int* word, double* weight, int* nid) {
+    const int nid_level = v->L - levelsup;
+    int node = 0, level = 0, at_level = nid_level <= 0 ? 0 : -1;
+    do {
+        ++level;
+        const std::vector<int>& ch = v->children[node];
+        node = ch[0];
+        double best = (double)forb_distance(f, &v->desc[(size_t)node * 32]);
+        for (size_t c = 1; c < ch.size(); ++c) {
+            const double d = (double)forb_distance(f, &v->desc[(size_t)ch[c] * 32]);
+            if (d < best) { best = d; node = ch[c]; }
+        }
+        if (level == nid_level) at_level = node;
+    } while (!v->children[node].empty());
+    *word = v->word_of_node[node];
+    *weight = v->weight[node];
+    *nid = at_level >= 0 ? at_level : node;
+}
+
+int mcso_bow_transform(const mcso_voc* v, const uint8_t* desc, int n, int levelsup, int* word, double* weight, int* node) {
+    for (int i = 0; i < n; ++i) {
+        int w, nd; double wt;
+        voc_descend(v, desc + (size_t)i * 32, levelsup, &w, &wt, &nd);
+        if (word) word[i] = w;
+        if (weight) weight[i] = wt;
+        if (node) node[i] = nd;
+    }
+    return 0;
+}
+
+// transform(features, BowVector, FeatureVector, levelsup)  TemplatedVocabulary.h:1126-1194 with
+// BowVector::addWeight / addIfNotExist / normalize (BowVector.cpp:34-95) and FeatureVector::addFeature (FeatureVector.cpp:28-42)
+int mcso_bow_vectors(const mcso_voc* v, const uint8_t* desc, int n, int levelsup, int* bow_words, double* bow_values, int* n_bow,
+                     int* fv_nodes, int* fv_off, int* n_fv, int* fv_feat) {
+    std::map<unsigned, double> bow;
+    std::map<unsigned, std::vector<unsigned>> fv;
+    // scoring objects: mustNormalize (ScoringObject.h:74-89): all but DOT_PRODUCT; L2 norm only for L2_NORM
+    const bool must = v->scoring != 5;
+    const bool l2 = v->scoring == 1;
+    const bool accumulate = v->weighting == 0 || v->weighting == 1;          // TF_IDF, TF
+    if (!v->children.empty() && !v->children[0].empty())
+        for (int i = 0; i < n; ++i) {
+            int w, nd; double wt;
+            voc_descend(v, desc + (size_t)i * 32, levelsup, &w, &wt, &nd);
+            if (!(wt > 0)) continue;                                         // stopped word
+            auto it = bow.find((unsigned)w);
+            if (it == bow.end()) bow[(unsigned)w] = wt;
+            else if (accumulate) it->second += wt;
+            fv[(unsigned)nd].push_back((unsigned)i);
+        }
+    if (accumulate && !bow.empty() && !must) {
+        const double nd = (double)bow.size();
+        for (auto& e : bow) e.second /= nd;
+    }
+    if (must) {
+        double norm = 0.0;
+        if (!l2) for (auto& e : bow) norm += std::fabs(e.second);
+        else { for (auto& e : bow) norm += e.second * e.second; norm = std::sqrt(norm); }
+        if (norm > 0.0) for (auto& e : bow) e.second /= norm;
+    }
+    int k = 0;
+    for (auto& e : bow) { bow_words[k] = (int)e.first; bow_values[k] = e.second; ++k; }
+    *n_bow = k;
+    int f = 0, o = 0;
+    for (auto& e : fv) {
+        fv_nodes[f] = (int)e.first; fv_off[f] = o;
+        for (unsigned i : e.second) fv_feat[o++] = (int)i;
+        ++f;
+    }
+    fv_off[f] = o; *n_fv = f;
+    return 0;
+}
+
+// GeneralScoring::score flavours  ScoringObject.cpp:23-313 (the lower_bound skips there are a plain sorted merge)
+double mcso_bow_score(int scoring, const int* w1, const double* v1, int n1, const int* w2, const double* v2, int n2) {
+    const double LOG_EPS = std::log(DBL_EPSILON);                            // ScoringObject.cpp:18
+    double score = 0;
+    int i = 0, j = 0;
+    while (i < n1 && j < n2) {
+        const double vi = v1[i], wi = v2[j];
+        if (w1[i] == w2[j]) {
+            switch (scoring) {
+                case 0: score += std::fabs(vi - wi) - std::fabs(vi) - std::fabs(wi); break;
+                case 1: case 5: score += vi * wi; break;
+                case 2: if (vi + wi != 0.0) score += vi * wi / (vi + wi); break;
+                case 3: if (vi != 0 && wi != 0) score += vi * std::log(vi / wi); break;
+                case 4: score += std::sqrt(vi * wi); break;
+            }
+            ++i; ++j;
+        } else if (w1[i] < w2[j]) {
+            if (scoring == 3) score += vi * (std::log(vi) - LOG_EPS);        // KL also charges words only v1 has (:196-200)
+            ++i;
+        } else {
+            ++j;
+        }
+    }
+    switch (scoring) {
+        case 0: return -score / 2.0;
+        case 1: return score >= 1 ? 1.0 : 1.0 - std::sqrt(1.0 - score);
+        case 2: return 2. * score;
+        case 3:
+            for (; i < n1; ++i) if (v1[i] != 0) score += v1[i] * (std::log(v1[i]) - LOG_EPS);
+            return score;
+        default: return score;
+    }
+}
+
+// cORBmatcher::SearchByBoW(cMultiKeyFrame*, cMultiFrame&, vpMapPointMatches)  src/cORBmatcher.cpp:179-324
+// (mbCheckOrientation == false).  Feature vectors as CSR (nodes ascending).
+int mcso_search_by_bow(const uint8_t* desc1, const uint8_t* mask1, const uint8_t* valid1, int n1, const int* fv1_nodes,
+                       const int* fv1_off, int n_fv1, const int* fv1_feat, const uint8_t* desc2, const uint8_t* mask2, int n2,
+                       const int* fv2_nodes, const int* fv2_off, int n_fv2, const int* fv2_feat, int dim, int th_low,
+                       double nnratio, int* match_of_2, int* nmatches) {
+    const bool masks = mask1 && mask2;
+    for (int i = 0; i < n2; ++i) match_of_2[i] = -1;
+    int nm = 0, a = 0, b = 0;
+    while (a < n_fv1 && b < n_fv2) {
+        if (fv1_nodes[a] == fv2_nodes[b]) {
+            for (int ia = fv1_off[a]; ia < fv1_off[a + 1]; ++ia) {
+                const int i1 = fv1_feat[ia];
+                if (valid1 && !valid1[i1]) continue;
+                int best1 = INT_MAX, best2 = INT_MAX, bestIdx = -1;
+                for (int ib = fv2_off[b]; ib < fv2_off[b + 1]; ++ib) {
+                    const int i2 = fv2_feat[ib];
+                    if (match_of_2[i2] >= 0) continue;
+                    const int dist = masks ? dist64m(row64(desc1, i1, dim), row64(desc2, i2, dim), row64(mask1, i1, dim),
+                                                     row64(mask2, i2, dim), dim)
+                                           : dist64(row64(desc1, i1, dim), row64(desc2, i2, dim), dim);
+                    if (dist < best1) { best2 = best1; best1 = dist; bestIdx = i2; }
+                    else if (dist < best2) best2 = dist;
+                }
+                if (best1 <= th_low && (double)best1 < nnratio * (double)best2) {
+                    match_of_2[bestIdx] = i1;
+                    ++nm;
+                }
+            }
+            ++a; ++b;
+        } else if (fv1_nodes[a] < fv2_nodes[b]) ++a;
+        else ++b;
+    }
+    *nmatches = nm;
+    return 0;
 }
 
 }  // extern "C"

@@ -251,3 +251,56 @@ def frame_prepare(keys, key_cam, cams):
     ning = C.c_int(0)
     lib().mcso_frame_prepare(_p(keys), _p(key_cam), n, ocs, nc, _p(rays), _p(start), _p(items), C.byref(ning))
     return rays, start, items[:ning.value].copy()
+
+
+# ---- bag of words (restatement of the DBoW2 vocabulary as the reference uses it) ----------------------------
+class OracleVocabulary:
+    """voc: dict / npz with k, L, scoring, weighting, parent, weight, desc, node_order, word_node (tools/extract_vocabulary.py)."""
+
+    def __init__(self, voc, scoring=None, weighting=None):
+        self.scoring = int(voc["scoring"] if scoring is None else scoring)
+        self.weighting = int(voc["weighting"] if weighting is None else weighting)
+        par = np.ascontiguousarray(voc["parent"], np.int32); wt = np.ascontiguousarray(voc["weight"], np.float64)
+        ds = np.ascontiguousarray(voc["desc"], np.uint8); wn = np.ascontiguousarray(voc["word_node"], np.int32)
+        order = voc["node_order"] if "node_order" in voc else None
+        order = None if order is None else np.ascontiguousarray(order, np.int32)
+        lib().mcso_voc_create.restype = C.c_void_p
+        self.h = C.c_void_p(lib().mcso_voc_create(int(voc["k"]), int(voc["L"]), self.scoring, self.weighting, len(par), _p(par), _p(wt),
+                                                  _p(ds), _p(order), len(wn), _p(wn)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().mcso_voc_destroy(self.h); self.h = None
+
+    def transform_features(self, desc, levelsup=4):
+        desc = np.ascontiguousarray(desc, np.uint8); n = len(desc)
+        w = np.zeros(n, np.int32); wt = np.zeros(n, np.float64); nd = np.zeros(n, np.int32)
+        lib().mcso_bow_transform(self.h, _p(desc), n, levelsup, _p(w), _p(wt), _p(nd))
+        return w, wt, nd
+
+    def transform(self, desc, levelsup=4):
+        """-> (bow_words, bow_values, fv_nodes, fv_offsets, fv_features)"""
+        desc = np.ascontiguousarray(desc, np.uint8); n = len(desc)
+        bw = np.zeros(max(n, 1), np.int32); bv = np.zeros(max(n, 1), np.float64); nb = C.c_int(0)
+        fn = np.zeros(max(n, 1), np.int32); fo = np.zeros(n + 2, np.int32); nf = C.c_int(0); ff = np.zeros(max(n, 1), np.int32)
+        lib().mcso_bow_vectors(self.h, _p(desc), n, levelsup, _p(bw), _p(bv), C.byref(nb), _p(fn), _p(fo), C.byref(nf), _p(ff))
+        return bw[:nb.value].copy(), bv[:nb.value].copy(), fn[:nf.value].copy(), fo[:nf.value + 1].copy(), ff[:fo[nf.value]].copy()
+
+    def score(self, w1, v1, w2, v2):
+        w1 = np.ascontiguousarray(w1, np.int32); w2 = np.ascontiguousarray(w2, np.int32)
+        v1 = np.ascontiguousarray(v1, np.float64); v2 = np.ascontiguousarray(v2, np.float64)
+        lib().mcso_bow_score.restype = C.c_double
+        return lib().mcso_bow_score(self.scoring, _p(w1), _p(v1), len(w1), _p(w2), _p(v2), len(w2))
+
+
+def search_by_bow(d1, m1, valid1, fv1, d2, m2, fv2, th_low, nnratio):
+    """fv = (nodes, offsets, features) -> (nmatches, match_of_2)"""
+    d1, d2 = np.ascontiguousarray(d1, np.uint8), np.ascontiguousarray(d2, np.uint8)
+    m1 = None if m1 is None else np.ascontiguousarray(m1, np.uint8)
+    m2 = None if m2 is None else np.ascontiguousarray(m2, np.uint8)
+    valid1 = None if valid1 is None else np.ascontiguousarray(valid1, np.uint8)
+    a = [np.ascontiguousarray(x, np.int32) for x in fv1]; b = [np.ascontiguousarray(x, np.int32) for x in fv2]
+    out = np.zeros(len(d2), np.int32); n = C.c_int(0)
+    lib().mcso_search_by_bow(_p(d1), _p(m1), _p(valid1), len(d1), _p(a[0]), _p(a[1]), len(a[0]), _p(a[2]), _p(d2), _p(m2), len(d2),
+                             _p(b[0]), _p(b[1]), len(b[0]), _p(b[2]), d1.shape[1], th_low, C.c_double(nnratio), _p(out), C.byref(n))
+    return n.value, out
