@@ -22,6 +22,9 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -216,6 +219,86 @@ struct MapPointFields {            // ref include/cMapPoint.h (tracking fields) 
     }
 };
 
+// ---- ORBVocabulary (ref include/cORBVocabulary.h:34 = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>) ----
+namespace DBoW2 {
+// BowVector / FeatureVector keep DBoW2's container types (ref ThirdParty/DBoW2/DBoW2/BowVector.h:62, FeatureVector.h:24)
+typedef unsigned int WordId;
+typedef double WordValue;
+typedef unsigned int NodeId;
+class BowVector : public std::map<WordId, WordValue> {};
+class FeatureVector : public std::map<NodeId, std::vector<unsigned int> > {};
+}  // namespace DBoW2
+
+class ORBVocabulary {
+public:
+    ORBVocabulary() : h_(nullptr), n_words_(0) {}
+    ~ORBVocabulary() { if (h_) mcs_vocabulary_destroy(h_); }
+    ORBVocabulary(const ORBVocabulary&) = delete;
+    ORBVocabulary& operator=(const ORBVocabulary&) = delete;
+    // DBoW2 text layout (ref TemplatedVocabulary.h:1338-1425): "k L scoring weighting", then one line per node
+    // "parent isLeaf d0 .. d31 weight"; node ids and word ids follow the line order.
+    bool loadFromTextFile(const std::string& filename) {
+        std::ifstream f(filename.c_str());
+        if (!f) return false;
+        int k, L, sc, wg;
+        std::string line;
+        if (!std::getline(f, line)) return false;
+        { std::stringstream ss(line); ss >> k >> L >> sc >> wg; }
+        if (k < 0 || k > 20 || L < 1 || L > 10 || sc < 0 || sc > 5 || wg < 0 || wg > 3) return false;     // same sanity check as ref :1359-1363
+        std::vector<int> parent(1, -1), words;
+        std::vector<double> weight(1, 0.0);
+        std::vector<uint8_t> desc(32, 0);
+        while (std::getline(f, line)) {
+            if (line.find_first_not_of(" \t\r\n") == std::string::npos) continue;
+            std::stringstream ss(line);
+            int pid = 0, leaf = 0; double w = 0;
+            ss >> pid >> leaf;
+            const int nid = (int)parent.size();
+            for (int i = 0; i < 32; ++i) { int b = 0; ss >> b; desc.push_back((uint8_t)b); }
+            ss >> w;
+            parent.push_back(pid); weight.push_back(w);
+            if (leaf > 0) words.push_back(nid);
+        }
+        return create(k, L, sc, wg, parent, weight, desc, words);
+    }
+    bool create(int k, int L, int scoring, int weighting, const std::vector<int>& parent, const std::vector<double>& weight,
+                const std::vector<uint8_t>& desc, const std::vector<int>& word_node, const int* node_order = nullptr) {
+        if (h_) { mcs_vocabulary_destroy(h_); h_ = nullptr; }
+        mcs::check(mcs_vocabulary_create(k, L, scoring, weighting, (int)parent.size(), parent.data(), weight.data(), desc.data(), node_order,
+                                         (int)word_node.size(), word_node.data(), &h_));
+        n_words_ = (unsigned)word_node.size();
+        return true;
+    }
+    unsigned int size() const { return n_words_; }
+    bool empty() const { return n_words_ == 0; }
+    // transform(features, BowVector&, FeatureVector&, levelsup)  ref :1126-1194; features = descriptor rows of all cameras
+    void transform(const mcs::Mat8& features, DBoW2::BowVector& v, DBoW2::FeatureVector& fv, int levelsup) const {
+        v.clear(); fv.clear();
+        if (!h_ || features.rows == 0) return;
+        const int n = features.rows;
+        std::vector<int> bw(n), fn(n), fo(n + 1), ff(n);
+        std::vector<double> bv(n);
+        int nb = 0, nf = 0;
+        mcs::check(mcs_bow_vectors(h_, features.ptr(), n, levelsup, bw.data(), bv.data(), &nb, fn.data(), fo.data(), &nf, ff.data()));
+        for (int i = 0; i < nb; ++i) v.insert(v.end(), std::make_pair((DBoW2::WordId)bw[i], bv[i]));
+        for (int i = 0; i < nf; ++i)
+            fv.insert(fv.end(), std::make_pair((DBoW2::NodeId)fn[i], std::vector<unsigned int>(ff.begin() + fo[i], ff.begin() + fo[i + 1])));
+    }
+    double score(const DBoW2::BowVector& a, const DBoW2::BowVector& b) const {
+        std::vector<int> wa, wb; std::vector<double> va, vb;
+        for (const auto& e : a) { wa.push_back((int)e.first); va.push_back(e.second); }
+        for (const auto& e : b) { wb.push_back((int)e.first); vb.push_back(e.second); }
+        double s = 0;
+        mcs::check(mcs_bow_score(h_, wa.data(), va.data(), (int)wa.size(), wb.data(), vb.data(), (int)wb.size(), &s));
+        return s;
+    }
+    const mcs_vocabulary* handle() const { return h_; }
+
+private:
+    mcs_vocabulary* h_;
+    unsigned n_words_;
+};
+
 class cORBmatcher {
 public:
     // ref src/cORBmatcher.cpp:46-64
@@ -253,9 +336,32 @@ public:
                                         mbFeatDim, TH_LOW_, mfNNratio, vpMatches12.data(), &n));
         return n;
     }
+    // SearchByBoW(cMultiKeyFrame* pKF, cMultiFrame& F, vpMapPointMatches)  ref :179-324: matching inside common vocabulary
+    // nodes.  validKF flags key-frame keypoints with a good map point; vpMatchesF[i] = key-frame keypoint matched to frame
+    // keypoint i, or -1 (the caller maps it to pKF->GetMapPointMatches()[...]).
+    int SearchByBoW(const mcs::Mat8& descKF, const mcs::Mat8& maskKF, const std::vector<uint8_t>& validKF,
+                    const DBoW2::FeatureVector& featVecKF, const mcs::Mat8& descF, const mcs::Mat8& maskF,
+                    const DBoW2::FeatureVector& featVecF, std::vector<int>& vpMatchesF) {
+        std::vector<int> n1, o1, f1, n2, o2, f2;
+        flatten(featVecKF, n1, o1, f1); flatten(featVecF, n2, o2, f2);
+        int n = 0;
+        vpMatchesF.assign(descF.rows, -1);
+        mcs::check(mcs_search_by_bow(descKF.ptr(), havingMasks ? maskKF.ptr() : nullptr, validKF.empty() ? nullptr : validKF.data(), descKF.rows,
+                                     n1.data(), o1.data(), (int)n1.size(), f1.data(), descF.ptr(), havingMasks ? maskF.ptr() : nullptr, descF.rows,
+                                     n2.data(), o2.data(), (int)n2.size(), f2.data(), mbFeatDim, TH_LOW_, mfNNratio, vpMatchesF.data(), &n));
+        return n;
+    }
     int TH_LOW_, TH_HIGH_;
 
 protected:
+    static void flatten(const DBoW2::FeatureVector& fv, std::vector<int>& nodes, std::vector<int>& off, std::vector<int>& feat) {
+        off.push_back(0);
+        for (const auto& e : fv) {
+            nodes.push_back((int)e.first);
+            for (unsigned int i : e.second) feat.push_back((int)i);
+            off.push_back((int)feat.size());
+        }
+    }
     double mfNNratio;
     bool mbCheckOrientation;      // the reference compiles the orientation check out (include/cORBmatcher.h:40)
     int mbFeatDim;

@@ -518,3 +518,120 @@ class cORBmatcher:
         _check(lib().mcs_match_bruteforce(_p(d1), _p(m1), _p(v1), len(d1), _p(d2), _p(m2), _p(v2), len(d2), d1.shape[1],
                                           self.TH_LOW_, C.c_double(self.mfNNratio), _p(m12), C.byref(n)))
         return n.value, m12
+
+    def SearchByBoWFrame(self, desc_kf, featvec_kf, desc_f, featvec_f, mask_kf=None, mask_f=None, valid_kf=None):
+        """SearchByBoW(cMultiKeyFrame* pKF, cMultiFrame& F, vpMapPointMatches) (ref src/cORBmatcher.cpp:179-324): matching
+        restricted to keypoints that fall into the same vocabulary node.  featvec_* = (nodes, offsets, features) as returned
+        by ORBVocabulary.transform.  Returns (nmatches, match_of_f) with match_of_f[i] = key-frame keypoint or -1."""
+        d1 = np.ascontiguousarray(desc_kf, np.uint8)
+        d2 = np.ascontiguousarray(desc_f, np.uint8)
+        use = self.havingMasks and mask_kf is not None and mask_f is not None
+        m1 = np.ascontiguousarray(mask_kf, np.uint8) if use else None
+        m2 = np.ascontiguousarray(mask_f, np.uint8) if use else None
+        v1 = None if valid_kf is None else np.ascontiguousarray(valid_kf, np.uint8)
+        a = [np.ascontiguousarray(x, np.int32) for x in featvec_kf]
+        b = [np.ascontiguousarray(x, np.int32) for x in featvec_f]
+        out = np.zeros(len(d2), np.int32)
+        n = C.c_int32(0)
+        _check(lib().mcs_search_by_bow(_p(d1), _p(m1), _p(v1), len(d1), _p(a[0]), _p(a[1]), len(a[0]), _p(a[2]), _p(d2), _p(m2), len(d2),
+                                       _p(b[0]), _p(b[1]), len(b[0]), _p(b[2]), d1.shape[1], self.TH_LOW_, C.c_double(self.mfNNratio),
+                                       _p(out), C.byref(n)))
+        return n.value, out
+
+
+class ORBVocabulary:
+    """Mirror of ORBVocabulary = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> (ref include/cORBVocabulary.h:34) for the
+    calls the SLAM front end makes: load, transform(features, BowVector, FeatureVector, levelsup), score, size.
+    The tree lives on the GPU (mcs_vocabulary_create); `voc` is a mapping with k, L, scoring, weighting, parent, weight,
+    desc, word_node and optionally node_order (tools/extract_vocabulary.py writes that layout)."""
+
+    def __init__(self, voc, scoring=None, weighting=None):
+        self.k, self.L = int(voc["k"]), int(voc["L"])
+        self.scoring = int(voc["scoring"] if scoring is None else scoring)
+        self.weighting = int(voc["weighting"] if weighting is None else weighting)
+        par = np.ascontiguousarray(voc["parent"], np.int32)
+        wt = np.ascontiguousarray(voc["weight"], np.float64)
+        ds = np.ascontiguousarray(voc["desc"], np.uint8)
+        wn = np.ascontiguousarray(voc["word_node"], np.int32)
+        order = voc["node_order"] if "node_order" in voc else None
+        order = None if order is None else np.ascontiguousarray(order, np.int32)
+        if ds.shape != (len(par), 32) or len(wt) != len(par):
+            raise ValueError("vocabulary arrays disagree in size")
+        self._n_words = len(wn)
+        self._h = C.c_void_p()
+        _check(lib().mcs_vocabulary_create(self.k, self.L, self.scoring, self.weighting, len(par), _p(par), _p(wt), _p(ds), _p(order),
+                                           len(wn), _p(wn), C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().mcs_vocabulary_destroy(self._h)
+            self._h = None
+
+    @staticmethod
+    def loadFromTextFile(path, **kw):
+        """DBoW2 text layout (ref TemplatedVocabulary.h:1338-1425): 'k L scoring weighting', then one line per node
+        'parent isLeaf d0..d31 weight', node ids and word ids in line order."""
+        lines = [ln for ln in open(path).read().split("\n") if ln.strip()]
+        k, L, sc, wg = (int(t) for t in lines[0].split()[:4])
+        n = len(lines)
+        parent = np.zeros(n, np.int32); weight = np.zeros(n); desc = np.zeros((n, 32), np.uint8); words = []
+        for i, ln in enumerate(lines[1:], start=1):
+            t = ln.split()
+            parent[i] = int(t[0]); desc[i] = [int(x) for x in t[2:34]]; weight[i] = float(t[34])
+            if int(t[1]) > 0:
+                words.append(i)
+        return ORBVocabulary(dict(k=k, L=L, scoring=sc, weighting=wg, parent=parent, weight=weight, desc=desc,
+                                  word_node=np.asarray(words, np.int32)), **kw)
+
+    @staticmethod
+    def load(path, **kw):
+        """DBoW2 YAML layout as cv::FileStorage writes it (ref TemplatedVocabulary.h:1476-1624)."""
+        import re
+        txt = open(path).read()
+        head = {key: int(re.search(r"\b%s:\s*(\d+)" % key, txt).group(1)) for key in ("k", "L", "scoringType", "weightingType")}
+        nodes = re.findall(r"nodeId:(\d+),\s*parentId:(\d+),\s*weight:([-+0-9.eE]+),\s*descriptor:\"([^\"]*)\"", txt)
+        words = re.findall(r"wordId:(\d+),\s*nodeId:(\d+)", txt)
+        n = len(nodes) + 1
+        parent = np.zeros(n, np.int32); weight = np.zeros(n); desc = np.zeros((n, 32), np.uint8); order = np.zeros(n - 1, np.int32)
+        for i, (nid, pid, w, d) in enumerate(nodes):
+            nid = int(nid); order[i] = nid; parent[nid] = int(pid); weight[nid] = float(w + "0" if w.endswith(".") else w)
+            desc[nid] = [int(x) for x in d.split()]
+        wn = np.zeros(len(words), np.int32)
+        for wid, nid in words:
+            wn[int(wid)] = int(nid)
+        return ORBVocabulary(dict(k=head["k"], L=head["L"], scoring=head["scoringType"], weighting=head["weightingType"], parent=parent,
+                                  weight=weight, desc=desc, node_order=order, word_node=wn), **kw)
+
+    def size(self):
+        return self._n_words
+
+    def transform_features(self, desc, levelsup=4):
+        """per descriptor: (word id, word weight, node id at level L - levelsup)  (ref :1218-1261)"""
+        desc = np.ascontiguousarray(desc, np.uint8)
+        if desc.ndim != 2 or desc.shape[1] != 32:
+            raise ValueError("the vocabulary works on 32-byte descriptors (FORB::L)")
+        n = len(desc)
+        w = np.zeros(n, np.int32); wt = np.zeros(n, np.float64); nd = np.zeros(n, np.int32)
+        _check(lib().mcs_bow_transform(self._h, _p(desc), n, levelsup, _p(w), _p(wt), _p(nd)))
+        return w, wt, nd
+
+    def transform(self, desc, levelsup=4):
+        """transform(features, BowVector&, FeatureVector&, levelsup) (ref :1126-1194).
+        -> (bow_words, bow_values, (fv_nodes, fv_offsets, fv_features))"""
+        desc = np.ascontiguousarray(desc, np.uint8)
+        if desc.ndim != 2 or (len(desc) and desc.shape[1] != 32):
+            raise ValueError("the vocabulary works on 32-byte descriptors (FORB::L)")
+        n = len(desc)
+        bw = np.zeros(max(n, 1), np.int32); bv = np.zeros(max(n, 1), np.float64); nb = C.c_int32(0)
+        fn = np.zeros(max(n, 1), np.int32); fo = np.zeros(n + 2, np.int32); nf = C.c_int32(0); ff = np.zeros(max(n, 1), np.int32)
+        _check(lib().mcs_bow_vectors(self._h, _p(desc), n, levelsup, _p(bw), _p(bv), C.byref(nb), _p(fn), _p(fo), C.byref(nf), _p(ff)))
+        k = nf.value
+        return bw[:nb.value].copy(), bv[:nb.value].copy(), (fn[:k].copy(), fo[:k + 1].copy(), ff[:fo[k]].copy())
+
+    def score(self, v1, v2):
+        """score(BowVector, BowVector) with the vocabulary's scoring type; v = (words, values)."""
+        w1 = np.ascontiguousarray(v1[0], np.int32); x1 = np.ascontiguousarray(v1[1], np.float64)
+        w2 = np.ascontiguousarray(v2[0], np.int32); x2 = np.ascontiguousarray(v2[1], np.float64)
+        s = C.c_double(0)
+        _check(lib().mcs_bow_score(self._h, _p(w1), _p(x1), len(w1), _p(w2), _p(x2), len(w2), C.byref(s)))
+        return s.value

@@ -62,12 +62,6 @@ __device__ __forceinline__ int sample_px(const uint8_t* bimg, const uint8_t* uim
     return uimg[(size_t)reflect101(row, g.h) * g.pitch + reflect101(col, g.w)];
 }
 
-__device__ __forceinline__ double2 lds_pair(unsigned addr) {
-    double2 r;
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(addr));
-    return r;
-}
-
 constexpr int kDescWarps = 4;
 constexpr int kPatchR = 25;                       // staged patch: rows/cols ky/kx -25 .. +25 (keypoints are >= 25 px inside the ROI)
 constexpr int kPatchS = 64;                       // bytes per staged patch row (4-byte aligned start + 51 columns)
@@ -134,8 +128,7 @@ __device__ __noinline__ unsigned orb_pattern_global(const char2* s_pat, double c
     return out;
 }
 
-template <int PPL /* pattern points per lane: 16 for descSize <= 32, 32 for descSize 64 */, int MINB = 4,
-          bool CSM = false /* polynomial coefficients in shared memory instead of registers */>
+template <int PPL /* pattern points per lane: 16 for descSize <= 32, 32 for descSize 64 */, int MINB = 4>
 __global__ void __launch_bounds__(kDescWarps * 32, MINB)
 describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, const mcs_ocam* __restrict__ cams,
                 const DistortLut* __restrict__ luts, const int* __restrict__ cam_of_image,
@@ -145,7 +138,6 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
     __shared__ char2 s_pat[PPL * 32];            // [j][lane] : point 16*byte + k with byte = lane + 32*(j/16), k = j%16
     __shared__ __align__(16) double2 s_patd[PPL * 32];   // same, as doubles (int->double conversions run on the slow XU pipe)
     __shared__ mcs_ocam s_cam[kDescWarps];
-    __shared__ __align__(16) double s_poly[kDescWarps][kLutStride];
     __shared__ __align__(16) uint8_t s_patch[kDescWarps][(2 * kPatchR + 1) * kPatchS];
     const int ds = geom->desc_size;
     for (int i = threadIdx.x; i < PPL * 32; i += blockDim.x) {
@@ -157,16 +149,13 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
     __syncthreads();
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    // one warp per slot (a persistent grid-stride variant measured 4 % slower: static imbalance + 60 B more spills)
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int sel_total = geom->sel_total;
+    const int b = warp_global / sel_total;
+    if (b >= n_images) return;
+    const int slot = warp_global - b * sel_total;
     const int L = geom->nlevels;
-    const long long total_warps = (long long)n_images * sel_total;
-    // persistent blocks: the pattern tables above are built once per block, every warp then walks the slots with a
-    // grid-sized stride
-    for (long long warp_global = (long long)blockIdx.x * kDescWarps + wib; warp_global < total_warps;
-         warp_global += (long long)gridDim.x * kDescWarps) {
-    const int b = (int)(warp_global / sel_total);
-    const int slot = (int)(warp_global - (long long)b * sel_total);
-    __syncwarp();                                 // the previous keypoint's patch is no longer read
     int level = 0, off = 0;
     for (int l = 0; l < L; ++l)
         if (slot >= geom->lv[l].sel_off) level = l;
@@ -179,9 +168,9 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
         for (int l = 0; l < L; ++l) tot += sel_count[b * L + l];
         counts_out[b] = min(tot, capacity);
     }
-    if (p >= cnt) continue;
+    if (p >= cnt) return;
     const int oidx = off + p;
-    if (oidx >= capacity) continue;
+    if (oidx >= capacity) return;
     const uint32_t c = sel_xys[(size_t)b * sel_total + slot];
     const int kx = corner_x(c), ky = corner_y(c);
     const uint8_t* uimg = args.lvl[level] + (size_t)b * g.img_bytes;
@@ -313,12 +302,7 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                 const double2 cc = __ldg(cp + 1 + k);
                 P[2 * k] = cc.x; P[2 * k + 1] = cc.y;
             }
-            if (CSM) {
-                if (lane < kLutStride / 2) ((double2*)s_poly[wib])[lane] = __ldg(cp + lane);
-                __syncwarp();
-            }
         }
-        const unsigned sp = (unsigned)__cvta_generic_to_shared(s_poly[wib]);
         const double inv_n = 1.0 / (double)(16 * ds);
         const bool lane_valid = (PPL == 32) || (lane < ds);      // descSize 16: lanes 16..31 own no byte
         for (int q = 0; q < npat; ++q) {
@@ -341,20 +325,9 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                 const double rinv = fma(y0 * e, fma(0.375, e, 0.5), y0), r = s2 * rinv;
                 // R(r) by Horner; |tau| > 1 (a point outside the fitted interval, or NaN from s2 == 0) is caught below
                 const double tau = fma(r, t_scale, t_off);
-                double gg;
-                if (CSM) {                      // warp-uniform 128-bit broadcast loads, not hoisted (register pressure)
-                    double2 cc = lds_pair(sp + 16 * (kLutDeg + 1) / 2);
-                    gg = fma(cc.y, tau, cc.x);
+                double gg = P[kLutDeg];
 #pragma unroll
-                    for (int k = (kLutDeg + 1) / 2 - 1; k >= 1; --k) {
-                        cc = lds_pair(sp + 16 * k);
-                        gg = fma(gg, tau, cc.y); gg = fma(gg, tau, cc.x);
-                    }
-                } else {
-                    gg = P[kLutDeg];
-#pragma unroll
-                    for (int k = kLutDeg - 1; k >= 0; --k) gg = fma(gg, tau, P[k]);
-                }
+                for (int k = kLutDeg - 1; k >= 0; --k) gg = fma(gg, tau, P[k]);
                 worst_tau = max(worst_tau, __double2hiint(tau) & 0x7fffffff);
                 gg *= rinv;
                 const double uu = xr * gg, vv = yr * gg;
@@ -427,7 +400,6 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
         k.octave = level; k.class_id = -1;
         kps_out[(size_t)b * capacity + oidx] = k;
     }
-    }   // slot loop
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -515,28 +487,8 @@ cudaError_t launch_describe(const PyramidGeom& G, const PyramidGeom* G_dev, int 
                             const int* sel_count, mcs_keypoint* kps, uint8_t* desc, uint8_t* dmask, int* counts, int capacity,
                             cudaStream_t st) {
     const long long warps = (long long)n_images * G.sel_total;
-    static const int variant = getenv("MCS_K3_MINB") ? atoi(getenv("MCS_K3_MINB")) : 4;     // occupancy experiment knob
-    static const int waves = getenv("MCS_K3_WAVES") ? atoi(getenv("MCS_K3_WAVES")) : 8;
-    static int n_sm = 0;
-    if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
-    const long long all_blocks = (warps + kDescWarps - 1) / kDescWarps;
-    const int blocks = (int)std::max<long long>(1, std::min<long long>(all_blocks, (long long)n_sm * 4 * waves));
-    if (G.desc_size <= 32 && variant == 5)
-        describe_kernel<16, 5><<<blocks, kDescWarps * 32, 0, st>>>(G_dev, args, cams, luts, cam_of_image, sel_xys, sel_count, kps, desc,
-                                                                  dmask, counts, capacity, n_images);
-    else if (G.desc_size <= 32 && variant == 6)
-        describe_kernel<16, 6><<<blocks, kDescWarps * 32, 0, st>>>(G_dev, args, cams, luts, cam_of_image, sel_xys, sel_count, kps, desc,
-                                                                  dmask, counts, capacity, n_images);
-    else if (G.desc_size <= 32 && variant == 15)
-        describe_kernel<16, 5, true><<<blocks, kDescWarps * 32, 0, st>>>(G_dev, args, cams, luts, cam_of_image, sel_xys, sel_count, kps, desc,
-                                                                        dmask, counts, capacity, n_images);
-    else if (G.desc_size <= 32 && variant == 16)
-        describe_kernel<16, 6, true><<<blocks, kDescWarps * 32, 0, st>>>(G_dev, args, cams, luts, cam_of_image, sel_xys, sel_count, kps, desc,
-                                                                        dmask, counts, capacity, n_images);
-    else if (G.desc_size <= 32 && variant == 3)
-        describe_kernel<16, 3><<<blocks, kDescWarps * 32, 0, st>>>(G_dev, args, cams, luts, cam_of_image, sel_xys, sel_count, kps, desc,
-                                                                  dmask, counts, capacity, n_images);
-    else if (G.desc_size <= 32)
+    // 128 registers (4 CTAs of 4 warps per SM): measured faster than 96 / 80 registers with more warps (spills), see DESIGN.md
+    if (G.desc_size <= 32)
         describe_kernel<16><<<blocks, kDescWarps * 32, 0, st>>>(G_dev, args, cams, luts, cam_of_image, sel_xys, sel_count, kps, desc,
                                                                dmask, counts, capacity, n_images);
     else

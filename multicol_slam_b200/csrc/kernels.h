@@ -58,4 +58,21 @@ cudaError_t launch_frustum(int n_cams, const double* mtmc_inv, const double* mtm
                            int n_points, const double* pos, const double* nrm, const double* dmin, const double* dmax, const double* sf,
                            int n_levels, uint8_t* in_view, int* level, double* px, double* py, double* vcos, cudaStream_t st);
 
+// ---- bag of words (bow_kernels.cu) ----
+// vocabulary tree on the device: CSR children in the reference's order, 32-byte node descriptors as uint4 pairs
+struct VocabularyDev {
+    const int* child_off;        // [n_nodes + 1]
+    const int* child_ids;        // [n_nodes - 1]
+    const uint4* desc;           // [2 * n_nodes]
+    const int* word_of_node;     // [n_nodes], -1 for inner nodes
+    const double* weight;        // [n_nodes]
+    int n_nodes, L;
+};
+cudaError_t launch_bow_descend(const VocabularyDev& v, const uint8_t* desc, int n, int levelsup, int* word, double* weight,
+                               int* node, cudaStream_t st);
+// one query of the feature-vector guided search: key-frame keypoint `feature` against cand[cand_start .. +cand_count)
+struct GroupQuery { int feature, cand_start, cand_count, out_off; };
+cudaError_t launch_group_distance(const GroupQuery* queries, int nq, const uint8_t* desc1, const uint8_t* mask1, const uint8_t* desc2,
+                                  const uint8_t* mask2, const int* cand, int dim, int* out, cudaStream_t st);
+
 }  // namespace mcs

@@ -1,6 +1,6 @@
 // Drives the reference-shaped C++ classes of include/mcs_shim.hpp: extraction through operator() on a synthetic
 // image, SearchByBoW between the frame and a bit-flipped copy.  Prints a line the pytest wrapper parses.
-// usage: shim_smoke <image.raw> <mask.raw> <w> <h>   (cam = Lafida camera 0, hard-coded from the fixture)
+// usage: shim_smoke <image.raw> <mask.raw> <w> <h> [vocabulary.txt]   (cam = Lafida camera 0, hard-coded from the fixture)
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -43,9 +43,24 @@ int main(int argc, char** argv) {
         int n = matcher.SearchByBoW(desc, dmask, {}, other, dmask, {}, m12);
         int self = 0;
         for (int r = 0; r < desc.rows; ++r) self += m12[r] == r;
-        printf("SHIM nkp=%zu levels=%d ds=%d hash=%llu same_mask=%d untouched=%d matches=%d self=%d d01=%d\n", kps.size(), extractor.GetLevels(),
-               extractor.GetDescriptorSize(), sum, (int)same_mask, (int)untouched, n, self,
-               DescriptorDistance64(desc.ptr64(0), other.ptr64(0), 32));
+        // bag of words (optional 5th argument: vocabulary in DBoW2 text layout): transform both frames, then the
+        // feature-vector guided SearchByBoW(KF, F) and the L1 score
+        int bow = -1, fvn = -1, bm = -1; unsigned long long bowhash = 0; double score = -1;
+        if (argc > 5) {
+            ORBVocabulary voc;
+            if (!voc.loadFromTextFile(argv[5])) { printf("SHIM error: vocabulary\n"); return 1; }
+            DBoW2::BowVector bv1, bv2; DBoW2::FeatureVector fv1, fv2;
+            voc.transform(desc, bv1, fv1, 4); voc.transform(other, bv2, fv2, 4);
+            bow = (int)bv1.size(); fvn = (int)fv1.size();
+            for (const auto& e : fv1) { bowhash = bowhash * 1315423911ull + e.first; for (unsigned i : e.second) bowhash = bowhash * 1315423911ull + i; }
+            for (const auto& e : bv1) bowhash = bowhash * 1315423911ull + e.first;
+            score = voc.score(bv1, bv2);
+            std::vector<int> mf;
+            bm = matcher.SearchByBoW(desc, dmask, {}, fv1, other, dmask, fv2, mf);
+        }
+        printf("SHIM nkp=%zu levels=%d ds=%d hash=%llu same_mask=%d untouched=%d matches=%d self=%d d01=%d bow=%d fvn=%d bowhash=%llu bm=%d score=%.17g\n",
+               kps.size(), extractor.GetLevels(), extractor.GetDescriptorSize(), sum, (int)same_mask, (int)untouched, n, self,
+               DescriptorDistance64(desc.ptr64(0), other.ptr64(0), 32), bow, fvn, bowhash, bm, score);
     } catch (const std::exception& e) {
         printf("SHIM error: %s\n", e.what());
         return 1;

@@ -28,7 +28,13 @@ def test_shim_extract_and_match(api, oa, cams, tmp_path):
     img, mask = synth.frame(cam, 4), synth.mirror_mask(cam)
     (tmp_path / "i.raw").write_bytes(img.tobytes())
     (tmp_path / "m.raw").write_bytes(mask.tobytes())
-    out = subprocess.run([str(EXE), str(tmp_path / "i.raw"), str(tmp_path / "m.raw"), "754", "480"], capture_output=True, text=True)
+    import sys
+    sys.path.insert(0, str(ROOT / "tools"))
+    from extract_vocabulary import write_text
+    voc = np.load(ROOT / "tests" / "golden" / "voc_small_9_6.npz")
+    write_text({k: voc[k] for k in voc.files}, tmp_path / "voc.txt")
+    out = subprocess.run([str(EXE), str(tmp_path / "i.raw"), str(tmp_path / "m.raw"), "754", "480", str(tmp_path / "voc.txt")],
+                         capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     kv = dict(t.split("=") for t in out.stdout.split()[1:])
     ok, od, om = oa.OracleExtractor(nfeatures=1000, do_dbrief=True, learn_masks=True).extract(img, mask, cam)
@@ -39,3 +45,19 @@ def test_shim_extract_and_match(api, oa, cams, tmp_path):
     assert kv["same_mask"] == "1" and kv["untouched"] == "1" and kv["levels"] == "8" and kv["ds"] == "32" and kv["d01"] == "1"
     n, m12 = oa.match_bruteforce(od, od ^ np.eye(32, dtype=np.uint8)[np.arange(len(od)) % 32], 32, 0.9, om, om)
     assert int(kv["matches"]) == n and int(kv["self"]) == int((m12 == np.arange(len(od))).sum())
+    # bag of words through the C++ ORBVocabulary / SearchByBoW(KF, F)
+    other = od ^ np.eye(32, dtype=np.uint8)[np.arange(len(od)) % 32]
+    o = oa.OracleVocabulary(voc)
+    bw, bv, fn, fo, ff = o.transform(od, 4)
+    bw2, bv2, fn2, fo2, ff2 = o.transform(other, 4)
+    h = 0
+    for k in range(len(fn)):
+        h = (h * 1315423911 + int(fn[k])) & 0xFFFFFFFFFFFFFFFF
+        for i in ff[fo[k]:fo[k + 1]]:
+            h = (h * 1315423911 + int(i)) & 0xFFFFFFFFFFFFFFFF
+    for w in bw:
+        h = (h * 1315423911 + int(w)) & 0xFFFFFFFFFFFFFFFF
+    assert int(kv["bow"]) == len(bw) and int(kv["fvn"]) == len(fn) and int(kv["bowhash"]) == h
+    assert float(kv["score"]) == o.score(bw, bv, bw2, bv2)
+    nb, _ = oa.search_by_bow(od, om, None, (fn, fo, ff), other, om, (fn2, fo2, ff2), 32, 0.9)
+    assert int(kv["bm"]) == nb and nb > 500
