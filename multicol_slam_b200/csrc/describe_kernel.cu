@@ -487,6 +487,7 @@ cudaError_t launch_describe(const PyramidGeom& G, const PyramidGeom* G_dev, int 
                             const int* sel_count, mcs_keypoint* kps, uint8_t* desc, uint8_t* dmask, int* counts, int capacity,
                             cudaStream_t st) {
     const long long warps = (long long)n_images * G.sel_total;
+    const int blocks = (int)std::max<long long>(1, (warps + kDescWarps - 1) / kDescWarps);
     // 128 registers (4 CTAs of 4 warps per SM): measured faster than 96 / 80 registers with more warps (spills), see DESIGN.md
     if (G.desc_size <= 32)
         describe_kernel<16><<<blocks, kDescWarps * 32, 0, st>>>(G_dev, args, cams, luts, cam_of_image, sel_xys, sel_count, kps, desc,
