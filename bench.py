@@ -297,9 +297,21 @@ def main():
         roof = {"kernel": "pyr_fast_kernel (K1, 8 launches/step, one per level)", "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": "bytes per launch (average over the 8 level launches); " + str(traffic_src),
                 "algorithmic_bytes_per_launch_avg": alg_bytes_img * B / NLEVELS, "peak_source": peak_src,
-                "issue_slot_utilisation_pct_ncu": 76.1,
+                "issue_slot_utilisation_pct_ncu": 72.5,
                 "algorithmic_bytes_per_camera_frame": alg_bytes_img, "ms_per_launch_avg": k1_ms_launch,
                 "stage_ms": {"k1_pyr_blur_fast": k_ms[0], "k2_octree": k_ms[1], "k3_angle_describe": k_ms[2], "m2_match_stream": match_ms}}
+        # the other stages against the same HBM peak (all compute-bound; bytes per SURVEY 8d)
+        n_feat = int(feats_rank)
+        k3_bytes = n_feat * (845 + 51 * 51 + 28 + 64)        # IC disc + blurred patch + keypoint + descriptor/mask
+        m2_pairs = (B - N_CAMS) if B > N_CAMS else 0
+        m2_bytes = m2_pairs * (64 * 2 * NFEATURES + 12 * NFEATURES) # 32(1+m)(Q+D) + 12Q per image pair
+        roof["other_stages"] = {
+            "k3_describe_kernel": {"bound": "fp64 issue / latency (ncu: FP64 pipe 41 %, issue 47 %)", "algorithmic_GB_per_s": k3_bytes / (k_ms[2] * 1e-3) / 1e9,
+                                   "frac_of_hbm_peak": k3_bytes / (k_ms[2] * 1e-3) / 1e9 / peak},
+            "m2_hamming_stream_kernel": {"bound": "integer ALU (ncu: ALU pipe 81 %)", "algorithmic_GB_per_s": m2_bytes / (match_ms * 1e-3) / 1e9,
+                                         "frac_of_hbm_peak": m2_bytes / (match_ms * 1e-3) / 1e9 / peak,
+                                         "pair_distances_per_s": m2_pairs * float(NFEATURES) * NFEATURES / (match_ms * 1e-3)},
+            "k2_octree_kernel": {"bound": "latency (one CTA per image-level, serial passes)", "ms": k_ms[1]}}
         cpu = None
         if not args.no_cpu_baseline:
             cores = usable_cores()

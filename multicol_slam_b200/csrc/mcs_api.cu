@@ -641,9 +641,20 @@ int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams
     const int dpitch = (width + 63) & ~63;
     // Software pipeline over chunks of frames: H2D (copy stream) | re-pitch + K1..K3 + matching (compute stream) |
     // D2H (output stream).  The chunk inputs are copied linearly and re-pitched on the device.
-    const int n_chunks = std::min(std::max(n_frames / 8, 1), 4);       // >= 8 frames per chunk keeps every kernel above one wave
-    const int fpc = (n_frames + n_chunks - 1) / n_chunks;             // frames per chunk
-    const int ipc = fpc * n_cams;                                     // images per chunk
+    // Chunk plan: at most 4 chunks of >= 8 frames (every kernel stays above one wave); with >= 32 frames the first chunk is
+    // a short one (1/16 of the stream) so that the un-overlapped head -- its H2D copy -- is short too.
+    std::vector<int> chunk_lo;                                        // first frame of every chunk, + n_frames
+    if (n_frames >= 32) {
+        const int first = std::max(4, n_frames / 16), rest = n_frames - first, each = (rest + 2) / 3;
+        chunk_lo = {0, first, std::min(first + each, n_frames), std::min(first + 2 * each, n_frames), n_frames};
+    } else {
+        const int nc = std::min(std::max(n_frames / 8, 1), 4), each = (n_frames + nc - 1) / nc;
+        for (int c = 0; c <= nc; ++c) chunk_lo.push_back(std::min(c * each, n_frames));
+    }
+    const int n_chunks = (int)chunk_lo.size() - 1;
+    int fpc = 0;
+    for (int c = 0; c < n_chunks; ++c) fpc = std::max(fpc, chunk_lo[c + 1] - chunk_lo[c]);
+    const int ipc = fpc * n_cams;                                     // images in the largest chunk
     const size_t tight_img = (size_t)stride * height, pitched_img = (size_t)dpitch * height;
     std::vector<int> coi(n_images);
     for (int i = 0; i < n_images; ++i) coi[i] = i % n_cams;
@@ -655,17 +666,18 @@ int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams
     CK(ex->counts.ensure(n_images));
     CK(ex->match_idx.ensure((size_t)n_images * capacity * K));
     CK(ex->match_dist.ensure((size_t)n_images * capacity * K));
-    std::vector<cudaEvent_t> ev_in(n_chunks), ev_free(n_chunks), ev_done(n_chunks);
+    std::vector<cudaEvent_t> ev_in(n_chunks), ev_free(n_chunks), ev_feat(n_chunks), ev_done(n_chunks);
     for (int c = 0; c < n_chunks; ++c) {
         CK(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ev_free[c], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_feat[c], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
     }
     int rc = MCS_OK;
     const uint8_t* dmask_for_match = ex->p.learn_masks ? ex->dmask.p : nullptr;
     for (int c = 0; c < n_chunks && rc == MCS_OK; ++c) {
-        const int img_lo = c * ipc, nimg = std::min(ipc, n_images - img_lo);
-        if (nimg <= 0) break;
+        const int img_lo = chunk_lo[c] * n_cams, nimg = (chunk_lo[c + 1] - chunk_lo[c]) * n_cams;
+        if (nimg <= 0) continue;
         uint8_t* tight = ex->in_tight.p + (size_t)(c & 1) * tight_img * ipc;
         if (c >= 2) CK(cudaStreamWaitEvent(ex->s_copy, ev_free[c - 2], 0));          // staging buffer consumed
         CK(cudaMemcpyAsync(tight, images + (size_t)img_lo * tight_img, tight_img * nimg, cudaMemcpyHostToDevice, ex->s_copy));
@@ -677,11 +689,12 @@ int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams
                           ex->kps.p + (size_t)img_lo * capacity, ex->desc.p + (size_t)img_lo * capacity * ds,
                           ex->dmask.p + (size_t)img_lo * capacity * ds, ex->counts.p + img_lo, capacity, st, c == 0);
         if (rc) break;
+        CK(cudaEventRecord(ev_feat[c], st));                              // features of the chunk are final: their D2H overlaps the matching
         CK(launch_hamming_stream(ex->desc.p, dmask_for_match, ex->counts.p, img_lo, nimg, n_cams, capacity, ds, K, ex->match_idx.p,
                                  ex->match_dist.p, st));
         CK(cudaEventRecord(ev_done[c], st));
-        CK(cudaStreamWaitEvent(ex->s_out, ev_done[c], 0));
         cudaStream_t so = ex->s_out;
+        CK(cudaStreamWaitEvent(so, ev_feat[c], 0));
         CK(cudaMemcpyAsync(counts_out + img_lo, ex->counts.p + img_lo, sizeof(int) * nimg, cudaMemcpyDeviceToHost, so));
         CK(cudaMemcpyAsync(kps_out + (size_t)img_lo * capacity, ex->kps.p + (size_t)img_lo * capacity,
                            sizeof(mcs_keypoint) * (size_t)nimg * capacity, cudaMemcpyDeviceToHost, so));
@@ -690,16 +703,17 @@ int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams
         if (dmask_out)
             CK(cudaMemcpyAsync(dmask_out + (size_t)img_lo * capacity * ds, ex->dmask.p + (size_t)img_lo * capacity * ds,
                                (size_t)nimg * capacity * ds, cudaMemcpyDeviceToHost, so));
+        CK(cudaStreamWaitEvent(so, ev_done[c], 0));
         CK(cudaMemcpyAsync(match_idx_out + (size_t)img_lo * capacity * K, ex->match_idx.p + (size_t)img_lo * capacity * K,
                            sizeof(int) * (size_t)nimg * capacity * K, cudaMemcpyDeviceToHost, so));
         CK(cudaMemcpyAsync(match_dist_out + (size_t)img_lo * capacity * K, ex->match_dist.p + (size_t)img_lo * capacity * K,
                            sizeof(int) * (size_t)nimg * capacity * K, cudaMemcpyDeviceToHost, so));
     }
     cudaError_t e1 = cudaStreamSynchronize(ex->s_copy), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(ex->s_out);
-    for (int c = 0; c < n_chunks; ++c) { cudaEventDestroy(ev_in[c]); cudaEventDestroy(ev_free[c]); cudaEventDestroy(ev_done[c]); }
+    for (int c = 0; c < n_chunks; ++c) { cudaEventDestroy(ev_in[c]); cudaEventDestroy(ev_free[c]); cudaEventDestroy(ev_feat[c]); cudaEventDestroy(ev_done[c]); }
     if (rc) return rc;
     CK(e1); CK(e2); CK(e3);
-    ex->last_n_images = std::min(ipc, n_images - (n_chunks - 1) * ipc);
+    ex->last_n_images = (chunk_lo[n_chunks] - chunk_lo[n_chunks - 1]) * n_cams;
     return check_status(ex, st);
 }
 
