@@ -23,7 +23,7 @@ constexpr unsigned long long kNoKey = 0xFFFFFFFFFFFFFFFFull;
 // ---- bit-sliced population count (Harley-Seal carry-save adders) -------------------------------------------------
 // POPC issues on the XU pipe of sm_100 at 16 lanes/clk/SM (4x slower than LOP3), which makes a plain popcount loop
 // the bottleneck of brute-force Hamming.  A carry-save adder (2 LOP3) turns three words into a "ones" and a "twos"
-// word; reducing 16 (8) words this way needs 5 (4) POPC instead of 16 (8).
+// word; reducing 16 (8) words this way needs 9 (4) POPC instead of 16 (8).
 // (a ^ b) & c in one LOP3 (immLut = (0xF0 ^ 0xCC) & 0xAA); the compiler otherwise keeps the shared xor separate
 __device__ __forceinline__ uint32_t xor_and(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t d;
@@ -42,20 +42,21 @@ __device__ __forceinline__ unsigned popc_sum8(const uint32_t (&w)[8]) {
     csa(c0, c1, c2, t0, d0);
     return __popc(s2) + __popc(w[7]) + 2 * __popc(t0) + 4 * __popc(d0);
 }
+// 16 words (masked distance): two carry-save levels on the ones, none on the twos -- 14 LOP3 + 9 POPC.  ALU (LOP3/IADD, 64 lanes/clk/SM)
+// and XU (POPC, 16 lanes/clk/SM) run concurrently, so the cheapest split loads both about equally; measured on the stream
+// matcher (381 x 2000 x 2000 masked pairs): full tree 22 LOP3 + 5 POPC 4.62 ms, one level 10 + 11 4.33 ms, this one 4.08 ms.
 __device__ __forceinline__ unsigned popc_sum16(const uint32_t (&w)[16]) {
-    uint32_t s0, c0, s1, c1, s2, c2, s3, c3, s4, c4, s5, c5, s6, c6, t0, d0, t1, d1, t2, d2, f0, e0;
+    uint32_t s0, c0, s1, c1, s2, c2, s3, c3, s4, c4, a0, b0, a1, b1;
     csa(w[0], w[1], w[2], s0, c0);
     csa(w[3], w[4], w[5], s1, c1);
     csa(w[6], w[7], w[8], s2, c2);
     csa(w[9], w[10], w[11], s3, c3);
     csa(w[12], w[13], w[14], s4, c4);
-    csa(s0, s1, s2, s5, c5);
-    csa(s3, s4, w[15], s6, c6);
-    csa(c0, c1, c2, t0, d0);
-    csa(c3, c4, c5, t1, d1);
-    csa(t0, t1, c6, t2, d2);
-    csa(d0, d1, d2, f0, e0);
-    return __popc(s5) + __popc(s6) + 2 * __popc(t2) + 4 * __popc(f0) + 8 * __popc(e0);
+    csa(s0, s1, s2, a0, b0);
+    csa(s3, s4, w[15], a1, b1);
+    const unsigned ones = __popc(a0) + __popc(a1);
+    const unsigned twos = __popc(c0) + __popc(c1) + __popc(c2) + __popc(c3) + __popc(c4) + __popc(b0) + __popc(b1);
+    return ones + 2 * twos;
 }
 // sum over k of popc(x_k) [unmasked] or popc(x_k & qm_k) + popc(x_k & dm_k) [masked, before the /2], x_k = q_k ^ d_k
 template <int WORDS, bool MASKED>

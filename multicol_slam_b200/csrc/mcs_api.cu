@@ -87,7 +87,8 @@ struct mcs_extractor {
     DevBuf<uint8_t> lvl[kMaxLevels], blur[kMaxLevels];
     DevBuf<uint8_t> masks;
     DevBuf<mcs_ocam> cams;
-    DevBuf<int> cam_of_image;
+    DevBuf<int> cam_of_image, coi_all;
+    const int* coi_last = nullptr;      // camera-of-image table the last run used (device)
     DevBuf<uint32_t> raw;
     DevBuf<uint16_t> node_of;
     DevBuf<int> raw_count, sel_count, status, counts;
@@ -100,6 +101,7 @@ struct mcs_extractor {
     cudaStream_t s_copy = nullptr, s_out = nullptr;
     // distortion tables, rebuilt when the camera set changes
     std::vector<mcs_ocam> lut_cams;
+    std::vector<uint8_t> masks_host;    // what ex->masks holds
     DevBuf<double> lut_coef;
     DevBuf<DistortLut> luts;
     bool profiling = false;
@@ -241,10 +243,50 @@ int ensure_batch(mcs_extractor* ex, int B) {
     return MCS_OK;
 }
 
+// Small per-call host inputs (masks, camera models, distortion tables, status word).  They travel over the same
+// H2D copy engine as the image chunks of the stream call, so they must be enqueued BEFORE any large copy: a 1 MB
+// mask upload queued behind 100 MB of images stalls the compute stream for the whole transfer (measured: +5 ms).
+int upload_small_inputs(mcs_extractor* ex, int W, int H, const uint8_t* masks, const mcs_ocam* cams, int n_cams, cudaStream_t st) {
+    CK(ex->masks.ensure((size_t)n_cams * W * H));
+    CK(ex->cams.ensure(n_cams));
+    // the masks rarely change between calls (static mirror masks): a 1 MB compare is cheaper than a pageable upload
+    const size_t mbytes = (size_t)n_cams * W * H;
+    if (ex->masks_host.size() != mbytes || std::memcmp(ex->masks_host.data(), masks, mbytes) != 0) {
+        CK(cudaStreamSynchronize(st));                     // a previous call may still read the old masks
+        ex->masks_host.assign(masks, masks + mbytes);
+        CK(cudaMemcpyAsync(ex->masks.p, ex->masks_host.data(), mbytes, cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemcpyAsync(ex->cams.p, cams, sizeof(mcs_ocam) * n_cams, cudaMemcpyHostToDevice, st));
+    if ((ex->p.do_dbrief || ex->p.learn_masks) &&
+        ((int)ex->lut_cams.size() != n_cams || std::memcmp(ex->lut_cams.data(), cams, sizeof(mcs_ocam) * n_cams) != 0)) {
+        std::vector<double> all;
+        std::vector<size_t> offs(n_cams);
+        std::vector<int> ns(n_cams);
+        for (int c = 0; c < n_cams; ++c) {
+            std::vector<double> coef;
+            build_distort_lut(cams[c], coef, ns[c]);
+            offs[c] = all.size();
+            all.insert(all.end(), coef.begin(), coef.end());
+        }
+        CK(cudaStreamSynchronize(st));                 // a previous call may still read the old tables
+        CK(ex->lut_coef.ensure(all.size()));
+        CK(ex->luts.ensure(n_cams));
+        std::vector<DistortLut> h(n_cams);
+        for (int c = 0; c < n_cams; ++c) h[c] = DistortLut{ex->lut_coef.p + offs[c], ns[c], 1.0};
+        CK(cudaMemcpyAsync(ex->lut_coef.p, all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ex->luts.p, h.data(), sizeof(DistortLut) * n_cams, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));                 // host staging vectors die here
+        ex->lut_cams.assign(cams, cams + n_cams);
+    }
+    CK(cudaMemsetAsync(ex->status.p, 0, sizeof(int), st));
+
+    return MCS_OK;
+}
+
 int run_pipeline(mcs_extractor* ex, int n_images, const uint8_t* images_dev, int W, int H, int stride,
                  const uint8_t* masks, const mcs_ocam* cams, int n_cams, const int* cam_of_image,
                  mcs_keypoint* kps_dev, uint8_t* desc_dev, uint8_t* dmask_dev, int* counts_dev, int capacity,
-                 cudaStream_t st, bool first_chunk = true) {
+                 cudaStream_t st, bool first_chunk = true, const int* coi_dev = nullptr) {
     if (n_cams < 1 || n_cams > 64) return fail(MCS_ERR_INVALID, "n_cams must be in [1,64]");
     for (int i = 0; i < n_images; ++i)
         if (cam_of_image[i] < 0 || cam_of_image[i] >= n_cams) return fail(MCS_ERR_INVALID, "cam_of_image out of range");
@@ -254,42 +296,22 @@ int run_pipeline(mcs_extractor* ex, int n_images, const uint8_t* images_dev, int
     if (rc) return rc;
     const PyramidGeom& G = ex->G;
     if (first_chunk) {
-    // small per-call host inputs
-        CK(ex->masks.ensure((size_t)n_cams * W * H));
-        CK(ex->cams.ensure(n_cams));
-        CK(cudaMemcpyAsync(ex->masks.p, masks, (size_t)n_cams * W * H, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ex->cams.p, cams, sizeof(mcs_ocam) * n_cams, cudaMemcpyHostToDevice, st));
-        if ((ex->p.do_dbrief || ex->p.learn_masks) &&
-            ((int)ex->lut_cams.size() != n_cams || std::memcmp(ex->lut_cams.data(), cams, sizeof(mcs_ocam) * n_cams) != 0)) {
-            std::vector<double> all;
-            std::vector<size_t> offs(n_cams);
-            std::vector<int> ns(n_cams);
-            for (int c = 0; c < n_cams; ++c) {
-                std::vector<double> coef;
-                build_distort_lut(cams[c], coef, ns[c]);
-                offs[c] = all.size();
-                all.insert(all.end(), coef.begin(), coef.end());
-            }
-            CK(cudaStreamSynchronize(st));                 // a previous call may still read the old tables
-            CK(ex->lut_coef.ensure(all.size()));
-            CK(ex->luts.ensure(n_cams));
-            std::vector<DistortLut> h(n_cams);
-            for (int c = 0; c < n_cams; ++c) h[c] = DistortLut{ex->lut_coef.p + offs[c], ns[c], 1.0};
-            CK(cudaMemcpyAsync(ex->lut_coef.p, all.data(), all.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-            CK(cudaMemcpyAsync(ex->luts.p, h.data(), sizeof(DistortLut) * n_cams, cudaMemcpyHostToDevice, st));
-            CK(cudaStreamSynchronize(st));                 // host staging vectors die here
-            ex->lut_cams.assign(cams, cams + n_cams);
-        }
-        CK(cudaMemsetAsync(ex->status.p, 0, sizeof(int), st));
+        rc = upload_small_inputs(ex, W, H, masks, cams, n_cams, st);
+        if (rc) return rc;
     }
-    CK(cudaMemcpyAsync(ex->cam_of_image.p, cam_of_image, sizeof(int) * n_images, cudaMemcpyHostToDevice, st));
+    const int* coi_d = coi_dev;
+    if (!coi_d) {
+        CK(cudaMemcpyAsync(ex->cam_of_image.p, cam_of_image, sizeof(int) * n_images, cudaMemcpyHostToDevice, st));
+        coi_d = ex->cam_of_image.p;
+    }
+    ex->coi_last = coi_d;
     CK(cudaMemsetAsync(ex->raw_count.p, 0, sizeof(int) * n_images * G.nlevels, st));
     if (ex->profiling) CK(cudaEventRecord(ex->ev[0], st));
     for (int l = 0; l < G.nlevels; ++l) {
         const uint8_t* src = l ? ex->lvl[l - 1].p : images_dev;
         const size_t src_bytes = l ? G.lv[l - 1].img_bytes : (size_t)stride * H;
         launch_pyr_fast(G, l, n_images, src, src_bytes, ex->lvl[l].p, ex->blur[l].p, ex->masks.p, W, (size_t)W * H,
-                        ex->cam_of_image.p, ex->raw.p, ex->raw_count.p, st);
+                        coi_d, ex->raw.p, ex->raw_count.p, st);
     }
     CK(cudaGetLastError());
     if (ex->profiling) CK(cudaEventRecord(ex->ev[1], st));
@@ -299,7 +321,7 @@ int run_pipeline(mcs_extractor* ex, int n_images, const uint8_t* images_dev, int
     if (ex->profiling) CK(cudaEventRecord(ex->ev[2], st));
     DescribeArgs a;
     for (int l = 0; l < kMaxLevels; ++l) { a.lvl[l] = ex->lvl[l].p; a.blur[l] = ex->blur[l].p; }
-    CK(launch_describe(G, ex->G_dev.p, n_images, a, ex->cams.p, ex->luts.p, ex->cam_of_image.p, ex->sel_xys.p, ex->sel_count.p,
+    CK(launch_describe(G, ex->G_dev.p, n_images, a, ex->cams.p, ex->luts.p, coi_d, ex->sel_xys.p, ex->sel_count.p,
                        kps_dev, desc_dev, dmask_dev, counts_dev, capacity, st));
     if (ex->profiling) CK(cudaEventRecord(ex->ev[3], st));
     ex->last_n_images = n_images;
@@ -449,7 +471,7 @@ void mcs_extractor_destroy(mcs_extractor* ex) {
     cudaSetDevice(ex->device);
     ex->lut_blob.release(); ex->G_dev.release(); ex->in_images.release();
     for (int l = 0; l < kMaxLevels; ++l) { ex->lvl[l].release(); ex->blur[l].release(); }
-    ex->masks.release(); ex->cams.release(); ex->cam_of_image.release(); ex->raw.release(); ex->node_of.release();
+    ex->masks.release(); ex->cams.release(); ex->cam_of_image.release(); ex->coi_all.release(); ex->raw.release(); ex->node_of.release();
     ex->raw_count.release(); ex->sel_count.release(); ex->status.release(); ex->counts.release(); ex->sel_xys.release();
     ex->kps.release(); ex->desc.release(); ex->dmask.release();
     ex->match_idx.release(); ex->match_dist.release(); ex->lut_coef.release(); ex->luts.release();
@@ -568,7 +590,7 @@ int mcs_extractor_debug_read(mcs_extractor* ex, int32_t image_index, int32_t lev
         std::vector<int> coi(ex->last_n_images);
         CK(cudaMemcpy(mx.data(), g.mx0, g.w * 2, cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(my.data(), g.my0, g.h * 2, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(coi.data(), ex->cam_of_image.p, sizeof(int) * ex->last_n_images, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(coi.data(), ex->coi_last, sizeof(int) * ex->last_n_images, cudaMemcpyDeviceToHost));
         std::vector<uint8_t> m0((size_t)ex->G.width * ex->G.height);
         CK(cudaMemcpy(m0.data(), ex->masks.p + (size_t)coi[image_index] * m0.size(), m0.size(), cudaMemcpyDeviceToHost));
         for (int y = 0; y < g.h; ++y)
@@ -651,6 +673,16 @@ int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams
         const int nc = std::min(std::max(n_frames / 8, 1), 4), each = (n_frames + nc - 1) / nc;
         for (int c = 0; c <= nc; ++c) chunk_lo.push_back(std::min(c * each, n_frames));
     }
+    if (const char* plan = getenv("MCS_STREAM_CHUNKS")) {               // experiment knob: comma-separated frames per chunk
+        std::vector<int> lo(1, 0);
+        for (const char* q = plan; *q && lo.back() < n_frames;) {
+            lo.push_back(std::min(n_frames, lo.back() + std::max(1, atoi(q))));
+            while (*q && *q != ',') ++q;
+            if (*q == ',') ++q;
+        }
+        if (lo.back() < n_frames) lo.push_back(n_frames);
+        chunk_lo = lo;
+    }
     const int n_chunks = (int)chunk_lo.size() - 1;
     int fpc = 0;
     for (int c = 0; c < n_chunks; ++c) fpc = std::max(fpc, chunk_lo[c + 1] - chunk_lo[c]);
@@ -673,25 +705,39 @@ int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams
         CK(cudaEventCreateWithFlags(&ev_feat[c], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
     }
-    int rc = MCS_OK;
+    int rc = build_geometry(ex, width, height, dpitch);
+    if (rc == MCS_OK) rc = ensure_batch(ex, ipc);
+    if (rc == MCS_OK) rc = upload_small_inputs(ex, width, height, masks, cams, n_cams, st);     // before the first image copy, see there
+    if (rc) return rc;
+    CK(ex->coi_all.ensure(n_images));
+    CK(cudaMemcpyAsync(ex->coi_all.p, coi.data(), sizeof(int) * n_images, cudaMemcpyHostToDevice, st));
     const uint8_t* dmask_for_match = ex->p.learn_masks ? ex->dmask.p : nullptr;
+    // MCS_TRACE_STREAM=1: per-chunk timeline on stderr (H2D begin/end, compute begin/features/end, D2H end), ms from the first H2D
+    static const bool trace = getenv("MCS_TRACE_STREAM") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t s_) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s_); tev.push_back(e); } };
     for (int c = 0; c < n_chunks && rc == MCS_OK; ++c) {
         const int img_lo = chunk_lo[c] * n_cams, nimg = (chunk_lo[c + 1] - chunk_lo[c]) * n_cams;
         if (nimg <= 0) continue;
         uint8_t* tight = ex->in_tight.p + (size_t)(c & 1) * tight_img * ipc;
         if (c >= 2) CK(cudaStreamWaitEvent(ex->s_copy, ev_free[c - 2], 0));          // staging buffer consumed
+        mark(ex->s_copy);
         CK(cudaMemcpyAsync(tight, images + (size_t)img_lo * tight_img, tight_img * nimg, cudaMemcpyHostToDevice, ex->s_copy));
+        mark(ex->s_copy);
         CK(cudaEventRecord(ev_in[c], ex->s_copy));
         CK(cudaStreamWaitEvent(st, ev_in[c], 0));
+        mark(st);
         launch_repitch(tight, stride, ex->in_images.p, dpitch, width, (size_t)height * nimg, st);
         CK(cudaEventRecord(ev_free[c], st));
         rc = run_pipeline(ex, nimg, ex->in_images.p, width, height, dpitch, masks, cams, n_cams, coi.data() + img_lo,
                           ex->kps.p + (size_t)img_lo * capacity, ex->desc.p + (size_t)img_lo * capacity * ds,
-                          ex->dmask.p + (size_t)img_lo * capacity * ds, ex->counts.p + img_lo, capacity, st, c == 0);
+                          ex->dmask.p + (size_t)img_lo * capacity * ds, ex->counts.p + img_lo, capacity, st, false, ex->coi_all.p + img_lo);
         if (rc) break;
+        mark(st);
         CK(cudaEventRecord(ev_feat[c], st));                              // features of the chunk are final: their D2H overlaps the matching
         CK(launch_hamming_stream(ex->desc.p, dmask_for_match, ex->counts.p, img_lo, nimg, n_cams, capacity, ds, K, ex->match_idx.p,
                                  ex->match_dist.p, st));
+        mark(st);
         CK(cudaEventRecord(ev_done[c], st));
         cudaStream_t so = ex->s_out;
         CK(cudaStreamWaitEvent(so, ev_feat[c], 0));
@@ -708,9 +754,19 @@ int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams
                            sizeof(int) * (size_t)nimg * capacity * K, cudaMemcpyDeviceToHost, so));
         CK(cudaMemcpyAsync(match_dist_out + (size_t)img_lo * capacity * K, ex->match_dist.p + (size_t)img_lo * capacity * K,
                            sizeof(int) * (size_t)nimg * capacity * K, cudaMemcpyDeviceToHost, so));
+        mark(so);
     }
     cudaError_t e1 = cudaStreamSynchronize(ex->s_copy), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(ex->s_out);
     for (int c = 0; c < n_chunks; ++c) { cudaEventDestroy(ev_in[c]); cudaEventDestroy(ev_free[c]); cudaEventDestroy(ev_feat[c]); cudaEventDestroy(ev_done[c]); }
+    if (trace && !tev.empty()) {
+        for (size_t i = 0; i + 5 < tev.size() + 0 && i < tev.size(); i += 6) {
+            float t[6];
+            for (int k = 0; k < 6 && i + k < tev.size(); ++k) cudaEventElapsedTime(&t[k], tev[0], tev[i + k]);
+            fprintf(stderr, "[mcs stream] chunk %zu: h2d %.2f-%.2f  compute %.2f  features %.2f  matched %.2f  d2h done %.2f ms\n", i / 6,
+                    t[0], t[1], t[2], t[3], t[4], t[5]);
+        }
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    }
     if (rc) return rc;
     CK(e1); CK(e2); CK(e3);
     ex->last_n_images = (chunk_lo[n_chunks] - chunk_lo[n_chunks - 1]) * n_cams;
