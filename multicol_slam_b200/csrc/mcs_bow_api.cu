@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include "../../include/mcs_b200.h"
 #include "kernels.h"
+#include "dev_scratch.h"
 
 using namespace mcs;
 
@@ -31,12 +32,6 @@ int bfail(int code, const std::string& msg) { mcs_set_error_(msg); return code; 
         }                                                                                              \
     } while (0)
 
-struct Dev {   // RAII device allocation
-    void* p = nullptr;
-    ~Dev() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 16)); }
-    template <typename T> T* as() { return (T*)p; }
-};
 
 }  // namespace
 

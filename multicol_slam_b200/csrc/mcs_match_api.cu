@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "kernels.h"
+#include "dev_scratch.h"
 #include "mcs_common.cuh"
 
 using namespace mcs;
@@ -30,12 +31,6 @@ int mfail(int code, const std::string& msg);   // records the message for mcs_la
         }                                                                                              \
     } while (0)
 
-struct Dev {   // RAII device allocation
-    void* p = nullptr;
-    ~Dev() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 16)); }
-    template <typename T> T* as() { return (T*)p; }
-};
 
 inline int cv_round(double v) { return (int)lrint(v); }
 
