@@ -698,13 +698,26 @@ int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams
     CK(ex->counts.ensure(n_images));
     CK(ex->match_idx.ensure((size_t)n_images * capacity * K));
     CK(ex->match_dist.ensure((size_t)n_images * capacity * K));
-    std::vector<cudaEvent_t> ev_in(n_chunks), ev_free(n_chunks), ev_feat(n_chunks), ev_done(n_chunks);
+    struct Events {                       // destroyed on every path out of this function
+        std::vector<cudaEvent_t> v;
+        ~Events() { for (cudaEvent_t e : v) cudaEventDestroy(e); }
+        cudaError_t add(cudaEvent_t* out, unsigned flags) {
+            cudaError_t e = cudaEventCreateWithFlags(out, flags);
+            if (e == cudaSuccess) v.push_back(*out);
+            return e;
+        }
+    } events;
+    std::vector<cudaEvent_t> ev_in(n_chunks), ev_free(n_chunks), ev_feat(n_chunks), ev_done(n_chunks), tev;
     for (int c = 0; c < n_chunks; ++c) {
-        CK(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ev_free[c], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ev_feat[c], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
+        CK(events.add(&ev_in[c], cudaEventDisableTiming));
+        CK(events.add(&ev_free[c], cudaEventDisableTiming));
+        CK(events.add(&ev_feat[c], cudaEventDisableTiming));
+        CK(events.add(&ev_done[c], cudaEventDisableTiming));
     }
+    static const bool trace = getenv("MCS_TRACE_STREAM") != nullptr;    // per-chunk timeline on stderr
+    // Everything asynchronous happens inside enqueue(); whatever it returns, the three streams are drained before this
+    // function returns, because the copies read caller memory and the local cam-of-image table.
+    auto enqueue = [&]() -> int {
     int rc = build_geometry(ex, width, height, dpitch);
     if (rc == MCS_OK) rc = ensure_batch(ex, ipc);
     if (rc == MCS_OK) rc = upload_small_inputs(ex, width, height, masks, cams, n_cams, st);     // before the first image copy, see there
@@ -713,9 +726,7 @@ int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams
     CK(cudaMemcpyAsync(ex->coi_all.p, coi.data(), sizeof(int) * n_images, cudaMemcpyHostToDevice, st));
     const uint8_t* dmask_for_match = ex->p.learn_masks ? ex->dmask.p : nullptr;
     // MCS_TRACE_STREAM=1: per-chunk timeline on stderr (H2D begin/end, compute begin/features/end, D2H end), ms from the first H2D
-    static const bool trace = getenv("MCS_TRACE_STREAM") != nullptr;
-    std::vector<cudaEvent_t> tev;
-    auto mark = [&](cudaStream_t s_) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s_); tev.push_back(e); } };
+    auto mark = [&](cudaStream_t s_) { if (trace) { cudaEvent_t e; if (events.add(&e, cudaEventDefault) == cudaSuccess) { cudaEventRecord(e, s_); tev.push_back(e); } } };
     for (int c = 0; c < n_chunks && rc == MCS_OK; ++c) {
         const int img_lo = chunk_lo[c] * n_cams, nimg = (chunk_lo[c + 1] - chunk_lo[c]) * n_cams;
         if (nimg <= 0) continue;
@@ -756,16 +767,17 @@ int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams
                            sizeof(int) * (size_t)nimg * capacity * K, cudaMemcpyDeviceToHost, so));
         mark(so);
     }
+    return rc;
+    };
+    const int rc = enqueue();
     cudaError_t e1 = cudaStreamSynchronize(ex->s_copy), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(ex->s_out);
-    for (int c = 0; c < n_chunks; ++c) { cudaEventDestroy(ev_in[c]); cudaEventDestroy(ev_free[c]); cudaEventDestroy(ev_feat[c]); cudaEventDestroy(ev_done[c]); }
     if (trace && !tev.empty()) {
-        for (size_t i = 0; i + 5 < tev.size() + 0 && i < tev.size(); i += 6) {
+        for (size_t i = 0; i + 5 < tev.size(); i += 6) {
             float t[6];
             for (int k = 0; k < 6 && i + k < tev.size(); ++k) cudaEventElapsedTime(&t[k], tev[0], tev[i + k]);
             fprintf(stderr, "[mcs stream] chunk %zu: h2d %.2f-%.2f  compute %.2f  features %.2f  matched %.2f  d2h done %.2f ms\n", i / 6,
                     t[0], t[1], t[2], t[3], t[4], t[5]);
         }
-        for (cudaEvent_t e : tev) cudaEventDestroy(e);
     }
     if (rc) return rc;
     CK(e1); CK(e2); CK(e3);
