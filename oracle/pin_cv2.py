@@ -142,7 +142,51 @@ def pipeline():
                                 raw_crc=np.array([zlib.crc32(oe.debug_read(l, 3).tobytes()) for l in range(8)], np.int64))
 
 
+def pipeline_extra():
+    """More parameter corners of the same pipeline, pyref (real cv2 primitives) vs the C++ oracle: other scale factors
+    (other resize LUTs), level counts, FAST thresholds, feature budgets, descriptor sizes and sensor sizes.  Written as
+    tests/golden/pin_*.npz and checked on CPU only (tests/test_oracle_golden.py::test_pinned_parameter_corners)."""
+    cams = synth.lafida_cams()
+    big = synth.scaled_cam(cams[1], 1280, 720)
+    small = synth.scaled_cam(cams[2], 333, 211)
+    cases = [
+        ("init_th5_nf2000", cams[0], 31, dict(nfeatures=2000, fast_threshold=5, do_dbrief=True, learn_masks=True)),
+        ("sf15_l5_dbrief", cams[1], 32, dict(nfeatures=800, scale_factor=1.5, nlevels=5, do_dbrief=True, learn_masks=False)),
+        ("sf20_l3_orb", cams[2], 33, dict(nfeatures=600, scale_factor=2.0, nlevels=3)),
+        ("sf11_l8_mdbrief", cams[0], 34, dict(nfeatures=500, scale_factor=1.1, nlevels=8, do_dbrief=True, learn_masks=True)),
+        ("desc16_mdbrief", cams[1], 35, dict(nfeatures=400, do_dbrief=True, learn_masks=True, desc_size=16)),
+        ("desc64_dbrief", cams[2], 36, dict(nfeatures=300, do_dbrief=True, learn_masks=False, desc_size=64)),
+        ("1280x720_mdbrief", big, 37, dict(nfeatures=1200, do_dbrief=True, learn_masks=True)),
+        ("333x211_l4_th40_orb", small, 38, dict(nfeatures=300, nlevels=4, fast_threshold=40)),
+    ]
+    for name, cam, seed, kw in cases:
+        img = synth.frame(cam, seed)
+        mask = synth.mirror_mask(cam)
+        pc = pyref.Cam(cam["c"], cam["d"], cam["e"], cam["u0"], cam["v0"], cam["pol"], cam["inv_pol"], cam["width"],
+                       cam["height"], cam["mirror_mask"])
+        pe = pyref.Extractor(**kw)
+        r = pe(img, mask, pc)
+        oe = oa.OracleExtractor(**kw)
+        k, d, m = oe.extract(img, mask, cam)
+        L = pe.nlevels
+        ok = kps_equal(r["kps"], k) and np.array_equal(r["desc"], d) and (not kw.get("learn_masks") or np.array_equal(r["dmask"], m))
+        for l in range(L):
+            ok = ok and np.array_equal(r["pyr"][l], oe.debug_read(l, 0)) and np.array_equal(r["blur"][l], oe.debug_read(l, 1))
+            raw = np.array([[int(a[0]) + 22, int(a[1]) + 22, int(a[2])] for a in r["raws"][l]], np.int32).reshape(-1, 3)
+            ok = ok and np.array_equal(raw, oe.debug_read(l, 3))
+        check(f"extra {name}: {len(k)} keypoints, all stages", ok)
+        np.savez_compressed(GOLD / f"pin_{name}.npz", seed=np.int64(seed), nlevels=np.int64(L),
+                            cam_json=np.frombuffer(__import__("json").dumps(cam).encode(), np.uint8),
+                            params_json=np.frombuffer(__import__("json").dumps(kw).encode(), np.uint8),
+                            kps=k, desc=d, dmask=m, image_crc=np.int64(zlib.crc32(img.tobytes())),
+                            level_crc=np.array([zlib.crc32(oe.debug_read(l, 0).tobytes()) for l in range(L)], np.int64),
+                            blur_crc=np.array([zlib.crc32(oe.debug_read(l, 1).tobytes()) for l in range(L)], np.int64),
+                            raw_crc=np.array([zlib.crc32(oe.debug_read(l, 3).tobytes()) for l in range(L)], np.int64))
+
+
 if __name__ == "__main__":
-    primitives()
-    pipeline()
+    if "--extra-only" not in sys.argv:
+        primitives()
+        pipeline()
+    pipeline_extra()
     print("all pinned")
