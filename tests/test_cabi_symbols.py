@@ -71,3 +71,33 @@ def test_no_cpu_fallback(api):
     q = np.zeros((4, 32), np.uint8)
     with pytest.raises(api.McsError):
         api.hamming_topk(q, q, 2)
+
+
+def test_bow_validation_and_no_cpu_fallback(api):
+    """Vocabulary arguments are validated on the host before any device work; without a device the bag-of-words entry
+    points fail with MCS_ERR_NO_DEVICE like the rest of the library (no CPU path)."""
+    import pathlib
+    voc = np.load(pathlib.Path(__file__).resolve().parent / "golden" / "voc_small_9_6.npz")
+    bad = {k: voc[k].copy() for k in voc.files}
+    bad["parent"][7] = 7                                   # a node that is its own parent
+    with pytest.raises(api.McsError) as e:
+        api.ORBVocabulary(bad)
+    assert e.value.code == api.MCS_ERR_INVALID
+    bad = {k: voc[k].copy() for k in voc.files}
+    bad["word_node"][3] = 1                                # word id attached to an inner node
+    with pytest.raises(api.McsError) as e:
+        api.ORBVocabulary(bad)
+    assert e.value.code == api.MCS_ERR_INVALID
+    with pytest.raises(api.McsError) as e:
+        api.ORBVocabulary(voc, scoring=9)
+    assert e.value.code == api.MCS_ERR_INVALID
+    if api.device_count() > 0:
+        return
+    with pytest.raises(api.McsError) as e:
+        api.ORBVocabulary(voc)
+    assert e.value.code == api.MCS_ERR_NO_DEVICE
+    d = np.zeros((8, 32), np.uint8)
+    fv = (np.array([1], np.int32), np.array([0, 8], np.int32), np.arange(8, dtype=np.int32))
+    with pytest.raises(api.McsError) as e:
+        api.cORBmatcher(0.9, False, 32, False).SearchByBoWFrame(d, fv, d, fv)
+    assert e.value.code == api.MCS_ERR_NO_DEVICE
