@@ -6,7 +6,7 @@ TemplatedVocabulary::save, ThirdParty/DBoW2/DBoW2/TemplatedVocabulary.h:1476-156
                                    how the compiled reference (oracle/_ref/libdbow2_ref.so) loads it without cv::FileStorage
 
 Data only, no code is copied.  Run in the authoring container (needs /root/reference):
-    python tools/extract_vocabulary.py [--txt oracle/_ref/voc_small_9_6.txt]
+    python tools/extract_vocabulary.py [--npz] [--txt oracle/_ref/voc_small_9_6.txt]
 """
 import argparse, pathlib, re
 import numpy as np
@@ -62,6 +62,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--yml", default="/root/reference/Examples/small_orb_omni_voc_9_6.yml")
     ap.add_argument("--txt", default=None)
+    ap.add_argument("--npz", action="store_true", help="(re)write tests/golden/voc_small_9_6.npz; without it only a missing file is written")
     a = ap.parse_args()
     head, nodes, words = parse_yaml(a.yml)
     v = flatten(head, nodes, words)
@@ -78,8 +79,12 @@ def main():
     print("nodes %d  words %d  k %d  L %d  scoring %d  weighting %d" % (n, len(v["word_node"]), v["k"], v["L"], v["scoring"], v["weighting"]))
     print("leaf depth histogram", np.bincount(d[is_leaf]), " max children", np.bincount(v["parent"][1:]).max())
     out = ROOT / "tests" / "golden" / "voc_small_9_6.npz"
-    np.savez_compressed(out, **v)
-    print("wrote", out, out.stat().st_size, "bytes")
+    if a.npz or not out.exists():
+        np.savez_compressed(out, **v)
+        print("wrote", out, out.stat().st_size, "bytes")
+    else:
+        old = np.load(out)
+        assert all(np.array_equal(old[k], v[k]) for k in v), "committed fixture differs from the reference's vocabulary file"
     if a.txt:
         write_text(v, a.txt); print("wrote", a.txt)
 
