@@ -66,6 +66,12 @@ constexpr int kDescWarps = 4;
 constexpr int kPatchR = 25;                       // staged patch: rows/cols ky/kx -25 .. +25 (keypoints are >= 25 px inside the ROI)
 constexpr int kPatchS = 64;                       // bytes per staged patch row (4-byte aligned start + 51 columns)
 constexpr int kLutDeg = 9;                        // degree of the per-centre polynomial of R(r)  (kernels.h: DistortLut)
+#ifndef MCS_K3_HALVES
+#define MCS_K3_HALVES 0
+#endif
+#ifndef MCS_K3_MINB
+#define MCS_K3_MINB 4                // resident CTAs per SM the register budget is cut for (128 registers)
+#endif
 constexpr int kLutStride = 12;                    // doubles per centre: tau offset, tau scale, kLutDeg + 1 coefficients
 constexpr double kLutReach = 22.5;                // half-width of a centre's interval: pattern radius 15*sqrt(2) + 0.5 + margin
 
@@ -128,7 +134,7 @@ __device__ __noinline__ unsigned orb_pattern_global(const char2* s_pat, double c
     return out;
 }
 
-template <int PPL /* pattern points per lane: 16 for descSize <= 32, 32 for descSize 64 */, int MINB = 4>
+template <int PPL /* pattern points per lane: 16 for descSize <= 32, 32 for descSize 64 */, int MINB = MCS_K3_MINB>
 __global__ void __launch_bounds__(kDescWarps * 32, MINB)
 describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, const mcs_ocam* __restrict__ cams,
                 const DistortLut* __restrict__ luts, const int* __restrict__ cam_of_image,
@@ -138,6 +144,9 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
     __shared__ char2 s_pat[PPL * 32];            // [j][lane] : point 16*byte + k with byte = lane + 32*(j/16), k = j%16
     __shared__ __align__(16) double2 s_patd[PPL * 32];   // same, as doubles (int->double conversions run on the slow XU pipe)
     __shared__ mcs_ocam s_cam[kDescWarps];
+#if MCS_K3_HALVES
+    __shared__ int2 s_park[kDescWarps][PPL == 16 ? PPL * 32 : 1];    // projected coordinates of the current pattern, [point][lane]
+#endif
     __shared__ __align__(16) uint8_t s_patch[kDescWarps][(2 * kPatchR + 1) * kPatchS];
     const int ds = geom->desc_size;
     for (int i = threadIdx.x; i < PPL * 32; i += blockDim.x) {
@@ -306,6 +315,97 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
         const double inv_n = 1.0 / (double)(16 * ds);
         const bool lane_valid = (PPL == 32) || (lane < ds);      // descSize 16: lanes 16..31 own no byte
         for (int q = 0; q < npat; ++q) {
+#if MCS_K3_HALVES
+            if constexpr (PPL == 16) {
+            // Variant (compile-time, not the default): the 16 (32) points of a lane are processed in groups of 8.
+            // Pass 1 projects a group and parks its coordinates -- relative to the keypoint's own pixel, as 24-bit fixed point: the
+            // low word of (x + 1.5*2^28) is rn(x * 2^24) for |x| < 128 -- in shared memory; pass 2 reads them back, subtracts the
+            // mean, rounds, and does the bit tests of the group.  Live set and code size are half of the unrolled 16-point form.
+            // Error budget: two roundings of 2^-25 px + polynomial (< 2e-8) << the 4.8e-7 px tie guard (16 units below).
+            constexpr double kMagicF = 402653184.0;
+            constexpr int GRP = 8;
+            int2* park = s_park[wib];
+            double su = 0.0, sv = 0.0;
+            bool need_exact = false;
+            int worst_tau = 0, worst_rng = 0;          // high words of max |tau| and of max |relative coordinate|
+            const double du0 = cam.u0 - (double)__fmul_rn((float)kx, scale), dv0 = cam.v0 - (double)__fmul_rn((float)ky, scale);
+#pragma unroll 1
+            for (int g0 = 0; g0 < PPL; g0 += GRP) {
+#pragma unroll
+                for (int jj = 0; jj < GRP; ++jj) {
+                    const int j = g0 + jj;
+                    const double2 pp = s_patd[j * 32 + lane];
+                    const double xr = fma(pp.x, ca[q], fma(-pp.y, sa[q], ukx));
+                    const double yr = fma(pp.x, sa[q], fma(pp.y, ca[q], uky));
+                    const double s2 = fma(xr, xr, yr * yr);
+                    double y0;
+                    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(s2));
+                    const double e = fma(-(s2 * y0), y0, 1.0);
+                    const double rinv = fma(y0 * e, fma(0.375, e, 0.5), y0), r = s2 * rinv;
+                    const double tau = fma(r, t_scale, t_off);
+                    double gg = P[kLutDeg];
+#pragma unroll
+                    for (int k = kLutDeg - 1; k >= 0; --k) gg = fma(gg, tau, P[k]);
+                    worst_tau = max(worst_tau, __double2hiint(tau) & 0x7fffffff);
+                    gg *= rinv;
+                    const double uu = xr * gg, vv = yr * gg;
+                    const double ur = fma(uu, cam.c, fma(vv, cam.d, du0));
+                    const double vr = fma(uu, cam.e, vv + dv0);
+                    if (lane_valid) { su += ur; sv += vr; }
+                    worst_rng = max(worst_rng, max(__double2hiint(ur) & 0x7fffffff, __double2hiint(vr) & 0x7fffffff));
+                    park[j * 32 + lane] = make_int2(__double2loint(ur + kMagicF), __double2loint(vr + kMagicF));
+                }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                su += __shfl_xor_sync(0xffffffffu, su, o);
+                sv += __shfl_xor_sync(0xffffffffu, sv, o);
+            }
+            // every |ur|, |vr| < 32 (checked below) -> |mean| < 32: the differences below stay far inside 32 bits.
+            // t = (x - mean) * 2^24 + 2^23 + 8: t >> 24 is rn(x - mean) unless the low 24 bits are < 16, i.e. x - mean lies
+            // within 8 * 2^-24 = 4.8e-7 px of a rounding tie (then the exact path decides).
+            const int cu = __double2loint(su * inv_n + kMagicF) - ((1 << 23) + 8), cv = __double2loint(sv * inv_n + kMagicF) - ((1 << 23) + 8);
+            unsigned worst_tie = 0xFFFFFFFFu, worst_ofs = 0;
+            unsigned bits[BPL];
+#pragma unroll
+            for (int bb = 0; bb < BPL; ++bb) bits[bb] = 0;
+#pragma unroll 1
+            for (int g0 = 0; g0 < PPL; g0 += GRP) {
+                int ix[GRP], iy[GRP];
+#pragma unroll
+                for (int jj = 0; jj < GRP; ++jj) {
+                    const int2 f = park[(g0 + jj) * 32 + lane];     // this lane's own slot: no synchronisation needed
+                    const int tu = f.x - cu, tv = f.y - cv;
+                    worst_tie = min(worst_tie, min((unsigned)tu & 0xFFFFFFu, (unsigned)tv & 0xFFFFFFu));
+                    ix[jj] = tu >> 24; iy[jj] = tv >> 24;
+                    worst_ofs = max(worst_ofs, max((unsigned)(ix[jj] + kPatchR), (unsigned)(iy[jj] + kPatchR)));
+                    // keep the gathers inside the staged patch even when this pattern is going to be redone exactly
+                    ix[jj] = min(max(ix[jj], -kPatchR), kPatchR); iy[jj] = min(max(iy[jj], -kPatchR), kPatchR);
+                }
+                unsigned v = 0;
+#pragma unroll
+                for (int bit = 0; bit < GRP / 2; ++bit) {
+                    const int s0 = patch[pofs + iy[2 * bit] * kPatchS + ix[2 * bit]], s1 = patch[pofs + iy[2 * bit + 1] * kPatchS + ix[2 * bit + 1]];
+                    v |= (unsigned)(s0 < s1) << bit;
+                }
+                // group g0 holds bits (g0 % 16) / 2 .. +3 of byte g0 / 16
+                if (BPL == 1) bits[0] |= v << ((g0 & 15) >> 1);
+                else { if (g0 < 16) bits[0] |= v << ((g0 & 15) >> 1); else bits[BPL - 1] |= v << ((g0 & 15) >> 1); }
+            }
+            need_exact |= !have_lut || (lane_valid && (worst_tie < 16u || worst_ofs > 2u * kPatchR || worst_rng >= __double2hiint(32.0) ||
+                                                       worst_tau >= __double2hiint(1.0)));
+            if (__any_sync(0xffffffffu, need_exact)) {
+                const double aq = q == 0 ? a_base : (q == 1 ? a_base + a_rot : a_base - a_rot);
+                const unsigned e = exact_pattern<PPL>(&cam, s_pat, cos(aq), sin(aq), ukx, uky, lane, ds, bimg, uimg, &g, kx, ky);
+#pragma unroll
+                for (int bb = 0; bb < BPL; ++bb) val[q][bb] = (e >> (8 * bb)) & 0xFFu;
+                continue;
+            }
+#pragma unroll
+            for (int bb = 0; bb < BPL; ++bb) val[q][bb] = bits[bb];
+            } else
+#endif
+            {
             double us[PPL], vs[PPL];
             double su = 0.0, sv = 0.0;
             bool need_exact = false;
@@ -377,6 +477,7 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                     v |= (unsigned)(s0 < s1) << bit;
                 }
                 val[q][bb] = v;
+            }
             }
         }
     }
