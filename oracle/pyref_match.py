@@ -290,3 +290,93 @@ def is_in_frustum(mtmc_inv, mtmc, cam, mask, P, normal, min_dist, max_dist, scal
     level = int(np.searchsorted(np.asarray(scale_factors, np.float64), ratio, side="left"))      # std::lower_bound
     level = min(level, len(scale_factors) - 1)
     return u, v, level, view_cos
+
+
+# ---- the other window searches (M4): matching cores, projections supplied by the caller -----------------------------
+def window_search(F1, F2, grid2, window, valid1, nnratio, th_high, having_masks, min_level=0, max_level=INT_MAX):
+    """WindowSearch(F1, F2, windowSize, vpMapPointMatches2, minScaleLevel, maxScaleLevel)  src/cORBmatcher.cpp:326-474.
+    valid1[i1]: keypoint i1 of F1 carries a non-bad map point.  Returns (nmatches, vnMatches21)."""
+    m21 = np.full(len(F2.keys), -1, np.int64)
+    nmatches = 0
+    for i1 in range(len(F1.keys)):
+        if not valid1[i1]:
+            continue
+        level1 = int(F1.keys["octave"][i1])
+        if min_level > 0 and level1 < min_level:
+            continue
+        if max_level < INT_MAX and level1 > max_level:
+            continue
+        cam1 = int(F1.key_cam[i1])
+        # kp1.pt.x (float) is passed as const double&
+        cand = grid2.features_in_area(cam1, float(F1.keys["x"][i1]), float(F1.keys["y"][i1]), float(window))
+        if not cand:
+            continue
+        best, best2, besti = INT_MAX, INT_MAX, -1
+        for i2 in cand:
+            if m21[i2] >= 0:
+                continue
+            d = distance(F1.desc[i1], F2.desc[i2], F1.dmask[i1] if having_masks else None, F2.dmask[i2] if having_masks else None)
+            if d < best:
+                best2, best, besti = best, d, i2
+            elif d < best2:
+                best2 = d
+        if best <= best2 * nnratio and best <= th_high:
+            m21[besti] = i1
+            nmatches += 1
+    return nmatches, m21
+
+
+def search_by_projection_frames(F1, F2, grid2, window, valid1, uv, in_mask, assigned2, nnratio, th_high, having_masks):
+    """SearchByProjection(F1, F2, windowSize, vpMapPointMatches2)  src/cORBmatcher.cpp:476-573.  valid1: the caller's map-point
+    bookkeeping (:487-497); uv[i1, c], in_mask[i1, c]: projection of the map point into camera c of F2 and its mirror-mask test."""
+    a2 = np.array(assigned2, np.int64).copy()
+    nmatches = 0
+    for i1 in range(len(F1.keys)):
+        if not valid1[i1]:
+            continue
+        level1 = int(F1.keys["octave"][i1])
+        for c in range(len(F2.cam_w)):
+            if not in_mask[i1, c]:
+                continue
+            cand = grid2.features_in_area(c, uv[i1, c, 0], uv[i1, c, 1], float(window), level1, level1)
+            if not cand:
+                continue
+            best, best2, besti = INT_MAX, INT_MAX, -1
+            for i2 in cand:
+                if a2[i2] >= 0:
+                    continue
+                d = distance(F1.desc[i1], F2.desc[i2], F1.dmask[i1] if having_masks else None, F2.dmask[i2] if having_masks else None)
+                if d < best:
+                    best2, best, besti = best, d, i2
+                elif d < best2:
+                    best2 = d
+            if float(best) <= float(best2) * nnratio and best <= th_high:
+                a2[besti] = i1
+                nmatches += 1
+    return nmatches, a2
+
+
+def search_by_projection_last(Cur, grid_cur, Last, th, valid_last, uv, in_mask, assigned_cur, th_high, having_masks):
+    """SearchByProjection(CurrentFrame, LastFrame, th)  src/cORBmatcher.cpp:1990-2118 (motion model)."""
+    a = np.array(assigned_cur, np.int64).copy()
+    nmatches = 0
+    for i in range(len(Last.keys)):
+        if not valid_last[i] or not in_mask[i]:
+            continue
+        cam = int(Last.key_cam[i])
+        octave = int(Last.keys["octave"][i])
+        radius = th * float(Cur.scale_factors[octave])
+        cand = grid_cur.features_in_area(cam, uv[i, 0], uv[i, 1], radius, octave - 1, octave + 1)
+        if not cand:
+            continue
+        best, besti = INT_MAX, -1
+        for i2 in cand:
+            if a[i2] >= 0:
+                continue
+            d = distance(Last.desc[i], Cur.desc[i2], Last.dmask[i] if having_masks else None, Cur.dmask[i2] if having_masks else None)
+            if d < best:
+                best, besti = d, i2
+        if best <= th_high:
+            a[besti] = i
+            nmatches += 1
+    return nmatches, a

@@ -175,3 +175,45 @@ def test_project_mappoints(oa, pm, cams):
                 seen += 1
                 assert (px[i, c], py[i, c], level[i, c], vc[i, c]) == r, (i, c)
     assert seen > 100
+
+
+@pytest.mark.parametrize("masks", [False, True])
+def test_m4_window_searches(oa, pm, frames, masks):
+    """WindowSearch (:326), SearchByProjection(F1,F2,win) (:476), SearchByProjection(Current,Last,th) (:1990): restatements of the
+    three reference functions vs the oracle's generic rule loop (mcso_search_windows) fed with the queries the mirror builds."""
+    from multicol_slam_b200.api import RULE_BEST, RULE_RATIO, _queries
+    F1, F2 = frames
+    g2 = pm.Grid(F2.keys, F2.key_cam, [(754, 480)] * 3)
+    rng = np.random.default_rng(8 + masks)
+    valid1 = (rng.random(len(F1.keys)) < 0.8).astype(np.uint8)
+    th_high = 48 if masks else 96
+    qm = F1.dmask if masks else None
+    lv = F1.keys["octave"]
+    free2 = np.full(len(F2.keys), -1, np.int32)
+
+    sel = np.flatnonzero((valid1 != 0) & (lv >= 1) & (lv <= 5))
+    q = _queries(F1.key_cam[sel], F1.keys["x"][sel].astype(np.float64), F1.keys["y"][sel].astype(np.float64), 60.0, -1, -1, sel)
+    on, om21 = oa.search_windows(F2, q, F1.desc, qm, sel, RULE_RATIO, 0.8, th_high, free2.copy())
+    pn, pm21 = pm.window_search(F1, F2, g2, 60, valid1, 0.8, th_high, masks, 1, 5)
+    assert on == pn and np.array_equal(om21, pm21) and on > 100
+
+    uv = np.zeros((len(F1.keys), 3, 2)); in_mask = np.zeros((len(F1.keys), 3), np.uint8)
+    for c in range(3):
+        uv[:, c, 0] = F1.keys["x"] - 3.0 + rng.normal(0, 1, len(F1.keys))
+        uv[:, c, 1] = F1.keys["y"] - 2.0 + rng.normal(0, 1, len(F1.keys))
+        in_mask[:, c] = (F1.key_cam == c) | (rng.random(len(F1.keys)) < 0.1)
+    pre = free2.copy(); pre[::7] = 0
+    i1, c = np.nonzero((valid1 != 0)[:, None] & (in_mask != 0))
+    q = _queries(c, uv[i1, c, 0], uv[i1, c, 1], 40.0, lv[i1], lv[i1], i1)
+    on2, oa2 = oa.search_windows(F2, q, F1.desc, qm, i1, RULE_RATIO, 0.8, th_high, pre.copy())
+    pn2, pa2 = pm.search_by_projection_frames(F1, F2, g2, 40, valid1, uv, in_mask, pre.copy(), 0.8, th_high, masks)
+    assert on2 == pn2 and np.array_equal(oa2, pa2) and on2 > 100
+
+    uvl = np.stack([F1.keys["x"] - 3.0, F1.keys["y"] - 2.0], axis=1).astype(np.float64)
+    inm = (rng.random(len(F1.keys)) < 0.95).astype(np.uint8)
+    sel = np.flatnonzero((valid1 != 0) & (inm != 0))
+    l3 = lv[sel]
+    q = _queries(F1.key_cam[sel], uvl[sel, 0], uvl[sel, 1], 50.0 * F2.scale_factors[l3], l3 - 1, l3 + 1, sel)
+    on3, oa3 = oa.search_windows(F2, q, F1.desc, qm, sel, RULE_BEST, 0.8, th_high, free2.copy())
+    pn3, pa3 = pm.search_by_projection_last(F2, g2, F1, 50.0, valid1, uvl, inm, free2.copy(), th_high, masks)
+    assert on3 == pn3 and np.array_equal(oa3, pa3) and on3 > 100
