@@ -380,3 +380,28 @@ def search_by_projection_last(Cur, grid_cur, Last, th, valid_last, uv, in_mask, 
             a[besti] = i
             nmatches += 1
     return nmatches, a
+
+
+def fuse_candidates(KF, grid, uv, in_mask, level, th, mp_desc, mp_dmask, th_low, having_masks):
+    """Matching core of Fuse(pKF, curKF, vpMapPoints, th)  src/cORBmatcher.cpp:1265-1418 (same core in :1420, :1570 and
+    SearchBySim3 :1721): per (map point i, camera c) passing the mirror-mask / distance tests (in_mask), the key-frame keypoint
+    with the smallest distance inside radius th * scale[level] whose level is level-1 or level; kept if <= TH_LOW_.
+    The key-frame flavour of GetFeaturesInArea (src/cMultiKeyFrame.cpp:694-737) has no level argument; the level test is in the loop."""
+    best = np.full(in_mask.shape, -1, np.int64)
+    for i in range(in_mask.shape[0]):
+        for c in range(in_mask.shape[1]):
+            if not in_mask[i, c]:
+                continue
+            lvl = int(level[i, c])
+            radius = th * float(KF.scale_factors[lvl])
+            bd, bi = INT_MAX, -1
+            for k in grid.features_in_area(c, uv[i, c, 0], uv[i, c, 1], radius):
+                kl = int(KF.keys["octave"][k])
+                if kl < lvl - 1 or kl > lvl:
+                    continue
+                d = distance(mp_desc[i], KF.desc[k], mp_dmask[i] if having_masks else None, KF.dmask[k] if having_masks else None)
+                if d < bd:
+                    bd, bi = d, k
+            if bi >= 0 and bd <= th_low:
+                best[i, c] = bi
+    return best

@@ -217,3 +217,34 @@ def test_m4_window_searches(oa, pm, frames, masks):
     on3, oa3 = oa.search_windows(F2, q, F1.desc, qm, sel, RULE_BEST, 0.8, th_high, free2.copy())
     pn3, pa3 = pm.search_by_projection_last(F2, g2, F1, 50.0, valid1, uvl, inm, free2.copy(), th_high, masks)
     assert on3 == pn3 and np.array_equal(oa3, pa3) and on3 > 100
+
+
+@pytest.mark.parametrize("masks", [False, True])
+def test_fuse_candidates(oa, pm, frames, masks):
+    """matching core of Fuse / SearchBySim3 vs the oracle's stateless best rule (the mirror's FuseCandidates query layout)"""
+    from multicol_slam_b200.api import RULE_BEST_FREE, _queries
+    KF = frames[1]
+    grid = pm.Grid(KF.keys, KF.key_cam, [(754, 480)] * 3)
+    rng = np.random.default_rng(21 + masks)
+    n, nc = 500, 3
+    src = rng.integers(0, len(KF.keys), n)
+    desc = KF.desc[src].copy()
+    flip = rng.integers(0, 256, desc.shape, dtype=np.uint8) & rng.integers(0, 256, desc.shape, dtype=np.uint8) & rng.integers(0, 256, desc.shape, dtype=np.uint8)
+    desc ^= flip
+    dm = KF.dmask[src].copy()
+    uv = np.zeros((n, nc, 2)); in_mask = np.zeros((n, nc), np.uint8); level = np.zeros((n, nc), np.int32)
+    for c in range(nc):
+        own = KF.key_cam[src] == c
+        uv[:, c, 0] = np.where(own, KF.keys["x"][src] + rng.normal(0, 1.5, n), rng.uniform(0, 754, n))
+        uv[:, c, 1] = np.where(own, KF.keys["y"][src] + rng.normal(0, 1.5, n), rng.uniform(0, 480, n))
+        in_mask[:, c] = own | (rng.random(n) < 0.15)
+        level[:, c] = np.clip(KF.keys["octave"][src] + rng.integers(0, 2, n), 0, 7)
+    th_low = 32 if masks else 64
+    i, c = np.nonzero(in_mask != 0)
+    lv = level[i, c]
+    q = _queries(c, uv[i, c, 0], uv[i, c, 1], 3.0 * KF.scale_factors[lv], lv - 1, lv, i)
+    on, res = oa.search_windows(KF, q, desc, dm if masks else None, np.zeros(len(q), np.int32), RULE_BEST_FREE, 0.8, th_low,
+                                np.full(max(len(q), len(KF.keys)), -1, np.int32))
+    got = np.full(in_mask.shape, -1, np.int64); got[i, c] = res[:len(q)]
+    ref = pm.fuse_candidates(KF, grid, uv, in_mask, level, 3.0, desc, dm, th_low, masks)
+    assert np.array_equal(got, ref) and (ref >= 0).sum() == on and on > 150
