@@ -222,9 +222,20 @@ int mcs_search_by_bow(const uint8_t* desc1, const uint8_t* mask1, const uint8_t*
     if (n1 <= 0 || n2 <= 0 || n_fv1 <= 0 || n_fv2 <= 0) return MCS_OK;
     if (!desc1 || !desc2 || !fv1_nodes || !fv1_offsets || !fv1_features || !fv2_nodes || !fv2_offsets || !fv2_features)
         return bfail(MCS_ERR_INVALID, "null argument");
+    // feature vectors are std::map<NodeId, vector<unsigned>> in the reference: node ids strictly ascending, CSR offsets monotone
+    for (int side = 0; side < 2; ++side) {
+        const int32_t* nodes = side ? fv2_nodes : fv1_nodes;
+        const int32_t* off = side ? fv2_offsets : fv1_offsets;
+        const int n = side ? n_fv2 : n_fv1;
+        if (off[0] < 0) return bfail(MCS_ERR_INVALID, "feature-vector offsets must start at >= 0");
+        for (int i = 0; i < n; ++i) {
+            if (off[i + 1] < off[i]) return bfail(MCS_ERR_INVALID, "feature-vector offsets must be non-decreasing");
+            if (i > 0 && nodes[i] <= nodes[i - 1]) return bfail(MCS_ERR_INVALID, "feature-vector node ids must be strictly ascending");
+        }
+    }
     const int nf1 = fv1_offsets[n_fv1], nf2 = fv2_offsets[n_fv2];
-    for (int i = 0; i < nf1; ++i) if (fv1_features[i] < 0 || fv1_features[i] >= n1) return bfail(MCS_ERR_INVALID, "feature index out of range");
-    for (int i = 0; i < nf2; ++i) if (fv2_features[i] < 0 || fv2_features[i] >= n2) return bfail(MCS_ERR_INVALID, "feature index out of range");
+    for (int i = fv1_offsets[0]; i < nf1; ++i) if (fv1_features[i] < 0 || fv1_features[i] >= n1) return bfail(MCS_ERR_INVALID, "feature index out of range");
+    for (int i = fv2_offsets[0]; i < nf2; ++i) if (fv2_features[i] < 0 || fv2_features[i] >= n2) return bfail(MCS_ERR_INVALID, "feature index out of range");
     const bool masked = mask1 && mask2;
     // queries in the reference's visiting order: common nodes ascending, key-frame keypoints in list order (ref :199-217)
     std::vector<GroupQuery> qs;

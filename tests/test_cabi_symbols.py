@@ -101,3 +101,27 @@ def test_bow_validation_and_no_cpu_fallback(api):
     with pytest.raises(api.McsError) as e:
         api.cORBmatcher(0.9, False, 32, False).SearchByBoWFrame(d, fv, d, fv)
     assert e.value.code == api.MCS_ERR_NO_DEVICE
+
+
+def test_search_by_bow_argument_validation(api):
+    """malformed feature vectors are refused on the host (before any device work); a well-formed call gets past the validation
+    (and, without a device, ends in MCS_ERR_NO_DEVICE)"""
+    d = np.zeros((8, 32), np.uint8)
+    m = api.cORBmatcher(0.9, False, 32, False)
+    good = (np.array([1, 5], np.int32), np.array([0, 3, 8], np.int32), np.arange(8, dtype=np.int32))
+    for bad in ((np.array([5, 1], np.int32), good[1], good[2]),                       # node ids not ascending
+                (good[0], np.array([0, 9, 8], np.int32), good[2]),                    # offsets decreasing
+                (good[0], good[1], np.array([0, 1, 2, 3, 4, 5, 6, 99], np.int32))):   # feature index out of range
+        with pytest.raises(api.McsError) as e:
+            m.SearchByBoWFrame(d, bad, d, good)
+        assert e.value.code == api.MCS_ERR_INVALID
+        with pytest.raises(api.McsError) as e:
+            m.SearchByBoWFrame(d, good, d, bad)
+        assert e.value.code == api.MCS_ERR_INVALID
+    if api.device_count() == 0:
+        with pytest.raises(api.McsError) as e:
+            m.SearchByBoWFrame(d, good, d, good)
+        assert e.value.code == api.MCS_ERR_NO_DEVICE
+    else:
+        n, out = m.SearchByBoWFrame(d, good, d, good)
+        assert len(out) == 8
