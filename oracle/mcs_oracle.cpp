@@ -11,8 +11,11 @@
  * algorithm and PINNED against cv2 4.13.0 by oracle/pin_cv2.py (fixtures in tests/golden/).
  * The reference itself ships no tests and cannot be compiled here (no OpenCV C++), so the
  * reference-specific logic (cell grid, octree, descriptor, matchers) is pinned only through the
- * independent Python/cv2 restatement in oracle/pyref.py: "parity pinned to cv2 4.13 primitives +
- * an independent second restatement; unpinned by reference-run outputs".
+ * independent Python restatements in oracle/pyref.py (extractor, real cv2 primitives) and
+ * oracle/pyref_match.py (matchers): "parity pinned to cv2 4.13 primitives + an independent second
+ * restatement; unpinned by reference-run outputs".  Exception: the bag-of-words functions at the end
+ * of this file ARE pinned by reference-run outputs -- the reference's vendored DBoW2 compiles from its
+ * own sources (oracle/Makefile target `ref`, oracle/_ref/libdbow2_ref.so) and agrees bit for bit.
  *
  * Build: g++ -O2 -std=c++17 -ffp-contract=off -fPIC -shared (oracle/Makefile).
  * -ffp-contract=off: double expressions are evaluated without FMA contraction (ISO semantics).
