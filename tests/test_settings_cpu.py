@@ -1,14 +1,26 @@
-"""Configuration loaders (multicol_slam_b200/settings.py) on the reference's own Lafida configuration files
-(tests/golden/lafida_config/: data fixtures copied from Examples/Lafida).  CPU only."""
+"""Configuration loaders (multicol_slam_b200/settings.py) on the values of the reference's Lafida configuration
+(tests/golden/lafida_config.json holds the key/value content of Examples/Lafida/*.yaml; the files are re-written here in the
+flat cv::FileStorage YAML layout, with a header line and comments, so that the parser is exercised too).  CPU only."""
+import json
 import pathlib
 
 import numpy as np
 import pytest
 
-CFG = pathlib.Path(__file__).resolve().parent / "golden" / "lafida_config"
+
+@pytest.fixture(scope="module")
+def CFG(tmp_path_factory):
+    d = tmp_path_factory.mktemp("lafida_config")
+    content = json.loads((pathlib.Path(__file__).resolve().parent / "golden" / "lafida_config.json").read_text())
+    for name, kv in content.items():
+        lines = ["%YAML:1.0", "", "# written by tests/test_settings_cpu.py"]
+        for k, v in kv.items():
+            lines.append(f"{k}: {v!r}   # {k.split('.')[-1]}" if isinstance(v, float) else f"{k}: {v}")
+        (d / name).write_text("\n".join(lines) + "\n")
+    return d
 
 
-def test_interior_orientation_matches_packaged_cameras(cams):
+def test_interior_orientation_matches_packaged_cameras(cams, CFG):
     from multicol_slam_b200 import settings as S
     M_c, loaded = S.load_rig(CFG)
     assert loaded == cams                                     # multicol_slam_b200/data/lafida_cams.json came from the same files
@@ -22,7 +34,7 @@ def test_interior_orientation_matches_packaged_cameras(cams):
     assert np.allclose(c, [-0.0238361786473007, -2.05998171167958, 0.695126790868671], atol=1e-13)
 
 
-def test_rig_matrices_and_essential(cams):
+def test_rig_matrices_and_essential(cams, CFG):
     from multicol_slam_b200 import settings as S
     M_c, _ = S.load_rig(CFG)
     rng = np.random.default_rng(0)
@@ -45,7 +57,7 @@ def test_rig_matrices_and_essential(cams):
     assert Es.shape == (3, 3, 3, 3) and np.array_equal(Es[1, 2], S.compute_E(m1i[1], m2[2]))
 
 
-def test_extractor_settings():
+def test_extractor_settings(CFG):
     from multicol_slam_b200 import settings as S
     track, init = S.extractor_settings(CFG / "Slam_Settings_indoor1.yaml")
     assert track["nfeatures"] == 400 and init["nfeatures"] == 800 and track["fastThreshold"] == 20 and init["fastThreshold"] == 5
@@ -53,10 +65,10 @@ def test_extractor_settings():
     assert track["do_dBrief"] is False and track["learnMasks"] is False and track["useAgast"] is False and track["fastAgastType"] == 2
     assert {k: v for k, v in track.items() if k not in ("nfeatures", "fastThreshold")} == {k: v for k, v in init.items() if k not in ("nfeatures", "fastThreshold")}
     kv = S.read_opencv_yaml(CFG / "Slam_Settings_indoor1.yaml")
-    assert kv["Camera.fps"] == 25.0 and kv["UseMotionModel"] == 1 and kv["traj.EndFrame"] == 759
+    assert kv["Camera.fps"] == 25.0 and kv["Camera.RGB"] == 1 and kv["UseMotionModel"] == 1 and kv["traj.EndFrame"] == 759
 
 
-def test_extractor_settings_feed_the_oracle(oa, cams):
+def test_extractor_settings_feed_the_oracle(oa, cams, CFG):
     """the keyword sets are accepted by the extractor constructors (oracle here; same ExtractorParams as the GPU class)"""
     from multicol_slam_b200 import settings as S, synth
     track, init = S.extractor_settings(CFG / "Slam_Settings_indoor1.yaml")
