@@ -935,6 +935,9 @@ static bool check_epipolar(const double* r1, const double* r2, const double* E, 
 }
 
 // cORBmatcher::SearchForTriangulationRaw  src/cORBmatcher.cpp:968-1156 (mbCheckOrientation == false)
+// exported for tests/test_ref_pin_cpu.py (compared with the reference's own CheckDistEpipolarLine, src/misc.cpp:53-69)
+int mcso_check_epipolar(const double* r1, const double* r2, const double* E, double thresh) { return check_epipolar(r1, r2, E, thresh) ? 1 : 0; }
+
 int mcso_search_for_triangulation(const uint8_t* desc1, const uint8_t* mask1, const int* cam1, const uint8_t* free1, const double* rays1,
                                   int n1, const uint8_t* desc2, const uint8_t* mask2, const int* cam2, const uint8_t* free2,
                                   const double* rays2, int n2, int dim, int th_low, const double* E, int n_cams, double epi_thresh,

@@ -1,0 +1,2 @@
+// forwards to the stand-in (see ../opencv.hpp): test infrastructure
+#include "../opencv.hpp"
