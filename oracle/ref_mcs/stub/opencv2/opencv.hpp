@@ -145,7 +145,7 @@ template <class T, int N> struct Vec : public Matx<T, N, 1> {
     Vec() {}
     template <class... A, class = typename std::enable_if<(sizeof...(A) == N) && (N > 1)>::type>
     Vec(A... a) : Matx<T, N, 1>(a...) {}
-    explicit Vec(T v0) : Matx<T, N, 1>(v0) {}
+    Vec(T v0) : Matx<T, N, 1>(v0) {}                 // cv::Vec(_Tp v0) is implicit: `pt2 = 0.0;` (src/cam_system_omni.cpp:56)
     Vec(const Matx<T, N, 1>& m) : Matx<T, N, 1>(m) {}
     T& operator[](int i) { return this->val[i]; }
     const T& operator[](int i) const { return this->val[i]; }
@@ -182,6 +182,8 @@ typedef Matx<double, 4, 4> Matx44d;
 typedef Matx<double, 3, 1> Matx31d;
 typedef Matx<double, 6, 1> Matx61d;
 typedef Matx<double, 1, 3> Matx13d;
+typedef Matx<double, 3, 4> Matx34d;
+typedef Matx<double, 4, 1> Matx41d;
 typedef Vec<double, 2> Vec2d;
 typedef Vec<double, 3> Vec3d;
 typedef Vec<double, 4> Vec4d;
@@ -229,6 +231,7 @@ public:
         wrows_ = r; wcols_ = c; base_ = data;
     }
     Mat(const MatFillExpr& e) : Mat() { *this = e; }
+    template <class T, int M, int N> Mat(const Matx<T, M, N>& mx);            // copies (cv::Mat(const Matx&, copyData = true))
     Mat& operator=(const MatFillExpr& e) { create(e.rows, e.cols, e.type); setTo(e.value); return *this; }
 
     static MatFillExpr zeros(int r, int c, int type) { return MatFillExpr{r, c, type, 0.0}; }
@@ -311,6 +314,11 @@ template <> struct DepthOf<double> { enum { value = CV_64F }; };
 template <> struct DepthOf<float> { enum { value = CV_32F }; };
 template <> struct DepthOf<uchar> { enum { value = CV_8U }; };
 template <> struct DepthOf<int> { enum { value = CV_32S }; };
+
+template <class T, int M, int N> inline Mat::Mat(const Matx<T, M, N>& mx) : Mat() {
+    create(M, N, DepthOf<T>::value);
+    for (int i = 0; i < M; ++i) for (int j = 0; j < N; ++j) at<T>(i, j) = mx(i, j);
+}
 
 template <class T> class Mat_;
 template <class T> struct MatCommaInitializer_ {
