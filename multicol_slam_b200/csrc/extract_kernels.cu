@@ -334,11 +334,11 @@ cudaError_t launch_octree(const PyramidGeom& G, const PyramidGeom* G_dev, int n_
     cap = (cap + 31) & ~31;
     if (cap > kMaxNodes) return cudaErrorInvalidValue;
     const size_t smem = octree_smem_bytes(cap);
-    static size_t configured = 0;
-    if (smem > configured) {
+    // the attribute is per device and there may be one extractor per device / thread: set it on every launch (a cheap
+    // driver call next to a kernel that runs once per batch) instead of caching a process-wide high-water mark
+    if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     dim3 grid(G.nlevels, n_images);
     octree_kernel<<<grid, kOctThreads, smem, st>>>(G_dev, cap, raw, G.raw_total, raw_count, node_of, sel_xys, sel_count, status);

@@ -177,9 +177,6 @@ __global__ void topk_merge_kernel(const unsigned long long* __restrict__ part, c
     }
 }
 
-static unsigned long long* g_part = nullptr;     // per-process scratch for partial top-K lists
-static size_t g_part_bytes = 0;
-
 cudaError_t launch_hamming_topk(const uint8_t* q, const uint8_t* qmask, int nq, const uint8_t* d, const uint8_t* dmask,
                                 int nd, const uint8_t* db_skip, int dim, int K, int* topk_idx, int* topk_dist,
                                 cudaStream_t st) {
@@ -195,13 +192,12 @@ cudaError_t launch_hamming_topk(const uint8_t* q, const uint8_t* qmask, int nq, 
     splits = max(1, min(splits, tiles));
     const int chunk = ((tiles + splits - 1) / splits) * kDbTile;
     splits = max(1, (nd + chunk - 1) / chunk);
+    // partial top-K lists of the database splits: stream-ordered scratch owned by THIS call (cudaMallocAsync pool), so that
+    // concurrent callers -- the reference runs its matchers from three threads -- and different streams never share it
     const size_t need = (size_t)splits * nq * kTopKMax * sizeof(unsigned long long);
-    if (need > g_part_bytes) {
-        if (g_part) cudaFree(g_part);
-        cudaError_t e = cudaMalloc(&g_part, need);
-        if (e != cudaSuccess) { g_part = nullptr; g_part_bytes = 0; return e; }
-        g_part_bytes = need;
-    }
+    unsigned long long* g_part = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&g_part, need, st);
+    if (e != cudaSuccess) return e;
     dim3 grid(qblocks, splits);
     const bool masked = qmask && dmask;
 #define MCS_TOPK(W, M) hamming_topk_kernel<W, M><<<grid, kTopkThreads, 0, st>>>((const uint32_t*)q, (const uint32_t*)qmask, nq, \
@@ -211,7 +207,9 @@ cudaError_t launch_hamming_topk(const uint8_t* q, const uint8_t* qmask, int nq, 
     else { if (masked) MCS_TOPK(16, true); else MCS_TOPK(16, false); }
 #undef MCS_TOPK
     topk_merge_kernel<<<(nq + 127) / 128, 128, 0, st>>>(g_part, splits, nq, K, topk_idx, topk_dist);
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    const cudaError_t ef = cudaFreeAsync(g_part, st);        // after the merge in stream order
+    return e != cudaSuccess ? e : ef;
 }
 
 // Stream matching: image i = (frame f, camera c) is matched against image i - n_cams = (f-1, c); both live in

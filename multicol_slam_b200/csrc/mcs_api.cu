@@ -673,7 +673,8 @@ int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams
         const int nc = std::min(std::max(n_frames / 8, 1), 4), each = (n_frames + nc - 1) / nc;
         for (int c = 0; c <= nc; ++c) chunk_lo.push_back(std::min(c * each, n_frames));
     }
-    if (const char* plan = getenv("MCS_STREAM_CHUNKS")) {               // experiment knob: comma-separated frames per chunk
+#ifdef MCS_DEBUG_KNOBS                                                  // experiment knobs exist only in -DMCS_DEBUG_KNOBS builds
+    if (const char* plan = getenv("MCS_STREAM_CHUNKS")) {               // comma-separated frames per chunk
         std::vector<int> lo(1, 0);
         for (const char* q = plan; *q && lo.back() < n_frames;) {
             lo.push_back(std::min(n_frames, lo.back() + std::max(1, atoi(q))));
@@ -683,6 +684,7 @@ int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams
         if (lo.back() < n_frames) lo.push_back(n_frames);
         chunk_lo = lo;
     }
+#endif
     const int n_chunks = (int)chunk_lo.size() - 1;
     int fpc = 0;
     for (int c = 0; c < n_chunks; ++c) fpc = std::max(fpc, chunk_lo[c + 1] - chunk_lo[c]);
@@ -714,7 +716,11 @@ int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams
         CK(events.add(&ev_feat[c], cudaEventDisableTiming));
         CK(events.add(&ev_done[c], cudaEventDisableTiming));
     }
+#ifdef MCS_DEBUG_KNOBS
     static const bool trace = getenv("MCS_TRACE_STREAM") != nullptr;    // per-chunk timeline on stderr
+#else
+    constexpr bool trace = false;
+#endif
     // Everything asynchronous happens inside enqueue(); whatever it returns, the three streams are drained before this
     // function returns, because the copies read caller memory and the local cam-of-image table.
     auto enqueue = [&]() -> int {

@@ -62,6 +62,8 @@ int mcs_vocabulary_create(int32_t k, int32_t L, int32_t scoring, int32_t weighti
         if (pid < 0 || pid >= n_nodes || pid == nid) return bfail(MCS_ERR_INVALID, "parent id out of range");
         ++cnt[pid + 1];
     }
+    for (int i = 0; i < n_nodes; ++i)
+        if (cnt[i + 1] > 65535) return bfail(MCS_ERR_UNSUPPORTED, "more than 65535 children under one node (the descent packs the child position in 16 bits)");
     for (int i = 0; i < n_nodes; ++i) cnt[i + 1] += cnt[i];
     if (cnt[1] == 0) return bfail(MCS_ERR_INVALID, "the root has no children");
     std::vector<int> cur(cnt.begin(), cnt.end() - 1);
@@ -115,6 +117,12 @@ int mcs_bow_transform(const mcs_vocabulary* voc, const uint8_t* desc, int32_t n,
                       int32_t* node_id) {
     if (!voc || (n > 0 && !desc)) return bfail(MCS_ERR_INVALID, "null argument");
     if (n <= 0) return MCS_OK;
+    {   // the tree lives on the device that was current when the vocabulary was created: a call from a thread whose current
+        // device differs would hand the kernel foreign pointers
+        int cur = -1;
+        BCK(cudaGetDevice(&cur));
+        if (cur != voc->device) return bfail(MCS_ERR_INVALID, "vocabulary was created on another CUDA device than the current one");
+    }
     Dev dd, dw, dwt, dn;
     BCK(dd.alloc((size_t)n * 32)); BCK(dw.alloc((size_t)n * 4)); BCK(dwt.alloc((size_t)n * 8)); BCK(dn.alloc((size_t)n * 4));
     BCK(cudaMemcpy(dd.p, desc, (size_t)n * 32, cudaMemcpyHostToDevice));

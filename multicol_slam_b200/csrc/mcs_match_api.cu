@@ -346,6 +346,7 @@ int mcs_window_search(const mcs_frame_view* frame, const mcs_window_query* queri
     int rows = 0;
     for (int i = 0; i < nq; ++i) {
         if (queries[i].cam < 0 || queries[i].cam >= frame->n_cams) return mfail(MCS_ERR_INVALID, "query camera out of range");
+        if (queries[i].desc_index < 0) return mfail(MCS_ERR_INVALID, "negative query descriptor index");
         rows = std::max(rows, queries[i].desc_index + 1);
     }
     std::vector<mcs_window_query> qs(queries, queries + nq);
@@ -438,6 +439,7 @@ int mcs_search_windows(const mcs_frame_view* f, const mcs_window_query* queries,
     for (int i = 0; i < nq; ++i) {
         if (queries[i].cam < 0 || queries[i].cam >= f->n_cams) return mfail(MCS_ERR_INVALID, "query camera out of range");
         if (query_tag[i] < 0) return mfail(MCS_ERR_INVALID, "query tags must be >= 0");
+        if (queries[i].desc_index < 0) return mfail(MCS_ERR_INVALID, "negative query descriptor index");
         rows = std::max(rows, queries[i].desc_index + 1);
     }
     FrameDev fd;
