@@ -306,14 +306,26 @@ int  mcs_project_mappoints(int32_t n_cams, const double* mtmc_inv, const double*
  *                                                                       SearchByProjection(F, MapPoints, th) (:151-158)
  *   MCS_RULE_BEST_FREE    best <= threshold, candidates are NOT skipped when taken and nothing is marked: the per-query
  *                         answer is written to assigned[q] (best index or -1; `assigned` is then an output of nq entries).
- *                         This is the matching core of Fuse (:1326-1366, :1620-1660), SearchBySim3 (:1793-1830, :1869-1906)
- *                         and SearchByProjection(KF, Scw, ...) (:2345-2390): their level filter {l-1, l} goes into the query.
+ *                         This is the matching core of Fuse(pKF, curKF, ..) (:1326-1366), Fuse(pKF, Scw, ..) (:1620-1660) and
+ *                         SearchBySim3 (:1793-1830, :1869-1906): their level filter {l-1, l} goes into the query.
+ *   MCS_RULE_FIRST_FREE   Fuse(pKF, vpMapPoints, th) (:1420-1568, the overload cLocalMapping calls at src/cLocalMapping.cpp:450)
+ *                         as the reference really behaves: it computes the descriptor distance and DISCARDS it (:1506-1514, `dist`
+ *                         stays 0), so the first candidate of the window that passes the level filter wins with distance
+ *                         0 <= threshold.  Stateless like MCS_RULE_BEST_FREE: assigned[q] = that candidate or -1.
+ *   MCS_RULE_SCW          SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) (:2265-2392) as written: taken candidates
+ *                         (vpMatched[idx], i.e. assigned[idx] >= 0) are skipped; the descriptor compared for candidate idx of a
+ *                         query of camera c is ROW idx OF CAMERA c's MATRIX -- the contiguous keypoint id used as a per-camera row
+ *                         (:2367, :2372) -- i.e. contiguous keypoint first(c) + idx; candidates whose row lies beyond camera c's own
+ *                         rows (where the reference reads past the matrix: undefined) are dropped; accepted when
+ *                         best <= threshold && bestIdx > 0 (:2385, keypoint 0 can never be matched).  Needs camera-major keypoints.
  * On acceptance assigned[bestIdx] = query_tag[q] (tags must be >= 0).  The caller builds the queries (projection
  * front-end, "bad"/duplicate filters of the reference loops) and owns `assigned` (in/out, [n_keys], -1 = free). */
 #define MCS_RULE_RATIO        0
 #define MCS_RULE_BEST         1
 #define MCS_RULE_LEVEL_RATIO  2
 #define MCS_RULE_BEST_FREE    3
+#define MCS_RULE_FIRST_FREE   4
+#define MCS_RULE_SCW          5
 int  mcs_search_windows(const mcs_frame_view* frame, const mcs_window_query* queries, int32_t nq,
                         const uint8_t* qdesc, const uint8_t* qmask, const int32_t* query_tag,
                         int32_t rule, double nnratio, int32_t threshold, int32_t* assigned, int32_t* nmatches);

@@ -376,7 +376,7 @@ def project_mappoints(mtmc_inv, mtmc, cams, masks, world_pos, normal, min_dist, 
     return in_view, level, px, py, vc
 
 
-RULE_RATIO, RULE_BEST, RULE_LEVEL_RATIO, RULE_BEST_FREE = 0, 1, 2, 3
+RULE_RATIO, RULE_BEST, RULE_LEVEL_RATIO, RULE_BEST_FREE, RULE_FIRST_FREE, RULE_SCW = 0, 1, 2, 3, 4, 5
 
 
 def search_windows(frame, queries, qdesc, qmask, query_tag, rule, nnratio, threshold, assigned):
@@ -400,6 +400,91 @@ def _queries(cam, x, y, r, min_level, max_level, desc_index):
     q["cam"], q["x"], q["y"], q["r"] = cam, x, y, r
     q["min_level"], q["max_level"], q["desc_index"] = min_level, max_level, desc_index
     return q
+
+
+def _mm(A, B):
+    """cv::Matx product: s = 0; s += a(i,k) * b(k,j) in index order, plain doubles (no FMA, no BLAS reordering)"""
+    A, B = np.asarray(A, np.float64), np.asarray(B, np.float64)
+    B2 = B.reshape(B.shape[0], -1)
+    out = np.zeros((A.shape[0], B2.shape[1]))
+    for i in range(A.shape[0]):
+        for j in range(B2.shape[1]):
+            acc = 0.0
+            for k in range(A.shape[1]):
+                acc += float(A[i, k]) * float(B2[k, j])
+            out[i, j] = acc
+    return out.reshape((A.shape[0],) + B.shape[1:])
+
+
+def inv_rigid(M):
+    """cConverter::invMat (ref src/cConverter.cpp:31-44): [R^T | -R^T t]"""
+    M = np.asarray(M, np.float64)
+    Rt = M[:3, :3].T.copy()
+    t = _mm(-Rt, M[:3, 3])
+    out = np.eye(4)
+    out[:3, :3], out[:3, 3] = Rt, t
+    return out
+
+
+class Rig:
+    """cMultiCamSys_ as the matchers use it (ref include/cam_system_omni.h:53-206): MCS pose M_t, camera offsets M_c[c], interior
+    orientations; MtMc = M_t * M_c[c] and its rigid inverse kept like the reference does (flagMcMt)."""
+
+    def __init__(self, cams, M_c=None, M_t=None):
+        self.cams = list(cams)
+        n = len(self.cams)
+        self.M_c = np.ascontiguousarray(np.tile(np.eye(4), (n, 1, 1)) if M_c is None else M_c, np.float64)
+        self.masks = [mirror_mask(c) for c in self.cams]
+        self.set_pose(np.eye(4) if M_t is None else M_t)
+
+    def set_pose(self, M_t):
+        self.M_t = np.ascontiguousarray(M_t, np.float64)
+        self.MtMc = np.stack([_mm(self.M_t, self.M_c[c]) for c in range(len(self.cams))])
+        self.MtMc_inv = np.stack([inv_rigid(m) for m in self.MtMc])
+
+    def world_to_cam(self, c, p3):
+        """WorldToCamHom_fast (ref src/cam_system_omni.cpp:92-133) -> (u, v, camera-frame point)"""
+        pc = _mm(self.MtMc_inv[c], np.array([p3[0], p3[1], p3[2], 1.0]))
+        u, v = world_to_img(self.cams[c], float(pc[0]), float(pc[1]), float(pc[2]))
+        return u, v, pc
+
+    def in_mirror_mask(self, c, u, v):
+        """isPointInMirrorMask(u, v, 0) (ref src/cam_model_omni.cpp:163-178)"""
+        if not (np.isfinite(u) and np.isfinite(v)):
+            return False
+        ur, vr = int(np.rint(u)), int(np.rint(v))
+        m = self.masks[c]
+        if ur >= m.shape[1] or ur <= 0 or vr >= m.shape[0] or vr <= 0:
+            return False
+        return bool(m[vr, ur] > 0)
+
+
+def compute_E_rel(Trel):
+    """inline ComputeE(const cv::Matx44d& Trel) (ref include/misc.h:232-241): [t/|t|]_x * R"""
+    Trel = np.asarray(Trel, np.float64)
+    R = Trel[:3, :3]
+    t = Trel[:3, 3].copy()
+    n = float(np.sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]))
+    t = t / n
+    tx = np.array([[0.0, -t[2], t[1]], [t[2], 0.0, -t[0]], [-t[1], t[0], 0.0]])
+    return _mm(tx, R)
+
+
+def check_epipolar(ray1, ray2, E, thresh):
+    """CheckDistEpipolarLine (ref src/misc.cpp:53-69), cv::Matx accumulation order"""
+    r1, r2, E = (np.asarray(a, np.float64) for a in (ray1, ray2, E))
+    nom = float(_mm(_mm(r2.reshape(1, 3), E), r1.reshape(3, 1))[0, 0])
+    ex1 = _mm(E, r1.reshape(3, 1)).ravel()
+    etx2 = _mm(E.T.copy(), r2.reshape(3, 1)).ravel()
+    den = float(ex1[0] * ex1[0] + ex1[1] * ex1[1] + ex1[2] * ex1[2] + etx2[0] * etx2[0] + etx2[1] * etx2[1] + etx2[2] * etx2[2])
+    if den == 0.0:
+        return False
+    return (nom * nom) / den < thresh
+
+
+def _predict_level(scale_factors, ratio):
+    """lower_bound over the scale factors, clamped to the last level (ref src/cORBmatcher.cpp:1313-1317)"""
+    return min(int(np.searchsorted(scale_factors, ratio, side="left")), len(scale_factors) - 1)
 
 
 class cORBmatcher:
@@ -474,19 +559,153 @@ class cORBmatcher:
         return search_windows(CurrentFrame, q, LastFrame.desc, LastFrame.dmask if self.havingMasks else None, sel, RULE_BEST,
                               self.mfNNratio, self.TH_HIGH_, assigned_cur)
 
-    def FuseCandidates(self, KF, uv, in_mask, level, th, mp_desc, mp_dmask=None):
-        """Matching core of Fuse(pKF, curKF, vpMapPoints, th) (ref :1265-1418): for map point i and camera c (in_mask[i,c]) the best
-        keypoint of KF within th*scale[level] of uv[i,c] on levels {level-1, level}, accepted when its distance <= TH_LOW_.
+    def FuseCandidates(self, KF, uv, in_mask, level, th, mp_desc, mp_dmask=None, first_wins=False):
+        """Matching core of Fuse(pKF, curKF, vpMapPoints, th) (ref :1265-1418) and Fuse(pKF, Scw, vpPoints, th) (:1570-1719): for map
+        point i and camera c (in_mask[i,c]) the best keypoint of KF within th*scale[level] of uv[i,c] on levels {level-1, level},
+        accepted when its distance <= TH_LOW_.  first_wins=True is Fuse(pKF, vpMapPoints, th) (:1420-1568) as the reference behaves:
+        the distance is discarded there, the first in-level candidate of the window wins (MCS_RULE_FIRST_FREE).
         Returns best [n, n_cams] (keypoint index or -1); replacing / adding observations stays with the caller (host map bookkeeping)."""
         in_mask = np.asarray(in_mask) != 0
         i, c = np.nonzero(in_mask)
         lv = np.asarray(level)[i, c]
         q = _queries(c, np.asarray(uv)[i, c, 0], np.asarray(uv)[i, c, 1], th * KF.scale_factors[lv], lv - 1, lv, i)
-        n, res = search_windows(KF, q, mp_desc, mp_dmask if self.havingMasks else None, np.zeros(len(q), np.int32), RULE_BEST_FREE,
+        n, res = search_windows(KF, q, mp_desc, mp_dmask if self.havingMasks else None, np.zeros(len(q), np.int32),
+                                RULE_FIRST_FREE if first_wins else RULE_BEST_FREE,
                                 self.mfNNratio, self.TH_LOW_, np.full(max(len(q), len(KF.keys)), -1, np.int32))
         best = np.full(in_mask.shape, -1, np.int32)
         best[i, c] = res[:len(q)]
         return best
+
+    def SearchByProjectionScw(self, KF, query_cam, uv, level, th, valid, mp_desc, mp_dmask=None, matched=None):
+        """Matching part of SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) (ref :2265-2392) as written there.  Entry i of
+        vpPoints: valid[i] (not NULL / bad / already found, projected inside the mirror mask, distance in range), query_cam[i] =
+        keypoint_to_cam[i] -- the reference looks the camera up with the POINT's list position (:2326) --, uv[i], level[i] the
+        predicted level.  matched = vpMatched as map point ids per keypoint (-1 = NULL), updated.  Candidate descriptors are read
+        the way the reference does (contiguous id as per-camera row; MCS_RULE_SCW) and keypoint 0 can never be matched (:2385)."""
+        if matched is None:
+            matched = np.full(len(KF.keys), -1, np.int32)
+        sel = np.flatnonzero(np.asarray(valid) != 0)
+        lv = np.asarray(level)[sel]
+        q = _queries(np.asarray(query_cam)[sel], np.asarray(uv)[sel, 0], np.asarray(uv)[sel, 1], th * KF.scale_factors[lv], lv - 1, lv, sel)
+        return search_windows(KF, q, mp_desc, mp_dmask if self.havingMasks else None, sel, RULE_SCW, self.mfNNratio, self.TH_LOW_,
+                              matched)
+
+    def _project_for_fuse(self, KF, rig, Ow, world_pos, min_dist, max_dist, idx, float_dist):
+        """projection front-end shared by the Fuse overloads and SearchByProjection(KF, Scw): WorldToCamHom_fast ->
+        isPointInMirrorMask -> distance range -> predicted level (ref :1288-1318)"""
+        nc = len(rig.cams)
+        uv = np.zeros((len(idx), nc, 2)); ok = np.zeros((len(idx), nc), np.uint8); lvl = np.zeros((len(idx), nc), np.int32)
+        for k, i in enumerate(idx):
+            p = world_pos[i]
+            for c in range(nc):
+                u, v, _ = rig.world_to_cam(c, p)
+                if not rig.in_mirror_mask(c, u, v):
+                    continue
+                po = p - Ow
+                d = float(np.sqrt(po[0] * po[0] + po[1] * po[1] + po[2] * po[2]))
+                if float_dist:
+                    d = float(np.float32(d))                      # `const float dist3D = cv::norm(PO);` (ref :1301, :1472)
+                if d < min_dist[i] or d > max_dist[i]:
+                    continue
+                uv[k, c] = (u, v); ok[k, c] = 1
+                lvl[k, c] = _predict_level(KF.scale_factors, d / min_dist[i])
+        return uv, ok, lvl
+
+    def Fuse(self, KF, rig, kf_mp, points, world_pos, min_dist, max_dist, bad, in_kf, mp_desc, mp_dmask=None, th=2.5, variant=1,
+             Scw=None, cur_rays=None, kf_rays=None, cur_rig=None, _sw=None):
+        """The three Fuse overloads of the reference as whole entry points (projection on the host with the reference's double
+        arithmetic, window search + distances on the GPU, map bookkeeping replayed in order):
+          variant 0  Fuse(pKF, curKF, vpMapPoints, th)  (ref :1265-1418): points[i] is the map point of keypoint i of curKF; a hit
+                     on an occupied keypoint needs the epipolar check of the two bearing rays (cur_rays, kf_rays, cur_rig)
+          variant 1  Fuse(pKF, vpMapPoints, th)         (ref :1420-1568): distance discarded, first in-level candidate wins
+          variant 2  Fuse(pKF, Scw, vpPoints, th)       (ref :1570-1719): the rig pose is replaced by the Sim3's rigid part
+        kf_mp [n_keys] map point id per keypoint (-1 none), updated like pKF->AddMapPoint does; points: candidate map point ids
+        (-1 = NULL); bad / in_kf (IsInKeyFrame(pKF)) per map point.  Returns (nFused, ops) with ops rows (0, mp, keypoint) =
+        AddObservation + AddMapPoint and (1, mp, other) = Replace(other), in the reference's call order."""
+        sw = search_windows if _sw is None else _sw
+        kf_mp = np.ascontiguousarray(kf_mp, np.int32).copy()
+        world_pos = np.asarray(world_pos, np.float64)
+        if variant == 2:
+            S = np.asarray(Scw, np.float64)
+            sR = S[:3, :3]
+            inv_s = 1.0 / float(np.sqrt(sR[0, 0] * sR[0, 0] + sR[0, 1] * sR[0, 1] + sR[0, 2] * sR[0, 2]))
+            T = np.eye(4)
+            T[:3, :3], T[:3, 3] = inv_s * sR, inv_s * S[:3, 3]
+            rig = Rig(rig.cams, rig.M_c, inv_rigid(T))            # camSys.Set_M_t(invMat(Rt2Hom(Rcw, tcw)))  (ref :1576-1584)
+            already = set(int(m) for m in kf_mp if m >= 0 and not bad[m])
+            idx = [int(i) for i in points if not bad[i] and int(i) not in already]
+        else:
+            idx = [int(i) for i in points if i >= 0 and not bad[i] and not in_kf[i]]
+        Ow = rig.M_t[:3, 3].copy()
+        uv, ok, lvl = self._project_for_fuse(KF, rig, Ow, world_pos, min_dist, max_dist, idx, float_dist=(variant != 2))
+        k, c = np.nonzero(ok)
+        lv = lvl[k, c]
+        q = _queries(c, uv[k, c, 0], uv[k, c, 1], th * KF.scale_factors[lv], lv - 1, lv, np.asarray(idx, np.int64)[k])
+        n, res = sw(KF, q, mp_desc, mp_dmask if self.havingMasks else None, np.zeros(len(q), np.int32),
+                    RULE_FIRST_FREE if variant == 1 else RULE_BEST_FREE, self.mfNNratio, self.TH_LOW_,
+                    np.full(max(len(q), len(KF.keys)), -1, np.int32))
+        best = np.full(ok.shape, -1, np.int32)
+        best[k, c] = res[:len(q)]
+        ops, fused = [], 0
+        pos_of = {}
+        if variant == 0:
+            pos_of = {int(i): j for j, i in enumerate(points) if i >= 0}     # keypoint of curKF that carries map point i
+        for kk, i in enumerate(idx):
+            for cam in range(ok.shape[1]):
+                b = int(best[kk, cam])
+                if b < 0:
+                    continue
+                other = int(kf_mp[b])
+                if other >= 0:
+                    good = not bad[other]
+                    if variant == 0 and good:
+                        T1 = inv_rigid(cur_rig.MtMc[cam]) if cur_rig is not None else np.eye(4)
+                        E = compute_E_rel(_mm(T1, rig.MtMc[cam]))
+                        good = check_epipolar(cur_rays[pos_of[i]], kf_rays[b], E, 1e-2)
+                    if good:
+                        ops.append((1, i, other)); fused += 1
+                else:
+                    ops.append((0, i, b)); kf_mp[b] = i
+        return fused, np.asarray(ops, np.int32).reshape(-1, 3), kf_mp
+
+    def SearchByProjectionKFScw(self, KF, rig, Scw, points, matched, world_pos, min_dist, max_dist, bad, mp_desc, mp_dmask=None, th=10,
+                                _sw=None):
+        """SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) (ref :2265-2392) as a whole entry point, quirks included: the
+        camera of entry iMP of vpPoints is keypoint_to_cam[iMP] (:2326), candidate descriptors are read with the contiguous id as
+        per-camera row (:2367, :2372) and keypoint 0 is never matched (:2385).  points: map point ids (-1 = NULL), len <= n_keys;
+        matched: vpMatched as map point ids per keypoint (-1 = NULL).  Returns (nmatches, vpMatched)."""
+        sw = search_windows if _sw is None else _sw
+        S = np.asarray(Scw, np.float64)
+        sR = S[:3, :3]
+        inv_s = 1.0 / float(np.sqrt(sR[0, 0] * sR[0, 0] + sR[0, 1] * sR[0, 1] + sR[0, 2] * sR[0, 2]))
+        T = np.eye(4)
+        T[:3, :3], T[:3, 3] = inv_s * sR, inv_s * S[:3, 3]
+        rig = Rig(rig.cams, rig.M_c, inv_rigid(T))
+        Ow = rig.M_t[:3, 3].copy()
+        matched = np.ascontiguousarray(matched, np.int32).copy()
+        found = set(int(m) for m in matched if m >= 0)
+        world_pos = np.asarray(world_pos, np.float64)
+        qc, quv, qlv, qi = [], [], [], []
+        for iMP, i in enumerate(points):
+            i = int(i)
+            if i < 0 or bad[i] or i in found:
+                continue
+            cam = int(KF.key_cam[iMP])
+            u, v, _ = rig.world_to_cam(cam, world_pos[i])
+            if not rig.in_mirror_mask(cam, u, v):
+                continue
+            po = world_pos[i] - Ow
+            d = float(np.sqrt(po[0] * po[0] + po[1] * po[1] + po[2] * po[2]))
+            if d < min_dist[i] or d > max_dist[i]:
+                continue
+            qc.append(cam); quv.append((u, v)); qlv.append(_predict_level(KF.scale_factors, d / min_dist[i])); qi.append(i)
+        if not qi:
+            return 0, matched
+        lv = np.asarray(qlv)
+        quv = np.asarray(quv)
+        q = _queries(np.asarray(qc), quv[:, 0], quv[:, 1], float(int(th)) * KF.scale_factors[lv], lv - 1, lv, np.asarray(qi))
+        return sw(KF, q, mp_desc, mp_dmask if self.havingMasks else None, np.asarray(qi, np.int32), RULE_SCW, self.mfNNratio,
+                  self.TH_LOW_, matched)
 
     def SearchForTriangulationRaw(self, desc1, mask1, cam1, free1, rays1, desc2, mask2, cam2, free2, rays2, E, epi_thresh=1e-2):
         """SearchForTriangulationRaw(KF1, KF2, ...) (ref :968-1156): free1/free2 flag keypoints WITHOUT a map point, rays = bearing

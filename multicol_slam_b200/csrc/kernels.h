@@ -46,6 +46,10 @@ struct WindowFrameDev {
     const int* cell_start;                                  // [n_cams*64*48 + 1] CSR over (cam, ix, iy)
     const int* cell_items;                                  // [n_in_grid] keypoint ids, ascending inside a cell
     const double* winv; const double* hinv;                 // [n_cams]
+    // MCS_RULE_SCW only: [n_cams + 1] first contiguous keypoint id of every camera.  When set, candidate `id` of a query of
+    // camera c is compared through descriptor row cam_first[c] + id -- the reference indexes camera c's matrix with the
+    // contiguous id (src/cORBmatcher.cpp:2367,2372) -- and dropped when that row lies beyond the camera's own rows.
+    const int* cam_first = nullptr;
 };
 cudaError_t launch_window_search(const WindowFrameDev& f, const mcs_window_query* q, int nq, const uint8_t* qdesc,
                                  const uint8_t* qmask, int max_cand, int* cand_idx, int* cand_dist, int* cand_count,

@@ -357,14 +357,19 @@ window_search_kernel(const WindowFrameDev f, const mcs_window_query* __restrict_
                         // abs(kp.pt.x - x) > r with float - double -> double (ref :328)
                         if (ok) ok = !(fabs((double)f.kx[id] - x) > r || fabs((double)f.ky[id] - y) > r);
                     }
+                    int row = id;
+                    if (f.cam_first) {           // SearchByProjection(KF, Scw): contiguous id used as the row of camera `cam`
+                        row = f.cam_first[cam] + id;
+                        ok = ok && row < f.cam_first[cam + 1];
+                    }
                     const unsigned m = __ballot_sync(0xffffffffu, ok);
                     if (ok) {
                         const int pos = count + __popc(m & ((1u << lane) - 1u));
                         if (pos < max_cand) {
-                            const uint32_t* dd = (const uint32_t*)f.desc + (size_t)id * WORDS;
+                            const uint32_t* dd = (const uint32_t*)f.desc + (size_t)row * WORDS;
                             unsigned dist = 0;
                             if (MASKED) {
-                                const uint32_t* mm = (const uint32_t*)f.dmask + (size_t)id * WORDS;
+                                const uint32_t* mm = (const uint32_t*)f.dmask + (size_t)row * WORDS;
 #pragma unroll
                                 for (int k = 0; k < WORDS; ++k) {
                                     const uint32_t xw = qw[k] ^ dd[k];

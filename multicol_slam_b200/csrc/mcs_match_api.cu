@@ -36,7 +36,7 @@ inline int cv_round(double v) { return (int)lrint(v); }
 
 // frame uploaded for window searches
 struct FrameDev {
-    Dev kx, ky, koct, desc, dmask, cell_start, cell_items, winv, hinv;
+    Dev kx, ky, koct, desc, dmask, cell_start, cell_items, winv, hinv, cam_first;
     WindowFrameDev view;
 };
 
@@ -432,7 +432,7 @@ int mcs_search_windows(const mcs_frame_view* f, const mcs_window_query* queries,
                        const uint8_t* qmask, const int32_t* query_tag, int32_t rule, double nnratio, int32_t threshold,
                        int32_t* assigned, int32_t* nmatches) {
     if (!f || !queries || !qdesc || !query_tag || !assigned || !nmatches) return mfail(MCS_ERR_INVALID, "null argument");
-    if (rule < 0 || rule > 3) return mfail(MCS_ERR_INVALID, "unknown rule");
+    if (rule < 0 || rule > MCS_RULE_SCW) return mfail(MCS_ERR_INVALID, "unknown rule");
     *nmatches = 0;
     if (nq <= 0) return MCS_OK;
     int rows = 0;
@@ -445,6 +445,19 @@ int mcs_search_windows(const mcs_frame_view* f, const mcs_window_query* queries,
     FrameDev fd;
     int rc = upload_frame(f, fd, nullptr);
     if (rc) return rc;
+    if (rule == MCS_RULE_SCW) {
+        // descriptor row of candidate idx for a query of camera c = row idx of camera c's matrix (ref :2367,2372): needs the
+        // camera-major keypoint order of src/cMultiFrame.cpp:168-184
+        std::vector<int> first(f->n_cams + 1, 0);
+        for (int i = 0; i < f->n_keys; ++i) {
+            if (i && f->key_cam[i] < f->key_cam[i - 1]) return mfail(MCS_ERR_INVALID, "MCS_RULE_SCW needs camera-major keypoint order");
+            ++first[f->key_cam[i] + 1];
+        }
+        for (int c = 0; c < f->n_cams; ++c) first[c + 1] += first[c];
+        MCK(fd.cam_first.alloc(first.size() * 4));
+        MCK(cudaMemcpy(fd.cam_first.p, first.data(), first.size() * 4, cudaMemcpyHostToDevice));
+        fd.view.cam_first = fd.cam_first.as<int>();
+    }
     std::vector<mcs_window_query> qs(queries, queries + nq);
     std::vector<int> ci, cd, cc;
     int mc = 32;
@@ -453,11 +466,19 @@ int mcs_search_windows(const mcs_frame_view* f, const mcs_window_query* queries,
     int nm = 0;
     for (int qi = 0; qi < nq; ++qi) {       // sequential greedy replay over the GPU-computed candidate lists
         const int n = cc[qi];
-        if (n == 0) { if (rule == MCS_RULE_BEST_FREE) assigned[qi] = -1; continue; }
+        const bool stateless = rule == MCS_RULE_BEST_FREE || rule == MCS_RULE_FIRST_FREE;
+        if (n == 0) { if (stateless) assigned[qi] = -1; continue; }
+        if (rule == MCS_RULE_FIRST_FREE) {
+            // Fuse(pKF, vpMapPoints, th) computes the distance and throws it away (ref :1506-1514: `dist` stays 0), so the first
+            // candidate that passes the level filter wins with distance 0 <= TH_LOW_
+            assigned[qi] = 0 <= threshold ? ci[(size_t)qi * mc] : -1;
+            nm += assigned[qi] >= 0;
+            continue;
+        }
         int bestDist = INT_MAX, bestLevel = -1, bestDist2 = INT_MAX, bestLevel2 = -1, bestIdx = -1;
         for (int k = 0; k < n; ++k) {
             const int idx = ci[(size_t)qi * mc + k];
-            if (rule != MCS_RULE_BEST_FREE && assigned[idx] >= 0) continue;
+            if (!stateless && assigned[idx] >= 0) continue;
             const int dist = cd[(size_t)qi * mc + k];
             if (dist < bestDist) {
                 bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel;
@@ -475,6 +496,7 @@ int mcs_search_windows(const mcs_frame_view* f, const mcs_window_query* queries,
         bool ok;
         if (rule == MCS_RULE_RATIO) ok = (double)bestDist <= (double)bestDist2 * nnratio && bestDist <= threshold;
         else if (rule == MCS_RULE_BEST) ok = bestDist <= threshold;
+        else if (rule == MCS_RULE_SCW) ok = bestDist <= threshold && bestIdx > 0;          // `bestIdx > 0` as written at ref :2385
         else ok = bestDist <= threshold && !(bestLevel == bestLevel2 && bestDist > nnratio * bestDist2);
         if (ok && bestIdx >= 0) {
             assigned[bestIdx] = query_tag[qi];

@@ -1105,13 +1105,31 @@ int mcso_search_windows(const mcs_frame_view* f, const mcs_window_query* qs, int
     for (int i = 0; i < nq; ++i) {
         const mcs_window_query& q = qs[i];
         features_in_area(*f, g, q.cam, q.x, q.y, q.r, q.min_level, q.max_level, near);
-        if (near.empty()) { if (rule == 3) assigned[i] = -1; continue; }
+        const bool stateless = rule == 3 || rule == 4;
+        if (near.empty()) { if (stateless) assigned[i] = -1; continue; }
+        if (rule == 4) {   // Fuse(pKF, vpMapPoints, th) :1420-1568: the distance is computed and discarded (:1506-1514), dist stays 0
+            assigned[i] = 0 <= threshold ? near[0] : -1;
+            nm += assigned[i] >= 0;
+            continue;
+        }
+        int cam_first = 0, cam_end = f->n_keys;          // rule 5: rows of camera q.cam in the contiguous order
+        if (rule == 5) {
+            cam_first = 0;
+            while (cam_first < f->n_keys && f->key_cam[cam_first] != q.cam) ++cam_first;
+            cam_end = cam_first;
+            while (cam_end < f->n_keys && f->key_cam[cam_end] == q.cam) ++cam_end;
+        }
         int bestDist = INT_MAX, bestLevel = -1, bestDist2 = INT_MAX, bestLevel2 = -1, bestIdx = -1;
         for (int idx : near) {
-            if (rule != 3 && assigned[idx] >= 0) continue;
-            const int dist = masks ? dist64m(row64(qdesc, q.desc_index, f->dim), row64(f->desc, idx, f->dim),
-                                             row64(qmask, q.desc_index, f->dim), row64(f->dmask, idx, f->dim), f->dim)
-                                   : dist64(row64(qdesc, q.desc_index, f->dim), row64(f->desc, idx, f->dim), f->dim);
+            if (!stateless && assigned[idx] >= 0) continue;
+            int row = idx;
+            if (rule == 5) {   // SearchByProjection(pKF, Scw, ...) :2367,2372: GetDescriptorRowPtr(camIdx, idx) with the CONTIGUOUS idx
+                row = cam_first + idx;
+                if (row >= cam_end) continue;            // the reference reads past camera camIdx's matrix here (undefined): dropped
+            }
+            const int dist = masks ? dist64m(row64(qdesc, q.desc_index, f->dim), row64(f->desc, row, f->dim),
+                                             row64(qmask, q.desc_index, f->dim), row64(f->dmask, row, f->dim), f->dim)
+                                   : dist64(row64(qdesc, q.desc_index, f->dim), row64(f->desc, row, f->dim), f->dim);
             if (dist < bestDist) {
                 bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel; bestLevel = f->keys[idx].octave; bestIdx = idx;
             } else if (dist < bestDist2) {
@@ -1127,6 +1145,7 @@ int mcso_search_windows(const mcs_frame_view* f, const mcs_window_query* qs, int
         bool ok;
         if (rule == 0) ok = bestDist <= bestDist2 * nnratio && bestDist <= threshold;
         else if (rule == 1) ok = bestDist <= threshold;
+        else if (rule == 5) ok = bestDist <= threshold && bestIdx > 0;      // :2385
         else ok = bestDist <= threshold && !(bestLevel == bestLevel2 && bestDist > nnratio * bestDist2);
         if (ok && bestIdx >= 0) { assigned[bestIdx] = query_tag[i]; ++nm; }
     }

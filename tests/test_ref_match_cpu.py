@@ -22,6 +22,12 @@ def rm():
 
 
 @pytest.fixture(scope="module")
+def api():
+    import multicol_slam_b200.api as a            # holders and host-side compositions only; no device call is made in this file
+    return a
+
+
+@pytest.fixture(scope="module")
 def frames(oa, cams):
     """two consecutive 3-camera frames of the sliding-texture stream, extracted by the CPU oracle"""
     import multicol_slam_b200.api as api            # plain array holders only; no device call is made in this file
@@ -149,3 +155,112 @@ def test_check_orientation_constant():
     """every call site passes the compile-time constant checkOrientation == false (include/cORBmatcher.h:40): the wrapper does too"""
     txt = (ROOT / "oracle" / "ref_mcs" / "wrap_match.cpp").read_text()
     assert txt.count("checkOrientation") >= 10
+
+
+# ---- scenes with 3-D map points for the projection-based searches ---------------------------------------------------------------
+def make_scene(api, oa, cams, frame, seed, npts=500, pose_noise=0.0):
+    """A key frame = `frame` on a 3-camera rig, and map points that really project near its keypoints: each point sits on the
+    bearing ray of a keypoint at a random depth; descriptor = that keypoint's with a few flipped bits."""
+    rng = np.random.default_rng(seed)
+    nc = 3
+    M_c = np.tile(np.eye(4), (nc, 1, 1))
+    for c in range(nc):                                            # cameras looking 120 degrees apart, 10 cm off the rig centre
+        a = 2 * np.pi * c / nc
+        M_c[c, :3, :3] = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+        M_c[c, :3, 3] = [0.1 * np.sin(a), 0.0, 0.1 * np.cos(a)]
+    M_t = np.eye(4)
+    M_t[:3, 3] = [0.3, -0.2, 0.1]
+    rig = api.Rig(cams, M_c, M_t)
+    rays, _, _ = oa.frame_prepare(frame.keys, frame.key_cam, cams)
+    src = rng.choice(len(frame.keys), npts, replace=False)
+    depth = rng.uniform(2.0, 6.0, npts)
+    world = np.zeros((npts, 3))
+    for i, k in enumerate(src):
+        pc = np.append(rays[k] * depth[i], 1.0)
+        world[i] = api._mm(rig.MtMc[int(frame.key_cam[k])], pc)[:3] + rng.normal(0, pose_noise, 3)
+    desc = flip_bits(rng, frame.desc[src], 30)
+    dmask = frame.dmask[src].copy()
+    bad = (rng.random(npts) < 0.05).astype(np.uint8)
+    min_d, max_d = depth * rng.uniform(0.5, 0.9, npts), depth * rng.uniform(1.2, 3.0, npts)
+    return dict(rig=rig, M_c=M_c, M_t=M_t, rays=rays, src=src, world=world, desc=desc, dmask=dmask, bad=bad, min_d=min_d, max_d=max_d)
+
+
+@pytest.mark.parametrize("masks", [False, True])
+@pytest.mark.parametrize("variant", [1, 2])
+def test_fuse_equals_reference(oa, rm, api, frames, cams, masks, variant):
+    """Fuse(pKF, vpMapPoints, th) -- the live overload whose distance is discarded -- and Fuse(pKF, Scw, vpPoints, th): the host
+    composition over the oracle's window search reproduces the reference's map mutations in order"""
+    KF = frames[0]
+    sc = make_scene(api, oa, cams, KF, 11 + variant)
+    rng = np.random.default_rng(5)
+    n = len(sc["world"])
+    kf_mp = np.full(len(KF.keys), -1, np.int32)                    # a third of the key frame's keypoints already carry a (fresh) map point
+    occupied = rng.choice(len(KF.keys), len(KF.keys) // 3, replace=False)
+    extra_bad = (rng.random(len(occupied)) < 0.1).astype(np.uint8)
+    kf_mp[occupied] = n + np.arange(len(occupied))
+    bad = np.concatenate([sc["bad"], extra_bad])
+    in_kf = np.concatenate([(rng.random(n) < 0.1), np.ones(len(occupied), bool)])
+    obs_kf = np.where(in_kf, 0, -1).astype(np.int32)
+    tot = n + len(occupied)
+    pad = lambda a, fill=0.0: np.concatenate([a, np.full((len(occupied),) + a.shape[1:], fill, a.dtype)])
+    table = rm.MPTable(3, pad(sc["desc"]), dmask=pad(sc["dmask"]), bad=bad, world_pos=pad(sc["world"]), min_dist=pad(sc["min_d"], 1.0),
+                       max_dist=pad(sc["max_d"], 2.0), obs_kf=obs_kf, obs_idx=np.zeros(tot, np.int32))
+    points = np.arange(n, dtype=np.int32)
+    Scw = None
+    if variant == 2:
+        s = 1.3
+        Tcw = api.inv_rigid(sc["M_t"])
+        Scw = Tcw.copy()
+        Scw[:3, :3] *= s
+        Scw[:3, 3] *= s
+    kfr = rm.KF(KF, cams, M_c=sc["M_c"], M_t=sc["M_t"], mp=kf_mp, rays=sc["rays"])
+    rn, rops = rm.fuse(variant, kfr, table, points, 2.5, 0.6, masks, Scw=Scw)
+    m = api.cORBmatcher(0.6, False, 32, masks)
+    on, oops, _ = m.Fuse(KF, sc["rig"], kf_mp, points, pad(sc["world"]), pad(sc["min_d"], 1.0), pad(sc["max_d"], 2.0), bad, in_kf,
+                         pad(sc["desc"]), pad(sc["dmask"]), th=2.5, variant=variant, Scw=Scw, _sw=oa.search_windows)
+    assert rn == on and np.array_equal(rops, oops)
+    assert len(rops) > 100 and (rops[:, 0] == 1).sum() > 10 and (rops[:, 0] == 0).sum() > 10
+
+
+def test_fuse_1420_ignores_the_distance(oa, rm, api, frames, cams):
+    """the reference's Fuse(pKF, vpMapPoints, th) returns the same mutations whatever the map point descriptors are"""
+    KF = frames[0]
+    sc = make_scene(api, oa, cams, KF, 21)
+    n = len(sc["world"])
+    kf_mp = np.full(len(KF.keys), -1, np.int32)
+    out = []
+    for desc in (sc["desc"], 255 - sc["desc"]):
+        table = rm.MPTable(3, desc, dmask=sc["dmask"], bad=sc["bad"], world_pos=sc["world"], min_dist=sc["min_d"], max_dist=sc["max_d"])
+        out.append(rm.fuse(1, rm.KF(KF, cams, M_c=sc["M_c"], M_t=sc["M_t"], mp=kf_mp), table, np.arange(n, dtype=np.int32), 2.5, 0.6, False))
+    assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1]) and len(out[0][1]) > 100
+
+
+@pytest.mark.parametrize("masks", [False, True])
+def test_search_by_projection_scw_equals_reference(oa, rm, api, frames, cams, masks):
+    """SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) with its quirks (camera looked up with the list position, contiguous id
+    as descriptor row, bestIdx > 0).  The scene keeps every candidate inside the range where the reference's reads are defined:
+    all keypoints of the key frame belong to camera 0 (contiguous id == row)."""
+    import multicol_slam_b200.api as apimod
+    F = frames[0]
+    sel = np.flatnonzero(F.key_cam == 0)
+    KF = apimod.Frame(F.keys[sel], F.key_cam[sel], F.desc[sel], F.dmask[sel], SIZES, F.scale_factors)
+    sc = make_scene(api, oa, cams, KF, 31, npts=len(sel) - 5)
+    n = len(sc["world"])
+    # vpPoints entry iMP projects near keypoint src[iMP]; put point 3 at keypoint 0 so that the `bestIdx > 0` rule is exercised
+    points = np.arange(n, dtype=np.int32)
+    rng = np.random.default_rng(8)
+    points[rng.random(n) < 0.05] = -1
+    matched = np.full(len(KF.keys), -1, np.int32)
+    pre = rng.choice(len(KF.keys), 30, replace=False)
+    matched[pre] = rng.choice(n, 30, replace=False)
+    Tcw = api.inv_rigid(sc["M_t"])
+    Scw = Tcw.copy()
+    Scw[:3, :3] *= 0.8
+    Scw[:3, 3] *= 0.8
+    table = rm.MPTable(3, sc["desc"], dmask=sc["dmask"], bad=sc["bad"], world_pos=sc["world"], min_dist=sc["min_d"], max_dist=sc["max_d"])
+    rn, rmatched = rm.search_by_projection_scw(rm.KF(KF, cams, M_c=sc["M_c"], M_t=sc["M_t"]), table, Scw, points, matched, 10, 0.6, masks)
+    m = api.cORBmatcher(0.6, False, 32, masks)
+    on, omatched = m.SearchByProjectionKFScw(KF, sc["rig"], Scw, points, matched, sc["world"], sc["min_d"], sc["max_d"], sc["bad"],
+                                             sc["desc"], sc["dmask"], th=10, _sw=oa.search_windows)
+    assert rn == on and np.array_equal(rmatched, omatched) and rn > 50
+    assert omatched[0] == matched[0]                               # keypoint 0 is never assigned (:2385)
