@@ -200,6 +200,12 @@ class mdBRIEFextractorOct:
     def set_profiling(self, enable=True):
         _check(lib().mcs_extractor_set_profiling(self._h, int(enable)))
 
+    def tier_stats(self, enable=True):
+        """K3 diagnostics: (tier1, tier2, tier3) pattern counts since counting was switched on; enable/disable counting"""
+        out = np.zeros(3, np.int64)
+        _check(lib().mcs_extractor_tier_stats(self._h, int(enable), _p(out)))
+        return out
+
     def get_timings(self):
         """(K1 pyramid+blur+FAST all levels, K2 octree, K3 describe) of the last extract call, milliseconds."""
         ms = (C.c_float * 3)()

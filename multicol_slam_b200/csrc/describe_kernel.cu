@@ -15,14 +15,23 @@
 // atan + a 12-term Horner in double (~250 FP64 instructions; 1536 points per mdBRIEF keypoint).  Because the
 // third coordinate is the per-camera constant z = -a0, u = x*g(r)*c + y*g(r)*d + u0 with
 //     g(r) = R(r) / r,   R(r) = rho(atan(-z / r)),      r = sqrt(x^2 + y^2),
-// and R is a smooth 1-D function of r ("the distortion baked into a LUT" of the north star; g itself is not
-// tabulated because the fitted inverse polynomial leaves a tiny rho(-pi/2) != 0, i.e. a 1/r pole).  The host
-// tabulates R per camera as degree-5 polynomials on 1-px intervals fitted in long double (error < 1e-13 px, the
-// rounding noise of the reference's own double evaluation); the device evaluates rsqrt + 5 FMA + the affine map.
-// Only cvRound(u - mean) has to agree with the reference; a projected coordinate closer than 1e-7 px to a
-// rounding tie (p ~ 2e-4 per pattern) makes the warp recompute that pattern with the reference's exact
-// operation sequence (cam_model.cuh).  Radii outside the table take the exact path as well.
+// and R is a smooth 1-D function of r ("the distortion baked into a LUT" of the north star).  Only
+// cvRound(u - mean(u)) has to agree with the reference, so a pattern is evaluated by the cheapest of three tiers
+// whose error bound still decides every rounding:
+//   tier 1 (fp32, ~96 % of the patterns): everything RELATIVE to the keypoint.  With X_k the undistorted keypoint, r_k its
+//     radius and d the rotated pattern offset (|d| <= 21.3), n = r^2 - r_k^2 = 2 X_k.d + |d|^2 and delta = n / (r + r_k) carry
+//     the radius change without cancellation; the host tabulates, per camera and integer radius i, a degree-6 polynomial
+//     of R(i + s) - R(i) (double constant + float coefficients), from which g(r) - g(r_k) = (R(r) - R(r_k) - g_k delta) / r;
+//     then u - u_k = A [ g(r) d + (g(r) - g(r_k)) X_k ] with the affine part A.  All quantities are O(20 px), so fp32
+//     (ulp 1.9e-6 at 16..32) is enough: measured worst error 5e-6 px (tools/k3_fp32_model.py, numpy without FMA).  A pattern
+//     with any coordinate closer than kT1Guard = 2.5e-5 px to a rounding tie (or a sample outside the staged patch) falls
+//     through to tier 2;
+//   tier 2 (FP64, degree-9 polynomial of R around the keypoint's radius, |error| < 2e-8 px, two rolled passes: sum, then
+//     recompute + round): decides everything farther than 5e-7 px from a tie; also serves keypoints closer than
+//     kT1MinRadius px to the distortion centre, where g has a pole;
+//   tier 3 (exact): the reference's own operation sequence (cam_model.cuh), p ~ 2e-4 per pattern.
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "cam_model.cuh"
@@ -66,13 +75,16 @@ constexpr int kDescWarps = 4;
 constexpr int kPatchR = 25;                       // staged patch: rows/cols ky/kx -25 .. +25 (keypoints are >= 25 px inside the ROI)
 constexpr int kPatchS = 64;                       // bytes per staged patch row (4-byte aligned start + 51 columns)
 constexpr int kLutDeg = 9;                        // degree of the per-centre polynomial of R(r)  (kernels.h: DistortLut)
-#ifndef MCS_K3_HALVES
-#define MCS_K3_HALVES 0
-#endif
 #ifndef MCS_K3_MINB
-#define MCS_K3_MINB 4                // resident CTAs per SM the register budget is cut for (128 registers)
+#define MCS_K3_MINB 5                // resident CTAs per SM the register budget is cut for
 #endif
-constexpr int kLutStride = 12;                    // doubles per centre: tau offset, tau scale, kLutDeg + 1 coefficients
+constexpr int kT1Coef = 6;                        // tier 1: q(s') of degree 5, R(i + s) - R(i) = s' q(s'), s' = s / kT1Scale
+constexpr float kT1Scale = 32.f;
+constexpr double kT1MinRadius = 40.0;             // tier 1 needs r >= r_k - 21.3 well away from the pole of g at r = 0
+constexpr float kT1Guard = 2.5e-5f;               // px; 5x the worst tier-1 error measured by tools/k3_fp32_model.py
+// doubles per centre: [0] tau offset, [1] tau scale, [2..11] kLutDeg + 1 coefficients (tier 2);
+// [12] R(i), [13] q0 (double), [14..16] q1..q5 as floats (+ one pad float), [17] 1.0 when the tier-1 entry is usable
+constexpr int kLutStride = 18;
 constexpr double kLutReach = 22.5;                // half-width of a centre's interval: pattern radius 15*sqrt(2) + 0.5 + margin
 
 // Rare path: one pattern of one keypoint with the reference's exact operation sequence (two projection passes;
@@ -134,6 +146,94 @@ __device__ __noinline__ unsigned orb_pattern_global(const char2* s_pat, double c
     return out;
 }
 
+// Tier 2: one pattern through the per-keypoint degree-9 polynomial of R(r) in double (error < 2e-8 px).  Two rolled passes --
+// sum of the projected coordinates, then recompute + subtract the mean + round + sample -- so that the live set stays small;
+// the recomputation is the same instruction sequence, hence the same values.  Sets *need_exact when a coordinate lies within
+// 5e-7 px of a rounding tie, outside the fitted interval or outside the staged patch (tier 3 then decides).
+struct Tier2Poly { double t_off, t_scale, P[kLutDeg + 1]; };
+__device__ __forceinline__ void tier2_point(const Tier2Poly& L, const mcs_ocam& cam, const double2 pp, double ca, double sa, double ukx,
+                                            double uky, double& u, double& v, int& worst_tau) {
+    const double xr = fma(pp.x, ca, fma(-pp.y, sa, ukx));
+    const double yr = fma(pp.x, sa, fma(pp.y, ca, uky));
+    const double s2 = fma(xr, xr, yr * yr);
+    // 1/sqrt(s2): hardware approximation (~1e-7) + one third-order step -> < 1e-16 relative
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(s2));
+    const double e = fma(-(s2 * y0), y0, 1.0);
+    const double rinv = fma(y0 * e, fma(0.375, e, 0.5), y0), r = s2 * rinv;
+    // R(r) by Horner; |tau| > 1 (a point outside the fitted interval, or NaN from s2 == 0) is caught by the caller
+    const double tau = fma(r, L.t_scale, L.t_off);
+    double gg = L.P[kLutDeg];
+#pragma unroll
+    for (int k = kLutDeg - 1; k >= 0; --k) gg = fma(gg, tau, L.P[k]);
+    worst_tau = max(worst_tau, __double2hiint(tau) & 0x7fffffff);
+    gg *= rinv;
+    const double uu = xr * gg, vv = yr * gg;
+    u = fma(uu, cam.c, fma(vv, cam.d, cam.u0));
+    v = fma(uu, cam.e, vv + cam.v0);
+}
+template <int PPL>
+__device__ __noinline__ unsigned tier2_pattern(const mcs_ocam* camp, const double2* s_patd, const double* __restrict__ row, double ca,
+                                               double sa, double ukx, double uky, int lane, int ds, const uint8_t* patch, int pofs,
+                                               int* need_exact) {
+    const mcs_ocam& cam = *camp;
+    Tier2Poly L;
+    {
+        const double2* cp = (const double2*)row;
+        const double2 h = __ldg(cp);
+        L.t_off = h.x; L.t_scale = h.y;
+#pragma unroll
+        for (int k = 0; k < (kLutDeg + 1) / 2; ++k) {
+            const double2 cc = __ldg(cp + 1 + k);
+            L.P[2 * k] = cc.x; L.P[2 * k + 1] = cc.y;
+        }
+    }
+    const bool lane_valid = (PPL == 32) || (lane < ds);      // descSize 16: lanes 16..31 own no byte
+    double su = 0.0, sv = 0.0;
+    int worst_tau = 0;
+#pragma unroll 2
+    for (int j = 0; j < PPL; ++j) {
+        double u, v;
+        tier2_point(L, cam, s_patd[j * 32 + lane], ca, sa, ukx, uky, u, v, worst_tau);
+        if (lane_valid) { su += u; sv += v; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        su += __shfl_xor_sync(0xffffffffu, su, o);
+        sv += __shfl_xor_sync(0xffffffffu, sv, o);
+    }
+    const double inv_n = 1.0 / (double)(16 * ds);
+    const double mu = su * inv_n, mv = sv * inv_n;
+    // round-to-nearest-even through the 1.5*2^52 trick: no F2I/I2F (XU pipe), same result as lrint
+    constexpr double kMagic = 6755399441055744.0;
+    int worst_frac = 0;
+    unsigned worst_ofs = 0, out = 0;
+#pragma unroll 1
+    for (int j = 0; j < PPL; j += 2) {
+        int smp[2];
+#pragma unroll
+        for (int e2 = 0; e2 < 2; ++e2) {
+            double u, v;
+            tier2_point(L, cam, s_patd[(j + e2) * 32 + lane], ca, sa, ukx, uky, u, v, worst_tau);
+            const double du = u - mu, dv = v - mv;
+            const double tu = du + kMagic, tv = dv + kMagic;
+            int ix = __double2loint(tu), iy = __double2loint(tv);
+            // closeness to a rounding tie as integer maxima: the high word of |frac| orders like the double itself
+            const int hu = __double2hiint(du - (tu - kMagic)) & 0x7fffffff, hv = __double2hiint(dv - (tv - kMagic)) & 0x7fffffff;
+            worst_frac = max(worst_frac, max(hu, hv));
+            worst_ofs = max(worst_ofs, max((unsigned)(ix + kPatchR), (unsigned)(iy + kPatchR)));
+            ix = min(max(ix, -kPatchR), kPatchR); iy = min(max(iy, -kPatchR), kPatchR);      // stay inside the patch; redone if it mattered
+            smp[e2] = patch[pofs + iy * kPatchS + ix];
+        }
+        out |= (unsigned)(smp[0] < smp[1]) << (j >> 1);
+    }
+    // closer than ~7e-7 px to a rounding tie (high word of 0.5 - 5e-7), outside the fitted interval (|tau| >= 1; a NaN has a
+    // huge high word) or outside the staged patch -> exact path
+    if (lane_valid && (worst_frac >= __double2hiint(0.5 - 5e-7) || worst_ofs > 2u * kPatchR || worst_tau >= __double2hiint(1.0)))
+        *need_exact = 1;
+    return out;
+}
+
 template <int PPL /* pattern points per lane: 16 for descSize <= 32, 32 for descSize 64 */, int MINB = MCS_K3_MINB>
 __global__ void __launch_bounds__(kDescWarps * 32, MINB)
 describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, const mcs_ocam* __restrict__ cams,
@@ -144,9 +244,7 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
     __shared__ char2 s_pat[PPL * 32];            // [j][lane] : point 16*byte + k with byte = lane + 32*(j/16), k = j%16
     __shared__ __align__(16) double2 s_patd[PPL * 32];   // same, as doubles (int->double conversions run on the slow XU pipe)
     __shared__ mcs_ocam s_cam[kDescWarps];
-#if MCS_K3_HALVES
-    __shared__ int2 s_park[kDescWarps][PPL == 16 ? PPL * 32 : 1];    // projected coordinates of the current pattern, [point][lane]
-#endif
+    __shared__ __align__(8) float2 s_patf[PPL * 32];      // same, as floats (tier 1)
     __shared__ __align__(16) uint8_t s_patch[kDescWarps][(2 * kPatchR + 1) * kPatchS];
     const int ds = geom->desc_size;
     for (int i = threadIdx.x; i < PPL * 32; i += blockDim.x) {
@@ -154,6 +252,7 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
         const int byte = ln + 32 * (j >> 4), pt = 16 * byte + (j & 15);
         s_pat[i] = byte < ds ? make_char2(c_pairs[2 * pt], c_pairs[2 * pt + 1]) : make_char2(0, 0);
         s_patd[i] = make_double2((double)s_pat[i].x, (double)s_pat[i].y);
+        s_patf[i] = make_float2((float)s_pat[i].x, (float)s_pat[i].y);
     }
     __syncthreads();
 
@@ -297,187 +396,117 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
         const DistortLut lut = luts[ci];
         double ukx, uky;   // undistortPointsOcam(pt.x*scale, pt.y*scale, a0)  (ref :1306-1317)
         cam_undistort(cam, (double)__fmul_rn((float)kx, scale), (double)__fmul_rn((float)ky, scale), cam.pol[0], ukx, uky);
-        // R(r) around this keypoint: one degree-9 polynomial in tau = (r - m)/hw, valid for every pattern point
-        // (|r - rk| <= 21.3), picked by the keypoint's own undistorted radius; the coefficients live in registers
+        // the table row of this keypoint: centre i = rn(r_k); its polynomials are valid for every pattern point (|r - r_k| <= 21.3)
         const double rk = sqrt(ukx * ukx + uky * uky);
         const bool have_lut = rk < (double)(lut.n - 1);           // false for NaN as well -> exact path
-        double P[kLutDeg + 1], t_off, t_scale;
-        {
-            const double2* cp = (const double2*)(lut.coef + (size_t)(have_lut ? __double2int_rn(rk) : 0) * kLutStride);
-            const double2 h = __ldg(cp);
-            t_off = h.x; t_scale = h.y;
-#pragma unroll
-            for (int k = 0; k < (kLutDeg + 1) / 2; ++k) {
-                const double2 cc = __ldg(cp + 1 + k);
-                P[2 * k] = cc.x; P[2 * k + 1] = cc.y;
-            }
-        }
-        const double inv_n = 1.0 / (double)(16 * ds);
+        const int ci_lut = have_lut ? __double2int_rn(rk) : 0;
+        const double* row = lut.coef + (size_t)ci_lut * kLutStride;
         const bool lane_valid = (PPL == 32) || (lane < ds);      // descSize 16: lanes 16..31 own no byte
-        for (int q = 0; q < npat; ++q) {
-#if MCS_K3_HALVES
-            if constexpr (PPL == 16) {
-            // Variant (compile-time, not the default): the 16 (32) points of a lane are processed in groups of 8.
-            // Pass 1 projects a group and parks its coordinates -- relative to the keypoint's own pixel, as 24-bit fixed point: the
-            // low word of (x + 1.5*2^28) is rn(x * 2^24) for |x| < 128 -- in shared memory; pass 2 reads them back, subtracts the
-            // mean, rounds, and does the bit tests of the group.  Live set and code size are half of the unrolled 16-point form.
-            // Error budget: two roundings of 2^-25 px + polynomial (< 2e-8) << the 4.8e-7 px tie guard (16 units below).
-            constexpr double kMagicF = 402653184.0;
-            constexpr int GRP = 8;
-            int2* park = s_park[wib];
-            double su = 0.0, sv = 0.0;
-            bool need_exact = false;
-            int worst_tau = 0, worst_rng = 0;          // high words of max |tau| and of max |relative coordinate|
-            const double du0 = cam.u0 - (double)__fmul_rn((float)kx, scale), dv0 = cam.v0 - (double)__fmul_rn((float)ky, scale);
-#pragma unroll 1
-            for (int g0 = 0; g0 < PPL; g0 += GRP) {
+        // ---- tier-1 set-up (per keypoint, all lanes redundantly; ~25 FP64 instructions against 48 points x 3 patterns) ----
+        bool t1 = have_lut && rk >= kT1MinRadius && __ldg(row + 17) == 1.0;
+        float q[kT1Coef], K0f = 0.f, gkf = 0.f, s0f = 0.f, ukxf = 0.f, ukyf = 0.f, rk2f = 0.f, rkf = 0.f;
+        float ac = 0.f, ad = 0.f, ae = 0.f, ukx2f = 0.f, uky2f = 0.f;
+        if (t1) {
+            const double Ri = __ldg(row + 12), q0d = __ldg(row + 13);
+            const float2 c12 = __ldg((const float2*)(row + 14)), c34 = __ldg((const float2*)(row + 15)), c5x = __ldg((const float2*)(row + 16));
+            q[1] = c12.x; q[2] = c12.y; q[3] = c34.x; q[4] = c34.y; q[5] = c5x.x;
+            const double s0 = (rk - (double)ci_lut) * (1.0 / (double)kT1Scale);          // in units of s'
+            double pk = (double)q[5];
+            pk = fma(pk, s0, (double)q[4]); pk = fma(pk, s0, (double)q[3]); pk = fma(pk, s0, (double)q[2]);
+            pk = fma(pk, s0, (double)q[1]); pk = fma(pk, s0, q0d);
+            const double dRk = s0 * pk;                            // R(r_k) - R(i)
+            const double gk = (Ri + dRk) / rk;                     // g(r_k)
+            // h(s') = s' q'(s') - K0' = R(r) - R(r_k) - g_k (r - r_k):  q'_0 = q_0 - g_k*scale,  K0' = dRk - g_k (r_k - i)
+            q[0] = (float)(q0d - gk * (double)kT1Scale);
+            K0f = (float)(dRk - gk * (rk - (double)ci_lut));
+            gkf = (float)gk; s0f = (float)s0;
+            ukxf = (float)ukx; ukyf = (float)uky; rk2f = (float)(rk * rk); rkf = (float)rk;
+            ukx2f = 2.f * ukxf; uky2f = 2.f * ukyf;
+            ac = (float)cam.c; ad = (float)cam.d; ae = (float)cam.e;
+        }
+        for (int qi = 0; qi < npat; ++qi) {
+            bool done = false;
+            if (t1) {
+                // ---- tier 1: fp32, relative to the keypoint (see the header) ----
+                const float caf = (float)ca[qi], saf = (float)sa[qi];
+                float du[PPL], dv[PPL];
+                float su = 0.f, sv = 0.f;
 #pragma unroll
-                for (int jj = 0; jj < GRP; ++jj) {
-                    const int j = g0 + jj;
-                    const double2 pp = s_patd[j * 32 + lane];
-                    const double xr = fma(pp.x, ca[q], fma(-pp.y, sa[q], ukx));
-                    const double yr = fma(pp.x, sa[q], fma(pp.y, ca[q], uky));
-                    const double s2 = fma(xr, xr, yr * yr);
-                    double y0;
-                    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(s2));
-                    const double e = fma(-(s2 * y0), y0, 1.0);
-                    const double rinv = fma(y0 * e, fma(0.375, e, 0.5), y0), r = s2 * rinv;
-                    const double tau = fma(r, t_scale, t_off);
-                    double gg = P[kLutDeg];
+                for (int j = 0; j < PPL; ++j) {
+                    const float2 pp = s_patf[j * 32 + lane];
+                    const float dx = fmaf(pp.x, caf, -pp.y * saf), dy = fmaf(pp.x, saf, pp.y * caf);
+                    // n = r^2 - r_k^2 = 2 X_k.d + |d|^2
+                    const float n = fmaf(dx, dx + ukx2f, dy * (dy + uky2f));
+                    const float r2 = rk2f + n;
+                    float y, z;
+                    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(r2));   // MUFU + one Newton step each: ~1 ulp
+                    y = fmaf(0.5f * y, fmaf(-r2 * y, y, 1.f), y);              // 1 / r
+                    const float w = fmaf(r2, y, rkf);                          // r + r_k
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(z) : "f"(w));
+                    z = fmaf(z, fmaf(-w, z, 1.f), z);
+                    const float delta = n * z;                                 // r - r_k without cancellation
+                    const float sp = fmaf(delta, 1.f / kT1Scale, s0f);
+                    float pl = q[5];
+                    pl = fmaf(pl, sp, q[4]); pl = fmaf(pl, sp, q[3]); pl = fmaf(pl, sp, q[2]);
+                    pl = fmaf(pl, sp, q[1]); pl = fmaf(pl, sp, q[0]);
+                    const float dg = fmaf(sp, pl, -K0f) * y;                   // g(r) - g(r_k)
+                    const float g = gkf + dg;
+                    const float ex = fmaf(g, dx, dg * ukxf), ey = fmaf(g, dy, dg * ukyf);
+                    du[j] = fmaf(ac, ex, ad * ey);                             // u - u_k
+                    dv[j] = fmaf(ae, ex, ey);                                  // v - v_k
+                    if (lane_valid) { su += du[j]; sv += dv[j]; }
+                }
+                // mean over the 16*ds points: lane partial sums in fp32 (16..32 terms), the warp reduction in double
+                double sud = (double)su, svd = (double)sv;
 #pragma unroll
-                    for (int k = kLutDeg - 1; k >= 0; --k) gg = fma(gg, tau, P[k]);
-                    worst_tau = max(worst_tau, __double2hiint(tau) & 0x7fffffff);
-                    gg *= rinv;
-                    const double uu = xr * gg, vv = yr * gg;
-                    const double ur = fma(uu, cam.c, fma(vv, cam.d, du0));
-                    const double vr = fma(uu, cam.e, vv + dv0);
-                    if (lane_valid) { su += ur; sv += vr; }
-                    worst_rng = max(worst_rng, max(__double2hiint(ur) & 0x7fffffff, __double2hiint(vr) & 0x7fffffff));
-                    park[j * 32 + lane] = make_int2(__double2loint(ur + kMagicF), __double2loint(vr + kMagicF));
+                for (int o = 16; o; o >>= 1) {
+                    sud += __shfl_xor_sync(0xffffffffu, sud, o);
+                    svd += __shfl_xor_sync(0xffffffffu, svd, o);
+                }
+                const double inv_n = 1.0 / (double)(16 * ds);
+                const float mu = (float)(sud * inv_n), mv = (float)(svd * inv_n);
+                constexpr float kMagicF = 12582912.f;                          // 1.5 * 2^23: t + magic rounds t to the nearest even integer
+                bool flag = false;
+                unsigned bits[BPL];
+#pragma unroll
+                for (int bb = 0; bb < BPL; ++bb) bits[bb] = 0;
+#pragma unroll
+                for (int j = 0; j < PPL; j += 2) {
+                    int smp[2];
+#pragma unroll
+                    for (int e2 = 0; e2 < 2; ++e2) {
+                        const float tu = du[j + e2] - mu, tv = dv[j + e2] - mv;
+                        const float mu_r = tu + kMagicF, mv_r = tv + kMagicF;
+                        const float fu = tu - (mu_r - kMagicF), fv = tv - (mv_r - kMagicF);
+                        // near a rounding tie, or outside the staged patch (also catches NaN: the comparisons are written so that NaN flags)
+                        flag |= !(fabsf(fu) < 0.5f - kT1Guard) | !(fabsf(fv) < 0.5f - kT1Guard) | !(fabsf(tu) < (float)kPatchR + 0.4f) |
+                                !(fabsf(tv) < (float)kPatchR + 0.4f);
+                        int ix = __float_as_int(mu_r) - 0x4B400000, iy = __float_as_int(mv_r) - 0x4B400000;
+                        ix = min(max(ix, -kPatchR), kPatchR); iy = min(max(iy, -kPatchR), kPatchR);
+                        smp[e2] = patch[pofs + iy * kPatchS + ix];
+                    }
+                    bits[j >> 4] |= (unsigned)(smp[0] < smp[1]) << ((j & 15) >> 1);
+                }
+                if (!__any_sync(0xffffffffu, flag && lane_valid)) {
+#pragma unroll
+                    for (int bb = 0; bb < BPL; ++bb) val[qi][bb] = bits[bb];
+                    done = true;
+                    if (args.tier_stats && lane == 0) atomicAdd(args.tier_stats, 1ull);
                 }
             }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                su += __shfl_xor_sync(0xffffffffu, su, o);
-                sv += __shfl_xor_sync(0xffffffffu, sv, o);
-            }
-            // every |ur|, |vr| < 32 (checked below) -> |mean| < 32: the differences below stay far inside 32 bits.
-            // t = (x - mean) * 2^24 + 2^23 + 8: t >> 24 is rn(x - mean) unless the low 24 bits are < 16, i.e. x - mean lies
-            // within 8 * 2^-24 = 4.8e-7 px of a rounding tie (then the exact path decides).
-            const int cu = __double2loint(su * inv_n + kMagicF) - ((1 << 23) + 8), cv = __double2loint(sv * inv_n + kMagicF) - ((1 << 23) + 8);
-            unsigned worst_tie = 0xFFFFFFFFu, worst_ofs = 0;
-            unsigned bits[BPL];
-#pragma unroll
-            for (int bb = 0; bb < BPL; ++bb) bits[bb] = 0;
-#pragma unroll 1
-            for (int g0 = 0; g0 < PPL; g0 += GRP) {
-                int ix[GRP], iy[GRP];
-#pragma unroll
-                for (int jj = 0; jj < GRP; ++jj) {
-                    const int2 f = park[(g0 + jj) * 32 + lane];     // this lane's own slot: no synchronisation needed
-                    const int tu = f.x - cu, tv = f.y - cv;
-                    worst_tie = min(worst_tie, min((unsigned)tu & 0xFFFFFFu, (unsigned)tv & 0xFFFFFFu));
-                    ix[jj] = tu >> 24; iy[jj] = tv >> 24;
-                    worst_ofs = max(worst_ofs, max((unsigned)(ix[jj] + kPatchR), (unsigned)(iy[jj] + kPatchR)));
-                    // keep the gathers inside the staged patch even when this pattern is going to be redone exactly
-                    ix[jj] = min(max(ix[jj], -kPatchR), kPatchR); iy[jj] = min(max(iy[jj], -kPatchR), kPatchR);
+            if (!done) {
+                // ---- tier 2 (FP64 polynomial), then tier 3 (exact) where tier 2 cannot decide ----
+                unsigned e = 0;
+                int need_exact = have_lut ? 0 : 1;
+                if (have_lut) e = tier2_pattern<PPL>(&cam, s_patd, row, ca[qi], sa[qi], ukx, uky, lane, ds, patch, pofs, &need_exact);
+                const bool exact = __any_sync(0xffffffffu, need_exact != 0);
+                if (exact) {
+                    const double aq = qi == 0 ? a_base : (qi == 1 ? a_base + a_rot : a_base - a_rot);
+                    e = exact_pattern<PPL>(&cam, s_pat, cos(aq), sin(aq), ukx, uky, lane, ds, bimg, uimg, &g, kx, ky);
                 }
-                unsigned v = 0;
+                if (args.tier_stats && lane == 0) atomicAdd(args.tier_stats + (exact ? 2 : 1), 1ull);
 #pragma unroll
-                for (int bit = 0; bit < GRP / 2; ++bit) {
-                    const int s0 = patch[pofs + iy[2 * bit] * kPatchS + ix[2 * bit]], s1 = patch[pofs + iy[2 * bit + 1] * kPatchS + ix[2 * bit + 1]];
-                    v |= (unsigned)(s0 < s1) << bit;
-                }
-                // group g0 holds bits (g0 % 16) / 2 .. +3 of byte g0 / 16
-                if (BPL == 1) bits[0] |= v << ((g0 & 15) >> 1);
-                else { if (g0 < 16) bits[0] |= v << ((g0 & 15) >> 1); else bits[BPL - 1] |= v << ((g0 & 15) >> 1); }
-            }
-            need_exact |= !have_lut || (lane_valid && (worst_tie < 16u || worst_ofs > 2u * kPatchR || worst_rng >= __double2hiint(32.0) ||
-                                                       worst_tau >= __double2hiint(1.0)));
-            if (__any_sync(0xffffffffu, need_exact)) {
-                const double aq = q == 0 ? a_base : (q == 1 ? a_base + a_rot : a_base - a_rot);
-                const unsigned e = exact_pattern<PPL>(&cam, s_pat, cos(aq), sin(aq), ukx, uky, lane, ds, bimg, uimg, &g, kx, ky);
-#pragma unroll
-                for (int bb = 0; bb < BPL; ++bb) val[q][bb] = (e >> (8 * bb)) & 0xFFu;
-                continue;
-            }
-#pragma unroll
-            for (int bb = 0; bb < BPL; ++bb) val[q][bb] = bits[bb];
-            } else
-#endif
-            {
-            double us[PPL], vs[PPL];
-            double su = 0.0, sv = 0.0;
-            bool need_exact = false;
-            int worst_tau = 0;                         // high word of max |tau|
-            // round-to-nearest-even through the 1.5*2^52 trick: no F2I/I2F (XU pipe), same result as lrint
-            constexpr double kMagic = 6755399441055744.0;
-#pragma unroll
-            for (int j = 0; j < PPL; ++j) {
-                const double2 pp = s_patd[j * 32 + lane];
-                const double xr = fma(pp.x, ca[q], fma(-pp.y, sa[q], ukx));
-                const double yr = fma(pp.x, sa[q], fma(pp.y, ca[q], uky));
-                const double s2 = fma(xr, xr, yr * yr);
-                // 1/sqrt(s2): hardware approximation (~1e-7) + one third-order step -> < 1e-16 relative
-                double y0;
-                asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(s2));
-                const double e = fma(-(s2 * y0), y0, 1.0);
-                const double rinv = fma(y0 * e, fma(0.375, e, 0.5), y0), r = s2 * rinv;
-                // R(r) by Horner; |tau| > 1 (a point outside the fitted interval, or NaN from s2 == 0) is caught below
-                const double tau = fma(r, t_scale, t_off);
-                double gg = P[kLutDeg];
-#pragma unroll
-                for (int k = kLutDeg - 1; k >= 0; --k) gg = fma(gg, tau, P[k]);
-                worst_tau = max(worst_tau, __double2hiint(tau) & 0x7fffffff);
-                gg *= rinv;
-                const double uu = xr * gg, vv = yr * gg;
-                us[j] = fma(uu, cam.c, fma(vv, cam.d, cam.u0));
-                vs[j] = fma(uu, cam.e, vv + cam.v0);
-                if (lane_valid) { su += us[j]; sv += vs[j]; }
-            }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                su += __shfl_xor_sync(0xffffffffu, su, o);
-                sv += __shfl_xor_sync(0xffffffffu, sv, o);
-            }
-            const double mu = su * inv_n, mv = sv * inv_n;
-            int ix[PPL], iy[PPL];
-            // Closeness to a rounding tie and the patch range are tracked as integer maxima: the high word of |frac|
-            // orders like the double itself (non-negative), a NaN / huge value has a larger high word than any fraction.
-            int worst_frac = 0;
-            unsigned worst_ofs = 0;
-#pragma unroll
-            for (int j = 0; j < PPL; ++j) {
-                const double du = us[j] - mu, dv = vs[j] - mv;
-                const double tu = du + kMagic, tv = dv + kMagic;
-                ix[j] = __double2loint(tu); iy[j] = __double2loint(tv);
-                const int hu = __double2hiint(du - (tu - kMagic)) & 0x7fffffff, hv = __double2hiint(dv - (tv - kMagic)) & 0x7fffffff;
-                worst_frac = max(worst_frac, max(hu, hv));
-                worst_ofs = max(worst_ofs, max((unsigned)(ix[j] + kPatchR), (unsigned)(iy[j] + kPatchR)));
-            }
-            // closer than ~7e-7 px to a rounding tie (high word of 0.5 - 5e-7), or outside the staged patch -> exact path
-            // (inside the table window |u| is bounded by the fitted polynomial, so the magic-number rounding cannot alias;
-            //  a NaN shows up as a huge high word of the fraction)
-            need_exact |= !have_lut || (lane_valid && (worst_frac >= __double2hiint(0.5 - 5e-7) || worst_ofs > 2u * kPatchR ||
-                                                       worst_tau >= __double2hiint(1.0)));
-            if (__any_sync(0xffffffffu, need_exact)) {
-                const double aq = q == 0 ? a_base : (q == 1 ? a_base + a_rot : a_base - a_rot);
-                const unsigned e = exact_pattern<PPL>(&cam, s_pat, cos(aq), sin(aq), ukx, uky, lane, ds, bimg, uimg, &g, kx, ky);
-#pragma unroll
-                for (int bb = 0; bb < BPL; ++bb) val[q][bb] = (e >> (8 * bb)) & 0xFFu;
-                continue;
-            }
-#pragma unroll
-            for (int bb = 0; bb < BPL; ++bb) {
-                unsigned v = 0;
-#pragma unroll
-                for (int bit = 0; bit < 8; ++bit) {
-                    const int j0 = 16 * bb + 2 * bit;
-                    const int s0 = patch[pofs + iy[j0] * kPatchS + ix[j0]], s1 = patch[pofs + iy[j0 + 1] * kPatchS + ix[j0 + 1]];
-                    v |= (unsigned)(s0 < s1) << bit;
-                }
-                val[q][bb] = v;
-            }
+                for (int bb = 0; bb < BPL; ++bb) val[qi][bb] = (e >> (8 * bb)) & 0xFFu;
             }
         }
     }
@@ -579,7 +608,50 @@ void build_distort_lut(const mcs_ocam& cam, std::vector<double>& coef, int& n_ou
             worst = std::max(worst, (double)fabsl((long double)gv - R_exact((long double)r)));
         }
         if (!(worst < 2e-8))
-            for (int t = 0; t < kLutStride; ++t) e[t] = std::nan("");
+            for (int t = 0; t < 12; ++t) e[t] = std::nan("");
+        // ---- tier-1 entry: R(i + s) - R(i) = s' q(s'), s' = s / kT1Scale, q of degree kT1Coef - 1 interpolating at an even
+        // number of Chebyshev nodes of [-reach, reach] (no node at s = 0); enabled where the whole window keeps clear of r = 0
+        e[17] = 0.0;
+        if ((double)i >= kT1MinRadius - 1.0 && worst < 2e-8) {
+            constexpr int NQ = kT1Coef;
+            const long double Ri = R_exact((long double)i);
+            long double B[NQ][NQ + 1];
+            for (int k = 0; k < NQ; ++k) {
+                const long double sn = (long double)kLutReach * cosl((2 * k + 1) * 3.14159265358979323846264338327950288L / (2.0L * NQ));
+                const long double sp = sn / (long double)kT1Scale;
+                long double pw = 1.0L;
+                for (int t = 0; t < NQ; ++t) { B[k][t] = pw; pw *= sp; }
+                B[k][NQ] = (R_exact((long double)i + sn) - Ri) / sp;
+            }
+            for (int col = 0; col < NQ; ++col) {
+                int piv = col;
+                for (int r2 = col + 1; r2 < NQ; ++r2) if (fabsl(B[r2][col]) > fabsl(B[piv][col])) piv = r2;
+                for (int t = 0; t <= NQ; ++t) std::swap(B[col][t], B[piv][t]);
+                for (int r2 = 0; r2 < NQ; ++r2) {
+                    if (r2 == col) continue;
+                    const long double f = B[r2][col] / B[col][col];
+                    for (int t = col; t <= NQ; ++t) B[r2][t] -= f * B[col][t];
+                }
+            }
+            float qf[NQ + 1] = {0};
+            for (int t = 1; t < NQ; ++t) qf[t] = (float)(B[t][NQ] / B[t][t]);
+            const double q0 = (double)(B[0][NQ] / B[0][0]);
+            // fit error with the coefficients as the kernel holds them (q0 double, q1.. float), evaluated in long double
+            long double werr = 0.0L;
+            for (int sidx = 0; sidx <= 64; ++sidx) {
+                const long double sv = -(long double)kLutReach + 2.0L * (long double)kLutReach * ((long double)sidx + 0.37L) / 65.0L;
+                const long double sp = sv / (long double)kT1Scale;
+                long double pv = (long double)qf[NQ - 1];
+                for (int t = NQ - 2; t >= 1; --t) pv = pv * sp + (long double)qf[t];
+                pv = pv * sp + (long double)q0;
+                werr = std::max(werr, fabsl(sp * pv - (R_exact((long double)i + sv) - Ri)));
+            }
+            if (werr < 2e-7L) {                        // well below the fp32 evaluation noise the tie guard accounts for
+                e[12] = (double)Ri; e[13] = q0;
+                std::memcpy(&e[14], &qf[1], sizeof(float) * 6);      // q1..q5 + one zero pad float
+                e[17] = 1.0;
+            }
+        }
     }
 }
 

@@ -9,6 +9,7 @@ namespace mcs {
 struct DescribeArgs {
     const uint8_t* lvl[kMaxLevels];
     const uint8_t* blur[kMaxLevels];
+    unsigned long long* tier_stats = nullptr;   // diagnostics (mcs_extractor_tier_stats): patterns decided by tier 1 / 2 / 3 of K3
 };
 
 cudaError_t upload_constants(const signed char* pairs, const signed char* du, const signed char* dv);

@@ -105,6 +105,8 @@ struct mcs_extractor {
     DevBuf<double> lut_coef;
     DevBuf<DistortLut> luts;
     bool profiling = false;
+    bool tier_on = false;
+    DevBuf<unsigned long long> tier;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -321,6 +323,7 @@ int run_pipeline(mcs_extractor* ex, int n_images, const uint8_t* images_dev, int
     if (ex->profiling) CK(cudaEventRecord(ex->ev[2], st));
     DescribeArgs a;
     for (int l = 0; l < kMaxLevels; ++l) { a.lvl[l] = ex->lvl[l].p; a.blur[l] = ex->blur[l].p; }
+    a.tier_stats = ex->tier_on ? ex->tier.p : nullptr;
     CK(launch_describe(G, ex->G_dev.p, n_images, a, ex->cams.p, ex->luts.p, coi_d, ex->sel_xys.p, ex->sel_count.p,
                        kps_dev, desc_dev, dmask_dev, counts_dev, capacity, st));
     if (ex->profiling) CK(cudaEventRecord(ex->ev[3], st));
@@ -474,7 +477,7 @@ void mcs_extractor_destroy(mcs_extractor* ex) {
     ex->masks.release(); ex->cams.release(); ex->cam_of_image.release(); ex->coi_all.release(); ex->raw.release(); ex->node_of.release();
     ex->raw_count.release(); ex->sel_count.release(); ex->status.release(); ex->counts.release(); ex->sel_xys.release();
     ex->kps.release(); ex->desc.release(); ex->dmask.release();
-    ex->match_idx.release(); ex->match_dist.release(); ex->lut_coef.release(); ex->luts.release();
+    ex->match_idx.release(); ex->match_dist.release(); ex->lut_coef.release(); ex->luts.release(); ex->tier.release();
     for (int i = 0; i < 4; ++i) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
     ex->in_tight.release();
     if (ex->s_copy) cudaStreamDestroy(ex->s_copy);
@@ -623,6 +626,22 @@ int mcs_extractor_set_profiling(mcs_extractor* ex, int32_t enable) {
     CK(cudaSetDevice(ex->device));
     if (enable) for (int i = 0; i < 4; ++i) if (!ex->ev[i]) CK(cudaEventCreate(&ex->ev[i]));
     ex->profiling = enable != 0;
+    return MCS_OK;
+}
+
+int mcs_extractor_tier_stats(mcs_extractor* ex, int32_t enable, int64_t* counts3) {
+    if (!ex) return fail(MCS_ERR_INVALID, "null extractor");
+    CK(cudaSetDevice(ex->device));
+    CK(cudaDeviceSynchronize());
+    if (counts3) {
+        counts3[0] = counts3[1] = counts3[2] = 0;
+        if (ex->tier_on) CK(cudaMemcpy(counts3, ex->tier.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    }
+    if (enable && !ex->tier_on) {
+        CK(ex->tier.ensure(4));
+        CK(cudaMemset(ex->tier.p, 0, 4 * sizeof(unsigned long long)));
+    }
+    ex->tier_on = enable != 0;
     return MCS_OK;
 }
 

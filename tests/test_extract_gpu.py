@@ -228,3 +228,20 @@ def test_odd_sizes_batch(api, oa, cams):
             n = counts[i]
             assert n == len(ok) and kps[i, :n].tobytes() == ok.tobytes()
             assert np.array_equal(desc[i, :n], od) and np.array_equal(dmask[i, :n], om)
+
+
+def test_k3_tier_statistics(api, oa, cams):
+    """K3 evaluates the distorted patterns in three tiers (fp32 relative to the keypoint / FP64 polynomial / exact): the result is
+    bit-exact whatever tier decides (checked against the oracle here), and the cheap tier must carry almost all of the load"""
+    from multicol_slam_b200 import synth
+    cam = cams[1]
+    img, mask = synth.frame(cam, 123), synth.mirror_mask(cam)
+    ex = api.mdBRIEFextractorOct(nfeatures=2000, do_dBrief=True, learnMasks=True)
+    ex.tier_stats(True)
+    k, d, m = ex(img, mask, cam)
+    t = ex.tier_stats(False)
+    ok, od, om = oa.OracleExtractor(nfeatures=2000, do_dbrief=True, learn_masks=True).extract(img, mask, cam)
+    assert k.tobytes() == ok.tobytes() and np.array_equal(d, od) and np.array_equal(m, om)
+    assert t.sum() == 3 * len(k)
+    print("K3 tiers (fp32, fp64 polynomial, exact):", t.tolist(), t / t.sum())
+    assert t[0] > 0.85 * t.sum() and t[2] < 0.01 * t.sum()

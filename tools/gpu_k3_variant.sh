@@ -1,15 +1,18 @@
-# one GPU-box visit: baseline parity + bench, then the same with a K3 variant build (MCS_B200_LIB)
-VAR=${1:-multicol_slam_b200/libmcs_b200_k3h.so}
+# one GPU-box visit: parity (all GPU tests) + bench with the default build, then extractor parity + bench for every variant library given
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/gpu_tests.log 2>&1; tail -2 gpurun_out/gpu_tests.log
+timeout 120 python -m pytest tests/test_extract_gpu.py -m gpu -q -k tier -s 2>&1 | grep "K3 tiers"
 timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/bench_base.json 2> gpurun_out/bench_base.err
-MCS_B200_LIB=$PWD/$VAR timeout 600 python -m pytest tests/test_extract_gpu.py -m gpu -x -q > gpurun_out/gpu_tests_var.log 2>&1; tail -2 gpurun_out/gpu_tests_var.log
-MCS_B200_LIB=$PWD/$VAR timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/bench_var.json 2> gpurun_out/bench_var.err
-python - <<'PY'
-import json
-for n in ("base", "var"):
+for VAR in "$@"; do
+  N=$(basename $VAR .so)
+  MCS_B200_LIB=$PWD/$VAR timeout 600 python -m pytest tests/test_extract_gpu.py tests/test_ref_pin_gpu.py -m gpu -x -q > gpurun_out/gpu_tests_$N.log 2>&1; tail -1 gpurun_out/gpu_tests_$N.log
+  MCS_B200_LIB=$PWD/$VAR timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$N.json 2> gpurun_out/bench_$N.err
+done
+python - "$@" <<'PY'
+import json, sys, os
+for n in ["base"] + [os.path.basename(v)[:-3] for v in sys.argv[1:]]:
     try:
         j = json.loads(open(f"gpurun_out/bench_{n}.json").read().strip().splitlines()[-1])
-        print(n, j["value"], j["e2e"]["value"], j["ms_per_step"], j["roofline"]["stage_ms"])
+        print(n, round(j["value"], 2), round(j["e2e"]["value"], 2), round(j["ms_per_step"], 3), {k: round(v, 3) for k, v in j["roofline"]["stage_ms"].items()})
     except Exception as e:
         print(n, "failed", e)
 PY
