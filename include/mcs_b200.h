@@ -394,10 +394,35 @@ int  mcs_search_by_bow(const uint8_t* desc1, const uint8_t* mask1, const uint8_t
                        const int32_t* fv2_nodes, const int32_t* fv2_offsets, int32_t n_fv2, const int32_t* fv2_features,
                        int32_t dim, int32_t th_low, double nnratio, int32_t* match_of_2, int32_t* nmatches);
 
-/* ---- packed per-camera slot for the multi-GPU allgather ----------------------- */
-/* Slot layout (bytes): int32 n; int32 pad[3]; mcs_keypoint kp[capacity];
- * uint8 desc[capacity*dim]; uint8 dmask[capacity*dim].  Size below. */
-size_t mcs_slot_bytes(int32_t capacity, int32_t dim);
+/* ---- multi-GPU: one camera (or stream chunk) per GPU, ONE allgather of the packed feature buffer -------------- */
+/* Packed feature buffer of a batch of n_images images: the four output arrays of the batched extractor in one allocation,
+ *   [ counts int32[n_images] | mcs_keypoint[n_images][capacity] | desc u8[n_images][capacity][dim] | dmask u8[n_images][capacity][dim] ]
+ * every section on a 256-byte boundary.  offsets4 (may be NULL) receives the four byte offsets; returns the total size.  It is
+ * the only layout that travels between GPUs: K3 writes it in place, the allgather moves it, the matchers read it in place. */
+size_t mcs_packed_layout(int32_t n_images, int32_t capacity, int32_t dim, size_t* offsets4);
+size_t mcs_slot_bytes(int32_t capacity, int32_t dim);     /* == mcs_packed_layout(1, capacity, dim, NULL): one camera of a rig */
+
+/* mcs_extract_batch_device with the four outputs laid out as above inside packed_dev (device memory, mcs_packed_layout bytes). */
+int  mcs_extract_batch_packed_device(mcs_extractor* ex, int32_t n_images,
+                                     const uint8_t* images_dev, int32_t width, int32_t height, int32_t stride,
+                                     const uint8_t* masks, const mcs_ocam* cams, int32_t n_cams, const int32_t* cam_of_image,
+                                     void* packed_dev, int32_t capacity, void* stream);
+
+/* Communicator of the rig's GPUs: one process per GPU.  Rank 0 draws the 128-byte rendezvous token (ncclGetUniqueId) and the host
+ * program hands it to the other ranks by whatever it already has (MPI, torch.distributed, a socket); every rank then calls
+ * mcs_comm_create on its current CUDA device (collective; ncclCommInitRank).  NCCL is loaded at run time: the copy the process
+ * already carries (e.g. PyTorch's) or the system libnccl.so.2; MCS_ERR_UNSUPPORTED when there is none. */
+typedef struct mcs_comm mcs_comm;
+int  mcs_comm_unique_id(uint8_t* id128);
+int  mcs_comm_create(const uint8_t* id128, int32_t rank, int32_t world, mcs_comm** out);
+void mcs_comm_destroy(mcs_comm* comm);
+int  mcs_comm_info(const mcs_comm* comm, int32_t* rank, int32_t* world, int32_t* nccl_version);
+
+/* The single exchange of the path, the device-side counterpart of cMultiFrame's camera-order concatenation (ref
+ * src/cMultiFrame.cpp:168-184): every rank contributes its packed buffer (`bytes` identical on all ranks) and receives
+ * world * bytes in rank order in gathered_dev.  One ncclAllGather on `stream` (a cudaStream_t as void*), asynchronous: issue it
+ * right behind the extraction on the same stream, or on a second stream behind an event to overlap it with the next batch. */
+int  mcs_allgather_features(mcs_comm* comm, const void* packed_dev, size_t bytes, void* gathered_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -102,6 +102,9 @@ struct mcs_extractor {
     // distortion tables, rebuilt when the camera set changes
     std::vector<mcs_ocam> lut_cams;
     std::vector<uint8_t> masks_host;    // what ex->masks holds
+    std::vector<int16_t> h_mx[kMaxLevels], h_my[kMaxLevels];   // host copies of the level -> level-0 mask coordinate maps
+    DevBuf<uint8_t> tile_flags;         // [n_cams][tiles_total]: the K1 tile holds a pixel inside the camera's mask
+    bool tile_flags_valid = false;
     DevBuf<double> lut_coef;
     DevBuf<DistortLut> luts;
     bool profiling = false;
@@ -173,6 +176,21 @@ int build_geometry(mcs_extractor* ex, int W, int H, int in_stride) {
             for (int y = 0; y < g.h; ++y) { yofs[y] = (int16_t)y; yb0[y] = 2048; yb1[y] = 0; my[y] = (int16_t)y; }
         }
         pmx = mx; pmy = my;
+        ex->h_mx[l] = mx; ex->h_my[l] = my;
+        {   // staged source region of the widest / tallest tile (same index arithmetic as pyr_fast_kernel): the TMA box of the level
+            int bw = 16, bh = 1;
+            for (int tx = 0; tx < g.tiles_x; ++tx) {
+                const int xa = std::max(tx * kTW - kHalo, 0), xb = std::min(tx * kTW + kTW + kHalo, g.w) - 1;
+                const int lo = xofs[xa] & ~15, hi = std::min(xofs[xb] + 1, g.sw - 1);
+                bw = std::max(bw, hi - lo + 1);
+            }
+            for (int ty = 0; ty < g.tiles_y; ++ty) {
+                const int ya = std::max(ty * kTH - kHalo, 0), yb = std::min(ty * kTH + kTH + kHalo, g.h) - 1;
+                const int lo = std::min(std::max((int)yofs[ya], 0), g.sh - 1), hi = std::min(std::max(yofs[yb] + 1, 0), g.sh - 1);
+                bh = std::max(bh, hi - lo + 1);
+            }
+            g.box_w = (bw + 15) & ~15; g.box_h = bh;
+        }
         // FAST cell grid (ref :876-949)
         std::vector<int16_t> cellx(g.w, -1), celly(g.h, -1);
         const int minB = kEdge - 3, maxBX = g.w - kEdge + 3, maxBY = g.h - kEdge + 3;
@@ -209,6 +227,9 @@ int build_geometry(mcs_extractor* ex, int W, int H, int in_stride) {
         off[l] = {put(xofs), put(xa0), put(xa1), put(yofs), put(yb0), put(yb1), put(cellx), put(celly), put(mx), put(my)};
     }
     G.sel_total = sel_off; G.raw_total = raw_off; G.cap = ex->capacity;
+    G.tiles_total = 0;
+    for (int l = 0; l < L; ++l) { G.lv[l].tile_off = G.tiles_total; G.tiles_total += G.lv[l].tiles_x * G.lv[l].tiles_y; }
+    ex->tile_flags_valid = false;
     CK(ex->lut_blob.ensure(blob.size() * sizeof(int16_t)));
     CK(cudaMemcpyAsync(ex->lut_blob.p, blob.data(), blob.size() * sizeof(int16_t), cudaMemcpyHostToDevice, ex->stream));
     const int16_t* base = (const int16_t*)ex->lut_blob.p;
@@ -257,6 +278,30 @@ int upload_small_inputs(mcs_extractor* ex, int W, int H, const uint8_t* masks, c
         CK(cudaStreamSynchronize(st));                     // a previous call may still read the old masks
         ex->masks_host.assign(masks, masks + mbytes);
         CK(cudaMemcpyAsync(ex->masks.p, ex->masks_host.data(), mbytes, cudaMemcpyHostToDevice, st));
+        ex->tile_flags_valid = false;
+    }
+    if (!ex->tile_flags_valid) {
+        // per camera and K1 tile: does the tile hold a pixel whose (nearest-neighbour chained) mask value is set?
+        const PyramidGeom& G = ex->G;
+        std::vector<uint8_t> flags((size_t)n_cams * G.tiles_total, 0);
+        for (int c = 0; c < n_cams; ++c) {
+            const uint8_t* m0 = ex->masks_host.data() + (size_t)c * W * H;
+            for (int l = 0; l < G.nlevels; ++l) {
+                const LevelGeom& g = G.lv[l];
+                uint8_t* f = flags.data() + (size_t)c * G.tiles_total + g.tile_off;
+                for (int y = 0; y < g.h; ++y) {
+                    const uint8_t* mrow = m0 + (size_t)ex->h_my[l][y] * W;
+                    uint8_t* frow = f + (size_t)(y / kTH) * g.tiles_x;
+                    for (int x = 0; x < g.w; ++x) frow[x / kTW] |= mrow[ex->h_mx[l][x]];
+                }
+            }
+        }
+        for (auto& v : flags) v = v ? 1 : 0;
+        CK(cudaStreamSynchronize(st));                     // a previous call may still read the old flags
+        CK(ex->tile_flags.ensure(flags.size()));
+        CK(cudaMemcpyAsync(ex->tile_flags.p, flags.data(), flags.size(), cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));                     // `flags` is a host temporary
+        ex->tile_flags_valid = true;
     }
     CK(cudaMemcpyAsync(ex->cams.p, cams, sizeof(mcs_ocam) * n_cams, cudaMemcpyHostToDevice, st));
     if ((ex->p.do_dbrief || ex->p.learn_masks) &&
@@ -313,7 +358,7 @@ int run_pipeline(mcs_extractor* ex, int n_images, const uint8_t* images_dev, int
         const uint8_t* src = l ? ex->lvl[l - 1].p : images_dev;
         const size_t src_bytes = l ? G.lv[l - 1].img_bytes : (size_t)stride * H;
         launch_pyr_fast(G, l, n_images, src, src_bytes, ex->lvl[l].p, ex->blur[l].p, ex->masks.p, W, (size_t)W * H,
-                        coi_d, ex->raw.p, ex->raw_count.p, st);
+                        coi_d, ex->tile_flags.p, ex->raw.p, ex->raw_count.p, st);
     }
     CK(cudaGetLastError());
     if (ex->profiling) CK(cudaEventRecord(ex->ev[1], st));
@@ -477,7 +522,7 @@ void mcs_extractor_destroy(mcs_extractor* ex) {
     ex->masks.release(); ex->cams.release(); ex->cam_of_image.release(); ex->coi_all.release(); ex->raw.release(); ex->node_of.release();
     ex->raw_count.release(); ex->sel_count.release(); ex->status.release(); ex->counts.release(); ex->sel_xys.release();
     ex->kps.release(); ex->desc.release(); ex->dmask.release();
-    ex->match_idx.release(); ex->match_dist.release(); ex->lut_coef.release(); ex->luts.release(); ex->tier.release();
+    ex->match_idx.release(); ex->match_dist.release(); ex->lut_coef.release(); ex->luts.release(); ex->tier.release(); ex->tile_flags.release();
     for (int i = 0; i < 4; ++i) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
     ex->in_tight.release();
     if (ex->s_copy) cudaStreamDestroy(ex->s_copy);
@@ -810,8 +855,15 @@ int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams
     return check_status(ex, st);
 }
 
-size_t mcs_slot_bytes(int32_t capacity, int32_t dim) {
-    return 16 + (size_t)capacity * (sizeof(mcs_keypoint) + 2 * (size_t)dim);
+int mcs_extract_batch_packed_device(mcs_extractor* ex, int32_t n_images, const uint8_t* images_dev, int32_t width, int32_t height,
+                                    int32_t stride, const uint8_t* masks, const mcs_ocam* cams, int32_t n_cams,
+                                    const int32_t* cam_of_image, void* packed_dev, int32_t capacity, void* stream) {
+    if (!ex || !packed_dev) return fail(MCS_ERR_INVALID, "null argument");
+    size_t off[4];
+    mcs_packed_layout(n_images, capacity, ex->p.desc_size, off);
+    uint8_t* base = (uint8_t*)packed_dev;
+    return mcs_extract_batch_device(ex, n_images, images_dev, width, height, stride, masks, cams, n_cams, cam_of_image,
+                                    (mcs_keypoint*)(base + off[1]), base + off[2], base + off[3], (int32_t*)(base + off[0]), capacity, stream);
 }
 
 }  // extern "C"

@@ -22,6 +22,8 @@ struct LevelGeom {
     int w, h, pitch;              // level size, row pitch in bytes (multiple of 64)
     int sw, sh, spitch;           // source (level l-1, or the input image for l == 0)
     int tiles_x, tiles_y;
+    int tile_off;                 // offset of this level's tiles in the per-camera tile-flag table
+    int box_w, box_h;             // TMA box of the staged source region: bytes per row (multiple of 16) x rows, covers every tile
     int raw_cap;                  // capacity of the raw corner list of this level (per image)
     int quota;                    // mnFeaturesPerLevel[l]
     int sel_cap;                  // quota + 3
@@ -49,6 +51,7 @@ struct PyramidGeom {
     int cap;                       // output slots per image
     int sel_total;                 // sum of sel_cap
     size_t raw_total;              // sum of raw_cap (elements per image)
+    int tiles_total;               // sum of tiles_x * tiles_y
     LevelGeom lv[kMaxLevels];
 };
 

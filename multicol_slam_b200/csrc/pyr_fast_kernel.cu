@@ -14,11 +14,46 @@
 //     pixel pair: score = max over arcs of max(min9(E), -max9(E)) - 1, corner iff that maximum exceeds the threshold.
 // The kernel is bound by integer issue rate, not by HBM: ~100 thread-instructions per pixel
 // against ~2.5 bytes of DRAM traffic.
+#include <cstring>
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "kernels.h"
 #include "mcs_common.cuh"
 
 namespace mcs {
 
+// ---- TMA staging (cp.async.bulk.tensor + mbarrier) ---------------------------------------------------------------------------
+// The source region of a tile is one box of a 3-D tensor map (x bytes, y rows, image) over the level l-1 buffer: a single thread
+// issues the bulk copy, the hardware writes the box into shared memory (rows past the image are zero-filled) and signals an
+// mbarrier, while the other threads fill the per-tile tables.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE_%=;\n"
+        "bra MBAR_WAIT_%=;\n"
+        "MBAR_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+
+#ifndef MCS_K1_TMA
+#define MCS_K1_TMA 1                         // 0: stage the source region with __ldg + st.shared (A/B builds)
+#endif
 constexpr int kThreads = 256;
 constexpr int kSrcWB = 176;                 // staged source row stride (bytes, multiple of 16)
 constexpr int kT8S = 80;                    // byte tile row stride
@@ -29,12 +64,9 @@ constexpr int kMaxTileCorners = kTW * kTH / 4;
 __device__ __forceinline__ unsigned vneg2(unsigned a) { return __vadd2(~a, 0x00010001u); }
 
 // packed cornerScore<16> margin of a pixel pair: C = centre pair, R[k] = ring pairs -> max over the 16 arcs of
-// max(min9(R-C), min9(C-R)) per 16-bit lane (signed)
-__device__ __forceinline__ unsigned fast_margin2(unsigned C, const unsigned (&R)[16]) {
-    const unsigned NC = vneg2(C);
-    unsigned E[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) E[k] = __vadd2(R[k], NC);
+// max(min9(R-C), min9(C-R)) per 16-bit lane (signed).  min over an arc of (R_k - C) = (min over the arc of R_k) - C, so the
+// arc minima / maxima are taken on the ring values themselves and the centre enters once at the end.
+__device__ __forceinline__ unsigned fast_margin2(unsigned C, const unsigned (&E)[16]) {
     unsigned mn3[16], mx3[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
@@ -54,19 +86,21 @@ __device__ __forceinline__ unsigned fast_margin2(unsigned C, const unsigned (&R)
         bright = __vimax3_s16x2(bright, mn9[k], mn9[k + 1]);
         darkn = __vimin3_s16x2(darkn, mx9[k], mx9[k + 1]);
     }
-    bright = __vmaxs2(bright, mn9[15]);
-    darkn = __vmins2(darkn, mx9[15]);
-    return __vmaxs2(bright, vneg2(darkn));
+    bright = __vmaxs2(bright, mn9[15]);                     // max over arcs of the arc minimum of the ring
+    darkn = __vmins2(darkn, mx9[15]);                       // min over arcs of the arc maximum
+    return __vmaxs2(__vsub2(bright, C), __vsub2(C, darkn)); // values in 0..255: no 16-bit overflow
 }
 
 __global__ void __launch_bounds__(kThreads, 5)
-pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int fast_th, const int src_aligned,
+pyr_fast_kernel(const __grid_constant__ CUtensorMap src_map, const int use_tma,
+                const LevelGeom g, const int level, const int nlevels, const int fast_th, const int src_aligned,
                 const uint8_t* __restrict__ src, const size_t src_img_bytes,
                 uint8_t* __restrict__ dst, uint8_t* __restrict__ dst_blur,
                 const uint8_t* __restrict__ mask0, const int mask_w, const size_t mask_bytes,
-                const int* __restrict__ cam_of_image,
+                const int* __restrict__ cam_of_image, const uint8_t* __restrict__ tile_flags, const int tiles_total,
                 uint32_t* __restrict__ raw, const size_t raw_img_stride, int* __restrict__ raw_count) {
-    __shared__ __align__(16) uint8_t s_src[kSrcH * kSrcWB];
+    __shared__ __align__(128) uint8_t s_src[kSrcH * kSrcWB];
+    __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(16) uint8_t s_t8[kTileH * kT8S];
     __shared__ __align__(16) uint16_t s_a0[kTileH * kT16S];          // s_a0[y][x]   = px(x)
     __shared__ __align__(16) uint16_t s_a1[kTileH * kT16S];          // s_a1[y][i]   = px(i+1)
@@ -88,6 +122,10 @@ pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int
     const int b = blockIdx.z;
     const int X0 = blockIdx.x * kTW, Y0 = blockIdx.y * kTH;
     const uint8_t* simg = src + (size_t)b * src_img_bytes;
+    // FAST + NMS only where the tile holds at least one pixel inside the camera's mask: a corner is reported only if its own
+    // mask pixel is set (mask applied after NMS), and the scores of its 8 neighbours come from this CTA's own halo
+    const int cam_b = cam_of_image[b];
+    const bool fast_on = tile_flags[(size_t)cam_b * tiles_total + g.tile_off + blockIdx.y * g.tiles_x + blockIdx.x] != 0;
 
     // output-space range needed by this tile; after REFLECT_101 everything lies inside it
     const int xa = max(X0 - kHalo, 0), xb = min(X0 + kTW + kHalo, g.w) - 1;
@@ -95,7 +133,17 @@ pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int
     const int sx_lo = g.xofs[xa], sx_hi = min(g.xofs[xb] + 1, g.sw - 1);
     const int sy_lo = min(max((int)g.yofs[ya], 0), g.sh - 1), sy_hi = min(max(g.yofs[yb] + 1, 0), g.sh - 1);
     const int sx_base = sx_lo & ~15;
-    if (tid == 0) s_n = 0;
+    const int wb = use_tma ? g.box_w : kSrcWB;                          // row stride of the staged region in bytes
+    if (tid == 0) {
+        s_n = 0;
+        if (use_tma) {
+            // the barrier is initialised and armed by the same thread that issues the copy; every other thread first sees it
+            // after the __syncthreads below, then waits for phase 0
+            mbar_init(&s_bar, 1);
+            mbar_expect_tx(&s_bar, (uint32_t)(g.box_w * g.box_h));
+            tma_load_3d(s_src, &src_map, sx_base, sy_lo, b, &s_bar);
+        }
+    }
 
     // ---- per-tile slices of the resize / cell tables ----
     if (tid < kTileW) {
@@ -126,8 +174,8 @@ pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int
         const int y = Y0 + tid - 128;
         s_my[tid - 128] = y < g.h ? g.my0[y] : (int16_t)0;
     }
-    // ---- stage the source rows: 16-byte chunks, one warp per row ----
-    {
+    // ---- stage the source rows: by TMA (above), or -- caller images with an unaligned base / stride -- 16-byte chunks per warp ----
+    if (!use_tma) {
         const int nrows = sy_hi - sy_lo + 1;
         if (src_aligned) {
             const int nchunks = ((sx_hi - sx_base) >> 4) + 1;
@@ -153,6 +201,7 @@ pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int
         }
     }
     __syncthreads();
+    if (use_tma) mbar_wait(&s_bar, 0);
 
     // ---- bilinear resize (OpenCV 11-bit fixed point) into the three tile forms; a thread owns a pixel-pair column ----
     if (tid < (kTileW / 2) * 7) {
@@ -162,8 +211,8 @@ pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int
         const int a00 = s_xa0[tx], a01 = s_xa1[tx], a10 = s_xa0[tx + 1], a11 = s_xa1[tx + 1];
 #pragma unroll
         for (int ty = rg; ty < kTileH; ty += 7) {
-            const uint8_t* r0 = s_src + s_ys0[ty] * kSrcWB;
-            const uint8_t* r1 = s_src + s_ys1[ty] * kSrcWB;
+            const uint8_t* r0 = s_src + s_ys0[ty] * wb;
+            const uint8_t* r1 = s_src + s_ys1[ty] * wb;
             const int b0 = s_yb0[ty], b1 = s_yb1[ty];
             int v0, v1;
             if (level == 0) {            // identity resize: the general formula reduces to a copy
@@ -211,6 +260,7 @@ pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int
         s_h[i] = __vadd2(__vadd2(__vadd2(w0[-1], w1[-1]), __vadd2(w0[0], w1[0])), w0[1]);
     }
     // ---- (c) FAST margins of pixel pairs on the tile + 1 ring; pairs start at tile column 3 (odd) ----
+    if (fast_on)
 #pragma unroll
     for (int i = tid; i < (kTH + 2) * ((kTW + 2) / 2); i += kThreads) {
         const int y = i / ((kTW + 2) / 2), j = i - y * ((kTW + 2) / 2);
@@ -256,7 +306,8 @@ pyr_fast_kernel(const LevelGeom g, const int level, const int nlevels, const int
     // ---- (e) per-cell 3x3 non-max suppression on pixel pairs (packed 16x2), mask filter, tile-local compaction ----
     // Pair j of row y = pixels x = 2j, 2j+1 = score-tile columns 2j+1, 2j+2: centre word from the odd copy, left /
     // right neighbour pairs from the even copy.  A neighbour outside the pixel's FAST cell counts as 0 (cv::FAST runs per cell).
-    const uint8_t* m0p = mask0 + (size_t)cam_of_image[b] * mask_bytes;
+    if (!fast_on) return;                                   // uniform for the CTA: no corner can come out of this tile
+    const uint8_t* m0p = mask0 + (size_t)cam_b * mask_bytes;
 #pragma unroll
     for (int i = tid; i < kTH * (kTW / 2); i += kThreads) {
         const int y = i >> 5, j = i & 31;
@@ -314,12 +365,34 @@ void launch_repitch(const uint8_t* src, int src_stride, uint8_t* dst, int dst_pi
 
 void launch_pyr_fast(const PyramidGeom& G, int level, int n_images, const uint8_t* src, size_t src_img_bytes,
                      uint8_t* dst, uint8_t* dst_blur, const uint8_t* mask0, int mask_w, size_t mask_bytes,
-                     const int* cam_of_image, uint32_t* raw, int* raw_count, cudaStream_t st) {
+                     const int* cam_of_image, const uint8_t* tile_flags, uint32_t* raw, int* raw_count, cudaStream_t st) {
     const LevelGeom& g = G.lv[level];
     dim3 grid(g.tiles_x, g.tiles_y, n_images);
     const int aligned = (((uintptr_t)src & 15) == 0 && (g.spitch & 15) == 0 && (src_img_bytes & 15) == 0) ? 1 : 0;
-    pyr_fast_kernel<<<grid, kThreads, 0, st>>>(g, level, G.nlevels, G.fast_threshold, aligned, src, src_img_bytes, dst, dst_blur,
-                                               mask0, mask_w, mask_bytes, cam_of_image, raw, G.raw_total, raw_count);
+    // tensor map of the source: (row bytes, rows, images), box = the level's staged region.  Encoding is a host-side table fill
+    // (no driver round trip), done per launch because the base address and the batch size are per call.
+    CUtensorMap map;
+    std::memset(&map, 0, sizeof(map));
+    int use_tma = 0;
+#if MCS_K1_TMA
+    static PFN_cuTensorMapEncodeTiled_v12000 encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) fn = nullptr;
+        return (PFN_cuTensorMapEncodeTiled_v12000)fn;
+    }();
+    if (encode && aligned && g.box_w * g.box_h <= kSrcH * kSrcWB) {
+        const cuuint64_t dims[3] = {(cuuint64_t)g.spitch, (cuuint64_t)g.sh, (cuuint64_t)n_images};
+        const cuuint64_t strides[2] = {(cuuint64_t)g.spitch, (cuuint64_t)src_img_bytes};
+        const cuuint32_t box[3] = {(cuuint32_t)g.box_w, (cuuint32_t)g.box_h, 1u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        use_tma = encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)src, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+#endif
+    pyr_fast_kernel<<<grid, kThreads, 0, st>>>(map, use_tma, g, level, G.nlevels, G.fast_threshold, aligned, src, src_img_bytes, dst, dst_blur,
+                                               mask0, mask_w, mask_bytes, cam_of_image, tile_flags, G.tiles_total, raw, G.raw_total,
+                                               raw_count);
 }
 
 }  // namespace mcs

@@ -28,7 +28,8 @@ def test_struct_layouts(api):
     from multicol_slam_b200.ctypes_defs import ExtractorParams, KEYPOINT_DTYPE, Ocam, WindowQuery
     assert C.sizeof(Ocam) == 8 * 22 + 16 and C.sizeof(ExtractorParams) == 52
     assert KEYPOINT_DTYPE.itemsize == 28 and C.sizeof(WindowQuery) == 40
-    assert api.lib().mcs_slot_bytes(2016, 32) == 16 + 2016 * (28 + 64)
+    from multicol_slam_b200 import rig
+    assert api.lib().mcs_slot_bytes(2016, 32) == rig.slot_bytes(2016, 32) == 256 + (2016 * 28 + 255) // 256 * 256 + 2 * 2016 * 32
 
 
 def test_host_helpers_match_oracle(api, oa, cams):

@@ -59,6 +59,13 @@ def test_slot_roundtrip(api):
     d, m = rng.integers(0, 256, (17, 32)).astype(np.uint8), rng.integers(0, 256, (17, 32)).astype(np.uint8)
     buf = rig.pack_slot(k, d, m, 40, 32)
     assert buf.size == api.lib().mcs_slot_bytes(40, 32)
+    # the numpy packers follow the library's layout (mcs_packed_layout) for any batch size
+    import ctypes as C
+    for n, cap, dim in [(1, 40, 32), (3, 2016, 32), (384, 2016, 32), (7, 4016, 64), (2, 416, 16)]:
+        off = (C.c_size_t * 4)()
+        api.lib().mcs_packed_layout.restype = C.c_size_t
+        total = api.lib().mcs_packed_layout(n, cap, dim, off)
+        assert (list(off), total) == rig.packed_layout(n, cap, dim)
     k2, d2, m2 = rig.unpack_slot(buf, 40, 32)
     assert k2.tobytes() == k.tobytes() and np.array_equal(d, d2) and np.array_equal(m, m2)
     # empty camera
