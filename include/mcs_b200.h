@@ -161,6 +161,15 @@ int  mcs_match_stream_device(const uint8_t* desc_dev, const uint8_t* dmask_dev, 
                              int32_t n_frames, int32_t n_cams, int32_t capacity, int32_t dim, int32_t K,
                              int32_t* match_idx_dev, int32_t* match_dist_dev, void* stream);
 
+/* The greedy acceptance of SearchByBoW(KF1, KF2) (ref src/cORBmatcher.cpp:899-961: threshold, ratio test, every database
+ * keypoint used once, queries in index order) over the K-best lists of mcs_match_stream_device, on the device and on the same
+ * stream: matches12_dev [n_images*capacity] = matched slot of the previous frame's image or -1, nmatches_dev [n_images],
+ * redo_dev [n_images] = 1 where a list ran out before two unmatched entries were seen (recompute that pair with
+ * mcs_match_bruteforce; never observed with K = 4 on frame-to-frame data).  K >= 2. */
+int  mcs_match_stream_replay_device(const int32_t* match_idx_dev, const int32_t* match_dist_dev, const int32_t* counts_dev,
+                                    int32_t n_frames, int32_t n_cams, int32_t capacity, int32_t K, int32_t th_low, double nnratio,
+                                    int32_t* matches12_dev, int32_t* nmatches_dev, int32_t* redo_dev, void* stream);
+
 /* Per-stage device timings of the LAST extract call, measured with CUDA events on the launching stream when
  * profiling is enabled: ms[0] = K1 (pyramid+blur+FAST, all levels), ms[1] = K2 octree, ms[2] = K3 describe.
  * mcs_extractor_set_profiling(ex, 1) turns the event recording on (off by default). */
@@ -208,6 +217,13 @@ int  mcs_match_bruteforce(const uint8_t* q, const uint8_t* qmask, const uint8_t*
                           const uint8_t* d, const uint8_t* dmask, const uint8_t* valid2, int32_t nd,
                           int32_t dim, int32_t th_low, double nnratio,
                           int32_t* matches12, int32_t* nmatches);
+/* Same with query and database descriptors (and masks) resident in device memory -- e.g. the descriptor section of a packed
+ * feature buffer against a key-frame database that stays on the GPU; valid1 / valid2 / matches12 / nmatches are host memory.
+ * Runs on `stream` and returns when the result is complete. */
+int  mcs_match_bruteforce_device(const uint8_t* q_dev, const uint8_t* qmask_dev, const uint8_t* valid1, int32_t nq,
+                                 const uint8_t* d_dev, const uint8_t* dmask_dev, const uint8_t* valid2, int32_t nd,
+                                 int32_t dim, int32_t th_low, double nnratio, int32_t* matches12, int32_t* nmatches, void* stream);
+
 
 /* cORBmatcher::SearchForTriangulationRaw(KF1, KF2, ...) (ref src/cORBmatcher.cpp:968-1156): all-pairs scan, same camera only,
  * over the keypoints that carry NO map point (free1/free2 != 0); per query the candidates with distance <= th_low are

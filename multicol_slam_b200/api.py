@@ -179,6 +179,32 @@ class mdBRIEFextractorOct:
                                               C.c_void_p(out["dmask"].data_ptr()), C.c_void_p(out["counts"].data_ptr()), cap, st))
         return out
 
+    def packed_views(self, packed_t, n_images):
+        """views of a packed feature buffer (mcs_packed_layout) as the four output tensors"""
+        import torch
+        from . import rig
+        cap, ds = self.info.capacity, self.info.desc_size
+        offs, total = rig.packed_layout(n_images, cap, ds)
+        assert packed_t.numel() >= total
+        return dict(counts=packed_t[offs[0]:offs[0] + 4 * n_images].view(torch.int32),
+                    kps=packed_t[offs[1]:offs[1] + n_images * cap * 28].view(torch.int32).view(n_images, cap, 7),
+                    desc=packed_t[offs[2]:offs[2] + n_images * cap * ds].view(n_images, cap, ds),
+                    dmask=packed_t[offs[3]:offs[3] + n_images * cap * ds].view(n_images, cap, ds))
+
+    def extract_batch_packed_device(self, images_t, masks, cams, cam_of_image, packed_t, stream=None, width=None):
+        """mcs_extract_batch_packed_device: K3 writes counts | keypoints | descriptors | masks straight into packed_t (uint8
+        cuda tensor of rig.packed_layout(B, capacity, descSize)[1] bytes) -- the buffer mcs_allgather_features exchanges."""
+        import torch
+        B, H, P = images_t.shape
+        W = P if width is None else width
+        masks = np.ascontiguousarray(masks, np.uint8)
+        coi = np.ascontiguousarray(cam_of_image, np.int32)
+        ocs = (Ocam * len(cams))(*[as_ocam(c) for c in cams])
+        st = C.c_void_p(stream.cuda_stream if stream is not None else torch.cuda.current_stream(images_t.device).cuda_stream)
+        _check(lib().mcs_extract_batch_packed_device(self._h, B, C.c_void_p(images_t.data_ptr()), W, H, P, _p(masks), ocs, len(cams),
+                                                     _p(coi), C.c_void_p(packed_t.data_ptr()), self.info.capacity, st))
+        return self.packed_views(packed_t, B)
+
     def extract_match_stream(self, images, masks, cams, K=2, out=None):
         """images [F,C,H,W] u8 host (frame-major).  Extract every image and brute-force match each (frame,cam)
         against (frame-1,cam).  Returns dict(kps [F*C,cap], desc, dmask, counts, match_idx [F*C,cap,K], match_dist).
@@ -272,6 +298,39 @@ def match_stream_device(desc_t, dmask_t, counts_t, n_frames, n_cams, K=2, out=No
     _check(lib().mcs_match_stream_device(ptr(desc_t), ptr(dmask_t), ptr(counts_t), n_frames, n_cams, cap, dim, K, ptr(out[0]),
                                          ptr(out[1]), st))
     return out
+
+
+def match_stream_replay_device(idx_t, dist_t, counts_t, n_frames, n_cams, th_low, nnratio, out=None, stream=None):
+    """mcs_match_stream_replay_device: greedy SearchByBoW acceptance over the K-best lists, on the device.
+    -> (matches12 [F*C,cap] i32, nmatches [F*C] i32, redo [F*C] i32) cuda tensors"""
+    import torch
+    B, cap, K = idx_t.shape
+    dev = idx_t.device
+    if out is None:
+        out = (torch.empty((B, cap), dtype=torch.int32, device=dev), torch.empty(B, dtype=torch.int32, device=dev),
+               torch.empty(B, dtype=torch.int32, device=dev))
+    ptr = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    st = C.c_void_p(stream.cuda_stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream)
+    _check(lib().mcs_match_stream_replay_device(ptr(idx_t), ptr(dist_t), ptr(counts_t), n_frames, n_cams, cap, K, int(th_low),
+                                                C.c_double(nnratio), ptr(out[0]), ptr(out[1]), ptr(out[2]), st))
+    return out
+
+
+def match_bruteforce_device(q_t, qmask_t, valid1, d_t, dmask_t, valid2, th_low, nnratio, stream=None):
+    """mcs_match_bruteforce_device: SearchByBoW(KF1, KF2) with descriptors resident on the GPU (torch uint8 [n, dim]);
+    valid1 / valid2 host uint8 arrays or None.  Returns (nmatches, matches12 numpy)."""
+    import torch
+    nq, dim = q_t.shape
+    nd = d_t.shape[0]
+    v1 = None if valid1 is None else np.ascontiguousarray(valid1, np.uint8)
+    v2 = None if valid2 is None else np.ascontiguousarray(valid2, np.uint8)
+    m12 = np.zeros(nq, np.int32)
+    n = C.c_int32(0)
+    ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+    st = C.c_void_p(stream.cuda_stream if stream is not None else torch.cuda.current_stream(q_t.device).cuda_stream)
+    _check(lib().mcs_match_bruteforce_device(ptr(q_t), ptr(qmask_t), _p(v1), nq, ptr(d_t), ptr(dmask_t), _p(v2), nd, dim, int(th_low),
+                                             C.c_double(nnratio), _p(m12), C.byref(n), st))
+    return n.value, m12
 
 
 class Frame:

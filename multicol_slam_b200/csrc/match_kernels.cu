@@ -308,6 +308,67 @@ cudaError_t launch_hamming_stream(const uint8_t* desc, const uint8_t* dmask, con
     return cudaGetLastError();
 }
 
+// Greedy acceptance of SearchByBoW(KF1, KF2) (ref src/cORBmatcher.cpp:899-961) over the K-best lists of the stream matcher, on
+// the device: one warp per image; the lanes fetch the lists of 32 queries at a time (coalesced), lane 0 replays them in order.
+// A query takes the first two list entries that are still unmatched as best / second best (the lists are sorted by
+// (distance, index), i.e. the reference's strict `<` scan order) and is accepted when best < th_low and best < nnratio * second.
+// When a list is used up before two unmatched entries were seen the image is flagged in redo[] (the host recomputes that
+// image pair with deeper lists); with K = 4 this needs three of a query's four nearest neighbours to be taken already.
+__global__ void __launch_bounds__(32)
+stream_replay_kernel(const int* __restrict__ list_idx, const int* __restrict__ list_dist, const int* __restrict__ counts,
+                     const int n_cams, const int capacity, const int K, const int th_low, const double nnratio,
+                     int* __restrict__ matches12, int* __restrict__ nmatches, int* __restrict__ redo) {
+    extern __shared__ int s_mem[];
+    int* s_li = s_mem;                              // [32][K]
+    int* s_ld = s_mem + 32 * K;                     // [32][K]
+    unsigned* s_taken = (unsigned*)(s_mem + 64 * K);   // [(capacity + 31) / 32]
+    const int img = blockIdx.x, lane = threadIdx.x;
+    const int nq = img >= n_cams ? min(counts[img], capacity) : 0;
+    for (int i = lane; i < (capacity + 31) / 32; i += 32) s_taken[i] = 0u;
+    for (int i = lane; i < capacity; i += 32) matches12[(size_t)img * capacity + i] = -1;
+    int nm = 0, need_redo = 0;
+    __syncwarp();
+    for (int q0 = 0; q0 < nq; q0 += 32) {
+        const int nchunk = min(32, nq - q0);
+        for (int i = lane; i < nchunk * K; i += 32) {
+            s_li[i] = list_idx[((size_t)img * capacity + q0) * K + i];
+            s_ld[i] = list_dist[((size_t)img * capacity + q0) * K + i];
+        }
+        __syncwarp();
+        if (lane == 0 && !need_redo) {
+            for (int t = 0; t < nchunk; ++t) {
+                int best1 = 0x7FFFFFFF, best2 = 0x7FFFFFFF, bestIdx = -1, found = 0;
+                bool complete = false;
+                for (int k = 0; k < K; ++k) {
+                    const int id = s_li[t * K + k];
+                    if (id < 0) { complete = true; break; }          // the list holds every database entry there is
+                    if (s_taken[id >> 5] >> (id & 31) & 1u) continue;
+                    if (found == 0) { best1 = s_ld[t * K + k]; bestIdx = id; }
+                    else best2 = s_ld[t * K + k];
+                    if (++found == 2) break;
+                }
+                if (found < 2 && !complete && !(found == 1 && !(best1 < th_low))) { need_redo = 1; break; }
+                if (best1 < th_low && (double)best1 < nnratio * (double)best2) {
+                    matches12[(size_t)img * capacity + q0 + t] = bestIdx;
+                    s_taken[bestIdx >> 5] |= 1u << (bestIdx & 31);
+                    ++nm;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) { nmatches[img] = nm; redo[img] = need_redo; }
+}
+
+cudaError_t launch_stream_replay(const int* list_idx, const int* list_dist, const int* counts, int n_images, int n_cams, int capacity,
+                                 int K, int th_low, double nnratio, int* matches12, int* nmatches, int* redo, cudaStream_t st) {
+    if (n_images < 1) return cudaSuccess;
+    const size_t smem = (size_t)64 * K * 4 + (size_t)((capacity + 31) / 32) * 4;
+    stream_replay_kernel<<<n_images, 32, smem, st>>>(list_idx, list_dist, counts, n_cams, capacity, K, th_low, nnratio, matches12,
+                                                    nmatches, redo);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // window search
 // ------------------------------------------------------------------------------------------------

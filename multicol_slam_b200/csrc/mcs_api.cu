@@ -709,6 +709,17 @@ int mcs_match_stream_device(const uint8_t* desc_dev, const uint8_t* dmask_dev, c
     return MCS_OK;
 }
 
+int mcs_match_stream_replay_device(const int32_t* match_idx_dev, const int32_t* match_dist_dev, const int32_t* counts_dev,
+                                   int32_t n_frames, int32_t n_cams, int32_t capacity, int32_t K, int32_t th_low, double nnratio,
+                                   int32_t* matches12_dev, int32_t* nmatches_dev, int32_t* redo_dev, void* stream) {
+    if (!match_idx_dev || !match_dist_dev || !counts_dev || !matches12_dev || !nmatches_dev || !redo_dev)
+        return fail(MCS_ERR_INVALID, "null argument");
+    if (n_frames < 1 || n_cams < 1 || capacity < 1 || K < 2 || K > 8) return fail(MCS_ERR_INVALID, "bad sizes (K must be 2..8)");
+    CK(launch_stream_replay(match_idx_dev, match_dist_dev, counts_dev, n_frames * n_cams, n_cams, capacity, K, th_low, nnratio,
+                            matches12_dev, nmatches_dev, redo_dev, (cudaStream_t)stream));
+    return MCS_OK;
+}
+
 int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams, const uint8_t* images, int32_t width,
                              int32_t height, int32_t stride, const uint8_t* masks, const mcs_ocam* cams, mcs_keypoint* kps_out,
                              uint8_t* desc_out, uint8_t* dmask_out, int32_t* counts_out, int32_t capacity, int32_t K,

@@ -170,40 +170,29 @@ int mcs_hamming_topk(const uint8_t* q, const uint8_t* qmask, int32_t nq, const u
     return MCS_OK;
 }
 
-int mcs_match_bruteforce(const uint8_t* q, const uint8_t* qmask, const uint8_t* valid1, int32_t nq, const uint8_t* d,
-                         const uint8_t* dmask, const uint8_t* valid2, int32_t nd, int32_t dim, int32_t th_low, double nnratio,
-                         int32_t* matches12, int32_t* nmatches) {
-    if (!q || !d || !matches12 || !nmatches) return mfail(MCS_ERR_INVALID, "null argument");
-    if (dim != 16 && dim != 32 && dim != 64) return mfail(MCS_ERR_INVALID, "dim must be 16, 32 or 64");
-    *nmatches = 0;
-    for (int i = 0; i < nq; ++i) matches12[i] = -1;
-    if (nq <= 0 || nd <= 0) return MCS_OK;
-    const bool masked = qmask && dmask;
+// SearchByBoW(KF1, KF2) (ref :885-966) with the descriptors already on the device: K best unmatched database entries per query
+// on the GPU, sequential greedy replay on the host, further rounds for queries whose list was used up by earlier matches
+static int bruteforce_core(const uint8_t* q_dev, const uint8_t* qm_dev, const uint8_t* valid1, int nq, const uint8_t* d_dev,
+                           const uint8_t* dm_dev, const uint8_t* valid2, int nd, int dim, int th_low, double nnratio, int* matches12,
+                           int* nmatches, cudaStream_t st) {
+    const bool masked = qm_dev && dm_dev;
     constexpr int K = 4;
-    Dev dq, dqm, dd, ddm, ds, di, dt;
-    MCK(dq.alloc((size_t)nq * dim)); MCK(dd.alloc((size_t)nd * dim)); MCK(ds.alloc(nd));
-    MCK(di.alloc((size_t)nq * K * 4)); MCK(dt.alloc((size_t)nq * K * 4));
-    MCK(cudaMemcpy(dq.p, q, (size_t)nq * dim, cudaMemcpyHostToDevice));
-    MCK(cudaMemcpy(dd.p, d, (size_t)nd * dim, cudaMemcpyHostToDevice));
-    if (masked) {
-        MCK(dqm.alloc((size_t)nq * dim)); MCK(ddm.alloc((size_t)nd * dim));
-        MCK(cudaMemcpy(dqm.p, qmask, (size_t)nq * dim, cudaMemcpyHostToDevice));
-        MCK(cudaMemcpy(ddm.p, dmask, (size_t)nd * dim, cudaMemcpyHostToDevice));
-    }
+    Dev ds, di, dt;
+    MCK(ds.alloc(nd)); MCK(di.alloc((size_t)nq * K * 4)); MCK(dt.alloc((size_t)nq * K * 4));
     std::vector<uint8_t> skip(nd, 0), newly(nd, 0);
     if (valid2) for (int i = 0; i < nd; ++i) skip[i] = valid2[i] ? 0 : 1;
     std::vector<int> tidx((size_t)nq * K), tdist((size_t)nq * K);
     int q0 = 0, nm = 0;
     while (q0 < nq) {
         // GPU: K best unmatched database entries for every remaining query (state at the start of the round)
-        MCK(cudaMemcpy(ds.p, skip.data(), nd, cudaMemcpyHostToDevice));
+        MCK(cudaMemcpyAsync(ds.p, skip.data(), nd, cudaMemcpyHostToDevice, st));
         const int nrem = nq - q0;
-        int rc = mcs_hamming_topk_device(dq.as<uint8_t>() + (size_t)q0 * dim, masked ? dqm.as<uint8_t>() + (size_t)q0 * dim : nullptr,
-                                         nrem, dd.as<uint8_t>(), masked ? ddm.as<uint8_t>() : nullptr, nd, ds.as<uint8_t>(), dim, K,
-                                         di.as<int>(), dt.as<int>(), nullptr);
+        int rc = mcs_hamming_topk_device(q_dev + (size_t)q0 * dim, masked ? qm_dev + (size_t)q0 * dim : nullptr, nrem, d_dev,
+                                         masked ? dm_dev : nullptr, nd, ds.as<uint8_t>(), dim, K, di.as<int>(), dt.as<int>(), st);
         if (rc) return rc;
-        MCK(cudaMemcpy(tidx.data(), di.p, (size_t)nrem * K * 4, cudaMemcpyDeviceToHost));
-        MCK(cudaMemcpy(tdist.data(), dt.p, (size_t)nrem * K * 4, cudaMemcpyDeviceToHost));
+        MCK(cudaMemcpyAsync(tidx.data(), di.p, (size_t)nrem * K * 4, cudaMemcpyDeviceToHost, st));
+        MCK(cudaMemcpyAsync(tdist.data(), dt.p, (size_t)nrem * K * 4, cudaMemcpyDeviceToHost, st));
+        MCK(cudaStreamSynchronize(st));
         std::fill(newly.begin(), newly.end(), 0);
         // host: sequential replay (ref :899-961); a query whose list is exhausted by entries matched
         // during this round starts the next round
@@ -236,6 +225,40 @@ int mcs_match_bruteforce(const uint8_t* q, const uint8_t* qmask, const uint8_t* 
     }
     *nmatches = nm;
     return MCS_OK;
+}
+
+int mcs_match_bruteforce_device(const uint8_t* q_dev, const uint8_t* qmask_dev, const uint8_t* valid1, int32_t nq, const uint8_t* d_dev,
+                                const uint8_t* dmask_dev, const uint8_t* valid2, int32_t nd, int32_t dim, int32_t th_low, double nnratio,
+                                int32_t* matches12, int32_t* nmatches, void* stream) {
+    if (!q_dev || !d_dev || !matches12 || !nmatches) return mfail(MCS_ERR_INVALID, "null argument");
+    if (dim != 16 && dim != 32 && dim != 64) return mfail(MCS_ERR_INVALID, "dim must be 16, 32 or 64");
+    *nmatches = 0;
+    for (int i = 0; i < nq; ++i) matches12[i] = -1;
+    if (nq <= 0 || nd <= 0) return MCS_OK;
+    return bruteforce_core(q_dev, qmask_dev, valid1, nq, d_dev, dmask_dev, valid2, nd, dim, th_low, nnratio, matches12, nmatches,
+                           (cudaStream_t)stream);
+}
+
+int mcs_match_bruteforce(const uint8_t* q, const uint8_t* qmask, const uint8_t* valid1, int32_t nq, const uint8_t* d,
+                         const uint8_t* dmask, const uint8_t* valid2, int32_t nd, int32_t dim, int32_t th_low, double nnratio,
+                         int32_t* matches12, int32_t* nmatches) {
+    if (!q || !d || !matches12 || !nmatches) return mfail(MCS_ERR_INVALID, "null argument");
+    if (dim != 16 && dim != 32 && dim != 64) return mfail(MCS_ERR_INVALID, "dim must be 16, 32 or 64");
+    *nmatches = 0;
+    for (int i = 0; i < nq; ++i) matches12[i] = -1;
+    if (nq <= 0 || nd <= 0) return MCS_OK;
+    const bool masked = qmask && dmask;
+    Dev dq, dqm, dd, ddm;
+    MCK(dq.alloc((size_t)nq * dim)); MCK(dd.alloc((size_t)nd * dim));
+    MCK(cudaMemcpy(dq.p, q, (size_t)nq * dim, cudaMemcpyHostToDevice));
+    MCK(cudaMemcpy(dd.p, d, (size_t)nd * dim, cudaMemcpyHostToDevice));
+    if (masked) {
+        MCK(dqm.alloc((size_t)nq * dim)); MCK(ddm.alloc((size_t)nd * dim));
+        MCK(cudaMemcpy(dqm.p, qmask, (size_t)nq * dim, cudaMemcpyHostToDevice));
+        MCK(cudaMemcpy(ddm.p, dmask, (size_t)nd * dim, cudaMemcpyHostToDevice));
+    }
+    return bruteforce_core(dq.as<uint8_t>(), masked ? dqm.as<uint8_t>() : nullptr, valid1, nq, dd.as<uint8_t>(),
+                           masked ? ddm.as<uint8_t>() : nullptr, valid2, nd, dim, th_low, nnratio, matches12, nmatches, nullptr);
 }
 
 // CheckDistEpipolarLine (ref src/misc.cpp:53-69): cv::Matx products accumulate s = 0; s += a*b in index order

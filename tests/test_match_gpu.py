@@ -463,3 +463,50 @@ def test_fuse_candidates_stateless_rule(api, oa, cams):
                                  np.full(max(len(q), len(KF.keys)), -1, np.int32))
     assert np.array_equal(best[i, cc], ores[:len(q)])
     assert (best[i, cc] == src).mean() > 0.5 and (best[i, cc] >= 0).sum() == on
+
+
+def test_packed_extraction_replay_and_device_bruteforce(api, oa, cams):
+    """Round-2 device-resident pieces in one flow: K3 writing straight into the packed exchange buffer (mcs_packed_layout), the
+    stream matcher's K-best lists, the on-device greedy acceptance (mcs_match_stream_replay_device) and the device-resident
+    brute-force entry (mcs_match_bruteforce_device) -- all against the oracle's SearchByBoW(KF1, KF2) per image pair."""
+    import torch
+    from multicol_slam_b200 import rig, synth
+    Fn, nc = 5, 3
+    streams = [synth.texture_stream(cams[c], Fn, seed=70 + c) for c in range(nc)]
+    imgs = np.ascontiguousarray(np.stack(streams, axis=1)).reshape(Fn * nc, 480, 754)        # frame-major
+    masks = np.stack([synth.mirror_mask(c) for c in cams])
+    ex = api.mdBRIEFextractorOct(nfeatures=600, do_dBrief=True, learnMasks=True)
+    cap, ds, B = ex.capacity, 32, Fn * nc
+    dev = torch.device("cuda", 0)
+    pitched = torch.zeros((B, 480, 768), dtype=torch.uint8, device=dev)
+    pitched[:, :, :754] = torch.from_numpy(imgs).to(dev)
+    coi = np.tile(np.arange(nc, dtype=np.int32), Fn)
+    packed = torch.zeros(rig.packed_layout(B, cap, ds)[1], dtype=torch.uint8, device=dev)
+    st = torch.cuda.Stream(dev)
+    with torch.cuda.stream(st):
+        out = ex.extract_batch_packed_device(pitched, masks, cams, coi, packed, stream=st, width=754)
+        ref = ex.extract_batch_device(pitched, masks, cams, coi, stream=st, width=754)
+        idx, dist = api.match_stream_device(out["desc"], out["dmask"], out["counts"], Fn, nc, K=4, stream=st)
+        m12, nm, redo = api.match_stream_replay_device(idx, dist, out["counts"], Fn, nc, 32, 0.9, stream=st)
+    torch.cuda.synchronize(dev)
+    for k in ("counts", "kps", "desc", "dmask"):
+        assert torch.equal(out[k], ref[k]), k
+    # the numpy unpacker reads the same buffer
+    per_img = rig.unpack(packed.cpu().numpy(), B, cap, ds)
+    counts = out["counts"].cpu().numpy()
+    assert [len(p[0]) for p in per_img] == counts.tolist()
+    assert redo.sum().item() == 0
+    m12, nm = m12.cpu().numpy(), nm.cpu().numpy()
+    for img in range(B):
+        if img < nc:
+            assert nm[img] == 0 and (m12[img] == -1).all()
+            continue
+        q, d = per_img[img], per_img[img - nc]
+        on, om = oa.match_bruteforce(q[1], d[1], 32, 0.9, q[2], d[2])
+        assert on == nm[img] and np.array_equal(om, m12[img, :counts[img]])
+        # the same pair through the device-resident brute-force entry point
+        gn, gm = api.match_bruteforce_device(out["desc"][img, :counts[img]].contiguous(), out["dmask"][img, :counts[img]].contiguous(), None,
+                                             out["desc"][img - nc, :counts[img - nc]].contiguous(),
+                                             out["dmask"][img - nc, :counts[img - nc]].contiguous(), None, 32, 0.9)
+        assert gn == on and np.array_equal(gm, om)
+    assert nm.sum() > 1000
