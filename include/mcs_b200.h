@@ -155,6 +155,21 @@ int  mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cam
                               int32_t* counts_out, int32_t capacity,
                               int32_t K, int32_t* match_idx_out, int32_t* match_dist_out);
 
+/* The stream call with two optional extras:
+ *  - packed_dev (may be NULL): the features of the batch are also left in the caller's packed exchange buffer (device memory,
+ *    mcs_packed_layout(n_frames*n_cams, capacity, descSize) bytes): K3 writes them there, the host copies are taken from there,
+ *    and mcs_allgather_features can ship the buffer to the other GPUs of the rig right after the call;
+ *  - matches12_out / nmatches_out / redo_out (all three or none; K >= 2): the greedy acceptance of SearchByBoW(KF1, KF2)
+ *    (threshold th_low, ratio nnratio, every database keypoint used once; see mcs_match_stream_replay_device) evaluated on the
+ *    device over each chunk's K-best lists; host arrays [n_images*capacity], [n_images], [n_images]. */
+int  mcs_extract_match_stream_packed(mcs_extractor* ex, int32_t n_frames, int32_t n_cams,
+                                     const uint8_t* images, int32_t width, int32_t height, int32_t stride,
+                                     const uint8_t* masks, const mcs_ocam* cams,
+                                     mcs_keypoint* kps_out, uint8_t* desc_out, uint8_t* dmask_out,
+                                     int32_t* counts_out, int32_t capacity,
+                                     int32_t K, int32_t* match_idx_out, int32_t* match_dist_out, void* packed_dev,
+                                     int32_t th_low, double nnratio, int32_t* matches12_out, int32_t* nmatches_out, int32_t* redo_out);
+
 /* Device-resident matching half of the stream form (descriptor slots as written by
  * mcs_extract_batch_device); asynchronous on `stream`. dmask_dev may be NULL (unmasked distance). */
 int  mcs_match_stream_device(const uint8_t* desc_dev, const uint8_t* dmask_dev, const int32_t* counts_dev,

@@ -205,7 +205,7 @@ class mdBRIEFextractorOct:
                                                      _p(coi), C.c_void_p(packed_t.data_ptr()), self.info.capacity, st))
         return self.packed_views(packed_t, B)
 
-    def extract_match_stream(self, images, masks, cams, K=2, out=None):
+    def extract_match_stream(self, images, masks, cams, K=2, out=None, packed_t=None, greedy=None):
         """images [F,C,H,W] u8 host (frame-major).  Extract every image and brute-force match each (frame,cam)
         against (frame-1,cam).  Returns dict(kps [F*C,cap], desc, dmask, counts, match_idx [F*C,cap,K], match_dist).
         `out` may hold preallocated (e.g. pinned) numpy arrays with the same keys."""
@@ -218,6 +218,22 @@ class mdBRIEFextractorOct:
             out = dict(kps=np.zeros((B, cap), KEYPOINT_DTYPE), desc=np.zeros((B, cap, ds), np.uint8),
                        dmask=np.zeros((B, cap, ds), np.uint8), counts=np.zeros(B, np.int32),
                        match_idx=np.zeros((B, cap, K), np.int32), match_dist=np.zeros((B, cap, K), np.int32))
+        if packed_t is not None or greedy is not None:
+            # packed_t: features also stay in the caller's packed exchange buffer on the GPU; greedy = (th_low, nnratio): the greedy
+            # acceptance of SearchByBoW(KF1, KF2) on the device -> out["matches12"] [B,cap], out["nmatches"] [B], out["redo"] [B]
+            th, ratio = greedy if greedy is not None else (0, 0.0)
+            if greedy is not None:
+                for k, shp in (("matches12", (B, cap)), ("nmatches", (B,)), ("redo", (B,))):
+                    if k not in out:
+                        out[k] = np.zeros(shp, np.int32)
+            _check(lib().mcs_extract_match_stream_packed(self._h, F, Cn, _p(images), W, H, W, _p(masks), ocs, _p(out["kps"]),
+                                                         _p(out["desc"]), _p(out["dmask"]), _p(out["counts"]), cap, K,
+                                                         _p(out["match_idx"]), _p(out["match_dist"]),
+                                                         C.c_void_p(packed_t.data_ptr()) if packed_t is not None else None, int(th),
+                                                         C.c_double(ratio), _p(out.get("matches12")) if greedy is not None else None,
+                                                         _p(out.get("nmatches")) if greedy is not None else None,
+                                                         _p(out.get("redo")) if greedy is not None else None))
+            return out
         _check(lib().mcs_extract_match_stream(self._h, F, Cn, _p(images), W, H, W, _p(masks), ocs, _p(out["kps"]),
                                               _p(out["desc"]), _p(out["dmask"]), _p(out["counts"]), cap, K,
                                               _p(out["match_idx"]), _p(out["match_dist"])))

@@ -316,13 +316,13 @@ cudaError_t launch_hamming_stream(const uint8_t* desc, const uint8_t* dmask, con
 // image pair with deeper lists); with K = 4 this needs three of a query's four nearest neighbours to be taken already.
 __global__ void __launch_bounds__(32)
 stream_replay_kernel(const int* __restrict__ list_idx, const int* __restrict__ list_dist, const int* __restrict__ counts,
-                     const int n_cams, const int capacity, const int K, const int th_low, const double nnratio,
+                     const int n_cams, const int capacity, const int K, const int img_lo, const int th_low, const double nnratio,
                      int* __restrict__ matches12, int* __restrict__ nmatches, int* __restrict__ redo) {
     extern __shared__ int s_mem[];
     int* s_li = s_mem;                              // [32][K]
     int* s_ld = s_mem + 32 * K;                     // [32][K]
     unsigned* s_taken = (unsigned*)(s_mem + 64 * K);   // [(capacity + 31) / 32]
-    const int img = blockIdx.x, lane = threadIdx.x;
+    const int img = blockIdx.x + img_lo, lane = threadIdx.x;
     const int nq = img >= n_cams ? min(counts[img], capacity) : 0;
     for (int i = lane; i < (capacity + 31) / 32; i += 32) s_taken[i] = 0u;
     for (int i = lane; i < capacity; i += 32) matches12[(size_t)img * capacity + i] = -1;
@@ -360,11 +360,11 @@ stream_replay_kernel(const int* __restrict__ list_idx, const int* __restrict__ l
     if (lane == 0) { nmatches[img] = nm; redo[img] = need_redo; }
 }
 
-cudaError_t launch_stream_replay(const int* list_idx, const int* list_dist, const int* counts, int n_images, int n_cams, int capacity,
-                                 int K, int th_low, double nnratio, int* matches12, int* nmatches, int* redo, cudaStream_t st) {
+cudaError_t launch_stream_replay(const int* list_idx, const int* list_dist, const int* counts, int img_lo, int n_images, int n_cams,
+                                 int capacity, int K, int th_low, double nnratio, int* matches12, int* nmatches, int* redo, cudaStream_t st) {
     if (n_images < 1) return cudaSuccess;
     const size_t smem = (size_t)64 * K * 4 + (size_t)((capacity + 31) / 32) * 4;
-    stream_replay_kernel<<<n_images, 32, smem, st>>>(list_idx, list_dist, counts, n_cams, capacity, K, th_low, nnratio, matches12,
+    stream_replay_kernel<<<n_images, 32, smem, st>>>(list_idx, list_dist, counts, n_cams, capacity, K, img_lo, th_low, nnratio, matches12,
                                                     nmatches, redo);
     return cudaGetLastError();
 }

@@ -96,9 +96,9 @@ struct mcs_extractor {
     DevBuf<mcs_keypoint> kps;
     DevBuf<uint8_t> desc, dmask;
     int last_n_images = 0;
-    DevBuf<int> match_idx, match_dist;
+    DevBuf<int> match_idx, match_dist, m12, nmat, redo;
     DevBuf<uint8_t> in_tight;
-    cudaStream_t s_copy = nullptr, s_out = nullptr;
+    cudaStream_t s_copy = nullptr, s_out = nullptr, s_match = nullptr;
     // distortion tables, rebuilt when the camera set changes
     std::vector<mcs_ocam> lut_cams;
     std::vector<uint8_t> masks_host;    // what ex->masks holds
@@ -522,10 +522,11 @@ void mcs_extractor_destroy(mcs_extractor* ex) {
     ex->masks.release(); ex->cams.release(); ex->cam_of_image.release(); ex->coi_all.release(); ex->raw.release(); ex->node_of.release();
     ex->raw_count.release(); ex->sel_count.release(); ex->status.release(); ex->counts.release(); ex->sel_xys.release();
     ex->kps.release(); ex->desc.release(); ex->dmask.release();
-    ex->match_idx.release(); ex->match_dist.release(); ex->lut_coef.release(); ex->luts.release(); ex->tier.release(); ex->tile_flags.release();
+    ex->match_idx.release(); ex->match_dist.release(); ex->m12.release(); ex->nmat.release(); ex->redo.release(); ex->lut_coef.release(); ex->luts.release(); ex->tier.release(); ex->tile_flags.release();
     for (int i = 0; i < 4; ++i) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
     ex->in_tight.release();
     if (ex->s_copy) cudaStreamDestroy(ex->s_copy);
+    if (ex->s_match) cudaStreamDestroy(ex->s_match);
     if (ex->s_out) cudaStreamDestroy(ex->s_out);
     if (ex->stream) cudaStreamDestroy(ex->stream);
     delete ex;
@@ -715,15 +716,18 @@ int mcs_match_stream_replay_device(const int32_t* match_idx_dev, const int32_t* 
     if (!match_idx_dev || !match_dist_dev || !counts_dev || !matches12_dev || !nmatches_dev || !redo_dev)
         return fail(MCS_ERR_INVALID, "null argument");
     if (n_frames < 1 || n_cams < 1 || capacity < 1 || K < 2 || K > 8) return fail(MCS_ERR_INVALID, "bad sizes (K must be 2..8)");
-    CK(launch_stream_replay(match_idx_dev, match_dist_dev, counts_dev, n_frames * n_cams, n_cams, capacity, K, th_low, nnratio,
+    CK(launch_stream_replay(match_idx_dev, match_dist_dev, counts_dev, 0, n_frames * n_cams, n_cams, capacity, K, th_low, nnratio,
                             matches12_dev, nmatches_dev, redo_dev, (cudaStream_t)stream));
     return MCS_OK;
 }
 
-int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams, const uint8_t* images, int32_t width,
+}  // extern "C"
+
+static int extract_match_stream_impl(mcs_extractor* ex, int32_t n_frames, int32_t n_cams, const uint8_t* images, int32_t width,
                              int32_t height, int32_t stride, const uint8_t* masks, const mcs_ocam* cams, mcs_keypoint* kps_out,
                              uint8_t* desc_out, uint8_t* dmask_out, int32_t* counts_out, int32_t capacity, int32_t K,
-                             int32_t* match_idx_out, int32_t* match_dist_out) {
+                             int32_t* match_idx_out, int32_t* match_dist_out, void* packed_dev, int32_t th_low = 0, double nnratio = 0.0,
+                             int32_t* matches12_out = nullptr, int32_t* nmatches_out = nullptr, int32_t* redo_out = nullptr) {
     if (!ex || !images || !masks || !cams || !kps_out || !desc_out || !counts_out || !match_idx_out || !match_dist_out)
         return fail(MCS_ERR_INVALID, "null argument");
     if (n_frames < 1 || n_cams < 1 || width < 1 || height < 1 || stride < width) return fail(MCS_ERR_INVALID, "bad geometry");
@@ -734,6 +738,7 @@ int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams
     cudaStream_t st = ex->stream;
     if (!ex->s_copy) CK(cudaStreamCreateWithFlags(&ex->s_copy, cudaStreamNonBlocking));
     if (!ex->s_out) CK(cudaStreamCreateWithFlags(&ex->s_out, cudaStreamNonBlocking));
+    if (!ex->s_match) CK(cudaStreamCreateWithFlags(&ex->s_match, cudaStreamNonBlocking));
     const int n_images = n_frames * n_cams, ds = ex->p.desc_size;
     const int dpitch = (width + 63) & ~63;
     // Software pipeline over chunks of frames: H2D (copy stream) | re-pitch + K1..K3 + matching (compute stream) |
@@ -769,12 +774,27 @@ int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams
     for (int i = 0; i < n_images; ++i) coi[i] = i % n_cams;
     CK(ex->in_tight.ensure(2 * tight_img * ipc + 256));
     CK(ex->in_images.ensure(pitched_img * ipc + 256));
-    CK(ex->kps.ensure((size_t)n_images * capacity));
-    CK(ex->desc.ensure((size_t)n_images * capacity * ds));
-    CK(ex->dmask.ensure((size_t)n_images * capacity * ds));
-    CK(ex->counts.ensure(n_images));
+    // feature buffers: the extractor's own, or the caller's packed exchange buffer (mcs_packed_layout) when one is given
+    mcs_keypoint* kps_d; uint8_t* desc_d; uint8_t* dmask_d; int* counts_d;
+    if (packed_dev) {
+        size_t off[4];
+        mcs_packed_layout(n_images, capacity, ds, off);
+        uint8_t* base = (uint8_t*)packed_dev;
+        counts_d = (int*)(base + off[0]); kps_d = (mcs_keypoint*)(base + off[1]); desc_d = base + off[2]; dmask_d = base + off[3];
+    } else {
+        CK(ex->kps.ensure((size_t)n_images * capacity));
+        CK(ex->desc.ensure((size_t)n_images * capacity * ds));
+        CK(ex->dmask.ensure((size_t)n_images * capacity * ds));
+        CK(ex->counts.ensure(n_images));
+        kps_d = ex->kps.p; desc_d = ex->desc.p; dmask_d = ex->dmask.p; counts_d = ex->counts.p;
+    }
     CK(ex->match_idx.ensure((size_t)n_images * capacity * K));
     CK(ex->match_dist.ensure((size_t)n_images * capacity * K));
+    const bool replay = matches12_out != nullptr;
+    if (replay) {
+        if (K < 2 || !nmatches_out || !redo_out) return fail(MCS_ERR_INVALID, "the greedy acceptance needs K >= 2 and all three outputs");
+        CK(ex->m12.ensure((size_t)n_images * capacity)); CK(ex->nmat.ensure(n_images)); CK(ex->redo.ensure(n_images));
+    }
     struct Events {                       // destroyed on every path out of this function
         std::vector<cudaEvent_t> v;
         ~Events() { for (cudaEvent_t e : v) cudaEventDestroy(e); }
@@ -805,7 +825,7 @@ int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams
     if (rc) return rc;
     CK(ex->coi_all.ensure(n_images));
     CK(cudaMemcpyAsync(ex->coi_all.p, coi.data(), sizeof(int) * n_images, cudaMemcpyHostToDevice, st));
-    const uint8_t* dmask_for_match = ex->p.learn_masks ? ex->dmask.p : nullptr;
+    const uint8_t* dmask_for_match = ex->p.learn_masks ? dmask_d : nullptr;
     // MCS_TRACE_STREAM=1: per-chunk timeline on stderr (H2D begin/end, compute begin/features/end, D2H end), ms from the first H2D
     auto mark = [&](cudaStream_t s_) { if (trace) { cudaEvent_t e; if (events.add(&e, cudaEventDefault) == cudaSuccess) { cudaEventRecord(e, s_); tev.push_back(e); } } };
     for (int c = 0; c < n_chunks && rc == MCS_OK; ++c) {
@@ -822,36 +842,49 @@ int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams
         launch_repitch(tight, stride, ex->in_images.p, dpitch, width, (size_t)height * nimg, st);
         CK(cudaEventRecord(ev_free[c], st));
         rc = run_pipeline(ex, nimg, ex->in_images.p, width, height, dpitch, masks, cams, n_cams, coi.data() + img_lo,
-                          ex->kps.p + (size_t)img_lo * capacity, ex->desc.p + (size_t)img_lo * capacity * ds,
-                          ex->dmask.p + (size_t)img_lo * capacity * ds, ex->counts.p + img_lo, capacity, st, false, ex->coi_all.p + img_lo);
+                          kps_d + (size_t)img_lo * capacity, desc_d + (size_t)img_lo * capacity * ds,
+                          dmask_d + (size_t)img_lo * capacity * ds, counts_d + img_lo, capacity, st, false, ex->coi_all.p + img_lo);
         if (rc) break;
         mark(st);
         CK(cudaEventRecord(ev_feat[c], st));                              // features of the chunk are final: their D2H overlaps the matching
-        CK(launch_hamming_stream(ex->desc.p, dmask_for_match, ex->counts.p, img_lo, nimg, n_cams, capacity, ds, K, ex->match_idx.p,
-                                 ex->match_dist.p, st));
-        mark(st);
-        CK(cudaEventRecord(ev_done[c], st));
+        // the matching of chunk c runs on its own stream, so that K1..K3 of chunk c+1 (on `st`) fill the SMs behind its tail;
+        // it reads descriptors of this chunk and of the last frame of the previous one, both final at ev_feat[c]
+        CK(cudaStreamWaitEvent(ex->s_match, ev_feat[c], 0));
+        CK(launch_hamming_stream(desc_d, dmask_for_match, counts_d, img_lo, nimg, n_cams, capacity, ds, K, ex->match_idx.p,
+                                 ex->match_dist.p, ex->s_match));
+        if (replay)     // greedy acceptance of SearchByBoW(KF1, KF2) over the lists of this chunk, still on the device
+            CK(launch_stream_replay(ex->match_idx.p, ex->match_dist.p, counts_d, img_lo, nimg, n_cams, capacity, K, th_low, nnratio, ex->m12.p,
+                                    ex->nmat.p, ex->redo.p, ex->s_match));
+        mark(ex->s_match);
+        CK(cudaEventRecord(ev_done[c], ex->s_match));
         cudaStream_t so = ex->s_out;
         CK(cudaStreamWaitEvent(so, ev_feat[c], 0));
-        CK(cudaMemcpyAsync(counts_out + img_lo, ex->counts.p + img_lo, sizeof(int) * nimg, cudaMemcpyDeviceToHost, so));
-        CK(cudaMemcpyAsync(kps_out + (size_t)img_lo * capacity, ex->kps.p + (size_t)img_lo * capacity,
+        CK(cudaMemcpyAsync(counts_out + img_lo, counts_d + img_lo, sizeof(int) * nimg, cudaMemcpyDeviceToHost, so));
+        CK(cudaMemcpyAsync(kps_out + (size_t)img_lo * capacity, kps_d + (size_t)img_lo * capacity,
                            sizeof(mcs_keypoint) * (size_t)nimg * capacity, cudaMemcpyDeviceToHost, so));
-        CK(cudaMemcpyAsync(desc_out + (size_t)img_lo * capacity * ds, ex->desc.p + (size_t)img_lo * capacity * ds,
+        CK(cudaMemcpyAsync(desc_out + (size_t)img_lo * capacity * ds, desc_d + (size_t)img_lo * capacity * ds,
                            (size_t)nimg * capacity * ds, cudaMemcpyDeviceToHost, so));
         if (dmask_out)
-            CK(cudaMemcpyAsync(dmask_out + (size_t)img_lo * capacity * ds, ex->dmask.p + (size_t)img_lo * capacity * ds,
+            CK(cudaMemcpyAsync(dmask_out + (size_t)img_lo * capacity * ds, dmask_d + (size_t)img_lo * capacity * ds,
                                (size_t)nimg * capacity * ds, cudaMemcpyDeviceToHost, so));
         CK(cudaStreamWaitEvent(so, ev_done[c], 0));
         CK(cudaMemcpyAsync(match_idx_out + (size_t)img_lo * capacity * K, ex->match_idx.p + (size_t)img_lo * capacity * K,
                            sizeof(int) * (size_t)nimg * capacity * K, cudaMemcpyDeviceToHost, so));
         CK(cudaMemcpyAsync(match_dist_out + (size_t)img_lo * capacity * K, ex->match_dist.p + (size_t)img_lo * capacity * K,
                            sizeof(int) * (size_t)nimg * capacity * K, cudaMemcpyDeviceToHost, so));
+        if (replay) {
+            CK(cudaMemcpyAsync(matches12_out + (size_t)img_lo * capacity, ex->m12.p + (size_t)img_lo * capacity, sizeof(int) * (size_t)nimg * capacity,
+                               cudaMemcpyDeviceToHost, so));
+            CK(cudaMemcpyAsync(nmatches_out + img_lo, ex->nmat.p + img_lo, sizeof(int) * nimg, cudaMemcpyDeviceToHost, so));
+            CK(cudaMemcpyAsync(redo_out + img_lo, ex->redo.p + img_lo, sizeof(int) * nimg, cudaMemcpyDeviceToHost, so));
+        }
         mark(so);
     }
     return rc;
     };
     const int rc = enqueue();
     cudaError_t e1 = cudaStreamSynchronize(ex->s_copy), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(ex->s_out);
+    { const cudaError_t e4 = cudaStreamSynchronize(ex->s_match); if (e2 == cudaSuccess) e2 = e4; }
     if (trace && !tev.empty()) {
         for (size_t i = 0; i + 5 < tev.size(); i += 6) {
             float t[6];
@@ -864,6 +897,26 @@ int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams
     CK(e1); CK(e2); CK(e3);
     ex->last_n_images = (chunk_lo[n_chunks] - chunk_lo[n_chunks - 1]) * n_cams;
     return check_status(ex, st);
+}
+
+extern "C" {
+
+int mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cams, const uint8_t* images, int32_t width,
+                             int32_t height, int32_t stride, const uint8_t* masks, const mcs_ocam* cams, mcs_keypoint* kps_out,
+                             uint8_t* desc_out, uint8_t* dmask_out, int32_t* counts_out, int32_t capacity, int32_t K,
+                             int32_t* match_idx_out, int32_t* match_dist_out) {
+    return extract_match_stream_impl(ex, n_frames, n_cams, images, width, height, stride, masks, cams, kps_out, desc_out, dmask_out,
+                                     counts_out, capacity, K, match_idx_out, match_dist_out, nullptr);
+}
+
+int mcs_extract_match_stream_packed(mcs_extractor* ex, int32_t n_frames, int32_t n_cams, const uint8_t* images, int32_t width,
+                                    int32_t height, int32_t stride, const uint8_t* masks, const mcs_ocam* cams, mcs_keypoint* kps_out,
+                                    uint8_t* desc_out, uint8_t* dmask_out, int32_t* counts_out, int32_t capacity, int32_t K,
+                                    int32_t* match_idx_out, int32_t* match_dist_out, void* packed_dev, int32_t th_low, double nnratio,
+                                    int32_t* matches12_out, int32_t* nmatches_out, int32_t* redo_out) {
+    return extract_match_stream_impl(ex, n_frames, n_cams, images, width, height, stride, masks, cams, kps_out, desc_out, dmask_out,
+                                     counts_out, capacity, K, match_idx_out, match_dist_out, packed_dev, th_low, nnratio, matches12_out,
+                                     nmatches_out, redo_out);
 }
 
 int mcs_extract_batch_packed_device(mcs_extractor* ex, int32_t n_images, const uint8_t* images_dev, int32_t width, int32_t height,

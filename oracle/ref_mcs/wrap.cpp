@@ -30,6 +30,7 @@ static const size_t kCap = (size_t)3 << 30;                 // virtual reservati
 static char* base = nullptr;
 static std::atomic<size_t> off(0);
 static std::atomic<int> on(0);
+static std::atomic<int> deterministic(1);     // 0: plain malloc (re-entrant; the timing arm of bench.py runs many extractors at once)
 static void ensure() {
     if (!base) {
         void* p = mmap(nullptr, kCap, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
@@ -39,8 +40,9 @@ static void ensure() {
 }
 static inline bool owns(const void* p) { return base && (const char*)p >= base && (const char*)p < base + kCap; }
 struct Scope {
-    Scope() { ensure(); off.store(0); on.store(1); }
-    ~Scope() { on.store(0); }
+    bool active;
+    Scope() : active(deterministic.load() != 0) { if (active) { ensure(); off.store(0); on.store(1); } }
+    ~Scope() { if (active) on.store(0); }
 };
 }  // namespace arena
 void* operator new(size_t n) {
@@ -93,6 +95,10 @@ mcsref_extractor* mcsref_extractor_create(const mcs_extractor_params* p) {
     return h;
 }
 void mcsref_extractor_destroy(mcsref_extractor* h) { if (h) { delete h->ex; delete h; } }
+
+// 1 (default): monotonic heap during a call -> reproducible pointer tie-break, one call at a time.  0: the stock allocator --
+// the extractor is then re-entrant (one instance per thread) and its tie-break is whatever the heap gives, like the stock build.
+void mcsref_set_deterministic(int on) { arena::deterministic.store(on ? 1 : 0); }
 
 int mcsref_extractor_tables(mcsref_extractor* h, int* quotas, double* sf, double* isf, int* umax17) {
     for (int l = 0; l < h->p.nlevels; ++l) {

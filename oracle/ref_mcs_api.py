@@ -36,6 +36,12 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
+def set_deterministic(on):
+    """True (default): monotonic heap during a call (reproducible pointer tie-break, one call at a time); False: stock allocator,
+    re-entrant -- for timing the reference on many threads (bench.py --impl reference)"""
+    lib().mcsref_set_deterministic(int(bool(on)))
+
+
 def _oc(cam):
     return cam if isinstance(cam, Ocam) else make_ocam(cam)
 
