@@ -788,6 +788,102 @@ class cORBmatcher:
         return sw(KF, q, mp_desc, mp_dmask if self.havingMasks else None, np.asarray(qi, np.int32), RULE_SCW, self.mfNNratio,
                   self.TH_LOW_, matched)
 
+    def SearchBySim3(self, KF1, rig1, mp1, KF2, rig2, mp2, world_pos, min_dist, max_dist, bad, mp_desc, mp_dmask, s12, R12, t12, th,
+                     matches12=None, obs_idx2=None, _sw=None):
+        """SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) (ref :1721-1988) as a whole entry point: the map points of each
+        key frame are carried into the other one by the similarity, searched in a th*scale[level] window on levels {l-1, l}
+        (best distance <= TH_HIGH_), and only mutual agreements are kept.  mp1 / mp2: map point id per keypoint (-1 none);
+        matches12 [n1]: already matched map point ids (-1 none) -- their keypoints are excluded, obs_idx2[id] = keypoint of KF2 that
+        observes map point id (GetIndexInKeyFrame(pKF2)[0]).  Returns (nFound, vpMatches12 as map point ids)."""
+        sw = search_windows if _sw is None else _sw
+        n1, n2 = len(KF1.keys), len(KF2.keys)
+        m12 = np.full(n1, -1, np.int32) if matches12 is None else np.ascontiguousarray(matches12, np.int32).copy()
+        world_pos = np.asarray(world_pos, np.float64)
+        R12, t12 = np.asarray(R12, np.float64), np.asarray(t12, np.float64)
+        T1, T2 = inv_rigid(rig1.M_t), inv_rigid(rig2.M_t)                       # GetPoseInverse()
+        sR12 = s12 * R12
+        sR21 = (1.0 / s12) * R12.T.copy()
+        t21 = _mm(-sR21, t12)
+        done1, done2 = np.zeros(n1, bool), np.zeros(n2, bool)
+        for i in range(n1):
+            if m12[i] >= 0:
+                done1[i] = True
+                j = int(obs_idx2[m12[i]]) if obs_idx2 is not None else -1
+                if 0 <= j < n2:
+                    done2[j] = True
+
+        def one_way(KFa, mpa, Ta, sR, tt, KFb, rigb, skip_a):
+            """points of a -> frame b; returns best keypoint of b per keypoint of a (-1 none)"""
+            qc, quv, qlv, qi, qd = [], [], [], [], []
+            for i in range(len(KFa.keys)):
+                p = int(mpa[i])
+                if p < 0 or skip_a[i] or bad[p]:
+                    continue
+                cam = int(KFa.key_cam[i])
+                pa = _mm(Ta[:3, :3], world_pos[p]) + Ta[:3, 3]                  # point in the MCS frame of a
+                pb = _mm(sR, pa) + tt                                           # ... of b
+                p4 = _mm(inv_rigid(rigb.M_c[cam]), np.array([pb[0], pb[1], pb[2], 1.0]))
+                if pb[2] < 0.0:
+                    continue
+                u, v = world_to_img(rigb.cams[cam], float(p4[0]), float(p4[1]), float(p4[2]))
+                if not rigb.in_mirror_mask(cam, u, v):
+                    continue
+                d = float(np.sqrt(p4[0] * p4[0] + p4[1] * p4[1] + p4[2] * p4[2]))
+                if d < min_dist[p] or d > max_dist[p]:
+                    continue
+                qc.append(cam); quv.append((u, v)); qlv.append(_predict_level(KFb.scale_factors, d / min_dist[p])); qi.append(i); qd.append(p)
+            best = np.full(len(KFa.keys), -1, np.int32)
+            if qi:
+                lv, quv2 = np.asarray(qlv), np.asarray(quv)
+                q = _queries(np.asarray(qc), quv2[:, 0], quv2[:, 1], th * KFb.scale_factors[lv], lv - 1, lv, np.asarray(qd))
+                _, res = sw(KFb, q, mp_desc, mp_dmask if self.havingMasks else None, np.zeros(len(q), np.int32), RULE_BEST_FREE,
+                            self.mfNNratio, self.TH_HIGH_, np.full(max(len(q), len(KFb.keys)), -1, np.int32))
+                best[np.asarray(qi)] = res[:len(q)]
+            return best
+        b1 = one_way(KF1, mp1, T1, sR21, t21, KF2, rig2, done1)
+        b2 = one_way(KF2, mp2, T2, sR12, t12, KF1, rig1, done2)
+        found = 0
+        for i1 in range(n1):
+            i2 = int(b1[i1])
+            if i2 >= 0 and int(b2[i2]) == i1:
+                m12[i1] = mp2[i2]
+                found += 1
+        return found, m12
+
+    def SearchForTriangulationBetweenCameras(self, KF, rig, kf_mp, rays, cam1, cam2, _sw=None):
+        """SearchForTriangulationBetweenCameras(pKF1, cam1, cam2, ...) (ref :1158-1263): every keypoint of camera cam1 without a
+        map point is carried along its bearing ray into camera cam2 of the same rig (relative orientation of the two cameras),
+        searched in a 40 px window (all levels, nothing skipped), and accepted when the best distance is <= 100 and the two rays
+        satisfy the epipolar constraint.  Returns (nmatches, pairs [n,2] of contiguous keypoint ids)."""
+        sw = search_windows if _sw is None else _sw
+        rel = _mm(inv_rigid(rig.M_c[cam1]), rig.M_c[cam2])
+        E12 = compute_E_rel(rel)
+        Rrel = rel[:3, :3].T.copy()
+        trel = _mm(-Rrel, rel[:3, 3])
+        qi, quv = [], []
+        for i in range(len(KF.keys)):
+            if kf_mp[i] >= 0 or int(KF.key_cam[i]) != cam1:
+                continue
+            rp = _mm(Rrel, rays[i]) + trel
+            rp = rp / float(np.sqrt(rp[0] * rp[0] + rp[1] * rp[1] + rp[2] * rp[2]))
+            u, v = world_to_img(rig.cams[cam2], float(rp[0]), float(rp[1]), float(rp[2]))
+            if not rig.in_mirror_mask(cam2, u, v):
+                continue
+            qi.append(i); quv.append((u, v))
+        pairs = []
+        if qi:
+            quv = np.asarray(quv)
+            q = _queries(np.full(len(qi), cam2), quv[:, 0], quv[:, 1], 40.0, -1, -1, np.asarray(qi))
+            _, res = sw(KF, q, KF.desc, KF.dmask if self.havingMasks else None, np.zeros(len(q), np.int32), RULE_BEST_FREE, self.mfNNratio,
+                        100, np.full(max(len(q), len(KF.keys)), -1, np.int32))
+            for k, i in enumerate(qi):
+                b = int(res[k])
+                # the reference evaluates the epipolar test with the best candidate even when its distance fails (:1247-1249);
+                # RULE_BEST_FREE already applied bestDist <= 100
+                if b >= 0 and check_epipolar(rays[i], rays[b], E12, 1e-2):
+                    pairs.append((i, b))
+        return len(pairs), np.asarray(pairs, np.int32).reshape(-1, 2)
+
     def SearchForTriangulationRaw(self, desc1, mask1, cam1, free1, rays1, desc2, mask2, cam2, free2, rays2, E, epi_thresh=1e-2):
         """SearchForTriangulationRaw(KF1, KF2, ...) (ref :968-1156): free1/free2 flag keypoints WITHOUT a map point, rays = bearing
         vectors [n,3], E [n_cams,n_cams,3,3] from ComputeE.  Returns (nmatches, vMatches12)."""

@@ -264,3 +264,64 @@ def test_search_by_projection_scw_equals_reference(oa, rm, api, frames, cams, ma
                                              sc["desc"], sc["dmask"], th=10, _sw=oa.search_windows)
     assert rn == on and np.array_equal(rmatched, omatched) and rn > 50
     assert omatched[0] == matched[0]                               # keypoint 0 is never assigned (:2385)
+
+
+def test_search_for_triangulation_between_cameras_equals_reference(oa, rm, api, frames, cams):
+    """a rig whose cameras overlap: keypoints of camera 0 searched in camera 1 along their bearing rays"""
+    KF = frames[0]
+    nc = 3
+    M_c = np.tile(np.eye(4), (nc, 1, 1))
+    for c in range(nc):                                            # nearly parallel cameras, 20 cm apart
+        a = 0.05 * c
+        M_c[c, :3, :3] = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+        M_c[c, :3, 3] = [0.2 * c, 0.0, 0.0]
+    rig = api.Rig(cams, M_c, np.eye(4))
+    rays, _, _ = oa.frame_prepare(KF.keys, KF.key_cam, cams)
+    rng = np.random.default_rng(2)
+    kf_mp = np.where(rng.random(len(KF.keys)) < 0.3, 0, -1).astype(np.int32)
+    table = rm.MPTable(3, np.zeros((1, 32), np.uint8))
+    for masks in (False, True):
+        m = api.cORBmatcher(0.6, False, 32, masks)
+        for c1, c2 in ((0, 1), (2, 0)):
+            rn, rp = rm.search_for_triangulation_between(rm.KF(KF, cams, M_c=M_c, mp=kf_mp, rays=rays), table, c1, c2, 0.6, masks)
+            on, op = m.SearchForTriangulationBetweenCameras(KF, rig, kf_mp, rays, c1, c2, _sw=oa.search_windows)
+            assert rn == on and np.array_equal(rp, op)
+            assert rn > 50
+
+
+@pytest.mark.parametrize("masks", [False, True])
+def test_search_by_sim3_equals_reference(oa, rm, api, frames, cams, masks):
+    """two key frames seeing the same map points from poses related by a similarity; a few matches given beforehand"""
+    KF1 = KF2 = frames[0]
+    sc1 = make_scene(api, oa, cams, KF1, 51, npts=300)
+    # key frame 2 is a second view of the same keypoints: its own map points (ids 300..599) sit where key frame 1's do, up to
+    # a few millimetres, with their own descriptor variants -- so that the two projections find each other (mutual check)
+    rng2 = np.random.default_rng(52)
+    sc2 = dict(sc1)
+    sc2["world"] = sc1["world"] + rng2.normal(0, 0.003, sc1["world"].shape)
+    sc2["desc"] = flip_bits(rng2, KF1.desc[sc1["src"]], 30)
+    n = 600
+    world = np.concatenate([sc1["world"], sc2["world"]])
+    desc = np.concatenate([sc1["desc"], sc2["desc"]]); dmask = np.concatenate([sc1["dmask"], sc2["dmask"]])
+    bad = np.concatenate([sc1["bad"], np.roll(sc1["bad"], 7)])
+    min_d = np.concatenate([sc1["min_d"], sc2["min_d"]]) * 0.5; max_d = np.concatenate([sc1["max_d"], sc2["max_d"]]) * 2.0
+    mp1 = np.full(len(KF1.keys), -1, np.int32); mp1[sc1["src"]] = np.arange(300)
+    mp2 = np.full(len(KF2.keys), -1, np.int32); mp2[sc2["src"]] = 300 + np.arange(300)
+    rng = np.random.default_rng(6)
+    a = 0.002
+    R12 = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]])
+    s12, t12 = 1.002, np.array([0.002, -0.001, 0.003])
+    pre = np.full(len(KF1.keys), -1, np.int32)
+    some = rng.choice(sc1["src"], 10, replace=False)
+    pre[some] = 300 + rng.choice(300, 10, replace=False)           # already matched to map points of key frame 2
+    obs_kf = np.concatenate([np.zeros(300, np.int32), np.ones(300, np.int32)])
+    obs_idx = np.concatenate([sc1["src"], sc2["src"]]).astype(np.int32)
+    table = rm.MPTable(3, desc, dmask=dmask, bad=bad, world_pos=world, min_dist=min_d, max_dist=max_d, obs_kf=obs_kf, obs_idx=obs_idx)
+    k1 = rm.KF(KF1, cams, M_c=sc1["M_c"], M_t=sc1["M_t"], mp=mp1)
+    k2 = rm.KF(KF2, cams, M_c=sc2["M_c"], M_t=sc2["M_t"], mp=mp2)
+    rn, r12 = rm.search_by_sim3(k1, k2, table, s12, R12, t12, 7.5, pre, 0.6, masks)
+    m = api.cORBmatcher(0.6, False, 32, masks)
+    on, o12 = m.SearchBySim3(KF1, sc1["rig"], mp1, KF2, sc2["rig"], mp2, world, min_d, max_d, bad, desc, dmask, s12, R12, t12, 7.5,
+                             matches12=pre, obs_idx2=obs_idx, _sw=oa.search_windows)
+    assert rn == on and np.array_equal(r12, o12)
+    assert rn > 10

@@ -96,3 +96,53 @@ def test_scw_rule_gpu_vs_oracle_multicamera(api, oa, frames, cams, masks):
     gn, gm = m.SearchByProjectionKFScw(*args, th=10)
     on, om = m.SearchByProjectionKFScw(*args, th=10, _sw=oa.search_windows)
     assert gn == on and np.array_equal(gm, om)
+
+
+@pytest.mark.parametrize("masks", [False, True])
+def test_sim3_and_between_cameras_gpu(api, oa, rm, frames, cams, masks):
+    """SearchBySim3 and SearchForTriangulationBetweenCameras as whole entry points over the CUDA window search: same scenes as the
+    CPU checks against the reference's own matcher; here CUDA vs the reference library (or the oracle where it did not travel)"""
+    KF = frames[0]
+    m = api.cORBmatcher(0.6, False, 32, masks)
+    # between cameras
+    M_c = np.tile(np.eye(4), (3, 1, 1))
+    for c in range(3):
+        a = 0.05 * c
+        M_c[c, :3, :3] = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+        M_c[c, :3, 3] = [0.2 * c, 0.0, 0.0]
+    rig = api.Rig(cams, M_c, np.eye(4))
+    rays, _, _ = api.frame_prepare(KF.keys, KF.key_cam, cams)
+    rng = np.random.default_rng(2)
+    kf_mp = np.where(rng.random(len(KF.keys)) < 0.3, 0, -1).astype(np.int32)
+    gn, gp = m.SearchForTriangulationBetweenCameras(KF, rig, kf_mp, rays, 0, 1)
+    if rm:
+        rn, rp = rm.search_for_triangulation_between(rm.KF(KF, cams, M_c=M_c, mp=kf_mp, rays=rays), rm.MPTable(3, np.zeros((1, 32), np.uint8)), 0, 1, 0.6, masks)
+    else:
+        rn, rp = m.SearchForTriangulationBetweenCameras(KF, rig, kf_mp, rays, 0, 1, _sw=oa.search_windows)
+    assert gn == rn and np.array_equal(gp, rp) and gn > 50
+    # Sim3
+    sc1 = T.make_scene(api, oa, cams, KF, 51, npts=300)
+    rng2 = np.random.default_rng(52)
+    w2 = sc1["world"] + rng2.normal(0, 0.003, sc1["world"].shape)
+    d2 = T.flip_bits(rng2, KF.desc[sc1["src"]], 30)
+    world = np.concatenate([sc1["world"], w2]); desc = np.concatenate([sc1["desc"], d2]); dmask = np.concatenate([sc1["dmask"], sc1["dmask"]])
+    bad = np.concatenate([sc1["bad"], np.roll(sc1["bad"], 7)])
+    min_d = np.concatenate([sc1["min_d"], sc1["min_d"]]) * 0.5; max_d = np.concatenate([sc1["max_d"], sc1["max_d"]]) * 2.0
+    mp1 = np.full(len(KF.keys), -1, np.int32); mp1[sc1["src"]] = np.arange(300)
+    mp2 = np.full(len(KF.keys), -1, np.int32); mp2[sc1["src"]] = 300 + np.arange(300)
+    a = 0.002
+    R12 = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]])
+    s12, t12 = 1.002, np.array([0.002, -0.001, 0.003])
+    pre = np.full(len(KF.keys), -1, np.int32)
+    obs_idx = np.concatenate([sc1["src"], sc1["src"]]).astype(np.int32)
+    args = (KF, sc1["rig"], mp1, KF, sc1["rig"], mp2, world, min_d, max_d, bad, desc, dmask, s12, R12, t12, 7.5)
+    gn, g12 = m.SearchBySim3(*args, matches12=pre, obs_idx2=obs_idx)
+    if rm:
+        table = rm.MPTable(3, desc, dmask=dmask, bad=bad, world_pos=world, min_dist=min_d, max_dist=max_d,
+                           obs_kf=np.concatenate([np.zeros(300, np.int32), np.ones(300, np.int32)]), obs_idx=obs_idx)
+        k1 = rm.KF(KF, cams, M_c=sc1["M_c"], M_t=sc1["M_t"], mp=mp1)
+        k2 = rm.KF(KF, cams, M_c=sc1["M_c"], M_t=sc1["M_t"], mp=mp2)
+        rn, r12 = rm.search_by_sim3(k1, k2, table, s12, R12, t12, 7.5, pre, 0.6, masks)
+    else:
+        rn, r12 = m.SearchBySim3(*args, matches12=pre, obs_idx2=obs_idx, _sw=oa.search_windows)
+    assert gn == rn and np.array_equal(g12, r12) and gn > 10
