@@ -602,7 +602,7 @@ class cORBmatcher:
             vbPrevMatched[...] = prev
         return n.value, m12
 
-    def WindowSearch(self, F1, F2, windowSize, valid1, minScaleLevel=0, maxScaleLevel=2**31 - 1):
+    def WindowSearch(self, F1, F2, windowSize, valid1, minScaleLevel=0, maxScaleLevel=2**31 - 1, _sw=None):
         """WindowSearch(F1, F2, windowSize, vpMapPointMatches2, minScaleLevel, maxScaleLevel) (ref :326-474).
         valid1[i1]: F1 keypoint i1 carries a non-bad map point.  Returns (nmatches, vnMatches21: F1 index per F2 keypoint)."""
         lv = F1.keys["octave"]
@@ -610,8 +610,8 @@ class cORBmatcher:
                              ((maxScaleLevel >= 2**31 - 1) | (lv <= maxScaleLevel)))
         q = _queries(F1.key_cam[sel], F1.keys["x"][sel].astype(np.float64), F1.keys["y"][sel].astype(np.float64),
                      float(windowSize), -1, -1, sel)
-        return search_windows(F2, q, F1.desc, F1.dmask if self.havingMasks else None, sel, RULE_RATIO, self.mfNNratio,
-                              self.TH_HIGH_, np.full(len(F2.keys), -1, np.int32))
+        return (search_windows if _sw is None else _sw)(F2, q, F1.desc, F1.dmask if self.havingMasks else None, sel, RULE_RATIO,
+                                                        self.mfNNratio, self.TH_HIGH_, np.full(len(F2.keys), -1, np.int32))
 
     def SearchByProjectionFrames(self, F1, F2, windowSize, valid1, uv, in_mask, assigned2=None):
         """SearchByProjection(F1, F2, windowSize, vpMapPointMatches2) (ref :476-573).  valid1[i1]: keypoint i1 of F1 carries a
@@ -787,6 +787,58 @@ class cORBmatcher:
         q = _queries(np.asarray(qc), quv[:, 0], quv[:, 1], float(int(th)) * KF.scale_factors[lv], lv - 1, lv, np.asarray(qi))
         return sw(KF, q, mp_desc, mp_dmask if self.havingMasks else None, np.asarray(qi, np.int32), RULE_SCW, self.mfNNratio,
                   self.TH_LOW_, matched)
+
+    def SearchByProjectionFramesRig(self, F1, mp1, F2, rig2, mp2, world_pos, bad, windowSize, _sw=None):
+        """SearchByProjection(F1, F2, windowSize, vpMapPointMatches2) (ref :476-577) as a whole entry point: every map point of F1
+        (first occurrence only, not bad, not already in F2) is projected into EVERY camera of F2's rig and searched there on the level
+        of its F1 keypoint; ratio test + TH_HIGH_, greedy.  mp1 / mp2: map point id per keypoint (-1 none).
+        Returns (nmatches, vpMapPointMatches2 as map point ids)."""
+        sw = search_windows if _sw is None else _sw
+        out = np.ascontiguousarray(mp2, np.int32).copy()
+        already = set(int(x) for x in out)                   # spMapPointsAlreadyFound holds NULL as well: harmless
+        world_pos = np.asarray(world_pos, np.float64)
+        seen = set()
+        qc, quv, qlv, qi, tags = [], [], [], [], []
+        for i1 in range(len(F1.keys)):
+            p = int(mp1[i1])
+            if p < 0 or bad[p] or p in already or p in seen:
+                continue
+            seen.add(p)
+            for c in range(len(rig2.cams)):
+                u, v, _ = rig2.world_to_cam(c, world_pos[p])
+                if rig2.in_mirror_mask(c, u, v):
+                    qc.append(c); quv.append((u, v)); qlv.append(int(F1.keys["octave"][i1])); qi.append(i1); tags.append(p)
+        if not qi:
+            return 0, out
+        quv, lv = np.asarray(quv), np.asarray(qlv)
+        q = _queries(np.asarray(qc), quv[:, 0], quv[:, 1], float(int(windowSize)), lv, lv, np.asarray(qi))
+        return sw(F2, q, F1.desc, F1.dmask if self.havingMasks else None, np.asarray(tags, np.int32), RULE_RATIO, self.mfNNratio,
+                  self.TH_HIGH_, out)
+
+    def SearchByProjectionLastRig(self, CurrentFrame, rig_cur, cur_mp, LastFrame, last_mp, last_outlier, world_pos, bad, th, _sw=None):
+        """SearchByProjection(CurrentFrame, LastFrame, th) (ref :1990-2118, motion model) as a whole entry point: the map point of
+        every LastFrame keypoint (not bad, not an outlier) is projected into the SAME camera of the current rig pose and searched
+        on levels octave-1 .. octave+1 within th*scale[octave]; best distance <= TH_HIGH_, greedy on CurrentFrame.mvpMapPoints.
+        Returns (nmatches, CurrentFrame.mvpMapPoints as map point ids)."""
+        sw = search_windows if _sw is None else _sw
+        out = np.ascontiguousarray(cur_mp, np.int32).copy()
+        world_pos = np.asarray(world_pos, np.float64)
+        qc, quv, qlv, qi, tags = [], [], [], [], []
+        for i in range(len(LastFrame.keys)):
+            p = int(last_mp[i])
+            if p < 0 or bad[p] or (last_outlier is not None and last_outlier[i]):
+                continue
+            cam = int(LastFrame.key_cam[i])
+            u, v, _ = rig_cur.world_to_cam(cam, world_pos[p])
+            if not rig_cur.in_mirror_mask(cam, u, v):
+                continue
+            qc.append(cam); quv.append((u, v)); qlv.append(int(LastFrame.keys["octave"][i])); qi.append(i); tags.append(p)
+        if not qi:
+            return 0, out
+        quv, lv = np.asarray(quv), np.asarray(qlv)
+        q = _queries(np.asarray(qc), quv[:, 0], quv[:, 1], th * CurrentFrame.scale_factors[lv], lv - 1, lv + 1, np.asarray(qi))
+        return sw(CurrentFrame, q, LastFrame.desc, LastFrame.dmask if self.havingMasks else None, np.asarray(tags, np.int32), RULE_BEST,
+                  self.mfNNratio, self.TH_HIGH_, out)
 
     def SearchBySim3(self, KF1, rig1, mp1, KF2, rig2, mp2, world_pos, min_dist, max_dist, bad, mp_desc, mp_dmask, s12, R12, t12, th,
                      matches12=None, obs_idx2=None, _sw=None):

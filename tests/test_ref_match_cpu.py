@@ -325,3 +325,79 @@ def test_search_by_sim3_equals_reference(oa, rm, api, frames, cams, masks):
                              matches12=pre, obs_idx2=obs_idx, _sw=oa.search_windows)
     assert rn == on and np.array_equal(r12, o12)
     assert rn > 10
+
+
+@pytest.mark.parametrize("masks", [False, True])
+def test_projection_searches_between_frames_equal_reference(oa, rm, api, frames, cams, masks):
+    """SearchByProjection(F1, F2, window) (:476) and SearchByProjection(CurrentFrame, LastFrame, th) (:1990) as whole entry points:
+    F1 / LastFrame carry map points that really lie on their bearing rays; F2 / CurrentFrame is the next frame of the stream
+    under a slightly different rig pose"""
+    F1, F2 = frames
+    sc = make_scene(api, oa, cams, F1, 61, npts=600)
+    n = 600
+    mp1 = np.full(len(F1.keys), -1, np.int32); mp1[sc["src"]] = np.arange(n)
+    mp1[sc["src"][5]] = mp1[sc["src"][4]]                              # the same map point twice in F1: only its first keypoint counts
+    rng = np.random.default_rng(9)
+    M_t2 = sc["M_t"].copy()
+    M_t2[:3, 3] += [0.004, -0.003, 0.002]
+    rig2 = api.Rig(cams, sc["M_c"], M_t2)
+    mp2 = np.full(len(F2.keys), -1, np.int32)
+    mp2[rng.choice(len(F2.keys), 80, replace=False)] = rng.choice(n, 80, replace=False)      # some already found in F2
+    outlier = (rng.random(len(F1.keys)) < 0.1).astype(np.uint8)
+    table = rm.MPTable(3, sc["desc"], dmask=sc["dmask"], bad=sc["bad"], world_pos=sc["world"], min_dist=sc["min_d"], max_dist=sc["max_d"])
+    k1 = rm.KF(F1, cams, M_c=sc["M_c"], M_t=sc["M_t"], mp=mp1, outlier=outlier)
+    k2 = rm.KF(F2, cams, M_c=sc["M_c"], M_t=M_t2, mp=mp2)
+    m = api.cORBmatcher(0.8, False, 32, masks)
+    rn, rout = rm.search_by_projection_frames(k1, k2, table, 40, 0.8, masks)
+    on, oout = m.SearchByProjectionFramesRig(F1, mp1, F2, rig2, mp2, sc["world"], sc["bad"], 40, _sw=oa.search_windows)
+    assert rn == on and np.array_equal(rout, oout) and rn > 50
+    rn, rout = rm.search_by_projection_last(k2, k1, table, 50.0, 0.8, masks)
+    on, oout = m.SearchByProjectionLastRig(F2, rig2, mp2, F1, mp1, outlier, sc["world"], sc["bad"], 50.0, _sw=oa.search_windows)
+    assert rn == on and np.array_equal(rout, oout) and rn > 100
+
+
+@pytest.mark.parametrize("masks", [False, True])
+def test_window_search_triangulation_and_bow_frame_equal_reference(oa, rm, api, frames, cams, masks):
+    """WindowSearch (:326), SearchForTriangulationRaw (:968, incl. ComputeE / CheckDistEpipolarLine of the reference) and
+    SearchByBoW(KF, F) (:179) against the reference's own matcher"""
+    F1, F2 = frames
+    rng = np.random.default_rng(12 + masks)
+    n1, n2 = len(F1.keys), len(F2.keys)
+    m = api.cORBmatcher(0.8, False, 32, masks)
+    # WindowSearch: F1 keypoints with a (non-bad) map point look into a 60 px window of F2, levels >= 1
+    has1 = rng.random(n1) < 0.6
+    bad = (rng.random(n1) < 0.05).astype(np.uint8)
+    mp1 = np.where(has1, np.arange(n1), -1).astype(np.int32)
+    table = rm.MPTable(3, np.zeros((n1, 32), np.uint8), bad=bad)
+    rn, rout = rm.window_search(rm.KF(F1, cams, mp=mp1), rm.KF(F2, cams), table, 60, 1, 2**31 - 1, 0.8, masks)
+    on, o21 = m.WindowSearch(F1, F2, 60, has1 & (bad == 0), 1, _sw=oa.search_windows)
+    assert rn == on and np.array_equal(rout, o21) and rn > 50               # map point id == F1 keypoint index here
+    # SearchForTriangulationRaw: keypoints WITHOUT map points, same camera only, epipolar check with E from the two rig poses
+    sc = make_scene(api, oa, cams, F1, 71, npts=10)
+    M_t2 = sc["M_t"].copy()
+    M_t2[:3, 3] += [0.05, 0.01, -0.02]
+    rays1, _, _ = oa.frame_prepare(F1.keys, F1.key_cam, cams)
+    rays2, _, _ = oa.frame_prepare(F2.keys, F2.key_cam, cams)
+    free1, free2 = rng.random(n1) < 0.5, rng.random(n2) < 0.5
+    k1 = rm.KF(F1, cams, M_c=sc["M_c"], M_t=sc["M_t"], mp=np.where(free1, -1, 0).astype(np.int32), rays=rays1)
+    k2 = rm.KF(F2, cams, M_c=sc["M_c"], M_t=M_t2, mp=np.where(free2, -1, 0).astype(np.int32), rays=rays2)
+    rn, rpairs = rm.search_for_triangulation_raw(k1, k2, rm.MPTable(3, np.zeros((1, 32), np.uint8)), 0.6, masks)
+    r1, r2 = api.Rig(cams, sc["M_c"], sc["M_t"]), api.Rig(cams, sc["M_c"], M_t2)
+    import ref_mcs_api as ra
+    E = np.zeros((3, 3, 3, 3))
+    for i in range(3):
+        for j in range(3):
+            E[i, j] = ra.compute_E(r1.MtMc_inv[i], r2.MtMc[j])              # ComputeE(Get_MtMc_inv(i), Get_MtMc(j))  (ref :989-1000)
+    th_low = rm.thresholds(32, masks)[1]
+    on, om12 = oa.search_for_triangulation(F1.desc, F1.dmask if masks else None, F1.key_cam, free1, rays1, F2.desc, F2.dmask if masks else None,
+                                           F2.key_cam, free2, rays2, E, th_low)
+    opairs = np.array([(i, om12[i]) for i in range(n1) if om12[i] >= 0], np.int32).reshape(-1, 2)
+    assert rn == on and np.array_equal(rpairs, opairs)
+    # SearchByBoW(KF, F): feature vectors from the oracle vocabulary (pinned to the reference's DBoW2 elsewhere)
+    voc = oa.OracleVocabulary(np.load(ROOT / "tests" / "golden" / "voc_small_9_6.npz"))
+    fv1, fv2 = voc.transform(F1.desc, 4)[2:], voc.transform(F2.desc, 4)[2:]
+    table = rm.MPTable(3, np.zeros((n1, 32), np.uint8), bad=bad)
+    rn, rout = rm.search_by_bow_kff(rm.KF(F1, cams, mp=mp1, featvec=fv1), rm.KF(F2, cams, featvec=fv2), table, 0.7, masks)
+    on, oout = oa.search_by_bow(F1.desc, F1.dmask if masks else None, (has1 & (bad == 0)).astype(np.uint8), fv1, F2.desc,
+                                F2.dmask if masks else None, fv2, th_low, 0.7)
+    assert rn == on and np.array_equal(rout, oout) and rn > 30
