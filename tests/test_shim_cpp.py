@@ -20,6 +20,56 @@ def test_shim_compiles_and_links(api):
     assert EXE.exists()
 
 
+def test_shim_opencv_branch_compiles(tmp_path):
+    """the -DMCS_WITH_OPENCV branch of include/mcs_shim.hpp (cv::InputArray / cv::OutputArray / std::vector<cv::KeyPoint> overload of
+    operator()) against the stand-in OpenCV header the reference-run oracle is built with (oracle/ref_mcs/stub)"""
+    src = tmp_path / "cvshim.cpp"
+    src.write_text('''#include <opencv2/opencv.hpp>
+#include "mcs_shim.hpp"
+int use(MultiColSLAM::mdBRIEFextractorOct& ex, const MultiColSLAM::cCamModelGeneral_& cam, const cv::Mat& img, const cv::Mat& mask) {
+    std::vector<cv::KeyPoint> kps; cv::Mat d, m;
+    ex(img, mask, kps, cam, d, m);            // the reference's call shape (src/cMultiFrame.cpp:138-139)
+    return (int)kps.size() + d.rows + m.rows;
+}
+''')
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-DMCS_WITH_OPENCV", "-I" + str(ROOT / "oracle/ref_mcs/stub"),
+                           "-I" + str(ROOT / "include"), str(src)])
+
+
+REF = pathlib.Path("/root/reference")
+ADAPT = ROOT / "tests" / "cpp" / "adapter_check"
+
+
+def build_adapter_check():
+    """tests/cpp/adapter_check: the reference's own cORBmatcher (objects from `make -C oracle ref`) next to include/mcs_adapters.hpp"""
+    obj = ROOT / "oracle" / "_ref" / "obj"
+    inc = ["-I" + str(ROOT / "oracle/ref_mcs/stub"), "-I" + str(ROOT / "oracle/ref_mcs/stub/g2o_cfg/a/b"), "-I" + str(ROOT / "oracle/ref_mcs"),
+           "-I" + str(REF / "include"), "-I" + str(REF / "ThirdParty/Eigen"), "-I" + str(REF / "ThirdParty/g2o"),
+           "-I" + str(REF / "ThirdParty/OpenGV/include"), "-I" + str(REF / "ThirdParty")]
+    objs = [str(obj / f) for f in ("cORBmatcher.o", "cam_system_omni.o", "cConverter.o", "cam_model_omni.o", "misc.o", "FeatureVector.o")]
+    subprocess.check_call(["g++", "-O1", "-std=c++11", "-w", "-ffp-contract=off", "-include", str(ROOT / "oracle/ref_mcs/stub_slam.h")] + inc +
+                          [str(ROOT / "tests/cpp/adapter_check.cpp")] + objs +
+                          ["-L" + str(ROOT / "multicol_slam_b200"), "-lmcs_b200", "-Wl,-rpath," + str(ROOT / "multicol_slam_b200"), "-o", str(ADAPT)])
+
+
+def test_adapters_compile_against_reference_containers(api):
+    if not (REF.exists() and (ROOT / "oracle" / "_ref" / "obj" / "cORBmatcher.o").exists()):
+        pytest.skip("needs /root/reference and `make -C oracle ref`")
+    build_adapter_check()
+    assert ADAPT.exists()
+
+
+@pytest.mark.gpu
+def test_adapters_equal_reference_matcher():
+    """C++ drop-in check: the reference's cORBmatcher::SearchByProjection / SearchForInitialization / SearchByBoW(KF,KF) and the
+    adapters over the C ABI leave the same reference-shaped containers in the same state (binary built where /root/reference exists)"""
+    if not ADAPT.exists():
+        pytest.skip("tests/cpp/adapter_check was not built (needs /root/reference)")
+    out = subprocess.run([str(ADAPT)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "adapter_check passed" in out.stdout, out.stdout + out.stderr
+    assert out.stdout.count(" ok") == 6
+
+
 @pytest.mark.gpu
 def test_shim_extract_and_match(api, oa, cams, tmp_path):
     from multicol_slam_b200 import synth
