@@ -75,6 +75,9 @@ constexpr int kDescWarps = 4;
 constexpr int kPatchR = 25;                       // staged patch: rows/cols ky/kx -25 .. +25 (keypoints are >= 25 px inside the ROI)
 constexpr int kPatchS = 64;                       // bytes per staged patch row (4-byte aligned start + 51 columns)
 constexpr int kLutDeg = 9;                        // degree of the per-centre polynomial of R(r)  (kernels.h: DistortLut)
+#ifndef MCS_K3_T1
+#define MCS_K3_T1 1                  // 0: tier 1 off (A/B builds: everything goes through tier 2)
+#endif
 #ifndef MCS_K3_MINB
 #define MCS_K3_MINB 5                // resident CTAs per SM the register budget is cut for
 #endif
@@ -403,7 +406,7 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
         const double* row = lut.coef + (size_t)ci_lut * kLutStride;
         const bool lane_valid = (PPL == 32) || (lane < ds);      // descSize 16: lanes 16..31 own no byte
         // ---- tier-1 set-up (per keypoint, all lanes redundantly; ~25 FP64 instructions against 48 points x 3 patterns) ----
-        bool t1 = have_lut && rk >= kT1MinRadius && __ldg(row + 17) == 1.0;
+        bool t1 = MCS_K3_T1 && have_lut && rk >= kT1MinRadius && __ldg(row + 17) == 1.0;
         float q[kT1Coef], K0f = 0.f, gkf = 0.f, s0f = 0.f, ukxf = 0.f, ukyf = 0.f, rk2f = 0.f, rkf = 0.f;
         float ac = 0.f, ad = 0.f, ae = 0.f, ukx2f = 0.f, uky2f = 0.f;
         if (t1) {
