@@ -449,7 +449,7 @@ def main():
             ev_gath[i].record(cstream)
         if cfg_id == 2:
             api.match_stream_device(v["desc"], v["dmask"], v["counts"], F, NC, K=K, out=(midx, mdist), stream=stream)
-            api.match_stream_replay_device(midx, mdist, v["counts"], F, NC, m.TH_LOW_, 0.9, out=(m12, nmat, redo), stream=stream)
+            api.match_stream_replay_device(midx, mdist, v["counts"], v["desc"], v["dmask"], F, NC, m.TH_LOW_, 0.9, out=(m12, nmat, redo), stream=stream)
         elif cfg_id == 3:
             match_config3(v)
         else:
@@ -481,7 +481,7 @@ def main():
             e[0].record(stream)
             api.match_stream_device(out["desc"], out["dmask"], out["counts"], F, NC, K=K, out=(midx, mdist), stream=stream)
             e[1].record(stream)
-            api.match_stream_replay_device(midx, mdist, out["counts"], F, NC, m.TH_LOW_, 0.9, out=(m12, nmat, redo), stream=stream)
+            api.match_stream_replay_device(midx, mdist, out["counts"], out["desc"], out["dmask"], F, NC, m.TH_LOW_, 0.9, out=(m12, nmat, redo), stream=stream)
             e[2].record(stream)
             torch.cuda.synchronize(dev)
             match_ms, replay_ms = e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])

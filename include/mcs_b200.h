@@ -159,7 +159,7 @@ int  mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cam
  *  - packed_dev (may be NULL): the features of the batch are also left in the caller's packed exchange buffer (device memory,
  *    mcs_packed_layout(n_frames*n_cams, capacity, descSize) bytes): K3 writes them there, the host copies are taken from there,
  *    and mcs_allgather_features can ship the buffer to the other GPUs of the rig right after the call;
- *  - matches12_out / nmatches_out / redo_out (all three or none; K >= 2): the greedy acceptance of SearchByBoW(KF1, KF2)
+ *  - matches12_out / nmatches_out / redo_out (all three or none): the greedy acceptance of SearchByBoW(KF1, KF2)
  *    (threshold th_low, ratio nnratio, every database keypoint used once; see mcs_match_stream_replay_device) evaluated on the
  *    device over each chunk's K-best lists; host arrays [n_images*capacity], [n_images], [n_images]. */
 int  mcs_extract_match_stream_packed(mcs_extractor* ex, int32_t n_frames, int32_t n_cams,
@@ -178,11 +178,14 @@ int  mcs_match_stream_device(const uint8_t* desc_dev, const uint8_t* dmask_dev, 
 
 /* The greedy acceptance of SearchByBoW(KF1, KF2) (ref src/cORBmatcher.cpp:899-961: threshold, ratio test, every database
  * keypoint used once, queries in index order) over the K-best lists of mcs_match_stream_device, on the device and on the same
- * stream: matches12_dev [n_images*capacity] = matched slot of the previous frame's image or -1, nmatches_dev [n_images],
- * redo_dev [n_images] = 1 where a list ran out before two unmatched entries were seen (recompute that pair with
- * mcs_match_bruteforce; never observed with K = 4 on frame-to-frame data).  K >= 2. */
+ * stream.  A query is decided from its list whenever the list provably contains the answer (two unmatched entries, or bounds
+ * from the last list distance); otherwise the kernel rescans the previous image for that query, so the result equals the
+ * reference's sequential loop for every K >= 1.  matches12_dev [n_images*capacity] = matched slot of the previous frame's image
+ * or -1, nmatches_dev [n_images]; redo_dev [n_images] is always 0 (kept for callers that check it).  desc_dev / dmask_dev: the
+ * descriptor slots the lists were computed from (dmask_dev NULL = unmasked). */
 int  mcs_match_stream_replay_device(const int32_t* match_idx_dev, const int32_t* match_dist_dev, const int32_t* counts_dev,
-                                    int32_t n_frames, int32_t n_cams, int32_t capacity, int32_t K, int32_t th_low, double nnratio,
+                                    const uint8_t* desc_dev, const uint8_t* dmask_dev,
+                                    int32_t n_frames, int32_t n_cams, int32_t capacity, int32_t dim, int32_t K, int32_t th_low, double nnratio,
                                     int32_t* matches12_dev, int32_t* nmatches_dev, int32_t* redo_dev, void* stream);
 
 /* Per-stage device timings of the LAST extract call, measured with CUDA events on the launching stream when

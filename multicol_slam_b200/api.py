@@ -316,7 +316,7 @@ def match_stream_device(desc_t, dmask_t, counts_t, n_frames, n_cams, K=2, out=No
     return out
 
 
-def match_stream_replay_device(idx_t, dist_t, counts_t, n_frames, n_cams, th_low, nnratio, out=None, stream=None):
+def match_stream_replay_device(idx_t, dist_t, counts_t, desc_t, dmask_t, n_frames, n_cams, th_low, nnratio, out=None, stream=None):
     """mcs_match_stream_replay_device: greedy SearchByBoW acceptance over the K-best lists, on the device.
     -> (matches12 [F*C,cap] i32, nmatches [F*C] i32, redo [F*C] i32) cuda tensors"""
     import torch
@@ -325,10 +325,10 @@ def match_stream_replay_device(idx_t, dist_t, counts_t, n_frames, n_cams, th_low
     if out is None:
         out = (torch.empty((B, cap), dtype=torch.int32, device=dev), torch.empty(B, dtype=torch.int32, device=dev),
                torch.empty(B, dtype=torch.int32, device=dev))
-    ptr = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
     st = C.c_void_p(stream.cuda_stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream)
-    _check(lib().mcs_match_stream_replay_device(ptr(idx_t), ptr(dist_t), ptr(counts_t), n_frames, n_cams, cap, K, int(th_low),
-                                                C.c_double(nnratio), ptr(out[0]), ptr(out[1]), ptr(out[2]), st))
+    _check(lib().mcs_match_stream_replay_device(ptr(idx_t), ptr(dist_t), ptr(counts_t), ptr(desc_t), ptr(dmask_t), n_frames, n_cams, cap,
+                                                desc_t.shape[-1], K, int(th_low), C.c_double(nnratio), ptr(out[0]), ptr(out[1]), ptr(out[2]), st))
     return out
 
 

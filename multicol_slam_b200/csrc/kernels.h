@@ -39,8 +39,9 @@ cudaError_t launch_hamming_topk(const uint8_t* q, const uint8_t* qmask, int nq, 
                                 cudaStream_t st);
 cudaError_t launch_hamming_stream(const uint8_t* desc, const uint8_t* dmask, const int* counts, int img_lo, int img_count,
                                   int n_cams, int capacity, int dim, int K, int* out_idx, int* out_dist, cudaStream_t st);
-cudaError_t launch_stream_replay(const int* list_idx, const int* list_dist, const int* counts, int img_lo, int n_images, int n_cams,
-                                 int capacity, int K, int th_low, double nnratio, int* matches12, int* nmatches, int* redo, cudaStream_t st);
+cudaError_t launch_stream_replay(const int* list_idx, const int* list_dist, const int* counts, const uint8_t* desc, const uint8_t* dmask,
+                                 int dim, int img_lo, int n_images, int n_cams, int capacity, int K, int th_low, double nnratio,
+                                 int* matches12, int* nmatches, int* redo, cudaStream_t st);
 void launch_repitch(const uint8_t* src, int src_stride, uint8_t* dst, int dst_pitch, int width, size_t rows, cudaStream_t st);
 struct WindowFrameDev {
     int n_cams, n_keys, dim;

@@ -309,13 +309,19 @@ cudaError_t launch_hamming_stream(const uint8_t* desc, const uint8_t* dmask, con
 }
 
 // Greedy acceptance of SearchByBoW(KF1, KF2) (ref src/cORBmatcher.cpp:899-961) over the K-best lists of the stream matcher, on
-// the device: one warp per image; the lanes fetch the lists of 32 queries at a time (coalesced), lane 0 replays them in order.
-// A query takes the first two list entries that are still unmatched as best / second best (the lists are sorted by
-// (distance, index), i.e. the reference's strict `<` scan order) and is accepted when best < th_low and best < nnratio * second.
-// When a list is used up before two unmatched entries were seen the image is flagged in redo[] (the host recomputes that
-// image pair with deeper lists); with K = 4 this needs three of a query's four nearest neighbours to be taken already.
+// the device: one warp per image; the lanes fetch the lists of 32 queries at a time (coalesced), lane 0 walks them in order.
+// The lists are sorted by (distance, index) -- the reference's strict `<` scan order -- and were computed without knowledge of
+// which database entries earlier queries have taken.  With u0, u1 the first two list entries still unmatched and dK the
+// distance of the last list entry (every entry NOT in the list is at least that far), a query is decided from its list when
+//   two unmatched entries are in it (best = u0, second = u1), or the list holds every database entry, or
+//   one is (best = u0): rejected if u0 >= th_low, accepted if u0 < nnratio * dK (the true second is >= dK), or
+//   none is: rejected if dK >= th_low.
+// Otherwise the warp rescans the whole previous image for this one query (exact best / second among the unmatched entries), so
+// the result never depends on K; redo[] stays 0 and is kept for interface stability.
+template <int WORDS, bool MASKED>
 __global__ void __launch_bounds__(32)
 stream_replay_kernel(const int* __restrict__ list_idx, const int* __restrict__ list_dist, const int* __restrict__ counts,
+                     const uint32_t* __restrict__ desc, const uint32_t* __restrict__ dmask,
                      const int n_cams, const int capacity, const int K, const int img_lo, const int th_low, const double nnratio,
                      int* __restrict__ matches12, int* __restrict__ nmatches, int* __restrict__ redo) {
     extern __shared__ int s_mem[];
@@ -323,10 +329,12 @@ stream_replay_kernel(const int* __restrict__ list_idx, const int* __restrict__ l
     int* s_ld = s_mem + 32 * K;                     // [32][K]
     unsigned* s_taken = (unsigned*)(s_mem + 64 * K);   // [(capacity + 31) / 32]
     const int img = blockIdx.x + img_lo, lane = threadIdx.x;
-    const int nq = img >= n_cams ? min(counts[img], capacity) : 0;
+    const bool has_prev = img >= n_cams;
+    const int nq = has_prev ? min(counts[img], capacity) : 0;
+    const int nd = has_prev ? min(counts[img - n_cams], capacity) : 0;
     for (int i = lane; i < (capacity + 31) / 32; i += 32) s_taken[i] = 0u;
     for (int i = lane; i < capacity; i += 32) matches12[(size_t)img * capacity + i] = -1;
-    int nm = 0, need_redo = 0;
+    int nm = 0;
     __syncwarp();
     for (int q0 = 0; q0 < nq; q0 += 32) {
         const int nchunk = min(32, nq - q0);
@@ -335,37 +343,82 @@ stream_replay_kernel(const int* __restrict__ list_idx, const int* __restrict__ l
             s_ld[i] = list_dist[((size_t)img * capacity + q0) * K + i];
         }
         __syncwarp();
-        if (lane == 0 && !need_redo) {
-            for (int t = 0; t < nchunk; ++t) {
-                int best1 = 0x7FFFFFFF, best2 = 0x7FFFFFFF, bestIdx = -1, found = 0;
+        for (int t = 0; t < nchunk; ++t) {
+            int code = 0, bestIdx = -1;              // 0 no match, 1 match bestIdx, 2 undecided from the list
+            if (lane == 0) {
+                int best1 = 0x7FFFFFFF, best2 = 0x7FFFFFFF, found = 0, dK = 0x7FFFFFFF;
                 bool complete = false;
                 for (int k = 0; k < K; ++k) {
                     const int id = s_li[t * K + k];
                     if (id < 0) { complete = true; break; }          // the list holds every database entry there is
+                    dK = s_ld[t * K + k];
                     if (s_taken[id >> 5] >> (id & 31) & 1u) continue;
                     if (found == 0) { best1 = s_ld[t * K + k]; bestIdx = id; }
                     else best2 = s_ld[t * K + k];
                     if (++found == 2) break;
                 }
-                if (found < 2 && !complete && !(found == 1 && !(best1 < th_low))) { need_redo = 1; break; }
-                if (best1 < th_low && (double)best1 < nnratio * (double)best2) {
+                if (found == 2 || complete) code = (best1 < th_low && (double)best1 < nnratio * (double)best2) ? 1 : 0;
+                else if (found == 1) code = !(best1 < th_low) ? 0 : ((double)best1 < nnratio * (double)dK ? 1 : 2);
+                else code = !(dK < th_low) ? 0 : 2;
+            }
+            code = __shfl_sync(0xffffffffu, code, 0);
+            bestIdx = __shfl_sync(0xffffffffu, bestIdx, 0);
+            if (code == 2) {
+                // exact rescan of the previous image for this query: two smallest (distance, index) keys among the unmatched entries
+                const uint32_t* qp = desc + ((size_t)img * capacity + q0 + t) * WORDS;
+                const uint32_t* qmp = MASKED ? dmask + ((size_t)img * capacity + q0 + t) * WORDS : nullptr;
+                uint32_t qw[WORDS], qm[MASKED ? WORDS : 1];
+#pragma unroll
+                for (int k = 0; k < WORDS; ++k) { qw[k] = qp[k]; if (MASKED) qm[k] = qmp[k]; }
+                unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
+                for (int id = lane; id < nd; id += 32) {
+                    if (s_taken[id >> 5] >> (id & 31) & 1u) continue;
+                    const uint32_t* dp = desc + ((size_t)(img - n_cams) * capacity + id) * WORDS;
+                    unsigned dist = 0;
+                    if (MASKED) {
+                        const uint32_t* mp = dmask + ((size_t)(img - n_cams) * capacity + id) * WORDS;
+#pragma unroll
+                        for (int k = 0; k < WORDS; ++k) { const uint32_t x = qw[k] ^ dp[k]; dist += __popc(x & qm[k]) + __popc(x & mp[k]); }
+                        dist >>= 1;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < WORDS; ++k) dist += __popc(qw[k] ^ dp[k]);
+                    }
+                    const unsigned key = (dist << 16) | (unsigned)id;
+                    if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+                }
+                const unsigned B = __reduce_min_sync(0xffffffffu, k1);
+                const unsigned S = __reduce_min_sync(0xffffffffu, k1 == B ? k2 : k1);
+                const int best1 = B == 0xFFFFFFFFu ? 0x7FFFFFFF : (int)(B >> 16), best2 = S == 0xFFFFFFFFu ? 0x7FFFFFFF : (int)(S >> 16);
+                bestIdx = (int)(B & 0xFFFFu);
+                code = (best1 < th_low && (double)best1 < nnratio * (double)best2) ? 1 : 0;
+            }
+            if (code == 1) {
+                if (lane == 0) {
                     matches12[(size_t)img * capacity + q0 + t] = bestIdx;
                     s_taken[bestIdx >> 5] |= 1u << (bestIdx & 31);
-                    ++nm;
                 }
+                ++nm;
             }
+            __syncwarp();
         }
-        __syncwarp();
     }
-    if (lane == 0) { nmatches[img] = nm; redo[img] = need_redo; }
+    if (lane == 0) { nmatches[img] = nm; redo[img] = 0; }
 }
 
-cudaError_t launch_stream_replay(const int* list_idx, const int* list_dist, const int* counts, int img_lo, int n_images, int n_cams,
-                                 int capacity, int K, int th_low, double nnratio, int* matches12, int* nmatches, int* redo, cudaStream_t st) {
+cudaError_t launch_stream_replay(const int* list_idx, const int* list_dist, const int* counts, const uint8_t* desc, const uint8_t* dmask,
+                                 int dim, int img_lo, int n_images, int n_cams, int capacity, int K, int th_low, double nnratio,
+                                 int* matches12, int* nmatches, int* redo, cudaStream_t st) {
     if (n_images < 1) return cudaSuccess;
+    if (capacity > 65535 || (dim != 16 && dim != 32 && dim != 64)) return cudaErrorInvalidValue;
     const size_t smem = (size_t)64 * K * 4 + (size_t)((capacity + 31) / 32) * 4;
-    stream_replay_kernel<<<n_images, 32, smem, st>>>(list_idx, list_dist, counts, n_cams, capacity, K, img_lo, th_low, nnratio, matches12,
-                                                    nmatches, redo);
+    const bool masked = dmask != nullptr;
+#define MCS_SR(W, M) stream_replay_kernel<W, M><<<n_images, 32, smem, st>>>(list_idx, list_dist, counts, (const uint32_t*)desc, \
+        (const uint32_t*)dmask, n_cams, capacity, K, img_lo, th_low, nnratio, matches12, nmatches, redo)
+    if (dim == 16) { if (masked) MCS_SR(4, true); else MCS_SR(4, false); }
+    else if (dim == 32) { if (masked) MCS_SR(8, true); else MCS_SR(8, false); }
+    else { if (masked) MCS_SR(16, true); else MCS_SR(16, false); }
+#undef MCS_SR
     return cudaGetLastError();
 }
 

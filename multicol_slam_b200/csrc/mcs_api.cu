@@ -711,13 +711,15 @@ int mcs_match_stream_device(const uint8_t* desc_dev, const uint8_t* dmask_dev, c
 }
 
 int mcs_match_stream_replay_device(const int32_t* match_idx_dev, const int32_t* match_dist_dev, const int32_t* counts_dev,
-                                   int32_t n_frames, int32_t n_cams, int32_t capacity, int32_t K, int32_t th_low, double nnratio,
-                                   int32_t* matches12_dev, int32_t* nmatches_dev, int32_t* redo_dev, void* stream) {
-    if (!match_idx_dev || !match_dist_dev || !counts_dev || !matches12_dev || !nmatches_dev || !redo_dev)
+                                   const uint8_t* desc_dev, const uint8_t* dmask_dev, int32_t n_frames, int32_t n_cams, int32_t capacity,
+                                   int32_t dim, int32_t K, int32_t th_low, double nnratio, int32_t* matches12_dev, int32_t* nmatches_dev,
+                                   int32_t* redo_dev, void* stream) {
+    if (!match_idx_dev || !match_dist_dev || !counts_dev || !desc_dev || !matches12_dev || !nmatches_dev || !redo_dev)
         return fail(MCS_ERR_INVALID, "null argument");
-    if (n_frames < 1 || n_cams < 1 || capacity < 1 || K < 2 || K > 8) return fail(MCS_ERR_INVALID, "bad sizes (K must be 2..8)");
-    CK(launch_stream_replay(match_idx_dev, match_dist_dev, counts_dev, 0, n_frames * n_cams, n_cams, capacity, K, th_low, nnratio,
-                            matches12_dev, nmatches_dev, redo_dev, (cudaStream_t)stream));
+    if (n_frames < 1 || n_cams < 1 || capacity < 1 || capacity > 65535 || K < 1 || K > 8) return fail(MCS_ERR_INVALID, "bad sizes (K must be 1..8)");
+    if (dim != 16 && dim != 32 && dim != 64) return fail(MCS_ERR_INVALID, "dim must be 16, 32 or 64");
+    CK(launch_stream_replay(match_idx_dev, match_dist_dev, counts_dev, desc_dev, dmask_dev, dim, 0, n_frames * n_cams, n_cams, capacity, K,
+                            th_low, nnratio, matches12_dev, nmatches_dev, redo_dev, (cudaStream_t)stream));
     return MCS_OK;
 }
 
@@ -792,7 +794,7 @@ static int extract_match_stream_impl(mcs_extractor* ex, int32_t n_frames, int32_
     CK(ex->match_dist.ensure((size_t)n_images * capacity * K));
     const bool replay = matches12_out != nullptr;
     if (replay) {
-        if (K < 2 || !nmatches_out || !redo_out) return fail(MCS_ERR_INVALID, "the greedy acceptance needs K >= 2 and all three outputs");
+        if (!nmatches_out || !redo_out) return fail(MCS_ERR_INVALID, "the greedy acceptance needs all three outputs");
         CK(ex->m12.ensure((size_t)n_images * capacity)); CK(ex->nmat.ensure(n_images)); CK(ex->redo.ensure(n_images));
     }
     struct Events {                       // destroyed on every path out of this function
@@ -853,8 +855,8 @@ static int extract_match_stream_impl(mcs_extractor* ex, int32_t n_frames, int32_
         CK(launch_hamming_stream(desc_d, dmask_for_match, counts_d, img_lo, nimg, n_cams, capacity, ds, K, ex->match_idx.p,
                                  ex->match_dist.p, ex->s_match));
         if (replay)     // greedy acceptance of SearchByBoW(KF1, KF2) over the lists of this chunk, still on the device
-            CK(launch_stream_replay(ex->match_idx.p, ex->match_dist.p, counts_d, img_lo, nimg, n_cams, capacity, K, th_low, nnratio, ex->m12.p,
-                                    ex->nmat.p, ex->redo.p, ex->s_match));
+            CK(launch_stream_replay(ex->match_idx.p, ex->match_dist.p, counts_d, desc_d, dmask_for_match, ds, img_lo, nimg, n_cams, capacity, K,
+                                    th_low, nnratio, ex->m12.p, ex->nmat.p, ex->redo.p, ex->s_match));
         mark(ex->s_match);
         CK(cudaEventRecord(ev_done[c], ex->s_match));
         cudaStream_t so = ex->s_out;

@@ -487,8 +487,12 @@ def test_packed_extraction_replay_and_device_bruteforce(api, oa, cams):
         out = ex.extract_batch_packed_device(pitched, masks, cams, coi, packed, stream=st, width=754)
         ref = ex.extract_batch_device(pitched, masks, cams, coi, stream=st, width=754)
         idx, dist = api.match_stream_device(out["desc"], out["dmask"], out["counts"], Fn, nc, K=4, stream=st)
-        m12, nm, redo = api.match_stream_replay_device(idx, dist, out["counts"], Fn, nc, 32, 0.9, stream=st)
+        m12, nm, redo = api.match_stream_replay_device(idx, dist, out["counts"], out["desc"], out["dmask"], Fn, nc, 32, 0.9, stream=st)
+        # short lists force the in-kernel rescan of undecidable queries: the result must not depend on K
+        idx1, dist1 = api.match_stream_device(out["desc"], out["dmask"], out["counts"], Fn, nc, K=1, stream=st)
+        m12b, nmb, _ = api.match_stream_replay_device(idx1, dist1, out["counts"], out["desc"], out["dmask"], Fn, nc, 32, 0.9, stream=st)
     torch.cuda.synchronize(dev)
+    assert torch.equal(m12, m12b) and torch.equal(nm, nmb)
     for k in ("counts", "kps", "desc", "dmask"):
         assert torch.equal(out[k], ref[k]), k
     # the numpy unpacker reads the same buffer
