@@ -94,9 +94,10 @@ constexpr double kLutReach = 22.5;                // half-width of a centre's in
 // per-lane partial sums + butterfly: within ~1e-13 of the reference's sequential sum).
 // Returns the descriptor byte(s) of this lane for that pattern, byte bb in bits [8bb, 8bb+8).
 template <int PPL>
-__device__ __noinline__ unsigned exact_pattern(const mcs_ocam* cam, const char2* s_pat, double ca, double sa, double ukx,
+__device__ __noinline__ unsigned exact_pattern(const mcs_ocam* cam, const char2* s_pat, double angle, double ukx,
                                                double uky, int lane, int ds, const uint8_t* bimg, const uint8_t* uimg,
                                                const LevelGeom* g, int kx, int ky) {
+    const double ca = cos(angle), sa = sin(angle);      // the reference's own cos(angle) / sin(angle) (ref :430-436)
     const double z = -cam->pol[0];
     double su = 0.0, sv = 0.0;
     for (int j = 0; j < PPL; ++j) {
@@ -176,7 +177,7 @@ __device__ __forceinline__ void tier2_point(const Tier2Poly& L, const mcs_ocam& 
     v = fma(uu, cam.e, vv + cam.v0);
 }
 template <int PPL>
-__device__ __noinline__ unsigned tier2_pattern(const mcs_ocam* camp, const double2* s_patd, const double* __restrict__ row, double ca,
+__device__ __noinline__ unsigned tier2_pattern(const mcs_ocam* camp, const float2* s_patf, const double* __restrict__ row, double ca,
                                                double sa, double ukx, double uky, int lane, int ds, const uint8_t* patch, int pofs,
                                                int* need_exact) {
     const mcs_ocam& cam = *camp;
@@ -197,7 +198,7 @@ __device__ __noinline__ unsigned tier2_pattern(const mcs_ocam* camp, const doubl
 #pragma unroll 2
     for (int j = 0; j < PPL; ++j) {
         double u, v;
-        tier2_point(L, cam, s_patd[j * 32 + lane], ca, sa, ukx, uky, u, v, worst_tau);
+        { const float2 pf = s_patf[j * 32 + lane]; tier2_point(L, cam, make_double2((double)pf.x, (double)pf.y), ca, sa, ukx, uky, u, v, worst_tau); }
         if (lane_valid) { su += u; sv += v; }
     }
 #pragma unroll
@@ -217,7 +218,7 @@ __device__ __noinline__ unsigned tier2_pattern(const mcs_ocam* camp, const doubl
 #pragma unroll
         for (int e2 = 0; e2 < 2; ++e2) {
             double u, v;
-            tier2_point(L, cam, s_patd[(j + e2) * 32 + lane], ca, sa, ukx, uky, u, v, worst_tau);
+            { const float2 pf = s_patf[(j + e2) * 32 + lane]; tier2_point(L, cam, make_double2((double)pf.x, (double)pf.y), ca, sa, ukx, uky, u, v, worst_tau); }
             const double du = u - mu, dv = v - mv;
             const double tu = du + kMagic, tv = dv + kMagic;
             int ix = __double2loint(tu), iy = __double2loint(tv);
@@ -245,16 +246,18 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                 mcs_keypoint* __restrict__ kps_out, uint8_t* __restrict__ desc_out, uint8_t* __restrict__ dmask_out,
                 int* __restrict__ counts_out, const int capacity, const int n_images) {
     __shared__ char2 s_pat[PPL * 32];            // [j][lane] : point 16*byte + k with byte = lane + 32*(j/16), k = j%16
-    __shared__ __align__(16) double2 s_patd[PPL * 32];   // same, as doubles (int->double conversions run on the slow XU pipe)
     __shared__ mcs_ocam s_cam[kDescWarps];
-    __shared__ __align__(8) float2 s_patf[PPL * 32];      // same, as floats (tier 1)
+    __shared__ __align__(8) float2 s_patf[PPL * 32];      // same, as floats (int->float conversions run on the slow XU pipe)
+    // tier 1 parks the projected coordinates of the current pattern here between its two passes ([point][lane], this lane's own
+    // slots only): with rolled loops the kernel body stays inside the instruction cache -- the fully unrolled form stalled on
+    // instruction fetch for 5.6 of every 8.5 stalled warp-cycles (profiles/r2_k3_*.md)
+    extern __shared__ __align__(8) float2 s_park_dyn[];          // [kDescWarps][PPL * 32], dynamic: 16 KB (descSize <= 32) / 32 KB
     __shared__ __align__(16) uint8_t s_patch[kDescWarps][(2 * kPatchR + 1) * kPatchS];
     const int ds = geom->desc_size;
     for (int i = threadIdx.x; i < PPL * 32; i += blockDim.x) {
         const int j = i >> 5, ln = i & 31;
         const int byte = ln + 32 * (j >> 4), pt = 16 * byte + (j & 15);
         s_pat[i] = byte < ds ? make_char2(c_pairs[2 * pt], c_pairs[2 * pt + 1]) : make_char2(0, 0);
-        s_patd[i] = make_double2((double)s_pat[i].x, (double)s_pat[i].y);
         s_patf[i] = make_float2((float)s_pat[i].x, (float)s_pat[i].y);
     }
     __syncthreads();
@@ -427,14 +430,15 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
             ukx2f = 2.f * ukxf; uky2f = 2.f * ukyf;
             ac = (float)cam.c; ad = (float)cam.d; ae = (float)cam.e;
         }
+#pragma unroll 1                         // one copy of the pattern body: the kernel has to fit the instruction cache
         for (int qi = 0; qi < npat; ++qi) {
             bool done = false;
             if (t1) {
                 // ---- tier 1: fp32, relative to the keypoint (see the header) ----
                 const float caf = (float)ca[qi], saf = (float)sa[qi];
-                float du[PPL], dv[PPL];
+                float2* park = s_park_dyn + wib * (PPL * 32);
                 float su = 0.f, sv = 0.f;
-#pragma unroll
+#pragma unroll 4
                 for (int j = 0; j < PPL; ++j) {
                     const float2 pp = s_patf[j * 32 + lane];
                     const float dx = fmaf(pp.x, caf, -pp.y * saf), dy = fmaf(pp.x, saf, pp.y * caf);
@@ -455,9 +459,10 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                     const float dg = fmaf(sp, pl, -K0f) * y;                   // g(r) - g(r_k)
                     const float g = gkf + dg;
                     const float ex = fmaf(g, dx, dg * ukxf), ey = fmaf(g, dy, dg * ukyf);
-                    du[j] = fmaf(ac, ex, ad * ey);                             // u - u_k
-                    dv[j] = fmaf(ae, ex, ey);                                  // v - v_k
-                    if (lane_valid) { su += du[j]; sv += dv[j]; }
+                    const float du = fmaf(ac, ex, ad * ey);                    // u - u_k
+                    const float dv = fmaf(ae, ex, ey);                         // v - v_k
+                    park[j * 32 + lane] = make_float2(du, dv);
+                    if (lane_valid) { su += du; sv += dv; }
                 }
                 // mean over the 16*ds points: lane partial sums in fp32 (16..32 terms), the warp reduction in double
                 double sud = (double)su, svd = (double)sv;
@@ -470,29 +475,29 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                 const float mu = (float)(sud * inv_n), mv = (float)(svd * inv_n);
                 constexpr float kMagicF = 12582912.f;                          // 1.5 * 2^23: t + magic rounds t to the nearest even integer
                 bool flag = false;
-                unsigned bits[BPL];
-#pragma unroll
-                for (int bb = 0; bb < BPL; ++bb) bits[bb] = 0;
-#pragma unroll
+                unsigned bits0 = 0, bits1 = 0;                                 // descriptor byte(s) of this lane: points 0..15 / 16..31
+#pragma unroll 2
                 for (int j = 0; j < PPL; j += 2) {
                     int smp[2];
 #pragma unroll
                     for (int e2 = 0; e2 < 2; ++e2) {
-                        const float tu = du[j + e2] - mu, tv = dv[j + e2] - mv;
+                        const float2 c = park[(j + e2) * 32 + lane];           // this lane's own slot: no synchronisation needed
+                        const float tu = c.x - mu, tv = c.y - mv;
                         const float mu_r = tu + kMagicF, mv_r = tv + kMagicF;
                         const float fu = tu - (mu_r - kMagicF), fv = tv - (mv_r - kMagicF);
-                        // near a rounding tie, or outside the staged patch (also catches NaN: the comparisons are written so that NaN flags)
+                        // near a rounding tie, or outside the staged patch (the comparisons are written so that a NaN flags too)
                         flag |= !(fabsf(fu) < 0.5f - kT1Guard) | !(fabsf(fv) < 0.5f - kT1Guard) | !(fabsf(tu) < (float)kPatchR + 0.4f) |
                                 !(fabsf(tv) < (float)kPatchR + 0.4f);
                         int ix = __float_as_int(mu_r) - 0x4B400000, iy = __float_as_int(mv_r) - 0x4B400000;
                         ix = min(max(ix, -kPatchR), kPatchR); iy = min(max(iy, -kPatchR), kPatchR);
                         smp[e2] = patch[pofs + iy * kPatchS + ix];
                     }
-                    bits[j >> 4] |= (unsigned)(smp[0] < smp[1]) << ((j & 15) >> 1);
+                    const unsigned bit = (unsigned)(smp[0] < smp[1]) << ((j & 15) >> 1);
+                    if (PPL == 16 || j < 16) bits0 |= bit; else bits1 |= bit;
                 }
                 if (!__any_sync(0xffffffffu, flag && lane_valid)) {
-#pragma unroll
-                    for (int bb = 0; bb < BPL; ++bb) val[qi][bb] = bits[bb];
+                    val[qi][0] = bits0;
+                    if (BPL > 1) val[qi][BPL - 1] = bits1;
                     done = true;
                     if (args.tier_stats && lane == 0) atomicAdd(args.tier_stats, 1ull);
                 }
@@ -501,11 +506,11 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                 // ---- tier 2 (FP64 polynomial), then tier 3 (exact) where tier 2 cannot decide ----
                 unsigned e = 0;
                 int need_exact = have_lut ? 0 : 1;
-                if (have_lut) e = tier2_pattern<PPL>(&cam, s_patd, row, ca[qi], sa[qi], ukx, uky, lane, ds, patch, pofs, &need_exact);
+                if (have_lut) e = tier2_pattern<PPL>(&cam, s_patf, row, ca[qi], sa[qi], ukx, uky, lane, ds, patch, pofs, &need_exact);
                 const bool exact = __any_sync(0xffffffffu, need_exact != 0);
                 if (exact) {
                     const double aq = qi == 0 ? a_base : (qi == 1 ? a_base + a_rot : a_base - a_rot);
-                    e = exact_pattern<PPL>(&cam, s_pat, cos(aq), sin(aq), ukx, uky, lane, ds, bimg, uimg, &g, kx, ky);
+                    e = exact_pattern<PPL>(&cam, s_pat, aq, ukx, uky, lane, ds, bimg, uimg, &g, kx, ky);
                 }
                 if (args.tier_stats && lane == 0) atomicAdd(args.tier_stats + (exact ? 2 : 1), 1ull);
 #pragma unroll
@@ -665,11 +670,16 @@ cudaError_t launch_describe(const PyramidGeom& G, const PyramidGeom* G_dev, int 
     const long long warps = (long long)n_images * G.sel_total;
     const int blocks = (int)std::max<long long>(1, (warps + kDescWarps - 1) / kDescWarps);
     // 128 registers (4 CTAs of 4 warps per SM): measured faster than 96 / 80 registers with more warps (spills), see DESIGN.md
+    const size_t park16 = (size_t)kDescWarps * 16 * 32 * sizeof(float2), park32 = 2 * park16;
+    if (G.desc_size > 32) {        // static 23 KB + 32 KB parked coordinates: above the 48 KB default
+        cudaError_t e = cudaFuncSetAttribute(describe_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)park32);
+        if (e != cudaSuccess) return e;
+    }
     if (G.desc_size <= 32)
-        describe_kernel<16><<<blocks, kDescWarps * 32, 0, st>>>(G_dev, args, cams, luts, cam_of_image, sel_xys, sel_count, kps, desc,
+        describe_kernel<16><<<blocks, kDescWarps * 32, park16, st>>>(G_dev, args, cams, luts, cam_of_image, sel_xys, sel_count, kps, desc,
                                                                dmask, counts, capacity, n_images);
     else
-        describe_kernel<32><<<blocks, kDescWarps * 32, 0, st>>>(G_dev, args, cams, luts, cam_of_image, sel_xys, sel_count, kps, desc,
+        describe_kernel<32><<<blocks, kDescWarps * 32, park32, st>>>(G_dev, args, cams, luts, cam_of_image, sel_xys, sel_count, kps, desc,
                                                                dmask, counts, capacity, n_images);
     return cudaGetLastError();
 }
