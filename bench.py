@@ -370,7 +370,7 @@ def main():
     ex = api.mdBRIEFextractorOct(nfeatures=NF, nlevels=NLEVELS, do_dBrief=True, learnMasks=True)
     cap, ds = ex.capacity, 32
     m = api.cORBmatcher(0.9, False, ds, True)
-    K = 4
+    K = int(os.environ.get("MCS_BENCH_K", "4"))      # candidates kept per query by M2 (the replay is exact for any K; K sets how often it rescans)
     pbytes = rig.packed_layout(B, cap, ds)[1]
     packed = [torch.zeros(pbytes, dtype=torch.uint8, device=dev) for _ in range(2)]       # double buffered: the gather of step i
     views = [ex.packed_views(p, B) for p in packed]                                       # overlaps the extraction of step i+1

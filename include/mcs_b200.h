@@ -197,8 +197,9 @@ int  mcs_extractor_get_timings(mcs_extractor* ex, float* ms3);
 /* Diagnostics of the descriptor kernel (K3): the distorted patterns are evaluated by the cheapest of three tiers whose error
  * bound still decides every rounding of the reference (fp32 relative to the keypoint / FP64 polynomial / exact operation
  * sequence, multicol_slam_b200/csrc/describe_kernel.cu).  enable != 0 switches counting on for the following extract calls
- * (one atomic per pattern: not for timed runs); counts3 (may be NULL) receives the patterns decided by tier 1, 2, 3 since then. */
-int  mcs_extractor_tier_stats(mcs_extractor* ex, int32_t enable, int64_t* counts3);
+ * (one atomic per pattern: not for timed runs); counts4 (may be NULL) receives the patterns decided since then by
+ * [0] tier 1, [1] tier 1 after the FP64 repair of its near-tie points, [2] tier 2, [3] tier 3. */
+int  mcs_extractor_tier_stats(mcs_extractor* ex, int32_t enable, int64_t* counts4);
 
 /* Introspection for the parity tests: copy intermediate device buffers of the LAST extract call
  * (image 0 of the batch unless image_index is given) back to the host.

@@ -243,8 +243,8 @@ class mdBRIEFextractorOct:
         _check(lib().mcs_extractor_set_profiling(self._h, int(enable)))
 
     def tier_stats(self, enable=True):
-        """K3 diagnostics: (tier1, tier2, tier3) pattern counts since counting was switched on; enable/disable counting"""
-        out = np.zeros(3, np.int64)
+        """K3 diagnostics: (tier 1, tier 1 repaired, tier 2, tier 3) pattern counts since counting was switched on; enable/disable counting"""
+        out = np.zeros(4, np.int64)
         _check(lib().mcs_extractor_tier_stats(self._h, int(enable), _p(out)))
         return out
 

@@ -41,6 +41,9 @@
 namespace mcs {
 
 __constant__ signed char c_pairs[2048];          // learned_pattern_64_ORB (ref include/mdBRIEFextractorOct.h:44-47)
+// the same pattern as floats in the kernel's [j][lane] order (point 16*byte + k, byte = lane + 32*(j/16), k = j%16): the CTAs copy it
+// to shared memory with four 8-byte loads per thread instead of rebuilding it from bytes (constant-bank loads + I2F on the XU pipe)
+__device__ float2 g_patf[1024];
 __constant__ signed char c_disc_u[848], c_disc_v[848];   // c_disc_u[0..16] = umax[] of the IC_Angle disc (ref :187-202); rest unused
 
 // cv::fastAtan2, evaluated without FMA
@@ -78,6 +81,9 @@ constexpr int kLutDeg = 9;                        // degree of the per-centre po
 #ifndef MCS_K3_T1
 #define MCS_K3_T1 1                  // 0: tier 1 off (A/B builds: everything goes through tier 2)
 #endif
+#ifndef MCS_K3_REPAIR
+#define MCS_K3_REPAIR 1              // 0: flagged tier-1 patterns go straight to tier 2 (A/B builds)
+#endif
 #ifndef MCS_K3_MINB
 #define MCS_K3_MINB 5                // resident CTAs per SM the register budget is cut for
 #endif
@@ -94,14 +100,14 @@ constexpr double kLutReach = 22.5;                // half-width of a centre's in
 // per-lane partial sums + butterfly: within ~1e-13 of the reference's sequential sum).
 // Returns the descriptor byte(s) of this lane for that pattern, byte bb in bits [8bb, 8bb+8).
 template <int PPL>
-__device__ __noinline__ unsigned exact_pattern(const mcs_ocam* cam, const char2* s_pat, double angle, double ukx,
+__device__ __noinline__ unsigned exact_pattern(const mcs_ocam* cam, const float2* s_pat, double angle, double ukx,
                                                double uky, int lane, int ds, const uint8_t* bimg, const uint8_t* uimg,
                                                const LevelGeom* g, int kx, int ky) {
     const double ca = cos(angle), sa = sin(angle);      // the reference's own cos(angle) / sin(angle) (ref :430-436)
     const double z = -cam->pol[0];
     double su = 0.0, sv = 0.0;
     for (int j = 0; j < PPL; ++j) {
-        const char2 pp = s_pat[j * 32 + lane];
+        const float2 pp = s_pat[j * 32 + lane];
         const double px = (double)pp.x, py = (double)pp.y;
         const double xr = px * ca - py * sa + ukx;
         const double yr = px * sa + py * ca + uky;
@@ -119,7 +125,7 @@ __device__ __noinline__ unsigned exact_pattern(const mcs_ocam* cam, const char2*
     for (int j = 0; j < PPL; j += 2) {
         int smp[2];
         for (int e = 0; e < 2; ++e) {
-            const char2 pp = s_pat[(j + e) * 32 + lane];
+            const float2 pp = s_pat[(j + e) * 32 + lane];
             const double px = (double)pp.x, py = (double)pp.y;
             const double xr = px * ca - py * sa + ukx;
             const double yr = px * sa + py * ca + uky;
@@ -135,13 +141,13 @@ __device__ __noinline__ unsigned exact_pattern(const mcs_ocam* cam, const char2*
 // ORB rotation (ref :285-301) and generic sampling straight from global memory; used for ORB when an offset leaves
 // the staged patch (never for sane inputs) -- keeps the reference's read semantics (blurred ROI / reflected ring).
 template <int PPL>
-__device__ __noinline__ unsigned orb_pattern_global(const char2* s_pat, double ca, double sa, int lane, const uint8_t* bimg,
+__device__ __noinline__ unsigned orb_pattern_global(const float2* s_pat, double ca, double sa, int lane, const uint8_t* bimg,
                                                     const uint8_t* uimg, const LevelGeom* g, int kx, int ky) {
     unsigned out = 0;
     for (int j = 0; j < PPL; j += 2) {
         int smp[2];
         for (int e = 0; e < 2; ++e) {
-            const char2 pp = s_pat[(j + e) * 32 + lane];
+            const float2 pp = s_pat[(j + e) * 32 + lane];
             const double px = (double)pp.x, py = (double)pp.y;
             smp[e] = sample_px(bimg, uimg, *g, ky + __double2int_rn(px * sa + py * ca), kx + __double2int_rn(px * ca - py * sa));
         }
@@ -238,6 +244,75 @@ __device__ __noinline__ unsigned tier2_pattern(const mcs_ocam* camp, const float
     return out;
 }
 
+// Tier 1 repair: a tier-1 pattern in which a few coordinates came out closer than kT1Guard to a rounding tie.  The mean of the
+// parked fp32 values is re-summed in double (its error against the exact mean is the SYSTEMATIC part of the tier-1 error only:
+// <= 1.5e-7 px, tools/k3_fp32_model.py "mean err"), and just the flagged points are recomputed through the tier-2 polynomial
+// (|error| < 2e-8 px) relative to the keypoint's own image.  A recomputed coordinate still within kT1RepairGuard of a tie, or
+// outside the patch / fitted interval, sets *fail (the whole pattern then goes to tier 2).
+constexpr double kT1RepairGuard = 2e-6;
+template <int PPL>
+__device__ __noinline__ unsigned tier1_repair(const mcs_ocam* camp, const float2* s_patf, const float2* park, const double* __restrict__ row,
+                                              double ca, double sa, double ukx, double uky, int lane, int ds, const uint8_t* patch, int pofs,
+                                              int* fail) {
+    const mcs_ocam& cam = *camp;
+    Tier2Poly L;
+    {
+        const double2* cp = (const double2*)row;
+        const double2 h = __ldg(cp);
+        L.t_off = h.x; L.t_scale = h.y;
+#pragma unroll
+        for (int k = 0; k < (kLutDeg + 1) / 2; ++k) {
+            const double2 cc = __ldg(cp + 1 + k);
+            L.P[2 * k] = cc.x; L.P[2 * k + 1] = cc.y;
+        }
+    }
+    const bool lane_valid = (PPL == 32) || (lane < ds);
+    double su = 0.0, sv = 0.0;
+#pragma unroll 4
+    for (int j = 0; j < PPL; ++j) {
+        const float2 c = park[j * 32 + lane];
+        if (lane_valid) { su += (double)c.x; sv += (double)c.y; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        su += __shfl_xor_sync(0xffffffffu, su, o);
+        sv += __shfl_xor_sync(0xffffffffu, sv, o);
+    }
+    const double inv_n = 1.0 / (double)(16 * ds);
+    const double mu = su * inv_n, mv = sv * inv_n;
+    int worst_tau = 0;
+    double uk, vk;                                     // the keypoint's own image under the same polynomial
+    tier2_point(L, cam, make_double2(0.0, 0.0), ca, sa, ukx, uky, uk, vk, worst_tau);
+    constexpr double kMagic = 6755399441055744.0;
+    bool bad = false;
+    unsigned out = 0;
+#pragma unroll 1
+    for (int j = 0; j < PPL; j += 2) {
+        int smp[2];
+#pragma unroll 1
+        for (int e2 = 0; e2 < 2; ++e2) {
+            const float2 c = park[(j + e2) * 32 + lane];
+            double tu = (double)c.x - mu, tv = (double)c.y - mv;
+            double ru = (tu + kMagic) - kMagic, rv = (tv + kMagic) - kMagic;
+            if (!(fabs(tu - ru) < 0.5 - (double)kT1Guard) || !(fabs(tv - rv) < 0.5 - (double)kT1Guard)) {
+                double u, v;
+                const float2 pf = s_patf[(j + e2) * 32 + lane];
+                tier2_point(L, cam, make_double2((double)pf.x, (double)pf.y), ca, sa, ukx, uky, u, v, worst_tau);
+                tu = (u - uk) - mu; tv = (v - vk) - mv;
+                ru = (tu + kMagic) - kMagic; rv = (tv + kMagic) - kMagic;
+                bad |= !(fabs(tu - ru) < 0.5 - kT1RepairGuard) || !(fabs(tv - rv) < 0.5 - kT1RepairGuard);
+            }
+            bad |= !(fabs(tu) < (double)kPatchR + 0.4) || !(fabs(tv) < (double)kPatchR + 0.4);
+            int ix = (int)ru, iy = (int)rv;
+            ix = min(max(ix, -kPatchR), kPatchR); iy = min(max(iy, -kPatchR), kPatchR);
+            smp[e2] = patch[pofs + iy * kPatchS + ix];
+        }
+        out |= (unsigned)(smp[0] < smp[1]) << (j >> 1);
+    }
+    if (lane_valid && (bad || worst_tau >= __double2hiint(1.0))) *fail = 1;
+    return out;
+}
+
 template <int PPL /* pattern points per lane: 16 for descSize <= 32, 32 for descSize 64 */, int MINB = MCS_K3_MINB>
 __global__ void __launch_bounds__(kDescWarps * 32, MINB)
 describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, const mcs_ocam* __restrict__ cams,
@@ -245,21 +320,17 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                 const uint32_t* __restrict__ sel_xys, const int* __restrict__ sel_count,
                 mcs_keypoint* __restrict__ kps_out, uint8_t* __restrict__ desc_out, uint8_t* __restrict__ dmask_out,
                 int* __restrict__ counts_out, const int capacity, const int n_images) {
-    __shared__ char2 s_pat[PPL * 32];            // [j][lane] : point 16*byte + k with byte = lane + 32*(j/16), k = j%16
     __shared__ mcs_ocam s_cam[kDescWarps];
-    __shared__ __align__(8) float2 s_patf[PPL * 32];      // same, as floats (int->float conversions run on the slow XU pipe)
+    __shared__ __align__(8) float2 s_patf[PPL * 32];      // [j][lane] : point 16*byte + k with byte = lane + 32*(j/16), k = j%16, as floats
     // tier 1 parks the projected coordinates of the current pattern here between its two passes ([point][lane], this lane's own
     // slots only): with rolled loops the kernel body stays inside the instruction cache -- the fully unrolled form stalled on
     // instruction fetch for 5.6 of every 8.5 stalled warp-cycles (profiles/r2_k3_*.md)
     extern __shared__ __align__(8) float2 s_park_dyn[];          // [kDescWarps][PPL * 32], dynamic: 16 KB (descSize <= 32) / 32 KB
     __shared__ __align__(16) uint8_t s_patch[kDescWarps][(2 * kPatchR + 1) * kPatchS];
     const int ds = geom->desc_size;
-    for (int i = threadIdx.x; i < PPL * 32; i += blockDim.x) {
-        const int j = i >> 5, ln = i & 31;
-        const int byte = ln + 32 * (j >> 4), pt = 16 * byte + (j & 15);
-        s_pat[i] = byte < ds ? make_char2(c_pairs[2 * pt], c_pairs[2 * pt + 1]) : make_char2(0, 0);
-        s_patf[i] = make_float2((float)s_pat[i].x, (float)s_pat[i].y);
-    }
+    // (lanes that own no descriptor byte -- descSize 16 -- carry real pattern points too; every use is guarded by lane_valid)
+#pragma unroll
+    for (int i = threadIdx.x; i < PPL * 32; i += kDescWarps * 32) s_patf[i] = g_patf[i];
     __syncthreads();
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -371,14 +442,14 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
         bool far = false;
 #pragma unroll
         for (int j = 0; j < PPL; ++j) {
-            const char2 pp = s_pat[j * 32 + lane];
+            const float2 pp = s_patf[j * 32 + lane];
             const double px = (double)pp.x, py = (double)pp.y;
             ix[j] = __double2int_rn(px * ca[0] - py * sa[0]);
             iy[j] = __double2int_rn(px * sa[0] + py * ca[0]);
             far |= (unsigned)(ix[j] + kPatchR) > 2u * kPatchR || (unsigned)(iy[j] + kPatchR) > 2u * kPatchR;
         }
         if (__any_sync(0xffffffffu, far)) {
-            const unsigned e = orb_pattern_global<PPL>(s_pat, ca[0], sa[0], lane, bimg, uimg, &g, kx, ky);
+            const unsigned e = orb_pattern_global<PPL>(s_patf, ca[0], sa[0], lane, bimg, uimg, &g, kx, ky);
 #pragma unroll
             for (int bb = 0; bb < BPL; ++bb) val[0][bb] = (e >> (8 * bb)) & 0xFFu;
         } else {
@@ -410,8 +481,7 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
         const bool lane_valid = (PPL == 32) || (lane < ds);      // descSize 16: lanes 16..31 own no byte
         // ---- tier-1 set-up (per keypoint, all lanes redundantly; ~25 FP64 instructions against 48 points x 3 patterns) ----
         bool t1 = MCS_K3_T1 && have_lut && rk >= kT1MinRadius && __ldg(row + 17) == 1.0;
-        float q[kT1Coef], K0f = 0.f, gkf = 0.f, s0f = 0.f, ukxf = 0.f, ukyf = 0.f, rk2f = 0.f, rkf = 0.f;
-        float ac = 0.f, ad = 0.f, ae = 0.f, ukx2f = 0.f, uky2f = 0.f;
+        float q[kT1Coef], K0f = 0.f, gkf = 0.f, s0f = 0.f, rk2f = 0.f, rkf = 0.f, auk = 0.f, avk = 0.f;
         if (t1) {
             const double Ri = __ldg(row + 12), q0d = __ldg(row + 13);
             const float2 c12 = __ldg((const float2*)(row + 14)), c34 = __ldg((const float2*)(row + 15)), c5x = __ldg((const float2*)(row + 16));
@@ -426,24 +496,26 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
             q[0] = (float)(q0d - gk * (double)kT1Scale);
             K0f = (float)(dRk - gk * (rk - (double)ci_lut));
             gkf = (float)gk; s0f = (float)s0;
-            ukxf = (float)ukx; ukyf = (float)uky; rk2f = (float)(rk * rk); rkf = (float)rk;
-            ukx2f = 2.f * ukxf; uky2f = 2.f * ukyf;
-            ac = (float)cam.c; ad = (float)cam.d; ae = (float)cam.e;
+            rk2f = (float)(rk * rk); rkf = (float)rk;
+            auk = (float)(cam.c * ukx + cam.d * uky); avk = (float)(cam.e * ukx + uky);      // A X_k
         }
 #pragma unroll 1                         // one copy of the pattern body: the kernel has to fit the instruction cache
         for (int qi = 0; qi < npat; ++qi) {
             bool done = false;
             if (t1) {
                 // ---- tier 1: fp32, relative to the keypoint (see the header) ----
-                const float caf = (float)ca[qi], saf = (float)sa[qi];
+                // rotation folded into per-pattern constants (double -> float once): with p the pattern point and d = Rot p,
+                //   n = r^2 - r_k^2 = |p|^2 + 2 (Rot^T X_k).p            (|d| = |p|: no rotated point needed for n)
+                //   u - u_k = g (A Rot p).x + dg (A X_k).x               (A = affine part [c d; e 1])
+                const float nx = (float)(2.0 * (ukx * ca[qi] + uky * sa[qi])), ny = (float)(2.0 * (uky * ca[qi] - ukx * sa[qi]));
+                const float axx = (float)(cam.c * ca[qi] + cam.d * sa[qi]), axy = (float)(cam.d * ca[qi] - cam.c * sa[qi]);
+                const float ayx = (float)(cam.e * ca[qi] + sa[qi]), ayy = (float)(ca[qi] - cam.e * sa[qi]);
                 float2* park = s_park_dyn + wib * (PPL * 32);
                 float su = 0.f, sv = 0.f;
 #pragma unroll 4
                 for (int j = 0; j < PPL; ++j) {
                     const float2 pp = s_patf[j * 32 + lane];
-                    const float dx = fmaf(pp.x, caf, -pp.y * saf), dy = fmaf(pp.x, saf, pp.y * caf);
-                    // n = r^2 - r_k^2 = 2 X_k.d + |d|^2
-                    const float n = fmaf(dx, dx + ukx2f, dy * (dy + uky2f));
+                    const float n = fmaf(pp.x, nx, fmaf(pp.y, ny, fmaf(pp.x, pp.x, pp.y * pp.y)));
                     const float r2 = rk2f + n;
                     float y, z;
                     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(r2));   // MUFU + one Newton step each: ~1 ulp
@@ -458,9 +530,8 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                     pl = fmaf(pl, sp, q[1]); pl = fmaf(pl, sp, q[0]);
                     const float dg = fmaf(sp, pl, -K0f) * y;                   // g(r) - g(r_k)
                     const float g = gkf + dg;
-                    const float ex = fmaf(g, dx, dg * ukxf), ey = fmaf(g, dy, dg * ukyf);
-                    const float du = fmaf(ac, ex, ad * ey);                    // u - u_k
-                    const float dv = fmaf(ae, ex, ey);                         // v - v_k
+                    const float du = fmaf(g, fmaf(pp.x, axx, pp.y * axy), dg * auk);   // u - u_k
+                    const float dv = fmaf(g, fmaf(pp.x, ayx, pp.y * ayy), dg * avk);   // v - v_k
                     park[j * 32 + lane] = make_float2(du, dv);
                     if (lane_valid) { su += du; sv += dv; }
                 }
@@ -488,9 +559,11 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                         // near a rounding tie, or outside the staged patch (the comparisons are written so that a NaN flags too)
                         flag |= !(fabsf(fu) < 0.5f - kT1Guard) | !(fabsf(fv) < 0.5f - kT1Guard) | !(fabsf(tu) < (float)kPatchR + 0.4f) |
                                 !(fabsf(tv) < (float)kPatchR + 0.4f);
-                        int ix = __float_as_int(mu_r) - 0x4B400000, iy = __float_as_int(mv_r) - 0x4B400000;
-                        ix = min(max(ix, -kPatchR), kPatchR); iy = min(max(iy, -kPatchR), kPatchR);
-                        smp[e2] = patch[pofs + iy * kPatchS + ix];
+                        const int ix = __float_as_int(mu_r) - 0x4B400000, iy = __float_as_int(mv_r) - 0x4B400000;
+                        // one clamp of the byte offset keeps the read inside the patch array; an offset that needed it belongs to a
+                        // flagged coordinate (|t| >= 25.4) and the pattern is redone
+                        const int ofs = min(max(iy * kPatchS + ix, -(kPatchR * kPatchS + kPatchR)), kPatchR * kPatchS + kPatchR);
+                        smp[e2] = patch[pofs + ofs];
                     }
                     const unsigned bit = (unsigned)(smp[0] < smp[1]) << ((j & 15) >> 1);
                     if (PPL == 16 || j < 16) bits0 |= bit; else bits1 |= bit;
@@ -500,6 +573,15 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                     if (BPL > 1) val[qi][BPL - 1] = bits1;
                     done = true;
                     if (args.tier_stats && lane == 0) atomicAdd(args.tier_stats, 1ull);
+                } else if (MCS_K3_REPAIR) {
+                    int fail = 0;
+                    const unsigned e = tier1_repair<PPL>(&cam, s_patf, park, row, ca[qi], sa[qi], ukx, uky, lane, ds, patch, pofs, &fail);
+                    if (!__any_sync(0xffffffffu, fail != 0)) {
+#pragma unroll
+                        for (int bb = 0; bb < BPL; ++bb) val[qi][bb] = (e >> (8 * bb)) & 0xFFu;
+                        done = true;
+                        if (args.tier_stats && lane == 0) atomicAdd(args.tier_stats + 1, 1ull);
+                    }
                 }
             }
             if (!done) {
@@ -510,9 +592,9 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                 const bool exact = __any_sync(0xffffffffu, need_exact != 0);
                 if (exact) {
                     const double aq = qi == 0 ? a_base : (qi == 1 ? a_base + a_rot : a_base - a_rot);
-                    e = exact_pattern<PPL>(&cam, s_pat, aq, ukx, uky, lane, ds, bimg, uimg, &g, kx, ky);
+                    e = exact_pattern<PPL>(&cam, s_patf, aq, ukx, uky, lane, ds, bimg, uimg, &g, kx, ky);
                 }
-                if (args.tier_stats && lane == 0) atomicAdd(args.tier_stats + (exact ? 2 : 1), 1ull);
+                if (args.tier_stats && lane == 0) atomicAdd(args.tier_stats + (exact ? 3 : 2), 1ull);
 #pragma unroll
                 for (int bb = 0; bb < BPL; ++bb) val[qi][bb] = (e >> (8 * bb)) & 0xFFu;
             }
@@ -546,6 +628,15 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
 cudaError_t upload_constants(const signed char* pairs, const signed char* du, const signed char* dv) {
     cudaError_t e = cudaMemcpyToSymbol(c_pairs, pairs, 2048);
     if (e != cudaSuccess) return e;
+    {
+        std::vector<float2> pf(1024);
+        for (int i = 0; i < 1024; ++i) {
+            const int j = i >> 5, ln = i & 31, byte = ln + 32 * (j >> 4), pt = 16 * byte + (j & 15);
+            pf[i] = make_float2((float)pairs[2 * pt], (float)pairs[2 * pt + 1]);
+        }
+        e = cudaMemcpyToSymbol(g_patf, pf.data(), sizeof(float2) * 1024);
+        if (e != cudaSuccess) return e;
+    }
     e = cudaMemcpyToSymbol(c_disc_u, du, 848);
     if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbol(c_disc_v, dv, 848);

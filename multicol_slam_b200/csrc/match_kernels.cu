@@ -318,8 +318,60 @@ cudaError_t launch_hamming_stream(const uint8_t* desc, const uint8_t* dmask, con
 //   none is: rejected if dK >= th_low.
 // Otherwise the warp rescans the whole previous image for this one query (exact best / second among the unmatched entries), so
 // the result never depends on K; redo[] stays 0 and is kept for interface stability.
+constexpr int kReplayThreads = 256;
+
+__device__ __forceinline__ void named_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kReplayThreads) : "memory"); }
+
+// two smallest (distance << 16 | index) keys among this thread's share of the unmatched entries of the previous image
 template <int WORDS, bool MASKED>
-__global__ void __launch_bounds__(32)
+__device__ __forceinline__ void replay_scan(const uint32_t* __restrict__ desc, const uint32_t* __restrict__ dmask, const size_t q_row,
+                                            const size_t d_row0, const int nd, const unsigned* s_taken, const int tid,
+                                            unsigned& k1, unsigned& k2) {
+    uint4 qw[WORDS / 4], qm[MASKED ? WORDS / 4 : 1];
+    const uint4* qp = reinterpret_cast<const uint4*>(desc + q_row * WORDS);
+#pragma unroll
+    for (int k = 0; k < WORDS / 4; ++k) qw[k] = qp[k];
+    if (MASKED) {
+        const uint4* qmp = reinterpret_cast<const uint4*>(dmask + q_row * WORDS);
+#pragma unroll
+        for (int k = 0; k < WORDS / 4; ++k) qm[k] = qmp[k];
+    }
+    k1 = 0xFFFFFFFFu; k2 = 0xFFFFFFFFu;
+#pragma unroll 2
+    for (int id = tid; id < nd; id += kReplayThreads) {
+        if (s_taken[id >> 5] >> (id & 31) & 1u) continue;
+        const uint4* dp = reinterpret_cast<const uint4*>(desc + (d_row0 + id) * WORDS);
+        unsigned dist = 0;
+        if (MASKED) {
+            const uint4* mp = reinterpret_cast<const uint4*>(dmask + (d_row0 + id) * WORDS);
+#pragma unroll
+            for (int k = 0; k < WORDS / 4; ++k) {
+                const uint4 d = dp[k], m = mp[k];
+                const uint32_t x0 = qw[k].x ^ d.x, x1 = qw[k].y ^ d.y, x2 = qw[k].z ^ d.z, x3 = qw[k].w ^ d.w;
+                dist += __popc(x0 & qm[k].x) + __popc(x0 & m.x) + __popc(x1 & qm[k].y) + __popc(x1 & m.y) +
+                        __popc(x2 & qm[k].z) + __popc(x2 & m.z) + __popc(x3 & qm[k].w) + __popc(x3 & m.w);
+            }
+            dist >>= 1;
+        } else {
+#pragma unroll
+            for (int k = 0; k < WORDS / 4; ++k) {
+                const uint4 d = dp[k];
+                dist += __popc(qw[k].x ^ d.x) + __popc(qw[k].y ^ d.y) + __popc(qw[k].z ^ d.z) + __popc(qw[k].w ^ d.w);
+            }
+        }
+        const unsigned key = (dist << 16) | (unsigned)id;
+        if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
+    }
+    // warp: smallest and second smallest of the 64 keys (keys are unique: the index is part of the key)
+    const unsigned B = __reduce_min_sync(0xffffffffu, k1);
+    const unsigned S = __reduce_min_sync(0xffffffffu, k1 == B ? k2 : k1);
+    k1 = B; k2 = S;
+}
+
+// One CTA per image.  Warp 0 walks the queries in order (lane 0 decides from the list); the other warps sleep on a named barrier
+// and wake only for a rescan, where all 256 threads split the previous image.
+template <int WORDS, bool MASKED>
+__global__ void __launch_bounds__(kReplayThreads)
 stream_replay_kernel(const int* __restrict__ list_idx, const int* __restrict__ list_dist, const int* __restrict__ counts,
                      const uint32_t* __restrict__ desc, const uint32_t* __restrict__ dmask,
                      const int n_cams, const int capacity, const int K, const int img_lo, const int th_low, const double nnratio,
@@ -328,14 +380,28 @@ stream_replay_kernel(const int* __restrict__ list_idx, const int* __restrict__ l
     int* s_li = s_mem;                              // [32][K]
     int* s_ld = s_mem + 32 * K;                     // [32][K]
     unsigned* s_taken = (unsigned*)(s_mem + 64 * K);   // [(capacity + 31) / 32]
-    const int img = blockIdx.x + img_lo, lane = threadIdx.x;
+    __shared__ int s_cmd;
+    __shared__ unsigned s_k1[kReplayThreads / 32], s_k2[kReplayThreads / 32];
+    const int img = blockIdx.x + img_lo, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool has_prev = img >= n_cams;
     const int nq = has_prev ? min(counts[img], capacity) : 0;
     const int nd = has_prev ? min(counts[img - n_cams], capacity) : 0;
-    for (int i = lane; i < (capacity + 31) / 32; i += 32) s_taken[i] = 0u;
-    for (int i = lane; i < capacity; i += 32) matches12[(size_t)img * capacity + i] = -1;
+    const size_t d_row0 = has_prev ? (size_t)(img - n_cams) * capacity : 0;
+    for (int i = tid; i < (capacity + 31) / 32; i += kReplayThreads) s_taken[i] = 0u;
+    for (int i = tid; i < capacity; i += kReplayThreads) matches12[(size_t)img * capacity + i] = -1;
+    __syncthreads();
+    if (warp != 0) {
+        for (;;) {
+            named_bar(1);
+            const int cmd = *(volatile int*)&s_cmd;
+            if (cmd < 0) return;
+            unsigned k1, k2;
+            replay_scan<WORDS, MASKED>(desc, dmask, (size_t)img * capacity + cmd, d_row0, nd, s_taken, tid, k1, k2);
+            if (lane == 0) { s_k1[warp] = k1; s_k2[warp] = k2; }
+            named_bar(2);
+        }
+    }
     int nm = 0;
-    __syncwarp();
     for (int q0 = 0; q0 < nq; q0 += 32) {
         const int nchunk = min(32, nq - q0);
         for (int i = lane; i < nchunk * K; i += 32) {
@@ -365,28 +431,14 @@ stream_replay_kernel(const int* __restrict__ list_idx, const int* __restrict__ l
             bestIdx = __shfl_sync(0xffffffffu, bestIdx, 0);
             if (code == 2) {
                 // exact rescan of the previous image for this query: two smallest (distance, index) keys among the unmatched entries
-                const uint32_t* qp = desc + ((size_t)img * capacity + q0 + t) * WORDS;
-                const uint32_t* qmp = MASKED ? dmask + ((size_t)img * capacity + q0 + t) * WORDS : nullptr;
-                uint32_t qw[WORDS], qm[MASKED ? WORDS : 1];
-#pragma unroll
-                for (int k = 0; k < WORDS; ++k) { qw[k] = qp[k]; if (MASKED) qm[k] = qmp[k]; }
-                unsigned k1 = 0xFFFFFFFFu, k2 = 0xFFFFFFFFu;
-                for (int id = lane; id < nd; id += 32) {
-                    if (s_taken[id >> 5] >> (id & 31) & 1u) continue;
-                    const uint32_t* dp = desc + ((size_t)(img - n_cams) * capacity + id) * WORDS;
-                    unsigned dist = 0;
-                    if (MASKED) {
-                        const uint32_t* mp = dmask + ((size_t)(img - n_cams) * capacity + id) * WORDS;
-#pragma unroll
-                        for (int k = 0; k < WORDS; ++k) { const uint32_t x = qw[k] ^ dp[k]; dist += __popc(x & qm[k]) + __popc(x & mp[k]); }
-                        dist >>= 1;
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < WORDS; ++k) dist += __popc(qw[k] ^ dp[k]);
-                    }
-                    const unsigned key = (dist << 16) | (unsigned)id;
-                    if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
-                }
+                if (lane == 0) s_cmd = q0 + t;
+                named_bar(1);
+                unsigned k1, k2;
+                replay_scan<WORDS, MASKED>(desc, dmask, (size_t)img * capacity + q0 + t, d_row0, nd, s_taken, tid, k1, k2);
+                if (lane == 0) { s_k1[0] = k1; s_k2[0] = k2; }
+                named_bar(2);
+                k1 = lane < kReplayThreads / 32 ? s_k1[lane] : 0xFFFFFFFFu;
+                k2 = lane < kReplayThreads / 32 ? s_k2[lane] : 0xFFFFFFFFu;
                 const unsigned B = __reduce_min_sync(0xffffffffu, k1);
                 const unsigned S = __reduce_min_sync(0xffffffffu, k1 == B ? k2 : k1);
                 const int best1 = B == 0xFFFFFFFFu ? 0x7FFFFFFF : (int)(B >> 16), best2 = S == 0xFFFFFFFFu ? 0x7FFFFFFF : (int)(S >> 16);
@@ -403,7 +455,8 @@ stream_replay_kernel(const int* __restrict__ list_idx, const int* __restrict__ l
             __syncwarp();
         }
     }
-    if (lane == 0) { nmatches[img] = nm; redo[img] = 0; }
+    if (lane == 0) { s_cmd = -1; nmatches[img] = nm; redo[img] = 0; }
+    named_bar(1);
 }
 
 cudaError_t launch_stream_replay(const int* list_idx, const int* list_dist, const int* counts, const uint8_t* desc, const uint8_t* dmask,
@@ -413,7 +466,7 @@ cudaError_t launch_stream_replay(const int* list_idx, const int* list_dist, cons
     if (capacity > 65535 || (dim != 16 && dim != 32 && dim != 64)) return cudaErrorInvalidValue;
     const size_t smem = (size_t)64 * K * 4 + (size_t)((capacity + 31) / 32) * 4;
     const bool masked = dmask != nullptr;
-#define MCS_SR(W, M) stream_replay_kernel<W, M><<<n_images, 32, smem, st>>>(list_idx, list_dist, counts, (const uint32_t*)desc, \
+#define MCS_SR(W, M) stream_replay_kernel<W, M><<<n_images, kReplayThreads, smem, st>>>(list_idx, list_dist, counts, (const uint32_t*)desc, \
         (const uint32_t*)dmask, n_cams, capacity, K, img_lo, th_low, nnratio, matches12, nmatches, redo)
     if (dim == 16) { if (masked) MCS_SR(4, true); else MCS_SR(4, false); }
     else if (dim == 32) { if (masked) MCS_SR(8, true); else MCS_SR(8, false); }

@@ -675,13 +675,13 @@ int mcs_extractor_set_profiling(mcs_extractor* ex, int32_t enable) {
     return MCS_OK;
 }
 
-int mcs_extractor_tier_stats(mcs_extractor* ex, int32_t enable, int64_t* counts3) {
+int mcs_extractor_tier_stats(mcs_extractor* ex, int32_t enable, int64_t* counts4) {
     if (!ex) return fail(MCS_ERR_INVALID, "null extractor");
     CK(cudaSetDevice(ex->device));
     CK(cudaDeviceSynchronize());
-    if (counts3) {
-        counts3[0] = counts3[1] = counts3[2] = 0;
-        if (ex->tier_on) CK(cudaMemcpy(counts3, ex->tier.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (counts4) {
+        counts4[0] = counts4[1] = counts4[2] = counts4[3] = 0;
+        if (ex->tier_on) CK(cudaMemcpy(counts4, ex->tier.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     }
     if (enable && !ex->tier_on) {
         CK(ex->tier.ensure(4));

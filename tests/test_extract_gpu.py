@@ -160,7 +160,8 @@ def test_full_size_properties(api, cams):
         for l in range(8):
             assert (k["octave"] == l).sum() <= quotas[l] + 2           # the octree over-delivers by at most 2
         xi, yi = np.rint(k["x"]).astype(int), np.rint(k["y"]).astype(int)
-        assert np.all(masks[coi[i]][np.clip(yi, 0, 479), np.clip(xi, 0, 753)] > 0) or True
+        # the mask is tested on the LEVEL's nearest-neighbour copy (ref :1219-1247); at level 0 resolution a border keypoint may round outside
+        assert np.mean(masks[coi[i]][np.clip(yi, 0, 479), np.clip(xi, 0, 753)] > 0) > 0.99
         assert np.all((k["angle"] >= 0) & (k["angle"] < 360.0001))
         assert np.all(k["response"] >= 20)
     # idempotence: same input, same bytes
@@ -243,5 +244,5 @@ def test_k3_tier_statistics(api, oa, cams):
     ok, od, om = oa.OracleExtractor(nfeatures=2000, do_dbrief=True, learn_masks=True).extract(img, mask, cam)
     assert k.tobytes() == ok.tobytes() and np.array_equal(d, od) and np.array_equal(m, om)
     assert t.sum() == 3 * len(k)
-    print("K3 tiers (fp32, fp64 polynomial, exact):", t.tolist(), t / t.sum())
-    assert t[0] > 0.85 * t.sum() and t[2] < 0.01 * t.sum()
+    print("K3 tiers (fp32, fp32 + FP64 repair, fp64 polynomial, exact):", t.tolist(), t / t.sum())
+    assert t[0] > 0.85 * t.sum() and t[0] + t[1] > 0.93 * t.sum() and t[3] < 0.01 * t.sum()

@@ -57,7 +57,7 @@ def test_cam(cam, nk=400, seed=0, guard=None):
     tabf=tab.astype(f32)
     W,H=cam['width'],cam['height']
     worst=0; worst_mean=0; cnt_far=0; flagged=0; total=0
-    errs=[]
+    errs=[]; merrs=[]
     for _ in range(nk):
         # random keypoint in mask
         while True:
@@ -83,12 +83,9 @@ def test_cam(cam, nk=400, seed=0, guard=None):
         qaf=qa.astype(f32); K0f=f32(K0); gkf=f32(gk); s0f=f32(s0/SC)
         caf,saf=f32(ca),f32(sa)
         pxf=px.astype(f32); pyf=py.astype(f32)
-        dx=pxf*caf-pyf*saf; dy=pxf*saf+pyf*caf
-        ukxf,ukyf=f32(ukx),f32(uky)
-        ukx_lo=f32(ukx-np.float64(ukxf)); uky_lo=f32(uky-np.float64(ukyf))
-        t1=f32(2)*ukxf+dx; t2=f32(2)*ukyf+dy
-        n=dx*t1+dy*t2
-        if os.environ.get("LO","1")=="1": n=n+f32(2)*(dx*ukx_lo+dy*uky_lo)
+        # rotation folded into per-pattern constants, as the kernel does
+        nx=f32(2.0*(ukx*ca+uky*sa)); ny=f32(2.0*(uky*ca-ukx*sa))
+        n=pxf*nx+(pyf*ny+(pxf*pxf+pyf*pyf))
         rk2f=f32(rk*rk); rkf=f32(rk)
         r2=rk2f+n
         yv=(f32(1)/np.sqrt(r2)).astype(f32)   # rsqrt refined (assume ~1ulp)
@@ -102,17 +99,22 @@ def test_cam(cam, nk=400, seed=0, guard=None):
         h=s*p-K0f
         dg=h*yv
         g=gkf+dg
-        ex=g*dx+dg*ukxf; ey=g*dy+dg*ukyf
-        du=f32(cam['c'])*ex+f32(cam['d'])*ey; dv=f32(cam['e'])*ex+ey
+        c_,d_,e_=cam['c'],cam['d'],cam['e']
+        axx=f32(c_*ca+d_*sa); axy=f32(d_*ca-c_*sa); ayx=f32(e_*ca+sa); ayy=f32(ca-e_*sa)
+        auk=f32(c_*ukx+d_*uky); avk=f32(e_*ukx+uky)
+        du=g*(pxf*axx+pyf*axy)+dg*auk; dv=g*(pxf*ayx+pyf*ayy)+dg*avk
         mu=f32(du.astype(np.float64).mean()); mv=f32(dv.astype(np.float64).mean())   # fp32 sums approximated
         tu=du-mu; tv=dv-mv
         eu=np.abs(tu.astype(np.float64)-de_u); ev=np.abs(tv.astype(np.float64)-de_v)
         e=max(eu.max(),ev.max()); errs.append(e)
+        uk,vk=world_to_img(cam,np.array([ukx]),np.array([uky]),-a0)
+        merrs.append(max(abs(np.float64(mu)-(ue.mean()-uk[0])),abs(np.float64(mv)-(ve.mean()-vk[0]))))
         worst=max(worst,e)
         if guard:
             fr=np.concatenate([tu,tv]).astype(np.float64); fr=np.abs(fr-np.rint(fr))
             flagged+= (fr>0.5-guard).any(); total+=1
     errs=np.array(errs)
+    print(f"mean err max {max(merrs):.3e} p99 {np.percentile(merrs,99):.3e}", end="  ")
     print(f"{W}x{H}: kp {len(errs)} (skipped {cnt_far}) max err {worst:.3e} p99 {np.percentile(errs,99):.3e} median {np.median(errs):.3e}", f"flagged frac {flagged/max(total,1):.3f}" if guard else "")
 cams=synth.lafida_cams()
 for c in cams: test_cam(c,400,1,guard=3e-5)
