@@ -376,9 +376,10 @@ def main():
     views = [ex.packed_views(p, B) for p in packed]                                       # overlaps the extraction of step i+1
     gathered = [torch.empty(world * pbytes, dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
     comm = rig.Communicator(dev) if world > 1 else None
-    stream, cstream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    stream, cstream, mstream = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     ev_feat = [torch.cuda.Event() for _ in range(2)]
     ev_gath = [torch.cuda.Event() for _ in range(2)]
+    ev_match = [torch.cuda.Event() for _ in range(2)]
     midx = torch.empty((B, cap, K), dtype=torch.int32, device=dev)
     mdist = torch.empty((B, cap, K), dtype=torch.int32, device=dev)
     m12 = torch.empty((B, cap), dtype=torch.int32, device=dev)
@@ -441,15 +442,20 @@ def main():
         step_no[0] += 1
         if world > 1:
             stream.wait_event(ev_gath[i])                         # the gather that last read this buffer has finished
+        stream.wait_event(ev_match[i])                            # ... and so has the matching of two steps ago
         v = ex.extract_batch_packed_device(dev_images, masks, cams, coi, packed[i], stream=stream, width=W)
+        ev_feat[i].record(stream)
         if world > 1:                                             # one ncclAllGather, on its own stream behind the features
-            ev_feat[i].record(stream)
             cstream.wait_event(ev_feat[i])
             comm.allgather(packed[i], gathered[i], cstream)
             ev_gath[i].record(cstream)
         if cfg_id == 2:
-            api.match_stream_device(v["desc"], v["dmask"], v["counts"], F, NC, K=K, out=(midx, mdist), stream=stream)
-            api.match_stream_replay_device(midx, mdist, v["counts"], v["desc"], v["dmask"], F, NC, m.TH_LOW_, 0.9, out=(m12, nmat, redo), stream=stream)
+            # matching of step i on its own stream: the XU-bound popcount kernel and the latency-bound greedy replay (one CTA per
+            # image, mostly a single warp walking the queries in order) share the SMs with the extraction of step i + 1
+            mstream.wait_event(ev_feat[i])
+            api.match_stream_device(v["desc"], v["dmask"], v["counts"], F, NC, K=K, out=(midx, mdist), stream=mstream)
+            api.match_stream_replay_device(midx, mdist, v["counts"], v["desc"], v["dmask"], F, NC, m.TH_LOW_, 0.9, out=(m12, nmat, redo), stream=mstream)
+            ev_match[i].record(mstream)
         elif cfg_id == 3:
             match_config3(v)
         else:
@@ -470,6 +476,7 @@ def main():
         ex.set_profiling(True)
         k_ms = np.zeros(3)
         for _ in range(3):
+            torch.cuda.synchronize(dev)                           # stage times without the overlapped matching of the step before
             out = step()
             torch.cuda.synchronize(dev)
             k_ms += np.array(ex.get_timings())
@@ -496,6 +503,7 @@ def main():
             out = step()
         if world > 1:
             stream.wait_stream(cstream)                           # the last gathers belong to the timed region
+        stream.wait_stream(mstream)                               # ... and so does the matching of the last step
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -566,14 +574,29 @@ def main():
         assert int(np_out["nmatches"].sum()) == matches_rank, "e2e and device-resident greedy matches disagree"
 
     # ---- single-frame latency of the reference-shaped call: one multi-camera frame through mcs_extract_batch (host in/out) ----
-    lat_ms = None
+    lat_ms, lat_graph = None, None
     if rank == 0 and cfg_id == 2:
-        one = np.ascontiguousarray(host_images.numpy()[0])
-        ex.extract_batch(one, masks, cams, list(range(NC)))
+        # the C-ABI call itself (arguments prepared once, as the C++ caller has them): pageable host buffers in and out
+        import ctypes as C
+        from multicol_slam_b200.ctypes_defs import KEYPOINT_DTYPE, Ocam
+        two = [np.ascontiguousarray(host_images.numpy()[f]) for f in (0, 1)]
+        cap1, ds1 = ex.info.capacity, ex.info.desc_size
+        o_k, o_d = np.zeros((NC, cap1), KEYPOINT_DTYPE), np.zeros((NC, cap1, ds1), np.uint8)
+        o_m, o_c = np.zeros((NC, cap1, ds1), np.uint8), np.zeros(NC, np.int32)
+        ocs = (Ocam * NC)(*[api.as_ocam(c) for c in cams])
+        coi1 = np.arange(NC, dtype=np.int32)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        def one_frame(img):
+            rc = api.lib().mcs_extract_batch(ex._h, NC, vp(img), W, H, W, vp(masks), ocs, NC, vp(coi1), vp(o_k), vp(o_d), vp(o_m), vp(o_c), cap1)
+            assert rc == 0, api.lib().mcs_last_error()
+        for i in range(3):
+            one_frame(two[i & 1])
+        r0 = ex.graph_replays()
         t0 = time.perf_counter()
-        for _ in range(20):
-            ex.extract_batch(one, masks, cams, list(range(NC)))
-        lat_ms = (time.perf_counter() - t0) / 20 * 1e3
+        for i in range(50):
+            one_frame(two[i & 1])
+        lat_ms = (time.perf_counter() - t0) / 50 * 1e3
+        lat_graph = ex.graph_replays() - r0
     if rank == 0:
         # ---- roofline of K1 (fused pyramid + blur + FAST), algorithmic bytes per SURVEY 8d / DESIGN.md ----
         ex.extract_batch_packed_device(dev_images, masks, cams, coi, packed[0], stream=stream, width=W)
@@ -640,7 +663,7 @@ def main():
                              l2=f"inputs {host_images.numel() / 1e6:.0f} MB + pyramid and blurred pyramid {2 * P * B / 1e6:.0f} MB per step > 126 MB L2"),
             "e2e": {"value": e2e_val, "unit": "Mfeatures/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "api": e2e_api, "steps": e2e_steps},
             "gpu_launches": args.steps * launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-            "single_frame_latency_ms": {"value": lat_ms, "what": "one multi-camera frame, mcs_extract_batch with pageable host buffers, mean of 20"}}))
+            "single_frame_latency_ms": {"value": lat_ms, "what": "one multi-camera frame through mcs_extract_batch (C ABI, pageable host buffers in and out), mean of 50 alternating frames", "cuda_graph_replays": lat_graph}}))
     if comm is not None:
         torch.cuda.synchronize(dev)
         comm.close()

@@ -201,6 +201,12 @@ int  mcs_extractor_get_timings(mcs_extractor* ex, float* ms3);
  * [0] tier 1, [1] tier 1 after the FP64 repair of its near-tie points, [2] tier 2, [3] tier 3. */
 int  mcs_extractor_tier_stats(mcs_extractor* ex, int32_t enable, int64_t* counts4);
 
+/* mcs_extract_batch / mcs_extract with at most 16 images (the per-frame call of cMultiFrame's constructor, ref
+ * src/cMultiFrame.cpp:128-139) stage through pinned buffers owned by the extractor, and once a call repeats the previous one's
+ * geometry, camera table, camera models and masks the whole copy-in / K1..K3 / copy-out sequence is ONE cudaGraphLaunch.
+ * *n receives how many calls were served that way (diagnostics; tests assert the shortcut is taken and changes nothing). */
+int  mcs_extractor_graph_replays(mcs_extractor* ex, int64_t* n);
+
 /* Introspection for the parity tests: copy intermediate device buffers of the LAST extract call
  * (image 0 of the batch unless image_index is given) back to the host.
  *   what: 0 = unblurred level (w*h bytes), 1 = blurred level, 2 = mask level,

@@ -248,6 +248,12 @@ class mdBRIEFextractorOct:
         _check(lib().mcs_extractor_tier_stats(self._h, int(enable), _p(out)))
         return out
 
+    def graph_replays(self):
+        """calls served by replaying the cached CUDA graph of the per-frame sequence (mcs_extractor_graph_replays)"""
+        n = C.c_int64(0)
+        _check(lib().mcs_extractor_graph_replays(self._h, C.byref(n)))
+        return n.value
+
     def get_timings(self):
         """(K1 pyramid+blur+FAST all levels, K2 octree, K3 describe) of the last extract call, milliseconds."""
         ms = (C.c_float * 3)()

@@ -107,6 +107,14 @@ struct mcs_extractor {
     bool tile_flags_valid = false;
     DevBuf<double> lut_coef;
     DevBuf<DistortLut> luts;
+    // small host-buffer calls (mcs_extract_batch with <= kGraphMaxImages images: what cMultiFrame's constructor issues per frame):
+    // pinned staging on both sides and the whole copy-in / K1..K3 / copy-out sequence kept as an instantiated CUDA graph
+    uint8_t* pin_in = nullptr;  size_t pin_in_bytes = 0;
+    uint8_t* pin_out = nullptr; size_t pin_out_bytes = 0;
+    cudaGraphExec_t sf_exec = nullptr;
+    struct SfKey { int n = 0, w = 0, h = 0, stride = 0, capacity = 0; bool dm = false; std::vector<int> coi; std::vector<mcs_ocam> cams; } sf_key;
+    bool sf_valid = false;
+    long long sf_replays = 0;
     bool profiling = false;
     bool tier_on = false;
     DevBuf<unsigned long long> tier;
@@ -330,27 +338,11 @@ int upload_small_inputs(mcs_extractor* ex, int W, int H, const uint8_t* masks, c
     return MCS_OK;
 }
 
-int run_pipeline(mcs_extractor* ex, int n_images, const uint8_t* images_dev, int W, int H, int stride,
-                 const uint8_t* masks, const mcs_ocam* cams, int n_cams, const int* cam_of_image,
-                 mcs_keypoint* kps_dev, uint8_t* desc_dev, uint8_t* dmask_dev, int* counts_dev, int capacity,
-                 cudaStream_t st, bool first_chunk = true, const int* coi_dev = nullptr) {
-    if (n_cams < 1 || n_cams > 64) return fail(MCS_ERR_INVALID, "n_cams must be in [1,64]");
-    for (int i = 0; i < n_images; ++i)
-        if (cam_of_image[i] < 0 || cam_of_image[i] >= n_cams) return fail(MCS_ERR_INVALID, "cam_of_image out of range");
-    int rc = build_geometry(ex, W, H, stride);
-    if (rc) return rc;
-    rc = ensure_batch(ex, n_images);
-    if (rc) return rc;
+// K1 (per level) -> K2 -> K3 on `st`: kernel launches and memsets only (no allocation, no host synchronisation, no pageable
+// copy), so the sequence can be stream-captured into a CUDA graph.
+int enqueue_kernels(mcs_extractor* ex, int n_images, const uint8_t* images_dev, int W, int H, int stride, const int* coi_d,
+                    mcs_keypoint* kps_dev, uint8_t* desc_dev, uint8_t* dmask_dev, int* counts_dev, int capacity, cudaStream_t st) {
     const PyramidGeom& G = ex->G;
-    if (first_chunk) {
-        rc = upload_small_inputs(ex, W, H, masks, cams, n_cams, st);
-        if (rc) return rc;
-    }
-    const int* coi_d = coi_dev;
-    if (!coi_d) {
-        CK(cudaMemcpyAsync(ex->cam_of_image.p, cam_of_image, sizeof(int) * n_images, cudaMemcpyHostToDevice, st));
-        coi_d = ex->cam_of_image.p;
-    }
     ex->coi_last = coi_d;
     CK(cudaMemsetAsync(ex->raw_count.p, 0, sizeof(int) * n_images * G.nlevels, st));
     if (ex->profiling) CK(cudaEventRecord(ex->ev[0], st));
@@ -374,6 +366,40 @@ int run_pipeline(mcs_extractor* ex, int n_images, const uint8_t* images_dev, int
     if (ex->profiling) CK(cudaEventRecord(ex->ev[3], st));
     ex->last_n_images = n_images;
     return MCS_OK;
+}
+
+// Validation, geometry, buffer growth and the small host inputs of one call (everything that may allocate, synchronise or read
+// pageable host memory); *coi_d receives the device camera-of-image table the kernels should use.
+int prepare_inputs(mcs_extractor* ex, int n_images, int W, int H, int stride, const uint8_t* masks, const mcs_ocam* cams, int n_cams,
+                   const int* cam_of_image, cudaStream_t st, bool first_chunk, const int* coi_dev, const int** coi_d) {
+    if (n_cams < 1 || n_cams > 64) return fail(MCS_ERR_INVALID, "n_cams must be in [1,64]");
+    for (int i = 0; i < n_images; ++i)
+        if (cam_of_image[i] < 0 || cam_of_image[i] >= n_cams) return fail(MCS_ERR_INVALID, "cam_of_image out of range");
+    int rc = build_geometry(ex, W, H, stride);
+    if (rc) return rc;
+    rc = ensure_batch(ex, n_images);
+    if (rc) return rc;
+    if (first_chunk) {
+        rc = upload_small_inputs(ex, W, H, masks, cams, n_cams, st);
+        if (rc) return rc;
+    }
+    *coi_d = coi_dev;
+    if (!coi_dev) {
+        CK(cudaMemcpyAsync(ex->cam_of_image.p, cam_of_image, sizeof(int) * n_images, cudaMemcpyHostToDevice, st));
+        *coi_d = ex->cam_of_image.p;
+    }
+    ex->sf_valid = false;            // shared state (camera table, masks, tables) may now differ from what the cached graph assumes
+    return MCS_OK;
+}
+
+int run_pipeline(mcs_extractor* ex, int n_images, const uint8_t* images_dev, int W, int H, int stride,
+                 const uint8_t* masks, const mcs_ocam* cams, int n_cams, const int* cam_of_image,
+                 mcs_keypoint* kps_dev, uint8_t* desc_dev, uint8_t* dmask_dev, int* counts_dev, int capacity,
+                 cudaStream_t st, bool first_chunk = true, const int* coi_dev = nullptr) {
+    const int* coi_d = nullptr;
+    int rc = prepare_inputs(ex, n_images, W, H, stride, masks, cams, n_cams, cam_of_image, st, first_chunk, coi_dev, &coi_d);
+    if (rc) return rc;
+    return enqueue_kernels(ex, n_images, images_dev, W, H, stride, coi_d, kps_dev, desc_dev, dmask_dev, counts_dev, capacity, st);
 }
 
 int check_status(mcs_extractor* ex, cudaStream_t st) {
@@ -522,6 +548,9 @@ void mcs_extractor_destroy(mcs_extractor* ex) {
     ex->masks.release(); ex->cams.release(); ex->cam_of_image.release(); ex->coi_all.release(); ex->raw.release(); ex->node_of.release();
     ex->raw_count.release(); ex->sel_count.release(); ex->status.release(); ex->counts.release(); ex->sel_xys.release();
     ex->kps.release(); ex->desc.release(); ex->dmask.release();
+    if (ex->sf_exec) cudaGraphExecDestroy(ex->sf_exec);
+    if (ex->pin_in) cudaFreeHost(ex->pin_in);
+    if (ex->pin_out) cudaFreeHost(ex->pin_out);
     ex->match_idx.release(); ex->match_dist.release(); ex->m12.release(); ex->nmat.release(); ex->redo.release(); ex->lut_coef.release(); ex->luts.release(); ex->tier.release(); ex->tile_flags.release();
     for (int i = 0; i < 4; ++i) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
     ex->in_tight.release();
@@ -562,6 +591,50 @@ int mcs_extract_batch_device(mcs_extractor* ex, int32_t n_images, const uint8_t*
     return MCS_OK;
 }
 
+namespace {
+
+constexpr int kGraphMaxImages = 16;
+
+int pin_ensure(uint8_t*& p, size_t& cap, size_t need, bool* moved) {
+    if (need <= cap) return MCS_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    CK(cudaMallocHost((void**)&p, need));
+    cap = need; *moved = true;
+    return MCS_OK;
+}
+
+struct SmallOut { size_t status, counts, kps, desc, dmask, total; };
+SmallOut small_out_layout(int n, int capacity, int ds) {
+    SmallOut o;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    o.status = 0; o.counts = 256;
+    o.kps = o.counts + up(sizeof(int) * n);
+    o.desc = o.kps + up(sizeof(mcs_keypoint) * n * capacity);
+    o.dmask = o.desc + up((size_t)n * capacity * ds);
+    o.total = o.dmask + up((size_t)n * capacity * ds);
+    return o;
+}
+
+// copy-in, re-pitch, K1..K3, copy-out of one small call between the extractor's pinned staging buffers: capturable
+int enqueue_small(mcs_extractor* ex, int n, int W, int H, int stride, int dpitch, const int* coi_d, int capacity, bool with_dmask, cudaStream_t st) {
+    const int ds = ex->p.desc_size;
+    const SmallOut o = small_out_layout(n, capacity, ds);
+    CK(cudaMemcpyAsync(ex->in_tight.p, ex->pin_in, (size_t)stride * H * n, cudaMemcpyHostToDevice, st));
+    launch_repitch(ex->in_tight.p, stride, ex->in_images.p, dpitch, W, (size_t)H * n, st);
+    CK(cudaMemsetAsync(ex->status.p, 0, sizeof(int), st));
+    int rc = enqueue_kernels(ex, n, ex->in_images.p, W, H, dpitch, coi_d, ex->kps.p, ex->desc.p, ex->dmask.p, ex->counts.p, capacity, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ex->pin_out + o.status, ex->status.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ex->pin_out + o.counts, ex->counts.p, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ex->pin_out + o.kps, ex->kps.p, sizeof(mcs_keypoint) * n * capacity, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ex->pin_out + o.desc, ex->desc.p, (size_t)n * capacity * ds, cudaMemcpyDeviceToHost, st));
+    if (with_dmask) CK(cudaMemcpyAsync(ex->pin_out + o.dmask, ex->dmask.p, (size_t)n * capacity * ds, cudaMemcpyDeviceToHost, st));
+    return MCS_OK;
+}
+
+}  // namespace
+
 int mcs_extract_batch(mcs_extractor* ex, int32_t n_images, const uint8_t* images, int32_t width, int32_t height, int32_t stride,
                       const uint8_t* masks, const mcs_ocam* cams, int32_t n_cams, const int32_t* cam_of_image,
                       mcs_keypoint* kps_out, uint8_t* desc_out, uint8_t* dmask_out, int32_t* counts_out, int32_t capacity) {
@@ -576,6 +649,7 @@ int mcs_extract_batch(mcs_extractor* ex, int32_t n_images, const uint8_t* images
     // device staging with a 64-byte-aligned pitch so that K1 can use 128-bit loads
     const int dpitch = (width + 63) & ~63;
     const size_t img_bytes = (size_t)dpitch * height;
+    const void* before[6] = {ex->in_images.p, ex->kps.p, ex->desc.p, ex->dmask.p, ex->counts.p, ex->in_tight.p};
     CK(ex->in_images.ensure(img_bytes * n_images + 256));
     CK(ex->kps.ensure((size_t)n_images * capacity));
     CK(ex->desc.ensure((size_t)n_images * capacity * ds));
@@ -583,6 +657,73 @@ int mcs_extract_batch(mcs_extractor* ex, int32_t n_images, const uint8_t* images
     CK(ex->counts.ensure(n_images));
     // linear H2D + device re-pitch (a 2-D DMA of short rows is several times slower)
     CK(ex->in_tight.ensure((size_t)stride * height * n_images + 256));
+    const void* after[6] = {ex->in_images.p, ex->kps.p, ex->desc.p, ex->dmask.p, ex->counts.p, ex->in_tight.p};
+    bool moved = std::memcmp(before, after, sizeof(before)) != 0;
+
+    if (n_images <= kGraphMaxImages && !ex->profiling && !ex->tier_on) {
+        // ---- per-frame call: pinned staging + the whole sequence as one graph launch once the inputs repeat ----
+        if (n_cams < 1 || n_cams > 64) return fail(MCS_ERR_INVALID, "n_cams must be in [1,64]");
+        const size_t in_bytes = (size_t)stride * height * n_images, mbytes = (size_t)n_cams * width * height;
+        const SmallOut o = small_out_layout(n_images, capacity, ds);
+        int rc = pin_ensure(ex->pin_in, ex->pin_in_bytes, in_bytes, &moved);
+        if (rc) return rc;
+        rc = pin_ensure(ex->pin_out, ex->pin_out_bytes, o.total, &moved);
+        if (rc) return rc;
+        if (moved) ex->sf_valid = false;
+        std::memcpy(ex->pin_in, images, in_bytes);
+        const mcs_extractor::SfKey& k = ex->sf_key;
+        const bool hit = ex->sf_valid && ex->sf_exec && k.n == n_images && k.w == width && k.h == height && k.stride == stride &&
+                         k.capacity == capacity && k.dm == (dmask_out != nullptr) && (int)k.cams.size() == n_cams &&
+                         std::memcmp(k.coi.data(), cam_of_image, sizeof(int) * n_images) == 0 &&
+                         std::memcmp(k.cams.data(), cams, sizeof(mcs_ocam) * n_cams) == 0 && ex->masks_host.size() == mbytes &&
+                         std::memcmp(ex->masks_host.data(), masks, mbytes) == 0;
+        if (hit) {
+            CK(cudaGraphLaunch(ex->sf_exec, st));
+            ++ex->sf_replays;
+        } else {
+            const int* coi_d = nullptr;
+            rc = prepare_inputs(ex, n_images, width, height, stride, masks, cams, n_cams, cam_of_image, st, true, nullptr, &coi_d);
+            if (rc) return rc;
+            rc = enqueue_small(ex, n_images, width, height, stride, dpitch, coi_d, capacity, dmask_out != nullptr, st);
+            if (rc) return rc;
+            // record the same sequence for the next call with these inputs (capture executes nothing)
+            if (ex->sf_exec) { cudaGraphExecDestroy(ex->sf_exec); ex->sf_exec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                const int crc = enqueue_small(ex, n_images, width, height, stride, dpitch, coi_d, capacity, dmask_out != nullptr, st);
+                const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+                if (crc == MCS_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&ex->sf_exec, graph, 0) == cudaSuccess) {
+                    mcs_extractor::SfKey& nk = ex->sf_key;
+                    nk.n = n_images; nk.w = width; nk.h = height; nk.stride = stride; nk.capacity = capacity;
+                    nk.coi.assign(cam_of_image, cam_of_image + n_images);
+                    nk.cams.assign(cams, cams + n_cams);
+                    nk.dm = dmask_out != nullptr;
+                    ex->sf_valid = true;
+                } else {
+                    ex->sf_exec = nullptr;
+                    cudaGetLastError();          // a failed capture only costs the shortcut
+                }
+                if (graph) cudaGraphDestroy(graph);
+            } else {
+                cudaGetLastError();
+            }
+        }
+        CK(cudaStreamSynchronize(st));
+        const int status = *(const int*)(ex->pin_out + o.status);
+        if (status & 1) return fail(MCS_ERR_CAPACITY, "raw corner list overflow");
+        if (status & 2) return fail(MCS_ERR_CAPACITY, "octree node table overflow");
+        if (status & 4) return fail(MCS_ERR_CAPACITY, "selected keypoint slots overflow");
+        const int* cnt = (const int*)(ex->pin_out + o.counts);
+        for (int i = 0; i < n_images; ++i) {
+            const size_t nused = (size_t)std::min(std::max(cnt[i], 0), capacity), row = (size_t)i * capacity;
+            counts_out[i] = cnt[i];
+            std::memcpy(kps_out + row, ex->pin_out + o.kps + row * sizeof(mcs_keypoint), nused * sizeof(mcs_keypoint));
+            std::memcpy(desc_out + row * ds, ex->pin_out + o.desc + row * ds, nused * ds);
+            if (dmask_out) std::memcpy(dmask_out + row * ds, ex->pin_out + o.dmask + row * ds, nused * ds);
+        }
+        return MCS_OK;
+    }
+
     CK(cudaMemcpyAsync(ex->in_tight.p, images, (size_t)stride * height * n_images, cudaMemcpyHostToDevice, st));
     launch_repitch(ex->in_tight.p, stride, ex->in_images.p, dpitch, width, (size_t)height * n_images, st);
     int rc = run_pipeline(ex, n_images, ex->in_images.p, width, height, dpitch, masks, cams, n_cams, cam_of_image, ex->kps.p,
@@ -688,6 +829,12 @@ int mcs_extractor_tier_stats(mcs_extractor* ex, int32_t enable, int64_t* counts4
         CK(cudaMemset(ex->tier.p, 0, 4 * sizeof(unsigned long long)));
     }
     ex->tier_on = enable != 0;
+    return MCS_OK;
+}
+
+int mcs_extractor_graph_replays(mcs_extractor* ex, int64_t* n) {
+    if (!ex || !n) return fail(MCS_ERR_INVALID, "null argument");
+    *n = ex->sf_replays;
     return MCS_OK;
 }
 

@@ -246,3 +246,47 @@ def test_k3_tier_statistics(api, oa, cams):
     assert t.sum() == 3 * len(k)
     print("K3 tiers (fp32, fp32 + FP64 repair, fp64 polynomial, exact):", t.tolist(), t / t.sum())
     assert t[0] > 0.85 * t.sum() and t[0] + t[1] > 0.93 * t.sum() and t[3] < 0.01 * t.sum()
+
+
+@pytest.mark.gpu
+def test_per_frame_call_is_graph_replayed(api, oa, cams):
+    """mcs_extract_batch with a few images (the per-frame call of cMultiFrame's constructor) is served by one cached CUDA graph once
+    the static inputs repeat; the result is the oracle's whether a call was run eagerly, captured or replayed, and a change of the
+    masks, the camera table or the batch size drops the graph instead of replaying stale state"""
+    from multicol_slam_b200 import synth
+    masks = np.stack([synth.mirror_mask(c) for c in cams])
+    ex = api.mdBRIEFextractorOct(nfeatures=600, do_dBrief=True, learnMasks=True)
+    oe = oa.OracleExtractor(nfeatures=600, do_dbrief=True, learn_masks=True)
+
+    def check(frame, coi, msk):
+        imgs = np.stack([synth.frame(cams[c], 40 * frame + c) for c in coi])
+        kps, desc, dmask, counts = ex.extract_batch(imgs, msk, cams, coi)
+        for i, c in enumerate(coi):
+            ok, od, om = oe.extract(imgs[i], msk[c], cams[c])
+            n = counts[i]
+            assert n == len(ok) and kps[i, :n].tobytes() == ok.tobytes()
+            assert np.array_equal(desc[i, :n], od) and np.array_equal(dmask[i, :n], om)
+
+    for f in range(4):
+        check(f, [0, 1, 2], masks)
+    assert ex.graph_replays() >= 2                      # first call eager (+ capture), later ones replayed
+    r = ex.graph_replays()
+    masks2 = masks.copy(); masks2[1, :200, :] = 0       # another mask: must not replay with the old tile flags / mask pyramid
+    check(5, [0, 1, 2], masks2)
+    assert ex.graph_replays() == r
+    check(6, [0, 1, 2], masks2)
+    assert ex.graph_replays() == r + 1
+    check(7, [2, 1, 0], masks2)                         # another camera table
+    assert ex.graph_replays() == r + 1
+    check(8, [0, 1], masks2)                            # another batch size
+    check(9, [0, 1], masks2)
+    assert ex.graph_replays() == r + 2
+    # a device-path call in between touches the shared buffers: the next per-frame call runs eagerly again
+    import torch
+    t = torch.zeros((2, 480, 768), dtype=torch.uint8, device="cuda")
+    ex.extract_batch_device(t, masks2, cams, [0, 1], width=754)
+    torch.cuda.synchronize()
+    check(10, [0, 1], masks2)
+    assert ex.graph_replays() == r + 2
+    check(11, [0, 1], masks2)
+    assert ex.graph_replays() == r + 3
