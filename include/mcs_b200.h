@@ -161,7 +161,9 @@ int  mcs_extract_match_stream(mcs_extractor* ex, int32_t n_frames, int32_t n_cam
  *    and mcs_allgather_features can ship the buffer to the other GPUs of the rig right after the call;
  *  - matches12_out / nmatches_out / redo_out (all three or none): the greedy acceptance of SearchByBoW(KF1, KF2)
  *    (threshold th_low, ratio nnratio, every database keypoint used once; see mcs_match_stream_replay_device) evaluated on the
- *    device over each chunk's K-best lists; host arrays [n_images*capacity], [n_images], [n_images]. */
+ *    device over each chunk's K-best lists; host arrays [n_images*capacity], [n_images], [n_images].  In this mode the lists
+ *    returned in match_idx_out / match_dist_out hold only the entries that can influence the acceptance (distance below the
+ *    relevance bound of mcs_match_stream_greedy_device); shorter lists are padded with (-1, INT_MAX). */
 int  mcs_extract_match_stream_packed(mcs_extractor* ex, int32_t n_frames, int32_t n_cams,
                                      const uint8_t* images, int32_t width, int32_t height, int32_t stride,
                                      const uint8_t* masks, const mcs_ocam* cams,
@@ -187,6 +189,16 @@ int  mcs_match_stream_replay_device(const int32_t* match_idx_dev, const int32_t*
                                     const uint8_t* desc_dev, const uint8_t* dmask_dev,
                                     int32_t n_frames, int32_t n_cams, int32_t capacity, int32_t dim, int32_t K, int32_t th_low, double nnratio,
                                     int32_t* matches12_dev, int32_t* nmatches_dev, int32_t* redo_dev, void* stream);
+
+/* Both steps as one call -- the operation cLoopClosing / cTracking actually want from a brute-force match (SearchByBoW(KF1, KF2)'s
+ * acceptance rule, ref src/cORBmatcher.cpp:885-966, of every image against the same camera's image one frame earlier): K-best
+ * lists in scratch memory of the stream's pool, then the greedy replay.  Because th_low and nnratio are known to the list kernel
+ * here, entries that cannot influence any decision (distance >= the smallest b with (th_low - 1) < nnratio * b) are left out of
+ * the lists, which lets the kernel drop a pair after the first half of its words (see match_kernels.cu); the matches are the same
+ * as mcs_match_stream_device + mcs_match_stream_replay_device give for any K. */
+int  mcs_match_stream_greedy_device(const uint8_t* desc_dev, const uint8_t* dmask_dev, const int32_t* counts_dev,
+                                    int32_t n_frames, int32_t n_cams, int32_t capacity, int32_t dim, int32_t th_low, double nnratio,
+                                    int32_t* matches12_dev, int32_t* nmatches_dev, void* stream);
 
 /* Per-stage device timings of the LAST extract call, measured with CUDA events on the launching stream when
  * profiling is enabled: ms[0] = K1 (pyramid+blur+FAST, all levels), ms[1] = K2 octree, ms[2] = K3 describe.

@@ -338,6 +338,22 @@ def match_stream_replay_device(idx_t, dist_t, counts_t, desc_t, dmask_t, n_frame
     return out
 
 
+def match_stream_greedy_device(desc_t, dmask_t, counts_t, n_frames, n_cams, th_low, nnratio, out=None, stream=None):
+    """mcs_match_stream_greedy_device: every image against the same camera's image one frame earlier with SearchByBoW(KF1, KF2)'s
+    acceptance rule, lists + replay in one call.  desc_t/dmask_t [F*C,cap,dim] u8 cuda, counts_t [F*C] i32 cuda.
+    -> (matches12 [F*C,cap] i32, nmatches [F*C] i32) cuda tensors"""
+    import torch
+    B, cap, dim = desc_t.shape
+    dev = desc_t.device
+    if out is None:
+        out = (torch.empty((B, cap), dtype=torch.int32, device=dev), torch.empty(B, dtype=torch.int32, device=dev))
+    ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+    st = C.c_void_p(stream.cuda_stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream)
+    _check(lib().mcs_match_stream_greedy_device(ptr(desc_t), ptr(dmask_t), ptr(counts_t), n_frames, n_cams, cap, dim, int(th_low),
+                                                C.c_double(nnratio), ptr(out[0]), ptr(out[1]), st))
+    return out
+
+
 def match_bruteforce_device(q_t, qmask_t, valid1, d_t, dmask_t, valid2, th_low, nnratio, stream=None):
     """mcs_match_bruteforce_device: SearchByBoW(KF1, KF2) with descriptors resident on the GPU (torch uint8 [n, dim]);
     valid1 / valid2 host uint8 arrays or None.  Returns (nmatches, matches12 numpy)."""

@@ -35,10 +35,20 @@ cudaError_t launch_describe(const PyramidGeom& G, const PyramidGeom* G_dev, int 
 
 // matching (match_kernels.cu)
 cudaError_t launch_hamming_topk(const uint8_t* q, const uint8_t* qmask, int nq, const uint8_t* d, const uint8_t* dmask,
-                                int nd, const uint8_t* db_skip, int dim, int K, int* topk_idx, int* topk_dist,
+                                int nd, const uint8_t* db_skip, int dim, int K, unsigned bound, int* topk_idx, int* topk_dist,
                                 cudaStream_t st);
 cudaError_t launch_hamming_stream(const uint8_t* desc, const uint8_t* dmask, const int* counts, int img_lo, int img_count,
-                                  int n_cams, int capacity, int dim, int K, int* out_idx, int* out_dist, cudaStream_t st);
+                                  int n_cams, int capacity, int dim, int K, unsigned bound, int* out_idx, int* out_dist, cudaStream_t st);
+// Relevance bound of the greedy acceptance rule (best1 < th_low && best1 < nnratio * best2, ref src/cORBmatcher.cpp:899-961): the
+// smallest distance b >= th_low such that a second-best of b or more passes the ratio test for EVERY admissible best
+// (best <= th_low - 1).  A database entry at distance >= b can neither be an accepted best nor make a ratio test fail, so the
+// K-best kernels may leave it out of their lists (`bound` argument; 0xFFFFFFFF = keep everything) without changing any decision.
+inline unsigned greedy_dist_bound(int th_low, double nnratio) {
+    if (th_low <= 0) return 0u;                      // nothing can be accepted
+    long b = th_low;
+    while (b < (1L << 20) && !((double)(th_low - 1) < nnratio * (double)b)) ++b;
+    return (unsigned)b;
+}
 cudaError_t launch_stream_replay(const int* list_idx, const int* list_dist, const int* counts, const uint8_t* desc, const uint8_t* dmask,
                                  int dim, int img_lo, int n_images, int n_cams, int capacity, int K, int th_low, double nnratio,
                                  int* matches12, int* nmatches, int* redo, cudaStream_t st);

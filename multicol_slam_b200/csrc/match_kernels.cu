@@ -87,11 +87,61 @@ __device__ __forceinline__ unsigned hamming_words(const uint32_t (&qw)[WORDS], c
     return dist;
 }
 
+// Sum over N consecutive words, N = number of 32-bit words actually counted (2 per descriptor word when masked).
+template <int H, bool MASKED>
+__device__ __forceinline__ unsigned half_sum(const uint32_t* qw, const uint32_t* qm, const uint32_t* dd, const uint32_t* dm) {
+    if constexpr (MASKED) {
+        if constexpr (H == 8) {
+            uint32_t w[16];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { w[2 * k] = xor_and(qw[k], dd[k], qm[k]); w[2 * k + 1] = xor_and(qw[k], dd[k], dm[k]); }
+            return popc_sum16(w);
+        } else if constexpr (H == 4) {
+            uint32_t w[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { w[2 * k] = xor_and(qw[k], dd[k], qm[k]); w[2 * k + 1] = xor_and(qw[k], dd[k], dm[k]); }
+            return popc_sum8(w);
+        } else {
+            unsigned s = 0;
+#pragma unroll
+            for (int k = 0; k < H; ++k) s += __popc(xor_and(qw[k], dd[k], qm[k])) + __popc(xor_and(qw[k], dd[k], dm[k]));
+            return s;
+        }
+    } else {
+        if constexpr (H == 8) {
+            uint32_t w[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w[k] = qw[k] ^ dd[k];
+            return popc_sum8(w);
+        } else {
+            unsigned s = 0;
+#pragma unroll
+            for (int k = 0; k < H; ++k) s += __popc(qw[k] ^ dd[k]);
+            return s;
+        }
+    }
+}
+// Distance of one pair, evaluated in two halves.  The bit count of the first half is a lower bound of the whole, so a pair whose
+// first half already proves dist >= lim (lim = the current K-th best, or the caller's relevance bound) returns "infinity"
+// without touching the second half.  For descriptors of unrelated features the half count sits ~3 sigma above 2 * TH_LOW, so
+// with a relevance bound nearly every pair costs half the LOP3 / POPC work; the branch is per lane, but the second half is only
+// issued for warps in which some lane survived.
+template <int WORDS, bool MASKED>
+__device__ __forceinline__ unsigned hamming_bounded(const uint32_t (&qw)[WORDS], const uint32_t* qm, const uint32_t* dd, const uint32_t* dm,
+                                                    const unsigned lim) {
+    constexpr int H = WORDS / 2;
+    unsigned s = half_sum<H, MASKED>(qw, qm, dd, dm);
+    const unsigned lim2 = MASKED ? (lim > 0x7FFFFFFFu ? 0xFFFFFFFFu : 2u * lim) : lim;
+    if (s >= lim2) return 0xFFFFFFFFu;
+    s += half_sum<H, MASKED>(qw + H, MASKED ? qm + H : qm, dd + H, MASKED ? dm + H : dm);
+    return MASKED ? s >> 1 : s;
+}
+
 template <int WORDS, bool MASKED>
 __global__ void __launch_bounds__(kTopkThreads)
 hamming_topk_kernel(const uint32_t* __restrict__ q, const uint32_t* __restrict__ qmask, const int nq,
                     const uint32_t* __restrict__ d, const uint32_t* __restrict__ dmask, const int nd,
-                    const uint8_t* __restrict__ skip, const int K, const int chunk,
+                    const uint8_t* __restrict__ skip, const int K, const int chunk, const unsigned bound,
                     unsigned long long* __restrict__ part /* [splits][nq][kTopKMax] */) {
     __shared__ __align__(16) uint32_t s_d[kDbTile * WORDS];
     __shared__ __align__(16) uint32_t s_m[MASKED ? kDbTile * WORDS : 4];
@@ -129,9 +179,8 @@ hamming_topk_kernel(const uint32_t* __restrict__ q, const uint32_t* __restrict__
         for (int j = 0; j < tn; ++j) {
             if (s_skip[j]) continue;       // uniform across the CTA
             // bit-level Hamming distance; masked form = (popc(x&ma) + popc(x&mb)) / 2, integer division (ref :2472)
-            unsigned dist = hamming_words<WORDS, MASKED>(qw, qm, s_d + j * WORDS, s_m + j * WORDS);
-            if (MASKED) dist >>= 1;
-            if (dist < worst) {            // strict: equal distances keep the earlier index
+            const unsigned dist = hamming_bounded<WORDS, MASKED>(qw, qm, s_d + j * WORDS, s_m + j * WORDS, min(worst, bound));
+            if (dist < min(worst, bound)) {            // strict: equal distances keep the earlier index
                 unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)(t0 + j);
 #pragma unroll
                 for (int k = 0; k < kTopKMax; ++k) {
@@ -178,7 +227,7 @@ __global__ void topk_merge_kernel(const unsigned long long* __restrict__ part, c
 }
 
 cudaError_t launch_hamming_topk(const uint8_t* q, const uint8_t* qmask, int nq, const uint8_t* d, const uint8_t* dmask,
-                                int nd, const uint8_t* db_skip, int dim, int K, int* topk_idx, int* topk_dist,
+                                int nd, const uint8_t* db_skip, int dim, int K, unsigned bound, int* topk_idx, int* topk_dist,
                                 cudaStream_t st) {
     if (K < 1 || K > kTopKMax || (dim != 16 && dim != 32 && dim != 64)) return cudaErrorInvalidValue;
     if (nq <= 0) return cudaSuccess;
@@ -201,7 +250,7 @@ cudaError_t launch_hamming_topk(const uint8_t* q, const uint8_t* qmask, int nq, 
     dim3 grid(qblocks, splits);
     const bool masked = qmask && dmask;
 #define MCS_TOPK(W, M) hamming_topk_kernel<W, M><<<grid, kTopkThreads, 0, st>>>((const uint32_t*)q, (const uint32_t*)qmask, nq, \
-        (const uint32_t*)d, (const uint32_t*)dmask, nd, db_skip, K, chunk, g_part)
+        (const uint32_t*)d, (const uint32_t*)dmask, nd, db_skip, K, chunk, bound, g_part)
     if (dim == 16) { if (masked) MCS_TOPK(4, true); else MCS_TOPK(4, false); }
     else if (dim == 32) { if (masked) MCS_TOPK(8, true); else MCS_TOPK(8, false); }
     else { if (masked) MCS_TOPK(16, true); else MCS_TOPK(16, false); }
@@ -219,8 +268,8 @@ cudaError_t launch_hamming_topk(const uint8_t* q, const uint8_t* qmask, int nq, 
 template <int WORDS, bool MASKED>
 __global__ void __launch_bounds__(kTopkThreads)
 hamming_stream_kernel(const uint32_t* __restrict__ desc, const uint32_t* __restrict__ dmask, const int* __restrict__ counts,
-                      const int n_cams, const int capacity, const int K, const int img_lo, int* __restrict__ out_idx,
-                      int* __restrict__ out_dist) {
+                      const int n_cams, const int capacity, const int K, const int img_lo, const unsigned bound,
+                      int* __restrict__ out_idx, int* __restrict__ out_dist) {
     __shared__ __align__(16) uint32_t s_d[kDbTile * WORDS];
     __shared__ __align__(16) uint32_t s_m[MASKED ? kDbTile * WORDS : 4];
     const int img = blockIdx.y + img_lo;
@@ -267,9 +316,8 @@ hamming_stream_kernel(const uint32_t* __restrict__ desc, const uint32_t* __restr
         __syncthreads();
         for (int j = 0; j < tn; ++j) {
             // bit-level Hamming distance; masked form = (popc(x&ma) + popc(x&mb)) / 2, integer division (ref :2472)
-            unsigned dist = hamming_words<WORDS, MASKED>(qw, qm, s_d + j * WORDS, s_m + j * WORDS);
-            if (MASKED) dist >>= 1;
-            if (dist < worst) {
+            const unsigned dist = hamming_bounded<WORDS, MASKED>(qw, qm, s_d + j * WORDS, s_m + j * WORDS, min(worst, bound));
+            if (dist < min(worst, bound)) {
                 unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)(t0 + j);
 #pragma unroll
                 for (int k = 0; k < kTopKMax; ++k) {
@@ -294,13 +342,13 @@ hamming_stream_kernel(const uint32_t* __restrict__ desc, const uint32_t* __restr
 }
 
 cudaError_t launch_hamming_stream(const uint8_t* desc, const uint8_t* dmask, const int* counts, int img_lo, int img_count,
-                                  int n_cams, int capacity, int dim, int K, int* out_idx, int* out_dist, cudaStream_t st) {
+                                  int n_cams, int capacity, int dim, int K, unsigned bound, int* out_idx, int* out_dist, cudaStream_t st) {
     if (K < 1 || K > kTopKMax || (dim != 16 && dim != 32 && dim != 64)) return cudaErrorInvalidValue;
     if (img_count < 1) return cudaSuccess;
     dim3 grid((capacity + kTopkThreads - 1) / kTopkThreads, img_count);
     const bool masked = dmask != nullptr;
 #define MCS_HS(W, M) hamming_stream_kernel<W, M><<<grid, kTopkThreads, 0, st>>>((const uint32_t*)desc, (const uint32_t*)dmask, counts, \
-        n_cams, capacity, K, img_lo, out_idx, out_dist)
+        n_cams, capacity, K, img_lo, bound, out_idx, out_dist)
     if (dim == 16) { if (masked) MCS_HS(4, true); else MCS_HS(4, false); }
     else if (dim == 32) { if (masked) MCS_HS(8, true); else MCS_HS(8, false); }
     else { if (masked) MCS_HS(16, true); else MCS_HS(16, false); }

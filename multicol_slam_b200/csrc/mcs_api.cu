@@ -682,7 +682,7 @@ int mcs_extract_batch(mcs_extractor* ex, int32_t n_images, const uint8_t* images
             ++ex->sf_replays;
         } else {
             const int* coi_d = nullptr;
-            rc = prepare_inputs(ex, n_images, width, height, stride, masks, cams, n_cams, cam_of_image, st, true, nullptr, &coi_d);
+            rc = prepare_inputs(ex, n_images, width, height, dpitch /* K1 reads the re-pitched copy */, masks, cams, n_cams, cam_of_image, st, true, nullptr, &coi_d);
             if (rc) return rc;
             rc = enqueue_small(ex, n_images, width, height, stride, dpitch, coi_d, capacity, dmask_out != nullptr, st);
             if (rc) return rc;
@@ -853,7 +853,30 @@ int mcs_match_stream_device(const uint8_t* desc_dev, const uint8_t* dmask_dev, c
     if (n_frames < 1 || n_cams < 1 || capacity < 1 || K < 1 || K > 8) return fail(MCS_ERR_INVALID, "bad sizes (K must be 1..8)");
     if (dim != 16 && dim != 32 && dim != 64) return fail(MCS_ERR_INVALID, "dim must be 16, 32 or 64");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(launch_hamming_stream(desc_dev, dmask_dev, counts_dev, 0, n_frames * n_cams, n_cams, capacity, dim, K, match_idx_dev, match_dist_dev, st));
+    CK(launch_hamming_stream(desc_dev, dmask_dev, counts_dev, 0, n_frames * n_cams, n_cams, capacity, dim, K, 0xFFFFFFFFu, match_idx_dev, match_dist_dev, st));
+    return MCS_OK;
+}
+
+int mcs_match_stream_greedy_device(const uint8_t* desc_dev, const uint8_t* dmask_dev, const int32_t* counts_dev, int32_t n_frames,
+                                   int32_t n_cams, int32_t capacity, int32_t dim, int32_t th_low, double nnratio,
+                                   int32_t* matches12_dev, int32_t* nmatches_dev, void* stream) {
+    if (!desc_dev || !counts_dev || !matches12_dev || !nmatches_dev) return fail(MCS_ERR_INVALID, "null argument");
+    if (n_frames < 1 || n_cams < 1 || capacity < 1 || capacity > 65535) return fail(MCS_ERR_INVALID, "bad sizes (capacity must be 1..65535)");
+    if (dim != 16 && dim != 32 && dim != 64) return fail(MCS_ERR_INVALID, "dim must be 16, 32 or 64");
+    cudaStream_t st = (cudaStream_t)stream;
+    constexpr int K = 4;
+    const size_t n = (size_t)n_frames * n_cams * capacity;
+    int *li = nullptr, *ld = nullptr, *redo = nullptr;
+    CK(cudaMallocAsync((void**)&li, n * K * sizeof(int), st));
+    CK(cudaMallocAsync((void**)&ld, n * K * sizeof(int), st));
+    CK(cudaMallocAsync((void**)&redo, (size_t)n_frames * n_cams * sizeof(int), st));
+    cudaError_t e = launch_hamming_stream(desc_dev, dmask_dev, counts_dev, 0, n_frames * n_cams, n_cams, capacity, dim, K,
+                                          greedy_dist_bound(th_low, nnratio), li, ld, st);
+    if (e == cudaSuccess)
+        e = launch_stream_replay(li, ld, counts_dev, desc_dev, dmask_dev, dim, 0, n_frames * n_cams, n_cams, capacity, K, th_low, nnratio,
+                                 matches12_dev, nmatches_dev, redo, st);
+    cudaFreeAsync(li, st); cudaFreeAsync(ld, st); cudaFreeAsync(redo, st);
+    CK(e);
     return MCS_OK;
 }
 
@@ -999,8 +1022,9 @@ static int extract_match_stream_impl(mcs_extractor* ex, int32_t n_frames, int32_
         // the matching of chunk c runs on its own stream, so that K1..K3 of chunk c+1 (on `st`) fill the SMs behind its tail;
         // it reads descriptors of this chunk and of the last frame of the previous one, both final at ev_feat[c]
         CK(cudaStreamWaitEvent(ex->s_match, ev_feat[c], 0));
-        CK(launch_hamming_stream(desc_d, dmask_for_match, counts_d, img_lo, nimg, n_cams, capacity, ds, K, ex->match_idx.p,
-                                 ex->match_dist.p, ex->s_match));
+        // with the greedy acceptance on the device the lists only need the entries that can influence it (kernels.h: greedy_dist_bound)
+        CK(launch_hamming_stream(desc_d, dmask_for_match, counts_d, img_lo, nimg, n_cams, capacity, ds, K,
+                                 replay ? greedy_dist_bound(th_low, nnratio) : 0xFFFFFFFFu, ex->match_idx.p, ex->match_dist.p, ex->s_match));
         if (replay)     // greedy acceptance of SearchByBoW(KF1, KF2) over the lists of this chunk, still on the device
             CK(launch_stream_replay(ex->match_idx.p, ex->match_dist.p, counts_d, desc_d, dmask_for_match, ds, img_lo, nimg, n_cams, capacity, K,
                                     th_low, nnratio, ex->m12.p, ex->nmat.p, ex->redo.p, ex->s_match));

@@ -140,7 +140,7 @@ int mcs_hamming_topk_device(const uint8_t* q_dev, const uint8_t* qmask_dev, int3
     if (!q_dev || !d_dev || !topk_idx_dev || !topk_dist_dev) return mfail(MCS_ERR_INVALID, "null argument");
     if (nq < 0 || nd < 0 || K < 1 || K > 8) return mfail(MCS_ERR_INVALID, "bad sizes (K must be 1..8)");
     if (dim != 16 && dim != 32 && dim != 64) return mfail(MCS_ERR_INVALID, "dim must be 16, 32 or 64");
-    MCK(launch_hamming_topk(q_dev, qmask_dev, nq, d_dev, dmask_dev, nd, db_skip_dev, dim, K, topk_idx_dev, topk_dist_dev,
+    MCK(launch_hamming_topk(q_dev, qmask_dev, nq, d_dev, dmask_dev, nd, db_skip_dev, dim, K, 0xFFFFFFFFu, topk_idx_dev, topk_dist_dev,
                             (cudaStream_t)stream));
     return MCS_OK;
 }
@@ -187,9 +187,10 @@ static int bruteforce_core(const uint8_t* q_dev, const uint8_t* qm_dev, const ui
         // GPU: K best unmatched database entries for every remaining query (state at the start of the round)
         MCK(cudaMemcpyAsync(ds.p, skip.data(), nd, cudaMemcpyHostToDevice, st));
         const int nrem = nq - q0;
-        int rc = mcs_hamming_topk_device(q_dev + (size_t)q0 * dim, masked ? qm_dev + (size_t)q0 * dim : nullptr, nrem, d_dev,
-                                         masked ? dm_dev : nullptr, nd, ds.as<uint8_t>(), dim, K, di.as<int>(), dt.as<int>(), st);
-        if (rc) return rc;
+        // entries at or beyond the relevance bound of (th_low, nnratio) stay out of the lists: a list shorter than K then means
+        // "every entry that can influence the decision is here", and unrelated pairs cost half the popcount work (match_kernels.cu)
+        MCK(launch_hamming_topk(q_dev + (size_t)q0 * dim, masked ? qm_dev + (size_t)q0 * dim : nullptr, nrem, d_dev, masked ? dm_dev : nullptr,
+                                nd, ds.as<uint8_t>(), dim, K, greedy_dist_bound(th_low, nnratio), di.as<int>(), dt.as<int>(), st));
         MCK(cudaMemcpyAsync(tidx.data(), di.p, (size_t)nrem * K * 4, cudaMemcpyDeviceToHost, st));
         MCK(cudaMemcpyAsync(tdist.data(), dt.p, (size_t)nrem * K * 4, cudaMemcpyDeviceToHost, st));
         MCK(cudaStreamSynchronize(st));

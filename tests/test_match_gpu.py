@@ -491,8 +491,21 @@ def test_packed_extraction_replay_and_device_bruteforce(api, oa, cams):
         # short lists force the in-kernel rescan of undecidable queries: the result must not depend on K
         idx1, dist1 = api.match_stream_device(out["desc"], out["dmask"], out["counts"], Fn, nc, K=1, stream=st)
         m12b, nmb, _ = api.match_stream_replay_device(idx1, dist1, out["counts"], out["desc"], out["dmask"], Fn, nc, 32, 0.9, stream=st)
+        # lists + replay as one call, the lists cut at the relevance bound of (th_low, nnratio): same matches; also for other
+        # thresholds, including ones where the bound exceeds every possible distance
+        m12c, nmc = api.match_stream_greedy_device(out["desc"], out["dmask"], out["counts"], Fn, nc, 32, 0.9, stream=st)
+        other = []
+        for th, nn in ((50, 0.6), (100, 0.8), (20, 0.99), (300, 0.05)):
+            i2, d2 = api.match_stream_device(out["desc"], out["dmask"], out["counts"], Fn, nc, K=3, stream=st)
+            a = api.match_stream_replay_device(i2, d2, out["counts"], out["desc"], out["dmask"], Fn, nc, th, nn, stream=st)
+            b = api.match_stream_greedy_device(out["desc"], out["dmask"], out["counts"], Fn, nc, th, nn, stream=st)
+            other.append((a, b))
     torch.cuda.synchronize(dev)
     assert torch.equal(m12, m12b) and torch.equal(nm, nmb)
+    assert torch.equal(m12, m12c) and torch.equal(nm, nmc)
+    for a, b in other:
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert other[1][0][1].sum().item() > nm.sum().item()            # the looser rule accepts more: the sweep is not vacuous
     for k in ("counts", "kps", "desc", "dmask"):
         assert torch.equal(out[k], ref[k]), k
     # the numpy unpacker reads the same buffer
