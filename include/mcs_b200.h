@@ -194,8 +194,8 @@ int  mcs_match_stream_replay_device(const int32_t* match_idx_dev, const int32_t*
  * acceptance rule, ref src/cORBmatcher.cpp:885-966, of every image against the same camera's image one frame earlier): K-best
  * lists in scratch memory of the stream's pool, then the greedy replay.  Because th_low and nnratio are known to the list kernel
  * here, entries that cannot influence any decision (distance >= the smallest b with (th_low - 1) < nnratio * b) are left out of
- * the lists, which lets the kernel drop a pair after the first half of its words (see match_kernels.cu); the matches are the same
- * as mcs_match_stream_device + mcs_match_stream_replay_device give for any K. */
+ * the lists, so a list shorter than K proves that every relevant entry is in it and the replay rescans less often; the matches
+ * are the same as mcs_match_stream_device + mcs_match_stream_replay_device give for any K. */
 int  mcs_match_stream_greedy_device(const uint8_t* desc_dev, const uint8_t* dmask_dev, const int32_t* counts_dev,
                                     int32_t n_frames, int32_t n_cams, int32_t capacity, int32_t dim, int32_t th_low, double nnratio,
                                     int32_t* matches12_dev, int32_t* nmatches_dev, void* stream);
@@ -260,6 +260,9 @@ int  mcs_match_bruteforce(const uint8_t* q, const uint8_t* qmask, const uint8_t*
 int  mcs_match_bruteforce_device(const uint8_t* q_dev, const uint8_t* qmask_dev, const uint8_t* valid1, int32_t nq,
                                  const uint8_t* d_dev, const uint8_t* dmask_dev, const uint8_t* valid2, int32_t nd,
                                  int32_t dim, int32_t th_low, double nnratio, int32_t* matches12, int32_t* nmatches, void* stream);
+/* Diagnostics: K-best rounds the last mcs_match_bruteforce[_device] call of this thread needed (1 = every query was decided from
+ * its first list; a query whose list was used up by matches accepted earlier in the same round starts another one). */
+int  mcs_last_bruteforce_rounds(void);
 
 
 /* cORBmatcher::SearchForTriangulationRaw(KF1, KF2, ...) (ref src/cORBmatcher.cpp:968-1156): all-pairs scan, same camera only,

@@ -87,56 +87,6 @@ __device__ __forceinline__ unsigned hamming_words(const uint32_t (&qw)[WORDS], c
     return dist;
 }
 
-// Sum over N consecutive words, N = number of 32-bit words actually counted (2 per descriptor word when masked).
-template <int H, bool MASKED>
-__device__ __forceinline__ unsigned half_sum(const uint32_t* qw, const uint32_t* qm, const uint32_t* dd, const uint32_t* dm) {
-    if constexpr (MASKED) {
-        if constexpr (H == 8) {
-            uint32_t w[16];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { w[2 * k] = xor_and(qw[k], dd[k], qm[k]); w[2 * k + 1] = xor_and(qw[k], dd[k], dm[k]); }
-            return popc_sum16(w);
-        } else if constexpr (H == 4) {
-            uint32_t w[8];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { w[2 * k] = xor_and(qw[k], dd[k], qm[k]); w[2 * k + 1] = xor_and(qw[k], dd[k], dm[k]); }
-            return popc_sum8(w);
-        } else {
-            unsigned s = 0;
-#pragma unroll
-            for (int k = 0; k < H; ++k) s += __popc(xor_and(qw[k], dd[k], qm[k])) + __popc(xor_and(qw[k], dd[k], dm[k]));
-            return s;
-        }
-    } else {
-        if constexpr (H == 8) {
-            uint32_t w[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) w[k] = qw[k] ^ dd[k];
-            return popc_sum8(w);
-        } else {
-            unsigned s = 0;
-#pragma unroll
-            for (int k = 0; k < H; ++k) s += __popc(qw[k] ^ dd[k]);
-            return s;
-        }
-    }
-}
-// Distance of one pair, evaluated in two halves.  The bit count of the first half is a lower bound of the whole, so a pair whose
-// first half already proves dist >= lim (lim = the current K-th best, or the caller's relevance bound) returns "infinity"
-// without touching the second half.  For descriptors of unrelated features the half count sits ~3 sigma above 2 * TH_LOW, so
-// with a relevance bound nearly every pair costs half the LOP3 / POPC work; the branch is per lane, but the second half is only
-// issued for warps in which some lane survived.
-template <int WORDS, bool MASKED>
-__device__ __forceinline__ unsigned hamming_bounded(const uint32_t (&qw)[WORDS], const uint32_t* qm, const uint32_t* dd, const uint32_t* dm,
-                                                    const unsigned lim) {
-    constexpr int H = WORDS / 2;
-    unsigned s = half_sum<H, MASKED>(qw, qm, dd, dm);
-    const unsigned lim2 = MASKED ? (lim > 0x7FFFFFFFu ? 0xFFFFFFFFu : 2u * lim) : lim;
-    if (s >= lim2) return 0xFFFFFFFFu;
-    s += half_sum<H, MASKED>(qw + H, MASKED ? qm + H : qm, dd + H, MASKED ? dm + H : dm);
-    return MASKED ? s >> 1 : s;
-}
-
 template <int WORDS, bool MASKED>
 __global__ void __launch_bounds__(kTopkThreads)
 hamming_topk_kernel(const uint32_t* __restrict__ q, const uint32_t* __restrict__ qmask, const int nq,
@@ -179,8 +129,9 @@ hamming_topk_kernel(const uint32_t* __restrict__ q, const uint32_t* __restrict__
         for (int j = 0; j < tn; ++j) {
             if (s_skip[j]) continue;       // uniform across the CTA
             // bit-level Hamming distance; masked form = (popc(x&ma) + popc(x&mb)) / 2, integer division (ref :2472)
-            const unsigned dist = hamming_bounded<WORDS, MASKED>(qw, qm, s_d + j * WORDS, s_m + j * WORDS, min(worst, bound));
-            if (dist < min(worst, bound)) {            // strict: equal distances keep the earlier index
+            unsigned dist = hamming_words<WORDS, MASKED>(qw, qm, s_d + j * WORDS, s_m + j * WORDS);
+            if (MASKED) dist >>= 1;
+            if (dist < min(worst, bound)) {            // strict: equal distances keep the earlier index; entries at or beyond `bound` are not listed
                 unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)(t0 + j);
 #pragma unroll
                 for (int k = 0; k < kTopKMax; ++k) {
@@ -316,7 +267,8 @@ hamming_stream_kernel(const uint32_t* __restrict__ desc, const uint32_t* __restr
         __syncthreads();
         for (int j = 0; j < tn; ++j) {
             // bit-level Hamming distance; masked form = (popc(x&ma) + popc(x&mb)) / 2, integer division (ref :2472)
-            const unsigned dist = hamming_bounded<WORDS, MASKED>(qw, qm, s_d + j * WORDS, s_m + j * WORDS, min(worst, bound));
+            unsigned dist = hamming_words<WORDS, MASKED>(qw, qm, s_d + j * WORDS, s_m + j * WORDS);
+            if (MASKED) dist >>= 1;
             if (dist < min(worst, bound)) {
                 unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)(t0 + j);
 #pragma unroll

@@ -172,6 +172,9 @@ int mcs_hamming_topk(const uint8_t* q, const uint8_t* qmask, int32_t nq, const u
 
 // SearchByBoW(KF1, KF2) (ref :885-966) with the descriptors already on the device: K best unmatched database entries per query
 // on the GPU, sequential greedy replay on the host, further rounds for queries whose list was used up by earlier matches
+static thread_local int g_bf_rounds = 0;
+int mcs_last_bruteforce_rounds(void) { return g_bf_rounds; }
+
 static int bruteforce_core(const uint8_t* q_dev, const uint8_t* qm_dev, const uint8_t* valid1, int nq, const uint8_t* d_dev,
                            const uint8_t* dm_dev, const uint8_t* valid2, int nd, int dim, int th_low, double nnratio, int* matches12,
                            int* nmatches, cudaStream_t st) {
@@ -183,12 +186,14 @@ static int bruteforce_core(const uint8_t* q_dev, const uint8_t* qm_dev, const ui
     if (valid2) for (int i = 0; i < nd; ++i) skip[i] = valid2[i] ? 0 : 1;
     std::vector<int> tidx((size_t)nq * K), tdist((size_t)nq * K);
     int q0 = 0, nm = 0;
+    g_bf_rounds = 0;
     while (q0 < nq) {
+        ++g_bf_rounds;
         // GPU: K best unmatched database entries for every remaining query (state at the start of the round)
         MCK(cudaMemcpyAsync(ds.p, skip.data(), nd, cudaMemcpyHostToDevice, st));
         const int nrem = nq - q0;
         // entries at or beyond the relevance bound of (th_low, nnratio) stay out of the lists: a list shorter than K then means
-        // "every entry that can influence the decision is here", and unrelated pairs cost half the popcount work (match_kernels.cu)
+        // "every entry that can influence the decision is here" and the query never needs another round
         MCK(launch_hamming_topk(q_dev + (size_t)q0 * dim, masked ? qm_dev + (size_t)q0 * dim : nullptr, nrem, d_dev, masked ? dm_dev : nullptr,
                                 nd, ds.as<uint8_t>(), dim, K, greedy_dist_bound(th_low, nnratio), di.as<int>(), dt.as<int>(), st));
         MCK(cudaMemcpyAsync(tidx.data(), di.p, (size_t)nrem * K * 4, cudaMemcpyDeviceToHost, st));

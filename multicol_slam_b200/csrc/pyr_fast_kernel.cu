@@ -59,7 +59,7 @@ constexpr int kSrcWB = 176;                 // staged source row stride (bytes, 
 constexpr int kT8S = 80;                    // byte tile row stride
 constexpr int kT16S = 72;                   // 16-bit tile row stride (elements)
 constexpr int kScoreS = 68;                 // score tile row stride in 16-bit elements (66 used)
-constexpr int kMaxTileCorners = kTW * kTH / 4;
+constexpr int kWarpCorners = (kTH / (kThreads / 32)) * (kTW / 2);   // a warp owns kTH/8 rows; strict 3x3 maxima are never adjacent in a row
 
 __device__ __forceinline__ unsigned vneg2(unsigned a) { return __vadd2(~a, 0x00010001u); }
 
@@ -110,8 +110,8 @@ pyr_fast_kernel(const __grid_constant__ CUtensorMap src_map, const int use_tma,
     __shared__ int16_t s_ys0[kTileH], s_ys1[kTileH], s_yb0[kTileH], s_yb1[kTileH];
     __shared__ int16_t s_cellx[kTW + 2], s_celly[kTH + 2];
     __shared__ int16_t s_mx[kTW], s_my[kTH];                          // level-0 mask coordinates of the tile's pixels
-    __shared__ uint32_t s_list[kMaxTileCorners];
-    __shared__ int s_n, s_base;
+    __shared__ uint32_t s_list[(kThreads / 32) * kWarpCorners];       // one segment per warp: no atomics while collecting
+    __shared__ int s_wn[kThreads / 32], s_base;
 
     // 16-bit score tiles (two copies offset by one pixel, like the pixel tiles); they reuse the source staging
     // area, which is dead once the tile has been resized
@@ -135,7 +135,6 @@ pyr_fast_kernel(const __grid_constant__ CUtensorMap src_map, const int use_tma,
     const int sx_base = sx_lo & ~15;
     const int wb = use_tma ? g.box_w : kSrcWB;                          // row stride of the staged region in bytes
     if (tid == 0) {
-        s_n = 0;
         if (use_tma) {
             // the barrier is initialised and armed by the same thread that issues the copy; every other thread first sees it
             // after the __syncthreads below, then waits for phase 0
@@ -309,8 +308,10 @@ pyr_fast_kernel(const __grid_constant__ CUtensorMap src_map, const int use_tma,
     if (!fast_on) return;                                   // uniform for the CTA: no corner can come out of this tile
     const uint8_t* m0p = mask0 + (size_t)cam_b * mask_bytes;
     // A warp owns one tile row per pass (32 pixel pairs), every lane evaluates its pair branch-free and the warp VOTES: two
-    // ballots give the number of surviving corners and each lane's slot, one shared-memory atomic per warp and pass reserves
-    // the slots (the per-corner divergent append this replaces was 23 % of the kernel's instructions at 2.5 active lanes).
+    // ballots give the number of surviving corners and each lane's slot in the warp's own list segment (the per-corner divergent
+    // append this replaces was 23 % of the kernel's instructions at 2.5 active lanes; a per-pass shared atomic still 6 %).  The
+    // level-0 mask is only consulted when the row segment holds a strict maximum at all.
+    int wn = 0;                                             // corners this warp has collected (warp-uniform)
 #pragma unroll
     for (int i = tid; i < kTH * (kTW / 2); i += kThreads) {
         const int y = i >> 5, j = i & 31;
@@ -325,28 +326,34 @@ pyr_fast_kernel(const __grid_constant__ CUtensorMap src_map, const int use_tma,
         const int sv0 = (int)(C & 0xFFFFu), sv1 = (int)(C >> 16);
         // strict maximum of its 3x3 (implies a non-zero score), then the mask of its own pixel (mask applied after NMS)
         bool k0 = sv0 > (int)(nm & 0xFFFFu), k1 = sv1 > (int)(nm >> 16);
-        if (k0) k0 = m0p[(size_t)s_my[y] * mask_w + s_mx[2 * j]] != 0;
-        if (k1) k1 = m0p[(size_t)s_my[y] * mask_w + s_mx[2 * j + 1]] != 0;
-        const unsigned b0 = __ballot_sync(0xffffffffu, k0), b1 = __ballot_sync(0xffffffffu, k1);
-        const int n0 = __popc(b0), nn = n0 + __popc(b1);
-        if (nn) {                                                                // warp-uniform
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_n, nn);
-            base = __shfl_sync(0xffffffffu, base, 0);
+        unsigned b0 = __ballot_sync(0xffffffffu, k0), b1 = __ballot_sync(0xffffffffu, k1);
+        if (b0 | b1) {                                                           // warp-uniform: some pixel of this row segment is a maximum
+            if (k0) k0 = m0p[(size_t)s_my[y] * mask_w + s_mx[2 * j]] != 0;
+            if (k1) k1 = m0p[(size_t)s_my[y] * mask_w + s_mx[2 * j + 1]] != 0;
+            b0 = __ballot_sync(0xffffffffu, k0); b1 = __ballot_sync(0xffffffffu, k1);
+            const int n0 = __popc(b0);
             const unsigned lt = (1u << lane) - 1u;
-            if (k0) s_list[base + __popc(b0 & lt)] = pack_corner(X0 + 2 * j, Y0 + y, sv0);
-            if (k1) s_list[base + n0 + __popc(b1 & lt)] = pack_corner(X0 + 2 * j + 1, Y0 + y, sv1);
+            uint32_t* wl = s_list + wid * kWarpCorners + wn;
+            if (k0) wl[__popc(b0 & lt)] = pack_corner(X0 + 2 * j, Y0 + y, sv0);
+            if (k1) wl[n0 + __popc(b1 & lt)] = pack_corner(X0 + 2 * j + 1, Y0 + y, sv1);
+            wn += n0 + __popc(b1);
         }
     }
+    if (lane == 0) s_wn[wid] = wn;
     __syncthreads();
-    const int n = s_n;
+    int n = 0, my_off = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) {
+        if (w == wid) my_off = n;
+        n += s_wn[w];
+    }
     if (n == 0) return;
     if (tid == 0) s_base = atomicAdd(&raw_count[b * nlevels + level], n);
     __syncthreads();
     uint32_t* rlist = raw + (size_t)b * raw_img_stride + g.raw_off;
-    for (int i = tid; i < n; i += kThreads) {
-        const int pos = s_base + i;
-        if (pos < g.raw_cap) rlist[pos] = s_list[i];
+    for (int i = lane; i < wn; i += 32) {
+        const int pos = s_base + my_off + i;
+        if (pos < g.raw_cap) rlist[pos] = s_list[wid * kWarpCorners + i];
     }
 }
 

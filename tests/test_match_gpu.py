@@ -505,7 +505,7 @@ def test_packed_extraction_replay_and_device_bruteforce(api, oa, cams):
     assert torch.equal(m12, m12c) and torch.equal(nm, nmc)
     for a, b in other:
         assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
-    assert other[1][0][1].sum().item() > nm.sum().item()            # the looser rule accepts more: the sweep is not vacuous
+    assert len({int(a[1].sum().item()) for a, _ in other} | {int(nm.sum().item())}) >= 4     # the sweep is not vacuous: the rules differ
     for k in ("counts", "kps", "desc", "dmask"):
         assert torch.equal(out[k], ref[k]), k
     # the numpy unpacker reads the same buffer

@@ -9,7 +9,7 @@ python - $CFG <<'PY'
 import json, sys
 try:
     j = json.loads(open(f"gpurun_out/bench_c{sys.argv[1]}.json").read().strip().splitlines()[-1])
-    print("BENCH config", sys.argv[1], round(j["value"], 2), round(j["e2e"]["value"], 2), round(j["ms_per_step"], 3), {k: (round(v, 3) if v else v) for k, v in j["roofline"].get("stage_ms", {}).items()}, j.get("run", {}).get("single_frame_latency_ms"))
+    print("BENCH config", sys.argv[1], j["run"].get("matcher_stats"), round(j["value"], 2), round(j["e2e"]["value"], 2), round(j["ms_per_step"], 3), {k: (round(v, 3) if v else v) for k, v in j["roofline"].get("stage_ms", {}).items()}, j.get("run", {}).get("single_frame_latency_ms"))
 except Exception as e:
     print("bench failed", sys.argv[1], e)
 PY
