@@ -441,9 +441,11 @@ def main():
         t_m = time.perf_counter()
         counts = v["counts"].cpu().numpy()
         valid1 = (np.arange(cap)[None, :] < counts[:, None]).astype(np.uint8).reshape(-1)
-        n, _ = api.match_bruteforce_device(v["desc"].view(B * cap, ds), v["dmask"].view(B * cap, ds), valid1, scene["db_t"], scene["dbm_t"], None,
-                                           m.TH_LOW_, 0.9, stream=stream)
-        stats["matches"] = n
+        # every key frame of the batch against the database as its own SearchByBoW(KF1, KF2): independent "already matched" state
+        # per frame, the K-best lists of all frames from one launch
+        nms, _ = api.match_bruteforce_batch_device(v["desc"].view(B * cap, ds), v["dmask"].view(B * cap, ds), valid1, np.arange(B + 1) * cap,
+                                                   scene["db_t"], scene["dbm_t"], None, m.TH_LOW_, 0.9, stream=stream)
+        stats["matches"] = int(nms.sum())
         stats["kbest_rounds"] = int(api.lib().mcs_last_bruteforce_rounds())
         stats["match_call_ms"] = (time.perf_counter() - t_m) * 1e3      # includes waiting for this step's extraction (the counts read)
 

@@ -260,6 +260,16 @@ int  mcs_match_bruteforce(const uint8_t* q, const uint8_t* qmask, const uint8_t*
 int  mcs_match_bruteforce_device(const uint8_t* q_dev, const uint8_t* qmask_dev, const uint8_t* valid1, int32_t nq,
                                  const uint8_t* d_dev, const uint8_t* dmask_dev, const uint8_t* valid2, int32_t nd,
                                  int32_t dim, int32_t th_low, double nnratio, int32_t* matches12, int32_t* nmatches, void* stream);
+/* Several query sets against ONE database in one call -- the batched key frames of the loop-closure path (BASELINE config 4:
+ * every key frame of a batch against the key-frame database).  seg_start[0..n_seg] delimits the sets inside q_dev; each set is
+ * matched exactly as a separate mcs_match_bruteforce_device call would match it (its own "database entry already used" state,
+ * as between separate SearchByBoW(KF1, KF2) calls, ref src/cORBmatcher.cpp:885-966), but the K-best lists of all sets come from
+ * one kernel launch.  matches12 [seg_start[n_seg]], nmatches [n_seg]. */
+int  mcs_match_bruteforce_batch_device(const uint8_t* q_dev, const uint8_t* qmask_dev, const uint8_t* valid1,
+                                       const int32_t* seg_start, int32_t n_seg,
+                                       const uint8_t* d_dev, const uint8_t* dmask_dev, const uint8_t* valid2, int32_t nd,
+                                       int32_t dim, int32_t th_low, double nnratio, int32_t* matches12, int32_t* nmatches, void* stream);
+
 /* Diagnostics: K-best rounds the last mcs_match_bruteforce[_device] call of this thread needed (1 = every query was decided from
  * its first list; a query whose list was used up by matches accepted earlier in the same round starts another one). */
 int  mcs_last_bruteforce_rounds(void);

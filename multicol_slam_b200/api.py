@@ -338,6 +338,25 @@ def match_stream_replay_device(idx_t, dist_t, counts_t, desc_t, dmask_t, n_frame
     return out
 
 
+def match_bruteforce_batch_device(q_t, qmask_t, valid1, seg_start, d_t, dmask_t, valid2, th_low, nnratio, stream=None):
+    """mcs_match_bruteforce_batch_device: the query sets q_t[seg_start[s]:seg_start[s+1]] each matched against the database as a separate
+    SearchByBoW(KF1, KF2) would, K-best lists of all sets from one launch.  Returns (nmatches [n_seg] numpy, matches12 numpy)."""
+    import torch
+    nq, dim = q_t.shape
+    nd = d_t.shape[0]
+    seg = np.ascontiguousarray(seg_start, np.int32)
+    assert seg[-1] == nq
+    v1 = None if valid1 is None else np.ascontiguousarray(valid1, np.uint8)
+    v2 = None if valid2 is None else np.ascontiguousarray(valid2, np.uint8)
+    m12 = np.zeros(nq, np.int32)
+    nm = np.zeros(len(seg) - 1, np.int32)
+    ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+    st = C.c_void_p(stream.cuda_stream if stream is not None else torch.cuda.current_stream(q_t.device).cuda_stream)
+    _check(lib().mcs_match_bruteforce_batch_device(ptr(q_t), ptr(qmask_t), _p(v1), _p(seg), len(seg) - 1, ptr(d_t), ptr(dmask_t), _p(v2), nd, dim,
+                                                   int(th_low), C.c_double(nnratio), _p(m12), _p(nm), st))
+    return nm, m12
+
+
 def match_stream_greedy_device(desc_t, dmask_t, counts_t, n_frames, n_cams, th_low, nnratio, out=None, stream=None):
     """mcs_match_stream_greedy_device: every image against the same camera's image one frame earlier with SearchByBoW(KF1, KF2)'s
     acceptance rule, lists + replay in one call.  desc_t/dmask_t [F*C,cap,dim] u8 cuda, counts_t [F*C] i32 cuda.

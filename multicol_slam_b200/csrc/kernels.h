@@ -43,6 +43,23 @@ cudaError_t launch_hamming_stream(const uint8_t* desc, const uint8_t* dmask, con
 // smallest distance b >= th_low such that a second-best of b or more passes the ratio test for EVERY admissible best
 // (best <= th_low - 1).  A database entry at distance >= b can neither be an accepted best nor make a ratio test fail, so the
 // K-best kernels may leave it out of their lists (`bound` argument; 0xFFFFFFFF = keep everything) without changing any decision.
+// cudaMallocAsync scratch: by default the device pool hands freed memory back to the driver at the next synchronisation, which
+// turns every call's stream-ordered allocation into a real cudaMalloc (measured: 36 ms per mcs_match_stream_greedy_device call
+// instead of 7).  Keep freed blocks in the pool.
+inline cudaError_t keep_pool_memory() {
+    static bool done[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return e;
+    cudaMemPool_t pool;
+    e = cudaDeviceGetDefaultMemPool(&pool, dev);
+    if (e != cudaSuccess) return e;
+    unsigned long long keep = ~0ull;
+    e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    done[dev] = e == cudaSuccess;
+    return e;
+}
+
 inline unsigned greedy_dist_bound(int th_low, double nnratio) {
     if (th_low <= 0) return 0u;                      // nothing can be accepted
     long b = th_low;

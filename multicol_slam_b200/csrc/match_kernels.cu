@@ -196,7 +196,9 @@ cudaError_t launch_hamming_topk(const uint8_t* q, const uint8_t* qmask, int nq, 
     // concurrent callers -- the reference runs its matchers from three threads -- and different streams never share it
     const size_t need = (size_t)splits * nq * kTopKMax * sizeof(unsigned long long);
     unsigned long long* g_part = nullptr;
-    cudaError_t e = cudaMallocAsync((void**)&g_part, need, st);
+    cudaError_t e = keep_pool_memory();
+    if (e != cudaSuccess) return e;
+    e = cudaMallocAsync((void**)&g_part, need, st);
     if (e != cudaSuccess) return e;
     dim3 grid(qblocks, splits);
     const bool masked = qmask && dmask;

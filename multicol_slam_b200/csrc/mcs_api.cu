@@ -867,6 +867,7 @@ int mcs_match_stream_greedy_device(const uint8_t* desc_dev, const uint8_t* dmask
     constexpr int K = 4;
     const size_t n = (size_t)n_frames * n_cams * capacity;
     int *li = nullptr, *ld = nullptr, *redo = nullptr;
+    CK(keep_pool_memory());
     CK(cudaMallocAsync((void**)&li, n * K * sizeof(int), st));
     CK(cudaMallocAsync((void**)&ld, n * K * sizeof(int), st));
     CK(cudaMallocAsync((void**)&redo, (size_t)n_frames * n_cams * sizeof(int), st));

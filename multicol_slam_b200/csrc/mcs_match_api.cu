@@ -175,40 +175,47 @@ int mcs_hamming_topk(const uint8_t* q, const uint8_t* qmask, int32_t nq, const u
 static thread_local int g_bf_rounds = 0;
 int mcs_last_bruteforce_rounds(void) { return g_bf_rounds; }
 
+// seg[0..n_seg]: query segments (e.g. the key frames of a batch) whose "database entry already matched" state is independent, as
+// it is between separate SearchByBoW(KF1, KF2) calls of the reference; seg == nullptr: one segment [0, nq).  The first K-best
+// round serves all segments in ONE launch (they start from the same database state); a segment whose replay runs into a list
+// used up by its own earlier matches finishes alone with further rounds over its remaining queries.
 static int bruteforce_core(const uint8_t* q_dev, const uint8_t* qm_dev, const uint8_t* valid1, int nq, const uint8_t* d_dev,
                            const uint8_t* dm_dev, const uint8_t* valid2, int nd, int dim, int th_low, double nnratio, int* matches12,
-                           int* nmatches, cudaStream_t st) {
+                           int* nmatches, cudaStream_t st, const int* seg = nullptr, int n_seg = 1) {
     const bool masked = qm_dev && dm_dev;
     constexpr int K = 4;
+    const int one_seg[2] = {0, nq};
+    if (!seg) { seg = one_seg; n_seg = 1; }
     Dev ds, di, dt;
     MCK(ds.alloc(nd)); MCK(di.alloc((size_t)nq * K * 4)); MCK(dt.alloc((size_t)nq * K * 4));
-    std::vector<uint8_t> skip(nd, 0), newly(nd, 0);
-    if (valid2) for (int i = 0; i < nd; ++i) skip[i] = valid2[i] ? 0 : 1;
+    std::vector<uint8_t> base_skip(nd, 0), skip, newly(nd, 0);
+    if (valid2) for (int i = 0; i < nd; ++i) base_skip[i] = valid2[i] ? 0 : 1;
     std::vector<int> tidx((size_t)nq * K), tdist((size_t)nq * K);
-    int q0 = 0, nm = 0;
-    g_bf_rounds = 0;
-    while (q0 < nq) {
+    const unsigned bound = greedy_dist_bound(th_low, nnratio);
+    // GPU: K best unmatched database entries for queries [q0, q1) under the skip state `sk`.  Entries at or beyond the relevance
+    // bound of (th_low, nnratio) stay out of the lists: a list shorter than K then means "every entry that can influence the
+    // decision is here" and the query never needs another round.
+    auto kbest = [&](int q0, int q1, const std::vector<uint8_t>& sk) -> int {
         ++g_bf_rounds;
-        // GPU: K best unmatched database entries for every remaining query (state at the start of the round)
-        MCK(cudaMemcpyAsync(ds.p, skip.data(), nd, cudaMemcpyHostToDevice, st));
-        const int nrem = nq - q0;
-        // entries at or beyond the relevance bound of (th_low, nnratio) stay out of the lists: a list shorter than K then means
-        // "every entry that can influence the decision is here" and the query never needs another round
-        MCK(launch_hamming_topk(q_dev + (size_t)q0 * dim, masked ? qm_dev + (size_t)q0 * dim : nullptr, nrem, d_dev, masked ? dm_dev : nullptr,
-                                nd, ds.as<uint8_t>(), dim, K, greedy_dist_bound(th_low, nnratio), di.as<int>(), dt.as<int>(), st));
-        MCK(cudaMemcpyAsync(tidx.data(), di.p, (size_t)nrem * K * 4, cudaMemcpyDeviceToHost, st));
-        MCK(cudaMemcpyAsync(tdist.data(), dt.p, (size_t)nrem * K * 4, cudaMemcpyDeviceToHost, st));
+        MCK(cudaMemcpyAsync(ds.p, sk.data(), nd, cudaMemcpyHostToDevice, st));
+        const int n = q1 - q0;
+        MCK(launch_hamming_topk(q_dev + (size_t)q0 * dim, masked ? qm_dev + (size_t)q0 * dim : nullptr, n, d_dev, masked ? dm_dev : nullptr,
+                                nd, ds.as<uint8_t>(), dim, K, bound, di.as<int>(), dt.as<int>(), st));
+        MCK(cudaMemcpyAsync(tidx.data(), di.p, (size_t)n * K * 4, cudaMemcpyDeviceToHost, st));
+        MCK(cudaMemcpyAsync(tdist.data(), dt.p, (size_t)n * K * 4, cudaMemcpyDeviceToHost, st));
         MCK(cudaStreamSynchronize(st));
-        std::fill(newly.begin(), newly.end(), 0);
-        // host: sequential replay (ref :899-961); a query whose list is exhausted by entries matched
-        // during this round starts the next round
-        int i1 = q0;
-        for (; i1 < nq; ++i1) {
-            if (valid1 && !valid1[i1]) continue;
-            const int* li = &tidx[(size_t)(i1 - q0) * K];
-            const int* ld = &tdist[(size_t)(i1 - q0) * K];
+        return MCS_OK;
+    };
+    // host: sequential replay (ref :899-961) of queries [i0, i1) over lists that start at query `l0`; entries matched since the
+    // lists were computed are flagged in `newly`.  Returns the first query whose list was used up by them (i1 if none).
+    auto replay = [&](int i0, int i1, int l0, std::vector<uint8_t>& sk, int& nm) -> int {
+        int i = i0;
+        for (; i < i1; ++i) {
+            if (valid1 && !valid1[i]) continue;
+            const int* li = &tidx[(size_t)(i - l0) * K];
+            const int* ld = &tdist[(size_t)(i - l0) * K];
             int best1 = INT_MAX, best2 = INT_MAX, bestIdx = -1, found = 0;
-            bool complete = false;      // list holds every unmatched database entry
+            bool complete = false;      // list holds every unmatched database entry that matters
             for (int k = 0; k < K; ++k) {
                 if (li[k] < 0) { complete = true; break; }
                 if (newly[li[k]]) continue;
@@ -222,15 +229,55 @@ static int bruteforce_core(const uint8_t* q_dev, const uint8_t* qm_dev, const ui
                 if (!(found == 1 && !(best1 < th_low))) break;
             }
             if (best1 < th_low && (double)best1 < nnratio * (double)best2) {
-                matches12[i1] = bestIdx;
-                skip[bestIdx] = 1; newly[bestIdx] = 1;
+                matches12[i] = bestIdx;
+                sk[bestIdx] = 1; newly[bestIdx] = 1;
                 ++nm;
             }
         }
-        q0 = i1;
+        return i;
+    };
+    g_bf_rounds = 0;
+    int rc = kbest(0, nq, base_skip);
+    if (rc) return rc;
+    std::vector<int> stop(n_seg), nms(n_seg, 0);
+    std::vector<std::vector<int>> taken(n_seg);              // entries each segment matched in the shared first round
+    for (int s = 0; s < n_seg; ++s) {
+        skip = base_skip;
+        std::fill(newly.begin(), newly.end(), 0);
+        stop[s] = replay(seg[s], seg[s + 1], 0, skip, nms[s]);
+        if (stop[s] < seg[s + 1])
+            for (int i = seg[s]; i < stop[s]; ++i) if (matches12[i] >= 0) taken[s].push_back(matches12[i]);
     }
-    *nmatches = nm;
+    for (int s = 0; s < n_seg; ++s) {                        // segments that need more rounds finish alone
+        if (stop[s] >= seg[s + 1]) continue;
+        skip = base_skip;
+        for (int j : taken[s]) skip[j] = 1;
+        int q0 = stop[s];
+        while (q0 < seg[s + 1]) {
+            rc = kbest(q0, seg[s + 1], skip);
+            if (rc) return rc;
+            std::fill(newly.begin(), newly.end(), 0);
+            q0 = replay(q0, seg[s + 1], q0, skip, nms[s]);
+        }
+    }
+    for (int s = 0; s < n_seg; ++s) nmatches[s] = nms[s];
     return MCS_OK;
+}
+
+int mcs_match_bruteforce_batch_device(const uint8_t* q_dev, const uint8_t* qmask_dev, const uint8_t* valid1, const int32_t* seg_start,
+                                      int32_t n_seg, const uint8_t* d_dev, const uint8_t* dmask_dev, const uint8_t* valid2, int32_t nd,
+                                      int32_t dim, int32_t th_low, double nnratio, int32_t* matches12, int32_t* nmatches, void* stream) {
+    if (!q_dev || !d_dev || !matches12 || !nmatches || !seg_start) return mfail(MCS_ERR_INVALID, "null argument");
+    if (dim != 16 && dim != 32 && dim != 64) return mfail(MCS_ERR_INVALID, "dim must be 16, 32 or 64");
+    if (n_seg < 1 || seg_start[0] != 0) return mfail(MCS_ERR_INVALID, "seg_start must begin at 0 and hold n_seg + 1 offsets");
+    for (int s = 0; s < n_seg; ++s)
+        if (seg_start[s + 1] < seg_start[s]) return mfail(MCS_ERR_INVALID, "seg_start must be non-decreasing");
+    const int nq = seg_start[n_seg];
+    for (int s = 0; s < n_seg; ++s) nmatches[s] = 0;
+    for (int i = 0; i < nq; ++i) matches12[i] = -1;
+    if (nq <= 0 || nd <= 0) return MCS_OK;
+    return bruteforce_core(q_dev, qmask_dev, valid1, nq, d_dev, dmask_dev, valid2, nd, dim, th_low, nnratio, matches12, nmatches,
+                           (cudaStream_t)stream, seg_start, n_seg);
 }
 
 int mcs_match_bruteforce_device(const uint8_t* q_dev, const uint8_t* qmask_dev, const uint8_t* valid1, int32_t nq, const uint8_t* d_dev,

@@ -527,3 +527,41 @@ def test_packed_extraction_replay_and_device_bruteforce(api, oa, cams):
                                              out["dmask"][img - nc, :counts[img - nc]].contiguous(), None, 32, 0.9)
         assert gn == on and np.array_equal(gm, om)
     assert nm.sum() > 1000
+
+
+def test_bruteforce_batch_equals_separate_calls(api, oa):
+    """mcs_match_bruteforce_batch_device: key frames of a batch against one database, each with its own matched-entry state -- the
+    same matches as one mcs_match_bruteforce_device call (and the oracle's SearchByBoW(KF1, KF2)) per key frame; the sets share
+    database entries on purpose (near-duplicate queries across sets), which a shared state would hand out only once"""
+    import torch
+    rng = np.random.default_rng(5)
+    nd, per, nseg = 3000, 400, 4
+    db = rng.integers(0, 256, (nd, 32), dtype=np.uint8)
+    dbm = np.packbits(rng.random((nd, 256)) < 0.8, axis=1, bitorder="little")
+    base = db[rng.choice(nd, per, replace=False)].copy()
+    qs, qms = [], []
+    for s in range(nseg):
+        q = base.copy()
+        for i in range(per):
+            for b in rng.choice(256, rng.integers(0, 25), replace=False):
+                q[i, b // 8] ^= 1 << (b % 8)
+        qs.append(q)
+        qms.append(np.packbits(rng.random((per, 256)) < 0.7, axis=1, bitorder="little"))
+    q, qm = np.concatenate(qs), np.concatenate(qms)
+    valid1 = (rng.random(len(q)) < 0.9).astype(np.uint8)
+    valid2 = (rng.random(nd) < 0.95).astype(np.uint8)
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    seg = np.arange(nseg + 1) * per
+    nms, m12 = api.match_bruteforce_batch_device(t(q), t(qm), valid1, seg, t(db), t(dbm), valid2, 60, 0.8)
+    total = 0
+    for s in range(nseg):
+        sl = slice(seg[s], seg[s + 1])
+        n1, m1 = api.match_bruteforce_device(t(q[sl]), t(qm[sl]), valid1[sl], t(db), t(dbm), valid2, 60, 0.8)
+        on, om = oa.match_bruteforce(q[sl], db, 60, 0.8, qm[sl], dbm, valid1[sl], valid2)
+        assert n1 == on == nms[s] and np.array_equal(m1, om) and np.array_equal(m12[sl], om)
+        total += on
+    assert total > 0.5 * valid1.sum()
+    # a single shared state would differ: the sets compete for the same planted entries
+    n_shared, _ = api.match_bruteforce_device(t(q), t(qm), valid1, t(db), t(dbm), valid2, 60, 0.8)
+    assert n_shared < total
