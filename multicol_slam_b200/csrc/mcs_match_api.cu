@@ -176,91 +176,71 @@ static thread_local int g_bf_rounds = 0;
 int mcs_last_bruteforce_rounds(void) { return g_bf_rounds; }
 
 // seg[0..n_seg]: query segments (e.g. the key frames of a batch) whose "database entry already matched" state is independent, as
-// it is between separate SearchByBoW(KF1, KF2) calls of the reference; seg == nullptr: one segment [0, nq).  The first K-best
-// round serves all segments in ONE launch (they start from the same database state); a segment whose replay runs into a list
-// used up by its own earlier matches finishes alone with further rounds over its remaining queries.
+// it is between separate SearchByBoW(KF1, KF2) calls of the reference; seg == nullptr: one segment [0, nq).  One K-best launch
+// serves all queries of all segments (they start from the same database state).  The host then replays every segment in query
+// order; a query whose list was used up by matches accepted earlier in its segment gets a fresh list of its own (one-query
+// launch against the current state, kTopKMax entries), which always decides it -- the other queries keep their first lists.
 static int bruteforce_core(const uint8_t* q_dev, const uint8_t* qm_dev, const uint8_t* valid1, int nq, const uint8_t* d_dev,
                            const uint8_t* dm_dev, const uint8_t* valid2, int nd, int dim, int th_low, double nnratio, int* matches12,
                            int* nmatches, cudaStream_t st, const int* seg = nullptr, int n_seg = 1) {
     const bool masked = qm_dev && dm_dev;
-    constexpr int K = 4;
+    constexpr int K = 4, K1 = 8;
     const int one_seg[2] = {0, nq};
     if (!seg) { seg = one_seg; n_seg = 1; }
-    Dev ds, di, dt;
+    Dev ds, di, dt, di1, dt1;
     MCK(ds.alloc(nd)); MCK(di.alloc((size_t)nq * K * 4)); MCK(dt.alloc((size_t)nq * K * 4));
-    std::vector<uint8_t> base_skip(nd, 0), skip, newly(nd, 0);
+    MCK(di1.alloc(K1 * 4)); MCK(dt1.alloc(K1 * 4));
+    std::vector<uint8_t> base_skip(nd, 0), skip;
     if (valid2) for (int i = 0; i < nd; ++i) base_skip[i] = valid2[i] ? 0 : 1;
     std::vector<int> tidx((size_t)nq * K), tdist((size_t)nq * K);
+    int one_idx[K1], one_dist[K1];
+    // Entries at or beyond the relevance bound of (th_low, nnratio) stay out of the lists: a list shorter than K then means "every
+    // entry that can influence the decision is here".
     const unsigned bound = greedy_dist_bound(th_low, nnratio);
-    // GPU: K best unmatched database entries for queries [q0, q1) under the skip state `sk`.  Entries at or beyond the relevance
-    // bound of (th_low, nnratio) stay out of the lists: a list shorter than K then means "every entry that can influence the
-    // decision is here" and the query never needs another round.
-    auto kbest = [&](int q0, int q1, const std::vector<uint8_t>& sk) -> int {
-        ++g_bf_rounds;
-        MCK(cudaMemcpyAsync(ds.p, sk.data(), nd, cudaMemcpyHostToDevice, st));
-        const int n = q1 - q0;
-        MCK(launch_hamming_topk(q_dev + (size_t)q0 * dim, masked ? qm_dev + (size_t)q0 * dim : nullptr, n, d_dev, masked ? dm_dev : nullptr,
-                                nd, ds.as<uint8_t>(), dim, K, bound, di.as<int>(), dt.as<int>(), st));
-        MCK(cudaMemcpyAsync(tidx.data(), di.p, (size_t)n * K * 4, cudaMemcpyDeviceToHost, st));
-        MCK(cudaMemcpyAsync(tdist.data(), dt.p, (size_t)n * K * 4, cudaMemcpyDeviceToHost, st));
-        MCK(cudaStreamSynchronize(st));
-        return MCS_OK;
+    g_bf_rounds = 1;
+    MCK(cudaMemcpyAsync(ds.p, base_skip.data(), nd, cudaMemcpyHostToDevice, st));
+    MCK(launch_hamming_topk(q_dev, masked ? qm_dev : nullptr, nq, d_dev, masked ? dm_dev : nullptr, nd, ds.as<uint8_t>(), dim, K, bound,
+                            di.as<int>(), dt.as<int>(), st));
+    MCK(cudaMemcpyAsync(tidx.data(), di.p, (size_t)nq * K * 4, cudaMemcpyDeviceToHost, st));
+    MCK(cudaMemcpyAsync(tdist.data(), dt.p, (size_t)nq * K * 4, cudaMemcpyDeviceToHost, st));
+    MCK(cudaStreamSynchronize(st));
+    // best / second best among the list entries not taken so far (ref :899-961); false = the list cannot tell
+    auto from_list = [&](const int* li, const int* ld, int k_len, int& best1, int& best2, int& bestIdx) -> bool {
+        best1 = INT_MAX; best2 = INT_MAX; bestIdx = -1;
+        int found = 0;
+        for (int k = 0; k < k_len; ++k) {
+            if (li[k] < 0) return true;                    // the list holds every unmatched entry that matters
+            if (skip[li[k]]) continue;                     // matched by an earlier query of this segment
+            if (found == 0) { best1 = ld[k]; bestIdx = li[k]; }
+            else best2 = ld[k];
+            if (++found == 2) return true;
+        }
+        return found == 1 && !(best1 < th_low);            // second best unknown: irrelevant only if the best already fails
     };
-    // host: sequential replay (ref :899-961) of queries [i0, i1) over lists that start at query `l0`; entries matched since the
-    // lists were computed are flagged in `newly`.  Returns the first query whose list was used up by them (i1 if none).
-    auto replay = [&](int i0, int i1, int l0, std::vector<uint8_t>& sk, int& nm) -> int {
-        int i = i0;
-        for (; i < i1; ++i) {
+    for (int s = 0; s < n_seg; ++s) {
+        skip = base_skip;
+        int nm = 0;
+        for (int i = seg[s]; i < seg[s + 1]; ++i) {
             if (valid1 && !valid1[i]) continue;
-            const int* li = &tidx[(size_t)(i - l0) * K];
-            const int* ld = &tdist[(size_t)(i - l0) * K];
-            int best1 = INT_MAX, best2 = INT_MAX, bestIdx = -1, found = 0;
-            bool complete = false;      // list holds every unmatched database entry that matters
-            for (int k = 0; k < K; ++k) {
-                if (li[k] < 0) { complete = true; break; }
-                if (newly[li[k]]) continue;
-                if (found == 0) { best1 = ld[k]; bestIdx = li[k]; }
-                else if (found == 1) best2 = ld[k];
-                ++found;
-                if (found == 2) break;
-            }
-            if (found < 2 && !complete) {
-                // second best unknown; irrelevant only if the best already fails the threshold
-                if (!(found == 1 && !(best1 < th_low))) break;
+            int best1, best2, bestIdx;
+            if (!from_list(&tidx[(size_t)i * K], &tdist[(size_t)i * K], K, best1, best2, bestIdx)) {
+                ++g_bf_rounds;
+                MCK(cudaMemcpyAsync(ds.p, skip.data(), nd, cudaMemcpyHostToDevice, st));
+                MCK(launch_hamming_topk(q_dev + (size_t)i * dim, masked ? qm_dev + (size_t)i * dim : nullptr, 1, d_dev, masked ? dm_dev : nullptr,
+                                        nd, ds.as<uint8_t>(), dim, K1, bound, di1.as<int>(), dt1.as<int>(), st));
+                MCK(cudaMemcpyAsync(one_idx, di1.p, K1 * 4, cudaMemcpyDeviceToHost, st));
+                MCK(cudaMemcpyAsync(one_dist, dt1.p, K1 * 4, cudaMemcpyDeviceToHost, st));
+                MCK(cudaStreamSynchronize(st));
+                if (!from_list(one_idx, one_dist, K1, best1, best2, bestIdx)) return mfail(MCS_ERR_INVALID, "internal: fresh list undecided");
             }
             if (best1 < th_low && (double)best1 < nnratio * (double)best2) {
                 matches12[i] = bestIdx;
-                sk[bestIdx] = 1; newly[bestIdx] = 1;
+                skip[bestIdx] = 1;
                 ++nm;
             }
         }
-        return i;
-    };
-    g_bf_rounds = 0;
-    int rc = kbest(0, nq, base_skip);
-    if (rc) return rc;
-    std::vector<int> stop(n_seg), nms(n_seg, 0);
-    std::vector<std::vector<int>> taken(n_seg);              // entries each segment matched in the shared first round
-    for (int s = 0; s < n_seg; ++s) {
-        skip = base_skip;
-        std::fill(newly.begin(), newly.end(), 0);
-        stop[s] = replay(seg[s], seg[s + 1], 0, skip, nms[s]);
-        if (stop[s] < seg[s + 1])
-            for (int i = seg[s]; i < stop[s]; ++i) if (matches12[i] >= 0) taken[s].push_back(matches12[i]);
+        nmatches[s] = nm;
     }
-    for (int s = 0; s < n_seg; ++s) {                        // segments that need more rounds finish alone
-        if (stop[s] >= seg[s + 1]) continue;
-        skip = base_skip;
-        for (int j : taken[s]) skip[j] = 1;
-        int q0 = stop[s];
-        while (q0 < seg[s + 1]) {
-            rc = kbest(q0, seg[s + 1], skip);
-            if (rc) return rc;
-            std::fill(newly.begin(), newly.end(), 0);
-            q0 = replay(q0, seg[s + 1], q0, skip, nms[s]);
-        }
-    }
-    for (int s = 0; s < n_seg; ++s) nmatches[s] = nms[s];
     return MCS_OK;
 }
 
