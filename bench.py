@@ -421,6 +421,7 @@ def main():
         for k in h_feat:
             h_feat[k].copy_(v[k], non_blocking=True)
         stream.synchronize()
+        t_a = time.perf_counter()
         counts = h_feat["counts"].numpy()
         kps = h_feat["kps"].numpy().view(api.KEYPOINT_DTYPE).reshape(B, cap)
         # the F frames of this camera as the F "cameras" of one frame view: one projection launch, one window search, one replay
@@ -429,13 +430,18 @@ def main():
         desc = np.concatenate([h_feat["desc"].numpy()[f, :counts[f]] for f in range(F)])
         dmask = np.concatenate([h_feat["dmask"].numpy()[f, :counts[f]] for f in range(F)])
         Fr = api.Frame(keys, key_cam, desc, dmask, [(W, H)] * F, sf)
+        t_b = time.perf_counter()
         iv, lv, px, py, vc = api.project_mappoints(scene["mtmc_inv"], scene["mtmc"], [cams[cam_ids[0]]] * F, scene["masks_f"], scene["world"],
                                                    scene["normal"], scene["min_d"], scene["max_d"], sf)
+        t_c = time.perf_counter()
         mp = api.MapPoints(np.zeros(len(scene["world"]), np.uint8), iv, lv, px, py, vc, scene["mp_desc"], scene["mp_dmask"])
         mt = api.cORBmatcher(0.8, False, ds, True)
         n, _ = mt.SearchByProjection(Fr, mp, 3.0)
+        t_d = time.perf_counter()
         stats["matches"] = n
-        stats["match_call_ms"] = (time.perf_counter() - t_m3) * 1e3
+        stats["match_call_ms"] = (t_d - t_m3) * 1e3
+        stats["parts_ms"] = {"wait_extract+d2h": (t_a - t_m3) * 1e3, "frame_view": (t_b - t_a) * 1e3, "mcs_project_mappoints": (t_c - t_b) * 1e3,
+                             "mcs_search_by_projection": (t_d - t_c) * 1e3}
 
     def match_config4(v):
         t_m = time.perf_counter()
