@@ -864,7 +864,7 @@ int mcs_match_stream_greedy_device(const uint8_t* desc_dev, const uint8_t* dmask
     if (n_frames < 1 || n_cams < 1 || capacity < 1 || capacity > 65535) return fail(MCS_ERR_INVALID, "bad sizes (capacity must be 1..65535)");
     if (dim != 16 && dim != 32 && dim != 64) return fail(MCS_ERR_INVALID, "dim must be 16, 32 or 64");
     cudaStream_t st = (cudaStream_t)stream;
-    constexpr int K = 4;
+    constexpr int K = 8;      // under the relevance bound long lists are free in the distance loop and save rescans in the replay
     const size_t n = (size_t)n_frames * n_cams * capacity;
     int *li = nullptr, *ld = nullptr, *redo = nullptr;
     CK(keep_pool_memory());
