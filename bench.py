@@ -452,7 +452,6 @@ def main():
         nms, _ = api.match_bruteforce_batch_device(v["desc"].view(B * cap, ds), v["dmask"].view(B * cap, ds), valid1, np.arange(B + 1) * cap,
                                                    scene["db_t"], scene["dbm_t"], None, m.TH_LOW_, 0.9, stream=stream)
         stats["matches"] = int(nms.sum())
-        stats["kbest_rounds"] = int(api.lib().mcs_last_bruteforce_rounds())
         stats["match_call_ms"] = (time.perf_counter() - t_m) * 1e3      # includes waiting for this step's extraction (the counts read)
 
     step_no = [0]

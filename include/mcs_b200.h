@@ -270,8 +270,8 @@ int  mcs_match_bruteforce_batch_device(const uint8_t* q_dev, const uint8_t* qmas
                                        const uint8_t* d_dev, const uint8_t* dmask_dev, const uint8_t* valid2, int32_t nd,
                                        int32_t dim, int32_t th_low, double nnratio, int32_t* matches12, int32_t* nmatches, void* stream);
 
-/* Diagnostics: K-best launches the last mcs_match_bruteforce[_batch][_device] call of this thread needed: 1 for the lists of all
- * queries + 1 per query whose list had been used up by matches accepted earlier (that query gets a fresh one-query list). */
+/* Diagnostics: K-best launches the last mcs_match_bruteforce[_batch][_device] call of this thread needed.  Always 1 since the
+ * ordered acceptance runs on the device (queries whose list is used up are rescanned inside the replay kernel). */
 int  mcs_last_bruteforce_rounds(void);
 
 

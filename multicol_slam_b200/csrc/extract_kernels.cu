@@ -80,7 +80,7 @@ octree_kernel(const PyramidGeom* __restrict__ geom, const int cap /* node capaci
               const uint32_t* __restrict__ raw, const size_t raw_img_stride,
               const int* __restrict__ raw_count, uint16_t* __restrict__ node_of_all,
               uint32_t* __restrict__ sel_xys /* [B][sel_total] packed corner */, int* __restrict__ sel_count /* [B][L] */,
-              int* __restrict__ status) {
+              int* __restrict__ status, const int level_lo) {
     extern __shared__ __align__(16) unsigned char oct_smem[];
     unsigned long long* s_key = (unsigned long long*)oct_smem;          // pass-B sort keys / scan scratch / best-corner keys
     OctNode* s_nodes0 = (OctNode*)(s_key + cap);
@@ -91,7 +91,7 @@ octree_kernel(const PyramidGeom* __restrict__ geom, const int cap /* node capaci
     __shared__ int s_nn, s_cut;
     __shared__ unsigned s_seq;
 
-    const int level = blockIdx.x, b = blockIdx.y;
+    const int level = level_lo + blockIdx.x, b = blockIdx.y;
     const LevelGeom& g = geom->lv[level];
     const int L = geom->nlevels;
     const int tid = threadIdx.x;
@@ -328,7 +328,7 @@ octree_kernel(const PyramidGeom* __restrict__ geom, const int cap /* node capaci
 // ------------------------------------------------------------------------------------------------
 cudaError_t launch_octree(const PyramidGeom& G, const PyramidGeom* G_dev, int n_images, const uint32_t* raw,
                           const int* raw_count, uint16_t* node_of, uint32_t* sel_xys, int* sel_count, int* status,
-                          cudaStream_t st) {
+                          cudaStream_t st, int level_lo, int level_count) {
     int cap = 0;
     for (int l = 0; l < G.nlevels; ++l) cap = max(cap, G.lv[l].quota + 8);
     cap = (cap + 31) & ~31;
@@ -340,8 +340,9 @@ cudaError_t launch_octree(const PyramidGeom& G, const PyramidGeom* G_dev, int n_
         cudaError_t e = cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    dim3 grid(G.nlevels, n_images);
-    octree_kernel<<<grid, kOctThreads, smem, st>>>(G_dev, cap, raw, G.raw_total, raw_count, node_of, sel_xys, sel_count, status);
+    if (level_count < 0) level_count = G.nlevels - level_lo;
+    dim3 grid(level_count, n_images);
+    octree_kernel<<<grid, kOctThreads, smem, st>>>(G_dev, cap, raw, G.raw_total, raw_count, node_of, sel_xys, sel_count, status, level_lo);
     return cudaSuccess;
 }
 

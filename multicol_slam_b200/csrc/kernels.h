@@ -18,7 +18,7 @@ void launch_pyr_fast(const PyramidGeom& G, int level, int n_images, const uint8_
                      const int* cam_of_image, const uint8_t* tile_flags, uint32_t* raw, int* raw_count, cudaStream_t st);
 cudaError_t launch_octree(const PyramidGeom& G, const PyramidGeom* G_dev, int n_images, const uint32_t* raw,
                           const int* raw_count, uint16_t* node_of, uint32_t* sel_xys, int* sel_count, int* status,
-                          cudaStream_t st);
+                          cudaStream_t st, int level_lo = 0, int level_count = -1);
 // per-camera table of R(r) = rho(atan(-z/r)) (describe_kernel.cu): entry i is one degree-9 polynomial in
 // tau = r * e[1] + e[0] valid on [max(0, i - 22.5), i + 22.5] -- every pattern point of a keypoint whose undistorted
 // radius rounds to i; 12 doubles per entry (tau offset, tau scale, 10 coefficients)
@@ -69,6 +69,9 @@ inline unsigned greedy_dist_bound(int th_low, double nnratio) {
 cudaError_t launch_stream_replay(const int* list_idx, const int* list_dist, const int* counts, const uint8_t* desc, const uint8_t* dmask,
                                  int dim, int img_lo, int n_images, int n_cams, int capacity, int K, int th_low, double nnratio,
                                  int* matches12, int* nmatches, int* redo, cudaStream_t st);
+cudaError_t launch_bruteforce_replay(const int* list_idx, const int* list_dist, int K, const uint8_t* q, const uint8_t* qm, const uint8_t* valid1,
+                                     const int* seg, int n_seg, const uint8_t* d, const uint8_t* dm, const uint8_t* valid2, int nd, int dim,
+                                     int th_low, double nnratio, int* matches12, int* nmatches, cudaStream_t st);
 void launch_repitch(const uint8_t* src, int src_stride, uint8_t* dst, int dst_pitch, int width, size_t rows, cudaStream_t st);
 struct WindowFrameDev {
     int n_cams, n_keys, dim;

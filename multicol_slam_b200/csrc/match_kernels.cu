@@ -320,32 +320,35 @@ cudaError_t launch_hamming_stream(const uint8_t* desc, const uint8_t* dmask, con
 //   none is: rejected if dK >= th_low.
 // Otherwise the warp rescans the whole previous image for this one query (exact best / second among the unmatched entries), so
 // the result never depends on K; redo[] stays 0 and is kept for interface stability.
-constexpr int kReplayThreads = 256;
+constexpr int kReplayThreads = 256;          // stream matcher: <= 65535 database entries per image, many images in flight
+constexpr int kBfReplayThreads = 1024;       // key-frame database: one CTA per query set scans up to ~1.5 M entries per rescan
+constexpr int kKeyShift = 21;                // rescan keys = distance << 21 | index (index < 2^21, distance <= 512)
 
-__device__ __forceinline__ void named_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kReplayThreads) : "memory"); }
+template <int THREADS>
+__device__ __forceinline__ void named_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(THREADS) : "memory"); }
 
-// two smallest (distance << 16 | index) keys among this thread's share of the unmatched entries of the previous image
-template <int WORDS, bool MASKED>
-__device__ __forceinline__ void replay_scan(const uint32_t* __restrict__ desc, const uint32_t* __restrict__ dmask, const size_t q_row,
-                                            const size_t d_row0, const int nd, const unsigned* s_taken, const int tid,
-                                            unsigned& k1, unsigned& k2) {
+// two smallest (distance << kKeyShift | index) keys among this thread's share of the unmatched database entries
+template <int WORDS, bool MASKED, int THREADS>
+__device__ __forceinline__ void replay_scan(const uint32_t* __restrict__ qrow, const uint32_t* __restrict__ qmrow,
+                                            const uint32_t* __restrict__ dd, const uint32_t* __restrict__ dm, const int nd,
+                                            const unsigned* s_taken, const int tid, unsigned& k1, unsigned& k2) {
     uint4 qw[WORDS / 4], qm[MASKED ? WORDS / 4 : 1];
-    const uint4* qp = reinterpret_cast<const uint4*>(desc + q_row * WORDS);
+    const uint4* qp = reinterpret_cast<const uint4*>(qrow);
 #pragma unroll
     for (int k = 0; k < WORDS / 4; ++k) qw[k] = qp[k];
     if (MASKED) {
-        const uint4* qmp = reinterpret_cast<const uint4*>(dmask + q_row * WORDS);
+        const uint4* qmp = reinterpret_cast<const uint4*>(qmrow);
 #pragma unroll
         for (int k = 0; k < WORDS / 4; ++k) qm[k] = qmp[k];
     }
     k1 = 0xFFFFFFFFu; k2 = 0xFFFFFFFFu;
 #pragma unroll 2
-    for (int id = tid; id < nd; id += kReplayThreads) {
+    for (int id = tid; id < nd; id += THREADS) {
         if (s_taken[id >> 5] >> (id & 31) & 1u) continue;
-        const uint4* dp = reinterpret_cast<const uint4*>(desc + (d_row0 + id) * WORDS);
+        const uint4* dp = reinterpret_cast<const uint4*>(dd + (size_t)id * WORDS);
         unsigned dist = 0;
         if (MASKED) {
-            const uint4* mp = reinterpret_cast<const uint4*>(dmask + (d_row0 + id) * WORDS);
+            const uint4* mp = reinterpret_cast<const uint4*>(dm + (size_t)id * WORDS);
 #pragma unroll
             for (int k = 0; k < WORDS / 4; ++k) {
                 const uint4 d = dp[k], m = mp[k];
@@ -361,7 +364,7 @@ __device__ __forceinline__ void replay_scan(const uint32_t* __restrict__ desc, c
                 dist += __popc(qw[k].x ^ d.x) + __popc(qw[k].y ^ d.y) + __popc(qw[k].z ^ d.z) + __popc(qw[k].w ^ d.w);
             }
         }
-        const unsigned key = (dist << 16) | (unsigned)id;
+        const unsigned key = (dist << kKeyShift) | (unsigned)id;
         if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
     }
     // warp: smallest and second smallest of the 64 keys (keys are unique: the index is part of the key)
@@ -370,55 +373,46 @@ __device__ __forceinline__ void replay_scan(const uint32_t* __restrict__ desc, c
     k1 = B; k2 = S;
 }
 
-// One CTA per image.  Warp 0 walks the queries in order (lane 0 decides from the list); the other warps sleep on a named barrier
-// and wake only for a rescan, where all 256 threads split the previous image.
-template <int WORDS, bool MASKED>
-__global__ void __launch_bounds__(kReplayThreads)
-stream_replay_kernel(const int* __restrict__ list_idx, const int* __restrict__ list_dist, const int* __restrict__ counts,
-                     const uint32_t* __restrict__ desc, const uint32_t* __restrict__ dmask,
-                     const int n_cams, const int capacity, const int K, const int img_lo, const int th_low, const double nnratio,
-                     int* __restrict__ matches12, int* __restrict__ nmatches, int* __restrict__ redo) {
-    extern __shared__ int s_mem[];
-    int* s_li = s_mem;                              // [32][K]
-    int* s_ld = s_mem + 32 * K;                     // [32][K]
-    unsigned* s_taken = (unsigned*)(s_mem + 64 * K);   // [(capacity + 31) / 32]
-    __shared__ int s_cmd;
-    __shared__ unsigned s_k1[kReplayThreads / 32], s_k2[kReplayThreads / 32];
-    const int img = blockIdx.x + img_lo, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool has_prev = img >= n_cams;
-    const int nq = has_prev ? min(counts[img], capacity) : 0;
-    const int nd = has_prev ? min(counts[img - n_cams], capacity) : 0;
-    const size_t d_row0 = has_prev ? (size_t)(img - n_cams) * capacity : 0;
-    for (int i = tid; i < (capacity + 31) / 32; i += kReplayThreads) s_taken[i] = 0u;
-    for (int i = tid; i < capacity; i += kReplayThreads) matches12[(size_t)img * capacity + i] = -1;
-    __syncthreads();
+struct ReplayShared { int cmd; unsigned k1[32], k2[32]; };
+
+// The ordered walk over one query set (queries 0..nq-1 of the given rows, lists [nq][K]) against one database of nd entries whose
+// "already matched" bits live in s_taken.  Warp 0 walks the queries in order (lane 0 decides from the list); the other warps
+// sleep on a named barrier and wake only for a rescan, where all THREADS threads split the database.  Every thread of the CTA
+// must call this; returns the number of matches in warp 0 (other warps: 0).
+template <int WORDS, bool MASKED, int THREADS>
+__device__ __forceinline__ int replay_core(const int* __restrict__ list_idx, const int* __restrict__ list_dist, const int K, const int nq,
+                                           const uint8_t* __restrict__ valid1, const uint32_t* __restrict__ qd,
+                                           const uint32_t* __restrict__ qmk, const uint32_t* __restrict__ dd,
+                                           const uint32_t* __restrict__ dmk, const int nd, const int th_low, const double nnratio,
+                                           int* __restrict__ matches12, int* s_li, int* s_ld, unsigned* s_taken, ReplayShared* sh) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (warp != 0) {
         for (;;) {
-            named_bar(1);
-            const int cmd = *(volatile int*)&s_cmd;
-            if (cmd < 0) return;
+            named_bar<THREADS>(1);
+            const int cmd = *(volatile int*)&sh->cmd;
+            if (cmd < 0) return 0;
             unsigned k1, k2;
-            replay_scan<WORDS, MASKED>(desc, dmask, (size_t)img * capacity + cmd, d_row0, nd, s_taken, tid, k1, k2);
-            if (lane == 0) { s_k1[warp] = k1; s_k2[warp] = k2; }
-            named_bar(2);
+            replay_scan<WORDS, MASKED, THREADS>(qd + (size_t)cmd * WORDS, MASKED ? qmk + (size_t)cmd * WORDS : nullptr, dd, dmk, nd, s_taken, tid, k1, k2);
+            if (lane == 0) { sh->k1[warp] = k1; sh->k2[warp] = k2; }
+            named_bar<THREADS>(2);
         }
     }
     int nm = 0;
     for (int q0 = 0; q0 < nq; q0 += 32) {
         const int nchunk = min(32, nq - q0);
         for (int i = lane; i < nchunk * K; i += 32) {
-            s_li[i] = list_idx[((size_t)img * capacity + q0) * K + i];
-            s_ld[i] = list_dist[((size_t)img * capacity + q0) * K + i];
+            s_li[i] = list_idx[(size_t)q0 * K + i];
+            s_ld[i] = list_dist[(size_t)q0 * K + i];
         }
         __syncwarp();
         for (int t = 0; t < nchunk; ++t) {
             int code = 0, bestIdx = -1;              // 0 no match, 1 match bestIdx, 2 undecided from the list
-            if (lane == 0) {
+            if (lane == 0 && !(valid1 && !valid1[q0 + t])) {
                 int best1 = 0x7FFFFFFF, best2 = 0x7FFFFFFF, found = 0, dK = 0x7FFFFFFF;
                 bool complete = false;
                 for (int k = 0; k < K; ++k) {
                     const int id = s_li[t * K + k];
-                    if (id < 0) { complete = true; break; }          // the list holds every database entry there is
+                    if (id < 0) { complete = true; break; }          // the list holds every database entry that matters
                     dK = s_ld[t * K + k];
                     if (s_taken[id >> 5] >> (id & 31) & 1u) continue;
                     if (found == 0) { best1 = s_ld[t * K + k]; bestIdx = id; }
@@ -432,24 +426,24 @@ stream_replay_kernel(const int* __restrict__ list_idx, const int* __restrict__ l
             code = __shfl_sync(0xffffffffu, code, 0);
             bestIdx = __shfl_sync(0xffffffffu, bestIdx, 0);
             if (code == 2) {
-                // exact rescan of the previous image for this query: two smallest (distance, index) keys among the unmatched entries
-                if (lane == 0) s_cmd = q0 + t;
-                named_bar(1);
+                // exact rescan of the database for this query: two smallest (distance, index) keys among the unmatched entries
+                if (lane == 0) sh->cmd = q0 + t;
+                named_bar<THREADS>(1);
                 unsigned k1, k2;
-                replay_scan<WORDS, MASKED>(desc, dmask, (size_t)img * capacity + q0 + t, d_row0, nd, s_taken, tid, k1, k2);
-                if (lane == 0) { s_k1[0] = k1; s_k2[0] = k2; }
-                named_bar(2);
-                k1 = lane < kReplayThreads / 32 ? s_k1[lane] : 0xFFFFFFFFu;
-                k2 = lane < kReplayThreads / 32 ? s_k2[lane] : 0xFFFFFFFFu;
+                replay_scan<WORDS, MASKED, THREADS>(qd + (size_t)(q0 + t) * WORDS, MASKED ? qmk + (size_t)(q0 + t) * WORDS : nullptr, dd, dmk, nd, s_taken, tid, k1, k2);
+                if (lane == 0) { sh->k1[0] = k1; sh->k2[0] = k2; }
+                named_bar<THREADS>(2);
+                k1 = lane < THREADS / 32 ? sh->k1[lane] : 0xFFFFFFFFu;
+                k2 = lane < THREADS / 32 ? sh->k2[lane] : 0xFFFFFFFFu;
                 const unsigned B = __reduce_min_sync(0xffffffffu, k1);
                 const unsigned S = __reduce_min_sync(0xffffffffu, k1 == B ? k2 : k1);
-                const int best1 = B == 0xFFFFFFFFu ? 0x7FFFFFFF : (int)(B >> 16), best2 = S == 0xFFFFFFFFu ? 0x7FFFFFFF : (int)(S >> 16);
-                bestIdx = (int)(B & 0xFFFFu);
+                const int best1 = B == 0xFFFFFFFFu ? 0x7FFFFFFF : (int)(B >> kKeyShift), best2 = S == 0xFFFFFFFFu ? 0x7FFFFFFF : (int)(S >> kKeyShift);
+                bestIdx = (int)(B & ((1u << kKeyShift) - 1u));
                 code = (best1 < th_low && (double)best1 < nnratio * (double)best2) ? 1 : 0;
             }
             if (code == 1) {
                 if (lane == 0) {
-                    matches12[(size_t)img * capacity + q0 + t] = bestIdx;
+                    matches12[q0 + t] = bestIdx;
                     s_taken[bestIdx >> 5] |= 1u << (bestIdx & 31);
                 }
                 ++nm;
@@ -457,8 +451,36 @@ stream_replay_kernel(const int* __restrict__ list_idx, const int* __restrict__ l
             __syncwarp();
         }
     }
-    if (lane == 0) { s_cmd = -1; nmatches[img] = nm; redo[img] = 0; }
-    named_bar(1);
+    if (lane == 0) sh->cmd = -1;
+    named_bar<THREADS>(1);
+    return nm;
+}
+
+// Stream matcher: one CTA per image; queries = the image's slots, database = the same camera's image one frame earlier.
+template <int WORDS, bool MASKED>
+__global__ void __launch_bounds__(kReplayThreads)
+stream_replay_kernel(const int* __restrict__ list_idx, const int* __restrict__ list_dist, const int* __restrict__ counts,
+                     const uint32_t* __restrict__ desc, const uint32_t* __restrict__ dmask,
+                     const int n_cams, const int capacity, const int K, const int img_lo, const int th_low, const double nnratio,
+                     int* __restrict__ matches12, int* __restrict__ nmatches, int* __restrict__ redo) {
+    extern __shared__ int s_mem[];
+    int* s_li = s_mem;                              // [32][K]
+    int* s_ld = s_mem + 32 * K;                     // [32][K]
+    unsigned* s_taken = (unsigned*)(s_mem + 64 * K);   // [(capacity + 31) / 32]
+    __shared__ ReplayShared sh;
+    const int img = blockIdx.x + img_lo, tid = threadIdx.x;
+    const bool has_prev = img >= n_cams;
+    const int nq = has_prev ? min(counts[img], capacity) : 0;
+    const int nd = has_prev ? min(counts[img - n_cams], capacity) : 0;
+    const size_t q_row0 = (size_t)img * capacity, d_row0 = has_prev ? (size_t)(img - n_cams) * capacity : 0;
+    for (int i = tid; i < (capacity + 31) / 32; i += kReplayThreads) s_taken[i] = 0u;
+    for (int i = tid; i < capacity; i += kReplayThreads) matches12[q_row0 + i] = -1;
+    __syncthreads();
+    const int nm = replay_core<WORDS, MASKED, kReplayThreads>(list_idx + q_row0 * K, list_dist + q_row0 * K, K, nq, nullptr, desc + q_row0 * WORDS,
+                                                              MASKED ? dmask + q_row0 * WORDS : nullptr, desc + d_row0 * WORDS,
+                                                              MASKED ? dmask + d_row0 * WORDS : nullptr, nd, th_low, nnratio,
+                                                              matches12 + q_row0, s_li, s_ld, s_taken, &sh);
+    if (tid == 0) { nmatches[img] = nm; redo[img] = 0; }
 }
 
 cudaError_t launch_stream_replay(const int* list_idx, const int* list_dist, const int* counts, const uint8_t* desc, const uint8_t* dmask,
@@ -474,6 +496,55 @@ cudaError_t launch_stream_replay(const int* list_idx, const int* list_dist, cons
     else if (dim == 32) { if (masked) MCS_SR(8, true); else MCS_SR(8, false); }
     else { if (masked) MCS_SR(16, true); else MCS_SR(16, false); }
 #undef MCS_SR
+    return cudaGetLastError();
+}
+
+// Key-frame database: one CTA per query set (seg[s] .. seg[s+1]) against the same nd database entries, each set with its own
+// "already matched" bits (initialised from valid2), as separate SearchByBoW(KF1, KF2) calls of the reference would have.
+template <int WORDS, bool MASKED>
+__global__ void __launch_bounds__(kBfReplayThreads)
+bruteforce_replay_kernel(const int* __restrict__ list_idx, const int* __restrict__ list_dist, const int K,
+                         const uint32_t* __restrict__ q, const uint32_t* __restrict__ qm, const uint8_t* __restrict__ valid1,
+                         const int* __restrict__ seg, const uint32_t* __restrict__ d, const uint32_t* __restrict__ dm,
+                         const uint8_t* __restrict__ valid2, const int nd, const int th_low, const double nnratio,
+                         int* __restrict__ matches12, int* __restrict__ nmatches) {
+    extern __shared__ int s_mem[];
+    int* s_li = s_mem;
+    int* s_ld = s_mem + 32 * K;
+    unsigned* s_taken = (unsigned*)(s_mem + 64 * K);   // [(nd + 31) / 32]
+    __shared__ ReplayShared sh;
+    const int s = blockIdx.x, tid = threadIdx.x;
+    const int q0 = seg[s], nq = seg[s + 1] - q0;
+    for (int w = tid; w < (nd + 31) / 32; w += kBfReplayThreads) {
+        unsigned bits = 0u;
+        if (valid2)
+            for (int k = 0; k < 32 && w * 32 + k < nd; ++k) bits |= (valid2[w * 32 + k] ? 0u : 1u) << k;
+        s_taken[w] = bits;
+    }
+    for (int i = tid; i < nq; i += kBfReplayThreads) matches12[q0 + i] = -1;
+    __syncthreads();
+    const int nm = replay_core<WORDS, MASKED, kBfReplayThreads>(list_idx + (size_t)q0 * K, list_dist + (size_t)q0 * K, K, nq, valid1 ? valid1 + q0 : nullptr,
+                                                                q + (size_t)q0 * WORDS, MASKED ? qm + (size_t)q0 * WORDS : nullptr, d, dm, nd, th_low,
+                                                                nnratio, matches12 + q0, s_li, s_ld, s_taken, &sh);
+    if (tid == 0) nmatches[s] = nm;
+}
+
+cudaError_t launch_bruteforce_replay(const int* list_idx, const int* list_dist, int K, const uint8_t* q, const uint8_t* qm, const uint8_t* valid1,
+                                     const int* seg, int n_seg, const uint8_t* d, const uint8_t* dm, const uint8_t* valid2, int nd, int dim,
+                                     int th_low, double nnratio, int* matches12, int* nmatches, cudaStream_t st) {
+    if (n_seg < 1) return cudaSuccess;
+    if (nd >= (1 << kKeyShift) || (dim != 16 && dim != 32 && dim != 64)) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)64 * K * 4 + (size_t)((nd + 31) / 32) * 4;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    const bool masked = qm && dm;
+#define MCS_BR(W, M) { if (smem > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(bruteforce_replay_kernel<W, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+                                               if (e != cudaSuccess) return e; } \
+        bruteforce_replay_kernel<W, M><<<n_seg, kBfReplayThreads, smem, st>>>(list_idx, list_dist, K, (const uint32_t*)q, (const uint32_t*)qm, valid1, seg, \
+            (const uint32_t*)d, (const uint32_t*)dm, valid2, nd, th_low, nnratio, matches12, nmatches); }
+    if (dim == 16) { if (masked) MCS_BR(4, true) else MCS_BR(4, false) }
+    else if (dim == 32) { if (masked) MCS_BR(8, true) else MCS_BR(8, false) }
+    else { if (masked) MCS_BR(16, true) else MCS_BR(16, false) }
+#undef MCS_BR
     return cudaGetLastError();
 }
 

@@ -177,72 +177,43 @@ int mcs_last_bruteforce_rounds(void) { return g_bf_rounds; }
 
 // seg[0..n_seg]: query segments (e.g. the key frames of a batch) whose "database entry already matched" state is independent, as
 // it is between separate SearchByBoW(KF1, KF2) calls of the reference; seg == nullptr: one segment [0, nq).  One K-best launch
-// serves all queries of all segments (they start from the same database state).  The host then replays every segment in query
-// order; a query whose list was used up by matches accepted earlier in its segment gets a fresh list of its own (one-query
-// launch against the current state, kTopKMax entries), which always decides it -- the other queries keep their first lists.
+// serves all queries of all segments (they start from the same database state); the ordered acceptance (ref :899-961) then runs
+// on the device as well, one CTA per segment (bruteforce_replay_kernel): a query whose list was used up by matches accepted
+// earlier in its segment is rescanned exactly inside the kernel.  The host only moves the small validity / offset arrays in and
+// the matches out.
 static int bruteforce_core(const uint8_t* q_dev, const uint8_t* qm_dev, const uint8_t* valid1, int nq, const uint8_t* d_dev,
                            const uint8_t* dm_dev, const uint8_t* valid2, int nd, int dim, int th_low, double nnratio, int* matches12,
                            int* nmatches, cudaStream_t st, const int* seg = nullptr, int n_seg = 1) {
     const bool masked = qm_dev && dm_dev;
     // K = 8: with the relevance bound only entries that matter are ever inserted, so long lists cost nothing in the distance loop
-    // and leave few queries undecided (BASELINE config 4: 207 of 4000 per key frame at K = 4)
-    constexpr int K = 8, K1 = 8;
+    // and leave few queries to rescan (BASELINE config 4: 207 of 4000 per key frame at K = 4, 60 at K = 8)
+    constexpr int K = 8;
     const int one_seg[2] = {0, nq};
     if (!seg) { seg = one_seg; n_seg = 1; }
-    Dev ds, di, dt, di1, dt1;
+    if (nd >= (1 << 21)) return mfail(MCS_ERR_UNSUPPORTED, "more than 2^21 database descriptors in one call");
+    Dev ds, di, dt, dv1, dseg, dm12, dnm;
     MCK(ds.alloc(nd)); MCK(di.alloc((size_t)nq * K * 4)); MCK(dt.alloc((size_t)nq * K * 4));
-    MCK(di1.alloc(K1 * 4)); MCK(dt1.alloc(K1 * 4));
-    std::vector<uint8_t> base_skip(nd, 0), skip;
-    if (valid2) for (int i = 0; i < nd; ++i) base_skip[i] = valid2[i] ? 0 : 1;
-    std::vector<int> tidx((size_t)nq * K), tdist((size_t)nq * K);
-    int one_idx[K1], one_dist[K1];
+    MCK(dv1.alloc(nq)); MCK(dseg.alloc((size_t)(n_seg + 1) * 4)); MCK(dm12.alloc((size_t)nq * 4)); MCK(dnm.alloc((size_t)n_seg * 4));
+    std::vector<uint8_t> skip(nd, 0);
+    if (valid2) for (int i = 0; i < nd; ++i) skip[i] = valid2[i] ? 0 : 1;
+    g_bf_rounds = 1;
+    MCK(cudaMemcpyAsync(ds.p, skip.data(), nd, cudaMemcpyHostToDevice, st));
+    if (valid1) MCK(cudaMemcpyAsync(dv1.p, valid1, nq, cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(dseg.p, seg, (size_t)(n_seg + 1) * 4, cudaMemcpyHostToDevice, st));
     // Entries at or beyond the relevance bound of (th_low, nnratio) stay out of the lists: a list shorter than K then means "every
     // entry that can influence the decision is here".
-    const unsigned bound = greedy_dist_bound(th_low, nnratio);
-    g_bf_rounds = 1;
-    MCK(cudaMemcpyAsync(ds.p, base_skip.data(), nd, cudaMemcpyHostToDevice, st));
-    MCK(launch_hamming_topk(q_dev, masked ? qm_dev : nullptr, nq, d_dev, masked ? dm_dev : nullptr, nd, ds.as<uint8_t>(), dim, K, bound,
-                            di.as<int>(), dt.as<int>(), st));
-    MCK(cudaMemcpyAsync(tidx.data(), di.p, (size_t)nq * K * 4, cudaMemcpyDeviceToHost, st));
-    MCK(cudaMemcpyAsync(tdist.data(), dt.p, (size_t)nq * K * 4, cudaMemcpyDeviceToHost, st));
+    MCK(launch_hamming_topk(q_dev, masked ? qm_dev : nullptr, nq, d_dev, masked ? dm_dev : nullptr, nd, ds.as<uint8_t>(), dim, K,
+                            greedy_dist_bound(th_low, nnratio), di.as<int>(), dt.as<int>(), st));
+    // the replay kernel wants "valid" bytes for the database (1 = usable): reuse the skip buffer inverted on the fly is not worth a
+    // kernel -- upload the caller's array when there is one
+    Dev dv2;
+    if (valid2) { MCK(dv2.alloc(nd)); MCK(cudaMemcpyAsync(dv2.p, valid2, nd, cudaMemcpyHostToDevice, st)); }
+    MCK(launch_bruteforce_replay(di.as<int>(), dt.as<int>(), K, q_dev, masked ? qm_dev : nullptr, valid1 ? dv1.as<uint8_t>() : nullptr,
+                                 dseg.as<int>(), n_seg, d_dev, masked ? dm_dev : nullptr, valid2 ? dv2.as<uint8_t>() : nullptr, nd, dim, th_low,
+                                 nnratio, dm12.as<int>(), dnm.as<int>(), st));
+    MCK(cudaMemcpyAsync(matches12, dm12.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    MCK(cudaMemcpyAsync(nmatches, dnm.p, (size_t)n_seg * 4, cudaMemcpyDeviceToHost, st));
     MCK(cudaStreamSynchronize(st));
-    // best / second best among the list entries not taken so far (ref :899-961); false = the list cannot tell
-    auto from_list = [&](const int* li, const int* ld, int k_len, int& best1, int& best2, int& bestIdx) -> bool {
-        best1 = INT_MAX; best2 = INT_MAX; bestIdx = -1;
-        int found = 0;
-        for (int k = 0; k < k_len; ++k) {
-            if (li[k] < 0) return true;                    // the list holds every unmatched entry that matters
-            if (skip[li[k]]) continue;                     // matched by an earlier query of this segment
-            if (found == 0) { best1 = ld[k]; bestIdx = li[k]; }
-            else best2 = ld[k];
-            if (++found == 2) return true;
-        }
-        return found == 1 && !(best1 < th_low);            // second best unknown: irrelevant only if the best already fails
-    };
-    for (int s = 0; s < n_seg; ++s) {
-        skip = base_skip;
-        int nm = 0;
-        for (int i = seg[s]; i < seg[s + 1]; ++i) {
-            if (valid1 && !valid1[i]) continue;
-            int best1, best2, bestIdx;
-            if (!from_list(&tidx[(size_t)i * K], &tdist[(size_t)i * K], K, best1, best2, bestIdx)) {
-                ++g_bf_rounds;
-                MCK(cudaMemcpyAsync(ds.p, skip.data(), nd, cudaMemcpyHostToDevice, st));
-                MCK(launch_hamming_topk(q_dev + (size_t)i * dim, masked ? qm_dev + (size_t)i * dim : nullptr, 1, d_dev, masked ? dm_dev : nullptr,
-                                        nd, ds.as<uint8_t>(), dim, K1, bound, di1.as<int>(), dt1.as<int>(), st));
-                MCK(cudaMemcpyAsync(one_idx, di1.p, K1 * 4, cudaMemcpyDeviceToHost, st));
-                MCK(cudaMemcpyAsync(one_dist, dt1.p, K1 * 4, cudaMemcpyDeviceToHost, st));
-                MCK(cudaStreamSynchronize(st));
-                if (!from_list(one_idx, one_dist, K1, best1, best2, bestIdx)) return mfail(MCS_ERR_INVALID, "internal: fresh list undecided");
-            }
-            if (best1 < th_low && (double)best1 < nnratio * (double)best2) {
-                matches12[i] = bestIdx;
-                skip[bestIdx] = 1;
-                ++nm;
-            }
-        }
-        nmatches[s] = nm;
-    }
     return MCS_OK;
 }
 
