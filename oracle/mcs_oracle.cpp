@@ -6,16 +6,19 @@
  * Nothing under multicol_slam_b200/ may call into this file.
  *
  * Each function cites the reference file:line it restates (paths relative to /root/reference).
- * The image arithmetic of the reference lives in OpenCV (un-vendored, version unpinned by the
- * reference: README.md:141-142).  Those primitives are restated here from their published
- * algorithm and PINNED against cv2 4.13.0 by oracle/pin_cv2.py (fixtures in tests/golden/).
- * The reference itself ships no tests and cannot be compiled here (no OpenCV C++), so the
- * reference-specific logic (cell grid, octree, descriptor, matchers) is pinned only through the
- * independent Python restatements in oracle/pyref.py (extractor, real cv2 primitives) and
- * oracle/pyref_match.py (matchers): "parity pinned to cv2 4.13 primitives + an independent second
- * restatement; unpinned by reference-run outputs".  Exception: the bag-of-words functions at the end
- * of this file ARE pinned by reference-run outputs -- the reference's vendored DBoW2 compiles from its
- * own sources (oracle/Makefile target `ref`, oracle/_ref/libdbow2_ref.so) and agrees bit for bit.
+ * PINNED BY REFERENCE-RUN OUTPUTS.  The reference's own sources -- src/mdBRIEFextractorOct.cpp, src/cORBmatcher.cpp,
+ * src/cam_model_omni.cpp, src/cam_system_omni.cpp, src/misc.cpp, src/cConverter.cpp and the vendored DBoW2 -- are compiled where
+ * they lie (oracle/Makefile target `ref` -> oracle/_ref/libmcs_ref.so, libdbow2_ref.so) against a stand-in OpenCV header
+ * (oracle/ref_mcs/stub: cv::Mat + the six image primitives the extractor calls, themselves pinned bit for bit against cv2 4.13.0
+ * by oracle/pin_cv2.py / pin_ref.py) and data-only stand-ins of the three SLAM container classes the matcher reads
+ * (oracle/ref_mcs/stub_slam.h).  Every function of this file is checked against that library:
+ *   extractor (all stages, ORB / dBRIEF / mdBRIEF, 19 configurations)  tests/test_ref_pin_cpu.py, tests/golden/ref_extract_*.npz
+ *   every cORBmatcher entry point of the path                         tests/test_ref_match_cpu.py
+ *   bag of words                                                       tests/test_bow_cpu.py
+ * and the GPU path against the same outputs (tests/test_ref_pin_gpu.py, tests/test_ref_match_gpu.py, tests/golden/).
+ * One tie-break of the reference depends on heap addresses (sort of pair<int, ExtractorNode*>, src/mdBRIEFextractorOct.cpp:782);
+ * the reference library is run under a monotonic allocator so that "larger address" = "created later", which is the order
+ * this file (and the GPU kernel) implement by a creation counter.
  *
  * Build: g++ -O2 -std=c++17 -ffp-contract=off -fPIC -shared (oracle/Makefile).
  * -ffp-contract=off: double expressions are evaluated without FMA contraction (ISO semantics).
