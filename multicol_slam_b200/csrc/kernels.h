@@ -70,7 +70,7 @@ cudaError_t launch_stream_replay(const int* list_idx, const int* list_dist, cons
                                  int dim, int img_lo, int n_images, int n_cams, int capacity, int K, int th_low, double nnratio,
                                  int* matches12, int* nmatches, int* redo, cudaStream_t st);
 cudaError_t launch_bruteforce_replay(const int* list_idx, const int* list_dist, int K, const uint8_t* q, const uint8_t* qm, const uint8_t* valid1,
-                                     const int* seg, int n_seg, const uint8_t* d, const uint8_t* dm, const uint8_t* valid2, int nd, int dim,
+                                     const int* seg, int n_seg, int nq_total, const uint8_t* d, const uint8_t* dm, const uint8_t* valid2, int nd, int dim,
                                      int th_low, double nnratio, int* matches12, int* nmatches, cudaStream_t st);
 void launch_repitch(const uint8_t* src, int src_stride, uint8_t* dst, int dst_pitch, int width, size_t rows, cudaStream_t st);
 struct WindowFrameDev {

@@ -330,8 +330,9 @@ __device__ __forceinline__ void named_bar(int id) { asm volatile("bar.sync %0, %
 // two smallest (distance << kKeyShift | index) keys among this thread's share of the unmatched database entries
 template <int WORDS, bool MASKED, int THREADS>
 __device__ __forceinline__ void replay_scan(const uint32_t* __restrict__ qrow, const uint32_t* __restrict__ qmrow,
-                                            const uint32_t* __restrict__ dd, const uint32_t* __restrict__ dm, const int nd,
-                                            const unsigned* s_taken, const int tid, unsigned& k1, unsigned& k2) {
+                                            const uint32_t* __restrict__ dd, const uint32_t* __restrict__ dm, const int id_lo,
+                                            const int id_hi, const unsigned* s_taken /* bit (id - id_lo) */, const int tid,
+                                            unsigned& k1, unsigned& k2) {
     uint4 qw[WORDS / 4], qm[MASKED ? WORDS / 4 : 1];
     const uint4* qp = reinterpret_cast<const uint4*>(qrow);
 #pragma unroll
@@ -343,8 +344,8 @@ __device__ __forceinline__ void replay_scan(const uint32_t* __restrict__ qrow, c
     }
     k1 = 0xFFFFFFFFu; k2 = 0xFFFFFFFFu;
 #pragma unroll 2
-    for (int id = tid; id < nd; id += THREADS) {
-        if (s_taken[id >> 5] >> (id & 31) & 1u) continue;
+    for (int id = id_lo + tid; id < id_hi; id += THREADS) {
+        if (s_taken[(id - id_lo) >> 5] >> ((id - id_lo) & 31) & 1u) continue;
         const uint4* dp = reinterpret_cast<const uint4*>(dd + (size_t)id * WORDS);
         unsigned dist = 0;
         if (MASKED) {
@@ -375,6 +376,20 @@ __device__ __forceinline__ void replay_scan(const uint32_t* __restrict__ qrow, c
 
 struct ReplayShared { int cmd; unsigned k1[32], k2[32]; };
 
+// Several CTAs per query set (key-frame database): the leader CTA walks the queries; for a rescan it publishes the query in global
+// memory, every helper CTA scans its own shard of the database and delivers the two smallest keys, the leader scans shard 0
+// meanwhile and folds the partials.  Helpers learn which entries were matched since the last rescan from a log the leader appends
+// to.  All CTAs must be co-resident (cooperative launch): helpers spin on cmd_seq.
+constexpr int kCoopMax = 16;                 // helpers per query set
+struct CoopSeg {                             // one per query set, zeroed by the host before the launch
+    int cmd_seq;                             // rescans published so far; -1 = the walk is over
+    int cmd_query;                           // query (row relative to the set) of the latest rescan
+    int log_len;                             // entries of the set's log valid for the latest rescan
+    int done;                                // helper deliveries, cumulative
+    unsigned partial[2 * kCoopMax];
+};
+struct CoopLeader { CoopSeg* seg; int* log; int helpers; int shard_hi; };   // helpers == 0: plain single-CTA walk
+
 // The ordered walk over one query set (queries 0..nq-1 of the given rows, lists [nq][K]) against one database of nd entries whose
 // "already matched" bits live in s_taken.  Warp 0 walks the queries in order (lane 0 decides from the list); the other warps
 // sleep on a named barrier and wake only for a rescan, where all THREADS threads split the database.  Every thread of the CTA
@@ -384,15 +399,18 @@ __device__ __forceinline__ int replay_core(const int* __restrict__ list_idx, con
                                            const uint8_t* __restrict__ valid1, const uint32_t* __restrict__ qd,
                                            const uint32_t* __restrict__ qmk, const uint32_t* __restrict__ dd,
                                            const uint32_t* __restrict__ dmk, const int nd, const int th_low, const double nnratio,
-                                           int* __restrict__ matches12, int* s_li, int* s_ld, unsigned* s_taken, ReplayShared* sh) {
+                                           int* __restrict__ matches12, int* s_li, int* s_ld, unsigned* s_taken, ReplayShared* sh,
+                                           const CoopLeader coop = CoopLeader{nullptr, nullptr, 0, 0}) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int scan_hi = coop.helpers ? coop.shard_hi : nd;          // this CTA's share of a rescan
+    int nlog = 0, seq = 0;
     if (warp != 0) {
         for (;;) {
             named_bar<THREADS>(1);
             const int cmd = *(volatile int*)&sh->cmd;
             if (cmd < 0) return 0;
             unsigned k1, k2;
-            replay_scan<WORDS, MASKED, THREADS>(qd + (size_t)cmd * WORDS, MASKED ? qmk + (size_t)cmd * WORDS : nullptr, dd, dmk, nd, s_taken, tid, k1, k2);
+            replay_scan<WORDS, MASKED, THREADS>(qd + (size_t)cmd * WORDS, MASKED ? qmk + (size_t)cmd * WORDS : nullptr, dd, dmk, 0, scan_hi, s_taken, tid, k1, k2);
             if (lane == 0) { sh->k1[warp] = k1; sh->k2[warp] = k2; }
             named_bar<THREADS>(2);
         }
@@ -427,16 +445,35 @@ __device__ __forceinline__ int replay_core(const int* __restrict__ list_idx, con
             bestIdx = __shfl_sync(0xffffffffu, bestIdx, 0);
             if (code == 2) {
                 // exact rescan of the database for this query: two smallest (distance, index) keys among the unmatched entries
-                if (lane == 0) sh->cmd = q0 + t;
+                if (lane == 0) {
+                    sh->cmd = q0 + t;
+                    if (coop.helpers) {                     // publish the rescan to the helper CTAs before scanning shard 0 here
+                        coop.seg->cmd_query = q0 + t;
+                        coop.seg->log_len = nlog;
+                        __threadfence();
+                        atomicExch(&coop.seg->cmd_seq, ++seq);
+                    }
+                }
                 named_bar<THREADS>(1);
                 unsigned k1, k2;
-                replay_scan<WORDS, MASKED, THREADS>(qd + (size_t)(q0 + t) * WORDS, MASKED ? qmk + (size_t)(q0 + t) * WORDS : nullptr, dd, dmk, nd, s_taken, tid, k1, k2);
+                replay_scan<WORDS, MASKED, THREADS>(qd + (size_t)(q0 + t) * WORDS, MASKED ? qmk + (size_t)(q0 + t) * WORDS : nullptr, dd, dmk, 0, scan_hi, s_taken, tid, k1, k2);
                 if (lane == 0) { sh->k1[0] = k1; sh->k2[0] = k2; }
                 named_bar<THREADS>(2);
                 k1 = lane < THREADS / 32 ? sh->k1[lane] : 0xFFFFFFFFu;
                 k2 = lane < THREADS / 32 ? sh->k2[lane] : 0xFFFFFFFFu;
-                const unsigned B = __reduce_min_sync(0xffffffffu, k1);
-                const unsigned S = __reduce_min_sync(0xffffffffu, k1 == B ? k2 : k1);
+                unsigned B = __reduce_min_sync(0xffffffffu, k1);
+                unsigned S = __reduce_min_sync(0xffffffffu, k1 == B ? k2 : k1);
+                if (coop.helpers) {                         // fold the helpers' partial minima (lanes 0..helpers-1), own shard in lane 31
+                    if (lane == 0) {
+                        while (*(volatile int*)&coop.seg->done < seq * coop.helpers) {}
+                        __threadfence();
+                    }
+                    __syncwarp();
+                    k1 = lane < coop.helpers ? *(volatile unsigned*)&coop.seg->partial[2 * lane] : (lane == 31 ? B : 0xFFFFFFFFu);
+                    k2 = lane < coop.helpers ? *(volatile unsigned*)&coop.seg->partial[2 * lane + 1] : (lane == 31 ? S : 0xFFFFFFFFu);
+                    B = __reduce_min_sync(0xffffffffu, k1);
+                    S = __reduce_min_sync(0xffffffffu, k1 == B ? k2 : k1);
+                }
                 const int best1 = B == 0xFFFFFFFFu ? 0x7FFFFFFF : (int)(B >> kKeyShift), best2 = S == 0xFFFFFFFFu ? 0x7FFFFFFF : (int)(S >> kKeyShift);
                 bestIdx = (int)(B & ((1u << kKeyShift) - 1u));
                 code = (best1 < th_low && (double)best1 < nnratio * (double)best2) ? 1 : 0;
@@ -445,15 +482,65 @@ __device__ __forceinline__ int replay_core(const int* __restrict__ list_idx, con
                 if (lane == 0) {
                     matches12[q0 + t] = bestIdx;
                     s_taken[bestIdx >> 5] |= 1u << (bestIdx & 31);
+                    if (coop.helpers) coop.log[nlog] = bestIdx;      // visible to the helpers with the fence of the next publication
                 }
-                ++nm;
+                ++nm; ++nlog;
             }
             __syncwarp();
         }
     }
-    if (lane == 0) sh->cmd = -1;
+    if (lane == 0) {
+        sh->cmd = -1;
+        if (coop.helpers) atomicExch(&coop.seg->cmd_seq, -1);
+    }
     named_bar<THREADS>(1);
     return nm;
+}
+
+// helper CTA of a cooperative walk: scans database entries [lo, hi) for every rescan the leader publishes
+template <int WORDS, bool MASKED, int THREADS>
+__device__ __forceinline__ void replay_helper(CoopSeg* cs, const int* log, const int helper /* 0-based */, const uint32_t* __restrict__ qd,
+                                              const uint32_t* __restrict__ qmk, const uint32_t* __restrict__ dd,
+                                              const uint32_t* __restrict__ dmk, const int lo, const int hi, unsigned* s_taken /* bit (id - lo) */,
+                                              ReplayShared* sh) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int seen = 0, applied = 0;
+    for (;;) {
+        if (tid == 0) {
+            int sq;
+            while ((sq = *(volatile int*)&cs->cmd_seq) == seen) {}
+            sh->cmd = sq;
+        }
+        __syncthreads();
+        const int sq = sh->cmd;
+        if (sq < 0) return;
+        seen = sq;
+        __threadfence();
+        const int q = *(volatile int*)&cs->cmd_query, len = *(volatile int*)&cs->log_len;
+        for (int i = applied + tid; i < len; i += THREADS) {
+            const int id = *(volatile const int*)&log[i];
+            if (id >= lo && id < hi) atomicOr(&s_taken[(id - lo) >> 5], 1u << ((id - lo) & 31));
+        }
+        applied = len;
+        __syncthreads();
+        unsigned k1, k2;
+        replay_scan<WORDS, MASKED, THREADS>(qd + (size_t)q * WORDS, MASKED ? qmk + (size_t)q * WORDS : nullptr, dd, dmk, lo, hi, s_taken, tid, k1, k2);
+        if (lane == 0) { sh->k1[warp] = k1; sh->k2[warp] = k2; }
+        __syncthreads();
+        if (warp == 0) {
+            k1 = lane < THREADS / 32 ? sh->k1[lane] : 0xFFFFFFFFu;
+            k2 = lane < THREADS / 32 ? sh->k2[lane] : 0xFFFFFFFFu;
+            const unsigned B = __reduce_min_sync(0xffffffffu, k1);
+            const unsigned S = __reduce_min_sync(0xffffffffu, k1 == B ? k2 : k1);
+            if (lane == 0) {
+                *(volatile unsigned*)&cs->partial[2 * helper] = B;
+                *(volatile unsigned*)&cs->partial[2 * helper + 1] = S;
+                __threadfence();
+                atomicAdd(&cs->done, 1);
+            }
+        }
+        // sh->cmd is rewritten only after thread 0 has seen the next publication, which the leader issues after this delivery
+    }
 }
 
 // Stream matcher: one CTA per image; queries = the image's slots, database = the same camera's image one frame earlier.
@@ -507,45 +594,86 @@ bruteforce_replay_kernel(const int* __restrict__ list_idx, const int* __restrict
                          const uint32_t* __restrict__ q, const uint32_t* __restrict__ qm, const uint8_t* __restrict__ valid1,
                          const int* __restrict__ seg, const uint32_t* __restrict__ d, const uint32_t* __restrict__ dm,
                          const uint8_t* __restrict__ valid2, const int nd, const int th_low, const double nnratio,
-                         int* __restrict__ matches12, int* __restrict__ nmatches) {
+                         int* __restrict__ matches12, int* __restrict__ nmatches, CoopSeg* __restrict__ coop_seg, int* __restrict__ coop_log,
+                         const int helpers) {
     extern __shared__ int s_mem[];
     int* s_li = s_mem;
     int* s_ld = s_mem + 32 * K;
-    unsigned* s_taken = (unsigned*)(s_mem + 64 * K);   // [(nd + 31) / 32]
+    unsigned* s_taken = (unsigned*)(s_mem + 64 * K);   // leader: [(nd + 31) / 32]; helper: its shard only
     __shared__ ReplayShared sh;
-    const int s = blockIdx.x, tid = threadIdx.x;
+    const int s = blockIdx.x / (helpers + 1), role = blockIdx.x - s * (helpers + 1), tid = threadIdx.x;   // role 0 = leader
     const int q0 = seg[s], nq = seg[s + 1] - q0;
-    for (int w = tid; w < (nd + 31) / 32; w += kBfReplayThreads) {
+    // shards: leader [0, cut), helper h (1-based role) [cut + (h-1) * per, ...): equal shares, the leader takes one too
+    const int per = (nd + helpers) / (helpers + 1);
+    const int lo = role * per, hi = min(nd, lo + per);
+    const int bit_lo = role == 0 ? 0 : lo, bit_hi = role == 0 ? nd : hi;                 // the leader needs every bit for the list walk
+    for (int w = tid; w < (bit_hi - bit_lo + 31) / 32; w += kBfReplayThreads) {
         unsigned bits = 0u;
         if (valid2)
-            for (int k = 0; k < 32 && w * 32 + k < nd; ++k) bits |= (valid2[w * 32 + k] ? 0u : 1u) << k;
+            for (int k = 0; k < 32 && bit_lo + w * 32 + k < bit_hi; ++k) bits |= (valid2[bit_lo + w * 32 + k] ? 0u : 1u) << k;
         s_taken[w] = bits;
     }
-    for (int i = tid; i < nq; i += kBfReplayThreads) matches12[q0 + i] = -1;
+    if (role == 0)
+        for (int i = tid; i < nq; i += kBfReplayThreads) matches12[q0 + i] = -1;
     __syncthreads();
+    if (role != 0) {
+        replay_helper<WORDS, MASKED, kBfReplayThreads>(coop_seg + s, coop_log + q0, role - 1, q + (size_t)q0 * WORDS, MASKED ? qm + (size_t)q0 * WORDS : nullptr,
+                                                       d, dm, lo, hi, s_taken, &sh);
+        return;
+    }
+    const CoopLeader cl{helpers ? coop_seg + s : nullptr, helpers ? coop_log + q0 : nullptr, helpers, helpers ? hi : nd};
     const int nm = replay_core<WORDS, MASKED, kBfReplayThreads>(list_idx + (size_t)q0 * K, list_dist + (size_t)q0 * K, K, nq, valid1 ? valid1 + q0 : nullptr,
                                                                 q + (size_t)q0 * WORDS, MASKED ? qm + (size_t)q0 * WORDS : nullptr, d, dm, nd, th_low,
-                                                                nnratio, matches12 + q0, s_li, s_ld, s_taken, &sh);
+                                                                nnratio, matches12 + q0, s_li, s_ld, s_taken, &sh, cl);
     if (tid == 0) nmatches[s] = nm;
 }
 
 cudaError_t launch_bruteforce_replay(const int* list_idx, const int* list_dist, int K, const uint8_t* q, const uint8_t* qm, const uint8_t* valid1,
-                                     const int* seg, int n_seg, const uint8_t* d, const uint8_t* dm, const uint8_t* valid2, int nd, int dim,
+                                     const int* seg, int n_seg, int nq_total, const uint8_t* d, const uint8_t* dm, const uint8_t* valid2, int nd, int dim,
                                      int th_low, double nnratio, int* matches12, int* nmatches, cudaStream_t st) {
     if (n_seg < 1) return cudaSuccess;
     if (nd >= (1 << kKeyShift) || (dim != 16 && dim != 32 && dim != 64)) return cudaErrorInvalidValue;
     const size_t smem = (size_t)64 * K * 4 + (size_t)((nd + 31) / 32) * 4;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     const bool masked = qm && dm;
-#define MCS_BR(W, M) { if (smem > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(bruteforce_replay_kernel<W, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-                                               if (e != cudaSuccess) return e; } \
-        bruteforce_replay_kernel<W, M><<<n_seg, kBfReplayThreads, smem, st>>>(list_idx, list_dist, K, (const uint32_t*)q, (const uint32_t*)qm, valid1, seg, \
-            (const uint32_t*)d, (const uint32_t*)dm, valid2, nd, th_low, nnratio, matches12, nmatches); }
-    if (dim == 16) { if (masked) MCS_BR(4, true) else MCS_BR(4, false) }
-    else if (dim == 32) { if (masked) MCS_BR(8, true) else MCS_BR(8, false) }
-    else { if (masked) MCS_BR(16, true) else MCS_BR(16, false) }
+    int dev = 0, sms = 0, coop_ok = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, dev);
+    if (e != cudaSuccess) return e;
+    const void* fn = nullptr;
+#define MCS_BR(W, M) fn = (const void*)bruteforce_replay_kernel<W, M>
+    if (dim == 16) { if (masked) MCS_BR(4, true); else MCS_BR(4, false); }
+    else if (dim == 32) { if (masked) MCS_BR(8, true); else MCS_BR(8, false); }
+    else { if (masked) MCS_BR(16, true); else MCS_BR(16, false); }
 #undef MCS_BR
-    return cudaGetLastError();
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    // helper CTAs per query set: only worth it for a large database (a rescan of a few thousand entries is faster than a
+    // round trip through global memory), and only as many as can be co-resident with every leader
+    int per_sm = 0, helpers = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBfReplayThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (coop_ok && nd >= 32768) helpers = std::max(0, std::min(kCoopMax, per_sm * sms / n_seg - 1));
+    CoopSeg* cseg = nullptr; int* clog = nullptr;
+    if (helpers) {
+        e = keep_pool_memory();
+        if (e == cudaSuccess) e = cudaMallocAsync((void**)&cseg, sizeof(CoopSeg) * n_seg, st);
+        if (e == cudaSuccess) e = cudaMallocAsync((void**)&clog, sizeof(int) * (size_t)std::max(nq_total, 1), st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(cseg, 0, sizeof(CoopSeg) * n_seg, st);
+        if (e != cudaSuccess) return e;
+    }
+    const uint32_t *q32 = (const uint32_t*)q, *qm32 = (const uint32_t*)qm, *d32 = (const uint32_t*)d, *dm32 = (const uint32_t*)dm;
+    void* args[] = {(void*)&list_idx, (void*)&list_dist, (void*)&K, (void*)&q32, (void*)&qm32, (void*)&valid1, (void*)&seg, (void*)&d32, (void*)&dm32,
+                    (void*)&valid2, (void*)&nd, (void*)&th_low, (void*)&nnratio, (void*)&matches12, (void*)&nmatches, (void*)&cseg, (void*)&clog,
+                    (void*)&helpers};
+    const dim3 grid(n_seg * (helpers + 1)), block(kBfReplayThreads);
+    if (helpers) e = cudaLaunchCooperativeKernel(fn, grid, block, args, smem, st);       // co-residency guaranteed or the launch fails
+    else e = cudaLaunchKernel(fn, grid, block, args, smem, st);
+    if (helpers) { cudaFreeAsync(cseg, st); cudaFreeAsync(clog, st); }
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -209,7 +209,7 @@ static int bruteforce_core(const uint8_t* q_dev, const uint8_t* qm_dev, const ui
     Dev dv2;
     if (valid2) { MCK(dv2.alloc(nd)); MCK(cudaMemcpyAsync(dv2.p, valid2, nd, cudaMemcpyHostToDevice, st)); }
     MCK(launch_bruteforce_replay(di.as<int>(), dt.as<int>(), K, q_dev, masked ? qm_dev : nullptr, valid1 ? dv1.as<uint8_t>() : nullptr,
-                                 dseg.as<int>(), n_seg, d_dev, masked ? dm_dev : nullptr, valid2 ? dv2.as<uint8_t>() : nullptr, nd, dim, th_low,
+                                 dseg.as<int>(), n_seg, nq, d_dev, masked ? dm_dev : nullptr, valid2 ? dv2.as<uint8_t>() : nullptr, nd, dim, th_low,
                                  nnratio, dm12.as<int>(), dnm.as<int>(), st));
     MCK(cudaMemcpyAsync(matches12, dm12.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
     MCK(cudaMemcpyAsync(nmatches, dnm.p, (size_t)n_seg * 4, cudaMemcpyDeviceToHost, st));

@@ -565,3 +565,38 @@ def test_bruteforce_batch_equals_separate_calls(api, oa):
     # a single shared state would differ: the sets compete for the same planted entries
     n_shared, _ = api.match_bruteforce_device(t(q), t(qm), valid1, t(db), t(dbm), valid2, 60, 0.8)
     assert n_shared < total
+
+
+def test_bruteforce_large_database_cooperative_rescans(api, oa):
+    """a database large enough (>= 32768 entries) for the acceptance kernel to spread every rescan over helper CTAs; the data is
+    built so that rescans happen: every query set holds clusters of near-identical queries and the database 12 near copies of each
+    cluster centre, so the 8-entry lists of later cluster members are used up by the earlier ones"""
+    import torch
+    rng = np.random.default_rng(11)
+    nd, nseg, ncl, per_cl = 40000, 3, 60, 6
+    centres = rng.integers(0, 256, (ncl, 32), dtype=np.uint8)
+
+    def near(src, kmax):
+        out = src.copy()
+        for i in range(len(out)):
+            for b in rng.choice(256, rng.integers(0, kmax + 1), replace=False):
+                out[i, b // 8] ^= 1 << (b % 8)
+        return out
+    db = rng.integers(0, 256, (nd, 32), dtype=np.uint8)
+    slots = rng.choice(nd, ncl * 12, replace=False)
+    db[slots] = near(np.repeat(centres, 12, axis=0), 10)
+    dbm = np.packbits(rng.random((nd, 256)) < 0.9, axis=1, bitorder="little")
+    qs = [near(np.repeat(centres, per_cl, axis=0)[rng.permutation(ncl * per_cl)], 8) for _ in range(nseg)]
+    q = np.concatenate(qs)
+    qm = np.packbits(rng.random((len(q), 256)) < 0.9, axis=1, bitorder="little")
+    valid2 = (rng.random(nd) < 0.97).astype(np.uint8)
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    seg = np.arange(nseg + 1) * (ncl * per_cl)
+    # a permissive ratio so that cluster members keep taking entries (the strict 0.9 would reject most of them as ambiguous)
+    nms, m12 = api.match_bruteforce_batch_device(t(q), t(qm), None, seg, t(db), t(dbm), valid2, 40, 1.01)
+    for s in range(nseg):
+        sl = slice(seg[s], seg[s + 1])
+        on, om = oa.match_bruteforce(q[sl], db, 40, 1.01, qm[sl], dbm, None, valid2)
+        assert on == nms[s] and np.array_equal(m12[sl], om)
+        assert on > 0.8 * (seg[s + 1] - seg[s])
