@@ -424,25 +424,32 @@ __device__ __forceinline__ int replay_core(const int* __restrict__ list_idx, con
         }
         __syncwarp();
         for (int t = 0; t < nchunk; ++t) {
-            int code = 0, bestIdx = -1;              // 0 no match, 1 match bestIdx, 2 undecided from the list
-            if (lane == 0 && !(valid1 && !valid1[q0 + t])) {
-                int best1 = 0x7FFFFFFF, best2 = 0x7FFFFFFF, found = 0, dK = 0x7FFFFFFF;
-                bool complete = false;
-                for (int k = 0; k < K; ++k) {
-                    const int id = s_li[t * K + k];
-                    if (id < 0) { complete = true; break; }          // the list holds every database entry that matters
-                    dK = s_ld[t * K + k];
-                    if (s_taken[id >> 5] >> (id & 31) & 1u) continue;
-                    if (found == 0) { best1 = s_ld[t * K + k]; bestIdx = id; }
-                    else best2 = s_ld[t * K + k];
-                    if (++found == 2) break;
-                }
-                if (found == 2 || complete) code = (best1 < th_low && (double)best1 < nnratio * (double)best2) ? 1 : 0;
+            // Decision from the list, evaluated by the whole warp: lane k looks at list entry k (K <= 8), two ballots give the
+            // unmatched entries in list order -- no serial chain of dependent shared-memory loads per entry.
+            //   code 0 no match, 1 match bestIdx, 2 undecided from the list
+            int code = 0, bestIdx = -1;
+            {
+                const unsigned kmask = (1u << K) - 1u;
+                const int id = lane < K ? s_li[t * K + lane] : -1;
+                const int dl = lane < K ? s_ld[t * K + lane] : 0x7FFFFFFF;
+                const bool valid = id >= 0;
+                const bool open = valid && !(s_taken[id >> 5] >> (id & 31) & 1u);
+                const unsigned m_valid = __ballot_sync(0xffffffffu, valid) & kmask;
+                const unsigned m_open = __ballot_sync(0xffffffffu, open) & kmask;
+                const bool complete = m_valid != kmask;                 // a -1 entry: the list holds every database entry that matters
+                const int found = min(__popc(m_open), 2);
+                const int first = m_open ? __ffs(m_open) - 1 : 0;
+                const unsigned rest = m_open & ~(1u << first);
+                const int second = rest ? __ffs(rest) - 1 : 0, lastv = m_valid ? 31 - __clz(m_valid) : 0;
+                const int best1 = found >= 1 ? __shfl_sync(0xffffffffu, dl, first) : 0x7FFFFFFF;
+                const int best2 = found >= 2 ? __shfl_sync(0xffffffffu, dl, second) : 0x7FFFFFFF;
+                const int dK = m_valid ? __shfl_sync(0xffffffffu, dl, lastv) : 0x7FFFFFFF;      // every entry NOT in the list is at least this far
+                bestIdx = found >= 1 ? __shfl_sync(0xffffffffu, id, first) : -1;
+                if (valid1 && !valid1[q0 + t]) code = 0;
+                else if (found == 2 || complete) code = (best1 < th_low && (double)best1 < nnratio * (double)best2) ? 1 : 0;
                 else if (found == 1) code = !(best1 < th_low) ? 0 : ((double)best1 < nnratio * (double)dK ? 1 : 2);
                 else code = !(dK < th_low) ? 0 : 2;
             }
-            code = __shfl_sync(0xffffffffu, code, 0);
-            bestIdx = __shfl_sync(0xffffffffu, bestIdx, 0);
             if (code == 2) {
                 // exact rescan of the database for this query: two smallest (distance, index) keys among the unmatched entries
                 if (lane == 0) {
