@@ -327,54 +327,88 @@ constexpr int kKeyShift = 21;                // rescan keys = distance << 21 | i
 template <int THREADS>
 __device__ __forceinline__ void named_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(THREADS) : "memory"); }
 
-// two smallest (distance << kKeyShift | index) keys among this thread's share of the unmatched database entries
-template <int WORDS, bool MASKED, int THREADS>
-__device__ __forceinline__ void replay_scan(const uint32_t* __restrict__ qrow, const uint32_t* __restrict__ qmrow,
+// One pass over this thread's share of the unmatched database entries for up to R queries at once (rows[0..n)): per query the two
+// smallest (distance << kKeyShift | index) keys.  The database words are loaded once per entry whatever n is; a rescan is bound
+// by the latency of those loads, so the extra queries ride along almost for free.
+template <int WORDS, bool MASKED, int THREADS, int R>
+__device__ __forceinline__ void replay_scan(const uint32_t* __restrict__ qd, const uint32_t* __restrict__ qmk, const int* rows, const int n,
                                             const uint32_t* __restrict__ dd, const uint32_t* __restrict__ dm, const int id_lo,
                                             const int id_hi, const unsigned* s_taken /* bit (id - id_lo) */, const int tid,
-                                            unsigned& k1, unsigned& k2) {
-    uint4 qw[WORDS / 4], qm[MASKED ? WORDS / 4 : 1];
-    const uint4* qp = reinterpret_cast<const uint4*>(qrow);
+                                            unsigned (&k1)[R], unsigned (&k2)[R]) {
+    uint4 qw[R][WORDS / 4], qm[R][MASKED ? WORDS / 4 : 1];
 #pragma unroll
-    for (int k = 0; k < WORDS / 4; ++k) qw[k] = qp[k];
-    if (MASKED) {
-        const uint4* qmp = reinterpret_cast<const uint4*>(qmrow);
+    for (int r = 0; r < R; ++r) {
+        const int row = rows[r < n ? r : 0];
+        const uint4* qp = reinterpret_cast<const uint4*>(qd + (size_t)row * WORDS);
 #pragma unroll
-        for (int k = 0; k < WORDS / 4; ++k) qm[k] = qmp[k];
+        for (int k = 0; k < WORDS / 4; ++k) qw[r][k] = qp[k];
+        if (MASKED) {
+            const uint4* qmp = reinterpret_cast<const uint4*>(qmk + (size_t)row * WORDS);
+#pragma unroll
+            for (int k = 0; k < WORDS / 4; ++k) qm[r][k] = qmp[k];
+        }
+        k1[r] = 0xFFFFFFFFu; k2[r] = 0xFFFFFFFFu;
     }
-    k1 = 0xFFFFFFFFu; k2 = 0xFFFFFFFFu;
 #pragma unroll 2
     for (int id = id_lo + tid; id < id_hi; id += THREADS) {
         if (s_taken[(id - id_lo) >> 5] >> ((id - id_lo) & 31) & 1u) continue;
         const uint4* dp = reinterpret_cast<const uint4*>(dd + (size_t)id * WORDS);
-        unsigned dist = 0;
-        if (MASKED) {
-            const uint4* mp = reinterpret_cast<const uint4*>(dm + (size_t)id * WORDS);
+        const uint4* mp = MASKED ? reinterpret_cast<const uint4*>(dm + (size_t)id * WORDS) : nullptr;
+        uint4 d[WORDS / 4], m[MASKED ? WORDS / 4 : 1];
+#pragma unroll
+        for (int k = 0; k < WORDS / 4; ++k) { d[k] = dp[k]; if (MASKED) m[k] = mp[k]; }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (r >= n) break;
+            unsigned dist = 0;
 #pragma unroll
             for (int k = 0; k < WORDS / 4; ++k) {
-                const uint4 d = dp[k], m = mp[k];
-                const uint32_t x0 = qw[k].x ^ d.x, x1 = qw[k].y ^ d.y, x2 = qw[k].z ^ d.z, x3 = qw[k].w ^ d.w;
-                dist += __popc(x0 & qm[k].x) + __popc(x0 & m.x) + __popc(x1 & qm[k].y) + __popc(x1 & m.y) +
-                        __popc(x2 & qm[k].z) + __popc(x2 & m.z) + __popc(x3 & qm[k].w) + __popc(x3 & m.w);
+                const uint32_t x0 = qw[r][k].x ^ d[k].x, x1 = qw[r][k].y ^ d[k].y, x2 = qw[r][k].z ^ d[k].z, x3 = qw[r][k].w ^ d[k].w;
+                if (MASKED)
+                    dist += __popc(x0 & qm[r][k].x) + __popc(x0 & m[k].x) + __popc(x1 & qm[r][k].y) + __popc(x1 & m[k].y) +
+                            __popc(x2 & qm[r][k].z) + __popc(x2 & m[k].z) + __popc(x3 & qm[r][k].w) + __popc(x3 & m[k].w);
+                else
+                    dist += __popc(x0) + __popc(x1) + __popc(x2) + __popc(x3);
             }
-            dist >>= 1;
-        } else {
-#pragma unroll
-            for (int k = 0; k < WORDS / 4; ++k) {
-                const uint4 d = dp[k];
-                dist += __popc(qw[k].x ^ d.x) + __popc(qw[k].y ^ d.y) + __popc(qw[k].z ^ d.z) + __popc(qw[k].w ^ d.w);
-            }
+            if (MASKED) dist >>= 1;
+            const unsigned key = (dist << kKeyShift) | (unsigned)id;
+            if (key < k1[r]) { k2[r] = k1[r]; k1[r] = key; } else if (key < k2[r]) k2[r] = key;
         }
-        const unsigned key = (dist << kKeyShift) | (unsigned)id;
-        if (key < k1) { k2 = k1; k1 = key; } else if (key < k2) k2 = key;
     }
-    // warp: smallest and second smallest of the 64 keys (keys are unique: the index is part of the key)
-    const unsigned B = __reduce_min_sync(0xffffffffu, k1);
-    const unsigned S = __reduce_min_sync(0xffffffffu, k1 == B ? k2 : k1);
-    k1 = B; k2 = S;
+    // warp: smallest and second smallest of the 64 keys per query (keys are unique: the index is part of the key)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const unsigned B = __reduce_min_sync(0xffffffffu, k1[r]);
+        const unsigned S = __reduce_min_sync(0xffffffffu, k1[r] == B ? k2[r] : k1[r]);
+        k1[r] = B; k2[r] = S;
+    }
 }
 
-struct ReplayShared { int cmd; unsigned k1[32], k2[32]; };
+constexpr int kRescanBatch = 3;              // stream matcher: queries served by one pass over the previous image
+// decision of one query from its K-best list under the current matched bits, evaluated by a single lane (look-ahead only)
+__device__ __forceinline__ int list_code(const int* li, const int* ld, const int K, const unsigned* s_taken, const int th_low, const double nnratio) {
+    int best1 = 0x7FFFFFFF, best2 = 0x7FFFFFFF, found = 0, dK = 0x7FFFFFFF;
+    bool complete = false;
+    for (int k = 0; k < K; ++k) {
+        const int id = li[k];
+        if (id < 0) { complete = true; break; }
+        dK = ld[k];
+        if (s_taken[id >> 5] >> (id & 31) & 1u) continue;
+        if (found == 0) best1 = ld[k]; else best2 = ld[k];
+        if (++found == 2) break;
+    }
+    if (found == 2 || complete) return (best1 < th_low && (double)best1 < nnratio * (double)best2) ? 1 : 0;
+    if (found == 1) return !(best1 < th_low) ? 0 : ((double)best1 < nnratio * (double)dK ? 1 : 2);
+    return !(dK < th_low) ? 0 : 2;
+}
+
+struct ReplayShared {
+    int cmd;                                  // queries in the published batch (>= 1), -1 = the walk is over
+    int bq[kRescanBatch];                     // their rows
+    unsigned k1[32][kRescanBatch], k2[32][kRescanBatch];      // per warp: two smallest keys per batch query
+    int pq[kRescanBatch];                     // look-ahead results of the last batch: query row (-1 = none), best, second
+    unsigned pB[kRescanBatch], pS[kRescanBatch];
+};
 
 // Several CTAs per query set (key-frame database): the leader CTA walks the queries; for a rescan it publishes the query in global
 // memory, every helper CTA scans its own shard of the database and delivers the two smallest keys, the leader scans shard 0
@@ -394,7 +428,10 @@ struct CoopLeader { CoopSeg* seg; int* log; int helpers; int shard_hi; };   // h
 // "already matched" bits live in s_taken.  Warp 0 walks the queries in order (lane 0 decides from the list); the other warps
 // sleep on a named barrier and wake only for a rescan, where all THREADS threads split the database.  Every thread of the CTA
 // must call this; returns the number of matches in warp 0 (other warps: 0).
-template <int WORDS, bool MASKED, int THREADS>
+// R > 1: a rescan pass also serves the next queries of the current 32-query chunk that cannot be decided from their lists right
+// now (look-ahead).  Such a result stays exact as long as neither its best nor its second entry has been matched in between (the
+// minimum and second minimum of a set do not change when OTHER elements leave it); that is checked when the walk gets there.
+template <int WORDS, bool MASKED, int THREADS, int R>
 __device__ __forceinline__ int replay_core(const int* __restrict__ list_idx, const int* __restrict__ list_dist, const int K, const int nq,
                                            const uint8_t* __restrict__ valid1, const uint32_t* __restrict__ qd,
                                            const uint32_t* __restrict__ qmk, const uint32_t* __restrict__ dd,
@@ -409,13 +446,18 @@ __device__ __forceinline__ int replay_core(const int* __restrict__ list_idx, con
             named_bar<THREADS>(1);
             const int cmd = *(volatile int*)&sh->cmd;
             if (cmd < 0) return 0;
-            unsigned k1, k2;
-            replay_scan<WORDS, MASKED, THREADS>(qd + (size_t)cmd * WORDS, MASKED ? qmk + (size_t)cmd * WORDS : nullptr, dd, dmk, 0, scan_hi, s_taken, tid, k1, k2);
-            if (lane == 0) { sh->k1[warp] = k1; sh->k2[warp] = k2; }
+            unsigned k1[R], k2[R];
+            replay_scan<WORDS, MASKED, THREADS, R>(qd, qmk, sh->bq, cmd, dd, dmk, 0, scan_hi, s_taken, tid, k1, k2);
+            if (lane == 0) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) { sh->k1[warp][r] = k1[r]; sh->k2[warp][r] = k2[r]; }
+            }
             named_bar<THREADS>(2);
         }
     }
     int nm = 0;
+    if (lane < kRescanBatch) sh->pq[lane] = -1;
+    __syncwarp();
     for (int q0 = 0; q0 < nq; q0 += 32) {
         const int nchunk = min(32, nq - q0);
         for (int i = lane; i < nchunk * K; i += 32) {
@@ -451,35 +493,71 @@ __device__ __forceinline__ int replay_core(const int* __restrict__ list_idx, con
                 else code = !(dK < th_low) ? 0 : 2;
             }
             if (code == 2) {
-                // exact rescan of the database for this query: two smallest (distance, index) keys among the unmatched entries
-                if (lane == 0) {
-                    sh->cmd = q0 + t;
-                    if (coop.helpers) {                     // publish the rescan to the helper CTAs before scanning shard 0 here
-                        coop.seg->cmd_query = q0 + t;
-                        coop.seg->log_len = nlog;
-                        __threadfence();
-                        atomicExch(&coop.seg->cmd_seq, ++seq);
-                    }
+                unsigned B = 0xFFFFFFFFu, S = 0xFFFFFFFFu;
+                bool have = false;
+                if (R > 1) {                                // a look-ahead result of an earlier pass, still exact?
+#pragma unroll
+                    for (int r = 1; r < R; ++r)
+                        if (sh->pq[r] == q0 + t) {
+                            const unsigned pb = sh->pB[r], ps = sh->pS[r];
+                            const unsigned bi = pb & ((1u << kKeyShift) - 1u), si = ps & ((1u << kKeyShift) - 1u);
+                            const bool gone = (pb != 0xFFFFFFFFu && (s_taken[bi >> 5] >> (bi & 31) & 1u)) ||
+                                              (ps != 0xFFFFFFFFu && (s_taken[si >> 5] >> (si & 31) & 1u));
+                            if (!gone) { B = pb; S = ps; have = true; }
+                        }
                 }
-                named_bar<THREADS>(1);
-                unsigned k1, k2;
-                replay_scan<WORDS, MASKED, THREADS>(qd + (size_t)(q0 + t) * WORDS, MASKED ? qmk + (size_t)(q0 + t) * WORDS : nullptr, dd, dmk, 0, scan_hi, s_taken, tid, k1, k2);
-                if (lane == 0) { sh->k1[0] = k1; sh->k2[0] = k2; }
-                named_bar<THREADS>(2);
-                k1 = lane < THREADS / 32 ? sh->k1[lane] : 0xFFFFFFFFu;
-                k2 = lane < THREADS / 32 ? sh->k2[lane] : 0xFFFFFFFFu;
-                unsigned B = __reduce_min_sync(0xffffffffu, k1);
-                unsigned S = __reduce_min_sync(0xffffffffu, k1 == B ? k2 : k1);
-                if (coop.helpers) {                         // fold the helpers' partial minima (lanes 0..helpers-1), own shard in lane 31
-                    if (lane == 0) {
-                        while (*(volatile int*)&coop.seg->done < seq * coop.helpers) {}
-                        __threadfence();
+                if (!have) {
+                    // exact rescan of the database: two smallest (distance, index) keys among the unmatched entries, for this query
+                    // and (R > 1) for the next queries of the chunk that are undecided under the current matched bits
+                    int n = 1;
+                    unsigned cand = 0u;
+                    if (R > 1) {
+                        int c = 0;
+                        if (lane > t && lane < nchunk && !(valid1 && !valid1[q0 + lane]))
+                            c = list_code(s_li + lane * K, s_ld + lane * K, K, s_taken, th_low, nnratio);
+                        cand = __ballot_sync(0xffffffffu, c == 2);
+                        n += min(__popc(cand), R - 1);
                     }
-                    __syncwarp();
-                    k1 = lane < coop.helpers ? *(volatile unsigned*)&coop.seg->partial[2 * lane] : (lane == 31 ? B : 0xFFFFFFFFu);
-                    k2 = lane < coop.helpers ? *(volatile unsigned*)&coop.seg->partial[2 * lane + 1] : (lane == 31 ? S : 0xFFFFFFFFu);
-                    B = __reduce_min_sync(0xffffffffu, k1);
-                    S = __reduce_min_sync(0xffffffffu, k1 == B ? k2 : k1);
+                    if (lane == 0) {
+                        sh->cmd = n;
+                        sh->bq[0] = q0 + t;
+                        unsigned cm = cand;
+                        for (int r = 1; r < n; ++r) { sh->bq[r] = q0 + __ffs(cm) - 1; cm &= cm - 1u; }
+                        if (coop.helpers) {                 // publish the rescan to the helper CTAs before scanning shard 0 here (R == 1)
+                            coop.seg->cmd_query = q0 + t;
+                            coop.seg->log_len = nlog;
+                            __threadfence();
+                            atomicExch(&coop.seg->cmd_seq, ++seq);
+                        }
+                    }
+                    named_bar<THREADS>(1);
+                    unsigned k1[R], k2[R];
+                    replay_scan<WORDS, MASKED, THREADS, R>(qd, qmk, sh->bq, n, dd, dmk, 0, scan_hi, s_taken, tid, k1, k2);
+                    if (lane == 0) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) { sh->k1[0][r] = k1[r]; sh->k2[0][r] = k2[r]; }
+                    }
+                    named_bar<THREADS>(2);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const unsigned a1 = lane < THREADS / 32 ? sh->k1[lane][r] : 0xFFFFFFFFu;
+                        const unsigned a2 = lane < THREADS / 32 ? sh->k2[lane][r] : 0xFFFFFFFFu;
+                        const unsigned Br = __reduce_min_sync(0xffffffffu, a1);
+                        const unsigned Sr = __reduce_min_sync(0xffffffffu, a1 == Br ? a2 : a1);
+                        if (r == 0) { B = Br; S = Sr; }
+                        else if (lane == 0) { sh->pq[r] = r < n ? sh->bq[r] : -1; sh->pB[r] = Br; sh->pS[r] = Sr; }
+                    }
+                    if (coop.helpers) {                     // fold the helpers' partial minima (lanes 0..helpers-1), own shard in lane 31
+                        if (lane == 0) {
+                            while (*(volatile int*)&coop.seg->done < seq * coop.helpers) {}
+                            __threadfence();
+                        }
+                        __syncwarp();
+                        const unsigned a1 = lane < coop.helpers ? *(volatile unsigned*)&coop.seg->partial[2 * lane] : (lane == 31 ? B : 0xFFFFFFFFu);
+                        const unsigned a2 = lane < coop.helpers ? *(volatile unsigned*)&coop.seg->partial[2 * lane + 1] : (lane == 31 ? S : 0xFFFFFFFFu);
+                        B = __reduce_min_sync(0xffffffffu, a1);
+                        S = __reduce_min_sync(0xffffffffu, a1 == B ? a2 : a1);
+                    }
                 }
                 const int best1 = B == 0xFFFFFFFFu ? 0x7FFFFFFF : (int)(B >> kKeyShift), best2 = S == 0xFFFFFFFFu ? 0x7FFFFFFF : (int)(S >> kKeyShift);
                 bestIdx = (int)(B & ((1u << kKeyShift) - 1u));
@@ -530,15 +608,17 @@ __device__ __forceinline__ void replay_helper(CoopSeg* cs, const int* log, const
         }
         applied = len;
         __syncthreads();
-        unsigned k1, k2;
-        replay_scan<WORDS, MASKED, THREADS>(qd + (size_t)q * WORDS, MASKED ? qmk + (size_t)q * WORDS : nullptr, dd, dmk, lo, hi, s_taken, tid, k1, k2);
-        if (lane == 0) { sh->k1[warp] = k1; sh->k2[warp] = k2; }
+        unsigned k1[1], k2[1];
+        if (tid == 0) sh->bq[0] = q;
+        __syncthreads();
+        replay_scan<WORDS, MASKED, THREADS, 1>(qd, qmk, sh->bq, 1, dd, dmk, lo, hi, s_taken, tid, k1, k2);
+        if (lane == 0) { sh->k1[warp][0] = k1[0]; sh->k2[warp][0] = k2[0]; }
         __syncthreads();
         if (warp == 0) {
-            k1 = lane < THREADS / 32 ? sh->k1[lane] : 0xFFFFFFFFu;
-            k2 = lane < THREADS / 32 ? sh->k2[lane] : 0xFFFFFFFFu;
-            const unsigned B = __reduce_min_sync(0xffffffffu, k1);
-            const unsigned S = __reduce_min_sync(0xffffffffu, k1 == B ? k2 : k1);
+            const unsigned a1 = lane < THREADS / 32 ? sh->k1[lane][0] : 0xFFFFFFFFu;
+            const unsigned a2 = lane < THREADS / 32 ? sh->k2[lane][0] : 0xFFFFFFFFu;
+            const unsigned B = __reduce_min_sync(0xffffffffu, a1);
+            const unsigned S = __reduce_min_sync(0xffffffffu, a1 == B ? a2 : a1);
             if (lane == 0) {
                 *(volatile unsigned*)&cs->partial[2 * helper] = B;
                 *(volatile unsigned*)&cs->partial[2 * helper + 1] = S;
@@ -552,7 +632,7 @@ __device__ __forceinline__ void replay_helper(CoopSeg* cs, const int* log, const
 
 // Stream matcher: one CTA per image; queries = the image's slots, database = the same camera's image one frame earlier.
 template <int WORDS, bool MASKED>
-__global__ void __launch_bounds__(kReplayThreads)
+__global__ void __launch_bounds__(kReplayThreads, 3)      // all images of a 128-frame step resident at once (3 x 148 CTAs)
 stream_replay_kernel(const int* __restrict__ list_idx, const int* __restrict__ list_dist, const int* __restrict__ counts,
                      const uint32_t* __restrict__ desc, const uint32_t* __restrict__ dmask,
                      const int n_cams, const int capacity, const int K, const int img_lo, const int th_low, const double nnratio,
@@ -570,7 +650,7 @@ stream_replay_kernel(const int* __restrict__ list_idx, const int* __restrict__ l
     for (int i = tid; i < (capacity + 31) / 32; i += kReplayThreads) s_taken[i] = 0u;
     for (int i = tid; i < capacity; i += kReplayThreads) matches12[q_row0 + i] = -1;
     __syncthreads();
-    const int nm = replay_core<WORDS, MASKED, kReplayThreads>(list_idx + q_row0 * K, list_dist + q_row0 * K, K, nq, nullptr, desc + q_row0 * WORDS,
+    const int nm = replay_core<WORDS, MASKED, kReplayThreads, kRescanBatch>(list_idx + q_row0 * K, list_dist + q_row0 * K, K, nq, nullptr, desc + q_row0 * WORDS,
                                                               MASKED ? dmask + q_row0 * WORDS : nullptr, desc + d_row0 * WORDS,
                                                               MASKED ? dmask + d_row0 * WORDS : nullptr, nd, th_low, nnratio,
                                                               matches12 + q_row0, s_li, s_ld, s_taken, &sh);
@@ -629,7 +709,7 @@ bruteforce_replay_kernel(const int* __restrict__ list_idx, const int* __restrict
         return;
     }
     const CoopLeader cl{helpers ? coop_seg + s : nullptr, helpers ? coop_log + q0 : nullptr, helpers, helpers ? hi : nd};
-    const int nm = replay_core<WORDS, MASKED, kBfReplayThreads>(list_idx + (size_t)q0 * K, list_dist + (size_t)q0 * K, K, nq, valid1 ? valid1 + q0 : nullptr,
+    const int nm = replay_core<WORDS, MASKED, kBfReplayThreads, 1>(list_idx + (size_t)q0 * K, list_dist + (size_t)q0 * K, K, nq, valid1 ? valid1 + q0 : nullptr,
                                                                 q + (size_t)q0 * WORDS, MASKED ? qm + (size_t)q0 * WORDS : nullptr, d, dm, nd, th_low,
                                                                 nnratio, matches12 + q0, s_li, s_ld, s_taken, &sh, cl);
     if (tid == 0) nmatches[s] = nm;
