@@ -87,8 +87,37 @@ __device__ __forceinline__ unsigned hamming_words(const uint32_t (&qw)[WORDS], c
     return dist;
 }
 
+// ---- deferred insertion into the per-thread K-best list ---------------------------------------------------------------------
+// A pair whose distance beats the current K-th best (and the relevance bound) has to be inserted into the owning thread's sorted
+// register list.  Doing that on the spot runs the whole insertion sequence with one or two active lanes whenever ANY lane of the
+// warp has a candidate (ncu on the greedy stream matcher: 17 % of the kernel's warp instructions at 1.4 active lanes).  Instead a
+// candidate is parked in a small per-thread queue in shared memory and the queues are drained by all lanes together when one of
+// them is full (or the tile ends): the same insertions, issued with most lanes active.  Until a drain `worst` is stale, which
+// only lets a few more candidates through; the list content is identical (sorted insertion by (distance, index) keys).
+constexpr int kInsQueue = 4;
+__device__ __forceinline__ void topk_insert(unsigned long long (&best)[kTopKMax], const int K, unsigned long long key) {
+#pragma unroll
+    for (int k = 0; k < kTopKMax; ++k) {
+        if (k < K && key < best[k]) { const unsigned long long t = best[k]; best[k] = key; key = t; }
+    }
+}
+__device__ __forceinline__ unsigned topk_worst(const unsigned long long (&best)[kTopKMax], const int K) {
+    unsigned long long w = best[0];
+#pragma unroll
+    for (int k = 1; k < kTopKMax; ++k) if (k < K) w = best[k];
+    return (w == kNoKey) ? 0xFFFFFFFFu : (unsigned)(w >> 32);
+}
+__device__ __forceinline__ void topk_drain(unsigned long long (&best)[kTopKMax], const int K, unsigned long long (*s_q)[kTopkThreads], int& qn,
+                                           unsigned& worst) {
+#pragma unroll
+    for (int c = 0; c < kInsQueue; ++c)
+        if (c < qn) topk_insert(best, K, s_q[c][threadIdx.x]);
+    qn = 0;
+    worst = topk_worst(best, K);
+}
+
 template <int WORDS, bool MASKED>
-__global__ void __launch_bounds__(kTopkThreads)
+__global__ void __launch_bounds__(kTopkThreads, 6)
 hamming_topk_kernel(const uint32_t* __restrict__ q, const uint32_t* __restrict__ qmask, const int nq,
                     const uint32_t* __restrict__ d, const uint32_t* __restrict__ dmask, const int nd,
                     const uint8_t* __restrict__ skip, const int K, const int chunk, const unsigned bound,
@@ -96,6 +125,8 @@ hamming_topk_kernel(const uint32_t* __restrict__ q, const uint32_t* __restrict__
     __shared__ __align__(16) uint32_t s_d[kDbTile * WORDS];
     __shared__ __align__(16) uint32_t s_m[MASKED ? kDbTile * WORDS : 4];
     __shared__ uint8_t s_skip[kDbTile];
+    __shared__ unsigned long long s_q[kInsQueue][kTopkThreads];
+    int qn = 0;
 
     const int qi = blockIdx.x * kTopkThreads + threadIdx.x;
     const bool active = qi < nq;
@@ -131,19 +162,11 @@ hamming_topk_kernel(const uint32_t* __restrict__ q, const uint32_t* __restrict__
             // bit-level Hamming distance; masked form = (popc(x&ma) + popc(x&mb)) / 2, integer division (ref :2472)
             unsigned dist = hamming_words<WORDS, MASKED>(qw, qm, s_d + j * WORDS, s_m + j * WORDS);
             if (MASKED) dist >>= 1;
-            if (dist < min(worst, bound)) {            // strict: equal distances keep the earlier index; entries at or beyond `bound` are not listed
-                unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)(t0 + j);
-#pragma unroll
-                for (int k = 0; k < kTopKMax; ++k) {
-                    if (k < K && key < best[k]) { const unsigned long long t = best[k]; best[k] = key; key = t; }
-                }
-                const unsigned long long kth = best[0];
-                unsigned long long w = kth;
-#pragma unroll
-                for (int k = 1; k < kTopKMax; ++k) if (k < K) w = best[k];
-                worst = (w == kNoKey) ? 0xFFFFFFFFu : (unsigned)(w >> 32);
-            }
+            if (dist < min(worst, bound))              // strict: equal distances keep the earlier index; entries at or beyond `bound` are not listed
+                s_q[qn++][threadIdx.x] = ((unsigned long long)dist << 32) | (unsigned)(t0 + j);
+            if (__any_sync(0xffffffffu, qn == kInsQueue)) topk_drain(best, K, s_q, qn, worst);
         }
+        topk_drain(best, K, s_q, qn, worst);
     }
     if (active) {
         unsigned long long* o = part + ((size_t)blockIdx.y * nq + qi) * kTopKMax;
@@ -219,12 +242,14 @@ cudaError_t launch_hamming_topk(const uint8_t* q, const uint8_t* qmask, int nq, 
 // One thread owns one query; the (<= capacity) database descriptors of the previous frame are staged tile by
 // tile in shared memory.  Output: K best (index, distance) per query slot, (-1, INT_MAX) where none.
 template <int WORDS, bool MASKED>
-__global__ void __launch_bounds__(kTopkThreads)
+__global__ void __launch_bounds__(kTopkThreads, 6)
 hamming_stream_kernel(const uint32_t* __restrict__ desc, const uint32_t* __restrict__ dmask, const int* __restrict__ counts,
                       const int n_cams, const int capacity, const int K, const int img_lo, const unsigned bound,
                       int* __restrict__ out_idx, int* __restrict__ out_dist) {
     __shared__ __align__(16) uint32_t s_d[kDbTile * WORDS];
     __shared__ __align__(16) uint32_t s_m[MASKED ? kDbTile * WORDS : 4];
+    __shared__ unsigned long long s_q[kInsQueue][kTopkThreads];
+    int qn = 0;
     const int img = blockIdx.y + img_lo;
     const int qi = blockIdx.x * kTopkThreads + threadIdx.x;
     const bool has_prev = img >= n_cams;                 // frame 0 has no predecessor
@@ -271,18 +296,11 @@ hamming_stream_kernel(const uint32_t* __restrict__ desc, const uint32_t* __restr
             // bit-level Hamming distance; masked form = (popc(x&ma) + popc(x&mb)) / 2, integer division (ref :2472)
             unsigned dist = hamming_words<WORDS, MASKED>(qw, qm, s_d + j * WORDS, s_m + j * WORDS);
             if (MASKED) dist >>= 1;
-            if (dist < min(worst, bound)) {
-                unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)(t0 + j);
-#pragma unroll
-                for (int k = 0; k < kTopKMax; ++k) {
-                    if (k < K && key < best[k]) { const unsigned long long t = best[k]; best[k] = key; key = t; }
-                }
-                unsigned long long w = best[0];
-#pragma unroll
-                for (int k = 1; k < kTopKMax; ++k) if (k < K) w = best[k];
-                worst = (w == kNoKey) ? 0xFFFFFFFFu : (unsigned)(w >> 32);
-            }
+            if (dist < min(worst, bound))
+                s_q[qn++][threadIdx.x] = ((unsigned long long)dist << 32) | (unsigned)(t0 + j);
+            if (__any_sync(0xffffffffu, qn == kInsQueue)) topk_drain(best, K, s_q, qn, worst);
         }
+        topk_drain(best, K, s_q, qn, worst);
     }
     if (qi < capacity) {
         int* oi = out_idx + ((size_t)img * capacity + qi) * K;
@@ -384,7 +402,10 @@ __device__ __forceinline__ void replay_scan(const uint32_t* __restrict__ qd, con
     }
 }
 
-constexpr int kRescanBatch = 3;              // stream matcher: queries served by one pass over the previous image
+// Queries served by one pass over the previous image.  3 (the pass also serving the next undecided queries of the chunk) was measured on
+// the Lafida stream: 2.33 ms against 2.14 ms with 1 -- a pass is not purely latency-bound (8 entries x 50 instructions per thread and
+// query), and the look-ahead results are often invalidated by the matches in between.  The code path stays (R is a template parameter).
+constexpr int kRescanBatch = 1;
 // decision of one query from its K-best list under the current matched bits, evaluated by a single lane (look-ahead only)
 __device__ __forceinline__ int list_code(const int* li, const int* ld, const int K, const unsigned* s_taken, const int th_low, const double nnratio) {
     int best1 = 0x7FFFFFFF, best2 = 0x7FFFFFFF, found = 0, dK = 0x7FFFFFFF;
@@ -632,7 +653,7 @@ __device__ __forceinline__ void replay_helper(CoopSeg* cs, const int* log, const
 
 // Stream matcher: one CTA per image; queries = the image's slots, database = the same camera's image one frame earlier.
 template <int WORDS, bool MASKED>
-__global__ void __launch_bounds__(kReplayThreads, 3)      // all images of a 128-frame step resident at once (3 x 148 CTAs)
+__global__ void __launch_bounds__(kReplayThreads)
 stream_replay_kernel(const int* __restrict__ list_idx, const int* __restrict__ list_dist, const int* __restrict__ counts,
                      const uint32_t* __restrict__ desc, const uint32_t* __restrict__ dmask,
                      const int n_cams, const int capacity, const int K, const int img_lo, const int th_low, const double nnratio,
