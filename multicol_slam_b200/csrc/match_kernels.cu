@@ -87,37 +87,11 @@ __device__ __forceinline__ unsigned hamming_words(const uint32_t (&qw)[WORDS], c
     return dist;
 }
 
-// ---- deferred insertion into the per-thread K-best list ---------------------------------------------------------------------
-// A pair whose distance beats the current K-th best (and the relevance bound) has to be inserted into the owning thread's sorted
-// register list.  Doing that on the spot runs the whole insertion sequence with one or two active lanes whenever ANY lane of the
-// warp has a candidate (ncu on the greedy stream matcher: 17 % of the kernel's warp instructions at 1.4 active lanes).  Instead a
-// candidate is parked in a small per-thread queue in shared memory and the queues are drained by all lanes together when one of
-// them is full (or the tile ends): the same insertions, issued with most lanes active.  Until a drain `worst` is stale, which
-// only lets a few more candidates through; the list content is identical (sorted insertion by (distance, index) keys).
-constexpr int kInsQueue = 4;
-__device__ __forceinline__ void topk_insert(unsigned long long (&best)[kTopKMax], const int K, unsigned long long key) {
-#pragma unroll
-    for (int k = 0; k < kTopKMax; ++k) {
-        if (k < K && key < best[k]) { const unsigned long long t = best[k]; best[k] = key; key = t; }
-    }
-}
-__device__ __forceinline__ unsigned topk_worst(const unsigned long long (&best)[kTopKMax], const int K) {
-    unsigned long long w = best[0];
-#pragma unroll
-    for (int k = 1; k < kTopKMax; ++k) if (k < K) w = best[k];
-    return (w == kNoKey) ? 0xFFFFFFFFu : (unsigned)(w >> 32);
-}
-__device__ __forceinline__ void topk_drain(unsigned long long (&best)[kTopKMax], const int K, unsigned long long (*s_q)[kTopkThreads], int& qn,
-                                           unsigned& worst) {
-#pragma unroll
-    for (int c = 0; c < kInsQueue; ++c)
-        if (c < qn) topk_insert(best, K, s_q[c][threadIdx.x]);
-    qn = 0;
-    worst = topk_worst(best, K);
-}
-
+// (Parking candidates in a per-thread shared-memory queue and inserting them with all lanes together -- the insertion below runs
+// with 1.4 active lanes on average and is 17 % of the warp instructions of the greedy stream matcher -- was measured: 6.24 ms
+// against 4.66 ms; the vote + queue traffic per pair costs more than the divergent insertions.)
 template <int WORDS, bool MASKED>
-__global__ void __launch_bounds__(kTopkThreads, 6)
+__global__ void __launch_bounds__(kTopkThreads)
 hamming_topk_kernel(const uint32_t* __restrict__ q, const uint32_t* __restrict__ qmask, const int nq,
                     const uint32_t* __restrict__ d, const uint32_t* __restrict__ dmask, const int nd,
                     const uint8_t* __restrict__ skip, const int K, const int chunk, const unsigned bound,
@@ -125,8 +99,6 @@ hamming_topk_kernel(const uint32_t* __restrict__ q, const uint32_t* __restrict__
     __shared__ __align__(16) uint32_t s_d[kDbTile * WORDS];
     __shared__ __align__(16) uint32_t s_m[MASKED ? kDbTile * WORDS : 4];
     __shared__ uint8_t s_skip[kDbTile];
-    __shared__ unsigned long long s_q[kInsQueue][kTopkThreads];
-    int qn = 0;
 
     const int qi = blockIdx.x * kTopkThreads + threadIdx.x;
     const bool active = qi < nq;
@@ -162,11 +134,18 @@ hamming_topk_kernel(const uint32_t* __restrict__ q, const uint32_t* __restrict__
             // bit-level Hamming distance; masked form = (popc(x&ma) + popc(x&mb)) / 2, integer division (ref :2472)
             unsigned dist = hamming_words<WORDS, MASKED>(qw, qm, s_d + j * WORDS, s_m + j * WORDS);
             if (MASKED) dist >>= 1;
-            if (dist < min(worst, bound))              // strict: equal distances keep the earlier index; entries at or beyond `bound` are not listed
-                s_q[qn++][threadIdx.x] = ((unsigned long long)dist << 32) | (unsigned)(t0 + j);
-            if (__any_sync(0xffffffffu, qn == kInsQueue)) topk_drain(best, K, s_q, qn, worst);
+            if (dist < min(worst, bound)) {            // strict: equal distances keep the earlier index; entries at or beyond `bound` are not listed
+                unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)(t0 + j);
+#pragma unroll
+                for (int k = 0; k < kTopKMax; ++k) {
+                    if (k < K && key < best[k]) { const unsigned long long t = best[k]; best[k] = key; key = t; }
+                }
+                unsigned long long w = best[0];
+#pragma unroll
+                for (int k = 1; k < kTopKMax; ++k) if (k < K) w = best[k];
+                worst = (w == kNoKey) ? 0xFFFFFFFFu : (unsigned)(w >> 32);
+            }
         }
-        topk_drain(best, K, s_q, qn, worst);
     }
     if (active) {
         unsigned long long* o = part + ((size_t)blockIdx.y * nq + qi) * kTopKMax;
@@ -242,14 +221,12 @@ cudaError_t launch_hamming_topk(const uint8_t* q, const uint8_t* qmask, int nq, 
 // One thread owns one query; the (<= capacity) database descriptors of the previous frame are staged tile by
 // tile in shared memory.  Output: K best (index, distance) per query slot, (-1, INT_MAX) where none.
 template <int WORDS, bool MASKED>
-__global__ void __launch_bounds__(kTopkThreads, 6)
+__global__ void __launch_bounds__(kTopkThreads)
 hamming_stream_kernel(const uint32_t* __restrict__ desc, const uint32_t* __restrict__ dmask, const int* __restrict__ counts,
                       const int n_cams, const int capacity, const int K, const int img_lo, const unsigned bound,
                       int* __restrict__ out_idx, int* __restrict__ out_dist) {
     __shared__ __align__(16) uint32_t s_d[kDbTile * WORDS];
     __shared__ __align__(16) uint32_t s_m[MASKED ? kDbTile * WORDS : 4];
-    __shared__ unsigned long long s_q[kInsQueue][kTopkThreads];
-    int qn = 0;
     const int img = blockIdx.y + img_lo;
     const int qi = blockIdx.x * kTopkThreads + threadIdx.x;
     const bool has_prev = img >= n_cams;                 // frame 0 has no predecessor
@@ -296,11 +273,18 @@ hamming_stream_kernel(const uint32_t* __restrict__ desc, const uint32_t* __restr
             // bit-level Hamming distance; masked form = (popc(x&ma) + popc(x&mb)) / 2, integer division (ref :2472)
             unsigned dist = hamming_words<WORDS, MASKED>(qw, qm, s_d + j * WORDS, s_m + j * WORDS);
             if (MASKED) dist >>= 1;
-            if (dist < min(worst, bound))
-                s_q[qn++][threadIdx.x] = ((unsigned long long)dist << 32) | (unsigned)(t0 + j);
-            if (__any_sync(0xffffffffu, qn == kInsQueue)) topk_drain(best, K, s_q, qn, worst);
+            if (dist < min(worst, bound)) {
+                unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)(t0 + j);
+#pragma unroll
+                for (int k = 0; k < kTopKMax; ++k) {
+                    if (k < K && key < best[k]) { const unsigned long long t = best[k]; best[k] = key; key = t; }
+                }
+                unsigned long long w = best[0];
+#pragma unroll
+                for (int k = 1; k < kTopKMax; ++k) if (k < K) w = best[k];
+                worst = (w == kNoKey) ? 0xFFFFFFFFu : (unsigned)(w >> 32);
+            }
         }
-        topk_drain(best, K, s_q, qn, worst);
     }
     if (qi < capacity) {
         int* oi = out_idx + ((size_t)img * capacity + qi) * K;
