@@ -491,6 +491,8 @@ def test_packed_extraction_replay_and_device_bruteforce(api, oa, cams):
         # short lists force the in-kernel rescan of undecidable queries: the result must not depend on K
         idx1, dist1 = api.match_stream_device(out["desc"], out["dmask"], out["counts"], Fn, nc, K=1, stream=st)
         m12b, nmb, _ = api.match_stream_replay_device(idx1, dist1, out["counts"], out["desc"], out["dmask"], Fn, nc, 32, 0.9, stream=st)
+        idx8, dist8 = api.match_stream_device(out["desc"], out["dmask"], out["counts"], Fn, nc, K=8, stream=st)      # the 8-entry list kernel
+        m12d, nmd, _ = api.match_stream_replay_device(idx8, dist8, out["counts"], out["desc"], out["dmask"], Fn, nc, 32, 0.9, stream=st)
         # lists + replay as one call, the lists cut at the relevance bound of (th_low, nnratio): same matches; also for other
         # thresholds, including ones where the bound exceeds every possible distance
         m12c, nmc = api.match_stream_greedy_device(out["desc"], out["dmask"], out["counts"], Fn, nc, 32, 0.9, stream=st)
@@ -503,6 +505,8 @@ def test_packed_extraction_replay_and_device_bruteforce(api, oa, cams):
     torch.cuda.synchronize(dev)
     assert torch.equal(m12, m12b) and torch.equal(nm, nmb)
     assert torch.equal(m12, m12c) and torch.equal(nm, nmc)
+    assert torch.equal(m12, m12d) and torch.equal(nm, nmd)
+    assert torch.equal(idx8[:, :, :4], idx) and torch.equal(dist8[:, :, :4], dist)        # the first four of eight = the four-entry lists
     for a, b in other:
         assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
     assert len({int(a[1].sum().item()) for a, _ in other} | {int(nm.sum().item())}) >= 4     # the sweep is not vacuous: the rules differ
