@@ -90,12 +90,15 @@ __device__ __forceinline__ unsigned hamming_words(const uint32_t (&qw)[WORDS], c
 // (Parking candidates in a per-thread shared-memory queue and inserting them with all lanes together -- the insertion below runs
 // with 1.4 active lanes on average and is 17 % of the warp instructions of the greedy stream matcher -- was measured: 6.24 ms
 // against 4.66 ms; the vote + queue traffic per pair costs more than the divergent insertions.)
-template <int WORDS, bool MASKED>
+// Keys are 32 bits: distance << kTopkShift | database index (index < 2^21, distance <= 512), the list length KT is a compile-time
+// constant (4 or 8): see hamming_stream_kernel.
+constexpr int kTopkShift = 21;
+template <int WORDS, bool MASKED, int KT>
 __global__ void __launch_bounds__(kTopkThreads)
 hamming_topk_kernel(const uint32_t* __restrict__ q, const uint32_t* __restrict__ qmask, const int nq,
                     const uint32_t* __restrict__ d, const uint32_t* __restrict__ dmask, const int nd,
                     const uint8_t* __restrict__ skip, const int K, const int chunk, const unsigned bound,
-                    unsigned long long* __restrict__ part /* [splits][nq][kTopKMax] */) {
+                    unsigned* __restrict__ part /* [splits][nq][kTopKMax] */) {
     __shared__ __align__(16) uint32_t s_d[kDbTile * WORDS];
     __shared__ __align__(16) uint32_t s_m[MASKED ? kDbTile * WORDS : 4];
     __shared__ uint8_t s_skip[kDbTile];
@@ -108,10 +111,11 @@ hamming_topk_kernel(const uint32_t* __restrict__ q, const uint32_t* __restrict__
         qw[k] = active ? q[(size_t)qi * WORDS + k] : 0u;
         if (MASKED) qm[k] = active ? qmask[(size_t)qi * WORDS + k] : 0u;
     }
-    unsigned long long best[kTopKMax];
+    constexpr unsigned kNone = 0xFFFFFFFFu;
+    unsigned best[KT];
 #pragma unroll
-    for (int k = 0; k < kTopKMax; ++k) best[k] = kNoKey;
-    unsigned worst = 0xFFFFFFFFu;          // distance of the current K-th best
+    for (int k = 0; k < KT; ++k) best[k] = kNone;
+    unsigned worst = min(bound, 0x7FFu);   // a pair is listed only below the K-th best so far and the caller's bound
 
     const int j0 = blockIdx.y * chunk, j1 = min(j0 + chunk, nd);
     for (int t0 = j0; t0 < j1; t0 += kDbTile) {
@@ -134,55 +138,56 @@ hamming_topk_kernel(const uint32_t* __restrict__ q, const uint32_t* __restrict__
             // bit-level Hamming distance; masked form = (popc(x&ma) + popc(x&mb)) / 2, integer division (ref :2472)
             unsigned dist = hamming_words<WORDS, MASKED>(qw, qm, s_d + j * WORDS, s_m + j * WORDS);
             if (MASKED) dist >>= 1;
-            if (dist < min(worst, bound)) {            // strict: equal distances keep the earlier index; entries at or beyond `bound` are not listed
-                unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)(t0 + j);
+            if (dist < worst) {            // strict: equal distances keep the earlier index; entries at or beyond `bound` are not listed
+                unsigned key = (dist << kTopkShift) | (unsigned)(t0 + j);
 #pragma unroll
-                for (int k = 0; k < kTopKMax; ++k) {
-                    if (k < K && key < best[k]) { const unsigned long long t = best[k]; best[k] = key; key = t; }
+                for (int k = 0; k < KT; ++k) {
+                    if (k < K) { const unsigned lo = min(key, best[k]); key = max(key, best[k]); best[k] = lo; }
                 }
-                unsigned long long w = best[0];
+                unsigned w = best[0];
 #pragma unroll
-                for (int k = 1; k < kTopKMax; ++k) if (k < K) w = best[k];
-                worst = (w == kNoKey) ? 0xFFFFFFFFu : (unsigned)(w >> 32);
+                for (int k = 1; k < KT; ++k) if (k < K) w = best[k];
+                if (w != kNone) worst = min(worst, w >> kTopkShift);
             }
         }
     }
     if (active) {
-        unsigned long long* o = part + ((size_t)blockIdx.y * nq + qi) * kTopKMax;
+        unsigned* o = part + ((size_t)blockIdx.y * nq + qi) * kTopKMax;
 #pragma unroll
-        for (int k = 0; k < kTopKMax; ++k) o[k] = best[k];
+        for (int k = 0; k < kTopKMax; ++k) o[k] = k < KT ? best[k < KT ? k : 0] : kNone;
     }
 }
 
-__global__ void topk_merge_kernel(const unsigned long long* __restrict__ part, const int splits, const int nq, const int K,
+__global__ void topk_merge_kernel(const unsigned* __restrict__ part, const int splits, const int nq, const int K,
                                   int* __restrict__ topk_idx, int* __restrict__ topk_dist) {
     const int qi = blockIdx.x * blockDim.x + threadIdx.x;
     if (qi >= nq) return;
-    unsigned long long best[kTopKMax];
+    constexpr unsigned kNone = 0xFFFFFFFFu;
+    unsigned best[kTopKMax];
 #pragma unroll
-    for (int k = 0; k < kTopKMax; ++k) best[k] = kNoKey;
+    for (int k = 0; k < kTopKMax; ++k) best[k] = kNone;
     for (int s = 0; s < splits; ++s) {
-        const unsigned long long* p = part + ((size_t)s * nq + qi) * kTopKMax;
+        const unsigned* p = part + ((size_t)s * nq + qi) * kTopKMax;
         for (int i = 0; i < K; ++i) {
-            unsigned long long key = p[i];
-            if (key == kNoKey) break;
+            unsigned key = p[i];
+            if (key == kNone) break;
 #pragma unroll
             for (int k = 0; k < kTopKMax; ++k) {
-                if (k < K && key < best[k]) { const unsigned long long t = best[k]; best[k] = key; key = t; }
+                if (k < K) { const unsigned lo = min(key, best[k]); key = max(key, best[k]); best[k] = lo; }
             }
         }
     }
     for (int k = 0; k < K; ++k) {
-        const bool none = best[k] == kNoKey;
-        topk_idx[(size_t)qi * K + k] = none ? -1 : (int)(best[k] & 0xFFFFFFFFull);
-        topk_dist[(size_t)qi * K + k] = none ? 0x7FFFFFFF : (int)(best[k] >> 32);
+        const bool none = best[k] == kNone;
+        topk_idx[(size_t)qi * K + k] = none ? -1 : (int)(best[k] & ((1u << kTopkShift) - 1u));
+        topk_dist[(size_t)qi * K + k] = none ? 0x7FFFFFFF : (int)(best[k] >> kTopkShift);
     }
 }
 
 cudaError_t launch_hamming_topk(const uint8_t* q, const uint8_t* qmask, int nq, const uint8_t* d, const uint8_t* dmask,
                                 int nd, const uint8_t* db_skip, int dim, int K, unsigned bound, int* topk_idx, int* topk_dist,
                                 cudaStream_t st) {
-    if (K < 1 || K > kTopKMax || (dim != 16 && dim != 32 && dim != 64)) return cudaErrorInvalidValue;
+    if (K < 1 || K > kTopKMax || (dim != 16 && dim != 32 && dim != 64) || nd >= (1 << kTopkShift)) return cudaErrorInvalidValue;
     if (nq <= 0) return cudaSuccess;
     const int qblocks = (nq + kTopkThreads - 1) / kTopkThreads;
     int dev = 0, sms = 148;
@@ -196,19 +201,21 @@ cudaError_t launch_hamming_topk(const uint8_t* q, const uint8_t* qmask, int nq, 
     splits = max(1, (nd + chunk - 1) / chunk);
     // partial top-K lists of the database splits: stream-ordered scratch owned by THIS call (cudaMallocAsync pool), so that
     // concurrent callers -- the reference runs its matchers from three threads -- and different streams never share it
-    const size_t need = (size_t)splits * nq * kTopKMax * sizeof(unsigned long long);
-    unsigned long long* g_part = nullptr;
+    const size_t need = (size_t)splits * nq * kTopKMax * sizeof(unsigned);
+    unsigned* g_part = nullptr;
     cudaError_t e = keep_pool_memory();
     if (e != cudaSuccess) return e;
     e = cudaMallocAsync((void**)&g_part, need, st);
     if (e != cudaSuccess) return e;
     dim3 grid(qblocks, splits);
     const bool masked = qmask && dmask;
-#define MCS_TOPK(W, M) hamming_topk_kernel<W, M><<<grid, kTopkThreads, 0, st>>>((const uint32_t*)q, (const uint32_t*)qmask, nq, \
+#define MCS_TOPK2(W, M, KT) hamming_topk_kernel<W, M, KT><<<grid, kTopkThreads, 0, st>>>((const uint32_t*)q, (const uint32_t*)qmask, nq, \
         (const uint32_t*)d, (const uint32_t*)dmask, nd, db_skip, K, chunk, bound, g_part)
-    if (dim == 16) { if (masked) MCS_TOPK(4, true); else MCS_TOPK(4, false); }
-    else if (dim == 32) { if (masked) MCS_TOPK(8, true); else MCS_TOPK(8, false); }
-    else { if (masked) MCS_TOPK(16, true); else MCS_TOPK(16, false); }
+#define MCS_TOPK(W, M) { if (K <= 4) MCS_TOPK2(W, M, 4); else MCS_TOPK2(W, M, 8); }
+    if (dim == 16) { if (masked) MCS_TOPK(4, true) else MCS_TOPK(4, false) }
+    else if (dim == 32) { if (masked) MCS_TOPK(8, true) else MCS_TOPK(8, false) }
+    else { if (masked) MCS_TOPK(16, true) else MCS_TOPK(16, false) }
+#undef MCS_TOPK2
 #undef MCS_TOPK
     topk_merge_kernel<<<(nq + 127) / 128, 128, 0, st>>>(g_part, splits, nq, K, topk_idx, topk_dist);
     e = cudaGetLastError();

@@ -140,6 +140,7 @@ int mcs_hamming_topk_device(const uint8_t* q_dev, const uint8_t* qmask_dev, int3
     if (!q_dev || !d_dev || !topk_idx_dev || !topk_dist_dev) return mfail(MCS_ERR_INVALID, "null argument");
     if (nq < 0 || nd < 0 || K < 1 || K > 8) return mfail(MCS_ERR_INVALID, "bad sizes (K must be 1..8)");
     if (dim != 16 && dim != 32 && dim != 64) return mfail(MCS_ERR_INVALID, "dim must be 16, 32 or 64");
+    if (nd >= (1 << 21)) return mfail(MCS_ERR_UNSUPPORTED, "more than 2^21 - 1 database descriptors in one call (split the database)");
     MCK(launch_hamming_topk(q_dev, qmask_dev, nq, d_dev, dmask_dev, nd, db_skip_dev, dim, K, 0xFFFFFFFFu, topk_idx_dev, topk_dist_dev,
                             (cudaStream_t)stream));
     return MCS_OK;
