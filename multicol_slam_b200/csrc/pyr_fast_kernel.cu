@@ -51,6 +51,9 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
                  ::"r"(smem_u32(dst)), "l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 
+#ifndef MCS_K1_MINB
+#define MCS_K1_MINB 5                        // resident CTAs per SM the register budget is cut for (6 needs <= 40 registers)
+#endif
 #ifndef MCS_K1_TMA
 #define MCS_K1_TMA 1                         // 0: stage the source region with __ldg + st.shared (A/B builds)
 #endif
@@ -91,7 +94,7 @@ __device__ __forceinline__ unsigned fast_margin2(unsigned C, const unsigned (&E)
     return __vmaxs2(__vsub2(bright, C), __vsub2(C, darkn)); // values in 0..255: no 16-bit overflow
 }
 
-__global__ void __launch_bounds__(kThreads, 5)
+__global__ void __launch_bounds__(kThreads, MCS_K1_MINB)
 pyr_fast_kernel(const __grid_constant__ CUtensorMap src_map, const int use_tma,
                 const LevelGeom g, const int level, const int nlevels, const int fast_th, const int src_aligned,
                 const uint8_t* __restrict__ src, const size_t src_img_bytes,
@@ -110,13 +113,16 @@ pyr_fast_kernel(const __grid_constant__ CUtensorMap src_map, const int use_tma,
     __shared__ int16_t s_ys0[kTileH], s_ys1[kTileH], s_yb0[kTileH], s_yb1[kTileH];
     __shared__ int16_t s_cellx[kTW + 2], s_celly[kTH + 2];
     __shared__ int16_t s_mx[kTW], s_my[kTH];                          // level-0 mask coordinates of the tile's pixels
-    __shared__ uint32_t s_list[(kThreads / 32) * kWarpCorners];       // one segment per warp: no atomics while collecting
     __shared__ int s_wn[kThreads / 32], s_base;
 
     // 16-bit score tiles (two copies offset by one pixel, like the pixel tiles); they reuse the source staging
     // area, which is dead once the tile has been resized
     uint16_t* s_s0 = (uint16_t*)s_src;                                  // s_s0[y][x] = score(x),   x = score-tile column
     uint16_t* s_s1 = (uint16_t*)s_src + (kTH + 2) * kScoreS;            // s_s1[y][i] = score(i+1)
+    // corner list, one segment per warp (no atomics while collecting): lives in the 16-bit pixel tile, which is dead once the FAST
+    // margins are computed (phases b, c; the barrier before phase d separates them from phase e)
+    uint32_t* s_list = (uint32_t*)s_a0;
+    static_assert((kThreads / 32) * kWarpCorners * 4 <= kTileH * kT16S * 2, "corner list must fit into the dead pixel tile");
     static_assert(2 * (kTH + 2) * kScoreS * 2 <= kSrcH * kSrcWB, "score tiles must fit into the staging area");
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int b = blockIdx.z;
