@@ -291,20 +291,27 @@ int upload_small_inputs(mcs_extractor* ex, int W, int H, const uint8_t* masks, c
     if (!ex->tile_flags_valid) {
         // per camera and K1 tile: does the tile hold a pixel whose (nearest-neighbour chained) mask value is set?
         const PyramidGeom& G = ex->G;
-        std::vector<uint8_t> flags((size_t)n_cams * G.tiles_total, 0);
+        // 0 = no pixel of the tile is inside the mask (FAST / NMS skipped), 1 = some are, 2 = all are (no per-corner mask lookup)
+        std::vector<uint8_t> flags((size_t)n_cams * G.tiles_total, 0), all_in((size_t)n_cams * G.tiles_total, 1);
         for (int c = 0; c < n_cams; ++c) {
             const uint8_t* m0 = ex->masks_host.data() + (size_t)c * W * H;
             for (int l = 0; l < G.nlevels; ++l) {
                 const LevelGeom& g = G.lv[l];
                 uint8_t* f = flags.data() + (size_t)c * G.tiles_total + g.tile_off;
+                uint8_t* a = all_in.data() + (size_t)c * G.tiles_total + g.tile_off;
                 for (int y = 0; y < g.h; ++y) {
                     const uint8_t* mrow = m0 + (size_t)ex->h_my[l][y] * W;
                     uint8_t* frow = f + (size_t)(y / kTH) * g.tiles_x;
-                    for (int x = 0; x < g.w; ++x) frow[x / kTW] |= mrow[ex->h_mx[l][x]];
+                    uint8_t* arow = a + (size_t)(y / kTH) * g.tiles_x;
+                    for (int x = 0; x < g.w; ++x) {
+                        const uint8_t m = mrow[ex->h_mx[l][x]];
+                        frow[x / kTW] |= m;
+                        if (!m) arow[x / kTW] = 0;
+                    }
                 }
             }
         }
-        for (auto& v : flags) v = v ? 1 : 0;
+        for (size_t i = 0; i < flags.size(); ++i) flags[i] = flags[i] ? (all_in[i] ? 2 : 1) : 0;
         CK(cudaStreamSynchronize(st));                     // a previous call may still read the old flags
         CK(ex->tile_flags.ensure(flags.size()));
         CK(cudaMemcpyAsync(ex->tile_flags.p, flags.data(), flags.size(), cudaMemcpyHostToDevice, st));

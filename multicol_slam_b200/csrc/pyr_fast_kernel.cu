@@ -52,7 +52,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
 }
 
 #ifndef MCS_K1_MINB
-#define MCS_K1_MINB 5                        // resident CTAs per SM the register budget is cut for (6 needs <= 40 registers)
+#define MCS_K1_MINB 6                        // resident CTAs per SM the register budget is cut for (6 needs <= 40 registers)
 #endif
 #ifndef MCS_K1_TMA
 #define MCS_K1_TMA 1                         // 0: stage the source region with __ldg + st.shared (A/B builds)
@@ -131,7 +131,8 @@ pyr_fast_kernel(const __grid_constant__ CUtensorMap src_map, const int use_tma,
     // FAST + NMS only where the tile holds at least one pixel inside the camera's mask: a corner is reported only if its own
     // mask pixel is set (mask applied after NMS), and the scores of its 8 neighbours come from this CTA's own halo
     const int cam_b = cam_of_image[b];
-    const bool fast_on = tile_flags[(size_t)cam_b * tiles_total + g.tile_off + blockIdx.y * g.tiles_x + blockIdx.x] != 0;
+    const int tile_flag = tile_flags[(size_t)cam_b * tiles_total + g.tile_off + blockIdx.y * g.tiles_x + blockIdx.x];
+    const bool fast_on = tile_flag != 0, mask_full = tile_flag == 2;      // 2: every pixel of the tile is inside the mask
 
     // output-space range needed by this tile; after REFLECT_101 everything lies inside it
     const int xa = max(X0 - kHalo, 0), xb = min(X0 + kTW + kHalo, g.w) - 1;
@@ -334,9 +335,11 @@ pyr_fast_kernel(const __grid_constant__ CUtensorMap src_map, const int use_tma,
         bool k0 = sv0 > (int)(nm & 0xFFFFu), k1 = sv1 > (int)(nm >> 16);
         unsigned b0 = __ballot_sync(0xffffffffu, k0), b1 = __ballot_sync(0xffffffffu, k1);
         if (b0 | b1) {                                                           // warp-uniform: some pixel of this row segment is a maximum
-            if (k0) k0 = m0p[(size_t)s_my[y] * mask_w + s_mx[2 * j]] != 0;
-            if (k1) k1 = m0p[(size_t)s_my[y] * mask_w + s_mx[2 * j + 1]] != 0;
-            b0 = __ballot_sync(0xffffffffu, k0); b1 = __ballot_sync(0xffffffffu, k1);
+            if (!mask_full) {                                                    // CTA-uniform: tiles on the mask border only
+                if (k0) k0 = m0p[(size_t)s_my[y] * mask_w + s_mx[2 * j]] != 0;
+                if (k1) k1 = m0p[(size_t)s_my[y] * mask_w + s_mx[2 * j + 1]] != 0;
+                b0 = __ballot_sync(0xffffffffu, k0); b1 = __ballot_sync(0xffffffffu, k1);
+            }
             const int n0 = __popc(b0);
             const unsigned lt = (1u << lane) - 1u;
             uint32_t* wl = s_list + wid * kWarpCorners + wn;
