@@ -17,7 +17,6 @@ namespace mcs {
 constexpr int kTopKMax = 8;
 constexpr int kDbTile = 256;
 constexpr int kTopkThreads = 128;
-constexpr unsigned long long kNoKey = 0xFFFFFFFFFFFFFFFFull;
 
 
 // ---- bit-sliced population count (Harley-Seal carry-save adders) -------------------------------------------------
@@ -45,17 +44,31 @@ __device__ __forceinline__ unsigned popc_sum8(const uint32_t (&w)[8]) {
 // 16 words (masked distance): two carry-save levels on the ones, none on the twos -- 14 LOP3 + 9 POPC.  ALU (LOP3/IADD, 64 lanes/clk/SM)
 // and XU (POPC, 16 lanes/clk/SM) run concurrently, so the cheapest split loads both about equally; measured on the stream
 // matcher (381 x 2000 x 2000 masked pairs): full tree 22 LOP3 + 5 POPC 4.62 ms, one level 10 + 11 4.33 ms, this one 4.08 ms.
+#ifndef MCS_M2_TREE
+#define MCS_M2_TREE 0                // 0: 7 carry-save adders + 9 POPC, 1: 5 + 11, 2: 6 + 10 (A/B builds)
+#endif
 __device__ __forceinline__ unsigned popc_sum16(const uint32_t (&w)[16]) {
-    uint32_t s0, c0, s1, c1, s2, c2, s3, c3, s4, c4, a0, b0, a1, b1;
+    uint32_t s0, c0, s1, c1, s2, c2, s3, c3, s4, c4;
     csa(w[0], w[1], w[2], s0, c0);
     csa(w[3], w[4], w[5], s1, c1);
     csa(w[6], w[7], w[8], s2, c2);
     csa(w[9], w[10], w[11], s3, c3);
     csa(w[12], w[13], w[14], s4, c4);
+#if MCS_M2_TREE == 1
+    const unsigned ones = __popc(s0) + __popc(s1) + __popc(s2) + __popc(s3) + __popc(s4) + __popc(w[15]);
+    const unsigned twos = __popc(c0) + __popc(c1) + __popc(c2) + __popc(c3) + __popc(c4);
+#elif MCS_M2_TREE == 2
+    uint32_t a0, b0;
+    csa(s0, s1, s2, a0, b0);
+    const unsigned ones = __popc(a0) + __popc(s3) + __popc(s4) + __popc(w[15]);
+    const unsigned twos = __popc(c0) + __popc(c1) + __popc(c2) + __popc(c3) + __popc(c4) + __popc(b0);
+#else
+    uint32_t a0, b0, a1, b1;
     csa(s0, s1, s2, a0, b0);
     csa(s3, s4, w[15], a1, b1);
     const unsigned ones = __popc(a0) + __popc(a1);
     const unsigned twos = __popc(c0) + __popc(c1) + __popc(c2) + __popc(c3) + __popc(c4) + __popc(b0) + __popc(b1);
+#endif
     return ones + 2 * twos;
 }
 // sum over k of popc(x_k) [unmasked] or popc(x_k & qm_k) + popc(x_k & dm_k) [masked, before the /2], x_k = q_k ^ d_k
