@@ -351,7 +351,10 @@ cudaError_t launch_hamming_stream(const uint8_t* desc, const uint8_t* dmask, con
 //   none is: rejected if dK >= th_low.
 // Otherwise the warp rescans the whole previous image for this one query (exact best / second among the unmatched entries), so
 // the result never depends on K; redo[] stays 0 and is kept for interface stability.
-constexpr int kReplayThreads = 256;          // stream matcher: <= 65535 database entries per image, many images in flight
+#ifndef MCS_REPLAY_THREADS
+#define MCS_REPLAY_THREADS 256
+#endif
+constexpr int kReplayThreads = MCS_REPLAY_THREADS;   // stream matcher: <= 65535 database entries per image, many images in flight
 constexpr int kBfReplayThreads = 1024;       // key-frame database: one CTA per query set scans up to ~1.5 M entries per rescan
 constexpr int kKeyShift = 21;                // rescan keys = distance << 21 | index (index < 2^21, distance <= 512)
 
