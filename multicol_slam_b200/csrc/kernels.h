@@ -88,6 +88,8 @@ struct WindowFrameDev {
 cudaError_t launch_window_search(const WindowFrameDev& f, const mcs_window_query* q, int nq, const uint8_t* qdesc,
                                  const uint8_t* qmask, int max_cand, int* cand_idx, int* cand_dist, int* cand_count,
                                  cudaStream_t st);
+cudaError_t launch_compact_lists(const int* idx, const int* dist, const int* count, const int* off, int nq, int max_cand, int* oidx, int* odist,
+                                 cudaStream_t st);
 
 cudaError_t launch_frame_prepare(const mcs_keypoint* keys, const int* key_cam, int n_keys, const mcs_ocam* cams, int n_cams, float* kx,
                                  float* ky, int* koct, double* rays, int* cell_of, int* cursor, int* cell_start, int* cell_items,

@@ -680,7 +680,8 @@ int mcs_extract_batch(mcs_extractor* ex, int32_t n_images, const uint8_t* images
         rc = pin_ensure(ex->pin_out, ex->pin_out_bytes, o.total, &moved);
         if (rc) return rc;
         if (moved) ex->sf_valid = false;
-        std::memcpy(ex->pin_in, images, in_bytes);
+        // the caller's last row may hold only `width` valid bytes (a cv::Mat ROI with step > width at the end of its allocation)
+        std::memcpy(ex->pin_in, images, in_bytes - (size_t)(stride - width));
         const mcs_extractor::SfKey& k = ex->sf_key;
         bool hit = ex->sf_valid && ex->sf_exec && k.n == n_images && k.w == width && k.h == height && k.stride == stride &&
                    k.capacity == capacity && k.dm == (dmask_out != nullptr) && (int)k.cams.size() == n_cams &&
@@ -741,7 +742,7 @@ int mcs_extract_batch(mcs_extractor* ex, int32_t n_images, const uint8_t* images
         return MCS_OK;
     }
 
-    CK(cudaMemcpyAsync(ex->in_tight.p, images, (size_t)stride * height * n_images, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ex->in_tight.p, images, (size_t)stride * height * n_images - (size_t)(stride - width), cudaMemcpyHostToDevice, st));
     launch_repitch(ex->in_tight.p, stride, ex->in_images.p, dpitch, width, (size_t)height * n_images, st);
     int rc = run_pipeline(ex, n_images, ex->in_images.p, width, height, dpitch, masks, cams, n_cams, cam_of_image, ex->kps.p,
                           ex->desc.p, ex->dmask.p, ex->counts.p, capacity, st);
@@ -1024,7 +1025,8 @@ static int extract_match_stream_impl(mcs_extractor* ex, int32_t n_frames, int32_
         uint8_t* tight = ex->in_tight.p + (size_t)(c & 1) * tight_img * ipc;
         if (c >= 2) CK(cudaStreamWaitEvent(ex->s_copy, ev_free[c - 2], 0));          // staging buffer consumed
         mark(ex->s_copy);
-        CK(cudaMemcpyAsync(tight, images + (size_t)img_lo * tight_img, tight_img * nimg, cudaMemcpyHostToDevice, ex->s_copy));
+        CK(cudaMemcpyAsync(tight, images + (size_t)img_lo * tight_img, tight_img * nimg - (c == n_chunks - 1 ? (size_t)(stride - width) : 0),
+                           cudaMemcpyHostToDevice, ex->s_copy));
         mark(ex->s_copy);
         CK(cudaEventRecord(ev_in[c], ex->s_copy));
         CK(cudaStreamWaitEvent(st, ev_in[c], 0));

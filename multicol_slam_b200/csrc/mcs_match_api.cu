@@ -110,6 +110,50 @@ int window_search_host(const FrameDev& fd, const std::vector<mcs_window_query>& 
     }
 }
 
+// The same search with the candidates returned as ONE dense array in query order: candidates of query q are
+// cidx / cdist [coff[q] .. coff[q + 1]).  Only the counts and the candidates that exist cross PCIe.
+int window_search_compact(const FrameDev& fd, const mcs_window_query* qs, const int nq, const uint8_t* qdesc, const uint8_t* qmask,
+                          size_t qdesc_rows, int dim, std::vector<int>& cidx, std::vector<int>& cdist, std::vector<int>& coff, cudaStream_t st) {
+    coff.assign(nq + 1, 0);
+    cidx.clear(); cdist.clear();
+    if (nq == 0) return MCS_OK;
+    Dev dq, dqd, dqm, dc, doff;
+    MCK(dq.alloc(sizeof(mcs_window_query) * nq));
+    MCK(dqd.alloc(qdesc_rows * dim));
+    MCK(dc.alloc((size_t)nq * 4)); MCK(doff.alloc((size_t)nq * 4));
+    MCK(cudaMemcpyAsync(dq.p, qs, sizeof(mcs_window_query) * nq, cudaMemcpyHostToDevice, st));
+    MCK(cudaMemcpyAsync(dqd.p, qdesc, qdesc_rows * dim, cudaMemcpyHostToDevice, st));
+    const bool masked = qmask && fd.view.dmask;
+    if (masked) {
+        MCK(dqm.alloc(qdesc_rows * dim));
+        MCK(cudaMemcpyAsync(dqm.p, qmask, qdesc_rows * dim, cudaMemcpyHostToDevice, st));
+    }
+    std::vector<int> count(nq);
+    int max_cand = 32;
+    for (;;) {
+        Dev di, dd;
+        MCK(di.alloc((size_t)nq * max_cand * 4)); MCK(dd.alloc((size_t)nq * max_cand * 4));
+        MCK(launch_window_search(fd.view, dq.as<mcs_window_query>(), nq, dqd.as<uint8_t>(), masked ? dqm.as<uint8_t>() : nullptr,
+                                 max_cand, di.as<int>(), dd.as<int>(), dc.as<int>(), st));
+        MCK(cudaMemcpyAsync(count.data(), dc.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+        MCK(cudaStreamSynchronize(st));
+        const int mx = *std::max_element(count.begin(), count.end());
+        if (mx > max_cand) { max_cand = (mx + 31) & ~31; continue; }        // a list overflowed: once more with room for the longest
+        for (int q = 0; q < nq; ++q) coff[q + 1] = coff[q] + count[q];
+        const int total = coff[nq];
+        if (total == 0) return MCS_OK;
+        Dev doi, dod;
+        MCK(doi.alloc((size_t)total * 4)); MCK(dod.alloc((size_t)total * 4));
+        MCK(cudaMemcpyAsync(doff.p, coff.data(), (size_t)nq * 4, cudaMemcpyHostToDevice, st));
+        MCK(launch_compact_lists(di.as<int>(), dd.as<int>(), dc.as<int>(), doff.as<int>(), nq, max_cand, doi.as<int>(), dod.as<int>(), st));
+        cidx.resize(total); cdist.resize(total);
+        MCK(cudaMemcpyAsync(cidx.data(), doi.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+        MCK(cudaMemcpyAsync(cdist.data(), dod.p, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+        MCK(cudaStreamSynchronize(st));
+        return MCS_OK;
+    }
+}
+
 }  // namespace
 
 void mcs_set_error_(const std::string& msg);   // mcs_api.cu
@@ -488,28 +532,26 @@ int mcs_search_windows(const mcs_frame_view* f, const mcs_window_query* queries,
         MCK(cudaMemcpy(fd.cam_first.p, first.data(), first.size() * 4, cudaMemcpyHostToDevice));
         fd.view.cam_first = fd.cam_first.as<int>();
     }
-    std::vector<mcs_window_query> qs(queries, queries + nq);
-    std::vector<int> ci, cd, cc;
-    int mc = 32;
-    rc = window_search_host(fd, qs, qdesc, qmask, rows, f->dim, ci, cd, cc, mc, true, nullptr);
+    std::vector<int> ci, cd, co;
+    rc = window_search_compact(fd, queries, nq, qdesc, qmask, rows, f->dim, ci, cd, co, nullptr);
     if (rc) return rc;
     int nm = 0;
     for (int qi = 0; qi < nq; ++qi) {       // sequential greedy replay over the GPU-computed candidate lists
-        const int n = cc[qi];
+        const int n = co[qi + 1] - co[qi];
         const bool stateless = rule == MCS_RULE_BEST_FREE || rule == MCS_RULE_FIRST_FREE;
         if (n == 0) { if (stateless) assigned[qi] = -1; continue; }
         if (rule == MCS_RULE_FIRST_FREE) {
             // Fuse(pKF, vpMapPoints, th) computes the distance and throws it away (ref :1506-1514: `dist` stays 0), so the first
             // candidate that passes the level filter wins with distance 0 <= TH_LOW_
-            assigned[qi] = 0 <= threshold ? ci[(size_t)qi * mc] : -1;
+            assigned[qi] = 0 <= threshold ? ci[co[qi]] : -1;
             nm += assigned[qi] >= 0;
             continue;
         }
         int bestDist = INT_MAX, bestLevel = -1, bestDist2 = INT_MAX, bestLevel2 = -1, bestIdx = -1;
         for (int k = 0; k < n; ++k) {
-            const int idx = ci[(size_t)qi * mc + k];
+            const int idx = ci[co[qi] + k];
             if (!stateless && assigned[idx] >= 0) continue;
-            const int dist = cd[(size_t)qi * mc + k];
+            const int dist = cd[co[qi] + k];
             if (dist < bestDist) {
                 bestDist2 = bestDist; bestDist = dist; bestLevel2 = bestLevel;
                 bestLevel = f->keys[idx].octave; bestIdx = idx;
@@ -590,18 +632,17 @@ int mcs_search_for_initialization(const mcs_frame_view* f1, const mcs_frame_view
     FrameDev fd;
     int rc = upload_frame(f2, fd, nullptr);
     if (rc) return rc;
-    std::vector<int> ci, cd, cc;
-    int mc = 64;
-    rc = window_search_host(fd, qs, f1->desc, having_masks ? f1->dmask : nullptr, n1, f1->dim, ci, cd, cc, mc, true, nullptr);
+    std::vector<int> ci, cd, co;
+    rc = window_search_compact(fd, qs.data(), n1, f1->desc, having_masks ? f1->dmask : nullptr, n1, f1->dim, ci, cd, co, nullptr);
     if (rc) return rc;
     int nm = 0;
     std::vector<int> matchedDist(f2->n_keys, INT_MAX), matches21(f2->n_keys, -1);
     for (int i1 = 0; i1 < n1; ++i1) {            // ref :599-682
-        const int n = cc[i1];
+        const int n = co[i1 + 1] - co[i1];
         if (n == 0) continue;
         int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
         for (int k = 0; k < n; ++k) {
-            const int i2 = ci[(size_t)i1 * mc + k], dist = cd[(size_t)i1 * mc + k];
+            const int i2 = ci[co[i1] + k], dist = cd[co[i1] + k];
             if (matchedDist[i2] <= dist) continue;
             if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
             else if (dist < bestDist2) bestDist2 = dist;
