@@ -587,6 +587,12 @@ int mcs_search_by_projection(const mcs_frame_view* f, const mcs_mappoint_view* m
     // queries in the reference's visiting order: map point outer, camera inner (ref :74-98)
     std::vector<mcs_window_query> qs;
     std::vector<int> tags;
+    {
+        size_t n_view = 0;
+        const size_t n_all = (size_t)mps->n_points * f->n_cams;
+        for (size_t k = 0; k < n_all; ++k) n_view += mps->in_view[k] != 0;
+        qs.reserve(n_view); tags.reserve(n_view);
+    }
     const bool bFactor = th != 1.0;
     for (int i = 0; i < mps->n_points; ++i) {
         if (mps->bad && mps->bad[i]) continue;
