@@ -26,6 +26,13 @@
 //     (ulp 1.9e-6 at 16..32) is enough: measured worst error 5e-6 px (tools/k3_fp32_model.py, numpy without FMA).  A pattern
 //     with any coordinate closer than kT1Guard = 2.5e-5 px to a rounding tie (or a sample outside the staged patch) falls
 //     through to tier 2;
+//     m-form of tier 1 (centres >= ~64 px, 94 % of the Lafida keypoints): g itself is a smooth function of m = r^2 away from the
+//     centre, and n = m - m_k comes without a square root: with c_i, hw_i centre and half-width of centre i's window in m and
+//     t = (m - c_i) / hw_i in [-1, 1], the host tabulates g - G(c_i) = t P(t) (P of degree 7: 8 float coefficients, fit error
+//     below 1e-6 px in terms of the displacement it multiplies), so that g(r) - g(r_k) = t P(t) - t_k P(t_k) needs no rsqrt, no
+//     reciprocal and no Newton steps: 28 instead of 39 instructions per point.  Same measured error as the s-form (4.7e-6 px,
+//     tools/k3_fp32_model.py MFORM=1); nearer the centre the window is too wide in m (sqrt singularity of the odd part of R at
+//     m = 0) and the s-form above serves;
 //   tier 2 (FP64, degree-9 polynomial of R around the keypoint's radius, |error| < 2e-8 px, two rolled passes: sum, then
 //     recompute + round): decides everything farther than 5e-7 px from a tie; also serves keypoints closer than
 //     kT1MinRadius px to the distortion centre, where g has a pole;
@@ -84,6 +91,9 @@ constexpr int kLutDeg = 9;                        // degree of the per-centre po
 #ifndef MCS_K3_REPAIR
 #define MCS_K3_REPAIR 1              // 0: flagged tier-1 patterns go straight to tier 2 (A/B builds)
 #endif
+#ifndef MCS_K3_V3
+#define MCS_K3_V3 1                  // round-2 instruction diet (0 restores the previous forms for A/B builds): IC-angle disc read from a
+#endif                               // shared-memory copy, warp mean by one integer REDUX, tie / range test as running maxima
 #ifndef MCS_K3_MINB
 #define MCS_K3_MINB 6                // resident CTAs per SM the register budget is cut for (80 registers; 5 -> 96 registers: 6.25 vs 6.19 ms)
 #endif
@@ -93,8 +103,16 @@ constexpr double kT1MinRadius = 40.0;             // tier 1 needs r >= r_k - 21.
 constexpr float kT1Guard = 2.5e-5f;               // px; 5x the worst tier-1 error measured by tools/k3_fp32_model.py
 // doubles per centre: [0] tau offset, [1] tau scale, [2..11] kLutDeg + 1 coefficients (tier 2);
 // [12] R(i), [13] q0 (double), [14..16] q1..q5 as floats (+ one pad float), [17] 1.0 when the tier-1 entry is usable
-constexpr int kLutStride = 18;
 constexpr double kLutReach = 22.5;                // half-width of a centre's interval: pattern radius 15*sqrt(2) + 0.5 + margin
+// [18] G(c_i) (double), [19..22] a0..a7 of the m-form as floats, [23] 1.0 when the m-form entry is usable  (MCS_K3_MFORM)
+constexpr int kLutStride = 24;
+#ifndef MCS_K3_MFORM
+#define MCS_K3_MFORM 1               // tier 1 in the variable m = r^2 where the centre's table allows it (0: always the s-form; A/B builds)
+#endif
+constexpr int kT1MCoef = 8;                       // m-form: g(r) - G(c_i) = t P(t), P of degree 7, t = (r^2 - c_i) / hw_i
+// centre and half-width of centre i's window in m = r^2: r in [i - reach, i + reach]  (i >= reach, checked where the entry is built)
+__host__ __device__ inline double t1m_centre(int i) { return (double)i * (double)i + kLutReach * kLutReach; }
+__host__ __device__ inline double t1m_halfwidth(int i) { return 2.0 * kLutReach * (double)i; }
 
 // Rare path: one pattern of one keypoint with the reference's exact operation sequence (two projection passes;
 // per-lane partial sums + butterfly: within ~1e-13 of the reference's sequential sum).
@@ -389,6 +407,51 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
 
     // ---- IC_Angle (ref :221-248): integer moments over the 845-pixel disc, lane = column u = lane-16 (+ u = 16) ----
     int m10 = 0, m01 = 0;
+#if MCS_K3_V3
+    {
+        // The 33 x 33 neighbourhood of the UNBLURRED level is copied with aligned word loads (3 rows x 10 words per warp
+        // instruction) into this warp's slice of the parking buffer, which tier 1 only uses later; the moments are then summed from
+        // shared memory with compile-time offsets: row pairs +-k share one disc test, m01 += k (val(+k) - val(-k)).
+        constexpr int kIcS = 40;                            // bytes per staged row: 4-byte aligned start + 33 columns
+        uint8_t* ic = reinterpret_cast<uint8_t*>(s_park_dyn + wib * (PPL * 32));
+        const int xs = (kx - kHalfPatch) & ~3;              // >= 0: keypoints lie >= 25 px inside the level
+        {
+            const int rr = lane / 10, w = lane - rr * 10;
+            const uint32_t* gp = (const uint32_t*)(uimg + (size_t)(ky - kHalfPatch + rr) * pitch + xs) + w;
+            uint32_t* sp = (uint32_t*)(ic + rr * kIcS) + w;
+            uint32_t t[11];
+#pragma unroll
+            for (int k = 0; k < 11; ++k) t[k] = (lane < 30) ? __ldg(gp + (size_t)k * 3 * (pitch / 4)) : 0u;
+#pragma unroll
+            for (int k = 0; k < 11; ++k) if (lane < 30) sp[k * 3 * (kIcS / 4)] = t[k];
+        }
+        __syncwarp();
+        const int u = lane - kHalfPatch;                    // -16 .. 15
+        const int au = u < 0 ? -u : u;
+        const int vm = c_disc_u[au];                        // |v| <= vmax(|u|) = umax[|u|]: the disc is symmetric (ref :187-202)
+        const uint8_t* col = ic + kHalfPatch * kIcS + (kx - kHalfPatch - xs) + lane;
+        int sum = col[0];
+#pragma unroll
+        for (int k = 1; k <= kHalfPatch; ++k) {
+            const int a = col[k * kIcS], bb = col[-k * kIcS];
+            if (vm >= k) { sum += a + bb; m01 += k * (a - bb); }
+        }
+        m10 = u * sum;
+        const int um = c_disc_u[kHalfPatch];
+        if (lane < 2 * um + 1) {                            // column u = +16: rows |v| <= umax[16]
+            const int v = lane - um;
+            const int val = ic[(kHalfPatch + v) * kIcS + (kx - kHalfPatch - xs) + 2 * kHalfPatch];
+            m10 += kHalfPatch * val;
+            m01 += v * val;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        }
+        __syncwarp();                                       // the parking buffer is free again
+    }
+#else
     {
         const uint8_t* ctr = uimg + (size_t)ky * pitch + kx;
         const int u = lane - kHalfPatch;                    // -16 .. 15
@@ -413,6 +476,7 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
             m01 += __shfl_xor_sync(0xffffffffu, m01, o);
         }
     }
+#endif
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
     const int ci = cam_of_image[b];
@@ -481,8 +545,23 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
         const bool lane_valid = (PPL == 32) || (lane < ds);      // descSize 16: lanes 16..31 own no byte
         // ---- tier-1 set-up (per keypoint, all lanes redundantly; ~25 FP64 instructions against 48 points x 3 patterns) ----
         bool t1 = MCS_K3_T1 && have_lut && rk >= kT1MinRadius && __ldg(row + 17) == 1.0;
-        float q[kT1Coef], K0f = 0.f, gkf = 0.f, s0f = 0.f, rk2f = 0.f, rkf = 0.f, auk = 0.f, avk = 0.f;
-        if (t1) {
+        const bool mform = MCS_K3_MFORM && t1 && __ldg(row + 23) == 1.0;
+        float q[kT1MCoef], K0f = 0.f, gkf = 0.f, s0f = 0.f, rk2f = 0.f, rkf = 0.f, auk = 0.f, avk = 0.f;
+        if (mform) {
+            // m-form: t_k, K0 = t_k P(t_k), g_k = G(c_i) + K0 in double from the float coefficients the points will use
+            const float2 c01 = __ldg((const float2*)(row + 19)), c23 = __ldg((const float2*)(row + 20));
+            const float2 c45 = __ldg((const float2*)(row + 21)), c67 = __ldg((const float2*)(row + 22));
+            q[0] = c01.x; q[1] = c01.y; q[2] = c23.x; q[3] = c23.y; q[4] = c45.x; q[5] = c45.y; q[6] = c67.x; q[7] = c67.y;
+            const double inv_hw = 1.0 / t1m_halfwidth(ci_lut);
+            const double tk = (rk * rk - t1m_centre(ci_lut)) * inv_hw;
+            double pk = (double)q[7];
+#pragma unroll
+            for (int k = 6; k >= 0; --k) pk = fma(pk, tk, (double)q[k]);
+            const double K0 = tk * pk;
+            gkf = (float)(__ldg(row + 18) + K0);
+            K0f = (float)K0; s0f = (float)tk; rk2f = (float)inv_hw;              // s0f / rk2f double as t_k / (1 / hw) in the m-form
+            auk = (float)(cam.c * ukx + cam.d * uky); avk = (float)(cam.e * ukx + uky);      // A X_k
+        } else if (t1) {
             const double Ri = __ldg(row + 12), q0d = __ldg(row + 13);
             const float2 c12 = __ldg((const float2*)(row + 14)), c34 = __ldg((const float2*)(row + 15)), c5x = __ldg((const float2*)(row + 16));
             q[1] = c12.x; q[2] = c12.y; q[3] = c34.x; q[4] = c34.y; q[5] = c5x.x;
@@ -512,6 +591,23 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                 const float ayx = (float)(cam.e * ca[qi] + sa[qi]), ayy = (float)(ca[qi] - cam.e * sa[qi]);
                 float2* park = s_park_dyn + wib * (PPL * 32);
                 float su = 0.f, sv = 0.f;
+                if (mform) {
+#pragma unroll 4
+                    for (int j = 0; j < PPL; ++j) {
+                        const float2 pp = s_patf[j * 32 + lane];
+                        const float n = fmaf(pp.x, nx, fmaf(pp.y, ny, fmaf(pp.x, pp.x, pp.y * pp.y)));   // m - m_k
+                        const float t = fmaf(n, rk2f, s0f);                       // (m - c_i) / hw_i
+                        float pl = q[kT1MCoef - 1];
+#pragma unroll
+                        for (int k = kT1MCoef - 2; k >= 0; --k) pl = fmaf(pl, t, q[k]);
+                        const float dg = fmaf(t, pl, -K0f);                        // g(r) - g(r_k)
+                        const float g = gkf + dg;
+                        const float du = fmaf(g, fmaf(pp.x, axx, pp.y * axy), dg * auk);   // u - u_k
+                        const float dv = fmaf(g, fmaf(pp.x, ayx, pp.y * ayy), dg * avk);   // v - v_k
+                        park[j * 32 + lane] = make_float2(du, dv);
+                        if (lane_valid) { su += du; sv += dv; }
+                    }
+                } else
 #pragma unroll 4
                 for (int j = 0; j < PPL; ++j) {
                     const float2 pp = s_patf[j * 32 + lane];
@@ -535,17 +631,29 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                     park[j * 32 + lane] = make_float2(du, dv);
                     if (lane_valid) { su += du; sv += dv; }
                 }
-                // mean over the 16*ds points: lane partial sums in fp32 (16..32 terms), the warp reduction in double
+                // mean over the 16*ds points: lane partial sums in fp32 (16..32 terms)
+                const double inv_n = 1.0 / (double)(16 * ds);
+                bool flag = false;
+#if MCS_K3_V3
+                // ... and the warp sum as ONE integer REDUX per coordinate in 2^-17 px fixed point: a lane's rounding is <= 3.8e-6 px,
+                // the mean is off by <= 32 * 3.8e-6 / 512 = 2.4e-7 px (inside the tier-1 error budget, kT1Guard).  A lane sum of 500 px
+                // or more (or a NaN) cannot come from a sane pattern (|du| <= ~22 px) and sends the pattern on, so the 32-bit sum
+                // (< 32 * 500 * 2^17 = 2^31) never wraps.
+                flag = !(fabsf(su) < 500.f) | !(fabsf(sv) < 500.f);
+                const int iu = __reduce_add_sync(0xffffffffu, flag ? 0 : __float2int_rn(su * 131072.f));
+                const int iv = __reduce_add_sync(0xffffffffu, flag ? 0 : __float2int_rn(sv * 131072.f));
+                const float mu = (float)((double)iu * (inv_n * (1.0 / 131072.0))), mv = (float)((double)iv * (inv_n * (1.0 / 131072.0)));
+                float wf = 0.f, wt = 0.f;                                      // running maxima of |fraction - tie| and |offset|
+#else
                 double sud = (double)su, svd = (double)sv;
 #pragma unroll
                 for (int o = 16; o; o >>= 1) {
                     sud += __shfl_xor_sync(0xffffffffu, sud, o);
                     svd += __shfl_xor_sync(0xffffffffu, svd, o);
                 }
-                const double inv_n = 1.0 / (double)(16 * ds);
                 const float mu = (float)(sud * inv_n), mv = (float)(svd * inv_n);
+#endif
                 constexpr float kMagicF = 12582912.f;                          // 1.5 * 2^23: t + magic rounds t to the nearest even integer
-                bool flag = false;
                 unsigned bits0 = 0, bits1 = 0;                                 // descriptor byte(s) of this lane: points 0..15 / 16..31
 #pragma unroll 2
                 for (int j = 0; j < PPL; j += 2) {
@@ -556,9 +664,16 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                         const float tu = c.x - mu, tv = c.y - mv;
                         const float mu_r = tu + kMagicF, mv_r = tv + kMagicF;
                         const float fu = tu - (mu_r - kMagicF), fv = tv - (mv_r - kMagicF);
-                        // near a rounding tie, or outside the staged patch (the comparisons are written so that a NaN flags too)
+                        // near a rounding tie, or outside the staged patch
+#if MCS_K3_V3
+                        // (running maxima, tested once after the loop; a NaN coordinate has already flagged the pattern through its lane sum)
+                        wf = fmaxf(wf, fmaxf(fabsf(fu), fabsf(fv)));
+                        wt = fmaxf(wt, fmaxf(fabsf(tu), fabsf(tv)));
+#else
+                        // (the comparisons are written so that a NaN flags too)
                         flag |= !(fabsf(fu) < 0.5f - kT1Guard) | !(fabsf(fv) < 0.5f - kT1Guard) | !(fabsf(tu) < (float)kPatchR + 0.4f) |
                                 !(fabsf(tv) < (float)kPatchR + 0.4f);
+#endif
                         const int ix = __float_as_int(mu_r) - 0x4B400000, iy = __float_as_int(mv_r) - 0x4B400000;
                         // one clamp of the byte offset keeps the read inside the patch array; an offset that needed it belongs to a
                         // flagged coordinate (|t| >= 25.4) and the pattern is redone
@@ -568,6 +683,9 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                     const unsigned bit = (unsigned)(smp[0] < smp[1]) << ((j & 15) >> 1);
                     if (PPL == 16 || j < 16) bits0 |= bit; else bits1 |= bit;
                 }
+#if MCS_K3_V3
+                flag |= !(wf < 0.5f - kT1Guard) | !(wt < (float)kPatchR + 0.4f);
+#endif
                 if (!__any_sync(0xffffffffu, flag && lane_valid)) {
                     val[qi][0] = bits0;
                     if (BPL > 1) val[qi][BPL - 1] = bits1;
@@ -752,6 +870,48 @@ void build_distort_lut(const mcs_ocam& cam, std::vector<double>& coef, int& n_ou
                 e[12] = (double)Ri; e[13] = q0;
                 std::memcpy(&e[14], &qf[1], sizeof(float) * 6);      // q1..q5 + one zero pad float
                 e[17] = 1.0;
+            }
+        }
+        // ---- m-form entry of tier 1: G(m) = R(sqrt(m)) / sqrt(m) on the centre's window in m = r^2, G(c + hw t) - G(c) = t P(t) with P
+        // of degree kT1MCoef - 1 interpolating at an even number of Chebyshev nodes of [-1, 1] (no node at t = 0).  What the fit error
+        // multiplies is the keypoint's own image offset |A X_k| ~ r_k, so it is accepted below 1e-6 px in those terms -- the same bound
+        // the s-form entry is held to.
+        e[23] = 0.0;
+        if (e[17] == 1.0 && (double)i > kLutReach + 1.0) {
+            constexpr int NM = kT1MCoef;
+            const long double cm = (long double)t1m_centre(i), hm = (long double)t1m_halfwidth(i);
+            auto G_exact = [&](long double m) { const long double r = sqrtl(m); return R_exact(r) / r; };
+            const long double Gc = G_exact(cm);
+            long double B[NM][NM + 1];
+            for (int k = 0; k < NM; ++k) {
+                const long double tn = cosl((2 * k + 1) * 3.14159265358979323846264338327950288L / (2.0L * NM));
+                long double pw = 1.0L;
+                for (int t = 0; t < NM; ++t) { B[k][t] = pw; pw *= tn; }
+                B[k][NM] = (G_exact(cm + hm * tn) - Gc) / tn;
+            }
+            for (int col = 0; col < NM; ++col) {
+                int piv = col;
+                for (int r2 = col + 1; r2 < NM; ++r2) if (fabsl(B[r2][col]) > fabsl(B[piv][col])) piv = r2;
+                for (int t = 0; t <= NM; ++t) std::swap(B[col][t], B[piv][t]);
+                for (int r2 = 0; r2 < NM; ++r2) {
+                    if (r2 == col) continue;
+                    const long double f = B[r2][col] / B[col][col];
+                    for (int t = col; t <= NM; ++t) B[r2][t] -= f * B[col][t];
+                }
+            }
+            float af[NM];
+            for (int t = 0; t < NM; ++t) af[t] = (float)(B[t][NM] / B[t][t]);
+            long double werr = 0.0L;
+            for (int sidx = 0; sidx <= 96; ++sidx) {
+                const long double tv = -1.0L + 2.0L * ((long double)sidx + 0.37L) / 97.0L;
+                long double pv = (long double)af[NM - 1];
+                for (int t = NM - 2; t >= 0; --t) pv = pv * tv + (long double)af[t];
+                werr = std::max(werr, fabsl(tv * pv - (G_exact(cm + hm * tv) - Gc)));
+            }
+            if (werr * ((long double)i + 1.0L) < 1e-6L) {
+                e[18] = (double)Gc;
+                std::memcpy(&e[19], af, sizeof(float) * NM);
+                e[23] = 1.0;
             }
         }
     }

@@ -47,7 +47,7 @@ __device__ __forceinline__ unsigned popc_sum8(const uint32_t (&w)[8]) {
 #ifndef MCS_M2_TREE
 #define MCS_M2_TREE 0                // 0: 7 carry-save adders + 9 POPC, 1: 5 + 11, 2: 6 + 10 (A/B builds)
 #endif
-__device__ __forceinline__ unsigned popc_sum16(const uint32_t (&w)[16]) {
+__device__ __forceinline__ void popc_sum16(const uint32_t (&w)[16], unsigned& ones_out, unsigned& twos_out) {
     uint32_t s0, c0, s1, c1, s2, c2, s3, c3, s4, c4;
     csa(w[0], w[1], w[2], s0, c0);
     csa(w[3], w[4], w[5], s1, c1);
@@ -69,13 +69,15 @@ __device__ __forceinline__ unsigned popc_sum16(const uint32_t (&w)[16]) {
     const unsigned ones = __popc(a0) + __popc(a1);
     const unsigned twos = __popc(c0) + __popc(c1) + __popc(c2) + __popc(c3) + __popc(c4) + __popc(b0) + __popc(b1);
 #endif
-    return ones + 2 * twos;
+    ones_out += ones; twos_out += twos;
 }
-// sum over k of popc(x_k) [unmasked] or popc(x_k & qm_k) + popc(x_k & dm_k) [masked, before the /2], x_k = q_k ^ d_k
+// sum over k of popc(x_k) [unmasked] or (popc(x_k & qm_k) + popc(x_k & dm_k)) / 2 [masked: the integer division of ref :2472
+// applied to the carry-save form, (ones + 2 twos) >> 1 == twos + (ones >> 1)], x_k = q_k ^ d_k
 template <int WORDS, bool MASKED>
 __device__ __forceinline__ unsigned hamming_words(const uint32_t (&qw)[WORDS], const uint32_t* qm, const uint32_t* dd, const uint32_t* dm) {
     unsigned dist = 0;
     if (MASKED) {
+        unsigned ones = 0, twos = 0;
 #pragma unroll
         for (int h = 0; h < WORDS; h += 8) {
             uint32_t w[16];
@@ -86,8 +88,11 @@ __device__ __forceinline__ unsigned hamming_words(const uint32_t (&qw)[WORDS], c
                     w[2 * k + 1] = xor_and(qw[h + k], dd[h + k], dm[h + k]);
                 } else { w[2 * k] = 0; w[2 * k + 1] = 0; }
             }
-            dist += popc_sum16(w);
+            popc_sum16(w, ones, twos);
         }
+        unsigned half;                       // (inline shift: the compiler otherwise wraps the plain `ones >> 1` in two 16-bit masks)
+        asm("shr.u32 %0, %1, 1;" : "=r"(half) : "r"(ones));
+        dist = twos + half;
     } else {
 #pragma unroll
         for (int h = 0; h < WORDS; h += 8) {
@@ -150,7 +155,6 @@ hamming_topk_kernel(const uint32_t* __restrict__ q, const uint32_t* __restrict__
             if (s_skip[j]) continue;       // uniform across the CTA
             // bit-level Hamming distance; masked form = (popc(x&ma) + popc(x&mb)) / 2, integer division (ref :2472)
             unsigned dist = hamming_words<WORDS, MASKED>(qw, qm, s_d + j * WORDS, s_m + j * WORDS);
-            if (MASKED) dist >>= 1;
             if (dist < worst) {            // strict: equal distances keep the earlier index; entries at or beyond `bound` are not listed
                 unsigned key = (dist << kTopkShift) | (unsigned)(t0 + j);
 #pragma unroll
@@ -243,11 +247,18 @@ cudaError_t launch_hamming_topk(const uint8_t* q, const uint8_t* qmask, int nq, 
 // The per-thread list holds 32-bit keys (distance << 16 | slot; slots < 65536, distances <= 512) and its length KT is a compile-time
 // constant (4 or 8): the sorted insertion -- executed by the one or two lanes of a warp that have a candidate -- is 3 instructions
 // per list position instead of ~6 on 64-bit keys over all 8 positions.
-template <int WORDS, bool MASKED, int KT>
+//
+// CAND: every pair below `bound` (the relevance bound of the acceptance rule, kernels.h: greedy_dist_bound) is also appended, in
+// database order, to the query's candidate row (kCandCap keys, row r of image i at cand[(i * capacity + r) * kCandCap]) and
+// counted in cand_cnt -- the count keeps running past kCandCap, so that cnt <= kCandCap PROVES the row holds every database
+// entry that can influence the acceptance.  One thread owns one query: no atomics.  KT == 0: no K-best lists at all (the
+// acceptance kernel below works from the candidate rows alone).
+constexpr int kCandCap = 32;                 // one candidate per lane of the acceptance warp
+template <int WORDS, bool MASKED, int KT, bool CAND>
 __global__ void __launch_bounds__(kTopkThreads)
 hamming_stream_kernel(const uint32_t* __restrict__ desc, const uint32_t* __restrict__ dmask, const int* __restrict__ counts,
                       const int n_cams, const int capacity, const int K, const int img_lo, const unsigned bound,
-                      int* __restrict__ out_idx, int* __restrict__ out_dist) {
+                      int* __restrict__ out_idx, int* __restrict__ out_dist, unsigned* __restrict__ cand, int* __restrict__ cand_cnt) {
     __shared__ __align__(16) uint32_t s_d[kDbTile * WORDS];
     __shared__ __align__(16) uint32_t s_m[MASKED ? kDbTile * WORDS : 4];
     const int img = blockIdx.y + img_lo;
@@ -256,7 +267,7 @@ hamming_stream_kernel(const uint32_t* __restrict__ desc, const uint32_t* __restr
     const int nq = has_prev ? min(counts[img], capacity) : 0;
     const int nd = has_prev ? min(counts[img - n_cams], capacity) : 0;
     if ((int)(blockIdx.x * kTopkThreads) >= nq) {        // nothing to match in this block: mark the slots empty
-        if (qi < capacity)
+        if (KT > 0 && qi < capacity)
             for (int k = 0; k < K; ++k) {
                 out_idx[((size_t)img * capacity + qi) * K + k] = -1;
                 out_dist[((size_t)img * capacity + qi) * K + k] = 0x7FFFFFFF;
@@ -273,10 +284,13 @@ hamming_stream_kernel(const uint32_t* __restrict__ desc, const uint32_t* __restr
         if (MASKED) qm[k] = active ? qmk[k] : 0u;
     }
     constexpr unsigned kNone = 0xFFFFFFFFu;
-    unsigned best[KT];
+    unsigned best[KT > 0 ? KT : 1];
 #pragma unroll
     for (int k = 0; k < KT; ++k) best[k] = kNone;
-    unsigned worst = min(bound, 0xFFFFu);                // a pair is listed only below the K-th best so far and the caller's bound
+    const unsigned bnd = min(bound, 0xFFFFu);
+    unsigned worst = bnd;                                // a pair is listed only below the K-th best so far and the caller's bound
+    int cnt = 0;                                         // CAND: pairs below the bound seen so far
+    unsigned* crow = CAND ? cand + ((size_t)img * capacity + qi) * kCandCap : nullptr;
     const uint32_t* dbase = desc + (size_t)(img - n_cams) * capacity * WORDS;
     const uint32_t* mbase = MASKED ? dmask + (size_t)(img - n_cams) * capacity * WORDS : nullptr;
     for (int t0 = 0; t0 < nd; t0 += kDbTile) {
@@ -293,24 +307,31 @@ hamming_stream_kernel(const uint32_t* __restrict__ desc, const uint32_t* __restr
             }
         }
         __syncthreads();
+#pragma unroll 2
         for (int j = 0; j < tn; ++j) {
             // bit-level Hamming distance; masked form = (popc(x&ma) + popc(x&mb)) / 2, integer division (ref :2472)
-            unsigned dist = hamming_words<WORDS, MASKED>(qw, qm, s_d + j * WORDS, s_m + j * WORDS);
-            if (MASKED) dist >>= 1;
-            if (dist < worst) {                          // strict: equal distances keep the earlier slot
+            const unsigned dist = hamming_words<WORDS, MASKED>(qw, qm, s_d + j * WORDS, s_m + j * WORDS);
+            if (dist < (CAND ? bnd : worst)) {           // strict: equal distances keep the earlier slot
                 unsigned key = (dist << 16) | (unsigned)(t0 + j);
-#pragma unroll
-                for (int k = 0; k < KT; ++k) {
-                    if (k < K) { const unsigned lo = min(key, best[k]); key = max(key, best[k]); best[k] = lo; }
+                if (CAND) {
+                    if (cnt < kCandCap) crow[cnt] = key;
+                    ++cnt;
                 }
-                unsigned w = best[0];
+                if (KT > 0 && (!CAND || dist < worst)) {
 #pragma unroll
-                for (int k = 1; k < KT; ++k) if (k < K) w = best[k];
-                if (w != kNone) worst = min(worst, w >> 16);
+                    for (int k = 0; k < KT; ++k) {
+                        if (k < K) { const unsigned lo = min(key, best[k]); key = max(key, best[k]); best[k] = lo; }
+                    }
+                    unsigned w = best[0];
+#pragma unroll
+                    for (int k = 1; k < KT; ++k) if (k < K) w = best[k];
+                    if (w != kNone) worst = min(worst, w >> 16);
+                }
             }
         }
     }
-    if (qi < capacity) {
+    if (CAND && active) cand_cnt[(size_t)img * capacity + qi] = cnt;
+    if (KT > 0 && qi < capacity) {
         int* oi = out_idx + ((size_t)img * capacity + qi) * K;
         int* od = out_dist + ((size_t)img * capacity + qi) * K;
 #pragma unroll
@@ -325,14 +346,19 @@ hamming_stream_kernel(const uint32_t* __restrict__ desc, const uint32_t* __restr
 }
 
 cudaError_t launch_hamming_stream(const uint8_t* desc, const uint8_t* dmask, const int* counts, int img_lo, int img_count,
-                                  int n_cams, int capacity, int dim, int K, unsigned bound, int* out_idx, int* out_dist, cudaStream_t st) {
-    if (K < 1 || K > kTopKMax || (dim != 16 && dim != 32 && dim != 64) || capacity > 65535) return cudaErrorInvalidValue;
+                                  int n_cams, int capacity, int dim, int K, unsigned bound, int* out_idx, int* out_dist, cudaStream_t st,
+                                  unsigned* cand, int* cand_cnt) {
+    const bool with_cand = cand != nullptr;
+    if (K < (with_cand ? 0 : 1) || K > kTopKMax || (dim != 16 && dim != 32 && dim != 64) || capacity > 65535) return cudaErrorInvalidValue;
+    if (with_cand && !cand_cnt) return cudaErrorInvalidValue;
+    if (K > 0 && (!out_idx || !out_dist)) return cudaErrorInvalidValue;
     if (img_count < 1) return cudaSuccess;
     dim3 grid((capacity + kTopkThreads - 1) / kTopkThreads, img_count);
     const bool masked = dmask != nullptr;
-#define MCS_HS2(W, M, KT) hamming_stream_kernel<W, M, KT><<<grid, kTopkThreads, 0, st>>>((const uint32_t*)desc, (const uint32_t*)dmask, counts, \
-        n_cams, capacity, K, img_lo, bound, out_idx, out_dist)
-#define MCS_HS(W, M) { if (K <= 4) MCS_HS2(W, M, 4); else MCS_HS2(W, M, 8); }
+#define MCS_HS2(W, M, KT, C) hamming_stream_kernel<W, M, KT, C><<<grid, kTopkThreads, 0, st>>>((const uint32_t*)desc, (const uint32_t*)dmask, counts, \
+        n_cams, capacity, K, img_lo, bound, out_idx, out_dist, cand, cand_cnt)
+#define MCS_HS(W, M) { if (with_cand) { if (K == 0) MCS_HS2(W, M, 0, true); else if (K <= 4) MCS_HS2(W, M, 4, true); else MCS_HS2(W, M, 8, true); } \
+                       else if (K <= 4) MCS_HS2(W, M, 4, false); else MCS_HS2(W, M, 8, false); }
     if (dim == 16) { if (masked) MCS_HS(4, true) else MCS_HS(4, false) }
     else if (dim == 32) { if (masked) MCS_HS(8, true) else MCS_HS(8, false) }
     else { if (masked) MCS_HS(16, true) else MCS_HS(16, false) }
@@ -707,6 +733,123 @@ cudaError_t launch_stream_replay(const int* list_idx, const int* list_dist, cons
     else if (dim == 32) { if (masked) MCS_SR(8, true); else MCS_SR(8, false); }
     else { if (masked) MCS_SR(16, true); else MCS_SR(16, false); }
 #undef MCS_SR
+    return cudaGetLastError();
+}
+
+// Stream matcher, acceptance from candidate rows (hamming_stream_kernel<.., CAND = true>).  A row that did not overflow holds EVERY
+// database entry below the relevance bound, so the reference's sequential decision (ref src/cORBmatcher.cpp:899-961: best and
+// second best among the entries no earlier query has taken) is two warp minima over the row's still-unmatched keys -- lane k
+// owns candidate k, keys are (distance << 16 | slot), i.e. ordered like the reference's strict `<` scan.  No K-best list, no
+// bound reasoning, and no rescan unless a row overflowed (more than kCandCap entries below the bound: the rescan path of
+// replay_core, all threads of the CTA).  Warp 0 walks the queries; rows of 32 queries at a time are fetched into shared memory
+// with all loads in flight together.
+static_assert(kCandCap == 32 && kCandCap == kStreamCandCap, "one candidate per lane");
+template <int WORDS, bool MASKED>
+__global__ void __launch_bounds__(kReplayThreads)
+stream_accept_kernel(const unsigned* __restrict__ cand, const int* __restrict__ cand_cnt, const int* __restrict__ counts,
+                     const uint32_t* __restrict__ desc, const uint32_t* __restrict__ dmask,
+                     const int n_cams, const int capacity, const int img_lo, const int th_low, const double nnratio,
+                     int* __restrict__ matches12, int* __restrict__ nmatches, int* __restrict__ redo) {
+    extern __shared__ int s_mem[];
+    unsigned* s_cand = (unsigned*)s_mem;                       // [32][kCandCap]
+    int* s_cnt = s_mem + 32 * kCandCap;                        // [32]
+    unsigned* s_taken = (unsigned*)(s_cnt + 32);               // [(capacity + 31) / 32]
+    __shared__ ReplayShared sh;
+    constexpr unsigned kNone = 0xFFFFFFFFu;
+    const int img = blockIdx.x + img_lo, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool has_prev = img >= n_cams;
+    const int nq = has_prev ? min(counts[img], capacity) : 0;
+    const int nd = has_prev ? min(counts[img - n_cams], capacity) : 0;
+    const size_t q_row0 = (size_t)img * capacity, d_row0 = has_prev ? (size_t)(img - n_cams) * capacity : 0;
+    const uint32_t* qd = desc + q_row0 * WORDS;
+    const uint32_t* qmk = MASKED ? dmask + q_row0 * WORDS : nullptr;
+    const uint32_t* dd = desc + d_row0 * WORDS;
+    const uint32_t* dmk = MASKED ? dmask + d_row0 * WORDS : nullptr;
+    for (int i = tid; i < (capacity + 31) / 32; i += kReplayThreads) s_taken[i] = 0u;
+    for (int i = tid; i < capacity; i += kReplayThreads) matches12[q_row0 + i] = -1;
+    __syncthreads();
+    if (warp != 0) {                                           // rescan helpers: asleep unless a row overflowed
+        for (;;) {
+            named_bar<kReplayThreads>(1);
+            const int cmd = *(volatile int*)&sh.cmd;
+            if (cmd < 0) return;
+            unsigned k1[1], k2[1];
+            replay_scan<WORDS, MASKED, kReplayThreads, 1>(qd, qmk, sh.bq, 1, dd, dmk, 0, nd, s_taken, tid, k1, k2);
+            if (lane == 0) { sh.k1[warp][0] = k1[0]; sh.k2[warp][0] = k2[0]; }
+            named_bar<kReplayThreads>(2);
+        }
+    }
+    int nm = 0;
+    const unsigned* crow0 = cand + q_row0 * kCandCap;
+    for (int q0 = 0; q0 < nq; q0 += 32) {
+        const int nchunk = min(32, nq - q0);
+        const int c_me = lane < nchunk ? cand_cnt[q_row0 + q0 + lane] : 0;
+        s_cnt[lane] = c_me;
+#pragma unroll
+        for (int h = 0; h < 32; h += 16) {                     // 16 row loads in flight, then 16 stores
+            unsigned r[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int cj = __shfl_sync(0xffffffffu, c_me, h + j);
+                r[j] = lane < cj ? crow0[(size_t)(q0 + h + j) * kCandCap + lane] : kNone;      // cj > 32: the whole (overflowed) row
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) s_cand[(h + j) * kCandCap + lane] = r[j];
+        }
+        __syncwarp();
+        unsigned todo = __ballot_sync(0xffffffffu, c_me > 0);  // a query without a candidate below the bound cannot match
+        while (todo) {
+            const int t = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const unsigned key = s_cand[t * kCandCap + lane];
+            const unsigned id = key & 0xFFFFu;
+            const bool open = key != kNone && !(s_taken[id >> 5] >> (id & 31) & 1u);
+            unsigned B = __reduce_min_sync(0xffffffffu, open ? key : kNone);
+            unsigned S = __reduce_min_sync(0xffffffffu, (open && key != B) ? key : kNone);
+            int shift = 16;
+            if (s_cnt[t] > kCandCap) {
+                // overflowed row: exact rescan of the previous image for this query (two smallest keys among the unmatched entries)
+                if (lane == 0) { sh.cmd = 1; sh.bq[0] = q0 + t; }
+                named_bar<kReplayThreads>(1);
+                unsigned k1[1], k2[1];
+                replay_scan<WORDS, MASKED, kReplayThreads, 1>(qd, qmk, sh.bq, 1, dd, dmk, 0, nd, s_taken, tid, k1, k2);
+                if (lane == 0) { sh.k1[0][0] = k1[0]; sh.k2[0][0] = k2[0]; }
+                named_bar<kReplayThreads>(2);
+                const unsigned a1 = lane < kReplayThreads / 32 ? sh.k1[lane][0] : kNone;
+                const unsigned a2 = lane < kReplayThreads / 32 ? sh.k2[lane][0] : kNone;
+                B = __reduce_min_sync(0xffffffffu, a1);
+                S = __reduce_min_sync(0xffffffffu, a1 == B ? a2 : a1);
+                shift = kKeyShift;
+            }
+            const int best1 = B == kNone ? 0x7FFFFFFF : (int)(B >> shift), best2 = S == kNone ? 0x7FFFFFFF : (int)(S >> shift);
+            if (best1 < th_low && (double)best1 < nnratio * (double)best2) {
+                if (lane == 0) {
+                    const int bestIdx = (int)(B & ((1u << shift) - 1u));
+                    matches12[q_row0 + q0 + t] = bestIdx;
+                    s_taken[bestIdx >> 5] |= 1u << (bestIdx & 31);
+                }
+                ++nm;
+            }
+            __syncwarp();
+        }
+    }
+    if (lane == 0) { sh.cmd = -1; nmatches[img] = nm; redo[img] = 0; }
+    named_bar<kReplayThreads>(1);
+}
+
+cudaError_t launch_stream_accept(const unsigned* cand, const int* cand_cnt, const int* counts, const uint8_t* desc, const uint8_t* dmask,
+                                 int dim, int img_lo, int n_images, int n_cams, int capacity, int th_low, double nnratio,
+                                 int* matches12, int* nmatches, int* redo, cudaStream_t st) {
+    if (n_images < 1) return cudaSuccess;
+    if (capacity > 65535 || (dim != 16 && dim != 32 && dim != 64) || !cand || !cand_cnt) return cudaErrorInvalidValue;
+    const size_t smem = (size_t)(32 * kCandCap + 32) * 4 + (size_t)((capacity + 31) / 32) * 4;
+    const bool masked = dmask != nullptr;
+#define MCS_SA(W, M) stream_accept_kernel<W, M><<<n_images, kReplayThreads, smem, st>>>(cand, cand_cnt, counts, (const uint32_t*)desc, \
+        (const uint32_t*)dmask, n_cams, capacity, img_lo, th_low, nnratio, matches12, nmatches, redo)
+    if (dim == 16) { if (masked) MCS_SA(4, true); else MCS_SA(4, false); }
+    else if (dim == 32) { if (masked) MCS_SA(8, true); else MCS_SA(8, false); }
+    else { if (masked) MCS_SA(16, true); else MCS_SA(16, false); }
+#undef MCS_SA
     return cudaGetLastError();
 }
 

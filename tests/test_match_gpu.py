@@ -603,4 +603,45 @@ def test_bruteforce_large_database_cooperative_rescans(api, oa):
         sl = slice(seg[s], seg[s + 1])
         on, om = oa.match_bruteforce(q[sl], db, 40, 1.01, qm[sl], dbm, None, valid2)
         assert on == nms[s] and np.array_equal(m12[sl], om)
-        assert on > 0.8 * (seg[s + 1] - seg[s])
+        assert on > 0.8 * (seg[s + 1] - seg[s])@pytest.mark.gpu
+@pytest.mark.parametrize("masked", [True, False])
+def test_stream_greedy_candidate_rows_overflow(api, oa, masked):
+    """mcs_match_stream_greedy_device decides from candidate rows (every database entry below the relevance bound, 32 slots per query).
+    Clustered descriptors -- dozens of near-duplicates per query -- overflow the rows, which must fall back to the exact in-kernel
+    rescan: same matches as the reference's sequential SearchByBoW(KF1, KF2) (oracle) and as the K-best-list path."""
+    import torch
+    rng = np.random.default_rng(5)
+    F, nc, cap, ds = 3, 2, 700, 32
+    B = F * nc
+    desc = np.zeros((B, cap, ds), np.uint8)
+    dmask = np.zeros((B, cap, ds), np.uint8)
+    counts = np.array([640, 700, 655, 690, 700, 610], np.int32)
+    centres = rng.integers(0, 256, (12, ds), dtype=np.uint8)
+    for b in range(B):
+        n = counts[b]
+        # 8 big clusters (60+ members each: rows overflow), 4 small ones (<= 20 members: rows complete), the rest unrelated
+        which = rng.choice(13, n, p=[0.09] * 8 + [0.025] * 4 + [0.18])
+        base = np.where((which < 12)[:, None], centres[np.minimum(which, 11)], rng.integers(0, 256, (n, ds), dtype=np.uint8))
+        flips = np.zeros((n, ds * 8), np.uint8)
+        for i in range(n):
+            flips[i, rng.choice(ds * 8, rng.integers(0, 14), replace=False)] = 1
+        desc[b, :n] = base ^ np.packbits(flips, axis=1, bitorder="little")
+        dmask[b, :n] = rng.integers(0, 256, (n, ds), dtype=np.uint8) | rng.integers(0, 256, (n, ds), dtype=np.uint8)
+    dev = torch.device("cuda", 0)
+    d_t, m_t, c_t = torch.from_numpy(desc).to(dev), torch.from_numpy(dmask).to(dev) if masked else None, torch.from_numpy(counts).to(dev)
+    for th, nn in ((32, 0.9), (20, 0.99), (40, 0.7)):
+        m12, nm = api.match_stream_greedy_device(d_t, m_t, c_t, F, nc, th, nn)
+        idx, dist = api.match_stream_device(d_t, m_t, c_t, F, nc, K=3)
+        m12l, nml, _ = api.match_stream_replay_device(idx, dist, c_t, d_t, m_t, F, nc, th, nn)
+        torch.cuda.synchronize(dev)
+        assert torch.equal(m12, m12l) and torch.equal(nm, nml), (th, nn)
+        m12, nm = m12.cpu().numpy(), nm.cpu().numpy()
+        for img in range(nc, B):
+            q, d = slice(0, counts[img]), slice(0, counts[img - nc])
+            on, om = oa.match_bruteforce(desc[img, q], desc[img - nc, d], th, nn, dmask[img, q] if masked else None,
+                                         dmask[img - nc, d] if masked else None)
+            assert on == nm[img] and np.array_equal(om, m12[img, :counts[img]]), (th, nn, img)
+        assert nm.sum() > 30
+
+
+

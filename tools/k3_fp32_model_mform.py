@@ -1,0 +1,97 @@
+import sys, os, numpy as np
+sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/oracle')
+from multicol_slam_b200 import synth
+import re
+f32=np.float32
+_txt=re.sub(r'/\*.*?\*/','',open('/root/repo/multicol_slam_b200/csrc/brief_pairs_64.inc').read(),flags=re.S)
+pairs=np.array([int(x) for x in re.findall(r'-?\d+',_txt)],dtype=np.int64)[:1024].reshape(512,2)
+def horner(c,x):
+    r=np.zeros_like(x)
+    for k in range(len(c)-1,-1,-1): r=r*x+c[k]
+    return r
+def world_to_img(cam,x,y,z):
+    n=np.sqrt(x*x+y*y); n=np.where(n==0,1e-14,n)
+    th=np.arctan(-z/n); rho=horner(cam['inv_pol'],th)
+    uu=x/n*rho; vv=y/n*rho
+    return uu*cam['c']+vv*cam['d']+cam['u0'], uu*cam['e']+vv+cam['v0']
+def img_to_world(cam,u,v):
+    inv=cam['c']-cam['d']*cam['e']
+    ut=u-cam['u0']; vt=v-cam['v0']
+    x=(ut-cam['d']*vt)/inv; y=(-cam['e']*ut+cam['c']*vt)/inv
+    z=-horner(cam['pol'],np.sqrt(x*x+y*y))
+    nn=np.sqrt(x*x+y*y+z*z)
+    return x/nn,y/nn,z/nn
+def Rfun(cam,r):
+    z=-cam['pol'][0]
+    return horner(cam['inv_pol'],np.arctan(-z/r))
+def Gm(cam,m):
+    r=np.sqrt(m); return Rfun(cam,r)/r
+DEG=int(os.environ.get("NQ","7")); REACH=22.5
+RKMIN=float(os.environ.get("RKMIN","23"))
+def centre(i):
+    lo=max(i-REACH,0.5)**2; hi=(i+REACH)**2
+    return 0.5*(lo+hi), 0.5*(hi-lo)
+def build_table(cam,n):
+    k=np.arange(DEG); nodes=np.cos((2*k+1)*np.pi/(2*DEG))
+    tab=np.zeros((n,DEG)); Gc=np.zeros(n); fiterr=np.zeros(n)
+    for i in range(1,n):
+        c,hw=centre(i)
+        Gc[i]=Gm(cam,np.array([c]))[0]
+        D=(Gm(cam,c+hw*nodes)-Gc[i])/nodes
+        V=np.vander(nodes,DEG,increasing=True)
+        tab[i]=np.linalg.solve(V,D)
+        tt=np.linspace(-1,1,201)
+        fiterr[i]=np.abs(tt*horner(tab[i],tt)-(Gm(cam,c+hw*tt)-Gc[i])).max()*i   # in px: times auk ~ r
+    return tab,Gc,fiterr
+def test_cam(cam,nk=400,seed=0,guard=3e-5):
+    rng=np.random.default_rng(seed)
+    a0=cam['pol'][0]
+    tab,Gc,fiterr=build_table(cam,4096)
+    print("fit err (px) by centre:", {i: float('%.2e'%fiterr[i]) for i in (5,10,23,30,40,60,100,200,400,1000,3000)})
+    W,H=cam['width'],cam['height']
+    errs=[]; merrs=[]; flagged=0; total=0; skipped=0
+    for _ in range(nk):
+        while True:
+            kx=rng.uniform(30,W-30); ky=rng.uniform(30,H-30)
+            if np.hypot(ky-cam['v0'],kx-cam['u0'])<cam['v0']+22-5: break
+        x,y,z=img_to_world(cam,np.float64(kx),np.float64(ky))
+        ukx=-x/z*a0; uky=-y/z*a0
+        rk=np.hypot(ukx,uky)
+        if rk<RKMIN or rk>4000: skipped+=1; continue
+        th=rng.uniform(0,2*np.pi); ca,sa=np.cos(th),np.sin(th)
+        px=pairs[:,0].astype(np.float64); py=pairs[:,1].astype(np.float64)
+        xr=px*ca-py*sa+ukx; yr=px*sa+py*ca+uky
+        ue,ve=world_to_img(cam,xr,yr,-a0)
+        de_u=ue-ue.mean(); de_v=ve-ve.mean()
+        i=int(np.rint(rk)); c,hw=centre(i)
+        a=tab[i]
+        tk=(rk*rk-c)/hw
+        K0=tk*horner(a,np.array([tk]))[0]
+        gk=Gc[i]+K0
+        af=a.astype(f32); K0f=f32(K0); gkf=f32(gk); tkf=f32(tk); invf=f32(1.0/hw)
+        pxf=px.astype(f32); pyf=py.astype(f32)
+        nx=f32(2.0*(ukx*ca+uky*sa)); ny=f32(2.0*(uky*ca-ukx*sa))
+        p2=(pxf*pxf+pyf*pyf)
+        n=pxf*nx+(pyf*ny+p2)
+        t=n*invf+tkf
+        p=np.full_like(t,af[DEG-1])
+        for k in range(DEG-2,-1,-1): p=p*t+af[k]
+        dg=t*p-K0f
+        g=gkf+dg
+        c_,d_,e_=cam['c'],cam['d'],cam['e']
+        axx=f32(c_*ca+d_*sa); axy=f32(d_*ca-c_*sa); ayx=f32(e_*ca+sa); ayy=f32(ca-e_*sa)
+        auk=f32(c_*ukx+d_*uky); avk=f32(e_*ukx+uky)
+        du=g*(pxf*axx+pyf*axy)+dg*auk; dv=g*(pxf*ayx+pyf*ayy)+dg*avk
+        mu=f32(du.astype(np.float64).mean()); mv=f32(dv.astype(np.float64).mean())
+        tu=du-mu; tv=dv-mv
+        eu=np.abs(tu.astype(np.float64)-de_u); ev=np.abs(tv.astype(np.float64)-de_v)
+        errs.append(max(eu.max(),ev.max()))
+        uk,vk=world_to_img(cam,np.array([ukx]),np.array([uky]),-a0)
+        merrs.append(max(abs(np.float64(mu)-(ue.mean()-uk[0])),abs(np.float64(mv)-(ve.mean()-vk[0]))))
+        fr=np.concatenate([tu,tv]).astype(np.float64); fr=np.abs(fr-np.rint(fr))
+        flagged+=(fr>0.5-guard).any(); total+=1
+    errs=np.array(errs)
+    print(f"{W}x{H}: kp {len(errs)} skipped {skipped} max err {errs.max():.3e} p99 {np.percentile(errs,99):.3e} median {np.median(errs):.3e} mean-err max {max(merrs):.3e} flagged {flagged/max(total,1):.3f}")
+cams=synth.lafida_cams()
+for c in cams: test_cam(c,600,1)
+test_cam(synth.scaled_cam(cams[1],1920,1080),600,2)
