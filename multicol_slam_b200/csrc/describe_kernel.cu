@@ -95,7 +95,8 @@ constexpr int kLutDeg = 9;                        // degree of the per-centre po
 #define MCS_K3_V3 1                  // round-2 instruction diet (0 restores the previous forms for A/B builds): IC-angle disc read from a
 #endif                               // shared-memory copy, warp mean by one integer REDUX, tie / range test as running maxima
 #ifndef MCS_K3_MINB
-#define MCS_K3_MINB 6                // resident CTAs per SM the register budget is cut for (80 registers; 5 -> 96 registers: 6.25 vs 6.19 ms)
+#define MCS_K3_MINB 5                // resident CTAs per SM the register budget is cut for: 5 -> 96 registers, no local-memory reload left in
+                                     // the hot loops (4.91 ms per 384 images); 6 -> 80 registers, 1 + 3 reloads per iteration (5.07 ms)
 #endif
 constexpr int kT1Coef = 6;                        // tier 1: q(s') of degree 5, R(i + s) - R(i) = s' q(s'), s' = s / kT1Scale
 constexpr float kT1Scale = 32.f;
@@ -331,6 +332,15 @@ __device__ __noinline__ unsigned tier1_repair(const mcs_ocam* camp, const float2
     return out;
 }
 
+// warp-uniform values of the keypoint a warp works on, kept in shared memory across the pattern loops (see the kernel)
+struct __align__(16) WarpCtx {
+    float t1[16];                   // tier-1 constants of the keypoint: q[0..7], K0f, gkf, s0f, rk2f, rkf, auk, avk
+    double ukx, uky, a_base, ca[3], sa[3];
+    const double* row;
+    int kx, ky, oidx, b, level;
+    uint32_t c;
+    float angle;
+};
 template <int PPL /* pattern points per lane: 16 for descSize <= 32, 32 for descSize 64 */, int MINB = MCS_K3_MINB>
 __global__ void __launch_bounds__(kDescWarps * 32, MINB)
 describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, const mcs_ocam* __restrict__ cams,
@@ -339,6 +349,7 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                 mcs_keypoint* __restrict__ kps_out, uint8_t* __restrict__ desc_out, uint8_t* __restrict__ dmask_out,
                 int* __restrict__ counts_out, const int capacity, const int n_images) {
     __shared__ mcs_ocam s_cam[kDescWarps];
+    __shared__ WarpCtx s_ctx[kDescWarps];
     __shared__ __align__(8) float2 s_patf[PPL * 32];      // [j][lane] : point 16*byte + k with byte = lane + 32*(j/16), k = j%16, as floats
     // tier 1 parks the projected coordinates of the current pattern here between its two passes ([point][lane], this lane's own
     // slots only): with rolled loops the kernel body stays inside the instruction cache -- the fully unrolled form stalled on
@@ -479,118 +490,155 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
 #endif
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
+    // Everything that is warp-uniform and only needed again in the rare paths or at the very end is parked in this warp's context in
+    // shared memory instead of living in registers across the pattern loops: at 80 registers (6 CTAs per SM) the compiler otherwise
+    // spills the INVARIANTS OF THE HOT LOOPS, and with 212 KB of the SM's 256 KB configured as shared memory those reloads miss the
+    // small L1 (measured: 3 local-memory loads for every global load, L1 hit rate 45 %, long-scoreboard the top stall reason).
+    WarpCtx& cx = s_ctx[wib];
     const int ci = cam_of_image[b];
     const bool masks = geom->learn_masks != 0, dbrief = geom->do_dbrief != 0 || masks;
-    const float scale = g.scale;
     const int npat = masks ? 3 : 1;
-    double ca[3], sa[3], a_base, a_rot;
     {
-        double a0;
+        double a0, s0, c0;
         if (masks) a0 = (double)__fdiv_rn(angle, 57.2957763671875f);              // angle / RHOf      (ref :425)
         else a0 = (double)__fmul_rn(angle, 0.01745329238474369f);                   // angle * DEG2RADf  (ref :313,367)
-        const double rot = 20.0 / (180.0 / 3.1415926535897932384626433832795);      // 20 / RHOd         (ref :424)
-        sincos(a0, &sa[0], &ca[0]);
-        a_base = a0; a_rot = rot;
-        // angle +- 20 deg by the addition theorems (1e-16 away from cos/sin(a0 +- rot); the exact path below uses the
-        // reference's own cos(angle +- rot) / sin(angle +- rot))
-        const double c20 = 0.93969262078590838405, s20 = 0.34202014332566873304;
-        ca[1] = fma(ca[0], c20, -sa[0] * s20); sa[1] = fma(sa[0], c20, ca[0] * s20);
-        ca[2] = fma(ca[0], c20, sa[0] * s20);  sa[2] = fma(sa[0], c20, -ca[0] * s20);
+        sincos(a0, &s0, &c0);
+        if (lane == 0) {
+            cx.kx = kx; cx.ky = ky; cx.oidx = oidx; cx.b = b; cx.level = level; cx.c = c; cx.angle = angle; cx.a_base = a0;
+            // angle +- 20 deg (20 / RHOd, ref :424) by the addition theorems (1e-16 away from cos/sin(a0 +- rot); the exact path uses
+            // the reference's own cos(angle +- rot) / sin(angle +- rot))
+            const double c20 = 0.93969262078590838405, s20 = 0.34202014332566873304;
+            cx.ca[0] = c0; cx.sa[0] = s0;
+            cx.ca[1] = fma(c0, c20, -s0 * s20); cx.sa[1] = fma(s0, c20, c0 * s20);
+            cx.ca[2] = fma(c0, c20, s0 * s20);  cx.sa[2] = fma(s0, c20, -c0 * s20);
+        }
     }
     constexpr int BPL = PPL / 16;                 // descriptor bytes per lane
-    unsigned val[3][BPL];
-    __syncwarp();                                 // patch staged
+    unsigned v0[BPL], vdiff[BPL];                 // bits of the pattern at the keypoint's angle; bits that differ in a +-20 degree re-test
+#pragma unroll
+    for (int bb = 0; bb < BPL; ++bb) { v0[bb] = 0u; vdiff[bb] = 0u; }
+    auto put = [&](int qi, unsigned e /* byte bb in bits [8bb, 8bb+8) */) {
+#pragma unroll
+        for (int bb = 0; bb < BPL; ++bb) {
+            const unsigned v = (e >> (8 * bb)) & 0xFFu;
+            if (qi == 0) v0[bb] = v; else vdiff[bb] |= v ^ v0[bb];
+        }
+    };
+    __syncwarp();                                 // patch staged, context written
     if (!dbrief) {
         // ---- ORB: rotatePattern (ref :285-301) ----
+        const double ca0 = cx.ca[0], sa0 = cx.sa[0];
         int ix[PPL], iy[PPL];
         bool far = false;
 #pragma unroll
         for (int j = 0; j < PPL; ++j) {
             const float2 pp = s_patf[j * 32 + lane];
             const double px = (double)pp.x, py = (double)pp.y;
-            ix[j] = __double2int_rn(px * ca[0] - py * sa[0]);
-            iy[j] = __double2int_rn(px * sa[0] + py * ca[0]);
+            ix[j] = __double2int_rn(px * ca0 - py * sa0);
+            iy[j] = __double2int_rn(px * sa0 + py * ca0);
             far |= (unsigned)(ix[j] + kPatchR) > 2u * kPatchR || (unsigned)(iy[j] + kPatchR) > 2u * kPatchR;
         }
         if (__any_sync(0xffffffffu, far)) {
-            const unsigned e = orb_pattern_global<PPL>(s_patf, ca[0], sa[0], lane, bimg, uimg, &g, kx, ky);
-#pragma unroll
-            for (int bb = 0; bb < BPL; ++bb) val[0][bb] = (e >> (8 * bb)) & 0xFFu;
+            put(0, orb_pattern_global<PPL>(s_patf, ca0, sa0, lane, bimg, uimg, &g, kx, ky));
         } else {
+            unsigned e = 0;
 #pragma unroll
             for (int bb = 0; bb < BPL; ++bb) {
-                unsigned v = 0;
 #pragma unroll
                 for (int bit = 0; bit < 8; ++bit) {
                     const int j0 = 16 * bb + 2 * bit;
                     const int s0 = patch[pofs + iy[j0] * kPatchS + ix[j0]], s1 = patch[pofs + iy[j0 + 1] * kPatchS + ix[j0 + 1]];
-                    v |= (unsigned)(s0 < s1) << bit;
+                    e |= (unsigned)(s0 < s1) << (8 * bb + bit);
                 }
-                val[0][bb] = v;
             }
+            put(0, e);
         }
     } else {
         // ---- dBRIEF / mdBRIEF: rotateAndDistortPattern (ref :250-283) ----
         if (lane < (int)(sizeof(mcs_ocam) / 8)) ((double*)&s_cam[wib])[lane] = ((const double*)&cams[ci])[lane];
         __syncwarp();
         const mcs_ocam& cam = s_cam[wib];
-        const DistortLut lut = luts[ci];
-        double ukx, uky;   // undistortPointsOcam(pt.x*scale, pt.y*scale, a0)  (ref :1306-1317)
-        cam_undistort(cam, (double)__fmul_rn((float)kx, scale), (double)__fmul_rn((float)ky, scale), cam.pol[0], ukx, uky);
-        // the table row of this keypoint: centre i = rn(r_k); its polynomials are valid for every pattern point (|r - r_k| <= 21.3)
-        const double rk = sqrt(ukx * ukx + uky * uky);
-        const bool have_lut = rk < (double)(lut.n - 1);           // false for NaN as well -> exact path
-        const int ci_lut = have_lut ? __double2int_rn(rk) : 0;
-        const double* row = lut.coef + (size_t)ci_lut * kLutStride;
         const bool lane_valid = (PPL == 32) || (lane < ds);      // descSize 16: lanes 16..31 own no byte
-        // ---- tier-1 set-up (per keypoint, all lanes redundantly; ~25 FP64 instructions against 48 points x 3 patterns) ----
-        bool t1 = MCS_K3_T1 && have_lut && rk >= kT1MinRadius && __ldg(row + 17) == 1.0;
-        const bool mform = MCS_K3_MFORM && t1 && __ldg(row + 23) == 1.0;
-        float q[kT1MCoef], K0f = 0.f, gkf = 0.f, s0f = 0.f, rk2f = 0.f, rkf = 0.f, auk = 0.f, avk = 0.f;
-        if (mform) {
-            // m-form: t_k, K0 = t_k P(t_k), g_k = G(c_i) + K0 in double from the float coefficients the points will use
-            const float2 c01 = __ldg((const float2*)(row + 19)), c23 = __ldg((const float2*)(row + 20));
-            const float2 c45 = __ldg((const float2*)(row + 21)), c67 = __ldg((const float2*)(row + 22));
-            q[0] = c01.x; q[1] = c01.y; q[2] = c23.x; q[3] = c23.y; q[4] = c45.x; q[5] = c45.y; q[6] = c67.x; q[7] = c67.y;
-            const double inv_hw = 1.0 / t1m_halfwidth(ci_lut);
-            const double tk = (rk * rk - t1m_centre(ci_lut)) * inv_hw;
-            double pk = (double)q[7];
+        bool have_lut, t1, mform;
+        {
+            float q[kT1MCoef], K0f = 0.f, gkf = 0.f, s0f = 0.f, rk2f = 0.f, rkf = 0.f, auk = 0.f, avk = 0.f;
 #pragma unroll
-            for (int k = 6; k >= 0; --k) pk = fma(pk, tk, (double)q[k]);
-            const double K0 = tk * pk;
-            gkf = (float)(__ldg(row + 18) + K0);
-            K0f = (float)K0; s0f = (float)tk; rk2f = (float)inv_hw;              // s0f / rk2f double as t_k / (1 / hw) in the m-form
-            auk = (float)(cam.c * ukx + cam.d * uky); avk = (float)(cam.e * ukx + uky);      // A X_k
-        } else if (t1) {
-            const double Ri = __ldg(row + 12), q0d = __ldg(row + 13);
-            const float2 c12 = __ldg((const float2*)(row + 14)), c34 = __ldg((const float2*)(row + 15)), c5x = __ldg((const float2*)(row + 16));
-            q[1] = c12.x; q[2] = c12.y; q[3] = c34.x; q[4] = c34.y; q[5] = c5x.x;
-            const double s0 = (rk - (double)ci_lut) * (1.0 / (double)kT1Scale);          // in units of s'
-            double pk = (double)q[5];
-            pk = fma(pk, s0, (double)q[4]); pk = fma(pk, s0, (double)q[3]); pk = fma(pk, s0, (double)q[2]);
-            pk = fma(pk, s0, (double)q[1]); pk = fma(pk, s0, q0d);
-            const double dRk = s0 * pk;                            // R(r_k) - R(i)
-            const double gk = (Ri + dRk) / rk;                     // g(r_k)
-            // h(s') = s' q'(s') - K0' = R(r) - R(r_k) - g_k (r - r_k):  q'_0 = q_0 - g_k*scale,  K0' = dRk - g_k (r_k - i)
-            q[0] = (float)(q0d - gk * (double)kT1Scale);
-            K0f = (float)(dRk - gk * (rk - (double)ci_lut));
-            gkf = (float)gk; s0f = (float)s0;
-            rk2f = (float)(rk * rk); rkf = (float)rk;
-            auk = (float)(cam.c * ukx + cam.d * uky); avk = (float)(cam.e * ukx + uky);      // A X_k
+            for (int k = 0; k < kT1MCoef; ++k) q[k] = 0.f;
+            const DistortLut lut = luts[ci];
+            const float scale = g.scale;
+            double ukx, uky;   // undistortPointsOcam(pt.x*scale, pt.y*scale, a0)  (ref :1306-1317)
+            cam_undistort(cam, (double)__fmul_rn((float)kx, scale), (double)__fmul_rn((float)ky, scale), cam.pol[0], ukx, uky);
+            // the table row of this keypoint: centre i = rn(r_k); its polynomials are valid for every pattern point (|r - r_k| <= 21.3)
+            const double rk = sqrt(ukx * ukx + uky * uky);
+            have_lut = rk < (double)(lut.n - 1);                  // false for NaN as well -> exact path
+            const int ci_lut = have_lut ? __double2int_rn(rk) : 0;
+            const double* row = lut.coef + (size_t)ci_lut * kLutStride;
+            if (lane == 0) { cx.ukx = ukx; cx.uky = uky; cx.row = row; }
+            // ---- tier-1 set-up (per keypoint, all lanes redundantly; ~25 FP64 instructions against 48 points x 3 patterns) ----
+            t1 = MCS_K3_T1 && have_lut && rk >= kT1MinRadius && __ldg(row + 17) == 1.0;
+            mform = MCS_K3_MFORM && t1 && __ldg(row + 23) == 1.0;
+            if (mform) {
+                // m-form: t_k, K0 = t_k P(t_k), g_k = G(c_i) + K0 in double from the float coefficients the points will use
+                const float2 c01 = __ldg((const float2*)(row + 19)), c23 = __ldg((const float2*)(row + 20));
+                const float2 c45 = __ldg((const float2*)(row + 21)), c67 = __ldg((const float2*)(row + 22));
+                q[0] = c01.x; q[1] = c01.y; q[2] = c23.x; q[3] = c23.y; q[4] = c45.x; q[5] = c45.y; q[6] = c67.x; q[7] = c67.y;
+                const double inv_hw = 1.0 / t1m_halfwidth(ci_lut);
+                const double tk = (rk * rk - t1m_centre(ci_lut)) * inv_hw;
+                double pk = (double)q[7];
+#pragma unroll
+                for (int k = 6; k >= 0; --k) pk = fma(pk, tk, (double)q[k]);
+                const double K0 = tk * pk;
+                gkf = (float)(__ldg(row + 18) + K0);
+                K0f = (float)K0; s0f = (float)tk; rk2f = (float)inv_hw;              // s0f / rk2f double as t_k / (1 / hw) in the m-form
+                auk = (float)(cam.c * ukx + cam.d * uky); avk = (float)(cam.e * ukx + uky);      // A X_k
+            } else if (t1) {
+                const double Ri = __ldg(row + 12), q0d = __ldg(row + 13);
+                const float2 c12 = __ldg((const float2*)(row + 14)), c34 = __ldg((const float2*)(row + 15)), c5x = __ldg((const float2*)(row + 16));
+                q[1] = c12.x; q[2] = c12.y; q[3] = c34.x; q[4] = c34.y; q[5] = c5x.x; q[6] = 0.f; q[7] = 0.f;
+                const double s0 = (rk - (double)ci_lut) * (1.0 / (double)kT1Scale);          // in units of s'
+                double pk = (double)q[5];
+                pk = fma(pk, s0, (double)q[4]); pk = fma(pk, s0, (double)q[3]); pk = fma(pk, s0, (double)q[2]);
+                pk = fma(pk, s0, (double)q[1]); pk = fma(pk, s0, q0d);
+                const double dRk = s0 * pk;                            // R(r_k) - R(i)
+                const double gk = (Ri + dRk) / rk;                     // g(r_k)
+                // h(s') = s' q'(s') - K0' = R(r) - R(r_k) - g_k (r - r_k):  q'_0 = q_0 - g_k*scale,  K0' = dRk - g_k (r_k - i)
+                q[0] = (float)(q0d - gk * (double)kT1Scale);
+                K0f = (float)(dRk - gk * (rk - (double)ci_lut));
+                gkf = (float)gk; s0f = (float)s0;
+                rk2f = (float)(rk * rk); rkf = (float)rk;
+                auk = (float)(cam.c * ukx + cam.d * uky); avk = (float)(cam.e * ukx + uky);      // A X_k
+            }
+            // the tier-1 constants go to the context as well: they are needed in pass 1 of every pattern only, and re-reading them
+            // there (four broadcast LDS.128) keeps 15 registers free across pass 2 and the rare-path calls
+            if (lane == 0) {
+                float4* tp = reinterpret_cast<float4*>(cx.t1);
+                tp[0] = make_float4(q[0], q[1], q[2], q[3]); tp[1] = make_float4(q[4], q[5], q[6], q[7]);
+                tp[2] = make_float4(K0f, gkf, s0f, rk2f);    tp[3] = make_float4(rkf, auk, avk, 0.f);
+            }
         }
+        __syncwarp();                             // context complete
 #pragma unroll 1                         // one copy of the pattern body: the kernel has to fit the instruction cache
         for (int qi = 0; qi < npat; ++qi) {
             bool done = false;
+            float2* park = s_park_dyn + wib * (PPL * 32);
             if (t1) {
                 // ---- tier 1: fp32, relative to the keypoint (see the header) ----
                 // rotation folded into per-pattern constants (double -> float once): with p the pattern point and d = Rot p,
                 //   n = r^2 - r_k^2 = |p|^2 + 2 (Rot^T X_k).p            (|d| = |p|: no rotated point needed for n)
                 //   u - u_k = g (A Rot p).x + dg (A X_k).x               (A = affine part [c d; e 1])
-                const float nx = (float)(2.0 * (ukx * ca[qi] + uky * sa[qi])), ny = (float)(2.0 * (uky * ca[qi] - ukx * sa[qi]));
-                const float axx = (float)(cam.c * ca[qi] + cam.d * sa[qi]), axy = (float)(cam.d * ca[qi] - cam.c * sa[qi]);
-                const float ayx = (float)(cam.e * ca[qi] + sa[qi]), ayy = (float)(ca[qi] - cam.e * sa[qi]);
-                float2* park = s_park_dyn + wib * (PPL * 32);
+                float nx, ny, axx, axy, ayx, ayy;
+                {
+                    const double caq = cx.ca[qi], saq = cx.sa[qi], ukx = cx.ukx, uky = cx.uky;
+                    nx = (float)(2.0 * (ukx * caq + uky * saq)); ny = (float)(2.0 * (uky * caq - ukx * saq));
+                    axx = (float)(cam.c * caq + cam.d * saq); axy = (float)(cam.d * caq - cam.c * saq);
+                    ayx = (float)(cam.e * caq + saq); ayy = (float)(caq - cam.e * saq);
+                }
                 float su = 0.f, sv = 0.f;
+                {
+                const float4* tp = reinterpret_cast<const float4*>(cx.t1);
+                const float4 tA = tp[0], tB = tp[1], tC = tp[2], tD = tp[3];
+                const float q[kT1MCoef] = {tA.x, tA.y, tA.z, tA.w, tB.x, tB.y, tB.z, tB.w};
+                const float K0f = tC.x, gkf = tC.y, s0f = tC.z, rk2f = tC.w, rkf = tD.x, auk = tD.y, avk = tD.z;
                 if (mform) {
 #pragma unroll 4
                     for (int j = 0; j < PPL; ++j) {
@@ -631,6 +679,7 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                     park[j * 32 + lane] = make_float2(du, dv);
                     if (lane_valid) { su += du; sv += dv; }
                 }
+                }
                 // mean over the 16*ds points: lane partial sums in fp32 (16..32 terms)
                 const double inv_n = 1.0 / (double)(16 * ds);
                 bool flag = false;
@@ -654,7 +703,7 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                 const float mu = (float)(sud * inv_n), mv = (float)(svd * inv_n);
 #endif
                 constexpr float kMagicF = 12582912.f;                          // 1.5 * 2^23: t + magic rounds t to the nearest even integer
-                unsigned bits0 = 0, bits1 = 0;                                 // descriptor byte(s) of this lane: points 0..15 / 16..31
+                unsigned bits = 0;                                             // descriptor byte(s) of this lane: points 0..15 | 16..31 << 8
 #pragma unroll 2
                 for (int j = 0; j < PPL; j += 2) {
                     int smp[2];
@@ -680,23 +729,20 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                         const int ofs = min(max(iy * kPatchS + ix, -(kPatchR * kPatchS + kPatchR)), kPatchR * kPatchS + kPatchR);
                         smp[e2] = patch[pofs + ofs];
                     }
-                    const unsigned bit = (unsigned)(smp[0] < smp[1]) << ((j & 15) >> 1);
-                    if (PPL == 16 || j < 16) bits0 |= bit; else bits1 |= bit;
+                    bits |= (unsigned)(smp[0] < smp[1]) << (j >> 1);          // point pair j/2: bits 0..7 = byte 0, 8..15 = byte 1
                 }
 #if MCS_K3_V3
                 flag |= !(wf < 0.5f - kT1Guard) | !(wt < (float)kPatchR + 0.4f);
 #endif
                 if (!__any_sync(0xffffffffu, flag && lane_valid)) {
-                    val[qi][0] = bits0;
-                    if (BPL > 1) val[qi][BPL - 1] = bits1;
+                    put(qi, bits);
                     done = true;
                     if (args.tier_stats && lane == 0) atomicAdd(args.tier_stats, 1ull);
                 } else if (MCS_K3_REPAIR) {
                     int fail = 0;
-                    const unsigned e = tier1_repair<PPL>(&cam, s_patf, park, row, ca[qi], sa[qi], ukx, uky, lane, ds, patch, pofs, &fail);
+                    const unsigned e = tier1_repair<PPL>(&cam, s_patf, park, cx.row, cx.ca[qi], cx.sa[qi], cx.ukx, cx.uky, lane, ds, patch, pofs, &fail);
                     if (!__any_sync(0xffffffffu, fail != 0)) {
-#pragma unroll
-                        for (int bb = 0; bb < BPL; ++bb) val[qi][bb] = (e >> (8 * bb)) & 0xFFu;
+                        put(qi, e);
                         done = true;
                         if (args.tier_stats && lane == 0) atomicAdd(args.tier_stats + 1, 1ull);
                     }
@@ -706,37 +752,43 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                 // ---- tier 2 (FP64 polynomial), then tier 3 (exact) where tier 2 cannot decide ----
                 unsigned e = 0;
                 int need_exact = have_lut ? 0 : 1;
-                if (have_lut) e = tier2_pattern<PPL>(&cam, s_patf, row, ca[qi], sa[qi], ukx, uky, lane, ds, patch, pofs, &need_exact);
+                if (have_lut) e = tier2_pattern<PPL>(&cam, s_patf, cx.row, cx.ca[qi], cx.sa[qi], cx.ukx, cx.uky, lane, ds, patch, pofs, &need_exact);
                 const bool exact = __any_sync(0xffffffffu, need_exact != 0);
                 if (exact) {
-                    const double aq = qi == 0 ? a_base : (qi == 1 ? a_base + a_rot : a_base - a_rot);
-                    e = exact_pattern<PPL>(&cam, s_patf, aq, ukx, uky, lane, ds, bimg, uimg, &g, kx, ky);
+                    const double rot = 20.0 / (180.0 / 3.1415926535897932384626433832795);      // 20 / RHOd         (ref :424)
+                    const double aq = qi == 0 ? cx.a_base : (qi == 1 ? cx.a_base + rot : cx.a_base - rot);
+                    const int lv = cx.level, bq = cx.b;
+                    const LevelGeom& gq = geom->lv[lv];
+                    e = exact_pattern<PPL>(&cam, s_patf, aq, cx.ukx, cx.uky, lane, ds, args.blur[lv] + (size_t)bq * gq.img_bytes,
+                                           args.lvl[lv] + (size_t)bq * gq.img_bytes, &gq, cx.kx, cx.ky);
                 }
                 if (args.tier_stats && lane == 0) atomicAdd(args.tier_stats + (exact ? 3 : 2), 1ull);
-#pragma unroll
-                for (int bb = 0; bb < BPL; ++bb) val[qi][bb] = (e >> (8 * bb)) & 0xFFu;
+                put(qi, e);
             }
         }
     }
+    {
+        const int bo = cx.b, oo = cx.oidx;
 #pragma unroll
-    for (int bb = 0; bb < BPL; ++bb) {
-        const int byte = lane + 32 * bb;
-        if (byte < ds) {
-            desc_out[((size_t)b * capacity + oidx) * ds + byte] = (uint8_t)val[0][bb];
-            if (dmask_out) {
+        for (int bb = 0; bb < BPL; ++bb) {
+            const int byte = lane + 32 * bb;
+            if (byte < ds) {
+                desc_out[((size_t)bo * capacity + oo) * ds + byte] = (uint8_t)v0[bb];
                 // stable bit <=> both +-20 degree re-tests agree with the bit (ref :449-451 ...)
-                const unsigned m = masks ? (~((val[1][bb] ^ val[0][bb]) | (val[2][bb] ^ val[0][bb])) & 0xFFu) : 0u;
-                dmask_out[((size_t)b * capacity + oidx) * ds + byte] = (uint8_t)m;
+                if (dmask_out) dmask_out[((size_t)bo * capacity + oo) * ds + byte] = (uint8_t)(masks ? (~vdiff[bb] & 0xFFu) : 0u);
             }
         }
-    }
-    if (lane == 0) {
-        mcs_keypoint k;
-        k.x = level ? __fmul_rn((float)kx, scale) : (float)kx;      // pt *= scale for l > 0 (ref :1327-1332)
-        k.y = level ? __fmul_rn((float)ky, scale) : (float)ky;
-        k.size = g.patch_size; k.angle = angle; k.response = (float)corner_s(c);
-        k.octave = level; k.class_id = -1;
-        kps_out[(size_t)b * capacity + oidx] = k;
+        if (lane == 0) {
+            const int lv = cx.level, kxo = cx.kx, kyo = cx.ky;
+            const LevelGeom& go = geom->lv[lv];
+            const float scale = go.scale;
+            mcs_keypoint k;
+            k.x = lv ? __fmul_rn((float)kxo, scale) : (float)kxo;      // pt *= scale for l > 0 (ref :1327-1332)
+            k.y = lv ? __fmul_rn((float)kyo, scale) : (float)kyo;
+            k.size = go.patch_size; k.angle = cx.angle; k.response = (float)corner_s(cx.c);
+            k.octave = lv; k.class_id = -1;
+            kps_out[(size_t)bo * capacity + oo] = k;
+        }
     }
 }
 

@@ -37,18 +37,8 @@ cudaError_t launch_describe(const PyramidGeom& G, const PyramidGeom* G_dev, int 
 cudaError_t launch_hamming_topk(const uint8_t* q, const uint8_t* qmask, int nq, const uint8_t* d, const uint8_t* dmask,
                                 int nd, const uint8_t* db_skip, int dim, int K, unsigned bound, int* topk_idx, int* topk_dist,
                                 cudaStream_t st);
-// cand / cand_cnt (optional, device): candidate rows of the acceptance kernel (launch_stream_accept) -- kStreamCandCap keys per
-// query slot + one count per slot; with them K may be 0 (no K-best lists, out_idx / out_dist unused)
-constexpr int kStreamCandCap = 32;
 cudaError_t launch_hamming_stream(const uint8_t* desc, const uint8_t* dmask, const int* counts, int img_lo, int img_count,
-                                  int n_cams, int capacity, int dim, int K, unsigned bound, int* out_idx, int* out_dist, cudaStream_t st,
-                                  unsigned* cand = nullptr, int* cand_cnt = nullptr);
-// the candidate rows are only worth building when the relevance bound is a small part of the distance range (else every pair is a
-// candidate and every row overflows): callers fall back to K-best lists + launch_stream_replay otherwise
-inline bool stream_cand_applicable(unsigned bound, int dim) { return bound <= (unsigned)(2 * dim); }
-cudaError_t launch_stream_accept(const unsigned* cand, const int* cand_cnt, const int* counts, const uint8_t* desc, const uint8_t* dmask,
-                                 int dim, int img_lo, int n_images, int n_cams, int capacity, int th_low, double nnratio,
-                                 int* matches12, int* nmatches, int* redo, cudaStream_t st);
+                                  int n_cams, int capacity, int dim, int K, unsigned bound, int* out_idx, int* out_dist, cudaStream_t st);
 // Relevance bound of the greedy acceptance rule (best1 < th_low && best1 < nnratio * best2, ref src/cORBmatcher.cpp:899-961): the
 // smallest distance b >= th_low such that a second-best of b or more passes the ratio test for EVERY admissible best
 // (best <= th_low - 1).  A database entry at distance >= b can neither be an accepted best nor make a ratio test fail, so the

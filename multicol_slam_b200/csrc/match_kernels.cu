@@ -154,7 +154,7 @@ hamming_topk_kernel(const uint32_t* __restrict__ q, const uint32_t* __restrict__
         for (int j = 0; j < tn; ++j) {
             if (s_skip[j]) continue;       // uniform across the CTA
             // bit-level Hamming distance; masked form = (popc(x&ma) + popc(x&mb)) / 2, integer division (ref :2472)
-            unsigned dist = hamming_words<WORDS, MASKED>(qw, qm, s_d + j * WORDS, s_m + j * WORDS);
+            const unsigned dist = hamming_words<WORDS, MASKED>(qw, qm, s_d + j * WORDS, s_m + j * WORDS);
             if (dist < worst) {            // strict: equal distances keep the earlier index; entries at or beyond `bound` are not listed
                 unsigned key = (dist << kTopkShift) | (unsigned)(t0 + j);
 #pragma unroll
@@ -247,18 +247,11 @@ cudaError_t launch_hamming_topk(const uint8_t* q, const uint8_t* qmask, int nq, 
 // The per-thread list holds 32-bit keys (distance << 16 | slot; slots < 65536, distances <= 512) and its length KT is a compile-time
 // constant (4 or 8): the sorted insertion -- executed by the one or two lanes of a warp that have a candidate -- is 3 instructions
 // per list position instead of ~6 on 64-bit keys over all 8 positions.
-//
-// CAND: every pair below `bound` (the relevance bound of the acceptance rule, kernels.h: greedy_dist_bound) is also appended, in
-// database order, to the query's candidate row (kCandCap keys, row r of image i at cand[(i * capacity + r) * kCandCap]) and
-// counted in cand_cnt -- the count keeps running past kCandCap, so that cnt <= kCandCap PROVES the row holds every database
-// entry that can influence the acceptance.  One thread owns one query: no atomics.  KT == 0: no K-best lists at all (the
-// acceptance kernel below works from the candidate rows alone).
-constexpr int kCandCap = 32;                 // one candidate per lane of the acceptance warp
-template <int WORDS, bool MASKED, int KT, bool CAND>
+template <int WORDS, bool MASKED, int KT>
 __global__ void __launch_bounds__(kTopkThreads)
 hamming_stream_kernel(const uint32_t* __restrict__ desc, const uint32_t* __restrict__ dmask, const int* __restrict__ counts,
                       const int n_cams, const int capacity, const int K, const int img_lo, const unsigned bound,
-                      int* __restrict__ out_idx, int* __restrict__ out_dist, unsigned* __restrict__ cand, int* __restrict__ cand_cnt) {
+                      int* __restrict__ out_idx, int* __restrict__ out_dist) {
     __shared__ __align__(16) uint32_t s_d[kDbTile * WORDS];
     __shared__ __align__(16) uint32_t s_m[MASKED ? kDbTile * WORDS : 4];
     const int img = blockIdx.y + img_lo;
@@ -267,7 +260,7 @@ hamming_stream_kernel(const uint32_t* __restrict__ desc, const uint32_t* __restr
     const int nq = has_prev ? min(counts[img], capacity) : 0;
     const int nd = has_prev ? min(counts[img - n_cams], capacity) : 0;
     if ((int)(blockIdx.x * kTopkThreads) >= nq) {        // nothing to match in this block: mark the slots empty
-        if (KT > 0 && qi < capacity)
+        if (qi < capacity)
             for (int k = 0; k < K; ++k) {
                 out_idx[((size_t)img * capacity + qi) * K + k] = -1;
                 out_dist[((size_t)img * capacity + qi) * K + k] = 0x7FFFFFFF;
@@ -284,13 +277,10 @@ hamming_stream_kernel(const uint32_t* __restrict__ desc, const uint32_t* __restr
         if (MASKED) qm[k] = active ? qmk[k] : 0u;
     }
     constexpr unsigned kNone = 0xFFFFFFFFu;
-    unsigned best[KT > 0 ? KT : 1];
+    unsigned best[KT];
 #pragma unroll
     for (int k = 0; k < KT; ++k) best[k] = kNone;
-    const unsigned bnd = min(bound, 0xFFFFu);
-    unsigned worst = bnd;                                // a pair is listed only below the K-th best so far and the caller's bound
-    int cnt = 0;                                         // CAND: pairs below the bound seen so far
-    unsigned* crow = CAND ? cand + ((size_t)img * capacity + qi) * kCandCap : nullptr;
+    unsigned worst = min(bound, 0xFFFFu);                // a pair is listed only below the K-th best so far and the caller's bound
     const uint32_t* dbase = desc + (size_t)(img - n_cams) * capacity * WORDS;
     const uint32_t* mbase = MASKED ? dmask + (size_t)(img - n_cams) * capacity * WORDS : nullptr;
     for (int t0 = 0; t0 < nd; t0 += kDbTile) {
@@ -311,27 +301,20 @@ hamming_stream_kernel(const uint32_t* __restrict__ desc, const uint32_t* __restr
         for (int j = 0; j < tn; ++j) {
             // bit-level Hamming distance; masked form = (popc(x&ma) + popc(x&mb)) / 2, integer division (ref :2472)
             const unsigned dist = hamming_words<WORDS, MASKED>(qw, qm, s_d + j * WORDS, s_m + j * WORDS);
-            if (dist < (CAND ? bnd : worst)) {           // strict: equal distances keep the earlier slot
+            if (dist < worst) {                          // strict: equal distances keep the earlier slot
                 unsigned key = (dist << 16) | (unsigned)(t0 + j);
-                if (CAND) {
-                    if (cnt < kCandCap) crow[cnt] = key;
-                    ++cnt;
-                }
-                if (KT > 0 && (!CAND || dist < worst)) {
 #pragma unroll
-                    for (int k = 0; k < KT; ++k) {
-                        if (k < K) { const unsigned lo = min(key, best[k]); key = max(key, best[k]); best[k] = lo; }
-                    }
-                    unsigned w = best[0];
-#pragma unroll
-                    for (int k = 1; k < KT; ++k) if (k < K) w = best[k];
-                    if (w != kNone) worst = min(worst, w >> 16);
+                for (int k = 0; k < KT; ++k) {
+                    if (k < K) { const unsigned lo = min(key, best[k]); key = max(key, best[k]); best[k] = lo; }
                 }
+                unsigned w = best[0];
+#pragma unroll
+                for (int k = 1; k < KT; ++k) if (k < K) w = best[k];
+                if (w != kNone) worst = min(worst, w >> 16);
             }
         }
     }
-    if (CAND && active) cand_cnt[(size_t)img * capacity + qi] = cnt;
-    if (KT > 0 && qi < capacity) {
+    if (qi < capacity) {
         int* oi = out_idx + ((size_t)img * capacity + qi) * K;
         int* od = out_dist + ((size_t)img * capacity + qi) * K;
 #pragma unroll
@@ -346,19 +329,14 @@ hamming_stream_kernel(const uint32_t* __restrict__ desc, const uint32_t* __restr
 }
 
 cudaError_t launch_hamming_stream(const uint8_t* desc, const uint8_t* dmask, const int* counts, int img_lo, int img_count,
-                                  int n_cams, int capacity, int dim, int K, unsigned bound, int* out_idx, int* out_dist, cudaStream_t st,
-                                  unsigned* cand, int* cand_cnt) {
-    const bool with_cand = cand != nullptr;
-    if (K < (with_cand ? 0 : 1) || K > kTopKMax || (dim != 16 && dim != 32 && dim != 64) || capacity > 65535) return cudaErrorInvalidValue;
-    if (with_cand && !cand_cnt) return cudaErrorInvalidValue;
-    if (K > 0 && (!out_idx || !out_dist)) return cudaErrorInvalidValue;
+                                  int n_cams, int capacity, int dim, int K, unsigned bound, int* out_idx, int* out_dist, cudaStream_t st) {
+    if (K < 1 || K > kTopKMax || (dim != 16 && dim != 32 && dim != 64) || capacity > 65535) return cudaErrorInvalidValue;
     if (img_count < 1) return cudaSuccess;
     dim3 grid((capacity + kTopkThreads - 1) / kTopkThreads, img_count);
     const bool masked = dmask != nullptr;
-#define MCS_HS2(W, M, KT, C) hamming_stream_kernel<W, M, KT, C><<<grid, kTopkThreads, 0, st>>>((const uint32_t*)desc, (const uint32_t*)dmask, counts, \
-        n_cams, capacity, K, img_lo, bound, out_idx, out_dist, cand, cand_cnt)
-#define MCS_HS(W, M) { if (with_cand) { if (K == 0) MCS_HS2(W, M, 0, true); else if (K <= 4) MCS_HS2(W, M, 4, true); else MCS_HS2(W, M, 8, true); } \
-                       else if (K <= 4) MCS_HS2(W, M, 4, false); else MCS_HS2(W, M, 8, false); }
+#define MCS_HS2(W, M, KT) hamming_stream_kernel<W, M, KT><<<grid, kTopkThreads, 0, st>>>((const uint32_t*)desc, (const uint32_t*)dmask, counts, \
+        n_cams, capacity, K, img_lo, bound, out_idx, out_dist)
+#define MCS_HS(W, M) { if (K <= 4) MCS_HS2(W, M, 4); else MCS_HS2(W, M, 8); }
     if (dim == 16) { if (masked) MCS_HS(4, true) else MCS_HS(4, false) }
     else if (dim == 32) { if (masked) MCS_HS(8, true) else MCS_HS(8, false) }
     else { if (masked) MCS_HS(16, true) else MCS_HS(16, false) }
@@ -395,17 +373,17 @@ __device__ __forceinline__ void replay_scan(const uint32_t* __restrict__ qd, con
                                             const uint32_t* __restrict__ dd, const uint32_t* __restrict__ dm, const int id_lo,
                                             const int id_hi, const unsigned* s_taken /* bit (id - id_lo) */, const int tid,
                                             unsigned (&k1)[R], unsigned (&k2)[R]) {
-    uint4 qw[R][WORDS / 4], qm[R][MASKED ? WORDS / 4 : 1];
+    uint32_t qw[R][WORDS], qm[R][MASKED ? WORDS : 1];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int row = rows[r < n ? r : 0];
         const uint4* qp = reinterpret_cast<const uint4*>(qd + (size_t)row * WORDS);
 #pragma unroll
-        for (int k = 0; k < WORDS / 4; ++k) qw[r][k] = qp[k];
+        for (int k = 0; k < WORDS / 4; ++k) { const uint4 t = qp[k]; qw[r][4 * k] = t.x; qw[r][4 * k + 1] = t.y; qw[r][4 * k + 2] = t.z; qw[r][4 * k + 3] = t.w; }
         if (MASKED) {
             const uint4* qmp = reinterpret_cast<const uint4*>(qmk + (size_t)row * WORDS);
 #pragma unroll
-            for (int k = 0; k < WORDS / 4; ++k) qm[r][k] = qmp[k];
+            for (int k = 0; k < WORDS / 4; ++k) { const uint4 t = qmp[k]; qm[r][4 * k] = t.x; qm[r][4 * k + 1] = t.y; qm[r][4 * k + 2] = t.z; qm[r][4 * k + 3] = t.w; }
         }
         k1[r] = 0xFFFFFFFFu; k2[r] = 0xFFFFFFFFu;
     }
@@ -414,23 +392,18 @@ __device__ __forceinline__ void replay_scan(const uint32_t* __restrict__ qd, con
         if (s_taken[(id - id_lo) >> 5] >> ((id - id_lo) & 31) & 1u) continue;
         const uint4* dp = reinterpret_cast<const uint4*>(dd + (size_t)id * WORDS);
         const uint4* mp = MASKED ? reinterpret_cast<const uint4*>(dm + (size_t)id * WORDS) : nullptr;
-        uint4 d[WORDS / 4], m[MASKED ? WORDS / 4 : 1];
+        uint32_t dw[WORDS], mw[MASKED ? WORDS : 1];
 #pragma unroll
-        for (int k = 0; k < WORDS / 4; ++k) { d[k] = dp[k]; if (MASKED) m[k] = mp[k]; }
+        for (int k = 0; k < WORDS / 4; ++k) {
+            const uint4 t = dp[k]; dw[4 * k] = t.x; dw[4 * k + 1] = t.y; dw[4 * k + 2] = t.z; dw[4 * k + 3] = t.w;
+            if (MASKED) { const uint4 u = mp[k]; mw[4 * k] = u.x; mw[4 * k + 1] = u.y; mw[4 * k + 2] = u.z; mw[4 * k + 3] = u.w; }
+        }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             if (r >= n) break;
-            unsigned dist = 0;
-#pragma unroll
-            for (int k = 0; k < WORDS / 4; ++k) {
-                const uint32_t x0 = qw[r][k].x ^ d[k].x, x1 = qw[r][k].y ^ d[k].y, x2 = qw[r][k].z ^ d[k].z, x3 = qw[r][k].w ^ d[k].w;
-                if (MASKED)
-                    dist += __popc(x0 & qm[r][k].x) + __popc(x0 & m[k].x) + __popc(x1 & qm[r][k].y) + __popc(x1 & m[k].y) +
-                            __popc(x2 & qm[r][k].z) + __popc(x2 & m[k].z) + __popc(x3 & qm[r][k].w) + __popc(x3 & m[k].w);
-                else
-                    dist += __popc(x0) + __popc(x1) + __popc(x2) + __popc(x3);
-            }
-            if (MASKED) dist >>= 1;
+            // the list kernels' distance (carry-save popcount: 9 POPC instead of 16 per masked 256-bit pair -- a rescan is bound by the
+            // POPC rate of the SM as soon as the descriptors come from shared memory)
+            const unsigned dist = hamming_words<WORDS, MASKED>(qw[r], qm[r], dw, mw);
             const unsigned key = (dist << kKeyShift) | (unsigned)id;
             if (key < k1[r]) { k2[r] = k1[r]; k1[r] = key; } else if (key < k2[r]) k2[r] = key;
         }
@@ -500,7 +473,12 @@ __device__ __forceinline__ int replay_core(const int* __restrict__ list_idx, con
                                            const uint32_t* __restrict__ qmk, const uint32_t* __restrict__ dd,
                                            const uint32_t* __restrict__ dmk, const int nd, const int th_low, const double nnratio,
                                            int* __restrict__ matches12, int* s_li, int* s_ld, unsigned* s_taken, ReplayShared* sh,
+                                           uint32_t* s_qc /* [2][32][WORDS]: descriptors (and masks) of the current 32-query chunk */,
                                            const CoopLeader coop = CoopLeader{nullptr, nullptr, 0, 0}) {
+    // rescans read their query from this chunk copy (sh->bq holds the chunk-relative row): no global-memory round trip between the
+    // decision to rescan and the scan itself
+    const uint32_t* s_qd = s_qc;
+    const uint32_t* s_qm = MASKED ? s_qc + 32 * WORDS : nullptr;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int scan_hi = coop.helpers ? coop.shard_hi : nd;          // this CTA's share of a rescan
     int nlog = 0, seq = 0;
@@ -510,7 +488,7 @@ __device__ __forceinline__ int replay_core(const int* __restrict__ list_idx, con
             const int cmd = *(volatile int*)&sh->cmd;
             if (cmd < 0) return 0;
             unsigned k1[R], k2[R];
-            replay_scan<WORDS, MASKED, THREADS, R>(qd, qmk, sh->bq, cmd, dd, dmk, 0, scan_hi, s_taken, tid, k1, k2);
+            replay_scan<WORDS, MASKED, THREADS, R>(s_qd, s_qm, sh->bq, cmd, dd, dmk, 0, scan_hi, s_taken, tid, k1, k2);
             if (lane == 0) {
 #pragma unroll
                 for (int r = 0; r < R; ++r) { sh->k1[warp][r] = k1[r]; sh->k2[warp][r] = k2[r]; }
@@ -526,6 +504,10 @@ __device__ __forceinline__ int replay_core(const int* __restrict__ list_idx, con
         for (int i = lane; i < nchunk * K; i += 32) {
             s_li[i] = list_idx[(size_t)q0 * K + i];
             s_ld[i] = list_dist[(size_t)q0 * K + i];
+        }
+        for (int i = lane; i < nchunk * (WORDS / 4); i += 32) {
+            reinterpret_cast<uint4*>(s_qc)[i] = reinterpret_cast<const uint4*>(qd + (size_t)q0 * WORDS)[i];
+            if (MASKED) reinterpret_cast<uint4*>(s_qc + 32 * WORDS)[i] = reinterpret_cast<const uint4*>(qmk + (size_t)q0 * WORDS)[i];
         }
         __syncwarp();
         for (int t = 0; t < nchunk; ++t) {
@@ -583,9 +565,9 @@ __device__ __forceinline__ int replay_core(const int* __restrict__ list_idx, con
                     }
                     if (lane == 0) {
                         sh->cmd = n;
-                        sh->bq[0] = q0 + t;
+                        sh->bq[0] = t;                     // chunk-relative rows (see s_qd)
                         unsigned cm = cand;
-                        for (int r = 1; r < n; ++r) { sh->bq[r] = q0 + __ffs(cm) - 1; cm &= cm - 1u; }
+                        for (int r = 1; r < n; ++r) { sh->bq[r] = __ffs(cm) - 1; cm &= cm - 1u; }
                         if (coop.helpers) {                 // publish the rescan to the helper CTAs before scanning shard 0 here (R == 1)
                             coop.seg->cmd_query = q0 + t;
                             coop.seg->log_len = nlog;
@@ -595,7 +577,7 @@ __device__ __forceinline__ int replay_core(const int* __restrict__ list_idx, con
                     }
                     named_bar<THREADS>(1);
                     unsigned k1[R], k2[R];
-                    replay_scan<WORDS, MASKED, THREADS, R>(qd, qmk, sh->bq, n, dd, dmk, 0, scan_hi, s_taken, tid, k1, k2);
+                    replay_scan<WORDS, MASKED, THREADS, R>(s_qd, s_qm, sh->bq, n, dd, dmk, 0, scan_hi, s_taken, tid, k1, k2);
                     if (lane == 0) {
 #pragma unroll
                         for (int r = 0; r < R; ++r) { sh->k1[0][r] = k1[r]; sh->k2[0][r] = k2[r]; }
@@ -608,7 +590,7 @@ __device__ __forceinline__ int replay_core(const int* __restrict__ list_idx, con
                         const unsigned Br = __reduce_min_sync(0xffffffffu, a1);
                         const unsigned Sr = __reduce_min_sync(0xffffffffu, a1 == Br ? a2 : a1);
                         if (r == 0) { B = Br; S = Sr; }
-                        else if (lane == 0) { sh->pq[r] = r < n ? sh->bq[r] : -1; sh->pB[r] = Br; sh->pS[r] = Sr; }
+                        else if (lane == 0) { sh->pq[r] = r < n ? q0 + sh->bq[r] : -1; sh->pB[r] = Br; sh->pS[r] = Sr; }
                     }
                     if (coop.helpers) {                     // fold the helpers' partial minima (lanes 0..helpers-1), own shard in lane 31
                         if (lane == 0) {
@@ -705,6 +687,7 @@ stream_replay_kernel(const int* __restrict__ list_idx, const int* __restrict__ l
     int* s_ld = s_mem + 32 * K;                     // [32][K]
     unsigned* s_taken = (unsigned*)(s_mem + 64 * K);   // [(capacity + 31) / 32]
     __shared__ ReplayShared sh;
+    __shared__ __align__(16) uint32_t s_qc[(MASKED ? 2 : 1) * 32 * WORDS];
     const int img = blockIdx.x + img_lo, tid = threadIdx.x;
     const bool has_prev = img >= n_cams;
     const int nq = has_prev ? min(counts[img], capacity) : 0;
@@ -716,7 +699,48 @@ stream_replay_kernel(const int* __restrict__ list_idx, const int* __restrict__ l
     const int nm = replay_core<WORDS, MASKED, kReplayThreads, kRescanBatch>(list_idx + q_row0 * K, list_dist + q_row0 * K, K, nq, nullptr, desc + q_row0 * WORDS,
                                                               MASKED ? dmask + q_row0 * WORDS : nullptr, desc + d_row0 * WORDS,
                                                               MASKED ? dmask + d_row0 * WORDS : nullptr, nd, th_low, nnratio,
-                                                              matches12 + q_row0, s_li, s_ld, s_taken, &sh);
+                                                              matches12 + q_row0, s_li, s_ld, s_taken, &sh, s_qc);
+    if (tid == 0) { nmatches[img] = nm; redo[img] = 0; }
+}
+
+// The same walk with the previous image's descriptors (and masks) RESIDENT IN SHARED MEMORY: a rescan then costs ~1.5 us instead
+// of ~6 us (its 8 x 64 bytes per thread come from shared memory instead of L2), at the price of one CTA per SM (capacity x 2 x dim
+// bytes, 129 KB for 2016 slots of mdBRIEF-256).  Used when the launch holds no more images than the device has SMs -- a chunk of the
+// host-facing stream pipeline, whose last acceptance launch is the un-overlapped tail of the call; a full 384-image step keeps the
+// kernel above (2.6 CTAs per SM in flight hide each other's latency, and the extraction kernels of the next step share the SMs).
+template <int WORDS, bool MASKED>
+__global__ void __launch_bounds__(kReplayThreads, 1)
+stream_replay_smem_kernel(const int* __restrict__ list_idx, const int* __restrict__ list_dist, const int* __restrict__ counts,
+                          const uint32_t* __restrict__ desc, const uint32_t* __restrict__ dmask,
+                          const int n_cams, const int capacity, const int K, const int img_lo, const int th_low, const double nnratio,
+                          int* __restrict__ matches12, int* __restrict__ nmatches, int* __restrict__ redo) {
+    extern __shared__ __align__(16) int s_mem[];
+    uint32_t* s_db = (uint32_t*)s_mem;                                     // [capacity][WORDS]
+    uint32_t* s_dbm = s_db + (MASKED ? (size_t)capacity * WORDS : 0);      // [capacity][WORDS]
+    int* s_li = (int*)(s_dbm + (size_t)capacity * WORDS);                  // [32][K]
+    int* s_ld = s_li + 32 * K;                                             // [32][K]
+    unsigned* s_taken = (unsigned*)(s_ld + 32 * K);                        // [(capacity + 31) / 32]
+    __shared__ ReplayShared sh;
+    __shared__ __align__(16) uint32_t s_qc[(MASKED ? 2 : 1) * 32 * WORDS];
+    const int img = blockIdx.x + img_lo, tid = threadIdx.x;
+    const bool has_prev = img >= n_cams;
+    const int nq = has_prev ? min(counts[img], capacity) : 0;
+    const int nd = has_prev ? min(counts[img - n_cams], capacity) : 0;
+    const size_t q_row0 = (size_t)img * capacity, d_row0 = has_prev ? (size_t)(img - n_cams) * capacity : 0;
+    for (int i = tid; i < (capacity + 31) / 32; i += kReplayThreads) s_taken[i] = 0u;
+    for (int i = tid; i < capacity; i += kReplayThreads) matches12[q_row0 + i] = -1;
+    if (nq > 0) {
+        const uint4* src = (const uint4*)(desc + d_row0 * WORDS);
+        for (int i = tid; i < nd * WORDS / 4; i += kReplayThreads) ((uint4*)s_db)[i] = src[i];
+        if (MASKED) {
+            const uint4* msrc = (const uint4*)(dmask + d_row0 * WORDS);
+            for (int i = tid; i < nd * WORDS / 4; i += kReplayThreads) ((uint4*)s_dbm)[i] = msrc[i];
+        }
+    }
+    __syncthreads();
+    const int nm = replay_core<WORDS, MASKED, kReplayThreads, kRescanBatch>(list_idx + q_row0 * K, list_dist + q_row0 * K, K, nq, nullptr, desc + q_row0 * WORDS,
+                                                              MASKED ? dmask + q_row0 * WORDS : nullptr, s_db, MASKED ? s_dbm : nullptr, nd, th_low,
+                                                              nnratio, matches12 + q_row0, s_li, s_ld, s_taken, &sh, s_qc);
     if (tid == 0) { nmatches[img] = nm; redo[img] = 0; }
 }
 
@@ -727,129 +751,32 @@ cudaError_t launch_stream_replay(const int* list_idx, const int* list_dist, cons
     if (capacity > 65535 || (dim != 16 && dim != 32 && dim != 64)) return cudaErrorInvalidValue;
     const size_t smem = (size_t)64 * K * 4 + (size_t)((capacity + 31) / 32) * 4;
     const bool masked = dmask != nullptr;
+    // one wave of images: the database of every image fits beside its walk (see stream_replay_smem_kernel)
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    const size_t smem_db = smem + (size_t)capacity * dim * (masked ? 2 : 1) + 16;
+    if (n_images <= sms && smem_db <= 200u * 1024u) {
+        const void* fn = nullptr;
+#define MCS_SRS(W, M) fn = (const void*)stream_replay_smem_kernel<W, M>
+        if (dim == 16) { if (masked) MCS_SRS(4, true); else MCS_SRS(4, false); }
+        else if (dim == 32) { if (masked) MCS_SRS(8, true); else MCS_SRS(8, false); }
+        else { if (masked) MCS_SRS(16, true); else MCS_SRS(16, false); }
+#undef MCS_SRS
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_db);     // per device, set every time
+        if (e != cudaSuccess) return e;
+        const uint32_t *d32 = (const uint32_t*)desc, *m32 = (const uint32_t*)dmask;
+        void* args[] = {(void*)&list_idx, (void*)&list_dist, (void*)&counts, (void*)&d32, (void*)&m32, (void*)&n_cams, (void*)&capacity, (void*)&K,
+                        (void*)&img_lo, (void*)&th_low, (void*)&nnratio, (void*)&matches12, (void*)&nmatches, (void*)&redo};
+        return cudaLaunchKernel(fn, dim3(n_images), dim3(kReplayThreads), args, smem_db, st);
+    }
 #define MCS_SR(W, M) stream_replay_kernel<W, M><<<n_images, kReplayThreads, smem, st>>>(list_idx, list_dist, counts, (const uint32_t*)desc, \
         (const uint32_t*)dmask, n_cams, capacity, K, img_lo, th_low, nnratio, matches12, nmatches, redo)
     if (dim == 16) { if (masked) MCS_SR(4, true); else MCS_SR(4, false); }
     else if (dim == 32) { if (masked) MCS_SR(8, true); else MCS_SR(8, false); }
     else { if (masked) MCS_SR(16, true); else MCS_SR(16, false); }
 #undef MCS_SR
-    return cudaGetLastError();
-}
-
-// Stream matcher, acceptance from candidate rows (hamming_stream_kernel<.., CAND = true>).  A row that did not overflow holds EVERY
-// database entry below the relevance bound, so the reference's sequential decision (ref src/cORBmatcher.cpp:899-961: best and
-// second best among the entries no earlier query has taken) is two warp minima over the row's still-unmatched keys -- lane k
-// owns candidate k, keys are (distance << 16 | slot), i.e. ordered like the reference's strict `<` scan.  No K-best list, no
-// bound reasoning, and no rescan unless a row overflowed (more than kCandCap entries below the bound: the rescan path of
-// replay_core, all threads of the CTA).  Warp 0 walks the queries; rows of 32 queries at a time are fetched into shared memory
-// with all loads in flight together.
-static_assert(kCandCap == 32 && kCandCap == kStreamCandCap, "one candidate per lane");
-template <int WORDS, bool MASKED>
-__global__ void __launch_bounds__(kReplayThreads)
-stream_accept_kernel(const unsigned* __restrict__ cand, const int* __restrict__ cand_cnt, const int* __restrict__ counts,
-                     const uint32_t* __restrict__ desc, const uint32_t* __restrict__ dmask,
-                     const int n_cams, const int capacity, const int img_lo, const int th_low, const double nnratio,
-                     int* __restrict__ matches12, int* __restrict__ nmatches, int* __restrict__ redo) {
-    extern __shared__ int s_mem[];
-    unsigned* s_cand = (unsigned*)s_mem;                       // [32][kCandCap]
-    int* s_cnt = s_mem + 32 * kCandCap;                        // [32]
-    unsigned* s_taken = (unsigned*)(s_cnt + 32);               // [(capacity + 31) / 32]
-    __shared__ ReplayShared sh;
-    constexpr unsigned kNone = 0xFFFFFFFFu;
-    const int img = blockIdx.x + img_lo, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool has_prev = img >= n_cams;
-    const int nq = has_prev ? min(counts[img], capacity) : 0;
-    const int nd = has_prev ? min(counts[img - n_cams], capacity) : 0;
-    const size_t q_row0 = (size_t)img * capacity, d_row0 = has_prev ? (size_t)(img - n_cams) * capacity : 0;
-    const uint32_t* qd = desc + q_row0 * WORDS;
-    const uint32_t* qmk = MASKED ? dmask + q_row0 * WORDS : nullptr;
-    const uint32_t* dd = desc + d_row0 * WORDS;
-    const uint32_t* dmk = MASKED ? dmask + d_row0 * WORDS : nullptr;
-    for (int i = tid; i < (capacity + 31) / 32; i += kReplayThreads) s_taken[i] = 0u;
-    for (int i = tid; i < capacity; i += kReplayThreads) matches12[q_row0 + i] = -1;
-    __syncthreads();
-    if (warp != 0) {                                           // rescan helpers: asleep unless a row overflowed
-        for (;;) {
-            named_bar<kReplayThreads>(1);
-            const int cmd = *(volatile int*)&sh.cmd;
-            if (cmd < 0) return;
-            unsigned k1[1], k2[1];
-            replay_scan<WORDS, MASKED, kReplayThreads, 1>(qd, qmk, sh.bq, 1, dd, dmk, 0, nd, s_taken, tid, k1, k2);
-            if (lane == 0) { sh.k1[warp][0] = k1[0]; sh.k2[warp][0] = k2[0]; }
-            named_bar<kReplayThreads>(2);
-        }
-    }
-    int nm = 0;
-    const unsigned* crow0 = cand + q_row0 * kCandCap;
-    for (int q0 = 0; q0 < nq; q0 += 32) {
-        const int nchunk = min(32, nq - q0);
-        const int c_me = lane < nchunk ? cand_cnt[q_row0 + q0 + lane] : 0;
-        s_cnt[lane] = c_me;
-#pragma unroll
-        for (int h = 0; h < 32; h += 16) {                     // 16 row loads in flight, then 16 stores
-            unsigned r[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int cj = __shfl_sync(0xffffffffu, c_me, h + j);
-                r[j] = lane < cj ? crow0[(size_t)(q0 + h + j) * kCandCap + lane] : kNone;      // cj > 32: the whole (overflowed) row
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) s_cand[(h + j) * kCandCap + lane] = r[j];
-        }
-        __syncwarp();
-        unsigned todo = __ballot_sync(0xffffffffu, c_me > 0);  // a query without a candidate below the bound cannot match
-        while (todo) {
-            const int t = __ffs(todo) - 1;
-            todo &= todo - 1u;
-            const unsigned key = s_cand[t * kCandCap + lane];
-            const unsigned id = key & 0xFFFFu;
-            const bool open = key != kNone && !(s_taken[id >> 5] >> (id & 31) & 1u);
-            unsigned B = __reduce_min_sync(0xffffffffu, open ? key : kNone);
-            unsigned S = __reduce_min_sync(0xffffffffu, (open && key != B) ? key : kNone);
-            int shift = 16;
-            if (s_cnt[t] > kCandCap) {
-                // overflowed row: exact rescan of the previous image for this query (two smallest keys among the unmatched entries)
-                if (lane == 0) { sh.cmd = 1; sh.bq[0] = q0 + t; }
-                named_bar<kReplayThreads>(1);
-                unsigned k1[1], k2[1];
-                replay_scan<WORDS, MASKED, kReplayThreads, 1>(qd, qmk, sh.bq, 1, dd, dmk, 0, nd, s_taken, tid, k1, k2);
-                if (lane == 0) { sh.k1[0][0] = k1[0]; sh.k2[0][0] = k2[0]; }
-                named_bar<kReplayThreads>(2);
-                const unsigned a1 = lane < kReplayThreads / 32 ? sh.k1[lane][0] : kNone;
-                const unsigned a2 = lane < kReplayThreads / 32 ? sh.k2[lane][0] : kNone;
-                B = __reduce_min_sync(0xffffffffu, a1);
-                S = __reduce_min_sync(0xffffffffu, a1 == B ? a2 : a1);
-                shift = kKeyShift;
-            }
-            const int best1 = B == kNone ? 0x7FFFFFFF : (int)(B >> shift), best2 = S == kNone ? 0x7FFFFFFF : (int)(S >> shift);
-            if (best1 < th_low && (double)best1 < nnratio * (double)best2) {
-                if (lane == 0) {
-                    const int bestIdx = (int)(B & ((1u << shift) - 1u));
-                    matches12[q_row0 + q0 + t] = bestIdx;
-                    s_taken[bestIdx >> 5] |= 1u << (bestIdx & 31);
-                }
-                ++nm;
-            }
-            __syncwarp();
-        }
-    }
-    if (lane == 0) { sh.cmd = -1; nmatches[img] = nm; redo[img] = 0; }
-    named_bar<kReplayThreads>(1);
-}
-
-cudaError_t launch_stream_accept(const unsigned* cand, const int* cand_cnt, const int* counts, const uint8_t* desc, const uint8_t* dmask,
-                                 int dim, int img_lo, int n_images, int n_cams, int capacity, int th_low, double nnratio,
-                                 int* matches12, int* nmatches, int* redo, cudaStream_t st) {
-    if (n_images < 1) return cudaSuccess;
-    if (capacity > 65535 || (dim != 16 && dim != 32 && dim != 64) || !cand || !cand_cnt) return cudaErrorInvalidValue;
-    const size_t smem = (size_t)(32 * kCandCap + 32) * 4 + (size_t)((capacity + 31) / 32) * 4;
-    const bool masked = dmask != nullptr;
-#define MCS_SA(W, M) stream_accept_kernel<W, M><<<n_images, kReplayThreads, smem, st>>>(cand, cand_cnt, counts, (const uint32_t*)desc, \
-        (const uint32_t*)dmask, n_cams, capacity, img_lo, th_low, nnratio, matches12, nmatches, redo)
-    if (dim == 16) { if (masked) MCS_SA(4, true); else MCS_SA(4, false); }
-    else if (dim == 32) { if (masked) MCS_SA(8, true); else MCS_SA(8, false); }
-    else { if (masked) MCS_SA(16, true); else MCS_SA(16, false); }
-#undef MCS_SA
     return cudaGetLastError();
 }
 
@@ -868,6 +795,7 @@ bruteforce_replay_kernel(const int* __restrict__ list_idx, const int* __restrict
     int* s_ld = s_mem + 32 * K;
     unsigned* s_taken = (unsigned*)(s_mem + 64 * K);   // leader: [(nd + 31) / 32]; helper: its shard only
     __shared__ ReplayShared sh;
+    __shared__ __align__(16) uint32_t s_qc[(MASKED ? 2 : 1) * 32 * WORDS];
     const int s = blockIdx.x / (helpers + 1), role = blockIdx.x - s * (helpers + 1), tid = threadIdx.x;   // role 0 = leader
     const int q0 = seg[s], nq = seg[s + 1] - q0;
     // shards: leader [0, cut), helper h (1-based role) [cut + (h-1) * per, ...): equal shares, the leader takes one too
@@ -891,7 +819,7 @@ bruteforce_replay_kernel(const int* __restrict__ list_idx, const int* __restrict
     const CoopLeader cl{helpers ? coop_seg + s : nullptr, helpers ? coop_log + q0 : nullptr, helpers, helpers ? hi : nd};
     const int nm = replay_core<WORDS, MASKED, kBfReplayThreads, 1>(list_idx + (size_t)q0 * K, list_dist + (size_t)q0 * K, K, nq, valid1 ? valid1 + q0 : nullptr,
                                                                 q + (size_t)q0 * WORDS, MASKED ? qm + (size_t)q0 * WORDS : nullptr, d, dm, nd, th_low,
-                                                                nnratio, matches12 + q0, s_li, s_ld, s_taken, &sh, cl);
+                                                                nnratio, matches12 + q0, s_li, s_ld, s_taken, &sh, s_qc, cl);
     if (tid == 0) nmatches[s] = nm;
 }
 

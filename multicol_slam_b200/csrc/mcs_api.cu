@@ -96,8 +96,7 @@ struct mcs_extractor {
     DevBuf<mcs_keypoint> kps;
     DevBuf<uint8_t> desc, dmask;
     int last_n_images = 0;
-    DevBuf<int> match_idx, match_dist, m12, nmat, redo, cand_cnt;
-    DevBuf<unsigned> cand;                   // candidate rows of the stream matcher's acceptance (kStreamCandCap keys per slot)
+    DevBuf<int> match_idx, match_dist, m12, nmat, redo;
     DevBuf<uint8_t> in_tight;
     cudaStream_t s_copy = nullptr, s_out = nullptr, s_match = nullptr;
     // distortion tables, rebuilt when the camera set changes
@@ -564,7 +563,7 @@ void mcs_extractor_destroy(mcs_extractor* ex) {
     if (ex->sf_exec) cudaGraphExecDestroy(ex->sf_exec);
     if (ex->pin_in) cudaFreeHost(ex->pin_in);
     if (ex->pin_out) cudaFreeHost(ex->pin_out);
-    ex->match_idx.release(); ex->match_dist.release(); ex->cand.release(); ex->cand_cnt.release(); ex->m12.release(); ex->nmat.release(); ex->redo.release(); ex->lut_coef.release(); ex->luts.release(); ex->tier.release(); ex->tile_flags.release();
+    ex->match_idx.release(); ex->match_dist.release(); ex->m12.release(); ex->nmat.release(); ex->redo.release(); ex->lut_coef.release(); ex->luts.release(); ex->tier.release(); ex->tile_flags.release();
     for (int i = 0; i < 4; ++i) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
     ex->in_tight.release();
     if (ex->s_copy) cudaStreamDestroy(ex->s_copy);
@@ -883,30 +882,15 @@ int mcs_match_stream_greedy_device(const uint8_t* desc_dev, const uint8_t* dmask
     if (n_frames < 1 || n_cams < 1 || capacity < 1 || capacity > 65535) return fail(MCS_ERR_INVALID, "bad sizes (capacity must be 1..65535)");
     if (dim != 16 && dim != 32 && dim != 64) return fail(MCS_ERR_INVALID, "dim must be 16, 32 or 64");
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t n = (size_t)n_frames * n_cams * capacity;
-    const unsigned bound = greedy_dist_bound(th_low, nnratio);
-    CK(keep_pool_memory());
-    if (stream_cand_applicable(bound, dim)) {
-        // candidate rows (every pair below the relevance bound) + acceptance from the rows: no K-best lists, no rescans unless a row overflows
-        unsigned* cand = nullptr; int *cnt = nullptr, *redo = nullptr;
-        CK(cudaMallocAsync((void**)&cand, n * kStreamCandCap * sizeof(unsigned), st));
-        CK(cudaMallocAsync((void**)&cnt, n * sizeof(int), st));
-        CK(cudaMallocAsync((void**)&redo, (size_t)n_frames * n_cams * sizeof(int), st));
-        cudaError_t e = launch_hamming_stream(desc_dev, dmask_dev, counts_dev, 0, n_frames * n_cams, n_cams, capacity, dim, 0, bound, nullptr, nullptr, st,
-                                              cand, cnt);
-        if (e == cudaSuccess)
-            e = launch_stream_accept(cand, cnt, counts_dev, desc_dev, dmask_dev, dim, 0, n_frames * n_cams, n_cams, capacity, th_low, nnratio,
-                                     matches12_dev, nmatches_dev, redo, st);
-        cudaFreeAsync(cand, st); cudaFreeAsync(cnt, st); cudaFreeAsync(redo, st);
-        CK(e);
-        return MCS_OK;
-    }
     constexpr int K = 4;      // measured on the Lafida stream: K = 8 saves 0.9 ms of rescans in the replay and costs 1.2 ms in the list kernel
+    const size_t n = (size_t)n_frames * n_cams * capacity;
     int *li = nullptr, *ld = nullptr, *redo = nullptr;
+    CK(keep_pool_memory());
     CK(cudaMallocAsync((void**)&li, n * K * sizeof(int), st));
     CK(cudaMallocAsync((void**)&ld, n * K * sizeof(int), st));
     CK(cudaMallocAsync((void**)&redo, (size_t)n_frames * n_cams * sizeof(int), st));
-    cudaError_t e = launch_hamming_stream(desc_dev, dmask_dev, counts_dev, 0, n_frames * n_cams, n_cams, capacity, dim, K, bound, li, ld, st);
+    cudaError_t e = launch_hamming_stream(desc_dev, dmask_dev, counts_dev, 0, n_frames * n_cams, n_cams, capacity, dim, K,
+                                          greedy_dist_bound(th_low, nnratio), li, ld, st);
     if (e == cudaSuccess)
         e = launch_stream_replay(li, ld, counts_dev, desc_dev, dmask_dev, dim, 0, n_frames * n_cams, n_cams, capacity, K, th_low, nnratio,
                                  matches12_dev, nmatches_dev, redo, st);
@@ -1002,9 +986,6 @@ static int extract_match_stream_impl(mcs_extractor* ex, int32_t n_frames, int32_
         if (!nmatches_out || !redo_out) return fail(MCS_ERR_INVALID, "the greedy acceptance needs all three outputs");
         CK(ex->m12.ensure((size_t)n_images * capacity)); CK(ex->nmat.ensure(n_images)); CK(ex->redo.ensure(n_images));
     }
-    const unsigned greedy_bound = replay ? greedy_dist_bound(th_low, nnratio) : 0xFFFFFFFFu;
-    const bool use_cand = replay && stream_cand_applicable(greedy_bound, ds);       // acceptance from candidate rows (match_kernels.cu)
-    if (use_cand) { CK(ex->cand.ensure((size_t)n_images * capacity * kStreamCandCap)); CK(ex->cand_cnt.ensure((size_t)n_images * capacity)); }
     struct Events {                       // destroyed on every path out of this function
         std::vector<cudaEvent_t> v;
         ~Events() { for (cudaEvent_t e : v) cudaEventDestroy(e); }
@@ -1062,12 +1043,9 @@ static int extract_match_stream_impl(mcs_extractor* ex, int32_t n_frames, int32_
         // it reads descriptors of this chunk and of the last frame of the previous one, both final at ev_feat[c]
         CK(cudaStreamWaitEvent(ex->s_match, ev_feat[c], 0));
         // with the greedy acceptance on the device the lists only need the entries that can influence it (kernels.h: greedy_dist_bound)
-        CK(launch_hamming_stream(desc_d, dmask_for_match, counts_d, img_lo, nimg, n_cams, capacity, ds, K, greedy_bound, ex->match_idx.p,
-                                 ex->match_dist.p, ex->s_match, use_cand ? ex->cand.p : nullptr, use_cand ? ex->cand_cnt.p : nullptr));
-        if (use_cand)   // greedy acceptance of SearchByBoW(KF1, KF2) from the candidate rows of this chunk, still on the device
-            CK(launch_stream_accept(ex->cand.p, ex->cand_cnt.p, counts_d, desc_d, dmask_for_match, ds, img_lo, nimg, n_cams, capacity, th_low, nnratio,
-                                    ex->m12.p, ex->nmat.p, ex->redo.p, ex->s_match));
-        else if (replay)     // ... or over the K-best lists (wide relevance bound)
+        CK(launch_hamming_stream(desc_d, dmask_for_match, counts_d, img_lo, nimg, n_cams, capacity, ds, K,
+                                 replay ? greedy_dist_bound(th_low, nnratio) : 0xFFFFFFFFu, ex->match_idx.p, ex->match_dist.p, ex->s_match));
+        if (replay)     // greedy acceptance of SearchByBoW(KF1, KF2) over the lists of this chunk, still on the device
             CK(launch_stream_replay(ex->match_idx.p, ex->match_dist.p, counts_d, desc_d, dmask_for_match, ds, img_lo, nimg, n_cams, capacity, K,
                                     th_low, nnratio, ex->m12.p, ex->nmat.p, ex->redo.p, ex->s_match));
         mark(ex->s_match);

@@ -603,12 +603,14 @@ def test_bruteforce_large_database_cooperative_rescans(api, oa):
         sl = slice(seg[s], seg[s + 1])
         on, om = oa.match_bruteforce(q[sl], db, 40, 1.01, qm[sl], dbm, None, valid2)
         assert on == nms[s] and np.array_equal(m12[sl], om)
-        assert on > 0.8 * (seg[s + 1] - seg[s])@pytest.mark.gpu
+        assert on > 0.8 * (seg[s + 1] - seg[s])
+
+
 @pytest.mark.parametrize("masked", [True, False])
-def test_stream_greedy_candidate_rows_overflow(api, oa, masked):
-    """mcs_match_stream_greedy_device decides from candidate rows (every database entry below the relevance bound, 32 slots per query).
-    Clustered descriptors -- dozens of near-duplicates per query -- overflow the rows, which must fall back to the exact in-kernel
-    rescan: same matches as the reference's sequential SearchByBoW(KF1, KF2) (oracle) and as the K-best-list path."""
+def test_stream_greedy_clustered_descriptors(api, oa, masked):
+    """mcs_match_stream_greedy_device on clustered descriptors -- dozens of near-duplicates per query, i.e. K-best lists that are
+    exhausted by earlier queries and force the exact in-kernel rescan all the time: same matches as the reference's sequential
+    SearchByBoW(KF1, KF2) (oracle), and as the separate lists + replay calls with a different list length."""
     import torch
     rng = np.random.default_rng(5)
     F, nc, cap, ds = 3, 2, 700, 32
@@ -619,7 +621,7 @@ def test_stream_greedy_candidate_rows_overflow(api, oa, masked):
     centres = rng.integers(0, 256, (12, ds), dtype=np.uint8)
     for b in range(B):
         n = counts[b]
-        # 8 big clusters (60+ members each: rows overflow), 4 small ones (<= 20 members: rows complete), the rest unrelated
+        # 8 big clusters (60+ members each), 4 small ones (<= 20 members), the rest unrelated
         which = rng.choice(13, n, p=[0.09] * 8 + [0.025] * 4 + [0.18])
         base = np.where((which < 12)[:, None], centres[np.minimum(which, 11)], rng.integers(0, 256, (n, ds), dtype=np.uint8))
         flips = np.zeros((n, ds * 8), np.uint8)
@@ -642,6 +644,3 @@ def test_stream_greedy_candidate_rows_overflow(api, oa, masked):
                                          dmask[img - nc, d] if masked else None)
             assert on == nm[img] and np.array_equal(om, m12[img, :counts[img]]), (th, nn, img)
         assert nm.sum() > 30
-
-
-
