@@ -98,6 +98,13 @@ constexpr int kLutDeg = 9;                        // degree of the per-centre po
 #define MCS_K3_MINB 5                // resident CTAs per SM the register budget is cut for: 5 -> 96 registers, no local-memory reload left in
                                      // the hot loops (4.91 ms per 384 images); 6 -> 80 registers, 1 + 3 reloads per iteration (5.07 ms)
 #endif
+#ifndef MCS_K3_U1
+#define MCS_K3_U1 4                  // unroll of tier-1 pass 1 (m-form), points per iteration   (A/B builds)
+#endif
+#ifndef MCS_K3_U2
+#define MCS_K3_U2 2                  // unroll of tier-1 pass 2, point PAIRS per iteration        (A/B builds)
+#endif
+constexpr int kT1Unroll1 = MCS_K3_U1, kT1Unroll2 = MCS_K3_U2;
 constexpr int kT1Coef = 6;                        // tier 1: q(s') of degree 5, R(i + s) - R(i) = s' q(s'), s' = s / kT1Scale
 constexpr float kT1Scale = 32.f;
 constexpr double kT1MinRadius = 40.0;             // tier 1 needs r >= r_k - 21.3 well away from the pole of g at r = 0
@@ -640,7 +647,7 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
                 const float q[kT1MCoef] = {tA.x, tA.y, tA.z, tA.w, tB.x, tB.y, tB.z, tB.w};
                 const float K0f = tC.x, gkf = tC.y, s0f = tC.z, rk2f = tC.w, rkf = tD.x, auk = tD.y, avk = tD.z;
                 if (mform) {
-#pragma unroll 4
+#pragma unroll kT1Unroll1
                     for (int j = 0; j < PPL; ++j) {
                         const float2 pp = s_patf[j * 32 + lane];
                         const float n = fmaf(pp.x, nx, fmaf(pp.y, ny, fmaf(pp.x, pp.x, pp.y * pp.y)));   // m - m_k
@@ -704,7 +711,7 @@ describe_kernel(const PyramidGeom* __restrict__ geom, const DescribeArgs args, c
 #endif
                 constexpr float kMagicF = 12582912.f;                          // 1.5 * 2^23: t + magic rounds t to the nearest even integer
                 unsigned bits = 0;                                             // descriptor byte(s) of this lane: points 0..15 | 16..31 << 8
-#pragma unroll 2
+#pragma unroll kT1Unroll2
                 for (int j = 0; j < PPL; j += 2) {
                     int smp[2];
 #pragma unroll

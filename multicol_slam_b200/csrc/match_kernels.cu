@@ -708,8 +708,11 @@ stream_replay_kernel(const int* __restrict__ list_idx, const int* __restrict__ l
 // bytes, 129 KB for 2016 slots of mdBRIEF-256).  Used when the launch holds no more images than the device has SMs -- a chunk of the
 // host-facing stream pipeline, whose last acceptance launch is the un-overlapped tail of the call; a full 384-image step keeps the
 // kernel above (2.6 CTAs per SM in flight hide each other's latency, and the extraction kernels of the next step share the SMs).
+// (1024 threads: alone on its SM, the CTA needs its own warps to hide the latency of the scan's dependent chains -- with 256 threads,
+// two warps per scheduler, a launch of 36 images took as long as one of 384)
+constexpr int kSmemReplayThreads = 1024;
 template <int WORDS, bool MASKED>
-__global__ void __launch_bounds__(kReplayThreads, 1)
+__global__ void __launch_bounds__(kSmemReplayThreads, 1)
 stream_replay_smem_kernel(const int* __restrict__ list_idx, const int* __restrict__ list_dist, const int* __restrict__ counts,
                           const uint32_t* __restrict__ desc, const uint32_t* __restrict__ dmask,
                           const int n_cams, const int capacity, const int K, const int img_lo, const int th_low, const double nnratio,
@@ -727,18 +730,18 @@ stream_replay_smem_kernel(const int* __restrict__ list_idx, const int* __restric
     const int nq = has_prev ? min(counts[img], capacity) : 0;
     const int nd = has_prev ? min(counts[img - n_cams], capacity) : 0;
     const size_t q_row0 = (size_t)img * capacity, d_row0 = has_prev ? (size_t)(img - n_cams) * capacity : 0;
-    for (int i = tid; i < (capacity + 31) / 32; i += kReplayThreads) s_taken[i] = 0u;
-    for (int i = tid; i < capacity; i += kReplayThreads) matches12[q_row0 + i] = -1;
+    for (int i = tid; i < (capacity + 31) / 32; i += kSmemReplayThreads) s_taken[i] = 0u;
+    for (int i = tid; i < capacity; i += kSmemReplayThreads) matches12[q_row0 + i] = -1;
     if (nq > 0) {
         const uint4* src = (const uint4*)(desc + d_row0 * WORDS);
-        for (int i = tid; i < nd * WORDS / 4; i += kReplayThreads) ((uint4*)s_db)[i] = src[i];
+        for (int i = tid; i < nd * WORDS / 4; i += kSmemReplayThreads) ((uint4*)s_db)[i] = src[i];
         if (MASKED) {
             const uint4* msrc = (const uint4*)(dmask + d_row0 * WORDS);
-            for (int i = tid; i < nd * WORDS / 4; i += kReplayThreads) ((uint4*)s_dbm)[i] = msrc[i];
+            for (int i = tid; i < nd * WORDS / 4; i += kSmemReplayThreads) ((uint4*)s_dbm)[i] = msrc[i];
         }
     }
     __syncthreads();
-    const int nm = replay_core<WORDS, MASKED, kReplayThreads, kRescanBatch>(list_idx + q_row0 * K, list_dist + q_row0 * K, K, nq, nullptr, desc + q_row0 * WORDS,
+    const int nm = replay_core<WORDS, MASKED, kSmemReplayThreads, kRescanBatch>(list_idx + q_row0 * K, list_dist + q_row0 * K, K, nq, nullptr, desc + q_row0 * WORDS,
                                                               MASKED ? dmask + q_row0 * WORDS : nullptr, s_db, MASKED ? s_dbm : nullptr, nd, th_low,
                                                               nnratio, matches12 + q_row0, s_li, s_ld, s_taken, &sh, s_qc);
     if (tid == 0) { nmatches[img] = nm; redo[img] = 0; }
@@ -769,7 +772,7 @@ cudaError_t launch_stream_replay(const int* list_idx, const int* list_dist, cons
         const uint32_t *d32 = (const uint32_t*)desc, *m32 = (const uint32_t*)dmask;
         void* args[] = {(void*)&list_idx, (void*)&list_dist, (void*)&counts, (void*)&d32, (void*)&m32, (void*)&n_cams, (void*)&capacity, (void*)&K,
                         (void*)&img_lo, (void*)&th_low, (void*)&nnratio, (void*)&matches12, (void*)&nmatches, (void*)&redo};
-        return cudaLaunchKernel(fn, dim3(n_images), dim3(kReplayThreads), args, smem_db, st);
+        return cudaLaunchKernel(fn, dim3(n_images), dim3(kSmemReplayThreads), args, smem_db, st);
     }
 #define MCS_SR(W, M) stream_replay_kernel<W, M><<<n_images, kReplayThreads, smem, st>>>(list_idx, list_dist, counts, (const uint32_t*)desc, \
         (const uint32_t*)dmask, n_cams, capacity, K, img_lo, th_low, nnratio, matches12, nmatches, redo)
