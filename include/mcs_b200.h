@@ -213,6 +213,17 @@ int  mcs_extractor_get_timings(mcs_extractor* ex, float* ms3);
  * [0] tier 1, [1] tier 1 after the FP64 repair of its near-tie points, [2] tier 2, [3] tier 3. */
 int  mcs_extractor_tier_stats(mcs_extractor* ex, int32_t enable, int64_t* counts4);
 
+/* The per-camera table behind tiers 1 and 2 of the descriptor kernel, as the host builds it (no GPU needed): one row of
+ * *row_doubles doubles per integer radius i of the undistorted plane, R(r) = rho(atan(-z / r)) the radial distortion function of
+ * cam (ref src/cam_model_omni.cpp:49-67):
+ *   [0..1]  tau offset / scale and [2..11] the degree-9 polynomial of R on [i - 22.5, i + 22.5]            (tier 2; NaN = disabled)
+ *   [12] R(i), [13] q0, [14..16] q1..q5 as floats: R(i + s) - R(i) = s' q(s'), s' = s / 32, [17] 1.0 = usable (tier 1, s-form)
+ *   [18] G(c_i), [19..22] a0..a7 as floats: G(c_i + hw_i t) - G(c_i) = t P(t), G(m) = R(sqrt m) / sqrt m, c_i = i^2 + 22.5^2,
+ *           hw_i = 45 i, [23] 1.0 = usable                                                                  (tier 1, m-form)
+ * rows_out (may be NULL to query the sizes) receives min(*n_rows, max_rows) rows.  Exists so that the tables can be checked
+ * against the camera model independently of the kernel (tests/test_distort_table_cpu.py). */
+int  mcs_cam_distort_table(const mcs_ocam* cam, double* rows_out, int32_t max_rows, int32_t* n_rows, int32_t* row_doubles);
+
 /* mcs_extract_batch / mcs_extract with at most 16 images (the per-frame call of cMultiFrame's constructor, ref
  * src/cMultiFrame.cpp:128-139) stage through pinned buffers owned by the extractor, and once a call repeats the previous one's
  * geometry, camera table, camera models and masks the whole copy-in / K1..K3 / copy-out sequence is ONE cudaGraphLaunch.

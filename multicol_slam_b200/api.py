@@ -71,6 +71,16 @@ def mirror_mask(cam):
     return out
 
 
+def distort_table(cam):
+    """mcs_cam_distort_table: the per-radius table of the descriptor kernel's tiers 1 and 2 for one camera -> float64 [n, row]"""
+    oc = as_ocam(cam)
+    n, row = C.c_int32(0), C.c_int32(0)
+    _check(lib().mcs_cam_distort_table(C.byref(oc), None, 0, C.byref(n), C.byref(row)))
+    out = np.zeros((n.value, row.value), np.float64)
+    _check(lib().mcs_cam_distort_table(C.byref(oc), _p(out), n.value, C.byref(n), C.byref(row)))
+    return out
+
+
 def world_to_img(cam, x, y, z):
     oc = as_ocam(cam)
     u, v = C.c_double(), C.c_double()

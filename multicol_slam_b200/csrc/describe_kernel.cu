@@ -7,9 +7,10 @@
 //   output assembly     ref :1327-1335  (pt *= scale for levels > 0)
 //
 // Layout of the work: lane b of the warp owns descriptor byte b, i.e. the 16 pattern points 16b..16b+15 (8 test
-// pairs).  For the distorted variants the lane keeps the 16 projected points of one pattern in registers, the
-// warp reduces their sum (the reference subtracts the mean of all 512 projected points, :262-281), then every
-// lane rounds and samples its own points: no shuffles, no second projection pass.
+// pairs).  For the distorted variants the lane parks the 16 projected points of one pattern in its own shared-memory
+// slots, the warp reduces their sum (the reference subtracts the mean of all 512 projected points, :262-281), then every
+// lane rounds and samples its own points: no shuffles, no second projection pass.  Warp-uniform state that is only needed
+// again in the rare paths or at the end lives in a per-warp context in shared memory (WarpCtx), not in registers.
 //
 // Fisheye projection cost.  cCamModelGeneral_::WorldToImg evaluates, per pattern point, sqrt + 3 divisions +
 // atan + a 12-term Horner in double (~250 FP64 instructions; 1536 points per mdBRIEF keypoint).  Because the
@@ -982,7 +983,7 @@ cudaError_t launch_describe(const PyramidGeom& G, const PyramidGeom* G_dev, int 
                             cudaStream_t st) {
     const long long warps = (long long)n_images * G.sel_total;
     const int blocks = (int)std::max<long long>(1, (warps + kDescWarps - 1) / kDescWarps);
-    // 128 registers (4 CTAs of 4 warps per SM): measured faster than 96 / 80 registers with more warps (spills), see DESIGN.md
+    // 96 registers, 5 CTAs of 4 warps per SM (MCS_K3_MINB): the budget at which no local-memory reload is left in the hot loops, see DESIGN.md
     const size_t park16 = (size_t)kDescWarps * 16 * 32 * sizeof(float2), park32 = 2 * park16;
     if (G.desc_size > 32) {        // static 23 KB + 32 KB parked coordinates: above the 48 KB default
         cudaError_t e = cudaFuncSetAttribute(describe_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)park32);

@@ -708,9 +708,9 @@ stream_replay_kernel(const int* __restrict__ list_idx, const int* __restrict__ l
 // bytes, 129 KB for 2016 slots of mdBRIEF-256).  Used when the launch holds no more images than the device has SMs -- a chunk of the
 // host-facing stream pipeline, whose last acceptance launch is the un-overlapped tail of the call; a full 384-image step keeps the
 // kernel above (2.6 CTAs per SM in flight hide each other's latency, and the extraction kernels of the next step share the SMs).
-// (1024 threads: alone on its SM, the CTA needs its own warps to hide the latency of the scan's dependent chains -- with 256 threads,
-// two warps per scheduler, a launch of 36 images took as long as one of 384)
-constexpr int kSmemReplayThreads = 1024;
+// (256 threads as in the kernel above; 1024 -- more warps of its own for the CTA that is alone on its SM -- measured no better:
+// e2e 44.7 against 46.0 Mfeatures/s)
+constexpr int kSmemReplayThreads = kReplayThreads;
 template <int WORDS, bool MASKED>
 __global__ void __launch_bounds__(kSmemReplayThreads, 1)
 stream_replay_smem_kernel(const int* __restrict__ list_idx, const int* __restrict__ list_dist, const int* __restrict__ counts,

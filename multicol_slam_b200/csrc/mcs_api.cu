@@ -238,6 +238,9 @@ int build_geometry(mcs_extractor* ex, int W, int H, int in_stride) {
     G.tiles_total = 0;
     for (int l = 0; l < L; ++l) { G.lv[l].tile_off = G.tiles_total; G.tiles_total += G.lv[l].tiles_x * G.lv[l].tiles_y; }
     ex->tile_flags_valid = false;
+    // kernels of an earlier *_device call on a caller-supplied stream may still read the tables about to be rewritten (a change of the
+    // image size is rare: drain the device)
+    CK(cudaDeviceSynchronize());
     CK(ex->lut_blob.ensure(blob.size() * sizeof(int16_t)));
     CK(cudaMemcpyAsync(ex->lut_blob.p, blob.data(), blob.size() * sizeof(int16_t), cudaMemcpyHostToDevice, ex->stream));
     const int16_t* base = (const int16_t*)ex->lut_blob.p;
@@ -847,6 +850,18 @@ int mcs_extractor_tier_stats(mcs_extractor* ex, int32_t enable, int64_t* counts4
         CK(cudaMemset(ex->tier.p, 0, 4 * sizeof(unsigned long long)));
     }
     ex->tier_on = enable != 0;
+    return MCS_OK;
+}
+
+int mcs_cam_distort_table(const mcs_ocam* cam, double* rows_out, int32_t max_rows, int32_t* n_rows, int32_t* row_doubles) {
+    if (!cam || !n_rows || !row_doubles) return fail(MCS_ERR_INVALID, "null argument");
+    if (rows_out && max_rows < 0) return fail(MCS_ERR_INVALID, "negative max_rows");
+    std::vector<double> coef;
+    int n = 0;
+    build_distort_lut(*cam, coef, n);
+    *n_rows = n;
+    *row_doubles = n > 0 ? (int32_t)(coef.size() / (size_t)n) : 0;
+    if (rows_out && n > 0) std::memcpy(rows_out, coef.data(), sizeof(double) * (size_t)std::min(n, (int)max_rows) * (size_t)*row_doubles);
     return MCS_OK;
 }
 
