@@ -135,7 +135,8 @@ int  mcs_extract_batch(mcs_extractor* ex, int32_t n_images,
 /* Same, all image/output buffers resident in device memory; asynchronous on `stream`
  * (a cudaStream_t passed as void*; NULL = the extractor's own stream, then the call
  * synchronises before returning).  masks/cams/cam_of_image stay host pointers (tiny, cached
- * on the device by the extractor). */
+ * on the device by the extractor).  With a caller stream the capacity checks of the call (raw corner list, octree node table,
+ * keypoint slots: MCS_ERR_CAPACITY) cannot be reported by the call itself: mcs_extractor_check_status does that afterwards. */
 int  mcs_extract_batch_device(mcs_extractor* ex, int32_t n_images,
                               const uint8_t* images_dev, int32_t width, int32_t height, int32_t stride,
                               const uint8_t* masks, const mcs_ocam* cams, int32_t n_cams,
@@ -212,6 +213,11 @@ int  mcs_extractor_get_timings(mcs_extractor* ex, float* ms3);
  * (one atomic per pattern: not for timed runs); counts4 (may be NULL) receives the patterns decided since then by
  * [0] tier 1, [1] tier 1 after the FP64 repair of its near-tie points, [2] tier 2, [3] tier 3. */
 int  mcs_extractor_tier_stats(mcs_extractor* ex, int32_t enable, int64_t* counts4);
+
+/* Overflow report of the LAST asynchronous extract call (mcs_extract_batch_device / ..._packed_device on a caller stream):
+ * synchronises `stream` (the stream that call ran on; NULL = the extractor's own) and returns MCS_ERR_CAPACITY if a raw corner
+ * list, the octree node table or the keypoint slots were too small for some image (results are truncated then), MCS_OK otherwise. */
+int  mcs_extractor_check_status(mcs_extractor* ex, void* stream);
 
 /* The per-camera table behind tiers 1 and 2 of the descriptor kernel, as the host builds it (no GPU needed): one row of
  * *row_doubles doubles per integer radius i of the undistorted plane, R(r) = rho(atan(-z / r)) the radial distortion function of

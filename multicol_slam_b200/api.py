@@ -258,6 +258,11 @@ class mdBRIEFextractorOct:
         _check(lib().mcs_extractor_tier_stats(self._h, int(enable), _p(out)))
         return out
 
+    def check_status(self, stream=None):
+        """mcs_extractor_check_status: overflow report of the last asynchronous extract call (raises MCS_ERR_CAPACITY); synchronises the stream"""
+        st = C.c_void_p(stream.cuda_stream) if stream is not None else None
+        _check(lib().mcs_extractor_check_status(self._h, st))
+
     def graph_replays(self):
         """calls served by replaying the cached CUDA graph of the per-frame sequence (mcs_extractor_graph_replays)"""
         n = C.c_int64(0)

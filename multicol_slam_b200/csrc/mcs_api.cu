@@ -853,6 +853,13 @@ int mcs_extractor_tier_stats(mcs_extractor* ex, int32_t enable, int64_t* counts4
     return MCS_OK;
 }
 
+int mcs_extractor_check_status(mcs_extractor* ex, void* stream) {
+    if (!ex) return fail(MCS_ERR_INVALID, "null extractor");
+    if (!ex->status.p) return MCS_OK;                       // nothing has run yet
+    CK(cudaSetDevice(ex->device));
+    return check_status(ex, stream ? (cudaStream_t)stream : ex->stream);
+}
+
 int mcs_cam_distort_table(const mcs_ocam* cam, double* rows_out, int32_t max_rows, int32_t* n_rows, int32_t* row_doubles) {
     if (!cam || !n_rows || !row_doubles) return fail(MCS_ERR_INVALID, "null argument");
     if (rows_out && max_rows < 0) return fail(MCS_ERR_INVALID, "negative max_rows");

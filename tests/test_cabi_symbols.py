@@ -56,6 +56,7 @@ def test_argument_validation(api):
     lib = api.lib()
     h = C.c_void_p()
     assert lib.mcs_extractor_create(None, C.byref(h)) == api.MCS_ERR_INVALID
+    assert lib.mcs_extractor_check_status(None, None) == api.MCS_ERR_INVALID
     p = make_params(use_agast=True)
     assert lib.mcs_extractor_create(C.byref(p), C.byref(h)) == api.MCS_ERR_UNSUPPORTED
     p = make_params(desc_size=24)

@@ -503,6 +503,7 @@ def test_packed_extraction_replay_and_device_bruteforce(api, oa, cams):
             b = api.match_stream_greedy_device(out["desc"], out["dmask"], out["counts"], Fn, nc, th, nn, stream=st)
             other.append((a, b))
     torch.cuda.synchronize(dev)
+    ex.check_status(st)                                   # asynchronous calls report overflows here: none in this configuration
     assert torch.equal(m12, m12b) and torch.equal(nm, nmb)
     assert torch.equal(m12, m12c) and torch.equal(nm, nmc)
     assert torch.equal(m12, m12d) and torch.equal(nm, nmd)
